@@ -1,0 +1,14 @@
+"""B200-native MPPI optimisation loop behind the plugin surface of nav2_sortham_controller.
+
+Only what the hot path needs lives here: ``csrc/`` (hand-written sm_100a CUDA kernels and the C ABI
+declared in ``include/mppi_b200.h``), ``host/`` (C++ mirror of the reference's Optimizer / critic
+interface over that ABI) and a thin ctypes binding (``_abi``, ``api``) used by tests and ``bench.py``.
+"""
+from . import _abi as abi  # noqa: F401
+from .api import (Cycle, Engine, MppiError, Result, circle_footprint, load_product, make_config,  # noqa: F401
+                  make_critic, make_robot)
+
+
+def MppiOptimizer(**cfg_kw):
+    """Engine bound to the CUDA library (raises MppiError if libmppi_b200.so is not built)."""
+    return Engine(load_product(), **cfg_kw)
