@@ -1,0 +1,1052 @@
+// mppi_api.cu -- the C ABI of include/mppi_b200.h over the sm_100a kernels of mppi_kernels.cuh.
+//
+// Host responsibilities (all O(N) or O(critics) scalar work per cycle, never O(B)):
+//   * keep the Optimizer state the reference keeps between cycles (control sequence, constraints, noise)
+//   * evaluate the per-cycle scalar gates of the critics exactly as the reference does on the host
+//     (withinPositionGoalTolerance, posePointAngle, findCircumscribedCost, ...), pack them with the path
+//     into one pinned record, and ship record + costmap with two async copies
+//   * launch K2 -> [exchange 1] -> K3 -> [exchange 2 -> K4], read back the 3T+2 floats of the result
+// There is no CPU implementation of the hot path in this file: without a CUDA device every call fails.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "mppi_kernels.cuh"
+
+using namespace mppi;
+
+namespace
+{
+
+struct NcclApi
+{
+  void * lib{nullptr};
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *){nullptr};
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int){nullptr};
+  ncclResult_t (*CommDestroy)(ncclComm_t){nullptr};
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t){nullptr};
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t){nullptr};
+  const char * (*GetErrorString)(ncclResult_t){nullptr};
+  bool load(std::string & err)
+  {
+    if (lib) {return true;}
+    // by soname: if torch (or anything else) already mapped an NCCL in this process, that copy is reused
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) {err = std::string("dlopen libnccl.so.2: ") + dlerror(); return false;}
+    GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+    CommInitRank = reinterpret_cast<decltype(CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+    CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+    AllReduce = reinterpret_cast<decltype(AllReduce)>(dlsym(lib, "ncclAllReduce"));
+    AllGather = reinterpret_cast<decltype(AllGather)>(dlsym(lib, "ncclAllGather"));
+    GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !AllGather) {
+      err = "libnccl.so.2 lacks a required symbol";
+      return false;
+    }
+    return true;
+  }
+};
+NcclApi g_nccl;
+
+struct Constraints {float vx_max, vx_min, vy, wz;};
+
+}  // namespace
+
+struct mppi_handle
+{
+  mppi_config cfg;
+  Constraints base, cur;
+  std::vector<mppi_critic_desc> critics;
+  mppi_robot_desc robot;
+  int B{0}, T{0};
+  int device{0};
+  cudaStream_t stream{nullptr};
+  cudaEvent_t ev0{nullptr}, ev1{nullptr};
+  // device
+  float * d_noise[3]{nullptr, nullptr, nullptr};
+  uint8_t * d_costmap{nullptr};
+  size_t costmap_capacity{0};
+  char * d_params{nullptr};
+  float * d_cs{nullptr};
+  float * d_crit_rows{nullptr};
+  float * d_samples[3]{nullptr, nullptr, nullptr};
+  float * d_end_xy{nullptr};
+  float * d_spill[3]{nullptr, nullptr, nullptr};
+  int * d_cells{nullptr};
+  float * d_costs{nullptr};
+  float * d_partials{nullptr};
+  float * d_rank_partial{nullptr};
+  float * d_gathered{nullptr};
+  float * d_out{nullptr};
+  DevState * d_st{nullptr};
+  float * d_inj[6]{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // score / integrate scratch, lazy
+  float * d_tmp{nullptr};                                                   // [B][T] transposition scratch, lazy
+  // pinned host
+  char * h_params{nullptr};
+  uint8_t * h_costmap{nullptr};
+  size_t h_costmap_capacity{0};
+  float * h_out{nullptr};
+  // state
+  size_t params_bytes{0};
+  uint64_t noise_stream{0};
+  uint32_t want_mask{0};
+  bool cycle_uploaded{false};
+  bool spilled_traj{false}, spilled_cells{false}, have_rows{false};
+  DevParams last;   // host copy of the last uploaded record
+  int segments_override{0};
+  int upd_blocks{0};
+  // sharding
+  ncclComm_t comm{nullptr};
+  int rank{0}, nranks{1};
+  std::string err;
+};
+
+namespace
+{
+
+constexpr size_t kParamsCapacity = sizeof(DevParams) + MPPI_MAX_PATH_POINTS * (4 * sizeof(float) + 1) + 64;
+
+#define CUDA_TRY(h, expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                               \
+      return MPPI_E_CUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+#define NCCL_TRY(h, expr)                                                                          \
+  do {                                                                                             \
+    ncclResult_t r_ = (expr);                                                                      \
+    if (r_ != ncclSuccess) {                                                                       \
+      (h)->err = std::string(#expr) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error"); \
+      return MPPI_E_NCCL;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+mppi_status fail(mppi_handle * h, mppi_status s, const std::string & msg)
+{
+  if (h) {h->err = msg;}
+  return s;
+}
+
+bool holonomic(const mppi_handle * h) {return h->cfg.motion_model == MPPI_MODEL_OMNI;}
+
+// ---- host-side scalar helpers, restating the reference's host code --------------------------------
+// utils::withinPositionGoalTolerance(float, ...) utils.hpp:233-249
+bool within_tolerance(float pose_tolerance, double rx, double ry, double gx, double gy)
+{
+  const double dist_sq = std::pow(gx - rx, 2) + std::pow(gy - ry, 2);
+  const float pose_tolerance_sq = pose_tolerance * pose_tolerance;
+  return dist_sq < pose_tolerance_sq;
+}
+// utils::withinPositionGoalTolerance(GoalChecker*, ...) utils.hpp:201-224
+bool within_checker_tolerance(double tol, double rx, double ry, double gx, double gy)
+{
+  if (tol >= 0.0) {
+    const double dx = rx - gx, dy = ry - gy;
+    if (dx * dx + dy * dy < tol * tol) {return true;}
+  }
+  return false;
+}
+double normalize_angle(double angle)
+{
+  const double result = std::fmod(angle + M_PI, 2.0 * M_PI);
+  if (result <= 0.0) {return result + M_PI;}
+  return result - M_PI;
+}
+// utils::posePointAngle utils.hpp:417-434
+float pose_point_angle(double pose_xd, double pose_yd, double pose_yawd, double point_x, double point_y, bool forward_preference)
+{
+  const float pose_x = pose_xd, pose_y = pose_yd, pose_yaw = pose_yawd;
+  const float yaw = atan2f(point_y - pose_y, point_x - pose_x);
+  if (!forward_preference) {
+    return std::min(
+      fabs(normalize_angle(static_cast<double>(pose_yaw) - yaw)),
+      fabs(normalize_angle(normalize_angle(pose_yaw + M_PI) - yaw)));
+  }
+  return fabs(normalize_angle(static_cast<double>(pose_yaw) - yaw));
+}
+// InflationLayer::computeCost + {Obstacles,Cost}Critic::findCircumscribedCost
+float circumscribed_cost(const mppi_robot_desc & robot, double resolution)
+{
+  double result = -1.0;
+  if (robot.inflation_layer_found) {
+    const double distance = robot.circumscribed_radius / resolution;
+    unsigned char cost = 0;
+    if (distance == 0) {
+      cost = LETHAL_OBSTACLE;
+    } else if (distance * resolution <= robot.inscribed_radius) {
+      cost = INSCRIBED_INFLATED_OBSTACLE;
+    } else {
+      const double factor = std::exp(-1.0 * robot.inflation_cost_scaling_factor * (distance * resolution - robot.inscribed_radius));
+      cost = static_cast<unsigned char>((INSCRIBED_INFLATED_OBSTACLE - 1) * factor);
+    }
+    result = cost;
+  }
+  return static_cast<float>(result);
+}
+
+const mppi_critic_desc * find_kind(const mppi_handle * h, int kind, int * idx)
+{
+  for (size_t i = 0; i < h->critics.size(); ++i) {
+    if (h->critics[i].kind == kind) {*idx = static_cast<int>(i); return &h->critics[i];}
+  }
+  *idx = -1;
+  return nullptr;
+}
+
+void set_common(CriticCommon & c, const mppi_critic_desc * d, int idx, bool gate)
+{
+  c.idx = idx;
+  c.on = (d && d->enabled && gate) ? 1 : 0;
+  c.power = d ? d->cost_power : 1u;
+  c.weight = d ? d->cost_weight : 0.0f;
+}
+
+// Fill the per-cycle record.  `in` may be null for integrate-only calls (mode 1).
+mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, unsigned preset_furthest, bool critics_active)
+{
+  DevParams & p = *reinterpret_cast<DevParams *>(h->h_params);
+  std::memset(&p, 0, sizeof(p));
+  const mppi_config & cfg = h->cfg;
+  p.B = h->B; p.T = h->T;
+  p.holonomic = holonomic(h) ? 1 : 0;
+  p.model = cfg.motion_model;
+  p.mode = mode;
+  p.dt = cfg.model_dt;
+  p.min_turning_r = cfg.ackermann_min_turning_r;
+  p.temperature = cfg.temperature;
+  p.gamma_vx = cfg.gamma / powf(cfg.vx_std, 2);
+  p.gamma_vy = cfg.gamma / powf(cfg.vy_std, 2);
+  p.gamma_wz = cfg.gamma / powf(cfg.wz_std, 2);
+  p.c_vx_max = h->cur.vx_max; p.c_vx_min = h->cur.vx_min; p.c_vy = h->cur.vy; p.c_wz = h->cur.wz;
+  p.preset_furthest = preset_furthest;
+  p.track_unknown = h->robot.track_unknown;
+  p.want_cells = (h->want_mask & MPPI_WANT_CELLS) ? 1 : 0;
+  p.fp_n = h->robot.footprint_size;
+  for (int i = 0; i < p.fp_n; ++i) {p.fp_x[i] = h->robot.footprint_x[i]; p.fp_y[i] = h->robot.footprint_y[i];}
+
+  const double rx = in->pose_x, ry = in->pose_y, gx = in->goal_x, gy = in->goal_y;
+  p.pose_x = rx; p.pose_y = ry;
+  p.yaw0 = static_cast<float>(in->pose_yaw);                  // const float initial_yaw = tf2::getYaw(...)
+  mppi_det_sincosf(p.yaw0, &p.sin0, &p.cos0);
+  p.speed_vx = static_cast<float>(in->speed_vx); p.speed_vy = static_cast<float>(in->speed_vy);
+  p.speed_wz = static_cast<float>(in->speed_wz);
+  p.goal_x = gx; p.goal_y = gy;
+  const int N = in->path_size;
+  if (N < 1 || N > MPPI_MAX_PATH_POINTS) {return fail(h, MPPI_E_CONFIG, "path_size must be in [1, MPPI_MAX_PATH_POINTS]");}
+  if (!in->path_x || !in->path_y || !in->path_yaw) {return fail(h, MPPI_E_CONFIG, "null path arrays");}
+  p.N = N;
+  p.goal_yaw = in->path_yaw[N - 1];
+  p.size_x = in->costmap.size_x; p.size_y = in->costmap.size_y;
+  p.res = in->costmap.resolution; p.ox = in->costmap.origin_x; p.oy = in->costmap.origin_y;
+
+  // path arrays behind the struct: x, y, yaw, arc-length prefix D (path_align_critic.cpp:83-90), PathAngle gate bytes
+  float * tail = reinterpret_cast<float *>(h->h_params + sizeof(DevParams));
+  p.off_path_x = 0; p.off_path_y = N; p.off_path_yaw = 2 * N; p.off_path_D = 3 * N; p.off_gate = 4 * N;
+  std::memcpy(tail, in->path_x, sizeof(float) * N);
+  std::memcpy(tail + N, in->path_y, sizeof(float) * N);
+  std::memcpy(tail + 2 * N, in->path_yaw, sizeof(float) * N);
+  float * D = tail + 3 * N;
+  D[0] = 0.0f;
+  for (int i = 1; i < N; ++i) {
+    const float dx = in->path_x[i] - in->path_x[i - 1];
+    const float dy = in->path_y[i] - in->path_y[i - 1];
+    const float curr_dist = sqrtf(dx * dx + dy * dy);
+    D[i] = D[i - 1] + curr_dist;
+  }
+  uint8_t * gate = reinterpret_cast<uint8_t *>(tail + 4 * N);
+  std::memset(gate, 0, N);
+  h->params_bytes = sizeof(DevParams) + sizeof(float) * 4 * N + ((N + 15) / 16) * 16;
+
+  p.n_critics = critics_active ? static_cast<int>(h->critics.size()) : 0;
+  for (int i = 0; i < kMaxCritics; ++i) {p.kind_of[i] = i < p.n_critics ? h->critics[i].kind : -1;}
+  for (CriticCommon * c : {&p.constraint, &p.cost, &p.goal, &p.goal_angle, &p.obst, &p.align, &p.legacy, &p.angle, &p.follow,
+      &p.forward, &p.twirl, &p.deadband})
+  {
+    c->idx = -1; c->on = 0; c->power = 1; c->weight = 0.0f;
+  }
+  bool any_gate_open = false;
+  if (critics_active) {
+    int idx;
+    const mppi_critic_desc * d;
+    if ((d = find_kind(h, MPPI_CRITIC_CONSTRAINT, &idx))) {
+      set_common(p.constraint, d, idx, true);
+      // constraint_critic.cpp:31-38 : parent parameters at init, not the speed-limited constraints
+      const float vx_max = cfg.vx_max, vy_max = cfg.vy_max, vx_min = cfg.vx_min;
+      const float min_sgn = vx_min > 0.0 ? 1.0 : -1.0;
+      p.max_vel = sqrtf(vx_max * vx_max + vy_max * vy_max);
+      p.min_vel = min_sgn * sqrtf(vx_min * vx_min + vy_max * vy_max);
+    }
+    if ((d = find_kind(h, MPPI_CRITIC_COST, &idx))) {
+      set_common(p.cost, d, idx, true);
+      p.cost.weight = d->cost_weight / 254.0f;                 // cost_critic.cpp:34
+      p.cost_fp = d->consider_footprint; p.cost_critical = d->critical_cost; p.cost_collision = d->collision_cost;
+      p.cost_near_goal = within_tolerance(d->near_goal_distance, rx, ry, gx, gy) ? 1 : 0;
+      p.cost_possibly_inscribed = circumscribed_cost(h->robot, p.res);
+      if (d->enabled && d->consider_footprint && p.fp_n < 1) {return fail(h, MPPI_E_CONFIG, "CostCritic.consider_footprint needs mppi_set_robot");}
+    }
+    if ((d = find_kind(h, MPPI_CRITIC_GOAL, &idx))) {
+      set_common(p.goal, d, idx, within_tolerance(d->threshold_to_consider, rx, ry, gx, gy));
+    }
+    if ((d = find_kind(h, MPPI_CRITIC_GOAL_ANGLE, &idx))) {
+      set_common(p.goal_angle, d, idx, within_tolerance(d->threshold_to_consider, rx, ry, gx, gy));
+    }
+    if ((d = find_kind(h, MPPI_CRITIC_OBSTACLES, &idx))) {
+      set_common(p.obst, d, idx, true);
+      p.obst_fp = d->consider_footprint; p.obst_collision = d->collision_cost;
+      p.obst_critical_w = d->critical_weight; p.obst_repulsion_w = d->repulsion_weight;
+      p.obst_near_goal = within_tolerance(d->near_goal_distance, rx, ry, gx, gy) ? 1 : 0;
+      p.obst_possibly_inscribed = circumscribed_cost(h->robot, p.res);
+      if (d->enabled && d->consider_footprint && p.fp_n < 1) {return fail(h, MPPI_E_CONFIG, "ObstaclesCritic.consider_footprint needs mppi_set_robot");}
+      // obstacles_critic.cpp:78-80: scale / radius are read only when an inflation layer exists
+      const float scale = h->robot.inflation_layer_found ? d->cost_scaling_factor : 0.0f;
+      const float infl_r = h->robot.inflation_layer_found ? d->inflation_radius : 0.0f;
+      p.obst_repulsion_enabled = !(infl_r == 0.0f || scale == 0.0f);
+      if (p.obst_repulsion_enabled) {
+        // distanceToObstacle (obstacles_critic.cpp:99-112) tabulated per byte cost; same libm as the oracle
+        const float min_radius = h->robot.inscribed_radius;
+        for (int fp = 0; fp < 2; ++fp) {
+          for (int v = 1; v < 256; ++v) {
+            float dist_to_obj = (scale * min_radius - logf(static_cast<float>(v)) + logf(253.0f)) / scale;
+            if (!fp) {dist_to_obj -= min_radius;}
+            if (dist_to_obj < d->collision_margin_distance) {
+              p.obst_lut_crit[fp][v] = d->collision_margin_distance - dist_to_obj;
+              p.obst_lut_rep[fp][v] = 0.0f;
+            } else {
+              p.obst_lut_crit[fp][v] = 0.0f;
+              p.obst_lut_rep[fp][v] = infl_r - dist_to_obj;
+            }
+          }
+        }
+      }
+    }
+    if ((d = find_kind(h, MPPI_CRITIC_PREFER_FORWARD, &idx))) {
+      set_common(p.forward, d, idx, !within_tolerance(d->threshold_to_consider, rx, ry, gx, gy));
+    }
+    if ((d = find_kind(h, MPPI_CRITIC_TWIRLING, &idx))) {
+      set_common(p.twirl, d, idx, !within_checker_tolerance(in->goal_checker_xy_tolerance, rx, ry, gx, gy));
+    }
+    if ((d = find_kind(h, MPPI_CRITIC_VELOCITY_DEADBAND, &idx))) {
+      set_common(p.deadband, d, idx, true);
+      p.db_vx = d->deadband_velocities[0]; p.db_vy = d->deadband_velocities[1]; p.db_wz = d->deadband_velocities[2];
+    }
+    if ((d = find_kind(h, MPPI_CRITIC_PATH_FOLLOW, &idx))) {
+      set_common(p.follow, d, idx, N >= 2 && !within_tolerance(d->threshold_to_consider, rx, ry, gx, gy));
+      p.follow_offset = d->offset_from_furthest;
+    }
+    if ((d = find_kind(h, MPPI_CRITIC_PATH_ALIGN, &idx))) {
+      set_common(p.align, d, idx, !within_tolerance(d->threshold_to_consider, rx, ry, gx, gy));
+      p.align_offset = d->offset_from_furthest; p.align_step = d->trajectory_point_step;
+      p.align_use_yaw = d->use_path_orientations; p.align_max_ratio = d->max_path_occupancy_ratio;
+      if (d->enabled && d->trajectory_point_step < 1) {return fail(h, MPPI_E_CONFIG, "PathAlignCritic.trajectory_point_step < 1");}
+    }
+    if ((d = find_kind(h, MPPI_CRITIC_PATH_ALIGN_LEGACY, &idx))) {
+      set_common(p.legacy, d, idx, !within_tolerance(d->threshold_to_consider, rx, ry, gx, gy));
+      p.legacy_offset = d->offset_from_furthest; p.legacy_step = d->trajectory_point_step;
+      p.legacy_use_yaw = d->use_path_orientations; p.legacy_max_ratio = d->max_path_occupancy_ratio;
+      if (d->enabled && d->trajectory_point_step < 1) {return fail(h, MPPI_E_CONFIG, "PathAlignLegacyCritic.trajectory_point_step < 1");}
+    }
+    if (p.align.on && p.legacy.on && p.align_step != p.legacy_step) {
+      return fail(h, MPPI_E_CONFIG, "PathAlignCritic and PathAlignLegacyCritic must share trajectory_point_step");
+    }
+    if (p.align.on || p.legacy.on) {
+      p.sample_step = p.align.on ? p.align_step : p.legacy_step;
+      p.n_samples = (p.T + p.sample_step - 1) / p.sample_step;
+      p.sample_yaw = (p.align.on && p.align_use_yaw) || (p.legacy.on && p.legacy_use_yaw);
+    }
+    if ((d = find_kind(h, MPPI_CRITIC_PATH_ANGLE, &idx))) {
+      set_common(p.angle, d, idx, !within_tolerance(d->threshold_to_consider, rx, ry, gx, gy));
+      p.angle_offset = d->offset_from_furthest;
+      // path_angle_critic.cpp:23-50
+      const float vx_min = cfg.vx_min;
+      bool reversing_allowed = true;
+      if (fabs(vx_min) < 1e-6) {reversing_allowed = false;} else if (vx_min < 0.0) {reversing_allowed = true;}
+      bool forward_preference = d->forward_preference != 0;
+      if (!reversing_allowed) {forward_preference = true;}
+      p.angle_reversing = reversing_allowed; p.angle_forward_pref = forward_preference;
+      if (p.angle.on) {
+        // path_angle_critic.cpp:79-83 for every index the furthest point could select
+        for (int j = 0; j < N; ++j) {
+          const float gxj = in->path_x[j], gyj = in->path_y[j];
+          const bool open = !(pose_point_angle(rx, ry, in->pose_yaw, gxj, gyj, forward_preference) < d->max_angle_to_furthest);
+          gate[j] = open ? 1 : 0;
+          any_gate_open = any_gate_open || open;
+        }
+      }
+    }
+  }
+  p.spill_traj = ((h->want_mask & MPPI_WANT_TRAJECTORIES) || any_gate_open || mode == 1) ? 1 : 0;
+  h->last = p;
+  return MPPI_OK;
+}
+
+int pick_segments(const mppi_handle * h)
+{
+  if (h->segments_override > 0) {return h->segments_override;}
+  const int tiles = (h->B + kTile - 1) / kTile;
+  int S = 8;
+  if (tiles > 148 * 4) {S = 4;}
+  while (S > 1 && S > h->T) {S >>= 1;}
+  return S;
+}
+
+DevBuffers make_bufs(mppi_handle * h, int mode)
+{
+  DevBuffers b;
+  if (mode == 0) {
+    b.in_a = h->d_noise[0]; b.in_b = h->d_noise[1]; b.in_c = h->d_noise[2];
+    b.in_x = b.in_y = b.in_yaw = nullptr;
+  } else {
+    b.in_a = h->d_inj[0]; b.in_b = h->d_inj[1]; b.in_c = h->d_inj[2];
+    b.in_x = h->d_inj[3]; b.in_y = h->d_inj[4]; b.in_yaw = h->d_inj[5];
+  }
+  b.cs = h->d_cs; b.crit_rows = h->d_crit_rows;
+  b.samples_x = h->d_samples[0]; b.samples_y = h->d_samples[1]; b.samples_yaw = h->d_samples[2];
+  b.end_xy = h->d_end_xy;
+  b.spill_x = h->d_spill[0]; b.spill_y = h->d_spill[1]; b.spill_yaw = h->d_spill[2];
+  b.spill_cells = h->d_cells;
+  b.costs = h->d_costs; b.partials = h->d_partials; b.rank_partial = h->d_rank_partial; b.out = h->d_out; b.st = h->d_st;
+  return b;
+}
+
+mppi_status upload_params(mppi_handle * h)
+{
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_params, h->h_params, h->params_bytes, cudaMemcpyHostToDevice, h->stream));
+  return MPPI_OK;
+}
+
+mppi_status upload_costmap(mppi_handle * h, const mppi_costmap & cm)
+{
+  const size_t bytes = static_cast<size_t>(cm.size_x) * cm.size_y;
+  if (bytes == 0 || !cm.cells) {return fail(h, MPPI_E_CONFIG, "empty costmap");}
+  if (!(cm.resolution > 0.0)) {return fail(h, MPPI_E_CONFIG, "costmap resolution must be > 0");}
+  if (bytes > h->costmap_capacity) {
+    // grow (outside the steady state: costmap size only changes on reconfiguration)
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->d_costmap) {cudaFree(h->d_costmap);}
+    if (h->h_costmap) {cudaFreeHost(h->h_costmap);}
+    h->d_costmap = nullptr; h->h_costmap = nullptr; h->costmap_capacity = 0;
+    CUDA_TRY(h, cudaMalloc(&h->d_costmap, bytes));
+    CUDA_TRY(h, cudaMallocHost(&h->h_costmap, bytes));
+    h->costmap_capacity = bytes;
+  }
+  // the caller's buffer is only valid during the call (it holds the costmap mutex): stage, then copy async
+  std::memcpy(h->h_costmap, cm.cells, bytes);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_costmap, h->h_costmap, bytes, cudaMemcpyHostToDevice, h->stream));
+  return MPPI_OK;
+}
+
+mppi_status launch_rollout(mppi_handle * h, int mode)
+{
+  const int S = pick_segments(h);
+  const size_t smem = rollout_smem_bytes(h->T, S);
+  if (smem > 227 * 1024) {return fail(h, MPPI_E_CONFIG, "time_steps too large for the shared-memory tile");}
+  const dim3 grid((h->B + kTile - 1) / kTile), block(kTile, S);
+  rollout_score_kernel<<<grid, block, smem, h->stream>>>(
+    reinterpret_cast<const DevParams *>(h->d_params), h->d_costmap, make_bufs(h, mode));
+  CUDA_TRY(h, cudaGetLastError());
+  return MPPI_OK;
+}
+
+mppi_status launch_update(mppi_handle * h, int mode, int iteration)
+{
+  const int N = h->last.N;
+  const size_t smem = sizeof(float) * (N + kUpdThreads + 32) + N + 16;
+  path_softmax_update_kernel<<<h->upd_blocks, kUpdThreads, smem, h->stream>>>(
+    reinterpret_cast<const DevParams *>(h->d_params), h->d_costmap, make_bufs(h, mode), h->nranks, iteration);
+  CUDA_TRY(h, cudaGetLastError());
+  return MPPI_OK;
+}
+
+// device part of optimize(): iteration_count x {K2, [exchange 1], K3, [exchange 2, K4]} + D2H of the result, no sync
+mppi_status enqueue_optimize(mppi_handle * h)
+{
+  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+  const int stride = 3 * h->T + 2;
+  for (int it = 0; it < h->cfg.iteration_count; ++it) {
+    mppi_status s = launch_rollout(h, 0);
+    if (s != MPPI_OK) {return s;}
+    if (h->nranks > 1) {
+      // exchange 1: furthest path point candidate + "some trajectory survived" flags, one MAX all-reduce
+      NCCL_TRY(h, g_nccl.AllReduce(h->d_st, h->d_st, 1 + kMaxCritics, ncclUint32, ncclMax, h->comm, h->stream));
+    }
+    s = launch_update(h, 0, it);
+    if (s != MPPI_OK) {return s;}
+    if (h->nranks > 1) {
+      // exchange 2: per-rank (min, sum, weighted control sums); merged redundantly on every rank
+      NCCL_TRY(h, g_nccl.AllGather(h->d_rank_partial, h->d_gathered, stride, ncclFloat32, h->comm, h->stream));
+      merge_partials_kernel<<<1, kUpdThreads, 0, h->stream>>>(
+        reinterpret_cast<const DevParams *>(h->d_params), h->d_gathered, h->nranks, stride, make_bufs(h, 0));
+      CUDA_TRY(h, cudaGetLastError());
+    }
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(float) * (3 * h->T + 2), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+  return MPPI_OK;
+}
+
+mppi_status finish_optimize(mppi_handle * h, mppi_cycle_out * out)
+{
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  const int T = h->T;
+  h->spilled_traj = h->last.spill_traj != 0;
+  h->spilled_cells = h->last.want_cells != 0;
+  h->have_rows = true;
+  if (out) {
+    if (out->control_vx) {std::memcpy(out->control_vx, h->h_out, sizeof(float) * T);}
+    if (out->control_vy) {std::memcpy(out->control_vy, h->h_out + T, sizeof(float) * T);}
+    if (out->control_wz) {std::memcpy(out->control_wz, h->h_out + 2 * T, sizeof(float) * T);}
+    int32_t ff;
+    uint32_t fu;
+    std::memcpy(&ff, h->h_out + 3 * T, 4);
+    std::memcpy(&fu, h->h_out + 3 * T + 1, 4);
+    out->fail_flag = ff;
+    out->furthest_reached_path_point = fu;
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    out->device_ms = ms;
+  }
+  return MPPI_OK;
+}
+
+mppi_status ensure_injection_buffers(mppi_handle * h)
+{
+  const size_t n = static_cast<size_t>(h->B) * h->T * sizeof(float);
+  for (int i = 0; i < 6; ++i) {
+    if (!h->d_inj[i]) {CUDA_TRY(h, cudaMalloc(&h->d_inj[i], n));}
+  }
+  return MPPI_OK;
+}
+mppi_status ensure_tmp(mppi_handle * h)
+{
+  if (!h->d_tmp) {CUDA_TRY(h, cudaMalloc(&h->d_tmp, static_cast<size_t>(h->B) * h->T * sizeof(float)));}
+  return MPPI_OK;
+}
+
+template<typename V>
+mppi_status fetch_time_major(mppi_handle * h, const V * d_src, V * host_dst)
+{
+  mppi_status s = ensure_tmp(h);
+  if (s != MPPI_OK) {return s;}
+  const dim3 grid((h->B + 31) / 32, (h->T + 31) / 32), block(32, 8);
+  transpose_tb_to_bt_kernel<V><<<grid, block, 0, h->stream>>>(d_src, reinterpret_cast<V *>(h->d_tmp), h->T, h->B);
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaMemcpyAsync(host_dst, h->d_tmp, static_cast<size_t>(h->B) * h->T * sizeof(V), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return MPPI_OK;
+}
+
+mppi_status do_reset(mppi_handle * h)
+{
+  const size_t T = h->T, B = h->B;
+  h->cur = h->base;
+  CUDA_TRY(h, cudaMemsetAsync(h->d_cs, 0, 3 * T * sizeof(float), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_costs, 0, B * sizeof(float), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_st, 0, sizeof(DevState), h->stream));
+  // NoiseGenerator::reset (noise_generator.cpp:76-95): redraw
+  const int threads = 256;
+  const long long total = static_cast<long long>(B) * ((T + 3) / 4);
+  const int blocks = static_cast<int>(std::min<long long>((total + threads - 1) / threads, 148LL * 16));
+  noise_philox_kernel<<<std::max(blocks, 1), threads, 0, h->stream>>>(
+    h->d_noise[0], h->d_noise[1], h->d_noise[2], h->B, h->T, h->cfg.vx_std, h->cfg.vy_std, h->cfg.wz_std,
+    holonomic(h) ? 1 : 0, h->cfg.seed, h->noise_stream, static_cast<uint64_t>(h->cfg.shard_offset));
+  CUDA_TRY(h, cudaGetLastError());
+  h->noise_stream++;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->cycle_uploaded = false;
+  return MPPI_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int32_t mppi_abi_version(void) {return MPPI_ABI_VERSION;}
+
+void mppi_config_default(mppi_config * c)
+{
+  std::memset(c, 0, sizeof(*c));
+  // Optimizer::getParams optimizer.cpp:69-84
+  c->batch_size = 1000; c->time_steps = 56; c->iteration_count = 1;
+  c->model_dt = 0.05f; c->temperature = 0.3f; c->gamma = 0.015f;
+  c->vx_max = 0.5; c->vx_min = -0.35; c->vy_max = 0.5; c->wz_max = 1.9;
+  c->vx_std = 0.2; c->vy_std = 0.2; c->wz_std = 0.4;
+  c->motion_model = MPPI_MODEL_DIFF_DRIVE;
+  c->ackermann_min_turning_r = 0.2;
+}
+
+void mppi_critic_default(int32_t kind, mppi_critic_desc * d)
+{
+  std::memset(d, 0, sizeof(*d));
+  d->kind = kind; d->enabled = 1; d->cost_power = 1;
+  d->trajectory_point_step = 4; d->max_path_occupancy_ratio = 0.07; d->use_path_orientations = 0;
+  d->max_angle_to_furthest = 1.2; d->forward_preference = 1; d->consider_footprint = 0;
+  d->near_goal_distance = 0.5; d->repulsion_weight = 1.5; d->critical_weight = 20.0;
+  d->collision_margin_distance = 0.10; d->cost_scaling_factor = 10.0; d->inflation_radius = 0.55;
+  d->critical_cost = 300.0;
+  switch (kind) {
+    case MPPI_CRITIC_CONSTRAINT: d->cost_weight = 4.0; break;                                      // constraint_critic.cpp:25-26
+    case MPPI_CRITIC_COST: d->cost_weight = 3.81; d->collision_cost = 1000000.0; break;             // cost_critic.cpp:24-34
+    case MPPI_CRITIC_GOAL: d->cost_weight = 5.0; d->threshold_to_consider = 1.4; break;             // goal_critic.cpp:27-29
+    case MPPI_CRITIC_GOAL_ANGLE: d->cost_weight = 3.0; d->threshold_to_consider = 0.5; break;       // goal_angle_critic.cpp:24-27
+    case MPPI_CRITIC_OBSTACLES: d->collision_cost = 10000.0; break;                                 // obstacles_critic.cpp:23-31
+    case MPPI_CRITIC_PATH_ALIGN:
+    case MPPI_CRITIC_PATH_ALIGN_LEGACY:                                                             // path_align_critic.cpp:29-38
+      d->cost_weight = 10.0; d->threshold_to_consider = 0.5; d->offset_from_furthest = 20; break;
+    case MPPI_CRITIC_PATH_ANGLE:                                                                    // path_angle_critic.cpp:35-46
+      d->cost_weight = 2.0; d->threshold_to_consider = 0.5; d->offset_from_furthest = 4; break;
+    case MPPI_CRITIC_PATH_FOLLOW:                                                                   // path_follow_critic.cpp:27-32
+      d->cost_weight = 5.0; d->threshold_to_consider = 1.4; d->offset_from_furthest = 6; break;
+    case MPPI_CRITIC_PREFER_FORWARD: d->cost_weight = 5.0; d->threshold_to_consider = 0.5; break;   // prefer_forward_critic.cpp:23-27
+    case MPPI_CRITIC_TWIRLING: d->cost_weight = 10.0; break;                                        // twirling_critic.cpp:24-25
+    case MPPI_CRITIC_VELOCITY_DEADBAND: d->cost_weight = 35.0; break;                               // velocity_deadband_critic.cpp:24-25
+    default: break;
+  }
+}
+
+const char * mppi_last_error(const mppi_handle * h) {return h ? h->err.c_str() : "null handle";}
+
+void mppi_destroy(mppi_handle * h)
+{
+  if (!h) {return;}
+  cudaSetDevice(h->device);
+  if (h->stream) {cudaStreamSynchronize(h->stream);}
+  if (h->comm && g_nccl.CommDestroy) {g_nccl.CommDestroy(h->comm);}
+  for (float * p : h->d_noise) {cudaFree(p);}
+  for (float * p : h->d_samples) {cudaFree(p);}
+  for (float * p : h->d_spill) {cudaFree(p);}
+  for (float * p : h->d_inj) {cudaFree(p);}
+  cudaFree(h->d_tmp); cudaFree(h->d_costmap); cudaFree(h->d_params); cudaFree(h->d_cs); cudaFree(h->d_crit_rows);
+  cudaFree(h->d_end_xy); cudaFree(h->d_cells); cudaFree(h->d_costs); cudaFree(h->d_partials); cudaFree(h->d_rank_partial);
+  cudaFree(h->d_gathered); cudaFree(h->d_out); cudaFree(h->d_st);
+  cudaFreeHost(h->h_params); cudaFreeHost(h->h_costmap); cudaFreeHost(h->h_out);
+  if (h->ev0) {cudaEventDestroy(h->ev0);}
+  if (h->ev1) {cudaEventDestroy(h->ev1);}
+  if (h->stream) {cudaStreamDestroy(h->stream);}
+  delete h;
+}
+
+mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
+{
+  if (!cfg || !out) {return MPPI_E_CONFIG;}
+  *out = nullptr;
+  mppi_handle * h = new mppi_handle();
+  h->cfg = *cfg;
+  *out = h;   // returned even on failure so that mppi_last_error() can be read; caller destroys it
+  auto bad = [&](const char * m) {h->err = m; return MPPI_E_CONFIG;};
+  if (cfg->batch_size < 1) {return bad("batch_size < 1");}
+  if (cfg->time_steps < 2 || cfg->time_steps > MPPI_MAX_TIME_STEPS) {return bad("time_steps must be in [2, MPPI_MAX_TIME_STEPS]");}
+  if (cfg->iteration_count < 1) {return bad("iteration_count < 1");}
+  if (cfg->motion_model < MPPI_MODEL_DIFF_DRIVE || cfg->motion_model > MPPI_MODEL_ACKERMANN) {
+    return bad("Model is not valid! Valid options are DiffDrive, Omni, or Ackermann");   // optimizer.cpp:421-424
+  }
+  if (!(cfg->temperature > 0.0f) || !(cfg->model_dt > 0.0f)) {return bad("temperature and model_dt must be > 0");}
+  if (!(cfg->vx_std > 0.0f) || !(cfg->vy_std > 0.0f) || !(cfg->wz_std > 0.0f)) {return bad("sampling std must be > 0");}
+  h->B = cfg->batch_size; h->T = cfg->time_steps; h->device = cfg->device;
+  h->base = {cfg->vx_max, cfg->vx_min, cfg->vy_max, cfg->wz_max};
+  h->cur = h->base;
+  std::memset(&h->robot, 0, sizeof(h->robot));
+  if (const char * e = std::getenv("MPPI_SEGMENTS")) {h->segments_override = std::atoi(e);}
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    h->err = "no CUDA device: this library has no CPU fallback";
+    return MPPI_E_CUDA;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, cudaFuncSetAttribute(rollout_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_TRY(h, cudaEventCreate(&h->ev0));
+  CUDA_TRY(h, cudaEventCreate(&h->ev1));
+  const size_t B = h->B, T = h->T, plane = B * T * sizeof(float);
+  for (int i = 0; i < 3; ++i) {
+    CUDA_TRY(h, cudaMalloc(&h->d_noise[i], plane));
+    CUDA_TRY(h, cudaMalloc(&h->d_samples[i], plane));
+    CUDA_TRY(h, cudaMalloc(&h->d_spill[i], plane));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_noise[i], 0, plane, h->stream));
+  }
+  CUDA_TRY(h, cudaMalloc(&h->d_cells, B * T * sizeof(int)));
+  CUDA_TRY(h, cudaMalloc(&h->d_params, kParamsCapacity));
+  CUDA_TRY(h, cudaMalloc(&h->d_cs, 3 * T * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->d_crit_rows, (kMaxCritics + kGammaRows) * B * sizeof(float)));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_crit_rows, 0, (kMaxCritics + kGammaRows) * B * sizeof(float), h->stream));
+  CUDA_TRY(h, cudaMalloc(&h->d_end_xy, 2 * B * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->d_costs, B * sizeof(float)));
+  h->upd_blocks = static_cast<int>((B + kUpdThreads - 1) / kUpdThreads);
+  const size_t stride = 3 * T + 2;
+  CUDA_TRY(h, cudaMalloc(&h->d_partials, h->upd_blocks * stride * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->d_rank_partial, stride * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->d_out, (stride + 2) * sizeof(float)));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_out, 0, (stride + 2) * sizeof(float), h->stream));
+  CUDA_TRY(h, cudaMalloc(&h->d_st, sizeof(DevState)));
+  CUDA_TRY(h, cudaMallocHost(&h->h_params, kParamsCapacity));
+  CUDA_TRY(h, cudaMallocHost(&h->h_out, (stride + 2) * sizeof(float)));
+  return do_reset(h);
+}
+
+mppi_status mppi_reset(mppi_handle * h)
+{
+  if (!h) {return MPPI_E_CONFIG;}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return do_reset(h);
+}
+
+mppi_status mppi_set_critics(mppi_handle * h, const mppi_critic_desc * critics, int32_t n)
+{
+  if (!h || n < 0 || (n > 0 && !critics)) {return MPPI_E_CONFIG;}
+  if (n > MPPI_MAX_CRITICS) {return fail(h, MPPI_E_CONFIG, "too many critics");}
+  bool seen[MPPI_CRITIC_KIND_COUNT] = {};
+  for (int i = 0; i < n; ++i) {
+    const int k = critics[i].kind;
+    if (k < 0 || k >= MPPI_CRITIC_KIND_COUNT) {return fail(h, MPPI_E_CONFIG, "unknown critic kind");}
+    if (seen[k]) {return fail(h, MPPI_E_CONFIG, "a critic kind may appear only once in the critics list");}
+    seen[k] = true;
+  }
+  h->critics.assign(critics, critics + n);
+  h->cycle_uploaded = false;
+  return MPPI_OK;
+}
+
+mppi_status mppi_set_robot(mppi_handle * h, const mppi_robot_desc * robot)
+{
+  if (!h || !robot) {return MPPI_E_CONFIG;}
+  if (robot->footprint_size < 0 || robot->footprint_size > MPPI_MAX_FOOTPRINT) {return fail(h, MPPI_E_CONFIG, "footprint_size out of range");}
+  h->robot = *robot;
+  h->cycle_uploaded = false;
+  return MPPI_OK;
+}
+
+mppi_status mppi_set_speed_limit(mppi_handle * h, double speed_limit, int32_t percentage)
+{
+  if (!h) {return MPPI_E_CONFIG;}
+  Constraints & s = h->cur;
+  const Constraints & b = h->base;
+  if (speed_limit == 0.0) {        // nav2_costmap_2d::NO_SPEED_LIMIT
+    s = b;
+  } else {
+    const double ratio = percentage ? speed_limit / 100.0 : speed_limit / b.vx_max;
+    s.vx_max = b.vx_max * ratio; s.vx_min = b.vx_min * ratio; s.vy = b.vy * ratio; s.wz = b.wz * ratio;
+  }
+  h->cycle_uploaded = false;
+  return MPPI_OK;
+}
+
+mppi_status mppi_get_constraints(const mppi_handle * h, float out4[4])
+{
+  if (!h || !out4) {return MPPI_E_CONFIG;}
+  out4[0] = h->cur.vx_max; out4[1] = h->cur.vx_min; out4[2] = h->cur.vy; out4[3] = h->cur.wz;
+  return MPPI_OK;
+}
+
+mppi_status mppi_set_noise(mppi_handle * h, const float * vx, const float * vy, const float * wz)
+{
+  if (!h || !vx || !wz) {return MPPI_E_CONFIG;}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t plane = static_cast<size_t>(h->B) * h->T * sizeof(float);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_noise[0], vx, plane, cudaMemcpyHostToDevice, h->stream));
+  if (vy) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_noise[1], vy, plane, cudaMemcpyHostToDevice, h->stream));
+  } else {
+    CUDA_TRY(h, cudaMemsetAsync(h->d_noise[1], 0, plane, h->stream));
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_noise[2], wz, plane, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return MPPI_OK;
+}
+
+mppi_status mppi_generate_noise(mppi_handle * h, uint64_t stream)
+{
+  if (!h) {return MPPI_E_CONFIG;}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const long long total = static_cast<long long>(h->B) * ((h->T + 3) / 4);
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 16));
+  noise_philox_kernel<<<std::max(blocks, 1), 256, 0, h->stream>>>(
+    h->d_noise[0], h->d_noise[1], h->d_noise[2], h->B, h->T, h->cfg.vx_std, h->cfg.vy_std, h->cfg.wz_std,
+    holonomic(h) ? 1 : 0, h->cfg.seed, stream, static_cast<uint64_t>(h->cfg.shard_offset));
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return MPPI_OK;
+}
+
+mppi_status mppi_get_noise(mppi_handle * h, float * vx, float * vy, float * wz)
+{
+  if (!h || !vx || !vy || !wz) {return MPPI_E_CONFIG;}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t plane = static_cast<size_t>(h->B) * h->T * sizeof(float);
+  CUDA_TRY(h, cudaMemcpyAsync(vx, h->d_noise[0], plane, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(vy, h->d_noise[1], plane, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(wz, h->d_noise[2], plane, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return MPPI_OK;
+}
+
+mppi_status mppi_set_control_sequence(mppi_handle * h, const float * vx, const float * vy, const float * wz)
+{
+  if (!h || !vx || !vy || !wz) {return MPPI_E_CONFIG;}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t n = h->T * sizeof(float);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_cs, vx, n, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_cs + h->T, vy, n, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_cs + 2 * h->T, wz, n, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return MPPI_OK;
+}
+
+mppi_status mppi_get_control_sequence(mppi_handle * h, float * vx, float * vy, float * wz)
+{
+  if (!h || !vx || !vy || !wz) {return MPPI_E_CONFIG;}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t n = h->T * sizeof(float);
+  CUDA_TRY(h, cudaMemcpyAsync(vx, h->d_cs, n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(vy, h->d_cs + h->T, n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(wz, h->d_cs + 2 * h->T, n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return MPPI_OK;
+}
+
+mppi_status mppi_shift_control_sequence(mppi_handle * h)
+{
+  if (!h) {return MPPI_E_CONFIG;}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  shift_control_sequence_kernel<<<1, 256, 0, h->stream>>>(h->d_cs, h->T, holonomic(h) ? 1 : 0);
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return MPPI_OK;
+}
+
+mppi_status mppi_set_outputs(mppi_handle * h, uint32_t want_mask)
+{
+  if (!h) {return MPPI_E_CONFIG;}
+  h->want_mask = want_mask;
+  h->cycle_uploaded = false;
+  return MPPI_OK;
+}
+
+mppi_status mppi_upload_cycle(mppi_handle * h, const mppi_cycle_in * in)
+{
+  if (!h || !in) {return MPPI_E_CONFIG;}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  mppi_status s = build_params(h, in, 0, kUnset, true);
+  if (s != MPPI_OK) {return s;}
+  if ((s = upload_params(h)) != MPPI_OK) {return s;}
+  if ((s = upload_costmap(h, in->costmap)) != MPPI_OK) {return s;}
+  h->cycle_uploaded = true;
+  return MPPI_OK;
+}
+
+mppi_status mppi_optimize_resident(mppi_handle * h, mppi_cycle_out * out)
+{
+  if (!h) {return MPPI_E_CONFIG;}
+  if (!h->cycle_uploaded) {return fail(h, MPPI_E_STATE, "mppi_optimize_resident before mppi_upload_cycle");}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  mppi_status s = enqueue_optimize(h);
+  if (s != MPPI_OK) {return s;}
+  return finish_optimize(h, out);
+}
+
+mppi_status mppi_optimize(mppi_handle * h, const mppi_cycle_in * in, mppi_cycle_out * out)
+{
+  mppi_status s = mppi_upload_cycle(h, in);
+  if (s != MPPI_OK) {return s;}
+  return mppi_optimize_resident(h, out);
+}
+
+mppi_status mppi_optimize_batch(mppi_handle ** hs, const mppi_cycle_in * ins, mppi_cycle_out * outs, int32_t n)
+{
+  if (!hs || !ins || n < 0) {return MPPI_E_CONFIG;}
+  mppi_status first = MPPI_OK;
+  std::vector<char> launched(n, 0);
+  for (int i = 0; i < n; ++i) {
+    mppi_status s = mppi_upload_cycle(hs[i], &ins[i]);
+    if (s == MPPI_OK) {s = enqueue_optimize(hs[i]);}
+    launched[i] = s == MPPI_OK;
+    if (s != MPPI_OK && first == MPPI_OK) {first = s;}
+  }
+  for (int i = 0; i < n; ++i) {
+    if (!launched[i]) {continue;}
+    cudaSetDevice(hs[i]->device);
+    const mppi_status s = finish_optimize(hs[i], outs ? &outs[i] : nullptr);
+    if (s != MPPI_OK && first == MPPI_OK) {first = s;}
+  }
+  return first;
+}
+
+mppi_status mppi_get_trajectories(mppi_handle * h, float * x, float * y, float * yaw)
+{
+  if (!h || !x || !y || !yaw) {return MPPI_E_CONFIG;}
+  if (!h->spilled_traj) {return fail(h, MPPI_E_STATE, "trajectories were not materialised: mppi_set_outputs(MPPI_WANT_TRAJECTORIES) before optimize");}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  mppi_status s;
+  if ((s = fetch_time_major<float>(h, h->d_spill[0], x)) != MPPI_OK) {return s;}
+  if ((s = fetch_time_major<float>(h, h->d_spill[1], y)) != MPPI_OK) {return s;}
+  return fetch_time_major<float>(h, h->d_spill[2], yaw);
+}
+
+mppi_status mppi_get_cells(mppi_handle * h, int32_t * cells)
+{
+  if (!h || !cells) {return MPPI_E_CONFIG;}
+  if (!h->spilled_cells) {return fail(h, MPPI_E_STATE, "cell indices were not materialised: mppi_set_outputs(MPPI_WANT_CELLS) before optimize");}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return fetch_time_major<int>(h, h->d_cells, cells);
+}
+
+mppi_status mppi_get_costs(mppi_handle * h, float * costs)
+{
+  if (!h || !costs) {return MPPI_E_CONFIG;}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, cudaMemcpyAsync(costs, h->d_costs, h->B * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return MPPI_OK;
+}
+
+mppi_status mppi_get_critic_costs(mppi_handle * h, int32_t index, float * costs)
+{
+  if (!h || !costs) {return MPPI_E_CONFIG;}
+  if (!h->have_rows) {return fail(h, MPPI_E_STATE, "no optimize has run yet");}
+  if (index < 0 || index >= static_cast<int>(h->critics.size())) {return fail(h, MPPI_E_CONFIG, "critic index out of range");}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, cudaMemcpyAsync(costs, h->d_crit_rows + static_cast<size_t>(index) * h->B, h->B * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return MPPI_OK;
+}
+
+mppi_status mppi_get_optimized_trajectory(mppi_handle * h, double pose_x, double pose_y, double pose_yaw, float * traj_t3)
+{
+  if (!h || !traj_t3) {return MPPI_E_CONFIG;}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  mppi_status s = ensure_tmp(h);
+  if (s != MPPI_OK) {return s;}
+  optimized_trajectory_kernel<<<1, 32, 0, h->stream>>>(h->d_cs, h->d_tmp, h->T, holonomic(h) ? 1 : 0, h->cfg.model_dt, pose_x, pose_y,
+    static_cast<float>(pose_yaw));
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaMemcpyAsync(traj_t3, h->d_tmp, 3 * h->T * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return MPPI_OK;
+}
+
+mppi_status mppi_integrate_state_velocities(
+  mppi_handle * h, double pose_x, double pose_y, double pose_yaw, const float * vx, const float * vy, const float * wz,
+  float * x, float * y, float * yaw)
+{
+  if (!h || !vx || !vy || !wz || !x || !y || !yaw) {return MPPI_E_CONFIG;}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  mppi_status s = ensure_injection_buffers(h);
+  if (s != MPPI_OK) {return s;}
+  const size_t plane = static_cast<size_t>(h->B) * h->T * sizeof(float);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_inj[0], vx, plane, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_inj[1], vy, plane, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_inj[2], wz, plane, cudaMemcpyHostToDevice, h->stream));
+  // a one-point dummy path and a 1x1 map: no critic runs in this mode
+  static const float zero = 0.0f;
+  static const uint8_t cell = 0;
+  mppi_cycle_in in;
+  std::memset(&in, 0, sizeof(in));
+  in.pose_x = pose_x; in.pose_y = pose_y; in.pose_yaw = pose_yaw;
+  in.goal_checker_xy_tolerance = -1.0;
+  in.path_size = 1; in.path_x = &zero; in.path_y = &zero; in.path_yaw = &zero;
+  in.costmap.cells = &cell; in.costmap.size_x = 1; in.costmap.size_y = 1; in.costmap.resolution = 1.0;
+  const uint32_t keep_mask = h->want_mask;
+  h->want_mask = 0;
+  s = build_params(h, &in, 1, kUnset, false);
+  h->want_mask = keep_mask;
+  if (s != MPPI_OK) {return s;}
+  if ((s = upload_params(h)) != MPPI_OK) {return s;}
+  if ((s = upload_costmap(h, in.costmap)) != MPPI_OK) {return s;}
+  h->cycle_uploaded = false;
+  if ((s = launch_rollout(h, 1)) != MPPI_OK) {return s;}
+  // K2 raised nothing persistent except the exchange-1 words; clear them for the next optimize
+  CUDA_TRY(h, cudaMemsetAsync(h->d_st, 0, sizeof(DevState), h->stream));
+  if ((s = fetch_time_major<float>(h, h->d_spill[0], x)) != MPPI_OK) {return s;}
+  if ((s = fetch_time_major<float>(h, h->d_spill[1], y)) != MPPI_OK) {return s;}
+  return fetch_time_major<float>(h, h->d_spill[2], yaw);
+}
+
+mppi_status mppi_score_trajectories(
+  mppi_handle * h, const mppi_cycle_in * in, const float * vx, const float * vy, const float * wz, const float * x,
+  const float * y, const float * yaw, float * costs_inout, uint32_t * furthest_inout, int32_t * fail_flag_out)
+{
+  if (!h || !in || !vx || !vy || !wz || !x || !y || !yaw || !costs_inout) {return MPPI_E_CONFIG;}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  mppi_status s = ensure_injection_buffers(h);
+  if (s != MPPI_OK) {return s;}
+  const size_t plane = static_cast<size_t>(h->B) * h->T * sizeof(float);
+  const float * src[6] = {vx, vy, wz, x, y, yaw};
+  for (int i = 0; i < 6; ++i) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_inj[i], src[i], plane, cudaMemcpyHostToDevice, h->stream));
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_costs, costs_inout, h->B * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  const unsigned preset = furthest_inout ? *furthest_inout : kUnset;
+  s = build_params(h, in, 2, preset, true);
+  if (s != MPPI_OK) {return s;}
+  if ((s = upload_params(h)) != MPPI_OK) {return s;}
+  if ((s = upload_costmap(h, in->costmap)) != MPPI_OK) {return s;}
+  h->cycle_uploaded = false;
+  if ((s = launch_rollout(h, 2)) != MPPI_OK) {return s;}
+  if ((s = launch_update(h, 2, 0)) != MPPI_OK) {return s;}
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(float) * (3 * h->T + 2), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(costs_inout, h->d_costs, h->B * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->spilled_traj = h->last.spill_traj != 0;
+  h->spilled_cells = h->last.want_cells != 0;
+  h->have_rows = true;
+  int32_t ff;
+  uint32_t fu;
+  std::memcpy(&ff, h->h_out + 3 * h->T, 4);
+  std::memcpy(&fu, h->h_out + 3 * h->T + 1, 4);
+  if (fail_flag_out) {*fail_flag_out = ff;}
+  if (furthest_inout) {*furthest_inout = fu;}
+  return MPPI_OK;
+}
+
+// ---- sharding ------------------------------------------------------------------------------------
+mppi_status mppi_comm_get_unique_id(uint8_t id_out[MPPI_NCCL_UNIQUE_ID_BYTES])
+{
+  std::string err;
+  if (!g_nccl.load(err)) {return MPPI_E_NCCL;}
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == MPPI_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) {return MPPI_E_NCCL;}
+  std::memcpy(id_out, &id, sizeof(id));
+  return MPPI_OK;
+}
+
+mppi_status mppi_comm_init(mppi_handle * h, const uint8_t id[MPPI_NCCL_UNIQUE_ID_BYTES], int32_t rank, int32_t nranks)
+{
+  if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) {return MPPI_E_CONFIG;}
+  if (!g_nccl.load(h->err)) {return MPPI_E_NCCL;}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  ncclUniqueId uid;
+  std::memcpy(&uid, id, sizeof(uid));
+  NCCL_TRY(h, g_nccl.CommInitRank(&h->comm, nranks, uid, rank));
+  h->rank = rank; h->nranks = nranks;
+  if (!h->d_gathered) {
+    CUDA_TRY(h, cudaMalloc(&h->d_gathered, static_cast<size_t>(nranks) * (3 * h->T + 2) * sizeof(float)));
+  }
+  return MPPI_OK;
+}
+
+mppi_status mppi_comm_destroy(mppi_handle * h)
+{
+  if (!h) {return MPPI_E_CONFIG;}
+  if (h->comm) {
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    g_nccl.CommDestroy(h->comm);
+    h->comm = nullptr;
+  }
+  h->rank = 0; h->nranks = 1;
+  return MPPI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,231 @@
+// mppi_device.cuh -- device-side data layout and helpers shared by the kernels.
+//
+// HBM layout (all owned by one mppi_handle, allocated once at create):
+//   noise_vx/vy/wz   float [B][T] row-major   the reference's layout (models/state.hpp), so that injected
+//                                              noise is a plain copy; read once per kernel, coalesced
+//   costmap          uint8 [size_y][size_x]    uploaded once per cycle with one async copy
+//   DevParams + path one packed record         uploaded once per cycle with one async copy
+//   crit_rows        float [R][B]              per-critic contribution rows + 3 gamma rows (plane-major =
+//                                              coalesced for lane == trajectory)
+//   samples / ends   float [K][B], [2][B]      every trajectory_point_step-th pose for PathAlign, end pose
+//   spill x/y/yaw    float [T][B] time-major   only when PathAngle may fire or trajectories are requested
+//   costs            float [B]                 persists across iteration_count iterations (quirk R20)
+//   partials         float [blocks][3T+2]      online-softmax partials merged by the last block
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mppi_b200.h"
+#include "../../include/mppi_det_math.h"
+
+namespace mppi
+{
+
+constexpr int kTile = 32;          // trajectories per tile == warp width (lane = trajectory)
+constexpr int kPad = 33;           // smem row pitch of the time-major tile [T][33]: conflict-free both ways
+constexpr int kMaxCritics = MPPI_MAX_CRITICS;
+constexpr int kGammaRows = 3;      // gamma-term rows stored after the critic rows
+constexpr unsigned kUnset = 0xFFFFFFFFu;
+
+constexpr unsigned char NO_INFORMATION = 255;
+constexpr unsigned char LETHAL_OBSTACLE = 254;
+constexpr unsigned char INSCRIBED_INFLATED_OBSTACLE = 253;
+
+struct CriticCommon
+{
+  int idx;            // position in the critics list, -1 when the kind is absent
+  int on;             // enabled && this cycle's host-side gate (withinPositionGoalTolerance & co) lets it run
+  unsigned power;
+  float weight;
+};
+
+// One record per cycle.  Scalars the host can decide (goal-distance gates, PathAngle gate per candidate
+// index, arc-length prefix of the path) are decided on the host with the same libm the oracle uses, so
+// every discrete decision taken on the device is a pure function of bit-exact inputs.
+struct DevParams
+{
+  int B, T, N, n_critics;
+  int holonomic, model;
+  int mode;                 // 0 rollout from noise, 1 injected state (integrate), 2 injected state + trajectories
+  float dt, min_turning_r;
+  float yaw0, cos0, sin0;
+  float speed_vx, speed_vy, speed_wz;
+  float goal_yaw;
+  float temperature;
+  float gamma_vx, gamma_vy, gamma_wz;        // gamma / std^2
+  float c_vx_max, c_vx_min, c_vy, c_wz;      // current (speed-limited) constraints
+  unsigned size_x, size_y;
+  int track_unknown;
+  unsigned preset_furthest;                  // score mode: caller-provided furthest point, kUnset otherwise
+  double pose_x, pose_y;
+  double goal_x, goal_y;
+  double res, ox, oy;
+  int kind_of[kMaxCritics];                  // list order -> kind
+  // per kind
+  CriticCommon constraint; float max_vel, min_vel;
+  CriticCommon cost; int cost_fp; float cost_critical, cost_collision; int cost_near_goal; float cost_possibly_inscribed;
+  CriticCommon goal;
+  CriticCommon goal_angle;
+  CriticCommon obst; int obst_fp; float obst_collision, obst_critical_w, obst_repulsion_w; int obst_near_goal;
+  float obst_possibly_inscribed; int obst_repulsion_enabled;
+  CriticCommon align; int align_offset, align_step, align_use_yaw; float align_max_ratio;
+  CriticCommon legacy; int legacy_offset, legacy_step, legacy_use_yaw; float legacy_max_ratio;
+  CriticCommon angle; int angle_offset; int angle_reversing, angle_forward_pref;
+  CriticCommon follow; int follow_offset;
+  CriticCommon forward;
+  CriticCommon twirl;
+  CriticCommon deadband; float db_vx, db_vy, db_wz;
+  // spills
+  int sample_step, n_samples, sample_yaw;    // PathAlign samples: p = 0, step, 2 step ... < T
+  int spill_traj;                            // write x,y,yaw time-major (PathAngle may fire / requested)
+  int want_cells;
+  int want_legacy_traj;                      // PathAlignLegacy needs all sampled poses too (uses samples)
+  // footprint
+  int fp_n;
+  double fp_x[MPPI_MAX_FOOTPRINT], fp_y[MPPI_MAX_FOOTPRINT];
+  // obstacle-critic look-up tables indexed by the byte cost: [0] point cost, [1] footprint cost
+  float obst_lut_crit[2][256];               // (d < margin) ? margin - d : 0
+  float obst_lut_rep[2][256];                // (d < margin) ? 0 : inflation_radius - d
+  // offsets (in floats) of the path arrays that follow this struct in the same buffer
+  int off_path_x, off_path_y, off_path_yaw, off_path_D, off_gate;
+};
+
+// Persistent per-optimize state shared between kernels (device memory, 1 record per handle).
+struct DevState
+{
+  unsigned furthest_candidate;          // max over trajectories of argmin over path (this iteration)  [exchange 1]
+  unsigned any_ok[kMaxCritics];         // obstacle-type critic q saw a non-colliding trajectory       [exchange 1]
+  unsigned furthest;                    // CriticData::furthest_reached_path_point
+  int furthest_set;
+  int fail_flag;
+  unsigned ticket;                      // last-block election of the update kernel
+  unsigned pad;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// nav2_costmap_2d::Costmap2D::worldToMap restated; all fp64, inputs are fp32 poses widened.
+// Returns the flat cell index my*size_x+mx or -1 (off-map).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int world_to_cell(
+  double wx, double wy, double ox, double oy, double res, unsigned size_x, unsigned size_y, unsigned & mx, unsigned & my)
+{
+  if (wx < ox || wy < oy) {return -1;}
+  const double qx = __ddiv_rn(wx - ox, res);
+  const double qy = __ddiv_rn(wy - oy, res);
+  if (!(qx < static_cast<double>(size_x)) || !(qy < static_cast<double>(size_y))) {return -1;}
+  mx = static_cast<unsigned>(qx);
+  my = static_cast<unsigned>(qy);
+  return static_cast<int>(my * size_x + mx);
+}
+
+// FootprintCollisionChecker::lineCost over nav2_util::LineIterator (integer Bresenham, both ends included)
+__device__ __forceinline__ int line_cost(const uint8_t * __restrict__ cm, unsigned size_x, int x0, int y0, int x1, int y1)
+{
+  int deltax = abs(x1 - x0), deltay = abs(y1 - y0);
+  int xinc1, xinc2, yinc1, yinc2;
+  if (x1 >= x0) {xinc1 = 1; xinc2 = 1;} else {xinc1 = -1; xinc2 = -1;}
+  if (y1 >= y0) {yinc1 = 1; yinc2 = 1;} else {yinc1 = -1; yinc2 = -1;}
+  int den, num, numadd, numpixels;
+  if (deltax >= deltay) {
+    xinc1 = 0; yinc2 = 0; den = deltax; num = deltax / 2; numadd = deltay; numpixels = deltax;
+  } else {
+    xinc2 = 0; yinc1 = 0; den = deltay; num = deltay / 2; numadd = deltax; numpixels = deltay;
+  }
+  int x = x0, y = y0;
+  int cost = 0;
+  for (int cur = 0; cur <= numpixels; ++cur) {
+    const int c = __ldg(cm + static_cast<unsigned>(y) * size_x + static_cast<unsigned>(x));
+    if (c == LETHAL_OBSTACLE) {return c;}
+    cost = max(cost, c);
+    num += numadd;
+    if (num >= den) {num -= den; x += xinc1; y += yinc1;}
+    x += xinc2; y += yinc2;
+  }
+  return cost;
+}
+
+// FootprintCollisionChecker::footprintCostAtPose + footprintCost
+__device__ __noinline__ int footprint_cost_at_pose(
+  const DevParams * __restrict__ p, const uint8_t * __restrict__ cm, float xf, float yf, float thf)
+{
+  const double x = xf, y = yf, th = thf;
+  double sin_th, cos_th;
+  sincos(th, &sin_th, &cos_th);
+  const int n = p->fp_n;
+  unsigned x0, y0, x1, y1;
+  {
+    const double fx = p->fp_x[0], fy = p->fp_y[0];
+    const double wx = x + (__dmul_rn(fx, cos_th) - __dmul_rn(fy, sin_th));
+    const double wy = y + (__dmul_rn(fx, sin_th) + __dmul_rn(fy, cos_th));
+    if (world_to_cell(wx, wy, p->ox, p->oy, p->res, p->size_x, p->size_y, x0, y0) < 0) {return LETHAL_OBSTACLE;}
+  }
+  const unsigned xstart = x0, ystart = y0;
+  x1 = x0; y1 = y0;
+  int footprint_cost = 0;
+  for (int i = 0; i + 1 < n; ++i) {
+    const double fx = p->fp_x[i + 1], fy = p->fp_y[i + 1];
+    const double wx = x + (__dmul_rn(fx, cos_th) - __dmul_rn(fy, sin_th));
+    const double wy = y + (__dmul_rn(fx, sin_th) + __dmul_rn(fy, cos_th));
+    if (world_to_cell(wx, wy, p->ox, p->oy, p->res, p->size_x, p->size_y, x1, y1) < 0) {return LETHAL_OBSTACLE;}
+    footprint_cost = max(line_cost(cm, p->size_x, x0, y0, x1, y1), footprint_cost);
+    x0 = x1; y0 = y1;
+    if (footprint_cost == LETHAL_OBSTACLE) {return footprint_cost;}
+  }
+  return max(line_cost(cm, p->size_x, xstart, ystart, x1, y1), footprint_cost);
+}
+
+// CostCritic::inCollision / ObstaclesCritic::inCollision on a byte cost
+__device__ __forceinline__ bool in_collision(int cost, bool consider_footprint, bool track_unknown)
+{
+  if (cost == LETHAL_OBSTACLE) {return true;}
+  if (cost == INSCRIBED_INFLATED_OBSTACLE) {return !consider_footprint;}
+  if (cost == NO_INFORMATION) {return !track_unknown;}
+  return false;
+}
+
+// utils::normalize_angles on one element: fmod(a + pi, 2 pi) in double, <= 0 -> + pi else - pi
+__device__ __forceinline__ double normalize_angle_d(double a)
+{
+  const double two_pi = 6.283185307179586476925286766559;
+  const double pi = 3.14159265358979323846;
+  double v = a + pi;
+  double theta;
+  if (v >= 0.0 && v < two_pi) {
+    theta = v;
+  } else if (v >= two_pi && v < 2.0 * two_pi) {
+    theta = v - two_pi;          // exact (Sterbenz), equals fmod
+  } else if (v < 0.0 && v > -two_pi) {
+    theta = v;                   // fmod keeps the sign of the dividend
+  } else {
+    theta = fmod(v, two_pi);
+  }
+  return theta <= 0.0 ? theta + pi : theta - pi;
+}
+
+// costs += pow(value, power) as the reference's xtensor expression evaluates it (pow and the sum in double)
+__device__ __forceinline__ float add_pow(float total, float value, unsigned power)
+{
+  if (power == 1u) {return __fadd_rn(total, value);}
+  return static_cast<float>(static_cast<double>(total) + pow(static_cast<double>(value), static_cast<double>(power)));
+}
+
+__device__ __forceinline__ float warp_min(float v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));}
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {v += __shfl_xor_sync(0xffffffffu, v, o);}
+  return v;
+}
+__device__ __forceinline__ unsigned warp_max_u(unsigned v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {v = max(v, __shfl_xor_sync(0xffffffffu, v, o));}
+  return v;
+}
+
+}  // namespace mppi

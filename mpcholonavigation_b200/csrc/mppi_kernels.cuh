@@ -1,0 +1,1009 @@
+// mppi_kernels.cuh -- the sm_100a kernels of the MPPI hot path.
+//
+//  K1 noise_philox_kernel          NoiseGenerator::generateNoisedControls   (noise_generator.cpp:107-122)
+//  K2 rollout_score_kernel         setNoisedControls + updateStateVelocities + predict + integrateStateVelocities
+//                                  + every critic that does not need the furthest path point
+//                                  (noise_generator.cpp:65-74, optimizer.cpp:251-273,313-343, motion_models.hpp:53-66,
+//                                   src/critics/{constraint,cost,goal,goal_angle,obstacles,prefer_forward,twirling,
+//                                   velocity_deadband}_critic.cpp, utils.hpp:292-319)
+//  K3 path_softmax_update_kernel   PathFollow / PathAlign / PathAlignLegacy / PathAngle critics, cost totals in list
+//                                  order with the fail_flag short-circuit, gamma term, softmax weights and the
+//                                  weighted control update, clip  (critic_manager.cpp:67-76, path_*_critic.cpp,
+//                                  optimizer.cpp:362-394,237-249)
+//  K4 merge_partials_kernel        cross-rank merge of the softmax partials (sharded configurations)
+//
+// Work shape of K2: one CTA owns a tile of 32 trajectories (lane == trajectory) and S warps split the
+// horizon into S contiguous segments.  The tile lives in shared memory time-major, [T][33] floats per
+// plane, which is bank-conflict free both for the coalesced row-major global load (lane == t) and for the
+// per-trajectory accesses (lane == trajectory).  The three cumulative sums (yaw, x, y) are evaluated
+// SEQUENTIALLY in t by one lane per trajectory with non-contractable fp32 adds: this is the reference's
+// summation order, and it is what makes the costmap cell indices bit-exact against the CPU oracle.
+// Everything else (sincos, costmap gathers, critic terms) is evaluated in parallel over (trajectory, t).
+#pragma once
+#include "mppi_device.cuh"
+
+namespace mppi
+{
+
+struct DevBuffers
+{
+  const float * in_a;   // mode 0: noise vx | mode 1,2: state vx      [B][T]
+  const float * in_b;   //         noise vy |            state vy
+  const float * in_c;   //         noise wz |            state wz
+  const float * in_x;   // mode 2: trajectories x, y, yaw             [B][T]
+  const float * in_y;
+  const float * in_yaw;
+  float * cs;           // control sequence [3][T]: vx, vy, wz
+  float * crit_rows;    // [n_critics + 3][B]
+  float * samples_x;    // [K][B]
+  float * samples_y;
+  float * samples_yaw;
+  float * end_xy;       // [2][B]
+  float * spill_x;      // [T][B]
+  float * spill_y;
+  float * spill_yaw;
+  int * spill_cells;    // [T][B]
+  float * costs;        // [B]
+  float * partials;     // [blocks][3T + 2]
+  float * rank_partial; // [3T + 2] (+ fail flag / furthest packed after it for the exchange)
+  float * out;          // [3T + 4]: new control sequence, fail flag, furthest (as bit patterns)
+  DevState * st;
+};
+
+// accumulator slots of the per-segment partials
+enum Acc
+{
+  A_CON = 0, A_FWD, A_TWIRL, A_DB, A_GOAL, A_GANG, A_GVX, A_GVY, A_GWZ, A_COST_REP, A_COST_HIT, A_OB_TRAJ, A_OB_REP,
+  A_OB_HIT, A_COUNT
+};
+
+__host__ __device__ inline size_t rollout_smem_bytes(int T, int S)
+{
+  // 6 tile planes + control sequence copy + per-trajectory initial velocities + segment partials + argmin scratch
+  return sizeof(float) * (static_cast<size_t>(6) * T * kPad + 3 * T + 3 * kTile + static_cast<size_t>(S) * A_COUNT * kTile +
+         2 * static_cast<size_t>(S) * kTile);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1: Philox4x32-10 + Box-Muller.  One thread = one trajectory x one quad of time steps x 3 planes;
+// counter = (t/4, plane, global trajectory, stream), key = seed: shards of a sharded batch tile exactly.
+// Stores are float4 (coalesced along t) when T % 4 == 0.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    if (r > 0) {k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;}
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0;
+    const uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float & z0, float & z1)
+{
+  const float u1 = static_cast<float>((a >> 8) + 1u) * 5.9604644775390625e-08f;   // (0,1]
+  const float u2 = static_cast<float>(b >> 8) * 5.9604644775390625e-08f;          // [0,1)
+  const float r = __fsqrt_rn(__fmul_rn(-2.0f, logf(u1)));
+  float s, c;
+  mppi_det_sincosf(__fmul_rn(6.283185307179586f, u2), &s, &c);
+  z0 = __fmul_rn(r, c);
+  z1 = __fmul_rn(r, s);
+}
+
+__global__ void __launch_bounds__(256) noise_philox_kernel(
+  float * __restrict__ nvx, float * __restrict__ nvy, float * __restrict__ nwz, int B, int T, float sx, float sy, float sw,
+  int holonomic, uint64_t seed, uint64_t stream, uint64_t shard_offset)
+{
+  const int quads = (T + 3) >> 2;
+  const long long total = static_cast<long long>(B) * quads;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+    i += static_cast<long long>(gridDim.x) * blockDim.x)
+  {
+    const int b = static_cast<int>(i / quads);
+    const int q = static_cast<int>(i - static_cast<long long>(b) * quads);
+    const uint32_t gb = static_cast<uint32_t>(static_cast<uint64_t>(b) + shard_offset);
+#pragma unroll
+    for (int plane = 0; plane < 3; ++plane) {
+      float * dst = plane == 0 ? nvx : (plane == 1 ? nvy : nwz);
+      const float sd = plane == 0 ? sx : (plane == 1 ? sy : sw);
+      float z[4] = {0.f, 0.f, 0.f, 0.f};
+      if (plane != 1 || holonomic) {
+        uint32_t r[4];
+        philox4x32_10(static_cast<uint32_t>(q), static_cast<uint32_t>(plane), gb, static_cast<uint32_t>(stream),
+          static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
+        box_muller(r[0], r[1], z[0], z[1]);
+        box_muller(r[2], r[3], z[2], z[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {z[j] = __fmul_rn(z[j], sd);}
+      }
+      float * row = dst + static_cast<size_t>(b) * T + 4 * q;
+      if ((T & 3) == 0) {
+        *reinterpret_cast<float4 *>(row) = make_float4(z[0], z[1], z[2], z[3]);
+      } else {
+        for (int j = 0; j < 4 && 4 * q + j < T; ++j) {row[j] = z[j];}
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rollout_score_kernel(
+  const DevParams * __restrict__ P, const uint8_t * __restrict__ cm, DevBuffers bufs)
+{
+  extern __shared__ float smem[];
+  const int T = P->T, B = P->B, S = blockDim.y;
+  const int lane = threadIdx.x, seg = threadIdx.y;
+  const int tplane = T * kPad;
+  float * s_cvx = smem;
+  float * s_cvy = s_cvx + tplane;
+  float * s_cwz = s_cvy + tplane;
+  float * s_yaw = s_cwz + tplane;
+  float * s_x = s_yaw + tplane;
+  float * s_y = s_x + tplane;
+  float * s_cs = s_y + tplane;                  // [3][T]
+  float * s_v0 = s_cs + 3 * T;                  // [3][32] initial velocities per trajectory
+  float * s_acc = s_v0 + 3 * kTile;             // [S][A_COUNT][32]
+  float * s_amin_d = s_acc + S * A_COUNT * kTile;   // [S][32]
+  int * s_amin_j = reinterpret_cast<int *>(s_amin_d + S * kTile);
+
+  const int b0 = blockIdx.x * kTile;
+  const int b = b0 + lane;
+  const bool live = b < B;
+  const int mode = P->mode;
+  const int hol = P->holonomic;
+  const float dt = P->dt;
+  const int tid = seg * kTile + lane;
+  const int nthreads = S * kTile;
+
+  // ---- P1: stage the tile.  Warp `seg` walks rows seg, seg+S, ...; lane walks t (coalesced 128 B rows).
+  for (int i = tid; i < 3 * T; i += nthreads) {s_cs[i] = bufs.cs[i];}
+  __syncthreads();
+  for (int r = seg; r < kTile; r += S) {
+    const int rb = b0 + r;
+    if (rb < B) {
+      const size_t row = static_cast<size_t>(rb) * T;
+      for (int t = lane; t < T; t += 32) {
+        const float a = __ldg(bufs.in_a + row + t);
+        const float c = __ldg(bufs.in_c + row + t);
+        const float bb = __ldg(bufs.in_b + row + t);
+        if (mode == 0) {
+          // setNoisedControls: c = control_sequence + noise (noise_generator.cpp:71-73)
+          s_cvx[t * kPad + r] = __fadd_rn(s_cs[t], a);
+          s_cvy[t * kPad + r] = __fadd_rn(s_cs[T + t], bb);
+          s_cwz[t * kPad + r] = __fadd_rn(s_cs[2 * T + t], c);
+        } else {
+          // injected state velocities: v[t] is stored where predict() would read it, c[t-1]
+          if (t == 0) {
+            s_v0[r] = a; s_v0[kTile + r] = bb; s_v0[2 * kTile + r] = c;
+          } else {
+            s_cvx[(t - 1) * kPad + r] = a; s_cvy[(t - 1) * kPad + r] = bb; s_cwz[(t - 1) * kPad + r] = c;
+          }
+        }
+        if (mode == 2) {
+          s_x[t * kPad + r] = __ldg(bufs.in_x + row + t);
+          s_y[t * kPad + r] = __ldg(bufs.in_y + row + t);
+          s_yaw[t * kPad + r] = __ldg(bufs.in_yaw + row + t);
+        }
+      }
+    }
+  }
+  if (mode == 0) {
+    // updateInitialStateVelocities (optimizer.cpp:258-267): v[:,0] = robot speed
+    if (seg == 0) {
+      s_v0[lane] = P->speed_vx; s_v0[kTile + lane] = hol ? P->speed_vy : 0.0f; s_v0[2 * kTile + lane] = P->speed_wz;
+    }
+  } else if (seg == 0 && live) {
+    const int o = (T - 1) * kPad + lane;
+    s_cvx[o] = 0.0f; s_cvy[o] = 0.0f; s_cwz[o] = 0.0f;
+  }
+  __syncthreads();
+
+  if (mode != 2) {
+    // ---- P2: yaw = cumsum(wz * dt) + yaw0, sequential in t (optimizer.cpp:319-320)
+    if (seg == 0 && live) {
+      const float yaw0 = P->yaw0;
+      float acc = 0.0f;
+      float wz = s_v0[2 * kTile + lane];
+#pragma unroll 4
+      for (int t = 0; t < T; ++t) {
+        const float term = __fmul_rn(wz, dt);
+        acc = t == 0 ? term : __fadd_rn(acc, term);
+        wz = s_cwz[t * kPad + lane];
+        s_yaw[t * kPad + lane] = __fadd_rn(acc, yaw0);
+      }
+    }
+    __syncthreads();
+    // ---- P3: dx*dt, dy*dt with the one-step yaw lag (optimizer.cpp:322-337), parallel over (trajectory, t)
+    if (live) {
+      const int L = (T + S - 1) / S;
+      const int t0 = seg * L, t1 = min(T, t0 + L);
+      const bool use_vy = hol || mode != 0;
+      for (int t = t0; t < t1; ++t) {
+        float sn, cn;
+        if (t == 0) {
+          sn = P->sin0; cn = P->cos0;
+        } else {
+          mppi_det_sincosf(s_yaw[(t - 1) * kPad + lane], &sn, &cn);
+        }
+        const float vx = t ? s_cvx[(t - 1) * kPad + lane] : s_v0[lane];
+        float dx = __fmul_rn(vx, cn);
+        float dy = __fmul_rn(vx, sn);
+        if (hol) {
+          const float vy = use_vy ? (t ? s_cvy[(t - 1) * kPad + lane] : s_v0[kTile + lane]) : 0.0f;
+          dx = __fsub_rn(dx, __fmul_rn(vy, sn));
+          dy = __fadd_rn(dy, __fmul_rn(vy, cn));
+        }
+        s_x[t * kPad + lane] = __fmul_rn(dx, dt);
+        s_y[t * kPad + lane] = __fmul_rn(dy, dt);
+      }
+    }
+    __syncthreads();
+    // ---- P4: x = pose.x (double) + cumsum(dx*dt) (float), sequential in t (optimizer.cpp:339-342)
+    if (live && (seg == 0 || (seg == 1 && S > 1))) {
+      const bool do_x = seg == 0, do_y = (S > 1) ? (seg == 1) : true;
+      if (do_x) {
+        const double x0 = P->pose_x;
+        float acc = 0.0f;
+#pragma unroll 4
+        for (int t = 0; t < T; ++t) {
+          const float v = s_x[t * kPad + lane];
+          acc = t == 0 ? v : __fadd_rn(acc, v);
+          s_x[t * kPad + lane] = static_cast<float>(x0 + static_cast<double>(acc));
+        }
+      }
+      if (do_y) {
+        const double y0 = P->pose_y;
+        float acc = 0.0f;
+#pragma unroll 4
+        for (int t = 0; t < T; ++t) {
+          const float v = s_y[t * kPad + lane];
+          acc = t == 0 ? v : __fadd_rn(acc, v);
+          s_y[t * kPad + lane] = static_cast<float>(y0 + static_cast<double>(acc));
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- P5: critics, parallel over (trajectory, segment of the horizon)
+  float acc[A_COUNT];
+#pragma unroll
+  for (int k = 0; k < A_COUNT; ++k) {acc[k] = 0.0f;}
+  if (live) {
+    const int L = (T + S - 1) / S;
+    const int t0 = seg * L, t1 = min(T, t0 + L);
+    const bool con_on = P->constraint.on, fwd_on = P->forward.on, twirl_on = P->twirl.on, db_on = P->deadband.on;
+    const bool goal_on = P->goal.on, gang_on = P->goal_angle.on, cost_on = P->cost.on, ob_on = P->obst.on;
+    const bool need_cell = cost_on || ob_on || P->want_cells;
+    const bool acker = P->model == MPPI_MODEL_ACKERMANN;
+    const bool track_unknown = P->track_unknown != 0;
+    const float max_vel = P->max_vel, min_vel = P->min_vel, min_r = P->min_turning_r;
+    const double gx = P->goal_x, gy = P->goal_y;
+    const float goal_yaw = P->goal_yaw;
+    const int step = P->sample_step;
+    int next_sample = step > 0 ? ((t0 + step - 1) / step) * step : T;
+    bool cost_hit = false, ob_hit = false;
+    const bool use_vy = hol || mode != 0;
+    for (int t = t0; t < t1; ++t) {
+      const int o = t * kPad + lane;
+      const float vx = t ? s_cvx[o - kPad] : s_v0[lane];
+      const float vy = use_vy ? (t ? s_cvy[o - kPad] : s_v0[kTile + lane]) : 0.0f;
+      const float wz = t ? s_cwz[o - kPad] : s_v0[2 * kTile + lane];
+      const float px = s_x[o], py = s_y[o], pyaw = s_yaw[o];
+
+      if (mode == 0) {
+        // gamma term of updateControlSequence (optimizer.cpp:365-380): sum_t cs[t] * (c[b,t] - cs[t])
+        const float csx = s_cs[t], csy = s_cs[T + t], csw = s_cs[2 * T + t];
+        acc[A_GVX] = __fadd_rn(acc[A_GVX], __fmul_rn(csx, __fsub_rn(s_cvx[o], csx)));
+        acc[A_GWZ] = __fadd_rn(acc[A_GWZ], __fmul_rn(csw, __fsub_rn(s_cwz[o], csw)));
+        if (hol) {acc[A_GVY] = __fadd_rn(acc[A_GVY], __fmul_rn(csy, __fsub_rn(s_cvy[o], csy)));}
+      }
+      if (con_on) {   // constraint_critic.cpp:49-52
+        const float sgn = vx > 0.0f ? 1.0f : -1.0f;
+        const float vel_total = sgn * sqrtf(vx * vx + vy * vy);
+        float e = fmaxf(vel_total - max_vel, 0.0f) + fmaxf(min_vel - vel_total, 0.0f);
+        if (acker) {e += fmaxf(min_r - fabsf(vx) / fabsf(wz), 0.0f);}
+        acc[A_CON] += e * dt;
+      }
+      if (fwd_on) {acc[A_FWD] += fmaxf(-vx, 0.0f) * dt;}           // prefer_forward_critic.cpp:42-46
+      if (twirl_on) {acc[A_TWIRL] += fabsf(wz);}                   // twirling_critic.cpp:40-41
+      if (db_on) {                                                 // velocity_deadband_critic.cpp:54-97
+        float e = fmaxf(fabsf(P->db_vx) - fabsf(vx), 0.0f);
+        if (hol) {e += fmaxf(fabsf(P->db_vy) - fabsf(vy), 0.0f);}
+        e += fmaxf(fabsf(P->db_wz) - fabsf(wz), 0.0f);
+        acc[A_DB] += e * dt;
+      }
+      if (goal_on) {                                               // goal_critic.cpp:50-52
+        const float dx = static_cast<float>(static_cast<double>(px) - gx);
+        const float dy = static_cast<float>(static_cast<double>(py) - gy);
+        acc[A_GOAL] += sqrtf(dx * dx + dy * dy);
+      }
+      if (gang_on) {                                               // goal_angle_critic.cpp:47-49
+        acc[A_GANG] += static_cast<float>(fabs(normalize_angle_d(static_cast<double>(__fsub_rn(goal_yaw, pyaw)))));
+      }
+      if (need_cell) {
+        unsigned mx, my;
+        const int cell = world_to_cell(px, py, P->ox, P->oy, P->res, P->size_x, P->size_y, mx, my);
+        if (P->want_cells) {bufs.spill_cells[static_cast<size_t>(t) * B + b] = cell;}
+        if ((cost_on && !cost_hit) || (ob_on && !ob_hit)) {
+          const int pose_cost = cell < 0 ? NO_INFORMATION : __ldg(cm + cell);
+          int fp_cost = -1;
+          if (cost_on && !cost_hit && pose_cost >= 1) {            // cost_critic.cpp:139-162
+            int c = pose_cost;
+            const float pic = P->cost_possibly_inscribed;
+            if (P->cost_fp && (static_cast<float>(c) >= pic || pic < 1.0f)) {
+              fp_cost = footprint_cost_at_pose(P, cm, px, py, pyaw);
+              c = fp_cost;
+            }
+            if (in_collision(c, P->cost_fp != 0, track_unknown)) {
+              cost_hit = true;
+            } else if (pose_cost >= INSCRIBED_INFLATED_OBSTACLE) {
+              acc[A_COST_REP] += P->cost_critical;
+            } else if (!P->cost_near_goal) {
+              acc[A_COST_REP] += static_cast<float>(pose_cost);
+            }
+          }
+          if (ob_on && !ob_hit) {                                  // obstacles_critic.cpp:145-170, :203-224
+            int c = pose_cost;
+            int using_fp = 0;
+            const float pic = P->obst_possibly_inscribed;
+            if (cell >= 0 && P->obst_fp && (static_cast<float>(c) >= pic || pic < 1.0f)) {
+              if (fp_cost < 0) {fp_cost = footprint_cost_at_pose(P, cm, px, py, pyaw);}
+              c = fp_cost;
+              using_fp = 1;
+            }
+            if (c >= 1) {
+              if (in_collision(c, P->obst_fp != 0, track_unknown)) {
+                ob_hit = true;
+              } else if (P->obst_repulsion_enabled) {
+                acc[A_OB_TRAJ] += P->obst_lut_crit[using_fp][c];
+                if (!P->obst_near_goal) {acc[A_OB_REP] += P->obst_lut_rep[using_fp][c];}
+              }
+            }
+          }
+        }
+      }
+      // spills for the path critics of K3
+      if (t == next_sample) {
+        const size_t k = static_cast<size_t>(t / step);
+        bufs.samples_x[k * B + b] = px;
+        bufs.samples_y[k * B + b] = py;
+        if (P->sample_yaw) {bufs.samples_yaw[k * B + b] = pyaw;}
+        next_sample += step;
+      }
+      if (t == T - 1) {
+        bufs.end_xy[b] = px;
+        bufs.end_xy[B + b] = py;
+      }
+      if (P->spill_traj) {
+        const size_t g = static_cast<size_t>(t) * B + b;
+        bufs.spill_x[g] = px; bufs.spill_y[g] = py; bufs.spill_yaw[g] = pyaw;
+      }
+    }
+    acc[A_COST_HIT] = cost_hit ? 1.0f : 0.0f;
+    acc[A_OB_HIT] = ob_hit ? 1.0f : 0.0f;
+  }
+#pragma unroll
+  for (int k = 0; k < A_COUNT; ++k) {s_acc[(seg * A_COUNT + k) * kTile + lane] = acc[k];}
+
+  // ---- furthest reached path point candidate: argmin over the path of the end pose (utils.hpp:292-319),
+  //      path range split over the warps, combined in order so the first minimum wins
+  const int N = P->N;
+  const bool need_furthest = (P->follow.idx >= 0 || P->angle.idx >= 0 || P->align.idx >= 0 || P->legacy.idx >= 0);
+  if (need_furthest) {
+    const float * __restrict__ path_x = reinterpret_cast<const float *>(P + 1) + P->off_path_x;
+    const float * __restrict__ path_y = reinterpret_cast<const float *>(P + 1) + P->off_path_y;
+    const float ex = s_x[(T - 1) * kPad + lane], ey = s_y[(T - 1) * kPad + lane];
+    const int per = (N + S - 1) / S;
+    const int j0 = seg * per, j1 = min(N, j0 + per);
+    float best = 3.402823466e+38f;
+    int best_j = j0 < N ? j0 : 0;
+    for (int j = j0; j < j1; ++j) {
+      const float dx = __fsub_rn(__ldg(path_x + j), ex);
+      const float dy = __fsub_rn(__ldg(path_y + j), ey);
+      const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+      if (d < best) {best = d; best_j = j;}
+    }
+    s_amin_d[seg * kTile + lane] = best;
+    s_amin_j[seg * kTile + lane] = best_j;
+  }
+  __syncthreads();
+
+  // ---- P6: combine the segments in order, finish the per-critic terms, publish
+  if (seg == 0) {
+    float tot[A_COUNT];
+#pragma unroll
+    for (int k = 0; k < A_COUNT; ++k) {tot[k] = 0.0f;}
+    bool cost_collided = false, ob_collided = false;
+    for (int s = 0; s < S; ++s) {
+      const float * a = s_acc + static_cast<size_t>(s) * A_COUNT * kTile + lane;
+#pragma unroll
+      for (int k = 0; k <= A_GWZ; ++k) {tot[k] = s == 0 ? a[k * kTile] : __fadd_rn(tot[k], a[k * kTile]);}
+      if (!cost_collided) {
+        tot[A_COST_REP] += a[A_COST_REP * kTile];
+        cost_collided = a[A_COST_HIT * kTile] != 0.0f;
+      }
+      if (!ob_collided) {
+        tot[A_OB_TRAJ] += a[A_OB_TRAJ * kTile];
+        tot[A_OB_REP] += a[A_OB_REP * kTile];
+        ob_collided = a[A_OB_HIT * kTile] != 0.0f;
+      }
+    }
+    const float Tf = static_cast<float>(T);
+    float * rows = bufs.crit_rows;
+    if (live) {
+      if (P->constraint.on) {rows[static_cast<size_t>(P->constraint.idx) * B + b] = add_pow(0.0f, tot[A_CON] * P->constraint.weight, P->constraint.power);}
+      if (P->forward.on) {rows[static_cast<size_t>(P->forward.idx) * B + b] = add_pow(0.0f, tot[A_FWD] * P->forward.weight, P->forward.power);}
+      if (P->twirl.on) {rows[static_cast<size_t>(P->twirl.idx) * B + b] = add_pow(0.0f, (tot[A_TWIRL] / Tf) * P->twirl.weight, P->twirl.power);}
+      if (P->deadband.on) {rows[static_cast<size_t>(P->deadband.idx) * B + b] = add_pow(0.0f, tot[A_DB] * P->deadband.weight, P->deadband.power);}
+      if (P->goal.on) {rows[static_cast<size_t>(P->goal.idx) * B + b] = add_pow(0.0f, (tot[A_GOAL] / Tf) * P->goal.weight, P->goal.power);}
+      if (P->goal_angle.on) {rows[static_cast<size_t>(P->goal_angle.idx) * B + b] = add_pow(0.0f, (tot[A_GANG] / Tf) * P->goal_angle.weight, P->goal_angle.power);}
+      if (P->cost.on) {   // cost_critic.cpp:159-166
+        const float rep = cost_collided ? P->cost_collision : tot[A_COST_REP];
+        rows[static_cast<size_t>(P->cost.idx) * B + b] = add_pow(0.0f, P->cost.weight * rep / Tf, P->cost.power);
+      }
+      if (P->obst.on) {   // obstacles_critic.cpp:169-176
+        const float raw = ob_collided ? P->obst_collision : tot[A_OB_TRAJ];
+        const float v = (P->obst_critical_w * raw) + (P->obst_repulsion_w * tot[A_OB_REP] / Tf);
+        rows[static_cast<size_t>(P->obst.idx) * B + b] = add_pow(0.0f, v, P->obst.power);
+      }
+      if (mode == 0) {
+        const size_t g = static_cast<size_t>(P->n_critics) * B + b;
+        rows[g] = tot[A_GVX]; rows[g + B] = tot[A_GVY]; rows[g + 2 * static_cast<size_t>(B)] = tot[A_GWZ];
+      }
+    }
+    // fail_flag inputs: did any trajectory of this tile survive?
+    if (P->cost.on) {
+      const unsigned ok = __ballot_sync(0xffffffffu, live && !cost_collided);
+      if (lane == 0 && ok) {atomicOr(&bufs.st->any_ok[P->cost.idx], 1u);}
+    }
+    if (P->obst.on) {
+      const unsigned ok = __ballot_sync(0xffffffffu, live && !ob_collided);
+      if (lane == 0 && ok) {atomicOr(&bufs.st->any_ok[P->obst.idx], 1u);}
+    }
+    if (need_furthest) {
+      float best = s_amin_d[lane];
+      int best_j = s_amin_j[lane];
+      for (int s = 1; s < S; ++s) {
+        const float d = s_amin_d[s * kTile + lane];
+        if (d < best) {best = d; best_j = s_amin_j[s * kTile + lane];}
+      }
+      const unsigned m = warp_max_u(live ? static_cast<unsigned>(best_j) : 0u);
+      if (lane == 0) {atomicMax(&bufs.st->furthest_candidate, m);}
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3
+// ---------------------------------------------------------------------------------------------------
+constexpr int kUpdThreads = 128;
+
+// utils::findClosestPathPt (utils.hpp:665-675) on the prefix D[0..n); out-of-range clamps to n-1
+__device__ __forceinline__ int find_closest_path_pt(const float * D, int n, float dist, int init)
+{
+  int lo = init, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (D[mid] < dist) {lo = mid + 1;} else {hi = mid;}
+  }
+  if (lo == init) {return 0;}
+  if (lo == n) {return n - 1;}
+  if (__fsub_rn(dist, D[lo - 1]) < __fsub_rn(D[lo], dist)) {return lo - 1;}
+  return lo;
+}
+
+__device__ __forceinline__ void finalize_controls(
+  const DevParams * __restrict__ P, const float * __restrict__ merged, float * __restrict__ cs, float * __restrict__ out, int tid, int nthr)
+{
+  // merged = [min, sum, W_vx[T], W_vy[T], W_wz[T]] ; cs = W / sum, then applyControlSequenceConstraints
+  const int T = P->T;
+  const float inv = merged[1];
+  for (int t = tid; t < T; t += nthr) {
+    float vx = merged[2 + t] / inv;
+    float wz = merged[2 + 2 * T + t] / inv;
+    float vy = cs[T + t];
+    if (P->holonomic) {
+      vy = merged[2 + T + t] / inv;
+      vy = fminf(fmaxf(vy, -P->c_vy), P->c_vy);
+    }
+    vx = fminf(fmaxf(vx, P->c_vx_min), P->c_vx_max);
+    wz = fminf(fmaxf(wz, -P->c_wz), P->c_wz);
+    if (P->model == MPPI_MODEL_ACKERMANN) {   // motion_models.hpp:110-117
+      const float r = P->min_turning_r;
+      if (fabsf(vx) / fabsf(wz) < r) {
+        const float sgn = wz > 0.0f ? 1.0f : (wz < 0.0f ? -1.0f : 0.0f);
+        wz = sgn * fabsf(vx) / r;
+      }
+    }
+    cs[t] = vx; cs[T + t] = vy; cs[2 * T + t] = wz;
+    out[t] = vx; out[T + t] = vy; out[2 * T + t] = wz;
+  }
+}
+
+// merge n partial records [m, s, W...] (online-softmax merge, SURVEY 8e exchange 2) into dst.
+// Called by every thread of one block; `parts` is scratch (slot 0 of each record is overwritten by its scale).
+__device__ __forceinline__ void merge_partials(
+  float * __restrict__ parts, int n, int stride, int T, float inv_temp, float * dst, float * s_red, int tid, int nthr)
+{
+  float m = 3.402823466e+38f;
+  for (int i = tid; i < n; i += nthr) {m = fminf(m, parts[static_cast<size_t>(i) * stride]);}
+  m = warp_min(m);
+  if ((tid & 31) == 0) {s_red[tid >> 5] = m;}
+  __syncthreads();
+  m = s_red[0];
+  for (int w = 1; w < nthr / 32; ++w) {m = fminf(m, s_red[w]);}
+  __syncthreads();
+  for (int i = tid; i < n; i += nthr) {
+    float * p = parts + static_cast<size_t>(i) * stride;
+    p[0] = expf(-(p[0] - m) * inv_temp);
+  }
+  __syncthreads();
+  for (int c = tid; c < 3 * T + 1; c += nthr) {
+    float acc = 0.0f;
+    for (int i = 0; i < n; ++i) {
+      const float * p = parts + static_cast<size_t>(i) * stride;
+      acc = fmaf(p[1 + c], p[0], acc);
+    }
+    dst[1 + c] = acc;
+  }
+  if (tid == 0) {dst[0] = m;}
+}
+
+__global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
+  const DevParams * __restrict__ P, const uint8_t * __restrict__ cm, DevBuffers bufs, int n_ranks, int iteration)
+{
+  extern __shared__ float smem[];
+  const int T = P->T, B = P->B, N = P->N, nc = P->n_critics;
+  const int tid = threadIdx.x;
+  const float * __restrict__ path_x = reinterpret_cast<const float *>(P + 1) + P->off_path_x;
+  const float * __restrict__ path_y = reinterpret_cast<const float *>(P + 1) + P->off_path_y;
+  const float * __restrict__ path_yaw = reinterpret_cast<const float *>(P + 1) + P->off_path_yaw;
+  const float * __restrict__ path_D = reinterpret_cast<const float *>(P + 1) + P->off_path_D;
+  const uint8_t * __restrict__ gate = reinterpret_cast<const uint8_t *>(reinterpret_cast<const float *>(P + 1) + P->off_gate);
+
+  float * s_D = smem;                                   // [N]
+  float * s_w = s_D + N;                                // [kUpdThreads]
+  float * s_red = s_w + kUpdThreads;                    // [32]
+  uint8_t * s_valid = reinterpret_cast<uint8_t *>(s_red + 32);   // [N]
+  __shared__ int sc_fail_at, sc_furthest, sc_furthest_set, sc_follow_idx, sc_align_go, sc_legacy_go, sc_angle_go, sc_angle_idx;
+  __shared__ int sc_closest;
+  __shared__ unsigned sc_last;
+
+  DevState * st = bufs.st;
+  const bool any_path_critic = (P->follow.on || P->align.on || P->legacy.on || P->angle.on);
+
+  // ---- phase 0a: path validity (utils.hpp:361-394) and the arc-length prefix into smem
+  if (any_path_critic) {
+    for (int j = tid; j < N; j += kUpdThreads) {
+      s_D[j] = path_D[j];
+      bool ok = false;
+      if (j < N - 1) {
+        unsigned mx, my;
+        const int cell = world_to_cell(__ldg(path_x + j), __ldg(path_y + j), P->ox, P->oy, P->res, P->size_x, P->size_y, mx, my);
+        if (cell >= 0) {
+          const int c = __ldg(cm + cell);
+          ok = !(c == LETHAL_OBSTACLE || c == INSCRIBED_INFLATED_OBSTACLE || (c == NO_INFORMATION && !P->track_unknown));
+        }
+      }
+      s_valid[j] = ok ? 1 : 0;
+    }
+  }
+  // closest path point to the start of the trajectories (utils.hpp:327-344): warp 0, first minimum wins
+  if (tid < 32) {
+    int cj = 0;
+    if ((P->align.on || P->legacy.on) && P->sample_step > 0) {
+      const float x0 = bufs.samples_x[0], y0 = bufs.samples_y[0];
+      float best = 3.402823466e+38f;
+      int best_j = 0x7fffffff;
+      for (int j = tid; j < N; j += 32) {
+        const float dx = __fsub_rn(__ldg(path_x + j), x0);
+        const float dy = __fsub_rn(__ldg(path_y + j), y0);
+        const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        if (d < best) {best = d; best_j = j;}
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+        if (od < best || (od == best && oj < best_j)) {best = od; best_j = oj;}
+      }
+      cj = best_j == 0x7fffffff ? 0 : best_j;
+    }
+    if (tid == 0) {sc_closest = cj;}
+  }
+  __syncthreads();
+
+  // ---- phase 0b: the scalar control flow of CriticManager::evalTrajectoriesScores, by one thread
+  if (tid == 0) {
+    int fail_at = nc;   // index of the critic that raised fail_flag; critics after it are skipped
+    if (iteration > 0 && st->fail_flag) {
+      fail_at = -1;     // fail_flag is only cleared in prepare(): a failed iteration mutes the following ones
+    } else {
+      for (int q = 0; q < nc; ++q) {
+        const int kind = P->kind_of[q];
+        const bool obstacle_like = (kind == MPPI_CRITIC_COST && P->cost.on) || (kind == MPPI_CRITIC_OBSTACLES && P->obst.on);
+        if (obstacle_like && st->any_ok[q] == 0u) {fail_at = q; break;}
+      }
+    }
+    unsigned furthest;
+    int fset;
+    if (iteration == 0) {
+      fset = P->preset_furthest != kUnset; furthest = fset ? P->preset_furthest : 0u;
+    } else {
+      fset = st->furthest_set; furthest = st->furthest;
+    }
+    auto runs = [&](const CriticCommon & c) {return c.on && c.idx <= fail_at;};
+    // critics in list order that call setPathFurthestPointIfNotSet
+    for (int q = 0; q < nc && !fset; ++q) {
+      if (q > fail_at) {break;}
+      const int kind = P->kind_of[q];
+      const bool wants = (kind == MPPI_CRITIC_PATH_FOLLOW && P->follow.on) || (kind == MPPI_CRITIC_PATH_ANGLE && P->angle.on) ||
+        (kind == MPPI_CRITIC_PATH_ALIGN && P->align.on) || (kind == MPPI_CRITIC_PATH_ALIGN_LEGACY && P->legacy.on);
+      if (wants) {furthest = st->furthest_candidate; fset = 1;}
+    }
+    sc_fail_at = fail_at;
+    sc_furthest = static_cast<int>(furthest);
+    sc_furthest_set = fset;
+    // PathFollow target (path_follow_critic.cpp:45-58)
+    int fidx = 0;
+    if (runs(P->follow)) {
+      const int path_size = N - 1;
+      fidx = min(static_cast<int>(furthest) + P->follow_offset, path_size);
+      bool valid = false;
+      while (!valid && fidx < path_size - 1) {
+        valid = s_valid[fidx] != 0;
+        if (!valid) {fidx++;}
+      }
+    }
+    sc_follow_idx = fidx;
+    // PathAlign gates (path_align_critic.cpp:56-72)
+    auto align_gate = [&](const CriticCommon & c, int offset, float max_ratio) -> int {
+        if (!runs(c)) {return 0;}
+        if (static_cast<int>(furthest) < offset) {return 0;}
+        const int closest = sc_closest;
+        unsigned invalid_ctr = 0;
+        const float range = static_cast<float>(static_cast<long long>(furthest) - closest);
+        for (int i = closest; i < static_cast<int>(furthest); ++i) {
+          if (!s_valid[i]) {invalid_ctr++;}
+          if (static_cast<float>(invalid_ctr) / range > max_ratio && invalid_ctr > 2) {return 0;}
+        }
+        return 1;
+      };
+    sc_align_go = align_gate(P->align, P->align_offset, P->align_max_ratio) && furthest > 0u;
+    sc_legacy_go = align_gate(P->legacy, P->legacy_offset, P->legacy_max_ratio) && (N - 1) >= 1;
+    // PathAngle gate (path_angle_critic.cpp:73-83): decided per candidate index on the host
+    int ago = 0, aidx = 0;
+    if (runs(P->angle)) {
+      aidx = min(static_cast<int>(furthest) + P->angle_offset, N - 1);
+      ago = gate[aidx] != 0;
+    }
+    sc_angle_go = ago; sc_angle_idx = aidx;
+  }
+  __syncthreads();
+
+  // ---- phase 1: one thread per trajectory: path critics + total in list order
+  const int b = blockIdx.x * kUpdThreads + tid;
+  const bool live = b < B;
+  const int fail_at = sc_fail_at;
+  const int furthest = sc_furthest;
+  float total = 3.402823466e+38f;
+  if (live) {
+    total = (iteration == 0 && P->mode == 0) ? 0.0f : bufs.costs[b];
+    float * rows = bufs.crit_rows;
+    for (int q = 0; q < nc; ++q) {
+      if (q > fail_at) {break;}
+      const int kind = P->kind_of[q];
+      float term = 0.0f;
+      bool has = false;
+      switch (kind) {
+        case MPPI_CRITIC_PATH_FOLLOW:
+          if (P->follow.on) {    // path_follow_critic.cpp:60-70
+            const float dx = bufs.end_xy[b] - __ldg(path_x + sc_follow_idx);
+            const float dy = bufs.end_xy[B + b] - __ldg(path_y + sc_follow_idx);
+            term = add_pow(0.0f, P->follow.weight * sqrtf(dx * dx + dy * dy), P->follow.power);
+            has = true;
+          }
+          break;
+        case MPPI_CRITIC_PATH_ALIGN:
+          if (sc_align_go) {     // path_align_critic.cpp:92-135, sequential and in the reference's fp32 order
+            const int step = P->align_step;
+            float traj_d = 0.0f, summed = 0.0f, num = 0.0f;
+            int path_pt = 0;
+            float prev_x = bufs.samples_x[b], prev_y = bufs.samples_y[b];
+            int k = 1;
+            for (int p = step; p < T; p += step, ++k) {
+              const float Tx = bufs.samples_x[static_cast<size_t>(k) * B + b];
+              const float Ty = bufs.samples_y[static_cast<size_t>(k) * B + b];
+              float dx = __fsub_rn(Tx, prev_x), dy = __fsub_rn(Ty, prev_y);
+              traj_d = __fadd_rn(traj_d, __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
+              path_pt = find_closest_path_pt(s_D, furthest, traj_d, path_pt);
+              if (s_valid[path_pt]) {
+                dx = __fsub_rn(__ldg(path_x + path_pt), Tx);
+                dy = __fsub_rn(__ldg(path_y + path_pt), Ty);
+                num = __fadd_rn(num, 1.0f);
+                if (P->align_use_yaw) {
+                  const float Tyaw = bufs.samples_yaw[static_cast<size_t>(k) * B + b];
+                  const float dyaw = static_cast<float>(normalize_angle_d(static_cast<double>(Tyaw) - static_cast<double>(__ldg(path_yaw + path_pt))));
+                  summed = __fadd_rn(summed, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dyaw, dyaw))));
+                } else {
+                  summed = __fadd_rn(summed, __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
+                }
+              }
+              prev_x = Tx; prev_y = Ty;
+            }
+            const float cost = num > 0.0f ? __fdiv_rn(summed, num) : 0.0f;
+            term = add_pow(0.0f, __fmul_rn(cost, P->align.weight), P->align.power);
+            has = true;
+          }
+          break;
+        case MPPI_CRITIC_PATH_ALIGN_LEGACY:
+          if (sc_legacy_go) {    // path_align_legacy_critic.cpp:97-128
+            const int step = P->legacy_step;
+            const int segs = N - 1;
+            float summed = 0.0f;
+            int k = 1;
+            for (int p = step; p < T; p += step, ++k) {
+              const float Tx = bufs.samples_x[static_cast<size_t>(k) * B + b];
+              const float Ty = bufs.samples_y[static_cast<size_t>(k) * B + b];
+              float Tyaw = 0.0f;
+              if (P->legacy_use_yaw) {Tyaw = bufs.samples_yaw[static_cast<size_t>(k) * B + b];}
+              float min_d = 3.402823466e+38f;
+              int min_s = 0;
+              for (int s = 0; s < segs - 1; ++s) {
+                const float dx = __fsub_rn(__ldg(path_x + s), Tx);
+                const float dy = __fsub_rn(__ldg(path_y + s), Ty);
+                float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                if (P->legacy_use_yaw) {
+                  const float dyaw = static_cast<float>(normalize_angle_d(static_cast<double>(Tyaw) - static_cast<double>(__ldg(path_yaw + s))));
+                  d = __fadd_rn(d, __fmul_rn(dyaw, dyaw));
+                }
+                if (d < min_d) {min_d = d; min_s = s;}
+              }
+              if (min_s != 0 && s_valid[min_s]) {summed = __fadd_rn(summed, __fsqrt_rn(min_d));}
+            }
+            const float evals = static_cast<float>(T / step);
+            term = add_pow(0.0f, __fmul_rn(__fdiv_rn(summed, evals), P->legacy.weight), P->legacy.power);
+            has = true;
+          }
+          break;
+        case MPPI_CRITIC_PATH_ANGLE:
+          if (sc_angle_go) {     // path_angle_critic.cpp:85-100
+            const float gx = __ldg(path_x + sc_angle_idx), gy = __ldg(path_y + sc_angle_idx);
+            float sum = 0.0f;
+            for (int t = 0; t < T; ++t) {
+              const size_t g = static_cast<size_t>(t) * B + b;
+              const float x = bufs.spill_x[g], y = bufs.spill_y[g], yaw = bufs.spill_yaw[g];
+              const float ybp = atan2f(__fsub_rn(gy, y), __fsub_rn(gx, x));
+              double v = fabs(normalize_angle_d(static_cast<double>(__fsub_rn(ybp, yaw))));
+              if (P->angle_reversing && !P->angle_forward_pref) {
+                const double corrected = v < 1.57079632679489661923 ? static_cast<double>(ybp) :
+                  normalize_angle_d(static_cast<double>(ybp) + 3.14159265358979323846);
+                v = fabs(normalize_angle_d(corrected - static_cast<double>(yaw)));
+              }
+              sum += static_cast<float>(v);
+            }
+            term = add_pow(0.0f, (sum / static_cast<float>(T)) * P->angle.weight, P->angle.power);
+            has = true;
+          }
+          break;
+        case MPPI_CRITIC_CONSTRAINT: has = P->constraint.on; break;
+        case MPPI_CRITIC_COST: has = P->cost.on; break;
+        case MPPI_CRITIC_GOAL: has = P->goal.on; break;
+        case MPPI_CRITIC_GOAL_ANGLE: has = P->goal_angle.on; break;
+        case MPPI_CRITIC_OBSTACLES: has = P->obst.on; break;
+        case MPPI_CRITIC_PREFER_FORWARD: has = P->forward.on; break;
+        case MPPI_CRITIC_TWIRLING: has = P->twirl.on; break;
+        case MPPI_CRITIC_VELOCITY_DEADBAND: has = P->deadband.on; break;
+        default: break;
+      }
+      const bool from_k3 = kind == MPPI_CRITIC_PATH_FOLLOW || kind == MPPI_CRITIC_PATH_ALIGN ||
+        kind == MPPI_CRITIC_PATH_ALIGN_LEGACY || kind == MPPI_CRITIC_PATH_ANGLE;
+      if (from_k3) {
+        rows[static_cast<size_t>(q) * B + b] = term;   // always defined for the per-critic getter
+      } else if (has) {
+        term = rows[static_cast<size_t>(q) * B + b];
+      }
+      if (has) {total = __fadd_rn(total, term);}
+    }
+    // rows of critics that did not run read as zero for the getter
+    for (int q = 0; q < nc; ++q) {
+      const int kind = P->kind_of[q];
+      const bool from_k3 = kind == MPPI_CRITIC_PATH_FOLLOW || kind == MPPI_CRITIC_PATH_ALIGN ||
+        kind == MPPI_CRITIC_PATH_ALIGN_LEGACY || kind == MPPI_CRITIC_PATH_ANGLE;
+      bool on = false;
+      switch (kind) {
+        case MPPI_CRITIC_CONSTRAINT: on = P->constraint.on; break;
+        case MPPI_CRITIC_COST: on = P->cost.on; break;
+        case MPPI_CRITIC_GOAL: on = P->goal.on; break;
+        case MPPI_CRITIC_GOAL_ANGLE: on = P->goal_angle.on; break;
+        case MPPI_CRITIC_OBSTACLES: on = P->obst.on; break;
+        case MPPI_CRITIC_PREFER_FORWARD: on = P->forward.on; break;
+        case MPPI_CRITIC_TWIRLING: on = P->twirl.on; break;
+        case MPPI_CRITIC_VELOCITY_DEADBAND: on = P->deadband.on; break;
+        default: break;
+      }
+      if (q > fail_at || (!from_k3 && !on)) {rows[static_cast<size_t>(q) * B + b] = 0.0f;}
+    }
+    if (P->mode == 0) {
+      // gamma term (optimizer.cpp:367-380): vx, then wz, then vy (holonomic)
+      const size_t g = static_cast<size_t>(nc) * B + b;
+      total = __fadd_rn(total, __fmul_rn(P->gamma_vx, rows[g]));
+      total = __fadd_rn(total, __fmul_rn(P->gamma_wz, rows[g + 2 * static_cast<size_t>(B)]));
+      if (P->holonomic) {total = __fadd_rn(total, __fmul_rn(P->gamma_vy, rows[g + B]));}
+    }
+    bufs.costs[b] = total;
+  }
+
+  if (P->mode != 0) {
+    // score mode: no control update; the last block publishes the flags
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {sc_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;}
+    __syncthreads();
+    if (sc_last && tid == 0) {
+      st->fail_flag = fail_at < nc ? 1 : 0;
+      st->furthest = static_cast<unsigned>(sc_furthest);
+      st->furthest_set = sc_furthest_set;
+      st->furthest_candidate = 0u;
+      for (int q = 0; q < kMaxCritics; ++q) {st->any_ok[q] = 0u;}
+      st->ticket = 0u;
+      float * out = bufs.out;
+      out[3 * T] = __int_as_float(st->fail_flag);
+      out[3 * T + 1] = __uint_as_float(sc_furthest_set ? static_cast<unsigned>(sc_furthest) : kUnset);
+    }
+    return;
+  }
+
+  // ---- phase 2: softmax partial of this block (optimizer.cpp:382-391): m = min, w = exp(-(c-m)/T), s = sum w
+  const float inv_temp = 1.0f / P->temperature;
+  float m = warp_min(total);
+  if ((tid & 31) == 0) {s_red[tid >> 5] = m;}
+  __syncthreads();
+  m = s_red[0];
+#pragma unroll
+  for (int w = 1; w < kUpdThreads / 32; ++w) {m = fminf(m, s_red[w]);}
+  __syncthreads();
+  const float w_b = live ? expf(-(total - m) * inv_temp) : 0.0f;
+  s_w[tid] = w_b;
+  float ssum = warp_sum(w_b);
+  if ((tid & 31) == 0) {s_red[tid >> 5] = ssum;}
+  __syncthreads();
+  ssum = 0.0f;
+#pragma unroll
+  for (int w = 0; w < kUpdThreads / 32; ++w) {ssum += s_red[w];}
+
+  // ---- phase 3: weighted column sums over this block's rows, W[c][t] = sum_b w_b * (cs[t] + noise[b,t])
+  const int stride = 3 * T + 2;
+  float * part = bufs.partials + static_cast<size_t>(blockIdx.x) * stride;
+  const int rows_here = min(kUpdThreads, B - blockIdx.x * kUpdThreads);
+  const size_t row0 = static_cast<size_t>(blockIdx.x) * kUpdThreads * T;
+  for (int c = tid; c < 3 * T; c += kUpdThreads) {
+    const int plane = c / T, t = c - plane * T;
+    const float * __restrict__ src = (plane == 0 ? bufs.in_a : (plane == 1 ? bufs.in_b : bufs.in_c)) + row0 + t;
+    const float cs_t = bufs.cs[c];
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    int r = 0;
+    for (; r + 3 < rows_here; r += 4) {
+      a0 = fmaf(s_w[r], __fadd_rn(cs_t, __ldg(src + static_cast<size_t>(r) * T)), a0);
+      a1 = fmaf(s_w[r + 1], __fadd_rn(cs_t, __ldg(src + static_cast<size_t>(r + 1) * T)), a1);
+      a2 = fmaf(s_w[r + 2], __fadd_rn(cs_t, __ldg(src + static_cast<size_t>(r + 2) * T)), a2);
+      a3 = fmaf(s_w[r + 3], __fadd_rn(cs_t, __ldg(src + static_cast<size_t>(r + 3) * T)), a3);
+    }
+    for (; r < rows_here; ++r) {a0 = fmaf(s_w[r], __fadd_rn(cs_t, __ldg(src + static_cast<size_t>(r) * T)), a0);}
+    part[2 + c] = (a0 + a1) + (a2 + a3);
+  }
+  if (tid == 0) {part[0] = m; part[1] = ssum;}
+
+  // ---- phase 4: the last block to finish merges all partials and writes the new control sequence
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {sc_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;}
+  __syncthreads();
+  if (!sc_last) {return;}
+  __threadfence();
+  float * merged = bufs.rank_partial;   // [3T + 2]
+  merge_partials(bufs.partials, gridDim.x, stride, T, inv_temp, merged, s_red, tid, kUpdThreads);
+  __syncthreads();
+  if (tid == 0) {
+    st->fail_flag = fail_at < nc ? 1 : 0;
+    st->furthest = static_cast<unsigned>(sc_furthest);
+    st->furthest_set = sc_furthest_set;
+    st->furthest_candidate = 0u;
+    for (int q = 0; q < kMaxCritics; ++q) {st->any_ok[q] = 0u;}
+    st->ticket = 0u;
+    float * out = bufs.out;
+    out[3 * T] = __int_as_float(st->fail_flag);
+    out[3 * T + 1] = __uint_as_float(sc_furthest_set ? static_cast<unsigned>(sc_furthest) : kUnset);
+  }
+  if (n_ranks <= 1) {
+    __threadfence_block();
+    __syncthreads();
+    finalize_controls(P, merged, bufs.cs, bufs.out, tid, kUpdThreads);
+  }
+}
+
+// K4: sharded configurations.  `gathered` holds n_ranks records [m, s, W...] (all-gathered over NCCL);
+// every rank merges them redundantly and applies the clip, so no broadcast is needed afterwards.
+__global__ void __launch_bounds__(kUpdThreads) merge_partials_kernel(
+  const DevParams * __restrict__ P, float * __restrict__ gathered, int n_ranks, int stride, DevBuffers bufs)
+{
+  __shared__ float s_merged[3 * MPPI_MAX_TIME_STEPS + 2];
+  __shared__ float s_red[32];
+  const float inv_temp = 1.0f / P->temperature;
+  merge_partials(gathered, n_ranks, stride, P->T, inv_temp, s_merged, s_red, threadIdx.x, kUpdThreads);
+  __syncthreads();
+  finalize_controls(P, s_merged, bufs.cs, bufs.out, threadIdx.x, kUpdThreads);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small utility kernels
+// ---------------------------------------------------------------------------------------------------
+// time-major [T][B] -> row-major [B][T] (getGeneratedTrajectories / cell indices for the host)
+template<typename V>
+__global__ void transpose_tb_to_bt_kernel(const V * __restrict__ src, V * __restrict__ dst, int T, int B)
+{
+  __shared__ V tile[32][33];
+  const int b0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, b = b0 + threadIdx.x;
+    if (t < T && b < B) {tile[i][threadIdx.x] = src[static_cast<size_t>(t) * B + b];}
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int b = b0 + i, t = t0 + threadIdx.x;
+    if (t < T && b < B) {dst[static_cast<size_t>(b) * T + t] = tile[threadIdx.x][i];}
+  }
+}
+
+// Optimizer::shiftControlSequence (optimizer.cpp:206-225): roll by -1, last = second to last
+__global__ void shift_control_sequence_kernel(float * __restrict__ cs, int T, int holonomic)
+{
+  __shared__ float tmp[MPPI_MAX_TIME_STEPS];
+  for (int plane = 0; plane < 3; ++plane) {
+    if (plane == 1 && !holonomic) {continue;}
+    float * v = cs + plane * T;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {tmp[t] = v[t];}
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      // rolled[t] = old[t+1] (rolled[T-1] = old[0]); then rolled[T-1] = rolled[T-2] = old[T-1]
+      v[t] = t < T - 1 ? tmp[t + 1] : (T >= 2 ? tmp[T - 1] : tmp[0]);
+    }
+    __syncthreads();
+  }
+}
+
+// Optimizer::getOptimizedTrajectory (optimizer.cpp:345-360, :275-311): one trajectory from the mean controls
+__global__ void optimized_trajectory_kernel(const float * __restrict__ cs, float * __restrict__ out_t3, int T, int holonomic,
+  float dt, double pose_x, double pose_y, float yaw0)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) {return;}
+  float acc = 0.0f, accx = 0.0f, accy = 0.0f, prev_yaw = yaw0;
+  for (int t = 0; t < T; ++t) {
+    const float term = __fmul_rn(cs[2 * T + t], dt);
+    acc = t == 0 ? term : __fadd_rn(acc, term);
+    const float yaw = __fadd_rn(acc, yaw0);
+    float sn, cn;
+    mppi_det_sincosf(prev_yaw, &sn, &cn);
+    float dx = __fmul_rn(cs[t], cn), dy = __fmul_rn(cs[t], sn);
+    if (holonomic) {
+      dx = __fsub_rn(dx, __fmul_rn(cs[T + t], sn));
+      dy = __fadd_rn(dy, __fmul_rn(cs[T + t], cn));
+    }
+    const float tx = __fmul_rn(dx, dt), ty = __fmul_rn(dy, dt);
+    accx = t == 0 ? tx : __fadd_rn(accx, tx);
+    accy = t == 0 ? ty : __fadd_rn(accy, ty);
+    out_t3[3 * t] = static_cast<float>(pose_x + static_cast<double>(accx));
+    out_t3[3 * t + 1] = static_cast<float>(pose_y + static_cast<double>(accy));
+    out_t3[3 * t + 2] = yaw;
+    prev_yaw = yaw;
+  }
+}
+
+}  // namespace mppi
