@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- rollout-steps/s and optimize() latency of the MPPI hot path.
+
+  python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl reference]
+
+A "step" is one Optimizer::optimize() (nav2_sortham_controller/src/optimizer.cpp:157-164) over one batch of
+synthetic input: iteration_count x {noised rollout, critics, softmax update}.  Protocol = the reference's own
+harness (benchmark/optimizer_benchmark.cpp:85-93): fixed robot pose, control sequence carried between cycles.
+
+workloads (BASELINE.json configs):
+  omni_1000x56        configs[0]/[1]: Omni 1000 x 56, dt 0.05, default critic set, 100x100 costmap, 40-point path,
+                      reference-style injected noise.  DEFAULT at N=1; at N>1 every rank runs its own robot of this
+                      shape (independent scenarios, no data-path collective: weak scaling, configs[4] style).
+  obstacles_16384x56  configs[2]: 16384 x 56, 400x400 costmap, ObstaclesCritic in footprint mode.
+  sharded_262144x100  configs[3]: 262144 x 100 sharded over the ranks, Philox noise by global trajectory index,
+                      NCCL exchanges of the furthest path point and of the softmax partials (strong scaling).
+  robots_256          configs[4]: 256 robots x (2000 x 56), 256/N per rank, launched as one batch per rank.
+
+value  = whole-job rollout-steps/s with inputs resident in HBM (mppi_upload_cycle once, then
+         mppi_optimize_resident per step), timed with CUDA events on the launching stream, max over ranks,
+         L2 flushed between timed steps.
+e2e    = the same metric through mppi_optimize() with HOST buffers: costmap + cycle record H2D and the control
+         sequence D2H inside the timed region (host wall clock per call).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from mpcholonavigation_b200 import Engine, scenarios  # noqa: E402
+
+METRIC = "rollout_steps_per_sec"
+UNIT = "rollout-steps/s"
+
+
+def algorithmic_bytes(B, T, N, cells, iterations=1):
+    """bytes(optimize) = iteration_count * (12 B T + 4 B) + cells + 24 T + 12 N"""
+    return iterations * (12 * B * T + 4 * B) + cells + 24 * T + 12 * N
+
+
+def pick_scenario(workload, rank, world):
+    if workload == "omni_1000x56":
+        sc = scenarios.config1() if world == 1 else scenarios.config5_robot(rank, batch=1000)
+        sc.name = "omni_1000x56"
+        return sc, "injected"
+    if workload == "obstacles_16384x56":
+        return scenarios.config3(), "injected"
+    if workload == "sharded_262144x100":
+        return scenarios.config4(), "philox"
+    raise SystemExit(f"unknown workload {workload}")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi's clocks line through NVML, sampled DURING the timed region."""
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.sm, self.reasons, self.sm_max = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = str(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.sm.append(int(self.nv.nvmlDeviceGetClockInfo(self.dev, self.nv.NVML_CLOCK_SM)))
+                mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev))
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
+
+
+def pct(a, q):
+    return float(np.percentile(np.asarray(a, np.float64), q))
+
+
+def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path, timed on this box's host cores.  The xtensor
+    reference cannot be built offline (no rclcpp / nav2_costmap_2d / xtensor): this is the oracle port built
+    with the reference's flags (oracle/Makefile, -O3 -mavx2 -mfma -ffast-math).  The reference is
+    single-threaded (XTENSOR_USE_TBB 0 / XTENSOR_USE_OPENMP 0, CMakeLists.txt:7-8), so cores = 1."""
+    if rank != 0:
+        return
+    from tests import oracle_loader
+    fns = oracle_loader.load(fast=True)
+    sc, noise_kind = pick_scenario(args.workload, 0, 1)
+    B, T = sc.cfg["batch_size"], sc.cfg["time_steps"]
+    e = Engine(fns, **sc.cfg)
+    e.set_robot(sc.robot)
+    e.set_critics(sc.critics)
+    if noise_kind == "injected":
+        e.set_noise(*sc.noise())
+    else:
+        e.generate_noise(0)
+    # bound the sample: a step of the big configs takes seconds on one core
+    est = B * T * 1.0e-7
+    steps = max(1, min(args.steps, int(60.0 / max(est, 1e-6))))
+    warm = max(1, min(args.warmup, 3))
+    for _ in range(warm):
+        e.optimize(sc.cycle)
+    lat = []
+    t_all = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        e.optimize(sc.cycle)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    wall = time.perf_counter() - t_all
+    iters = sc.cfg.get("iteration_count", 1)
+    value = B * T * iters * steps / wall
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": wall / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": sc.name, "batch_size": B, "time_steps": T, "critics": [c[0] for c in sc.critics],
+                   "noise": noise_kind},
+        "latency_ms": {"p50": pct(lat, 50), "p90": pct(lat, 90), "p99": pct(lat, 99)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{steps} optimize() calls of {sc.name} on 1 host thread, reference-flags build of the "
+                                   f"oracle port (xtensor reference not buildable offline); host has {os.cpu_count()} cpus"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(sc, noise_kind, budget_s=12.0):
+    from tests import oracle_loader
+    fns = oracle_loader.load(fast=True)
+    B, T = sc.cfg["batch_size"], sc.cfg["time_steps"]
+    e = Engine(fns, **sc.cfg)
+    e.set_robot(sc.robot)
+    e.set_critics(sc.critics)
+    if noise_kind == "injected":
+        e.set_noise(*sc.noise())
+    else:
+        e.generate_noise(0)
+    e.optimize(sc.cycle)
+    n, t0 = 0, time.perf_counter()
+    lat = []
+    while True:
+        t1 = time.perf_counter()
+        e.optimize(sc.cycle)
+        lat.append((time.perf_counter() - t1) * 1e3)
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 2000:
+            break
+    wall = time.perf_counter() - t0
+    return {"value": B * T * sc.cfg.get("iteration_count", 1) * n / wall, "unit": UNIT, "cores": 1, "kind": "port",
+            "p50_ms": pct(lat, 50),
+            "sample": f"{n} optimize() calls of {sc.name} in {wall:.1f} s on 1 host thread (reference is single-threaded); "
+                      f"oracle port, reference-flags build; host has {os.cpu_count()} cpus"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps (steady-state number)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload is None:
+        args.workload = "omni_1000x56"
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from mpcholonavigation_b200 import load_product
+    fns = load_product()
+    sharded = args.workload == "sharded_262144x100"
+    sc, noise_kind = pick_scenario(args.workload, rank, world)
+    cfg = dict(sc.cfg)
+    cfg["device"] = local_rank
+    B_total, T = cfg["batch_size"], cfg["time_steps"]
+    if sharded and world > 1:
+        assert B_total % world == 0
+        cfg["batch_size"] = B_total // world
+        cfg["shard_offset"] = rank * cfg["batch_size"]
+        cfg["shard_total"] = B_total
+    cfg["seed"] = 3
+    e = Engine(fns, **cfg)
+    e.set_robot(sc.robot)
+    e.set_critics(sc.critics)
+    if noise_kind == "injected":
+        e.set_noise(*sc.noise())
+    else:
+        e.generate_noise(0)
+    if sharded and world > 1:
+        import ctypes as C
+        from mpcholonavigation_b200 import abi
+        uid = torch.zeros(abi.NCCL_UNIQUE_ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_uint8 * abi.NCCL_UNIQUE_ID_BYTES)()
+            assert fns["comm_get_unique_id"](buf) == 0
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        e.comm_init(bytes(uid.cpu().tolist()), rank, world)
+
+    B_local = cfg["batch_size"]
+    iters = cfg.get("iteration_count", 1)
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def flush_l2():
+        if flush is not None:
+            flush.zero_()
+            torch.cuda.synchronize()
+
+    # ---- leg 1: device-resident inputs ---------------------------------------------------------
+    e.upload_cycle(sc.cycle)
+    for _ in range(args.warmup):
+        e.optimize_resident()
+    launches0 = e.get_profile()["kernel_launches"]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    dev_ms, wall_ms = [], []
+    t_region = time.perf_counter()
+    for _ in range(args.steps):
+        flush_l2()
+        t0 = time.perf_counter()
+        r = e.optimize_resident()
+        wall_ms.append((time.perf_counter() - t0) * 1e3)
+        dev_ms.append(r.device_ms)
+    barrier()
+    region_s = time.perf_counter() - t_region
+    launches = e.get_profile()["kernel_launches"] - launches0
+
+    # ---- leg 2: end to end through mppi_optimize() with host buffers ---------------------------
+    for _ in range(args.warmup):
+        e.optimize(sc.cycle)
+    barrier()
+    e2e_ms = []
+    for _ in range(args.steps):
+        flush_l2()
+        t0 = time.perf_counter()
+        e.optimize(sc.cycle)
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    barrier()
+    clocks = sampler.stop()
+    prof = e.get_profile()
+    h2d, d2h = prof["h2d_bytes"], prof["d2h_bytes"]
+
+    # ---- leg 3: per-kernel durations (profiling events on), same protocol -----------------------
+    e.set_profiling(True)
+    e.upload_cycle(sc.cycle)
+    k2, k3, xch = [], [], []
+    for i in range(min(args.steps, 300) + 3):
+        flush_l2()
+        e.optimize_resident()
+        p = e.get_profile()
+        if i >= 3:
+            k2.append(p["k2_ms"]); k3.append(p["k3_ms"]); xch.append(p["exchange_ms"])
+    e.set_profiling(False)
+
+    dev_total = float(np.sum(dev_ms))
+    e2e_total = float(np.sum(e2e_ms))
+    if world > 1:
+        t = torch.tensor([dev_total, e2e_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_total, e2e_total = float(t[0]), float(t[1])
+    units = B_total * T * iters * args.steps if sharded else B_local * T * iters * args.steps * world
+    value = units / (dev_total * 1e-3)
+    e2e_value = units / (e2e_total * 1e-3)
+
+    if rank == 0:
+        cells = int(sc.cycle.costmap.size)
+        N = len(sc.cycle.path_x)
+        alg = algorithmic_bytes(B_local, T, N, cells, iters)
+        k2_ms = float(np.mean(k2))
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst)"
+        else:
+            peak, peak_src = 6650.0, "fallback of B200_PROFILING.md"
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(sc.name)
+        achieved = alg / (k2_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_total / args.steps, "higher_is_better": True,
+            "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": sc.name, "batch_size": B_total, "time_steps": T, "iteration_count": iters,
+                       "critics": [c[0] for c in sc.critics], "costmap": list(sc.cycle.costmap.shape), "path_points": N,
+                       "noise": noise_kind, "per_rank_batch": B_local,
+                       "parallelism": ("sharded over ranks, 2 NCCL exchanges" if sharded and world > 1 else
+                                       ("independent robots, one per rank" if world > 1 else "single GPU")),
+                       "l2": "cold: 256 MiB written between timed steps" if flush is not None else "warm (no flush)"},
+            "clocks": clocks,
+            "latency_ms": {"device_p50": pct(dev_ms, 50), "device_p90": pct(dev_ms, 90), "device_p99": pct(dev_ms, 99),
+                           "resident_call_p50": pct(wall_ms, 50), "e2e_p50": pct(e2e_ms, 50), "e2e_p90": pct(e2e_ms, 90),
+                           "e2e_p99": pct(e2e_ms, 99)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "p50_ms": pct(e2e_ms, 50)},
+            "gpu_launches": int(launches),
+            "kernels_ms": {"K2_rollout_score": k2_ms, "K3_path_softmax_update": float(np.mean(k3)),
+                           "exchange_and_merge": float(np.mean(xch))},
+            "roofline": {"bound": "hbm", "kernel": "rollout_score_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                         "note": "small configs are L2-resident and latency-bound; the fraction is reported anyway"},
+            "timed_region_s": region_s,
+        }
+        if not args.no_cpu_baseline:
+            budget = 12.0 if B_total * T <= 2_000_000 else 25.0
+            line["cpu_baseline"] = cpu_baseline(pick_scenario(args.workload, 0, 1)[0], noise_kind, budget)
+        print(json.dumps(line), flush=True)
+    e.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

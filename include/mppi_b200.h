@@ -246,6 +246,15 @@ mppi_status mppi_score_trajectories(mppi_handle * h, const mppi_cycle_in * in,
                                     const float * x, const float * y, const float * yaw,
                                     float * costs_inout, uint32_t * furthest_inout, int32_t * fail_flag_out);
 
+/* ---- measurement hooks (bench.py: roofline of the dominant kernel, launch count) ---- */
+/* when enabled, CUDA events bracket each kernel of optimize() on the handle's stream (adds ~1 us per event) */
+mppi_status mppi_set_profiling(mppi_handle * h, int32_t enable);
+/* last optimize(), summed over iteration_count: ms_out[0] K2 rollout_score, [1] K3 path_softmax_update,
+ * [2] exchanges + K4 merge (sharded only), [3] whole device span incl. copies.  kernel_launches_total counts every
+ * kernel this handle has launched since create; h2d/d2h are the bytes copied by the last mppi_optimize(). */
+mppi_status mppi_get_profile(mppi_handle * h, float ms_out[4], uint64_t * kernel_launches_total,
+                             uint64_t * h2d_bytes, uint64_t * d2h_bytes);
+
 /* ---- sharding over GPUs: one handle per rank, tiny exchanges over NCCL ---- */
 #define MPPI_NCCL_UNIQUE_ID_BYTES 128
 mppi_status mppi_comm_get_unique_id(uint8_t id_out[MPPI_NCCL_UNIQUE_ID_BYTES]);

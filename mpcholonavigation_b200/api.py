@@ -264,6 +264,22 @@ class Engine:
         self._check(self.f["optimize_resident"](self.h, C.byref(out)))
         return self._result(out, arrs)
 
+    # -- measurement hooks ------------------------------------------------------------------
+    def set_profiling(self, enable=True):
+        self._check(self.f["set_profiling"](self.h, int(bool(enable))))
+
+    def get_profile(self):
+        ms = np.zeros(4, np.float32)
+        n, h2d, d2h = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self._check(self.f["get_profile"](self.h, _p(ms), C.byref(n), C.byref(h2d), C.byref(d2h)))
+        return dict(k2_ms=float(ms[0]), k3_ms=float(ms[1]), exchange_ms=float(ms[2]), span_ms=float(ms[3]),
+                    kernel_launches=n.value, h2d_bytes=h2d.value, d2h_bytes=d2h.value)
+
+    # -- sharding ---------------------------------------------------------------------------
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        buf = (C.c_uint8 * abi.NCCL_UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+        self._check(self.f["comm_init"](self.h, buf, rank, nranks))
+
     # -- introspection ----------------------------------------------------------------------
     def set_outputs(self, trajectories=False, cells=False, critic_costs=False):
         mask = (abi.WANT_TRAJECTORIES if trajectories else 0) | (abi.WANT_CELLS if cells else 0) | \

@@ -71,6 +71,11 @@ struct mppi_handle
   int device{0};
   cudaStream_t stream{nullptr};
   cudaEvent_t ev0{nullptr}, ev1{nullptr};
+  cudaEvent_t pev[4]{nullptr, nullptr, nullptr, nullptr};   // profiling: before K2, after K2, after K3, after exchange 2
+  bool profiling{false};
+  float prof_ms[4]{0.f, 0.f, 0.f, 0.f};
+  uint64_t launches{0};
+  uint64_t h2d_bytes{0}, d2h_bytes{0};
   // device
   float * d_noise[3]{nullptr, nullptr, nullptr};
   uint8_t * d_costmap{nullptr};
@@ -423,6 +428,7 @@ DevBuffers make_bufs(mppi_handle * h, int mode)
 mppi_status upload_params(mppi_handle * h)
 {
   CUDA_TRY(h, cudaMemcpyAsync(h->d_params, h->h_params, h->params_bytes, cudaMemcpyHostToDevice, h->stream));
+  h->h2d_bytes = h->params_bytes;
   return MPPI_OK;
 }
 
@@ -444,6 +450,7 @@ mppi_status upload_costmap(mppi_handle * h, const mppi_costmap & cm)
   // the caller's buffer is only valid during the call (it holds the costmap mutex): stage, then copy async
   std::memcpy(h->h_costmap, cm.cells, bytes);
   CUDA_TRY(h, cudaMemcpyAsync(h->d_costmap, h->h_costmap, bytes, cudaMemcpyHostToDevice, h->stream));
+  h->h2d_bytes += bytes;
   return MPPI_OK;
 }
 
@@ -456,6 +463,7 @@ mppi_status launch_rollout(mppi_handle * h, int mode)
   rollout_score_kernel<<<grid, block, smem, h->stream>>>(
     reinterpret_cast<const DevParams *>(h->d_params), h->d_costmap, make_bufs(h, mode));
   CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
   return MPPI_OK;
 }
 
@@ -466,6 +474,7 @@ mppi_status launch_update(mppi_handle * h, int mode, int iteration)
   path_softmax_update_kernel<<<h->upd_blocks, kUpdThreads, smem, h->stream>>>(
     reinterpret_cast<const DevParams *>(h->d_params), h->d_costmap, make_bufs(h, mode), h->nranks, iteration);
   CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
   return MPPI_OK;
 }
 
@@ -474,24 +483,31 @@ mppi_status enqueue_optimize(mppi_handle * h)
 {
   CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
   const int stride = 3 * h->T + 2;
+  const bool prof = h->profiling && h->cfg.iteration_count == 1;
   for (int it = 0; it < h->cfg.iteration_count; ++it) {
+    if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[0], h->stream));}
     mppi_status s = launch_rollout(h, 0);
     if (s != MPPI_OK) {return s;}
+    if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[1], h->stream));}
     if (h->nranks > 1) {
       // exchange 1: furthest path point candidate + "some trajectory survived" flags, one MAX all-reduce
       NCCL_TRY(h, g_nccl.AllReduce(h->d_st, h->d_st, 1 + kMaxCritics, ncclUint32, ncclMax, h->comm, h->stream));
     }
     s = launch_update(h, 0, it);
     if (s != MPPI_OK) {return s;}
+    if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[2], h->stream));}
     if (h->nranks > 1) {
       // exchange 2: per-rank (min, sum, weighted control sums); merged redundantly on every rank
       NCCL_TRY(h, g_nccl.AllGather(h->d_rank_partial, h->d_gathered, stride, ncclFloat32, h->comm, h->stream));
       merge_partials_kernel<<<1, kUpdThreads, 0, h->stream>>>(
         reinterpret_cast<const DevParams *>(h->d_params), h->d_gathered, h->nranks, stride, make_bufs(h, 0));
       CUDA_TRY(h, cudaGetLastError());
+      h->launches++;
     }
   }
+  if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[3], h->stream));}
   CUDA_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(float) * (3 * h->T + 2), cudaMemcpyDeviceToHost, h->stream));
+  h->d2h_bytes = sizeof(float) * (3 * h->T + 2);
   CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
   return MPPI_OK;
 }
@@ -516,6 +532,13 @@ mppi_status finish_optimize(mppi_handle * h, mppi_cycle_out * out)
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     out->device_ms = ms;
+  }
+  cudaEventElapsedTime(&h->prof_ms[3], h->ev0, h->ev1);
+  if (h->profiling && h->cfg.iteration_count == 1) {
+    cudaEventElapsedTime(&h->prof_ms[0], h->pev[0], h->pev[1]);
+    // with sharding the span pev[1]..pev[2] also holds exchange 1; K3 alone is not separable there
+    cudaEventElapsedTime(&h->prof_ms[1], h->pev[1], h->pev[2]);
+    cudaEventElapsedTime(&h->prof_ms[2], h->pev[2], h->pev[3]);
   }
   return MPPI_OK;
 }
@@ -562,6 +585,7 @@ mppi_status do_reset(mppi_handle * h)
     h->d_noise[0], h->d_noise[1], h->d_noise[2], h->B, h->T, h->cfg.vx_std, h->cfg.vy_std, h->cfg.wz_std,
     holonomic(h) ? 1 : 0, h->cfg.seed, h->noise_stream, static_cast<uint64_t>(h->cfg.shard_offset));
   CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
   h->noise_stream++;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->cycle_uploaded = false;
@@ -634,6 +658,7 @@ void mppi_destroy(mppi_handle * h)
   cudaFreeHost(h->h_params); cudaFreeHost(h->h_costmap); cudaFreeHost(h->h_out);
   if (h->ev0) {cudaEventDestroy(h->ev0);}
   if (h->ev1) {cudaEventDestroy(h->ev1);}
+  for (auto & e : h->pev) {if (e) {cudaEventDestroy(e);}}
   if (h->stream) {cudaStreamDestroy(h->stream);}
   delete h;
 }
@@ -669,6 +694,7 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CUDA_TRY(h, cudaEventCreate(&h->ev0));
   CUDA_TRY(h, cudaEventCreate(&h->ev1));
+  for (auto & e : h->pev) {CUDA_TRY(h, cudaEventCreate(&e));}
   const size_t B = h->B, T = h->T, plane = B * T * sizeof(float);
   for (int i = 0; i < 3; ++i) {
     CUDA_TRY(h, cudaMalloc(&h->d_noise[i], plane));
@@ -775,6 +801,7 @@ mppi_status mppi_generate_noise(mppi_handle * h, uint64_t stream)
     h->d_noise[0], h->d_noise[1], h->d_noise[2], h->B, h->T, h->cfg.vx_std, h->cfg.vy_std, h->cfg.wz_std,
     holonomic(h) ? 1 : 0, h->cfg.seed, stream, static_cast<uint64_t>(h->cfg.shard_offset));
   CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return MPPI_OK;
 }
@@ -1006,6 +1033,23 @@ mppi_status mppi_score_trajectories(
   std::memcpy(&fu, h->h_out + 3 * h->T + 1, 4);
   if (fail_flag_out) {*fail_flag_out = ff;}
   if (furthest_inout) {*furthest_inout = fu;}
+  return MPPI_OK;
+}
+
+mppi_status mppi_set_profiling(mppi_handle * h, int32_t enable)
+{
+  if (!h) {return MPPI_E_CONFIG;}
+  h->profiling = enable != 0;
+  return MPPI_OK;
+}
+
+mppi_status mppi_get_profile(mppi_handle * h, float ms_out[4], uint64_t * kernel_launches_total, uint64_t * h2d_bytes, uint64_t * d2h_bytes)
+{
+  if (!h) {return MPPI_E_CONFIG;}
+  if (ms_out) {for (int i = 0; i < 4; ++i) {ms_out[i] = h->prof_ms[i];}}
+  if (kernel_launches_total) {*kernel_launches_total = h->launches;}
+  if (h2d_bytes) {*h2d_bytes = h->h2d_bytes;}
+  if (d2h_bytes) {*d2h_bytes = h->d2h_bytes;}
   return MPPI_OK;
 }
 

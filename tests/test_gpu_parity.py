@@ -105,20 +105,50 @@ def test_other_motion_models(product_fns, oracle_fns, model):
     assert not rg.vy.any()
 
 
-def test_all_critics_and_iterations(product_fns, oracle_fns):
-    """all 12 critics in one list, iteration_count 2 (costs accumulate across iterations, quirk R20), power 2"""
+def _all_critics_scenario(iterations):
     sc = scenarios.config1(batch=256)
     sc.critics = sc.critics + [("ObstaclesCritic", dict(consider_footprint=1, cost_scaling_factor=3.0)),
                                ("PathAlignLegacyCritic", dict(offset_from_furthest=10)),
                                ("VelocityDeadbandCritic", dict(deadband_velocities=[0.05, 0.05, 0.05]))]
     sc.critics[0] = ("ConstraintCritic", dict(cost_power=2))
     sc.critics[5] = ("PathFollowCritic", dict(cost_power=2, offset_from_furthest=5))
-    sc.cfg["iteration_count"] = 2
+    sc.cfg["iteration_count"] = iterations
+    return sc
+
+
+def test_all_twelve_critics(product_fns, oracle_fns):
+    """all 12 critic plugins of critics.xml in one list, two of them with cost_power 2"""
+    sc = _all_critics_scenario(1)
     g, o = _pair(product_fns, oracle_fns, sc, sc.noise())
     for cycle in range(3):
         rg, ro = g.optimize(sc.cycle), o.optimize(sc.cycle)
         _compare_cycle(g, o, sc, rg, ro, f"cycle {cycle}")
         g.set_control_sequence(ro.vx, ro.vy, ro.wz)
+    for q in range(len(sc.critics)):
+        if sc.critics[q][0] not in ("GoalCritic", "GoalAngleCritic", "PathAngleCritic"):   # gated off in this scene
+            assert o.get_critic_costs(q).max() > 0.0, sc.critics[q][0]
+
+
+def test_iteration_count_two(product_fns, oracle_fns):
+    """iteration_count 2: costs accumulate across iterations (quirk R20) and the second rollout starts from the
+    first update.  That update differs in the last bits between the two sides (different reduction order over B),
+    so the second rollout is compared at tolerance level, not bit level."""
+    sc = _all_critics_scenario(2)
+    g, o = _pair(product_fns, oracle_fns, sc, sc.noise())
+    rg, ro = g.optimize(sc.cycle), o.optimize(sc.cycle)
+    for a, b in zip(g.get_trajectories(), o.get_trajectories()):
+        np.testing.assert_allclose(a, b, rtol=0, atol=2e-6)
+    assert np.count_nonzero(g.get_cells() != o.get_cells()) <= 2
+    cg, co = g.get_costs(), o.get_costs()
+    bad = ~np.isclose(cg, co, rtol=1e-3, atol=1e-4)
+    assert bad.sum() <= 2, bad.sum()
+    assert co.min() > 0 and (co > 1.5 * o.get_critic_costs(0)).all()
+    for a, b in ((rg.vx, ro.vx), (rg.vy, ro.vy), (rg.wz, ro.wz)):
+        np.testing.assert_allclose(a, b, rtol=1e-3, atol=1e-5)
+    # one iteration of the same scene gives different controls: the second iteration did run
+    sc1 = _all_critics_scenario(1)
+    g1, _ = _pair(product_fns, oracle_fns, sc1, sc1.noise())
+    assert not np.allclose(g1.optimize(sc1.cycle).vx, rg.vx, rtol=1e-3)
 
 
 def test_all_trajectories_collide_sets_fail_flag(product_fns, oracle_fns):
