@@ -109,6 +109,12 @@ struct mppi_handle
   DevParams last;   // host copy of the last uploaded record
   int segments_override{0};
   int upd_blocks{0};
+  // CUDA graphs of the steady-state cycle: [0] kernels + D2H (resident inputs), [1] H2D + kernels + D2H
+  cudaGraphExec_t gexec[2]{nullptr, nullptr};
+  size_t gkey_params[2]{0, 0}, gkey_costmap[2]{0, 0};
+  bool use_graph{true};
+  size_t costmap_bytes{0}, params_copy_bytes{0};
+  int upd_rows{kUpdThreads};   // trajectories per block of the update kernel
   // sharding
   ncclComm_t comm{nullptr};
   int rank{0}, nranks{1};
@@ -273,6 +279,12 @@ mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, un
   uint8_t * gate = reinterpret_cast<uint8_t *>(tail + 4 * N);
   std::memset(gate, 0, N);
   h->params_bytes = sizeof(DevParams) + sizeof(float) * 4 * N + ((N + 15) / 16) * 16;
+  // copy size rounded up to 64 path points so that the captured graph survives small changes of the pruned path
+  {
+    const size_t n64 = std::min<size_t>(MPPI_MAX_PATH_POINTS, ((static_cast<size_t>(N) + 63) / 64) * 64);
+    h->params_copy_bytes = std::min(kParamsCapacity, sizeof(DevParams) + 17 * n64 + 64);
+    h->params_copy_bytes = std::max(h->params_copy_bytes, h->params_bytes);
+  }
 
   p.n_critics = critics_active ? static_cast<int>(h->critics.size()) : 0;
   for (int i = 0; i < kMaxCritics; ++i) {p.kind_of[i] = i < p.n_critics ? h->critics[i].kind : -1;}
@@ -425,21 +437,24 @@ DevBuffers make_bufs(mppi_handle * h, int mode)
   return b;
 }
 
-mppi_status upload_params(mppi_handle * h)
+void drop_graphs(mppi_handle * h)
 {
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_params, h->h_params, h->params_bytes, cudaMemcpyHostToDevice, h->stream));
-  h->h2d_bytes = h->params_bytes;
-  return MPPI_OK;
+  for (auto & g : h->gexec) {
+    if (g) {cudaGraphExecDestroy(g); g = nullptr;}
+  }
 }
 
-mppi_status upload_costmap(mppi_handle * h, const mppi_costmap & cm)
+// validate + stage the costmap into pinned memory (the caller's buffer is only valid during the call: it holds
+// the costmap mutex, controller.cpp:99-100); the async H2D copy itself is issued by enqueue_uploads
+mppi_status stage_costmap(mppi_handle * h, const mppi_costmap & cm)
 {
   const size_t bytes = static_cast<size_t>(cm.size_x) * cm.size_y;
   if (bytes == 0 || !cm.cells) {return fail(h, MPPI_E_CONFIG, "empty costmap");}
   if (!(cm.resolution > 0.0)) {return fail(h, MPPI_E_CONFIG, "costmap resolution must be > 0");}
   if (bytes > h->costmap_capacity) {
-    // grow (outside the steady state: costmap size only changes on reconfiguration)
+    // grow (outside the steady state: the costmap size only changes on reconfiguration)
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    drop_graphs(h);
     if (h->d_costmap) {cudaFree(h->d_costmap);}
     if (h->h_costmap) {cudaFreeHost(h->h_costmap);}
     h->d_costmap = nullptr; h->h_costmap = nullptr; h->costmap_capacity = 0;
@@ -447,10 +462,15 @@ mppi_status upload_costmap(mppi_handle * h, const mppi_costmap & cm)
     CUDA_TRY(h, cudaMallocHost(&h->h_costmap, bytes));
     h->costmap_capacity = bytes;
   }
-  // the caller's buffer is only valid during the call (it holds the costmap mutex): stage, then copy async
   std::memcpy(h->h_costmap, cm.cells, bytes);
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_costmap, h->h_costmap, bytes, cudaMemcpyHostToDevice, h->stream));
-  h->h2d_bytes += bytes;
+  h->costmap_bytes = bytes;
+  return MPPI_OK;
+}
+
+mppi_status enqueue_uploads(mppi_handle * h)
+{
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_params, h->h_params, h->params_copy_bytes, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_costmap, h->h_costmap, h->costmap_bytes, cudaMemcpyHostToDevice, h->stream));
   return MPPI_OK;
 }
 
@@ -469,21 +489,18 @@ mppi_status launch_rollout(mppi_handle * h, int mode)
 
 mppi_status launch_update(mppi_handle * h, int mode, int iteration)
 {
-  const int N = h->last.N;
-  const size_t smem = sizeof(float) * (N + kUpdThreads + 32) + N + 16;
+  const size_t smem = sizeof(float) * (MPPI_MAX_PATH_POINTS + kUpdThreads + 32) + MPPI_MAX_PATH_POINTS + 16;
   path_softmax_update_kernel<<<h->upd_blocks, kUpdThreads, smem, h->stream>>>(
-    reinterpret_cast<const DevParams *>(h->d_params), h->d_costmap, make_bufs(h, mode), h->nranks, iteration);
+    reinterpret_cast<const DevParams *>(h->d_params), h->d_costmap, make_bufs(h, mode), h->nranks, iteration, h->upd_rows);
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   return MPPI_OK;
 }
 
 // device part of optimize(): iteration_count x {K2, [exchange 1], K3, [exchange 2, K4]} + D2H of the result, no sync
-mppi_status enqueue_optimize(mppi_handle * h)
+mppi_status enqueue_kernels(mppi_handle * h, bool prof)
 {
-  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
   const int stride = 3 * h->T + 2;
-  const bool prof = h->profiling && h->cfg.iteration_count == 1;
   for (int it = 0; it < h->cfg.iteration_count; ++it) {
     if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[0], h->stream));}
     mppi_status s = launch_rollout(h, 0);
@@ -507,7 +524,56 @@ mppi_status enqueue_optimize(mppi_handle * h)
   }
   if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[3], h->stream));}
   CUDA_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(float) * (3 * h->T + 2), cudaMemcpyDeviceToHost, h->stream));
+  return MPPI_OK;
+}
+
+// One cycle on the handle's stream: [uploads], kernels, result copy; bracketed by ev0 / ev1.  The steady state
+// (single rank, no per-kernel profiling) replays a captured CUDA graph: one launch instead of five.
+mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
+{
+  const bool prof = h->profiling && h->cfg.iteration_count == 1;
+  const bool graph_ok = h->use_graph && !prof && h->nranks == 1;
   h->d2h_bytes = sizeof(float) * (3 * h->T + 2);
+  h->h2d_bytes = with_upload ? h->params_copy_bytes + h->costmap_bytes : 0;
+  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+  if (graph_ok) {
+    const int slot = with_upload ? 1 : 0;
+    if (h->gexec[slot] && (h->gkey_params[slot] != h->params_copy_bytes || h->gkey_costmap[slot] != h->costmap_bytes)) {
+      cudaGraphExecDestroy(h->gexec[slot]);
+      h->gexec[slot] = nullptr;
+    }
+    if (!h->gexec[slot]) {
+      cudaGraph_t graph = nullptr;
+      const uint64_t launches_before = h->launches;
+      CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      mppi_status s = MPPI_OK;
+      if (with_upload) {s = enqueue_uploads(h);}
+      if (s == MPPI_OK) {s = enqueue_kernels(h, false);}
+      const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+      h->launches = launches_before;   // capture launched nothing
+      if (s != MPPI_OK || ce != cudaSuccess || !graph) {
+        if (graph) {cudaGraphDestroy(graph);}
+        cudaGetLastError();
+        h->use_graph = false;            // fall back to plain stream launches for this handle
+      } else {
+        const cudaError_t ie = cudaGraphInstantiate(&h->gexec[slot], graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) {cudaGetLastError(); h->gexec[slot] = nullptr; h->use_graph = false;}
+        h->gkey_params[slot] = h->params_copy_bytes;
+        h->gkey_costmap[slot] = h->costmap_bytes;
+      }
+    }
+    if (h->gexec[slot]) {
+      CUDA_TRY(h, cudaGraphLaunch(h->gexec[slot], h->stream));
+      h->launches += 2ull * h->cfg.iteration_count;
+      CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+      return MPPI_OK;
+    }
+  }
+  mppi_status s = MPPI_OK;
+  if (with_upload) {s = enqueue_uploads(h);}
+  if (s != MPPI_OK) {return s;}
+  if ((s = enqueue_kernels(h, prof)) != MPPI_OK) {return s;}
   CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
   return MPPI_OK;
 }
@@ -647,6 +713,7 @@ void mppi_destroy(mppi_handle * h)
   if (!h) {return;}
   cudaSetDevice(h->device);
   if (h->stream) {cudaStreamSynchronize(h->stream);}
+  drop_graphs(h);
   if (h->comm && g_nccl.CommDestroy) {g_nccl.CommDestroy(h->comm);}
   for (float * p : h->d_noise) {cudaFree(p);}
   for (float * p : h->d_samples) {cudaFree(p);}
@@ -684,6 +751,7 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   h->cur = h->base;
   std::memset(&h->robot, 0, sizeof(h->robot));
   if (const char * e = std::getenv("MPPI_SEGMENTS")) {h->segments_override = std::atoi(e);}
+  if (const char * e = std::getenv("MPPI_NO_GRAPH")) {h->use_graph = std::atoi(e) == 0;}
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
     h->err = "no CUDA device: this library has no CPU fallback";
@@ -709,7 +777,9 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   CUDA_TRY(h, cudaMemsetAsync(h->d_crit_rows, 0, (kMaxCritics + kGammaRows) * B * sizeof(float), h->stream));
   CUDA_TRY(h, cudaMalloc(&h->d_end_xy, 2 * B * sizeof(float)));
   CUDA_TRY(h, cudaMalloc(&h->d_costs, B * sizeof(float)));
-  h->upd_blocks = static_cast<int>((B + kUpdThreads - 1) / kUpdThreads);
+  h->upd_rows = B <= 16384 ? 32 : kUpdThreads;
+  if (const char * e = std::getenv("MPPI_UPDATE_ROWS")) {h->upd_rows = std::max(32, std::min(kUpdThreads, (std::atoi(e) / 32) * 32));}
+  h->upd_blocks = static_cast<int>((B + h->upd_rows - 1) / h->upd_rows);
   const size_t stride = 3 * T + 2;
   CUDA_TRY(h, cudaMalloc(&h->d_partials, h->upd_blocks * stride * sizeof(float)));
   CUDA_TRY(h, cudaMalloc(&h->d_rank_partial, stride * sizeof(float)));
@@ -866,8 +936,9 @@ mppi_status mppi_upload_cycle(mppi_handle * h, const mppi_cycle_in * in)
   CUDA_TRY(h, cudaSetDevice(h->device));
   mppi_status s = build_params(h, in, 0, kUnset, true);
   if (s != MPPI_OK) {return s;}
-  if ((s = upload_params(h)) != MPPI_OK) {return s;}
-  if ((s = upload_costmap(h, in->costmap)) != MPPI_OK) {return s;}
+  if ((s = stage_costmap(h, in->costmap)) != MPPI_OK) {return s;}
+  if ((s = enqueue_uploads(h)) != MPPI_OK) {return s;}
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->cycle_uploaded = true;
   return MPPI_OK;
 }
@@ -877,16 +948,29 @@ mppi_status mppi_optimize_resident(mppi_handle * h, mppi_cycle_out * out)
   if (!h) {return MPPI_E_CONFIG;}
   if (!h->cycle_uploaded) {return fail(h, MPPI_E_STATE, "mppi_optimize_resident before mppi_upload_cycle");}
   CUDA_TRY(h, cudaSetDevice(h->device));
-  mppi_status s = enqueue_optimize(h);
+  mppi_status s = enqueue_optimize(h, false);
   if (s != MPPI_OK) {return s;}
   return finish_optimize(h, out);
 }
 
+// prepare() + optimize(): pack the cycle record, stage the costmap, then ONE graph launch does
+// H2D(record) + H2D(costmap) + K2 + K3 + D2H(result); the call returns after the result is in host memory
+static mppi_status optimize_begin(mppi_handle * h, const mppi_cycle_in * in)
+{
+  if (!h || !in) {return MPPI_E_CONFIG;}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  mppi_status s = build_params(h, in, 0, kUnset, true);
+  if (s != MPPI_OK) {return s;}
+  if ((s = stage_costmap(h, in->costmap)) != MPPI_OK) {return s;}
+  h->cycle_uploaded = true;
+  return enqueue_optimize(h, true);
+}
+
 mppi_status mppi_optimize(mppi_handle * h, const mppi_cycle_in * in, mppi_cycle_out * out)
 {
-  mppi_status s = mppi_upload_cycle(h, in);
+  mppi_status s = optimize_begin(h, in);
   if (s != MPPI_OK) {return s;}
-  return mppi_optimize_resident(h, out);
+  return finish_optimize(h, out);
 }
 
 mppi_status mppi_optimize_batch(mppi_handle ** hs, const mppi_cycle_in * ins, mppi_cycle_out * outs, int32_t n)
@@ -895,8 +979,7 @@ mppi_status mppi_optimize_batch(mppi_handle ** hs, const mppi_cycle_in * ins, mp
   mppi_status first = MPPI_OK;
   std::vector<char> launched(n, 0);
   for (int i = 0; i < n; ++i) {
-    mppi_status s = mppi_upload_cycle(hs[i], &ins[i]);
-    if (s == MPPI_OK) {s = enqueue_optimize(hs[i]);}
+    const mppi_status s = optimize_begin(hs[i], &ins[i]);
     launched[i] = s == MPPI_OK;
     if (s != MPPI_OK && first == MPPI_OK) {first = s;}
   }
@@ -988,8 +1071,8 @@ mppi_status mppi_integrate_state_velocities(
   s = build_params(h, &in, 1, kUnset, false);
   h->want_mask = keep_mask;
   if (s != MPPI_OK) {return s;}
-  if ((s = upload_params(h)) != MPPI_OK) {return s;}
-  if ((s = upload_costmap(h, in.costmap)) != MPPI_OK) {return s;}
+  if ((s = stage_costmap(h, in.costmap)) != MPPI_OK) {return s;}
+  if ((s = enqueue_uploads(h)) != MPPI_OK) {return s;}
   h->cycle_uploaded = false;
   if ((s = launch_rollout(h, 1)) != MPPI_OK) {return s;}
   // K2 raised nothing persistent except the exchange-1 words; clear them for the next optimize
@@ -1016,8 +1099,8 @@ mppi_status mppi_score_trajectories(
   const unsigned preset = furthest_inout ? *furthest_inout : kUnset;
   s = build_params(h, in, 2, preset, true);
   if (s != MPPI_OK) {return s;}
-  if ((s = upload_params(h)) != MPPI_OK) {return s;}
-  if ((s = upload_costmap(h, in->costmap)) != MPPI_OK) {return s;}
+  if ((s = stage_costmap(h, in->costmap)) != MPPI_OK) {return s;}
+  if ((s = enqueue_uploads(h)) != MPPI_OK) {return s;}
   h->cycle_uploaded = false;
   if ((s = launch_rollout(h, 2)) != MPPI_OK) {return s;}
   if ((s = launch_update(h, 2, 0)) != MPPI_OK) {return s;}

@@ -557,8 +557,10 @@ __device__ __forceinline__ void merge_partials(
 }
 
 __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
-  const DevParams * __restrict__ P, const uint8_t * __restrict__ cm, DevBuffers bufs, int n_ranks, int iteration)
+  const DevParams * __restrict__ P, const uint8_t * __restrict__ cm, DevBuffers bufs, int n_ranks, int iteration, int R)
 {
+  // R = trajectories owned by this block (multiple of 32, <= kUpdThreads): small batches use small R so that
+  // the update spreads over many SMs; the column sums always use all kUpdThreads threads
   extern __shared__ float smem[];
   const int T = P->T, B = P->B, N = P->N, nc = P->n_critics;
   const int tid = threadIdx.x;
@@ -689,8 +691,8 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
   __syncthreads();
 
   // ---- phase 1: one thread per trajectory: path critics + total in list order
-  const int b = blockIdx.x * kUpdThreads + tid;
-  const bool live = b < B;
+  const int b = blockIdx.x * R + tid;
+  const bool live = tid < R && b < B;
   const int fail_at = sc_fail_at;
   const int furthest = sc_furthest;
   float total = 3.402823466e+38f;
@@ -882,22 +884,25 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
   // ---- phase 3: weighted column sums over this block's rows, W[c][t] = sum_b w_b * (cs[t] + noise[b,t])
   const int stride = 3 * T + 2;
   float * part = bufs.partials + static_cast<size_t>(blockIdx.x) * stride;
-  const int rows_here = min(kUpdThreads, B - blockIdx.x * kUpdThreads);
-  const size_t row0 = static_cast<size_t>(blockIdx.x) * kUpdThreads * T;
+  const int rows_here = min(R, B - blockIdx.x * R);
+  const size_t row0 = static_cast<size_t>(blockIdx.x) * R * T;
   for (int c = tid; c < 3 * T; c += kUpdThreads) {
     const int plane = c / T, t = c - plane * T;
     const float * __restrict__ src = (plane == 0 ? bufs.in_a : (plane == 1 ? bufs.in_b : bufs.in_c)) + row0 + t;
     const float cs_t = bufs.cs[c];
-    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    float a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {a[u] = 0.0f;}
     int r = 0;
-    for (; r + 3 < rows_here; r += 4) {
-      a0 = fmaf(s_w[r], __fadd_rn(cs_t, __ldg(src + static_cast<size_t>(r) * T)), a0);
-      a1 = fmaf(s_w[r + 1], __fadd_rn(cs_t, __ldg(src + static_cast<size_t>(r + 1) * T)), a1);
-      a2 = fmaf(s_w[r + 2], __fadd_rn(cs_t, __ldg(src + static_cast<size_t>(r + 2) * T)), a2);
-      a3 = fmaf(s_w[r + 3], __fadd_rn(cs_t, __ldg(src + static_cast<size_t>(r + 3) * T)), a3);
+    for (; r + 7 < rows_here; r += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {v[u] = __ldg(src + static_cast<size_t>(r + u) * T);}
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {a[u] = fmaf(s_w[r + u], __fadd_rn(cs_t, v[u]), a[u]);}
     }
-    for (; r < rows_here; ++r) {a0 = fmaf(s_w[r], __fadd_rn(cs_t, __ldg(src + static_cast<size_t>(r) * T)), a0);}
-    part[2 + c] = (a0 + a1) + (a2 + a3);
+    for (; r < rows_here; ++r) {a[0] = fmaf(s_w[r], __fadd_rn(cs_t, __ldg(src + static_cast<size_t>(r) * T)), a[0]);}
+    part[2 + c] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   }
   if (tid == 0) {part[0] = m; part[1] = ssum;}
 
