@@ -25,7 +25,7 @@ class MppiError(RuntimeError):
 def load_product(path: Optional[str] = None):
     """dlopen libmppi_b200.so and bind every symbol of the header.  Fails loudly if it is missing:
     there is no Python/CPU fallback for the hot path."""
-    path = path or PRODUCT_LIB
+    path = path or os.environ.get("MPPI_B200_LIB") or PRODUCT_LIB
     if not os.path.exists(path):
         raise MppiError(
             f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -261,6 +261,7 @@ mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, un
   p.goal_yaw = in->path_yaw[N - 1];
   p.size_x = in->costmap.size_x; p.size_y = in->costmap.size_y;
   p.res = in->costmap.resolution; p.ox = in->costmap.origin_x; p.oy = in->costmap.origin_y;
+  p.inv_res = 1.0 / p.res;
 
   // path arrays behind the struct: x, y, yaw, arc-length prefix D (path_align_critic.cpp:83-90), PathAngle gate bytes
   float * tail = reinterpret_cast<float *>(h->h_params + sizeof(DevParams));
@@ -404,6 +405,7 @@ mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, un
     }
   }
   p.spill_traj = ((h->want_mask & MPPI_WANT_TRAJECTORIES) || any_gate_open || mode == 1) ? 1 : 0;
+  p.need_furthest = (p.follow.idx >= 0 || p.angle.idx >= 0 || p.align.idx >= 0 || p.legacy.idx >= 0) ? 1 : 0;
   h->last = p;
   return MPPI_OK;
 }
@@ -477,7 +479,7 @@ mppi_status enqueue_uploads(mppi_handle * h)
 mppi_status launch_rollout(mppi_handle * h, int mode)
 {
   const int S = pick_segments(h);
-  const size_t smem = rollout_smem_bytes(h->T, S);
+  const size_t smem = rollout_smem_bytes(h->T, S, mode);
   if (smem > 227 * 1024) {return fail(h, MPPI_E_CONFIG, "time_steps too large for the shared-memory tile");}
   const dim3 grid((h->B + kTile - 1) / kTile), block(kTile, S);
   rollout_score_kernel<<<grid, block, smem, h->stream>>>(
@@ -489,7 +491,7 @@ mppi_status launch_rollout(mppi_handle * h, int mode)
 
 mppi_status launch_update(mppi_handle * h, int mode, int iteration)
 {
-  const size_t smem = sizeof(float) * (MPPI_MAX_PATH_POINTS + kUpdThreads + 32) + MPPI_MAX_PATH_POINTS + 16;
+  const size_t smem = kHotBytes + sizeof(float) * (MPPI_MAX_PATH_POINTS + kUpdThreads + 32) + MPPI_MAX_PATH_POINTS + 16;
   path_softmax_update_kernel<<<h->upd_blocks, kUpdThreads, smem, h->stream>>>(
     reinterpret_cast<const DevParams *>(h->d_params), h->d_costmap, make_bufs(h, mode), h->nranks, iteration, h->upd_rows);
   CUDA_TRY(h, cudaGetLastError());
@@ -512,12 +514,22 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
     }
     s = launch_update(h, 0, it);
     if (s != MPPI_OK) {return s;}
+    const bool many = h->upd_blocks > kLastBlockMergeMax;
+    const int merge_grid = (h->T + kMergeT - 1) / kMergeT;
+    if (many) {
+      // too many block partials for a serial merge in K3's last block: merge them in parallel
+      merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
+        reinterpret_cast<const DevParams *>(h->d_params), h->d_partials, h->upd_blocks, stride, make_bufs(h, 0),
+        h->nranks > 1 ? 0 : 1, h->d_rank_partial);
+      CUDA_TRY(h, cudaGetLastError());
+      h->launches++;
+    }
     if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[2], h->stream));}
     if (h->nranks > 1) {
       // exchange 2: per-rank (min, sum, weighted control sums); merged redundantly on every rank
       NCCL_TRY(h, g_nccl.AllGather(h->d_rank_partial, h->d_gathered, stride, ncclFloat32, h->comm, h->stream));
-      merge_partials_kernel<<<1, kUpdThreads, 0, h->stream>>>(
-        reinterpret_cast<const DevParams *>(h->d_params), h->d_gathered, h->nranks, stride, make_bufs(h, 0));
+      merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
+        reinterpret_cast<const DevParams *>(h->d_params), h->d_gathered, h->nranks, stride, make_bufs(h, 0), 1, nullptr);
       CUDA_TRY(h, cudaGetLastError());
       h->launches++;
     }
@@ -565,7 +577,7 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
     }
     if (h->gexec[slot]) {
       CUDA_TRY(h, cudaGraphLaunch(h->gexec[slot], h->stream));
-      h->launches += 2ull * h->cfg.iteration_count;
+      h->launches += (h->upd_blocks > kLastBlockMergeMax ? 3ull : 2ull) * h->cfg.iteration_count;
       CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
       return MPPI_OK;
     }
@@ -777,7 +789,7 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   CUDA_TRY(h, cudaMemsetAsync(h->d_crit_rows, 0, (kMaxCritics + kGammaRows) * B * sizeof(float), h->stream));
   CUDA_TRY(h, cudaMalloc(&h->d_end_xy, 2 * B * sizeof(float)));
   CUDA_TRY(h, cudaMalloc(&h->d_costs, B * sizeof(float)));
-  h->upd_rows = B <= 16384 ? 32 : kUpdThreads;
+  h->upd_rows = B <= 32 * kLastBlockMergeMax ? 32 : kUpdThreads;
   if (const char * e = std::getenv("MPPI_UPDATE_ROWS")) {h->upd_rows = std::max(32, std::min(kUpdThreads, (std::atoi(e) / 32) * 32));}
   h->upd_blocks = static_cast<int>((B + h->upd_rows - 1) / h->upd_rows);
   const size_t stride = 3 * T + 2;
@@ -872,6 +884,7 @@ mppi_status mppi_generate_noise(mppi_handle * h, uint64_t stream)
     holonomic(h) ? 1 : 0, h->cfg.seed, stream, static_cast<uint64_t>(h->cfg.shard_offset));
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
+  h->noise_stream = stream + 1;   // a later reset() draws the next stream
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return MPPI_OK;
 }

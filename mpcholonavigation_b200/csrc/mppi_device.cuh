@@ -13,6 +13,7 @@
 //   partials         float [blocks][3T+2]      online-softmax partials merged by the last block
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/mppi_b200.h"
@@ -79,16 +80,27 @@ struct DevParams
   int sample_step, n_samples, sample_yaw;    // PathAlign samples: p = 0, step, 2 step ... < T
   int spill_traj;                            // write x,y,yaw time-major (PathAngle may fire / requested)
   int want_cells;
-  int want_legacy_traj;                      // PathAlignLegacy needs all sampled poses too (uses samples)
-  // footprint
+  int need_furthest;                         // some path critic may ask for the furthest reached path point
+  // offsets (in floats) of the path arrays that follow this struct in the same buffer
+  int off_path_x, off_path_y, off_path_yaw, off_path_D, off_gate;
   int fp_n;
-  double fp_x[MPPI_MAX_FOOTPRINT], fp_y[MPPI_MAX_FOOTPRINT];
+  double inv_res;                            // 1 / res, used only by the exactness-checked fast path of world_to_cell
+  // ---- everything above is the "hot" part every CTA copies into shared memory (kHotBytes) ----
+  double fp_x[MPPI_MAX_FOOTPRINT], fp_y[MPPI_MAX_FOOTPRINT];   // footprint polygon
   // obstacle-critic look-up tables indexed by the byte cost: [0] point cost, [1] footprint cost
   float obst_lut_crit[2][256];               // (d < margin) ? margin - d : 0
   float obst_lut_rep[2][256];                // (d < margin) ? 0 : inflation_radius - d
-  // offsets (in floats) of the path arrays that follow this struct in the same buffer
-  int off_path_x, off_path_y, off_path_yaw, off_path_D, off_gate;
 };
+constexpr int kHotBytes = (static_cast<int>(offsetof(DevParams, fp_x)) + 15) & ~15;
+constexpr int kHotFloats = kHotBytes / 4;
+
+// cooperative copy of the hot part of the record into shared memory (16-byte vectors, coalesced)
+__device__ __forceinline__ void load_hot_params(float * s_hot, const DevParams * __restrict__ P, int tid, int nthreads)
+{
+  const float4 * src = reinterpret_cast<const float4 *>(P);
+  float4 * dst = reinterpret_cast<float4 *>(s_hot);
+  for (int i = tid; i < kHotBytes / 16; i += nthreads) {dst[i] = __ldg(src + i);}
+}
 
 // Persistent per-optimize state shared between kernels (device memory, 1 record per handle).
 struct DevState
@@ -118,6 +130,38 @@ __device__ __forceinline__ int world_to_cell(
   return static_cast<int>(my * size_x + mx);
 }
 
+// One coordinate of worldToMap with the IEEE division replaced by a multiplication where that is provably
+// harmless: q' = d * (1/res) is within a few ulp of the correctly rounded quotient q = d / res, so
+// trunc(q') == trunc(q) unless q' sits within `eps` of an integer; only then the true division is evaluated.
+// The result (cell index or off-map) is therefore identical to the reference arithmetic, bit for bit.
+__device__ __forceinline__ bool axis_cell_exact(double d, double res, double inv_res, unsigned size, unsigned & m)
+{
+  // d >= 0 is guaranteed by the caller (wx >= ox)
+  double q = __dmul_rn(d, inv_res);
+  if (!(q < 2147483000.0)) {return false;}                 // far off-map (also catches NaN)
+  int qi = __double2int_rz(q);
+  const double frac = q - static_cast<double>(qi);
+  const double eps = __dmul_rn(q, 1.0e-14) + 1.0e-300;     // >> 4 ulp(q), << cell size
+  if (frac < eps || frac > 1.0 - eps) {
+    q = __ddiv_rn(d, res);                                 // rare: decide with the reference's own division
+    if (!(q < static_cast<double>(size))) {return false;}
+    qi = __double2int_rz(q);
+  }
+  m = static_cast<unsigned>(qi);
+  return m < size;
+}
+
+__device__ __forceinline__ int world_to_cell_fast(
+  float xf, float yf, double ox, double oy, double res, double inv_res, unsigned size_x, unsigned size_y)
+{
+  const double wx = xf, wy = yf;
+  if (wx < ox || wy < oy) {return -1;}
+  unsigned mx, my;
+  if (!axis_cell_exact(wx - ox, res, inv_res, size_x, mx)) {return -1;}
+  if (!axis_cell_exact(wy - oy, res, inv_res, size_y, my)) {return -1;}
+  return static_cast<int>(my * size_x + mx);
+}
+
 // FootprintCollisionChecker::lineCost over nav2_util::LineIterator (integer Bresenham, both ends included)
 __device__ __forceinline__ int line_cost(const uint8_t * __restrict__ cm, unsigned size_x, int x0, int y0, int x1, int y1)
 {
@@ -144,34 +188,35 @@ __device__ __forceinline__ int line_cost(const uint8_t * __restrict__ cm, unsign
   return cost;
 }
 
-// FootprintCollisionChecker::footprintCostAtPose + footprintCost
+// FootprintCollisionChecker::footprintCostAtPose + footprintCost.  P is the record in GLOBAL memory (the polygon
+// is not part of the hot copy); the scalars come from the caller's registers.
 __device__ __noinline__ int footprint_cost_at_pose(
-  const DevParams * __restrict__ p, const uint8_t * __restrict__ cm, float xf, float yf, float thf)
+  const DevParams * __restrict__ P, int n, double ox, double oy, double res, unsigned size_x, unsigned size_y,
+  const uint8_t * __restrict__ cm, float xf, float yf, float thf)
 {
   const double x = xf, y = yf, th = thf;
   double sin_th, cos_th;
   sincos(th, &sin_th, &cos_th);
-  const int n = p->fp_n;
   unsigned x0, y0, x1, y1;
   {
-    const double fx = p->fp_x[0], fy = p->fp_y[0];
+    const double fx = __ldg(&P->fp_x[0]), fy = __ldg(&P->fp_y[0]);
     const double wx = x + (__dmul_rn(fx, cos_th) - __dmul_rn(fy, sin_th));
     const double wy = y + (__dmul_rn(fx, sin_th) + __dmul_rn(fy, cos_th));
-    if (world_to_cell(wx, wy, p->ox, p->oy, p->res, p->size_x, p->size_y, x0, y0) < 0) {return LETHAL_OBSTACLE;}
+    if (world_to_cell(wx, wy, ox, oy, res, size_x, size_y, x0, y0) < 0) {return LETHAL_OBSTACLE;}
   }
   const unsigned xstart = x0, ystart = y0;
   x1 = x0; y1 = y0;
   int footprint_cost = 0;
   for (int i = 0; i + 1 < n; ++i) {
-    const double fx = p->fp_x[i + 1], fy = p->fp_y[i + 1];
+    const double fx = __ldg(&P->fp_x[i + 1]), fy = __ldg(&P->fp_y[i + 1]);
     const double wx = x + (__dmul_rn(fx, cos_th) - __dmul_rn(fy, sin_th));
     const double wy = y + (__dmul_rn(fx, sin_th) + __dmul_rn(fy, cos_th));
-    if (world_to_cell(wx, wy, p->ox, p->oy, p->res, p->size_x, p->size_y, x1, y1) < 0) {return LETHAL_OBSTACLE;}
-    footprint_cost = max(line_cost(cm, p->size_x, x0, y0, x1, y1), footprint_cost);
+    if (world_to_cell(wx, wy, ox, oy, res, size_x, size_y, x1, y1) < 0) {return LETHAL_OBSTACLE;}
+    footprint_cost = max(line_cost(cm, size_x, x0, y0, x1, y1), footprint_cost);
     x0 = x1; y0 = y1;
     if (footprint_cost == LETHAL_OBSTACLE) {return footprint_cost;}
   }
-  return max(line_cost(cm, p->size_x, xstart, ystart, x1, y1), footprint_cost);
+  return max(line_cost(cm, size_x, xstart, ystart, x1, y1), footprint_cost);
 }
 
 // CostCritic::inCollision / ObstaclesCritic::inCollision on a byte cost

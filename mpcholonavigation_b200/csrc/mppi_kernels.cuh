@@ -10,7 +10,7 @@
 //                                  order with the fail_flag short-circuit, gamma term, softmax weights and the
 //                                  weighted control update, clip  (critic_manager.cpp:67-76, path_*_critic.cpp,
 //                                  optimizer.cpp:362-394,237-249)
-//  K4 merge_partials_kernel        cross-rank merge of the softmax partials (sharded configurations)
+//  K4 merge_finalize_kernel        parallel merge of the softmax partials (large batches; cross-rank when sharded)
 //
 // Work shape of K2: one CTA owns a tile of 32 trajectories (lane == trajectory) and S warps split the
 // horizon into S contiguous segments.  The tile lives in shared memory time-major, [T][33] floats per
@@ -57,11 +57,14 @@ enum Acc
   A_OB_HIT, A_COUNT
 };
 
-__host__ __device__ inline size_t rollout_smem_bytes(int T, int S)
+// shared memory of K2: hot params + control sequence + initial velocities + tile planes + partials + argmin scratch.
+// Rollout modes keep 4 planes (x and y are built IN PLACE over the vx / vy control planes once the velocity
+// critics have consumed them); the score mode (caller-provided trajectories) needs x and y beside the state: 6.
+__host__ __device__ inline int rollout_planes(int mode) {return mode == 2 ? 6 : 4;}
+__host__ __device__ inline size_t rollout_smem_bytes(int T, int S, int mode)
 {
-  // 6 tile planes + control sequence copy + per-trajectory initial velocities + segment partials + argmin scratch
-  return sizeof(float) * (static_cast<size_t>(6) * T * kPad + 3 * T + 3 * kTile + static_cast<size_t>(S) * A_COUNT * kTile +
-         2 * static_cast<size_t>(S) * kTile);
+  return sizeof(float) * (static_cast<size_t>(kHotFloats) + 3 * T + 3 * kTile + static_cast<size_t>(rollout_planes(mode)) * T * kPad +
+         static_cast<size_t>(S) * A_COUNT * kTile + 2 * static_cast<size_t>(S) * kTile);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -133,237 +136,279 @@ __global__ void __launch_bounds__(256) noise_philox_kernel(
 // ---------------------------------------------------------------------------------------------------
 // K2
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) rollout_score_kernel(
+#ifndef MPPI_K2_MIN_BLOCKS
+#define MPPI_K2_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
   const DevParams * __restrict__ P, const uint8_t * __restrict__ cm, DevBuffers bufs)
 {
   extern __shared__ float smem[];
-  const int T = P->T, B = P->B, S = blockDim.y;
+  const int S = blockDim.y;
   const int lane = threadIdx.x, seg = threadIdx.y;
+  const int tid = seg * kTile + lane;
+  const int nthreads = S * kTile;
+
+  // hot part of the per-cycle record -> shared memory (one coalesced round trip instead of scattered loads)
+  float * s_hot = smem;
+  load_hot_params(s_hot, P, tid, nthreads);
+  __syncthreads();
+  const DevParams & p = *reinterpret_cast<const DevParams *>(s_hot);
+  const int T = p.T, B = p.B, mode = p.mode;
   const int tplane = T * kPad;
-  float * s_cvx = smem;
-  float * s_cvy = s_cvx + tplane;
-  float * s_cwz = s_cvy + tplane;
+  float * s_cs = s_hot + kHotFloats;             // [3][T]
+  float * s_v0 = s_cs + 3 * T;                   // [3][32] initial velocities per trajectory
+  float * s_cvx = s_v0 + 3 * kTile;              // controls vx  -> (rollout modes) x
+  float * s_cvy = s_cvx + tplane;                // controls vy  -> (rollout modes) y
+  float * s_cwz = s_cvy + tplane;                // controls wz
   float * s_yaw = s_cwz + tplane;
-  float * s_x = s_yaw + tplane;
-  float * s_y = s_x + tplane;
-  float * s_cs = s_y + tplane;                  // [3][T]
-  float * s_v0 = s_cs + 3 * T;                  // [3][32] initial velocities per trajectory
-  float * s_acc = s_v0 + 3 * kTile;             // [S][A_COUNT][32]
-  float * s_amin_d = s_acc + S * A_COUNT * kTile;   // [S][32]
+  float * s_x = mode == 2 ? s_yaw + tplane : s_cvx;
+  float * s_y = mode == 2 ? s_x + tplane : s_cvy;
+  float * s_acc = s_yaw + tplane * (mode == 2 ? 3 : 1);   // [S][A_COUNT][32]
+  float * s_amin_d = s_acc + S * A_COUNT * kTile;         // [S][32]
   int * s_amin_j = reinterpret_cast<int *>(s_amin_d + S * kTile);
 
   const int b0 = blockIdx.x * kTile;
   const int b = b0 + lane;
   const bool live = b < B;
-  const int mode = P->mode;
-  const int hol = P->holonomic;
-  const float dt = P->dt;
-  const int tid = seg * kTile + lane;
-  const int nthreads = S * kTile;
+  const int hol = p.holonomic;
+  const float dt = p.dt;
 
   // ---- P1: stage the tile.  Warp `seg` walks rows seg, seg+S, ...; lane walks t (coalesced 128 B rows).
   for (int i = tid; i < 3 * T; i += nthreads) {s_cs[i] = bufs.cs[i];}
   __syncthreads();
-  for (int r = seg; r < kTile; r += S) {
-    const int rb = b0 + r;
-    if (rb < B) {
-      const size_t row = static_cast<size_t>(rb) * T;
-      for (int t = lane; t < T; t += 32) {
-        const float a = __ldg(bufs.in_a + row + t);
-        const float c = __ldg(bufs.in_c + row + t);
-        const float bb = __ldg(bufs.in_b + row + t);
-        if (mode == 0) {
+  if (mode == 0) {
+    for (int r = seg; r < kTile; r += S) {
+      const int rb = b0 + r;
+      if (rb < B) {
+        const float * __restrict__ pa = bufs.in_a + static_cast<size_t>(rb) * T;
+        const float * __restrict__ pb = bufs.in_b + static_cast<size_t>(rb) * T;
+        const float * __restrict__ pc = bufs.in_c + static_cast<size_t>(rb) * T;
+        int o = lane * kPad + r;
+        for (int t = lane; t < T; t += 32, o += 32 * kPad) {
           // setNoisedControls: c = control_sequence + noise (noise_generator.cpp:71-73)
-          s_cvx[t * kPad + r] = __fadd_rn(s_cs[t], a);
-          s_cvy[t * kPad + r] = __fadd_rn(s_cs[T + t], bb);
-          s_cwz[t * kPad + r] = __fadd_rn(s_cs[2 * T + t], c);
-        } else {
+          s_cvx[o] = __fadd_rn(s_cs[t], __ldg(pa + t));
+          s_cvy[o] = __fadd_rn(s_cs[T + t], __ldg(pb + t));
+          s_cwz[o] = __fadd_rn(s_cs[2 * T + t], __ldg(pc + t));
+        }
+      }
+    }
+    // updateInitialStateVelocities (optimizer.cpp:258-267): v[:,0] = robot speed
+    if (seg == 0) {
+      s_v0[lane] = p.speed_vx; s_v0[kTile + lane] = hol ? p.speed_vy : 0.0f; s_v0[2 * kTile + lane] = p.speed_wz;
+    }
+  } else {
+    for (int r = seg; r < kTile; r += S) {
+      const int rb = b0 + r;
+      if (rb < B) {
+        const size_t row = static_cast<size_t>(rb) * T;
+        for (int t = lane; t < T; t += 32) {
+          const float a = __ldg(bufs.in_a + row + t), bb = __ldg(bufs.in_b + row + t), c = __ldg(bufs.in_c + row + t);
           // injected state velocities: v[t] is stored where predict() would read it, c[t-1]
           if (t == 0) {
             s_v0[r] = a; s_v0[kTile + r] = bb; s_v0[2 * kTile + r] = c;
           } else {
             s_cvx[(t - 1) * kPad + r] = a; s_cvy[(t - 1) * kPad + r] = bb; s_cwz[(t - 1) * kPad + r] = c;
           }
-        }
-        if (mode == 2) {
-          s_x[t * kPad + r] = __ldg(bufs.in_x + row + t);
-          s_y[t * kPad + r] = __ldg(bufs.in_y + row + t);
-          s_yaw[t * kPad + r] = __ldg(bufs.in_yaw + row + t);
+          if (mode == 2) {
+            s_x[t * kPad + r] = __ldg(bufs.in_x + row + t);
+            s_y[t * kPad + r] = __ldg(bufs.in_y + row + t);
+            s_yaw[t * kPad + r] = __ldg(bufs.in_yaw + row + t);
+          }
         }
       }
     }
-  }
-  if (mode == 0) {
-    // updateInitialStateVelocities (optimizer.cpp:258-267): v[:,0] = robot speed
-    if (seg == 0) {
-      s_v0[lane] = P->speed_vx; s_v0[kTile + lane] = hol ? P->speed_vy : 0.0f; s_v0[2 * kTile + lane] = P->speed_wz;
+    if (seg == 0 && live) {
+      const int o = (T - 1) * kPad + lane;
+      s_cvx[o] = 0.0f; s_cvy[o] = 0.0f; s_cwz[o] = 0.0f;
     }
-  } else if (seg == 0 && live) {
-    const int o = (T - 1) * kPad + lane;
-    s_cvx[o] = 0.0f; s_cvy[o] = 0.0f; s_cwz[o] = 0.0f;
   }
   __syncthreads();
 
-  if (mode != 2) {
-    // ---- P2: yaw = cumsum(wz * dt) + yaw0, sequential in t (optimizer.cpp:319-320)
-    if (seg == 0 && live) {
-      const float yaw0 = P->yaw0;
-      float acc = 0.0f;
-      float wz = s_v0[2 * kTile + lane];
-#pragma unroll 4
-      for (int t = 0; t < T; ++t) {
-        const float term = __fmul_rn(wz, dt);
-        acc = t == 0 ? term : __fadd_rn(acc, term);
-        wz = s_cwz[t * kPad + lane];
-        s_yaw[t * kPad + lane] = __fadd_rn(acc, yaw0);
-      }
+  // my segment of the horizon, and the state velocities just before it (read before anyone overwrites a plane)
+  const int L = (T + S - 1) / S;
+  const int t0 = min(T, seg * L), t1 = min(T, t0 + L);
+  const bool use_vy = hol || mode != 0;
+  float pvx = 0.0f, pvy = 0.0f, pwz = 0.0f;
+  if (live && t0 < t1) {
+    if (t0 == 0) {
+      pvx = s_v0[lane]; pvy = s_v0[kTile + lane]; pwz = s_v0[2 * kTile + lane];
+    } else {
+      const int o = (t0 - 1) * kPad + lane;
+      pvx = s_cvx[o]; pvy = s_cvy[o]; pwz = s_cwz[o];
     }
-    __syncthreads();
-    // ---- P3: dx*dt, dy*dt with the one-step yaw lag (optimizer.cpp:322-337), parallel over (trajectory, t)
-    if (live) {
-      const int L = (T + S - 1) / S;
-      const int t0 = seg * L, t1 = min(T, t0 + L);
-      const bool use_vy = hol || mode != 0;
-      for (int t = t0; t < t1; ++t) {
-        float sn, cn;
-        if (t == 0) {
-          sn = P->sin0; cn = P->cos0;
-        } else {
-          mppi_det_sincosf(s_yaw[(t - 1) * kPad + lane], &sn, &cn);
-        }
-        const float vx = t ? s_cvx[(t - 1) * kPad + lane] : s_v0[lane];
-        float dx = __fmul_rn(vx, cn);
-        float dy = __fmul_rn(vx, sn);
-        if (hol) {
-          const float vy = use_vy ? (t ? s_cvy[(t - 1) * kPad + lane] : s_v0[kTile + lane]) : 0.0f;
-          dx = __fsub_rn(dx, __fmul_rn(vy, sn));
-          dy = __fadd_rn(dy, __fmul_rn(vy, cn));
-        }
-        s_x[t * kPad + lane] = __fmul_rn(dx, dt);
-        s_y[t * kPad + lane] = __fmul_rn(dy, dt);
-      }
-    }
-    __syncthreads();
-    // ---- P4: x = pose.x (double) + cumsum(dx*dt) (float), sequential in t (optimizer.cpp:339-342)
-    if (live && (seg == 0 || (seg == 1 && S > 1))) {
-      const bool do_x = seg == 0, do_y = (S > 1) ? (seg == 1) : true;
-      if (do_x) {
-        const double x0 = P->pose_x;
-        float acc = 0.0f;
-#pragma unroll 4
-        for (int t = 0; t < T; ++t) {
-          const float v = s_x[t * kPad + lane];
-          acc = t == 0 ? v : __fadd_rn(acc, v);
-          s_x[t * kPad + lane] = static_cast<float>(x0 + static_cast<double>(acc));
-        }
-      }
-      if (do_y) {
-        const double y0 = P->pose_y;
-        float acc = 0.0f;
-#pragma unroll 4
-        for (int t = 0; t < T; ++t) {
-          const float v = s_y[t * kPad + lane];
-          acc = t == 0 ? v : __fadd_rn(acc, v);
-          s_y[t * kPad + lane] = static_cast<float>(y0 + static_cast<double>(acc));
-        }
-      }
-    }
-    __syncthreads();
+    if (!use_vy) {pvy = 0.0f;}
   }
 
-  // ---- P5: critics, parallel over (trajectory, segment of the horizon)
+  // ---- P2: yaw = cumsum(wz * dt) + yaw0, sequential in t (optimizer.cpp:319-320)
+  if (mode != 2 && seg == 0 && live) {
+    const float yaw0 = p.yaw0;
+    float acc = 0.0f;
+    float wz = s_v0[2 * kTile + lane];
+    int o = lane;
+#pragma unroll 4
+    for (int t = 0; t < T; ++t, o += kPad) {
+      const float term = __fmul_rn(wz, dt);
+      acc = t == 0 ? term : __fadd_rn(acc, term);
+      wz = s_cwz[o];
+      s_yaw[o] = __fadd_rn(acc, yaw0);
+    }
+  }
+  __syncthreads();
+
+  // ---- P3: velocity critics + gamma term, then dx*dt / dy*dt with the one-step yaw lag written in place
   float acc[A_COUNT];
 #pragma unroll
   for (int k = 0; k < A_COUNT; ++k) {acc[k] = 0.0f;}
   if (live) {
-    const int L = (T + S - 1) / S;
-    const int t0 = seg * L, t1 = min(T, t0 + L);
-    const bool con_on = P->constraint.on, fwd_on = P->forward.on, twirl_on = P->twirl.on, db_on = P->deadband.on;
-    const bool goal_on = P->goal.on, gang_on = P->goal_angle.on, cost_on = P->cost.on, ob_on = P->obst.on;
-    const bool need_cell = cost_on || ob_on || P->want_cells;
-    const bool acker = P->model == MPPI_MODEL_ACKERMANN;
-    const bool track_unknown = P->track_unknown != 0;
-    const float max_vel = P->max_vel, min_vel = P->min_vel, min_r = P->min_turning_r;
-    const double gx = P->goal_x, gy = P->goal_y;
-    const float goal_yaw = P->goal_yaw;
-    const int step = P->sample_step;
-    int next_sample = step > 0 ? ((t0 + step - 1) / step) * step : T;
-    bool cost_hit = false, ob_hit = false;
-    const bool use_vy = hol || mode != 0;
-    for (int t = t0; t < t1; ++t) {
-      const int o = t * kPad + lane;
-      const float vx = t ? s_cvx[o - kPad] : s_v0[lane];
-      const float vy = use_vy ? (t ? s_cvy[o - kPad] : s_v0[kTile + lane]) : 0.0f;
-      const float wz = t ? s_cwz[o - kPad] : s_v0[2 * kTile + lane];
-      const float px = s_x[o], py = s_y[o], pyaw = s_yaw[o];
-
+    const bool con_on = p.constraint.on, fwd_on = p.forward.on, twirl_on = p.twirl.on, db_on = p.deadband.on;
+    const bool acker = p.model == MPPI_MODEL_ACKERMANN;
+    const float max_vel = p.max_vel, min_vel = p.min_vel, min_r = p.min_turning_r;
+    const float db_vx = fabsf(p.db_vx), db_vy = fabsf(p.db_vy), db_wz = fabsf(p.db_wz);
+    float g_vx = 0.0f, g_vy = 0.0f, g_wz = 0.0f, a_con = 0.0f, a_fwd = 0.0f, a_twirl = 0.0f, a_db = 0.0f;
+    int o = t0 * kPad + lane;
+    for (int t = t0; t < t1; ++t, o += kPad) {
+      const float cx = s_cvx[o], cy = s_cvy[o], cw = s_cwz[o];   // controls of step t (state velocities of t+1)
+      const float vx = pvx, vy = pvy, wz = pwz;                   // state velocities of step t
       if (mode == 0) {
         // gamma term of updateControlSequence (optimizer.cpp:365-380): sum_t cs[t] * (c[b,t] - cs[t])
         const float csx = s_cs[t], csy = s_cs[T + t], csw = s_cs[2 * T + t];
-        acc[A_GVX] = __fadd_rn(acc[A_GVX], __fmul_rn(csx, __fsub_rn(s_cvx[o], csx)));
-        acc[A_GWZ] = __fadd_rn(acc[A_GWZ], __fmul_rn(csw, __fsub_rn(s_cwz[o], csw)));
-        if (hol) {acc[A_GVY] = __fadd_rn(acc[A_GVY], __fmul_rn(csy, __fsub_rn(s_cvy[o], csy)));}
+        g_vx = __fadd_rn(g_vx, __fmul_rn(csx, __fsub_rn(cx, csx)));
+        g_wz = __fadd_rn(g_wz, __fmul_rn(csw, __fsub_rn(cw, csw)));
+        if (hol) {g_vy = __fadd_rn(g_vy, __fmul_rn(csy, __fsub_rn(cy, csy)));}
       }
       if (con_on) {   // constraint_critic.cpp:49-52
         const float sgn = vx > 0.0f ? 1.0f : -1.0f;
         const float vel_total = sgn * sqrtf(vx * vx + vy * vy);
         float e = fmaxf(vel_total - max_vel, 0.0f) + fmaxf(min_vel - vel_total, 0.0f);
         if (acker) {e += fmaxf(min_r - fabsf(vx) / fabsf(wz), 0.0f);}
-        acc[A_CON] += e * dt;
+        a_con += e * dt;
       }
-      if (fwd_on) {acc[A_FWD] += fmaxf(-vx, 0.0f) * dt;}           // prefer_forward_critic.cpp:42-46
-      if (twirl_on) {acc[A_TWIRL] += fabsf(wz);}                   // twirling_critic.cpp:40-41
-      if (db_on) {                                                 // velocity_deadband_critic.cpp:54-97
-        float e = fmaxf(fabsf(P->db_vx) - fabsf(vx), 0.0f);
-        if (hol) {e += fmaxf(fabsf(P->db_vy) - fabsf(vy), 0.0f);}
-        e += fmaxf(fabsf(P->db_wz) - fabsf(wz), 0.0f);
-        acc[A_DB] += e * dt;
+      if (fwd_on) {a_fwd += fmaxf(-vx, 0.0f) * dt;}           // prefer_forward_critic.cpp:42-46
+      if (twirl_on) {a_twirl += fabsf(wz);}                   // twirling_critic.cpp:40-41
+      if (db_on) {                                            // velocity_deadband_critic.cpp:54-97
+        float e = fmaxf(db_vx - fabsf(vx), 0.0f);
+        if (hol) {e += fmaxf(db_vy - fabsf(vy), 0.0f);}
+        e += fmaxf(db_wz - fabsf(wz), 0.0f);
+        a_db += e * dt;
       }
+      if (mode != 2) {
+        // integrateStateVelocities (optimizer.cpp:322-337): cos/sin of yaw[t-1]
+        float sn, cn;
+        if (t == 0) {
+          sn = p.sin0; cn = p.cos0;
+        } else {
+          mppi_det_sincosf(s_yaw[o - kPad], &sn, &cn);
+        }
+        float dx = __fmul_rn(vx, cn);
+        float dy = __fmul_rn(vx, sn);
+        if (hol) {
+          dx = __fsub_rn(dx, __fmul_rn(vy, sn));
+          dy = __fadd_rn(dy, __fmul_rn(vy, cn));
+        }
+        s_x[o] = __fmul_rn(dx, dt);    // in place over the control planes: (cx, cy) already live in registers
+        s_y[o] = __fmul_rn(dy, dt);
+      }
+      pvx = cx; pvy = use_vy ? cy : 0.0f; pwz = cw;
+    }
+    acc[A_GVX] = g_vx; acc[A_GVY] = g_vy; acc[A_GWZ] = g_wz;
+    acc[A_CON] = a_con; acc[A_FWD] = a_fwd; acc[A_TWIRL] = a_twirl; acc[A_DB] = a_db;
+  }
+
+  if (mode != 2) {
+    __syncthreads();
+    // ---- P4: x = pose.x (double) + cumsum(dx*dt) (float), sequential in t (optimizer.cpp:339-342)
+    if (live && seg < 2) {
+      const bool do_x = seg == 0, do_y = (S > 1) ? (seg == 1) : true;
+      if (do_x) {
+        const double x0 = p.pose_x;
+        float a = 0.0f;
+        int o = lane;
+#pragma unroll 4
+        for (int t = 0; t < T; ++t, o += kPad) {
+          const float v = s_x[o];
+          a = t == 0 ? v : __fadd_rn(a, v);
+          s_x[o] = static_cast<float>(x0 + static_cast<double>(a));
+        }
+      }
+      if (do_y) {
+        const double y0 = p.pose_y;
+        float a = 0.0f;
+        int o = lane;
+#pragma unroll 4
+        for (int t = 0; t < T; ++t, o += kPad) {
+          const float v = s_y[o];
+          a = t == 0 ? v : __fadd_rn(a, v);
+          s_y[o] = static_cast<float>(y0 + static_cast<double>(a));
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- P5: position critics + spills, parallel over (trajectory, segment of the horizon)
+  if (live) {
+    const bool goal_on = p.goal.on, gang_on = p.goal_angle.on, cost_on = p.cost.on, ob_on = p.obst.on;
+    const bool want_cells = p.want_cells != 0, spill = p.spill_traj != 0;
+    const bool need_cell = cost_on || ob_on || want_cells;
+    const bool track_unknown = p.track_unknown != 0;
+    const bool cost_fp = p.cost_fp != 0, ob_fp = p.obst_fp != 0;
+    const bool cost_near_goal = p.cost_near_goal != 0, ob_near_goal = p.obst_near_goal != 0, ob_rep_on = p.obst_repulsion_enabled != 0;
+    const float cost_pic = p.cost_possibly_inscribed, ob_pic = p.obst_possibly_inscribed, cost_critical = p.cost_critical;
+    const double gx = p.goal_x, gy = p.goal_y, ox = p.ox, oy = p.oy, res = p.res, inv_res = p.inv_res;
+    const unsigned size_x = p.size_x, size_y = p.size_y;
+    const float goal_yaw = p.goal_yaw;
+    const int step = p.sample_step;
+    int next_sample = T, sample_k = 0;
+    if (step > 0) {sample_k = (t0 + step - 1) / step; next_sample = sample_k * step;}
+    const bool sample_yaw = p.sample_yaw != 0;
+    bool cost_hit = false, ob_hit = false;
+    float a_goal = 0.0f, a_gang = 0.0f, cost_rep = 0.0f, ob_traj = 0.0f, ob_rep = 0.0f;
+    int o = t0 * kPad + lane;
+    size_t g = static_cast<size_t>(t0) * B + b;
+    for (int t = t0; t < t1; ++t, o += kPad, g += B) {
+      const float px = s_x[o], py = s_y[o];
       if (goal_on) {                                               // goal_critic.cpp:50-52
         const float dx = static_cast<float>(static_cast<double>(px) - gx);
         const float dy = static_cast<float>(static_cast<double>(py) - gy);
-        acc[A_GOAL] += sqrtf(dx * dx + dy * dy);
+        a_goal += sqrtf(dx * dx + dy * dy);
       }
       if (gang_on) {                                               // goal_angle_critic.cpp:47-49
-        acc[A_GANG] += static_cast<float>(fabs(normalize_angle_d(static_cast<double>(__fsub_rn(goal_yaw, pyaw)))));
+        a_gang += static_cast<float>(fabs(normalize_angle_d(static_cast<double>(__fsub_rn(goal_yaw, s_yaw[o])))));
       }
       if (need_cell) {
-        unsigned mx, my;
-        const int cell = world_to_cell(px, py, P->ox, P->oy, P->res, P->size_x, P->size_y, mx, my);
-        if (P->want_cells) {bufs.spill_cells[static_cast<size_t>(t) * B + b] = cell;}
+        const int cell = world_to_cell_fast(px, py, ox, oy, res, inv_res, size_x, size_y);
+        if (want_cells) {bufs.spill_cells[g] = cell;}
         if ((cost_on && !cost_hit) || (ob_on && !ob_hit)) {
           const int pose_cost = cell < 0 ? NO_INFORMATION : __ldg(cm + cell);
           int fp_cost = -1;
           if (cost_on && !cost_hit && pose_cost >= 1) {            // cost_critic.cpp:139-162
             int c = pose_cost;
-            const float pic = P->cost_possibly_inscribed;
-            if (P->cost_fp && (static_cast<float>(c) >= pic || pic < 1.0f)) {
-              fp_cost = footprint_cost_at_pose(P, cm, px, py, pyaw);
+            if (cost_fp && (static_cast<float>(c) >= cost_pic || cost_pic < 1.0f)) {
+              fp_cost = footprint_cost_at_pose(P, p.fp_n, ox, oy, res, size_x, size_y, cm, px, py, s_yaw[o]);
               c = fp_cost;
             }
-            if (in_collision(c, P->cost_fp != 0, track_unknown)) {
+            if (in_collision(c, cost_fp, track_unknown)) {
               cost_hit = true;
             } else if (pose_cost >= INSCRIBED_INFLATED_OBSTACLE) {
-              acc[A_COST_REP] += P->cost_critical;
-            } else if (!P->cost_near_goal) {
-              acc[A_COST_REP] += static_cast<float>(pose_cost);
+              cost_rep += cost_critical;
+            } else if (!cost_near_goal) {
+              cost_rep += static_cast<float>(pose_cost);
             }
           }
           if (ob_on && !ob_hit) {                                  // obstacles_critic.cpp:145-170, :203-224
             int c = pose_cost;
             int using_fp = 0;
-            const float pic = P->obst_possibly_inscribed;
-            if (cell >= 0 && P->obst_fp && (static_cast<float>(c) >= pic || pic < 1.0f)) {
-              if (fp_cost < 0) {fp_cost = footprint_cost_at_pose(P, cm, px, py, pyaw);}
+            if (cell >= 0 && ob_fp && (static_cast<float>(c) >= ob_pic || ob_pic < 1.0f)) {
+              if (fp_cost < 0) {fp_cost = footprint_cost_at_pose(P, p.fp_n, ox, oy, res, size_x, size_y, cm, px, py, s_yaw[o]);}
               c = fp_cost;
               using_fp = 1;
             }
             if (c >= 1) {
-              if (in_collision(c, P->obst_fp != 0, track_unknown)) {
+              if (in_collision(c, ob_fp, track_unknown)) {
                 ob_hit = true;
-              } else if (P->obst_repulsion_enabled) {
-                acc[A_OB_TRAJ] += P->obst_lut_crit[using_fp][c];
-                if (!P->obst_near_goal) {acc[A_OB_REP] += P->obst_lut_rep[using_fp][c];}
+              } else if (ob_rep_on) {
+                ob_traj += __ldg(&P->obst_lut_crit[using_fp][c]);
+                if (!ob_near_goal) {ob_rep += __ldg(&P->obst_lut_rep[using_fp][c]);}
               }
             }
           }
@@ -371,21 +416,21 @@ __global__ void __launch_bounds__(256) rollout_score_kernel(
       }
       // spills for the path critics of K3
       if (t == next_sample) {
-        const size_t k = static_cast<size_t>(t / step);
-        bufs.samples_x[k * B + b] = px;
-        bufs.samples_y[k * B + b] = py;
-        if (P->sample_yaw) {bufs.samples_yaw[k * B + b] = pyaw;}
-        next_sample += step;
+        const size_t k = static_cast<size_t>(sample_k) * B + b;
+        bufs.samples_x[k] = px;
+        bufs.samples_y[k] = py;
+        if (sample_yaw) {bufs.samples_yaw[k] = s_yaw[o];}
+        next_sample += step; sample_k++;
       }
-      if (t == T - 1) {
-        bufs.end_xy[b] = px;
-        bufs.end_xy[B + b] = py;
-      }
-      if (P->spill_traj) {
-        const size_t g = static_cast<size_t>(t) * B + b;
-        bufs.spill_x[g] = px; bufs.spill_y[g] = py; bufs.spill_yaw[g] = pyaw;
+      if (spill) {
+        bufs.spill_x[g] = px; bufs.spill_y[g] = py; bufs.spill_yaw[g] = s_yaw[o];
       }
     }
+    if (t1 == T && t0 < t1) {
+      bufs.end_xy[b] = s_x[(T - 1) * kPad + lane];
+      bufs.end_xy[B + b] = s_y[(T - 1) * kPad + lane];
+    }
+    acc[A_GOAL] = a_goal; acc[A_GANG] = a_gang; acc[A_COST_REP] = cost_rep; acc[A_OB_TRAJ] = ob_traj; acc[A_OB_REP] = ob_rep;
     acc[A_COST_HIT] = cost_hit ? 1.0f : 0.0f;
     acc[A_OB_HIT] = ob_hit ? 1.0f : 0.0f;
   }
@@ -394,11 +439,11 @@ __global__ void __launch_bounds__(256) rollout_score_kernel(
 
   // ---- furthest reached path point candidate: argmin over the path of the end pose (utils.hpp:292-319),
   //      path range split over the warps, combined in order so the first minimum wins
-  const int N = P->N;
-  const bool need_furthest = (P->follow.idx >= 0 || P->angle.idx >= 0 || P->align.idx >= 0 || P->legacy.idx >= 0);
+  const int N = p.N;
+  const bool need_furthest = p.need_furthest != 0;
   if (need_furthest) {
-    const float * __restrict__ path_x = reinterpret_cast<const float *>(P + 1) + P->off_path_x;
-    const float * __restrict__ path_y = reinterpret_cast<const float *>(P + 1) + P->off_path_y;
+    const float * __restrict__ path_x = reinterpret_cast<const float *>(P + 1) + p.off_path_x;
+    const float * __restrict__ path_y = reinterpret_cast<const float *>(P + 1) + p.off_path_y;
     const float ex = s_x[(T - 1) * kPad + lane], ey = s_y[(T - 1) * kPad + lane];
     const int per = (N + S - 1) / S;
     const int j0 = seg * per, j1 = min(N, j0 + per);
@@ -438,34 +483,34 @@ __global__ void __launch_bounds__(256) rollout_score_kernel(
     const float Tf = static_cast<float>(T);
     float * rows = bufs.crit_rows;
     if (live) {
-      if (P->constraint.on) {rows[static_cast<size_t>(P->constraint.idx) * B + b] = add_pow(0.0f, tot[A_CON] * P->constraint.weight, P->constraint.power);}
-      if (P->forward.on) {rows[static_cast<size_t>(P->forward.idx) * B + b] = add_pow(0.0f, tot[A_FWD] * P->forward.weight, P->forward.power);}
-      if (P->twirl.on) {rows[static_cast<size_t>(P->twirl.idx) * B + b] = add_pow(0.0f, (tot[A_TWIRL] / Tf) * P->twirl.weight, P->twirl.power);}
-      if (P->deadband.on) {rows[static_cast<size_t>(P->deadband.idx) * B + b] = add_pow(0.0f, tot[A_DB] * P->deadband.weight, P->deadband.power);}
-      if (P->goal.on) {rows[static_cast<size_t>(P->goal.idx) * B + b] = add_pow(0.0f, (tot[A_GOAL] / Tf) * P->goal.weight, P->goal.power);}
-      if (P->goal_angle.on) {rows[static_cast<size_t>(P->goal_angle.idx) * B + b] = add_pow(0.0f, (tot[A_GANG] / Tf) * P->goal_angle.weight, P->goal_angle.power);}
-      if (P->cost.on) {   // cost_critic.cpp:159-166
-        const float rep = cost_collided ? P->cost_collision : tot[A_COST_REP];
-        rows[static_cast<size_t>(P->cost.idx) * B + b] = add_pow(0.0f, P->cost.weight * rep / Tf, P->cost.power);
+      if (p.constraint.on) {rows[static_cast<size_t>(p.constraint.idx) * B + b] = add_pow(0.0f, tot[A_CON] * p.constraint.weight, p.constraint.power);}
+      if (p.forward.on) {rows[static_cast<size_t>(p.forward.idx) * B + b] = add_pow(0.0f, tot[A_FWD] * p.forward.weight, p.forward.power);}
+      if (p.twirl.on) {rows[static_cast<size_t>(p.twirl.idx) * B + b] = add_pow(0.0f, (tot[A_TWIRL] / Tf) * p.twirl.weight, p.twirl.power);}
+      if (p.deadband.on) {rows[static_cast<size_t>(p.deadband.idx) * B + b] = add_pow(0.0f, tot[A_DB] * p.deadband.weight, p.deadband.power);}
+      if (p.goal.on) {rows[static_cast<size_t>(p.goal.idx) * B + b] = add_pow(0.0f, (tot[A_GOAL] / Tf) * p.goal.weight, p.goal.power);}
+      if (p.goal_angle.on) {rows[static_cast<size_t>(p.goal_angle.idx) * B + b] = add_pow(0.0f, (tot[A_GANG] / Tf) * p.goal_angle.weight, p.goal_angle.power);}
+      if (p.cost.on) {   // cost_critic.cpp:159-166
+        const float rep = cost_collided ? p.cost_collision : tot[A_COST_REP];
+        rows[static_cast<size_t>(p.cost.idx) * B + b] = add_pow(0.0f, p.cost.weight * rep / Tf, p.cost.power);
       }
-      if (P->obst.on) {   // obstacles_critic.cpp:169-176
-        const float raw = ob_collided ? P->obst_collision : tot[A_OB_TRAJ];
-        const float v = (P->obst_critical_w * raw) + (P->obst_repulsion_w * tot[A_OB_REP] / Tf);
-        rows[static_cast<size_t>(P->obst.idx) * B + b] = add_pow(0.0f, v, P->obst.power);
+      if (p.obst.on) {   // obstacles_critic.cpp:169-176
+        const float raw = ob_collided ? p.obst_collision : tot[A_OB_TRAJ];
+        const float v = (p.obst_critical_w * raw) + (p.obst_repulsion_w * tot[A_OB_REP] / Tf);
+        rows[static_cast<size_t>(p.obst.idx) * B + b] = add_pow(0.0f, v, p.obst.power);
       }
       if (mode == 0) {
-        const size_t g = static_cast<size_t>(P->n_critics) * B + b;
+        const size_t g = static_cast<size_t>(p.n_critics) * B + b;
         rows[g] = tot[A_GVX]; rows[g + B] = tot[A_GVY]; rows[g + 2 * static_cast<size_t>(B)] = tot[A_GWZ];
       }
     }
     // fail_flag inputs: did any trajectory of this tile survive?
-    if (P->cost.on) {
+    if (p.cost.on) {
       const unsigned ok = __ballot_sync(0xffffffffu, live && !cost_collided);
-      if (lane == 0 && ok) {atomicOr(&bufs.st->any_ok[P->cost.idx], 1u);}
+      if (lane == 0 && ok) {atomicOr(&bufs.st->any_ok[p.cost.idx], 1u);}
     }
-    if (P->obst.on) {
+    if (p.obst.on) {
       const unsigned ok = __ballot_sync(0xffffffffu, live && !ob_collided);
-      if (lane == 0 && ok) {atomicOr(&bufs.st->any_ok[P->obst.idx], 1u);}
+      if (lane == 0 && ok) {atomicOr(&bufs.st->any_ok[p.obst.idx], 1u);}
     }
     if (need_furthest) {
       float best = s_amin_d[lane];
@@ -484,6 +529,8 @@ __global__ void __launch_bounds__(256) rollout_score_kernel(
 // K3
 // ---------------------------------------------------------------------------------------------------
 constexpr int kUpdThreads = 128;
+constexpr int kMergeT = 4;               // time steps owned by one block of merge_finalize_kernel
+constexpr int kLastBlockMergeMax = 64;   // K3's last block merges up to this many partials itself
 
 // utils::findClosestPathPt (utils.hpp:665-675) on the prefix D[0..n); out-of-range clamps to n-1
 __device__ __forceinline__ int find_closest_path_pt(const float * D, int n, float dist, int init)
@@ -557,20 +604,24 @@ __device__ __forceinline__ void merge_partials(
 }
 
 __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
-  const DevParams * __restrict__ P, const uint8_t * __restrict__ cm, DevBuffers bufs, int n_ranks, int iteration, int R)
+  const DevParams * __restrict__ Pg, const uint8_t * __restrict__ cm, DevBuffers bufs, int n_ranks, int iteration, int R)
 {
   // R = trajectories owned by this block (multiple of 32, <= kUpdThreads): small batches use small R so that
   // the update spreads over many SMs; the column sums always use all kUpdThreads threads
   extern __shared__ float smem[];
-  const int T = P->T, B = P->B, N = P->N, nc = P->n_critics;
   const int tid = threadIdx.x;
-  const float * __restrict__ path_x = reinterpret_cast<const float *>(P + 1) + P->off_path_x;
-  const float * __restrict__ path_y = reinterpret_cast<const float *>(P + 1) + P->off_path_y;
-  const float * __restrict__ path_yaw = reinterpret_cast<const float *>(P + 1) + P->off_path_yaw;
-  const float * __restrict__ path_D = reinterpret_cast<const float *>(P + 1) + P->off_path_D;
-  const uint8_t * __restrict__ gate = reinterpret_cast<const uint8_t *>(reinterpret_cast<const float *>(P + 1) + P->off_gate);
+  float * s_hot = smem;
+  load_hot_params(s_hot, Pg, tid, kUpdThreads);
+  __syncthreads();
+  const DevParams * P = reinterpret_cast<const DevParams *>(s_hot);   // hot fields only; arrays stay in global (Pg)
+  const int T = P->T, B = P->B, N = P->N, nc = P->n_critics;
+  const float * __restrict__ path_x = reinterpret_cast<const float *>(Pg + 1) + P->off_path_x;
+  const float * __restrict__ path_y = reinterpret_cast<const float *>(Pg + 1) + P->off_path_y;
+  const float * __restrict__ path_yaw = reinterpret_cast<const float *>(Pg + 1) + P->off_path_yaw;
+  const float * __restrict__ path_D = reinterpret_cast<const float *>(Pg + 1) + P->off_path_D;
+  const uint8_t * __restrict__ gate = reinterpret_cast<const uint8_t *>(reinterpret_cast<const float *>(Pg + 1) + P->off_gate);
 
-  float * s_D = smem;                                   // [N]
+  float * s_D = s_hot + kHotFloats;                     // [N]
   float * s_w = s_D + N;                                // [kUpdThreads]
   float * s_red = s_w + kUpdThreads;                    // [32]
   uint8_t * s_valid = reinterpret_cast<uint8_t *>(s_red + 32);   // [N]
@@ -720,9 +771,14 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
             int path_pt = 0;
             float prev_x = bufs.samples_x[b], prev_y = bufs.samples_y[b];
             int k = 1;
+            float nx = 0.0f, ny = 0.0f;   // one-deep prefetch of the next sampled pose (L2 latency off the serial chain)
+            if (step < T) {nx = bufs.samples_x[static_cast<size_t>(B) + b]; ny = bufs.samples_y[static_cast<size_t>(B) + b];}
             for (int p = step; p < T; p += step, ++k) {
-              const float Tx = bufs.samples_x[static_cast<size_t>(k) * B + b];
-              const float Ty = bufs.samples_y[static_cast<size_t>(k) * B + b];
+              const float Tx = nx, Ty = ny;
+              if (p + step < T) {
+                nx = bufs.samples_x[static_cast<size_t>(k + 1) * B + b];
+                ny = bufs.samples_y[static_cast<size_t>(k + 1) * B + b];
+              }
               float dx = __fsub_rn(Tx, prev_x), dy = __fsub_rn(Ty, prev_y);
               traj_d = __fadd_rn(traj_d, __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
               path_pt = find_closest_path_pt(s_D, furthest, traj_d, path_pt);
@@ -886,36 +942,75 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
   float * part = bufs.partials + static_cast<size_t>(blockIdx.x) * stride;
   const int rows_here = min(R, B - blockIdx.x * R);
   const size_t row0 = static_cast<size_t>(blockIdx.x) * R * T;
-  for (int c = tid; c < 3 * T; c += kUpdThreads) {
-    const int plane = c / T, t = c - plane * T;
-    const float * __restrict__ src = (plane == 0 ? bufs.in_a : (plane == 1 ? bufs.in_b : bufs.in_c)) + row0 + t;
-    const float cs_t = bufs.cs[c];
-    float a[8];
+  if ((T & 3) == 0) {
+    // 16-byte loads along t: one thread owns 4 consecutive columns of one plane, 4 rows in flight
+    const int rs = T >> 2;
+    for (int c4 = tid; c4 < (3 * T) >> 2; c4 += kUpdThreads) {
+      const int c = c4 << 2;
+      const int plane = c / T, t = c - plane * T;
+      const float4 * __restrict__ src =
+        reinterpret_cast<const float4 *>((plane == 0 ? bufs.in_a : (plane == 1 ? bufs.in_b : bufs.in_c)) + row0 + t);
+      const float4 cs4 = *reinterpret_cast<const float4 *>(bufs.cs + c);
+      float4 a[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {a[u] = 0.0f;}
-    int r = 0;
-    for (; r + 7 < rows_here; r += 8) {
-      float v[8];
+      for (int u = 0; u < 4; ++u) {a[u] = make_float4(0.f, 0.f, 0.f, 0.f);}
+      int r = 0;
+      for (; r + 3 < rows_here; r += 4) {
+        float4 v[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {v[u] = __ldg(src + static_cast<size_t>(r + u) * T);}
+        for (int u = 0; u < 4; ++u) {v[u] = __ldg(src + static_cast<size_t>(r + u) * rs);}
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {a[u] = fmaf(s_w[r + u], __fadd_rn(cs_t, v[u]), a[u]);}
+        for (int u = 0; u < 4; ++u) {
+          const float w = s_w[r + u];
+          a[u].x = fmaf(w, __fadd_rn(cs4.x, v[u].x), a[u].x);
+          a[u].y = fmaf(w, __fadd_rn(cs4.y, v[u].y), a[u].y);
+          a[u].z = fmaf(w, __fadd_rn(cs4.z, v[u].z), a[u].z);
+          a[u].w = fmaf(w, __fadd_rn(cs4.w, v[u].w), a[u].w);
+        }
+      }
+      for (; r < rows_here; ++r) {
+        const float4 v = __ldg(src + static_cast<size_t>(r) * rs);
+        const float w = s_w[r];
+        a[0].x = fmaf(w, __fadd_rn(cs4.x, v.x), a[0].x);
+        a[0].y = fmaf(w, __fadd_rn(cs4.y, v.y), a[0].y);
+        a[0].z = fmaf(w, __fadd_rn(cs4.z, v.z), a[0].z);
+        a[0].w = fmaf(w, __fadd_rn(cs4.w, v.w), a[0].w);
+      }
+      part[2 + c] = (a[0].x + a[1].x) + (a[2].x + a[3].x);
+      part[3 + c] = (a[0].y + a[1].y) + (a[2].y + a[3].y);
+      part[4 + c] = (a[0].z + a[1].z) + (a[2].z + a[3].z);
+      part[5 + c] = (a[0].w + a[1].w) + (a[2].w + a[3].w);
     }
-    for (; r < rows_here; ++r) {a[0] = fmaf(s_w[r], __fadd_rn(cs_t, __ldg(src + static_cast<size_t>(r) * T)), a[0]);}
-    part[2 + c] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  } else {
+    for (int c = tid; c < 3 * T; c += kUpdThreads) {
+      const int plane = c / T, t = c - plane * T;
+      const float * __restrict__ src = (plane == 0 ? bufs.in_a : (plane == 1 ? bufs.in_b : bufs.in_c)) + row0 + t;
+      const float cs_t = bufs.cs[c];
+      float a[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {a[u] = 0.0f;}
+      int r = 0;
+      for (; r + 7 < rows_here; r += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {v[u] = __ldg(src + static_cast<size_t>(r + u) * T);}
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {a[u] = fmaf(s_w[r + u], __fadd_rn(cs_t, v[u]), a[u]);}
+      }
+      for (; r < rows_here; ++r) {a[0] = fmaf(s_w[r], __fadd_rn(cs_t, __ldg(src + static_cast<size_t>(r) * T)), a[0]);}
+      part[2 + c] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    }
   }
   if (tid == 0) {part[0] = m; part[1] = ssum;}
 
-  // ---- phase 4: the last block to finish merges all partials and writes the new control sequence
+  // ---- phase 4: the last block to finish publishes the flags and, for small batches, merges all partials
+  //      and writes the new control sequence (large batches: merge_finalize_kernel, launched by the host)
   __threadfence();
   __syncthreads();
   if (tid == 0) {sc_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;}
   __syncthreads();
   if (!sc_last) {return;}
   __threadfence();
-  float * merged = bufs.rank_partial;   // [3T + 2]
-  merge_partials(bufs.partials, gridDim.x, stride, T, inv_temp, merged, s_red, tid, kUpdThreads);
-  __syncthreads();
   if (tid == 0) {
     st->fail_flag = fail_at < nc ? 1 : 0;
     st->furthest = static_cast<unsigned>(sc_furthest);
@@ -927,6 +1022,9 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
     out[3 * T] = __int_as_float(st->fail_flag);
     out[3 * T + 1] = __uint_as_float(sc_furthest_set ? static_cast<unsigned>(sc_furthest) : kUnset);
   }
+  if (static_cast<int>(gridDim.x) > kLastBlockMergeMax) {return;}
+  float * merged = bufs.rank_partial;   // [3T + 2]
+  merge_partials(bufs.partials, gridDim.x, stride, T, inv_temp, merged, s_red, tid, kUpdThreads);
   if (n_ranks <= 1) {
     __threadfence_block();
     __syncthreads();
@@ -934,17 +1032,89 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
   }
 }
 
-// K4: sharded configurations.  `gathered` holds n_ranks records [m, s, W...] (all-gathered over NCCL);
-// every rank merges them redundantly and applies the clip, so no broadcast is needed afterwards.
-__global__ void __launch_bounds__(kUpdThreads) merge_partials_kernel(
-  const DevParams * __restrict__ P, float * __restrict__ gathered, int n_ranks, int stride, DevBuffers bufs)
+// K4: parallel merge of n partial records [m, s, W...] (online-softmax merge, SURVEY 8e exchange 2).
+// Used (a) after K3 when the batch produced more partials than one block should merge serially, and
+// (b) in sharded configurations on the all-gathered per-rank records; every rank merges redundantly and
+// applies the clip, so no broadcast is needed afterwards.  One block owns kMergeT time steps (3 columns each)
+// and all its threads stride over the partials; `finalize` = 0 writes the merged record to dst instead.
+
+__global__ void __launch_bounds__(kUpdThreads) merge_finalize_kernel(
+  const DevParams * __restrict__ Pg, const float * __restrict__ parts, int n, int stride, DevBuffers bufs, int finalize,
+  float * __restrict__ dst)
 {
-  __shared__ float s_merged[3 * MPPI_MAX_TIME_STEPS + 2];
-  __shared__ float s_red[32];
-  const float inv_temp = 1.0f / P->temperature;
-  merge_partials(gathered, n_ranks, stride, P->T, inv_temp, s_merged, s_red, threadIdx.x, kUpdThreads);
+  __shared__ float s_red[kUpdThreads / 32];
+  __shared__ float s_col[3 * kMergeT + 1];
+  __shared__ float s_m;
+  const int tid = threadIdx.x;
+  const int T = Pg->T;
+  const float inv_temp = 1.0f / Pg->temperature;
+  // global minimum over the partials
+  float m = 3.402823466e+38f;
+  for (int i = tid; i < n; i += kUpdThreads) {m = fminf(m, __ldg(parts + static_cast<size_t>(i) * stride));}
+  m = warp_min(m);
+  if ((tid & 31) == 0) {s_red[tid >> 5] = m;}
   __syncthreads();
-  finalize_controls(P, s_merged, bufs.cs, bufs.out, threadIdx.x, kUpdThreads);
+  if (tid == 0) {
+    float mm = s_red[0];
+    for (int w = 1; w < kUpdThreads / 32; ++w) {mm = fminf(mm, s_red[w]);}
+    s_m = mm;
+  }
+  __syncthreads();
+  m = s_m;
+  const int t_first = blockIdx.x * kMergeT;
+  // column 0 = sum of weights, then (vx, vy, wz) of each owned time step
+  for (int k = 0; k < 3 * kMergeT + 1; ++k) {
+    int col;   // index into the record after the leading m: 0 = s, 1 + plane * T + t = W
+    if (k == 0) {
+      col = 0;
+    } else {
+      const int t = t_first + (k - 1) / 3, plane = (k - 1) % 3;
+      if (t >= T) {break;}
+      col = 1 + plane * T + t;
+    }
+    float acc = 0.0f;
+    for (int i = tid; i < n; i += kUpdThreads) {
+      const float * p = parts + static_cast<size_t>(i) * stride;
+      acc = fmaf(__ldg(p + 1 + col), expf(-(__ldg(p) - m) * inv_temp), acc);
+    }
+    acc = warp_sum(acc);
+    __syncthreads();
+    if ((tid & 31) == 0) {s_red[tid >> 5] = acc;}
+    __syncthreads();
+    if (tid == 0) {
+      float a = 0.0f;
+      for (int w = 0; w < kUpdThreads / 32; ++w) {a += s_red[w];}
+      s_col[k] = a;
+    }
+  }
+  __syncthreads();
+  if (tid < kMergeT && t_first + tid < T) {
+    const int t = t_first + tid;
+    const float ssum = s_col[0];
+    const float wvx = s_col[1 + 3 * tid], wvy = s_col[2 + 3 * tid], wwz = s_col[3 + 3 * tid];
+    if (!finalize) {
+      dst[0] = m; dst[1] = ssum;
+      dst[2 + t] = wvx; dst[2 + T + t] = wvy; dst[2 + 2 * T + t] = wwz;
+    } else {
+      // cs = W / sum, then applyControlSequenceConstraints (optimizer.cpp:237-249)
+      float vx = wvx / ssum, wz = wwz / ssum, vy = bufs.cs[T + t];
+      if (Pg->holonomic) {
+        vy = wvy / ssum;
+        vy = fminf(fmaxf(vy, -Pg->c_vy), Pg->c_vy);
+      }
+      vx = fminf(fmaxf(vx, Pg->c_vx_min), Pg->c_vx_max);
+      wz = fminf(fmaxf(wz, -Pg->c_wz), Pg->c_wz);
+      if (Pg->model == MPPI_MODEL_ACKERMANN) {   // motion_models.hpp:110-117
+        const float r = Pg->min_turning_r;
+        if (fabsf(vx) / fabsf(wz) < r) {
+          const float sgn = wz > 0.0f ? 1.0f : (wz < 0.0f ? -1.0f : 0.0f);
+          wz = sgn * fabsf(vx) / r;
+        }
+      }
+      bufs.cs[t] = vx; bufs.cs[T + t] = vy; bufs.cs[2 * T + t] = wz;
+      bufs.out[t] = vx; bufs.out[T + t] = vy; bufs.out[2 * T + t] = wz;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -1348,6 +1348,7 @@ int oracle_generate_noise(Optimizer * o, uint64_t stream)
 {
   o->noise_stream = stream;
   o->generateNoisedControls();
+  o->noise_stream = stream + 1;   // a later reset() draws the next stream
   return MPPI_OK;
 }
 int oracle_get_noise(Optimizer * o, float * vx, float * vy, float * wz)
