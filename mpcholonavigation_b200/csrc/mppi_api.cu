@@ -108,6 +108,7 @@ struct mppi_handle
   bool spilled_traj{false}, spilled_cells{false}, have_rows{false};
   DevParams last;   // host copy of the last uploaded record
   int segments_override{0};
+  bool stream_layout{false};   // large batches: time-major noise + thread-per-trajectory K2 + GEMV-style weighted sums
   int upd_blocks{0};
   // CUDA graphs of the steady-state cycle: [0] kernels + D2H (resident inputs), [1] H2D + kernels + D2H
   cudaGraphExec_t gexec[2]{nullptr, nullptr};
@@ -405,6 +406,7 @@ mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, un
     }
   }
   p.spill_traj = ((h->want_mask & MPPI_WANT_TRAJECTORIES) || any_gate_open || mode == 1) ? 1 : 0;
+  p.noise_tm = (h->stream_layout && mode == 0) ? 1 : 0;
   p.need_furthest = (p.follow.idx >= 0 || p.angle.idx >= 0 || p.align.idx >= 0 || p.legacy.idx >= 0) ? 1 : 0;
   h->last = p;
   return MPPI_OK;
@@ -478,6 +480,14 @@ mppi_status enqueue_uploads(mppi_handle * h)
 
 mppi_status launch_rollout(mppi_handle * h, int mode)
 {
+  if (mode == 0 && h->stream_layout) {
+    const size_t smem = kHotBytes + sizeof(float) * 3 * h->T;
+    rollout_score_stream_kernel<<<(h->B + kStreamThreads - 1) / kStreamThreads, kStreamThreads, smem, h->stream>>>(
+      reinterpret_cast<const DevParams *>(h->d_params), h->d_costmap, make_bufs(h, mode));
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+    return MPPI_OK;
+  }
   const int S = pick_segments(h);
   const size_t smem = rollout_smem_bytes(h->T, S, mode);
   if (smem > 227 * 1024) {return fail(h, MPPI_E_CONFIG, "time_steps too large for the shared-memory tile");}
@@ -516,7 +526,17 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
     if (s != MPPI_OK) {return s;}
     const bool many = h->upd_blocks > kLastBlockMergeMax;
     const int merge_grid = (h->T + kMergeT - 1) / kMergeT;
-    if (many) {
+    if (h->stream_layout) {
+      // K3 published costs + global minimum; weights and weighted control sums over the time-major noise
+      const int chunks = (h->B + kTmChunk - 1) / kTmChunk;
+      weighted_sums_tm_kernel<<<chunks, kUpdThreads, 0, h->stream>>>(reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, 0));
+      CUDA_TRY(h, cudaGetLastError());
+      merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
+        reinterpret_cast<const DevParams *>(h->d_params), h->d_partials, chunks, stride, make_bufs(h, 0),
+        h->nranks > 1 ? 0 : 1, h->d_rank_partial);
+      CUDA_TRY(h, cudaGetLastError());
+      h->launches += 2;
+    } else if (many) {
       // too many block partials for a serial merge in K3's last block: merge them in parallel
       merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
         reinterpret_cast<const DevParams *>(h->d_params), h->d_partials, h->upd_blocks, stride, make_bufs(h, 0),
@@ -577,7 +597,7 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
     }
     if (h->gexec[slot]) {
       CUDA_TRY(h, cudaGraphLaunch(h->gexec[slot], h->stream));
-      h->launches += (h->upd_blocks > kLastBlockMergeMax ? 3ull : 2ull) * h->cfg.iteration_count;
+      h->launches += (h->stream_layout ? 4ull : (h->upd_blocks > kLastBlockMergeMax ? 3ull : 2ull)) * h->cfg.iteration_count;
       CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
       return MPPI_OK;
     }
@@ -661,7 +681,7 @@ mppi_status do_reset(mppi_handle * h)
   const int blocks = static_cast<int>(std::min<long long>((total + threads - 1) / threads, 148LL * 16));
   noise_philox_kernel<<<std::max(blocks, 1), threads, 0, h->stream>>>(
     h->d_noise[0], h->d_noise[1], h->d_noise[2], h->B, h->T, h->cfg.vx_std, h->cfg.vy_std, h->cfg.wz_std,
-    holonomic(h) ? 1 : 0, h->cfg.seed, h->noise_stream, static_cast<uint64_t>(h->cfg.shard_offset));
+    holonomic(h) ? 1 : 0, h->cfg.seed, h->noise_stream, static_cast<uint64_t>(h->cfg.shard_offset), h->stream_layout ? 1 : 0);
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   h->noise_stream++;
@@ -764,6 +784,12 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   std::memset(&h->robot, 0, sizeof(h->robot));
   if (const char * e = std::getenv("MPPI_SEGMENTS")) {h->segments_override = std::atoi(e);}
   if (const char * e = std::getenv("MPPI_NO_GRAPH")) {h->use_graph = std::atoi(e) == 0;}
+  {
+    // batches too small to fill the GPU with one thread per trajectory keep the latency-oriented tile kernel
+    long long stream_min = 16384;
+    if (const char * e = std::getenv("MPPI_STREAM_MIN_BATCH")) {stream_min = std::atoll(e);}
+    h->stream_layout = cfg->batch_size >= stream_min;
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
     h->err = "no CUDA device: this library has no CPU fallback";
@@ -862,13 +888,26 @@ mppi_status mppi_set_noise(mppi_handle * h, const float * vx, const float * vy, 
   if (!h || !vx || !wz) {return MPPI_E_CONFIG;}
   CUDA_TRY(h, cudaSetDevice(h->device));
   const size_t plane = static_cast<size_t>(h->B) * h->T * sizeof(float);
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_noise[0], vx, plane, cudaMemcpyHostToDevice, h->stream));
-  if (vy) {
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_noise[1], vy, plane, cudaMemcpyHostToDevice, h->stream));
-  } else {
-    CUDA_TRY(h, cudaMemsetAsync(h->d_noise[1], 0, plane, h->stream));
+  const float * src[3] = {vx, vy, wz};
+  if (h->stream_layout) {
+    mppi_status s = ensure_tmp(h);
+    if (s != MPPI_OK) {return s;}
   }
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_noise[2], wz, plane, cudaMemcpyHostToDevice, h->stream));
+  for (int i = 0; i < 3; ++i) {
+    if (!src[i]) {
+      CUDA_TRY(h, cudaMemsetAsync(h->d_noise[i], 0, plane, h->stream));
+      continue;
+    }
+    if (!h->stream_layout) {
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_noise[i], src[i], plane, cudaMemcpyHostToDevice, h->stream));
+    } else {
+      // caller's layout is [B][T]; the stream layout keeps [T][B]
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_tmp, src[i], plane, cudaMemcpyHostToDevice, h->stream));
+      const dim3 grid((h->T + 31) / 32, (h->B + 31) / 32), block(32, 8);
+      transpose_tb_to_bt_kernel<float><<<grid, block, 0, h->stream>>>(h->d_tmp, h->d_noise[i], h->B, h->T);
+      CUDA_TRY(h, cudaGetLastError());
+    }
+  }
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return MPPI_OK;
 }
@@ -881,7 +920,7 @@ mppi_status mppi_generate_noise(mppi_handle * h, uint64_t stream)
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 16));
   noise_philox_kernel<<<std::max(blocks, 1), 256, 0, h->stream>>>(
     h->d_noise[0], h->d_noise[1], h->d_noise[2], h->B, h->T, h->cfg.vx_std, h->cfg.vy_std, h->cfg.wz_std,
-    holonomic(h) ? 1 : 0, h->cfg.seed, stream, static_cast<uint64_t>(h->cfg.shard_offset));
+    holonomic(h) ? 1 : 0, h->cfg.seed, stream, static_cast<uint64_t>(h->cfg.shard_offset), h->stream_layout ? 1 : 0);
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   h->noise_stream = stream + 1;   // a later reset() draws the next stream
@@ -894,9 +933,15 @@ mppi_status mppi_get_noise(mppi_handle * h, float * vx, float * vy, float * wz)
   if (!h || !vx || !vy || !wz) {return MPPI_E_CONFIG;}
   CUDA_TRY(h, cudaSetDevice(h->device));
   const size_t plane = static_cast<size_t>(h->B) * h->T * sizeof(float);
-  CUDA_TRY(h, cudaMemcpyAsync(vx, h->d_noise[0], plane, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(vy, h->d_noise[1], plane, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(wz, h->d_noise[2], plane, cudaMemcpyDeviceToHost, h->stream));
+  float * dst[3] = {vx, vy, wz};
+  for (int i = 0; i < 3; ++i) {
+    if (h->stream_layout) {
+      const mppi_status s = fetch_time_major<float>(h, h->d_noise[i], dst[i]);
+      if (s != MPPI_OK) {return s;}
+    } else {
+      CUDA_TRY(h, cudaMemcpyAsync(dst[i], h->d_noise[i], plane, cudaMemcpyDeviceToHost, h->stream));
+    }
+  }
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return MPPI_OK;
 }

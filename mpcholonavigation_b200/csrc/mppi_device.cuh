@@ -81,6 +81,7 @@ struct DevParams
   int spill_traj;                            // write x,y,yaw time-major (PathAngle may fire / requested)
   int want_cells;
   int need_furthest;                         // some path critic may ask for the furthest reached path point
+  int noise_tm;                              // noise planes are stored time-major [T][B] (stream layout) instead of [B][T]
   // offsets (in floats) of the path arrays that follow this struct in the same buffer
   int off_path_x, off_path_y, off_path_yaw, off_path_D, off_gate;
   int fp_n;
@@ -111,7 +112,7 @@ struct DevState
   int furthest_set;
   int fail_flag;
   unsigned ticket;                      // last-block election of the update kernel
-  unsigned pad;
+  float global_min;                     // stream layout: min over all costs, published by K3's last block
 };
 
 // ---------------------------------------------------------------------------------------------------

@@ -99,15 +99,16 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float & z0, f
 
 __global__ void __launch_bounds__(256) noise_philox_kernel(
   float * __restrict__ nvx, float * __restrict__ nvy, float * __restrict__ nwz, int B, int T, float sx, float sy, float sw,
-  int holonomic, uint64_t seed, uint64_t stream, uint64_t shard_offset)
+  int holonomic, uint64_t seed, uint64_t stream, uint64_t shard_offset, int time_major)
 {
   const int quads = (T + 3) >> 2;
   const long long total = static_cast<long long>(B) * quads;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
     i += static_cast<long long>(gridDim.x) * blockDim.x)
   {
-    const int b = static_cast<int>(i / quads);
-    const int q = static_cast<int>(i - static_cast<long long>(b) * quads);
+    // row-major [B][T]: consecutive threads walk t (float4 stores); time-major [T][B]: consecutive threads walk b
+    const int b = time_major ? static_cast<int>(i % B) : static_cast<int>(i / quads);
+    const int q = time_major ? static_cast<int>(i / B) : static_cast<int>(i - static_cast<long long>(b) * quads);
     const uint32_t gb = static_cast<uint32_t>(static_cast<uint64_t>(b) + shard_offset);
 #pragma unroll
     for (int plane = 0; plane < 3; ++plane) {
@@ -123,11 +124,15 @@ __global__ void __launch_bounds__(256) noise_philox_kernel(
 #pragma unroll
         for (int j = 0; j < 4; ++j) {z[j] = __fmul_rn(z[j], sd);}
       }
-      float * row = dst + static_cast<size_t>(b) * T + 4 * q;
-      if ((T & 3) == 0) {
-        *reinterpret_cast<float4 *>(row) = make_float4(z[0], z[1], z[2], z[3]);
+      if (time_major) {
+        for (int j = 0; j < 4 && 4 * q + j < T; ++j) {dst[static_cast<size_t>(4 * q + j) * B + b] = z[j];}
       } else {
-        for (int j = 0; j < 4 && 4 * q + j < T; ++j) {row[j] = z[j];}
+        float * row = dst + static_cast<size_t>(b) * T + 4 * q;
+        if ((T & 3) == 0) {
+          *reinterpret_cast<float4 *>(row) = make_float4(z[0], z[1], z[2], z[3]);
+        } else {
+          for (int j = 0; j < 4 && 4 * q + j < T; ++j) {row[j] = z[j];}
+        }
       }
     }
   }
@@ -522,6 +527,240 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
       const unsigned m = warp_max_u(live ? static_cast<unsigned>(best_j) : 0u);
       if (lane == 0) {atomicMax(&bufs.st->furthest_candidate, m);}
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2, stream variant (large batches): one thread owns one trajectory for the whole horizon and everything
+// lives in registers.  The noise planes are stored TIME-MAJOR [T][B] for this variant, so lane == trajectory
+// reads are coalesced straight from HBM/L2 with no shared-memory staging, no transposes and no barriers; the
+// next steps' noise is prefetched ahead of the dependent chain.  Arithmetic (order of the three cumulative
+// sums, non-contractable fp32 ops, fp64 index math) is identical to the tile variant and to the oracle.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kStreamThreads = 128;
+constexpr int kStreamPrefetch = 4;     // noise rows in flight per thread
+
+__global__ void __launch_bounds__(kStreamThreads, 4) rollout_score_stream_kernel(
+  const DevParams * __restrict__ P, const uint8_t * __restrict__ cm, DevBuffers bufs)
+{
+  extern __shared__ float smem[];
+  const int tid = threadIdx.x;
+  float * s_hot = smem;
+  load_hot_params(s_hot, P, tid, kStreamThreads);
+  __syncthreads();
+  const DevParams & p = *reinterpret_cast<const DevParams *>(s_hot);
+  const int T = p.T, B = p.B;
+  float * s_cs = s_hot + kHotFloats;   // [3][T]
+  for (int i = tid; i < 3 * T; i += kStreamThreads) {s_cs[i] = bufs.cs[i];}
+  __syncthreads();
+
+  const int b = blockIdx.x * kStreamThreads + tid;
+  const bool live = b < B;
+  const int bb = live ? b : B - 1;      // dead lanes shadow the last trajectory (no divergence, no stores)
+  const int hol = p.holonomic;
+  const float dt = p.dt;
+  const float * __restrict__ nvx = bufs.in_a + bb;
+  const float * __restrict__ nvy = bufs.in_b + bb;
+  const float * __restrict__ nwz = bufs.in_c + bb;
+
+  const bool con_on = p.constraint.on, fwd_on = p.forward.on, twirl_on = p.twirl.on, db_on = p.deadband.on;
+  const bool goal_on = p.goal.on, gang_on = p.goal_angle.on, cost_on = p.cost.on, ob_on = p.obst.on;
+  const bool want_cells = p.want_cells != 0, spill = p.spill_traj != 0;
+  const bool need_cell = cost_on || ob_on || want_cells;
+  const bool acker = p.model == MPPI_MODEL_ACKERMANN;
+  const bool track_unknown = p.track_unknown != 0;
+  const bool cost_fp = p.cost_fp != 0, ob_fp = p.obst_fp != 0;
+  const bool cost_near_goal = p.cost_near_goal != 0, ob_near_goal = p.obst_near_goal != 0, ob_rep_on = p.obst_repulsion_enabled != 0;
+  const float cost_pic = p.cost_possibly_inscribed, ob_pic = p.obst_possibly_inscribed, cost_critical = p.cost_critical;
+  const float max_vel = p.max_vel, min_vel = p.min_vel, min_r = p.min_turning_r;
+  const float db_vx = fabsf(p.db_vx), db_vy = fabsf(p.db_vy), db_wz = fabsf(p.db_wz);
+  const double x0 = p.pose_x, y0 = p.pose_y, ox = p.ox, oy = p.oy, res = p.res, inv_res = p.inv_res;
+  const unsigned size_x = p.size_x, size_y = p.size_y;
+  const float yaw0 = p.yaw0, goal_yaw = p.goal_yaw;
+  const int step = p.sample_step;
+  const bool sample_yaw = p.sample_yaw != 0;
+
+  float g_vx = 0.f, g_vy = 0.f, g_wz = 0.f, a_con = 0.f, a_fwd = 0.f, a_twirl = 0.f, a_db = 0.f;
+  float a_goal = 0.f, a_gang = 0.f, cost_rep = 0.f, ob_traj = 0.f, ob_rep = 0.f;
+  bool cost_hit = false, ob_hit = false;
+  float vx = p.speed_vx, vy = hol ? p.speed_vy : 0.0f, wz = p.speed_wz;   // state velocities of step 0 = robot speed
+  float acc_yaw = 0.f, acc_x = 0.f, acc_y = 0.f, yaw_prev = yaw0;
+  float px = 0.f, py = 0.f;
+  int next_sample = step > 0 ? 0 : T, sample_k = 0;
+
+  // software pipeline of the noise rows
+  float qx[kStreamPrefetch], qy[kStreamPrefetch], qw[kStreamPrefetch];
+#pragma unroll
+  for (int u = 0; u < kStreamPrefetch; ++u) {
+    const size_t off = static_cast<size_t>(min(u, T - 1)) * B;
+    qx[u] = __ldg(nvx + off); qy[u] = __ldg(nvy + off); qw[u] = __ldg(nwz + off);
+  }
+  size_t g = b;   // index of (t, b) in the time-major spills
+  for (int t0 = 0; t0 < T; t0 += kStreamPrefetch) {
+#pragma unroll
+    for (int u = 0; u < kStreamPrefetch; ++u) {
+      const int t = t0 + u;
+      if (t < T) {
+        // setNoisedControls (noise_generator.cpp:71-73)
+        const float csx = s_cs[t], csy = s_cs[T + t], csw = s_cs[2 * T + t];
+        const float cx = __fadd_rn(csx, qx[u]), cy = __fadd_rn(csy, qy[u]), cw = __fadd_rn(csw, qw[u]);
+        {   // refill this slot with the row kStreamPrefetch steps ahead
+          const size_t off = static_cast<size_t>(min(t + kStreamPrefetch, T - 1)) * B;
+          qx[u] = __ldg(nvx + off); qy[u] = __ldg(nvy + off); qw[u] = __ldg(nwz + off);
+        }
+        // gamma term (optimizer.cpp:365-380)
+        g_vx = __fadd_rn(g_vx, __fmul_rn(csx, __fsub_rn(cx, csx)));
+        g_wz = __fadd_rn(g_wz, __fmul_rn(csw, __fsub_rn(cw, csw)));
+        if (hol) {g_vy = __fadd_rn(g_vy, __fmul_rn(csy, __fsub_rn(cy, csy)));}
+        // velocity critics on the state velocities of step t
+        if (con_on) {
+          const float sgn = vx > 0.0f ? 1.0f : -1.0f;
+          const float vel_total = sgn * sqrtf(vx * vx + vy * vy);
+          float e = fmaxf(vel_total - max_vel, 0.0f) + fmaxf(min_vel - vel_total, 0.0f);
+          if (acker) {e += fmaxf(min_r - fabsf(vx) / fabsf(wz), 0.0f);}
+          a_con += e * dt;
+        }
+        if (fwd_on) {a_fwd += fmaxf(-vx, 0.0f) * dt;}
+        if (twirl_on) {a_twirl += fabsf(wz);}
+        if (db_on) {
+          float e = fmaxf(db_vx - fabsf(vx), 0.0f);
+          if (hol) {e += fmaxf(db_vy - fabsf(vy), 0.0f);}
+          e += fmaxf(db_wz - fabsf(wz), 0.0f);
+          a_db += e * dt;
+        }
+        // integrateStateVelocities (optimizer.cpp:319-342), sequential order
+        const float term = __fmul_rn(wz, dt);
+        acc_yaw = t == 0 ? term : __fadd_rn(acc_yaw, term);
+        const float yaw = __fadd_rn(acc_yaw, yaw0);
+        float sn, cn;
+        if (t == 0) {
+          sn = p.sin0; cn = p.cos0;
+        } else {
+          mppi_det_sincosf(yaw_prev, &sn, &cn);
+        }
+        float dx = __fmul_rn(vx, cn), dy = __fmul_rn(vx, sn);
+        if (hol) {
+          dx = __fsub_rn(dx, __fmul_rn(vy, sn));
+          dy = __fadd_rn(dy, __fmul_rn(vy, cn));
+        }
+        const float tx = __fmul_rn(dx, dt), ty = __fmul_rn(dy, dt);
+        acc_x = t == 0 ? tx : __fadd_rn(acc_x, tx);
+        acc_y = t == 0 ? ty : __fadd_rn(acc_y, ty);
+        px = static_cast<float>(x0 + static_cast<double>(acc_x));
+        py = static_cast<float>(y0 + static_cast<double>(acc_y));
+
+        // position critics
+        if (goal_on) {
+          const float ddx = static_cast<float>(static_cast<double>(px) - p.goal_x);
+          const float ddy = static_cast<float>(static_cast<double>(py) - p.goal_y);
+          a_goal += sqrtf(ddx * ddx + ddy * ddy);
+        }
+        if (gang_on) {a_gang += static_cast<float>(fabs(normalize_angle_d(static_cast<double>(__fsub_rn(goal_yaw, yaw)))));}
+        if (need_cell) {
+          const int cell = world_to_cell_fast(px, py, ox, oy, res, inv_res, size_x, size_y);
+          if (want_cells && live) {bufs.spill_cells[g] = cell;}
+          if ((cost_on && !cost_hit) || (ob_on && !ob_hit)) {
+            const int pose_cost = cell < 0 ? NO_INFORMATION : __ldg(cm + cell);
+            int fp_cost = -1;
+            if (cost_on && !cost_hit && pose_cost >= 1) {
+              int c = pose_cost;
+              if (cost_fp && (static_cast<float>(c) >= cost_pic || cost_pic < 1.0f)) {
+                fp_cost = footprint_cost_at_pose(P, p.fp_n, ox, oy, res, size_x, size_y, cm, px, py, yaw);
+                c = fp_cost;
+              }
+              if (in_collision(c, cost_fp, track_unknown)) {
+                cost_hit = true;
+              } else if (pose_cost >= INSCRIBED_INFLATED_OBSTACLE) {
+                cost_rep += cost_critical;
+              } else if (!cost_near_goal) {
+                cost_rep += static_cast<float>(pose_cost);
+              }
+            }
+            if (ob_on && !ob_hit) {
+              int c = pose_cost;
+              int using_fp = 0;
+              if (cell >= 0 && ob_fp && (static_cast<float>(c) >= ob_pic || ob_pic < 1.0f)) {
+                if (fp_cost < 0) {fp_cost = footprint_cost_at_pose(P, p.fp_n, ox, oy, res, size_x, size_y, cm, px, py, yaw);}
+                c = fp_cost;
+                using_fp = 1;
+              }
+              if (c >= 1) {
+                if (in_collision(c, ob_fp, track_unknown)) {
+                  ob_hit = true;
+                } else if (ob_rep_on) {
+                  ob_traj += __ldg(&P->obst_lut_crit[using_fp][c]);
+                  if (!ob_near_goal) {ob_rep += __ldg(&P->obst_lut_rep[using_fp][c]);}
+                }
+              }
+            }
+          }
+        }
+        if (live) {
+          if (t == next_sample) {
+            const size_t k = static_cast<size_t>(sample_k) * B + b;
+            bufs.samples_x[k] = px; bufs.samples_y[k] = py;
+            if (sample_yaw) {bufs.samples_yaw[k] = yaw;}
+            next_sample += step; sample_k++;
+          }
+          if (spill) {bufs.spill_x[g] = px; bufs.spill_y[g] = py; bufs.spill_yaw[g] = yaw;}
+        }
+        g += B;
+        // predict(): state velocities of step t+1 are the controls of step t (motion_models.hpp:53-66)
+        vx = cx; vy = hol ? cy : 0.0f; wz = cw;
+        yaw_prev = yaw;
+      }
+    }
+  }
+
+  // furthest reached path point candidate (utils.hpp:292-319): first minimum over the whole path
+  unsigned best_j = 0;
+  if (p.need_furthest) {
+    const float * __restrict__ path_x = reinterpret_cast<const float *>(P + 1) + p.off_path_x;
+    const float * __restrict__ path_y = reinterpret_cast<const float *>(P + 1) + p.off_path_y;
+    float best = 3.402823466e+38f;
+    const int N = p.N;
+    for (int j = 0; j < N; ++j) {
+      const float dx = __fsub_rn(__ldg(path_x + j), px);
+      const float dy = __fsub_rn(__ldg(path_y + j), py);
+      const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+      if (d < best) {best = d; best_j = j;}
+    }
+  }
+
+  // publish (same rows as the tile variant)
+  const float Tf = static_cast<float>(T);
+  float * rows = bufs.crit_rows;
+  if (live) {
+    bufs.end_xy[b] = px; bufs.end_xy[B + b] = py;
+    if (p.constraint.on) {rows[static_cast<size_t>(p.constraint.idx) * B + b] = add_pow(0.0f, a_con * p.constraint.weight, p.constraint.power);}
+    if (p.forward.on) {rows[static_cast<size_t>(p.forward.idx) * B + b] = add_pow(0.0f, a_fwd * p.forward.weight, p.forward.power);}
+    if (p.twirl.on) {rows[static_cast<size_t>(p.twirl.idx) * B + b] = add_pow(0.0f, (a_twirl / Tf) * p.twirl.weight, p.twirl.power);}
+    if (p.deadband.on) {rows[static_cast<size_t>(p.deadband.idx) * B + b] = add_pow(0.0f, a_db * p.deadband.weight, p.deadband.power);}
+    if (p.goal.on) {rows[static_cast<size_t>(p.goal.idx) * B + b] = add_pow(0.0f, (a_goal / Tf) * p.goal.weight, p.goal.power);}
+    if (p.goal_angle.on) {rows[static_cast<size_t>(p.goal_angle.idx) * B + b] = add_pow(0.0f, (a_gang / Tf) * p.goal_angle.weight, p.goal_angle.power);}
+    if (p.cost.on) {
+      const float rep = cost_hit ? p.cost_collision : cost_rep;
+      rows[static_cast<size_t>(p.cost.idx) * B + b] = add_pow(0.0f, p.cost.weight * rep / Tf, p.cost.power);
+    }
+    if (p.obst.on) {
+      const float raw = ob_hit ? p.obst_collision : ob_traj;
+      const float v = (p.obst_critical_w * raw) + (p.obst_repulsion_w * ob_rep / Tf);
+      rows[static_cast<size_t>(p.obst.idx) * B + b] = add_pow(0.0f, v, p.obst.power);
+    }
+    const size_t gr = static_cast<size_t>(p.n_critics) * B + b;
+    rows[gr] = g_vx; rows[gr + B] = g_vy; rows[gr + 2 * static_cast<size_t>(B)] = g_wz;
+  }
+  if (p.cost.on) {
+    const unsigned ok = __ballot_sync(0xffffffffu, live && !cost_hit);
+    if ((tid & 31) == 0 && ok) {atomicOr(&bufs.st->any_ok[p.cost.idx], 1u);}
+  }
+  if (p.obst.on) {
+    const unsigned ok = __ballot_sync(0xffffffffu, live && !ob_hit);
+    if ((tid & 31) == 0 && ok) {atomicOr(&bufs.st->any_ok[p.obst.idx], 1u);}
+  }
+  if (p.need_furthest) {
+    const unsigned m = warp_max_u(live ? best_j : 0u);
+    if ((tid & 31) == 0) {atomicMax(&bufs.st->furthest_candidate, m);}
   }
 }
 
@@ -928,6 +1167,38 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
 #pragma unroll
   for (int w = 1; w < kUpdThreads / 32; ++w) {m = fminf(m, s_red[w]);}
   __syncthreads();
+  if (P->noise_tm) {
+    // stream layout: the weighted sums run as a separate, layout-friendly kernel (weighted_sums_tm_kernel) once the
+    // global minimum is known.  Publish this block's minimum; the last block reduces them and the flags.
+    const int stride_tm = 3 * T + 2;
+    if (tid == 0) {bufs.partials[static_cast<size_t>(blockIdx.x) * stride_tm] = m;}
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {sc_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;}
+    __syncthreads();
+    if (!sc_last) {return;}
+    __threadfence();
+    float gm = 3.402823466e+38f;
+    for (int i = tid; i < static_cast<int>(gridDim.x); i += kUpdThreads) {gm = fminf(gm, bufs.partials[static_cast<size_t>(i) * stride_tm]);}
+    gm = warp_min(gm);
+    if ((tid & 31) == 0) {s_red[tid >> 5] = gm;}
+    __syncthreads();
+    if (tid == 0) {
+      gm = s_red[0];
+      for (int w = 1; w < kUpdThreads / 32; ++w) {gm = fminf(gm, s_red[w]);}
+      st->global_min = gm;
+      st->fail_flag = fail_at < nc ? 1 : 0;
+      st->furthest = static_cast<unsigned>(sc_furthest);
+      st->furthest_set = sc_furthest_set;
+      st->furthest_candidate = 0u;
+      for (int q = 0; q < kMaxCritics; ++q) {st->any_ok[q] = 0u;}
+      st->ticket = 0u;
+      float * out = bufs.out;
+      out[3 * T] = __int_as_float(st->fail_flag);
+      out[3 * T + 1] = __uint_as_float(sc_furthest_set ? static_cast<unsigned>(sc_furthest) : kUnset);
+    }
+    return;
+  }
   const float w_b = live ? expf(-(total - m) * inv_temp) : 0.0f;
   s_w[tid] = w_b;
   float ssum = warp_sum(w_b);
@@ -1029,6 +1300,92 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
     __threadfence_block();
     __syncthreads();
     finalize_controls(P, merged, bufs.cs, bufs.out, tid, kUpdThreads);
+  }
+}
+
+// K3c (stream layout): softmax weights and weighted control sums over time-major noise [T][B].
+// One block owns kTmChunk consecutive trajectories; every thread owns 4 groups of 4 consecutive b (16-byte loads,
+// coalesced along b) and keeps their weights in registers; each (plane, t) row is reduced with warp shuffles.
+// The record written is [m = global min, s, W...] so that merge_finalize_kernel merges it like any other partial.
+constexpr int kTmGroups = 4;
+constexpr int kTmChunk = kUpdThreads * 4 * kTmGroups;   // 2048 trajectories per block
+
+__global__ void __launch_bounds__(kUpdThreads) weighted_sums_tm_kernel(const DevParams * __restrict__ Pg, DevBuffers bufs)
+{
+  __shared__ float s_part[kUpdThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = Pg->T, B = Pg->B;
+  const float inv_temp = 1.0f / Pg->temperature;
+  const float gm = bufs.st->global_min;
+  const int stride = 3 * T + 2;
+  float * part = bufs.partials + static_cast<size_t>(blockIdx.x) * stride;
+  const int b0 = blockIdx.x * kTmChunk;
+  const bool vec = (B & 3) == 0;
+  // weights of my 16 trajectories
+  float w[kTmGroups][4];
+  float ssum = 0.0f;
+#pragma unroll
+  for (int gidx = 0; gidx < kTmGroups; ++gidx) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int b = b0 + (gidx * kUpdThreads + tid) * 4 + j;
+      w[gidx][j] = b < B ? expf(-(bufs.costs[b] - gm) * inv_temp) : 0.0f;
+      ssum += w[gidx][j];
+    }
+  }
+  auto block_sum = [&](float v) -> float {
+      v = warp_sum(v);
+      __syncthreads();
+      if (lane == 0) {s_part[warp] = v;}
+      __syncthreads();
+      float a = 0.0f;
+#pragma unroll
+      for (int k = 0; k < kUpdThreads / 32; ++k) {a += s_part[k];}
+      return a;
+    };
+  ssum = block_sum(ssum);
+  if (tid == 0) {part[0] = gm; part[1] = ssum;}
+  // rows in batches of 4: 16 independent 16-byte loads in flight per thread, one reduction round per batch
+  __shared__ float s_rows[kUpdThreads / 32][4];
+  for (int c0 = 0; c0 < 3 * T; c0 += 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = min(c0 + k, 3 * T - 1);
+      const int plane = c / T, t = c - plane * T;
+      const float * __restrict__ row = (plane == 0 ? bufs.in_a : (plane == 1 ? bufs.in_b : bufs.in_c)) + static_cast<size_t>(t) * B;
+      const float cs_t = bufs.cs[c];
+#pragma unroll
+      for (int gidx = 0; gidx < kTmGroups; ++gidx) {
+        const int b = b0 + (gidx * kUpdThreads + tid) * 4;
+        if (vec && b + 3 < B) {
+          const float4 v = __ldg(reinterpret_cast<const float4 *>(row + b));
+          acc[k] = fmaf(w[gidx][0], __fadd_rn(cs_t, v.x), acc[k]);
+          acc[k] = fmaf(w[gidx][1], __fadd_rn(cs_t, v.y), acc[k]);
+          acc[k] = fmaf(w[gidx][2], __fadd_rn(cs_t, v.z), acc[k]);
+          acc[k] = fmaf(w[gidx][3], __fadd_rn(cs_t, v.w), acc[k]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (b + j < B) {acc[k] = fmaf(w[gidx][j], __fadd_rn(cs_t, __ldg(row + b + j)), acc[k]);}
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {acc[k] = warp_sum(acc[k]);}
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {s_rows[warp][k] = acc[k];}
+    }
+    __syncthreads();
+    if (tid < 4 && c0 + tid < 3 * T) {
+      float a = 0.0f;
+#pragma unroll
+      for (int wv = 0; wv < kUpdThreads / 32; ++wv) {a += s_rows[wv][tid];}
+      part[2 + c0 + tid] = a;
+    }
   }
 }
 

@@ -49,6 +49,7 @@ def main():
     ap.add_argument("kernel")
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--launch", type=int, default=0, help="index among the launches of that kernel in the report")
+    ap.add_argument("--sort", default="samples", choices=["samples", "inst"])
     a = ap.parse_args()
     out = subprocess.run(["ncu", "-i", a.report, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     # the CSV holds one block per profiled launch: "Kernel Name", header row, rows
@@ -90,7 +91,8 @@ def main():
             pass
     print(f"kernel {blk['name'][:70]}: {tot_i} warp instructions, {tot_t} thread instructions, {tot_s} stall samples")
     print("  inst%  samp%  file:line  top stalls | source")
-    for line, e in sorted(per_line.items(), key=lambda kv: -kv[1][1])[: a.top]:
+    col = 1 if a.sort == "samples" else 0
+    for line, e in sorted(per_line.items(), key=lambda kv: -kv[1][col])[: a.top]:
         f, n = line if line else ("?", 0)
         text = src.get(f, [""] * (n + 1))[n - 1].strip()[:90] if n else ""
         stalls = ", ".join(f"{k[6:]}:{v}" for k, v in sorted(e[3].items(), key=lambda kv: -kv[1])[:3])

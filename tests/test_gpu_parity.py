@@ -268,3 +268,101 @@ def test_optimize_batch_matches_single(product_fns):
     for i in range(n):
         np.testing.assert_array_equal(bufs[i][0], singles[i].vx)
         np.testing.assert_array_equal(bufs[i][2], singles[i].wz)
+
+
+# ------------------------------------------------------------------------------------------------
+# stream layout (large batches): time-major noise, thread-per-trajectory K2, GEMV-style weighted sums.
+# The library picks it from the batch size; MPPI_STREAM_MIN_BATCH=1 forces it so that the same seeded
+# cases as above (oracle-sized) exercise that code path.
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture
+def stream_layout(monkeypatch):
+    monkeypatch.setenv("MPPI_STREAM_MIN_BATCH", "1")
+    yield
+    monkeypatch.delenv("MPPI_STREAM_MIN_BATCH", raising=False)
+
+
+@pytest.mark.parametrize("footprint,consider", [("circle", True), ("bowtie", True), ("circle", False)])
+def test_stream_config1_parity(product_fns, oracle_fns, stream_layout, footprint, consider):
+    sc = scenarios.config1(footprint=footprint, cost_consider_footprint=consider)
+    g, o = _pair(product_fns, oracle_fns, sc, sc.noise())
+    for cycle in range(1, 13):
+        rg, ro = g.optimize(sc.cycle), o.optimize(sc.cycle)
+        if cycle in (1, 2, 12):
+            _compare_cycle(g, o, sc, rg, ro, f"stream cycle {cycle}")
+        g.set_control_sequence(ro.vx, ro.vy, ro.wz)
+    nz = g.get_noise()
+    for a, b in zip(nz, sc.noise()):
+        np.testing.assert_array_equal(a, b)     # injected noise survives the layout change
+
+
+def test_stream_ragged_models_and_gates(product_fns, oracle_fns, stream_layout):
+    for batch, steps, model in ((1, 2, "Omni"), (33, 7, "DiffDrive"), (95, 30, "Omni"), (130, 57, "Ackermann"), (2050, 56, "Omni")):
+        sc = scenarios.config1(batch=batch, steps=steps, map_size=40, pose=(0.08, 0.06, 0.0))
+        sc.cfg["motion_model"] = model
+        g, o = _pair(product_fns, oracle_fns, sc, sc.noise())
+        rg, ro = g.optimize(sc.cycle), o.optimize(sc.cycle)
+        _compare_cycle(g, o, sc, rg, ro, f"stream {batch}x{steps} {model}")
+    # PathAngle firing, near-goal critics, all 12 critics
+    sc = scenarios.config1(batch=512)
+    sc.cycle.pose = (sc.cycle.pose[0], sc.cycle.pose[1], 2.6)
+    g, o = _pair(product_fns, oracle_fns, sc, sc.noise())
+    rg, ro = g.optimize(sc.cycle), o.optimize(sc.cycle)
+    _compare_cycle(g, o, sc, rg, ro, "stream facing away")
+    sc = scenarios.config1(batch=512, n_path=8)
+    g, o = _pair(product_fns, oracle_fns, sc, sc.noise())
+    rg, ro = g.optimize(sc.cycle), o.optimize(sc.cycle)
+    _compare_cycle(g, o, sc, rg, ro, "stream near goal")
+    sc = _all_critics_scenario(1)
+    g, o = _pair(product_fns, oracle_fns, sc, sc.noise())
+    for cycle in range(2):
+        rg, ro = g.optimize(sc.cycle), o.optimize(sc.cycle)
+        _compare_cycle(g, o, sc, rg, ro, f"stream all critics cycle {cycle}")
+        g.set_control_sequence(ro.vx, ro.vy, ro.wz)
+    sc = scenarios.config1(batch=128)
+    sc.cycle.costmap = np.full_like(sc.cycle.costmap, 254)
+    g, o = _pair(product_fns, oracle_fns, sc, sc.noise())
+    rg, ro = g.optimize(sc.cycle), o.optimize(sc.cycle)
+    assert rg.fail_flag and ro.fail_flag
+    _compare_cycle(g, o, sc, rg, ro, "stream lethal map")
+
+
+def test_stream_config3_and_philox(product_fns, oracle_fns, stream_layout):
+    sc = scenarios.config3(batch=2048)
+    g, o = _pair(product_fns, oracle_fns, sc, sc.noise())
+    for cycle in range(2):
+        rg, ro = g.optimize(sc.cycle), o.optimize(sc.cycle)
+        _compare_cycle(g, o, sc, rg, ro, f"stream obstacles cycle {cycle}")
+        g.set_control_sequence(ro.vx, ro.vy, ro.wz)
+    kw = dict(batch_size=301, time_steps=30, motion_model="Omni", seed=1234, shard_offset=77, shard_total=1000)
+    g, o = Engine(product_fns, **kw), Engine(oracle_fns, **kw)
+    g.generate_noise(9)
+    o.generate_noise(9)
+    for a, b, s in zip(g.get_noise(), o.get_noise(), (0.2, 0.2, 0.4)):
+        np.testing.assert_allclose(a, b, rtol=0, atol=4e-6 * s / 0.2)
+
+
+def test_tile_and_stream_agree_at_full_size(product_fns, monkeypatch):
+    """BASELINE configs[2] at full size: both K2 variants on the same 16384 x 56 problem (no oracle needed):
+    identical cell indices and trajectories, costs and controls within fp32 tolerance."""
+    sc = scenarios.config3()
+    noise = sc.noise()
+    res = []
+    for min_batch in ("1", "100000000"):
+        monkeypatch.setenv("MPPI_STREAM_MIN_BATCH", min_batch)
+        e = Engine(product_fns, **sc.cfg)
+        e.set_robot(sc.robot)
+        e.set_critics(sc.critics)
+        e.set_noise(*noise)
+        e.set_outputs(trajectories=True, cells=True)
+        r = e.optimize(sc.cycle)
+        res.append((r, e.get_cells(), e.get_trajectories(), e.get_costs()))
+        e.close()
+    monkeypatch.delenv("MPPI_STREAM_MIN_BATCH", raising=False)
+    (ra, ca, ta, ka), (rb, cb, tb, kb) = res
+    assert np.array_equal(ca, cb)
+    for a, b in zip(ta, tb):
+        assert np.array_equal(a, b)
+    np.testing.assert_allclose(ka, kb, rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(ra.vx, rb.vx, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(ra.wz, rb.wz, rtol=1e-4, atol=1e-6)
