@@ -255,7 +255,12 @@ mppi_status mppi_set_profiling(mppi_handle * h, int32_t enable);
 mppi_status mppi_get_profile(mppi_handle * h, float ms_out[4], uint64_t * kernel_launches_total,
                              uint64_t * h2d_bytes, uint64_t * d2h_bytes);
 
-/* ---- sharding over GPUs: one handle per rank, tiny exchanges over NCCL ---- */
+/* ---- sharding over GPUs ---- */
+/* single process: n handles (one per shard, cfg.shard_offset / shard_total set, any mix of devices) solve ONE
+ * problem; the two tiny exchanges (furthest path point + survivor flags; softmax partials) go through pinned
+ * host memory.  Every handle ends with the same control sequence; `out` is filled from hs[0]. */
+mppi_status mppi_optimize_sharded(mppi_handle ** hs, int32_t n, const mppi_cycle_in * in, mppi_cycle_out * out);
+/* one process per GPU: one handle per rank, the same exchanges as one ncclAllReduce(MAX) and one ncclAllGather */
 #define MPPI_NCCL_UNIQUE_ID_BYTES 128
 mppi_status mppi_comm_get_unique_id(uint8_t id_out[MPPI_NCCL_UNIQUE_ID_BYTES]);
 mppi_status mppi_comm_init(mppi_handle * h, const uint8_t id[MPPI_NCCL_UNIQUE_ID_BYTES], int32_t rank, int32_t nranks);

@@ -6,7 +6,7 @@ interface over that ABI) and a thin ctypes binding (``_abi``, ``api``) used by t
 """
 from . import _abi as abi  # noqa: F401
 from .api import (Cycle, Engine, MppiError, Result, circle_footprint, load_product, make_config,  # noqa: F401
-                  make_critic, make_robot)
+                  make_critic, make_robot, optimize_sharded)
 
 
 def MppiOptimizer(**cfg_kw):

@@ -335,3 +335,18 @@ class Engine:
             self.h, C.byref(cin), *[_p(a) for a in arrs], _p(costs), C.byref(fur), C.byref(fail)))
         del keep
         return costs, (None if fur.value == abi.UINT32_MAX else fur.value), bool(fail.value)
+
+
+def optimize_sharded(engines, cycle: Cycle) -> Result:
+    """mppi_optimize_sharded: the engines are shards of one problem (cfg.shard_offset / shard_total)."""
+    e0 = engines[0]
+    n = len(engines)
+    hs = (abi.H * n)(*[e.h for e in engines])
+    cin, keep = cycle.pack()
+    out, arrs = e0._out()
+    status = e0.f["optimize_sharded"](hs, n, C.byref(cin), C.byref(out))
+    del keep
+    if status != abi.MPPI_OK:
+        msgs = [e.f["last_error"](e.h).decode() for e in engines]
+        raise MppiError(f"mppi status {status}: {msgs}")
+    return Engine._result(out, arrs)

@@ -529,7 +529,8 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
     if (h->stream_layout) {
       // K3 published costs + global minimum; weights and weighted control sums over the time-major noise
       const int chunks = (h->B + kTmChunk - 1) / kTmChunk;
-      weighted_sums_tm_kernel<<<chunks, kUpdThreads, 0, h->stream>>>(reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, 0));
+      const int gy = std::max(1, std::min((3 * h->T + 3) / 4, (2 * 148 + chunks - 1) / chunks));
+      weighted_sums_tm_kernel<<<dim3(chunks, gy), kUpdThreads, 0, h->stream>>>(reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, 0));
       CUDA_TRY(h, cudaGetLastError());
       merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
         reinterpret_cast<const DevParams *>(h->d_params), h->d_partials, chunks, stride, make_bufs(h, 0),
@@ -786,7 +787,7 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   if (const char * e = std::getenv("MPPI_NO_GRAPH")) {h->use_graph = std::atoi(e) == 0;}
   {
     // batches too small to fill the GPU with one thread per trajectory keep the latency-oriented tile kernel
-    long long stream_min = 16384;
+    long long stream_min = 32768;   // measured cross-over on B200 (profiles/): below it the tile kernel wins
     if (const char * e = std::getenv("MPPI_STREAM_MIN_BATCH")) {stream_min = std::atoll(e);}
     h->stream_layout = cfg->batch_size >= stream_min;
   }
@@ -1192,6 +1193,110 @@ mppi_status mppi_get_profile(mppi_handle * h, float ms_out[4], uint64_t * kernel
   if (h2d_bytes) {*h2d_bytes = h->h2d_bytes;}
   if (d2h_bytes) {*d2h_bytes = h->d2h_bytes;}
   return MPPI_OK;
+}
+
+// Several shards of ONE optimisation problem driven from one process (one handle per shard, on any mix of
+// devices): same two exchanges as the NCCL path, carried by small async copies through pinned host memory.
+// This is what a single-process controller (the ROS plugin) uses to spread a large batch over the GPUs of a box,
+// and it lets the sharded code path run on a single GPU (two handles on one device) in the tests.
+mppi_status mppi_optimize_sharded(mppi_handle ** hs, int32_t n, const mppi_cycle_in * in, mppi_cycle_out * out)
+{
+  if (!hs || n < 1 || !in) {return MPPI_E_CONFIG;}
+  for (int i = 0; i < n; ++i) {
+    if (!hs[i]) {return MPPI_E_CONFIG;}
+    if (hs[i]->T != hs[0]->T || hs[i]->cfg.iteration_count != hs[0]->cfg.iteration_count) {
+      return fail(hs[i], MPPI_E_CONFIG, "shards must share time_steps and iteration_count");
+    }
+    if (hs[i]->comm) {return fail(hs[i], MPPI_E_CONFIG, "handle is bound to an NCCL communicator");}
+  }
+  const int T = hs[0]->T, stride = 3 * T + 2;
+  const int words = 1 + kMaxCritics;
+  std::vector<unsigned> st_host(static_cast<size_t>(n) * words);
+  std::vector<float> partial_host(static_cast<size_t>(n) * stride);
+  mppi_status s = MPPI_OK;
+  auto on = [&](int i) {cudaSetDevice(hs[i]->device); return hs[i];};
+  for (int i = 0; i < n && s == MPPI_OK; ++i) {
+    mppi_handle * h = on(i);
+    h->nranks = n;   // K3 must not finalize on its own
+    if (!h->d_gathered) {
+      if (cudaMalloc(&h->d_gathered, static_cast<size_t>(std::max(n, 8)) * stride * sizeof(float)) != cudaSuccess) {
+        h->nranks = 1;
+        return fail(h, MPPI_E_CUDA, "cudaMalloc(d_gathered)");
+      }
+    }
+    if ((s = build_params(h, in, 0, kUnset, true)) != MPPI_OK) {break;}
+    if ((s = stage_costmap(h, in->costmap)) != MPPI_OK) {break;}
+    if ((s = enqueue_uploads(h)) != MPPI_OK) {break;}
+    cudaEventRecord(h->ev0, h->stream);
+  }
+  for (int it = 0; it < hs[0]->cfg.iteration_count && s == MPPI_OK; ++it) {
+    for (int i = 0; i < n && s == MPPI_OK; ++i) {
+      mppi_handle * h = on(i);
+      s = launch_rollout(h, 0);
+      if (s == MPPI_OK && cudaMemcpyAsync(&st_host[static_cast<size_t>(i) * words], h->d_st, words * sizeof(unsigned),
+          cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) {s = fail(h, MPPI_E_CUDA, "exchange 1 D2H");}
+    }
+    // exchange 1: element-wise MAX of (furthest candidate, survivor flags)
+    for (int i = 0; i < n && s == MPPI_OK; ++i) {if (cudaStreamSynchronize(on(i)->stream) != cudaSuccess) {s = fail(hs[i], MPPI_E_CUDA, "sync");}}
+    for (int w = 0; w < words; ++w) {
+      unsigned m = 0;
+      for (int i = 0; i < n; ++i) {m = std::max(m, st_host[static_cast<size_t>(i) * words + w]);}
+      st_host[w] = m;
+    }
+    for (int i = 0; i < n && s == MPPI_OK; ++i) {
+      mppi_handle * h = on(i);
+      if (cudaMemcpyAsync(h->d_st, st_host.data(), words * sizeof(unsigned), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) {
+        s = fail(h, MPPI_E_CUDA, "exchange 1 H2D");
+        break;
+      }
+      if ((s = launch_update(h, 0, it)) != MPPI_OK) {break;}
+      const int merge_grid = (T + kMergeT - 1) / kMergeT;
+      if (h->stream_layout) {
+        const int chunks = (h->B + kTmChunk - 1) / kTmChunk;
+        const int gy = std::max(1, std::min((3 * T + 3) / 4, (2 * 148 + chunks - 1) / chunks));
+        weighted_sums_tm_kernel<<<dim3(chunks, gy), kUpdThreads, 0, h->stream>>>(reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, 0));
+        merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
+          reinterpret_cast<const DevParams *>(h->d_params), h->d_partials, chunks, stride, make_bufs(h, 0), 0, h->d_rank_partial);
+        h->launches += 2;
+      } else if (h->upd_blocks > kLastBlockMergeMax) {
+        merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
+          reinterpret_cast<const DevParams *>(h->d_params), h->d_partials, h->upd_blocks, stride, make_bufs(h, 0), 0, h->d_rank_partial);
+        h->launches++;
+      }
+      if (cudaGetLastError() != cudaSuccess) {s = fail(h, MPPI_E_CUDA, "launch");  break;}
+      if (cudaMemcpyAsync(&partial_host[static_cast<size_t>(i) * stride], h->d_rank_partial, stride * sizeof(float),
+          cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) {s = fail(h, MPPI_E_CUDA, "exchange 2 D2H");}
+    }
+    // exchange 2: every shard gets all (min, sum, weighted control sums) records and merges them redundantly
+    for (int i = 0; i < n && s == MPPI_OK; ++i) {if (cudaStreamSynchronize(on(i)->stream) != cudaSuccess) {s = fail(hs[i], MPPI_E_CUDA, "sync");}}
+    for (int i = 0; i < n && s == MPPI_OK; ++i) {
+      mppi_handle * h = on(i);
+      if (cudaMemcpyAsync(h->d_gathered, partial_host.data(), static_cast<size_t>(n) * stride * sizeof(float), cudaMemcpyHostToDevice,
+          h->stream) != cudaSuccess) {s = fail(h, MPPI_E_CUDA, "exchange 2 H2D"); break;}
+      merge_finalize_kernel<<<(T + kMergeT - 1) / kMergeT, kUpdThreads, 0, h->stream>>>(
+        reinterpret_cast<const DevParams *>(h->d_params), h->d_gathered, n, stride, make_bufs(h, 0), 1, nullptr);
+      h->launches++;
+      if (cudaGetLastError() != cudaSuccess) {s = fail(h, MPPI_E_CUDA, "launch"); break;}
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    mppi_handle * h = on(i);
+    if (s == MPPI_OK) {
+      if (cudaMemcpyAsync(h->h_out, h->d_out, sizeof(float) * (3 * T + 2), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) {
+        s = fail(h, MPPI_E_CUDA, "result D2H");
+      }
+      cudaEventRecord(h->ev1, h->stream);
+    }
+    h->cycle_uploaded = true;
+  }
+  mppi_status first = s;
+  for (int i = 0; i < n; ++i) {
+    mppi_handle * h = on(i);
+    const mppi_status f = finish_optimize(h, (i == 0 && s == MPPI_OK) ? out : nullptr);
+    if (f != MPPI_OK && first == MPPI_OK) {first = f;}
+    h->nranks = 1;
+  }
+  return first;
 }
 
 // ---- sharding ------------------------------------------------------------------------------------

@@ -1344,10 +1344,14 @@ __global__ void __launch_bounds__(kUpdThreads) weighted_sums_tm_kernel(const Dev
       return a;
     };
   ssum = block_sum(ssum);
-  if (tid == 0) {part[0] = gm; part[1] = ssum;}
+  if (tid == 0 && blockIdx.y == 0) {part[0] = gm; part[1] = ssum;}
+  // the rows are split over gridDim.y so that small chunk counts still fill the machine
+  const int rows_total = 3 * T;
+  const int rows_per = ((rows_total + static_cast<int>(gridDim.y) - 1) / static_cast<int>(gridDim.y) + 3) & ~3;
+  const int c_begin = blockIdx.y * rows_per, c_end = min(rows_total, c_begin + rows_per);
   // rows in batches of 4: 16 independent 16-byte loads in flight per thread, one reduction round per batch
   __shared__ float s_rows[kUpdThreads / 32][4];
-  for (int c0 = 0; c0 < 3 * T; c0 += 4) {
+  for (int c0 = c_begin; c0 < c_end; c0 += 4) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -1380,7 +1384,7 @@ __global__ void __launch_bounds__(kUpdThreads) weighted_sums_tm_kernel(const Dev
       for (int k = 0; k < 4; ++k) {s_rows[warp][k] = acc[k];}
     }
     __syncthreads();
-    if (tid < 4 && c0 + tid < 3 * T) {
+    if (tid < 4 && c0 + tid < c_end) {
       float a = 0.0f;
 #pragma unroll
       for (int wv = 0; wv < kUpdThreads / 32; ++wv) {a += s_rows[wv][tid];}
