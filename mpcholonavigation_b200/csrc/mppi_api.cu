@@ -412,6 +412,14 @@ mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, un
   return MPPI_OK;
 }
 
+// gridDim.y of weighted_sums_tm_kernel: enough row groups to put ~3 blocks on every SM, but at least one row per warp
+int weighted_sums_row_groups(int T, int chunks)
+{
+  const int rows = 3 * T, warps = kWsThreads / 32;
+  const int want = (3 * 148 + chunks - 1) / chunks;
+  return std::max(1, std::min((rows + warps - 1) / warps, want));
+}
+
 int pick_segments(const mppi_handle * h)
 {
   if (h->segments_override > 0) {return h->segments_override;}
@@ -528,9 +536,9 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
     const int merge_grid = (h->T + kMergeT - 1) / kMergeT;
     if (h->stream_layout) {
       // K3 published costs + global minimum; weights and weighted control sums over the time-major noise
-      const int chunks = (h->B + kTmChunk - 1) / kTmChunk;
-      const int gy = std::max(1, std::min((3 * h->T + 3) / 4, (2 * 148 + chunks - 1) / chunks));
-      weighted_sums_tm_kernel<<<dim3(chunks, gy), kUpdThreads, 0, h->stream>>>(reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, 0));
+      const int chunks = (h->B + kWsChunk - 1) / kWsChunk;
+      const int gy = weighted_sums_row_groups(h->T, chunks);
+      weighted_sums_tm_kernel<<<dim3(chunks, gy), kWsThreads, 0, h->stream>>>(reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, 0));
       CUDA_TRY(h, cudaGetLastError());
       merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
         reinterpret_cast<const DevParams *>(h->d_params), h->d_partials, chunks, stride, make_bufs(h, 0),
@@ -1252,9 +1260,9 @@ mppi_status mppi_optimize_sharded(mppi_handle ** hs, int32_t n, const mppi_cycle
       if ((s = launch_update(h, 0, it)) != MPPI_OK) {break;}
       const int merge_grid = (T + kMergeT - 1) / kMergeT;
       if (h->stream_layout) {
-        const int chunks = (h->B + kTmChunk - 1) / kTmChunk;
-        const int gy = std::max(1, std::min((3 * T + 3) / 4, (2 * 148 + chunks - 1) / chunks));
-        weighted_sums_tm_kernel<<<dim3(chunks, gy), kUpdThreads, 0, h->stream>>>(reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, 0));
+        const int chunks = (h->B + kWsChunk - 1) / kWsChunk;
+        const int gy = weighted_sums_row_groups(T, chunks);
+        weighted_sums_tm_kernel<<<dim3(chunks, gy), kWsThreads, 0, h->stream>>>(reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, 0));
         merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
           reinterpret_cast<const DevParams *>(h->d_params), h->d_partials, chunks, stride, make_bufs(h, 0), 0, h->d_rank_partial);
         h->launches += 2;

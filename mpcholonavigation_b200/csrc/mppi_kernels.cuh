@@ -1303,93 +1303,85 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
   }
 }
 
-// K3c (stream layout): softmax weights and weighted control sums over time-major noise [T][B].
-// One block owns kTmChunk consecutive trajectories; every thread owns 4 groups of 4 consecutive b (16-byte loads,
-// coalesced along b) and keeps their weights in registers; each (plane, t) row is reduced with warp shuffles.
-// The record written is [m = global min, s, W...] so that merge_finalize_kernel merges it like any other partial.
-constexpr int kTmGroups = 4;
-constexpr int kTmChunk = kUpdThreads * 4 * kTmGroups;   // 2048 trajectories per block
+// K3c (stream layout): softmax weights and weighted control sums over time-major noise [T][B]; a GEMV
+// W[c] = sum_b w_b * (cs[c] + noise[c][b]) that is pure HBM streaming (12 B per rollout step).
+// One block owns kWsChunk consecutive trajectories.  Every warp keeps the weights of the WHOLE chunk in
+// registers (lane owns kWsVec groups of 4 consecutive b: 16-byte loads, coalesced along b) and walks the
+// (plane, t) rows warp, warp + 8, ...: kWsVec independent 16-byte loads in flight per lane, one shuffle
+// reduction per row, no shared memory, no barriers.  The rows are split over gridDim.y so that small chunk
+// counts still fill the machine.  The record written per chunk is [m = global min, s, W...] so that
+// merge_finalize_kernel merges it like any other partial.
+constexpr int kWsThreads = 256;
+constexpr int kWsVec = 8;
+constexpr int kWsChunk = 32 * 4 * kWsVec;   // 1024 trajectories per block
 
-__global__ void __launch_bounds__(kUpdThreads) weighted_sums_tm_kernel(const DevParams * __restrict__ Pg, DevBuffers bufs)
+__global__ void __launch_bounds__(kWsThreads) weighted_sums_tm_kernel(const DevParams * __restrict__ Pg, DevBuffers bufs)
 {
-  __shared__ float s_part[kUpdThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = Pg->T, B = Pg->B;
   const float inv_temp = 1.0f / Pg->temperature;
   const float gm = bufs.st->global_min;
   const int stride = 3 * T + 2;
   float * part = bufs.partials + static_cast<size_t>(blockIdx.x) * stride;
-  const int b0 = blockIdx.x * kTmChunk;
-  const bool vec = (B & 3) == 0;
-  // weights of my 16 trajectories
-  float w[kTmGroups][4];
+  const int b0 = blockIdx.x * kWsChunk + lane * 4;
+  const bool full = (B & 3) == 0 && blockIdx.x * kWsChunk + kWsChunk <= B;   // whole chunk in range, rows 16-byte aligned
+  float w[kWsVec][4];
   float ssum = 0.0f;
 #pragma unroll
-  for (int gidx = 0; gidx < kTmGroups; ++gidx) {
+  for (int i = 0; i < kWsVec; ++i) {
+    const int b = b0 + i * 128;
+    float c[4];
+    if (full) {
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(bufs.costs + b));
+      c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {c[j] = b + j < B ? __ldg(bufs.costs + b + j) : 0.0f;}
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int b = b0 + (gidx * kUpdThreads + tid) * 4 + j;
-      w[gidx][j] = b < B ? expf(-(bufs.costs[b] - gm) * inv_temp) : 0.0f;
-      ssum += w[gidx][j];
+      w[i][j] = (full || b + j < B) ? expf(-(c[j] - gm) * inv_temp) : 0.0f;
+      ssum += w[i][j];
     }
   }
-  auto block_sum = [&](float v) -> float {
-      v = warp_sum(v);
-      __syncthreads();
-      if (lane == 0) {s_part[warp] = v;}
-      __syncthreads();
-      float a = 0.0f;
-#pragma unroll
-      for (int k = 0; k < kUpdThreads / 32; ++k) {a += s_part[k];}
-      return a;
-    };
-  ssum = block_sum(ssum);
-  if (tid == 0 && blockIdx.y == 0) {part[0] = gm; part[1] = ssum;}
-  // the rows are split over gridDim.y so that small chunk counts still fill the machine
+  if (blockIdx.y == 0 && warp == 0) {
+    ssum = warp_sum(ssum);
+    if (lane == 0) {part[0] = gm; part[1] = ssum;}
+  }
   const int rows_total = 3 * T;
-  const int rows_per = ((rows_total + static_cast<int>(gridDim.y) - 1) / static_cast<int>(gridDim.y) + 3) & ~3;
+  const int rows_per = (rows_total + static_cast<int>(gridDim.y) - 1) / static_cast<int>(gridDim.y);
   const int c_begin = blockIdx.y * rows_per, c_end = min(rows_total, c_begin + rows_per);
-  // rows in batches of 4: 16 independent 16-byte loads in flight per thread, one reduction round per batch
-  __shared__ float s_rows[kUpdThreads / 32][4];
-  for (int c0 = c_begin; c0 < c_end; c0 += 4) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = c_begin + warp; c < c_end; c += kWsThreads / 32) {
+    const int plane = c / T, t = c - plane * T;
+    const float * __restrict__ row = (plane == 0 ? bufs.in_a : (plane == 1 ? bufs.in_b : bufs.in_c)) + static_cast<size_t>(t) * B + b0;
+    const float cs_t = bufs.cs[c];
+    float acc0 = 0.0f, acc1 = 0.0f;
+    if (full) {
+      float4 v[kWsVec];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = min(c0 + k, 3 * T - 1);
-      const int plane = c / T, t = c - plane * T;
-      const float * __restrict__ row = (plane == 0 ? bufs.in_a : (plane == 1 ? bufs.in_b : bufs.in_c)) + static_cast<size_t>(t) * B;
-      const float cs_t = bufs.cs[c];
+      for (int i = 0; i < kWsVec; ++i) {v[i] = __ldg(reinterpret_cast<const float4 *>(row + i * 128));}
 #pragma unroll
-      for (int gidx = 0; gidx < kTmGroups; ++gidx) {
-        const int b = b0 + (gidx * kUpdThreads + tid) * 4;
-        if (vec && b + 3 < B) {
-          const float4 v = __ldg(reinterpret_cast<const float4 *>(row + b));
-          acc[k] = fmaf(w[gidx][0], __fadd_rn(cs_t, v.x), acc[k]);
-          acc[k] = fmaf(w[gidx][1], __fadd_rn(cs_t, v.y), acc[k]);
-          acc[k] = fmaf(w[gidx][2], __fadd_rn(cs_t, v.z), acc[k]);
-          acc[k] = fmaf(w[gidx][3], __fadd_rn(cs_t, v.w), acc[k]);
-        } else {
+      for (int i = 0; i < kWsVec; i += 2) {
+        acc0 = fmaf(w[i][0], __fadd_rn(cs_t, v[i].x), acc0);
+        acc0 = fmaf(w[i][1], __fadd_rn(cs_t, v[i].y), acc0);
+        acc0 = fmaf(w[i][2], __fadd_rn(cs_t, v[i].z), acc0);
+        acc0 = fmaf(w[i][3], __fadd_rn(cs_t, v[i].w), acc0);
+        acc1 = fmaf(w[i + 1][0], __fadd_rn(cs_t, v[i + 1].x), acc1);
+        acc1 = fmaf(w[i + 1][1], __fadd_rn(cs_t, v[i + 1].y), acc1);
+        acc1 = fmaf(w[i + 1][2], __fadd_rn(cs_t, v[i + 1].z), acc1);
+        acc1 = fmaf(w[i + 1][3], __fadd_rn(cs_t, v[i + 1].w), acc1);
+      }
+    } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (b + j < B) {acc[k] = fmaf(w[gidx][j], __fadd_rn(cs_t, __ldg(row + b + j)), acc[k]);}
-          }
+      for (int i = 0; i < kWsVec; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (b0 + i * 128 + j < B) {acc0 = fmaf(w[i][j], __fadd_rn(cs_t, __ldg(row + i * 128 + j)), acc0);}
         }
       }
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {acc[k] = warp_sum(acc[k]);}
-    __syncthreads();
-    if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {s_rows[warp][k] = acc[k];}
-    }
-    __syncthreads();
-    if (tid < 4 && c0 + tid < c_end) {
-      float a = 0.0f;
-#pragma unroll
-      for (int wv = 0; wv < kUpdThreads / 32; ++wv) {a += s_rows[wv][tid];}
-      part[2 + c0 + tid] = a;
-    }
+    const float a = warp_sum(acc0 + acc1);
+    if (lane == 0) {part[2 + c] = a;}
   }
 }
 
