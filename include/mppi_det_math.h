@@ -89,11 +89,12 @@ MPPI_HD void mppi_det_sincosf(float x, float * s_out, float * c_out)
   float pc = MPPI_FFMA(2.443315711809948e-5f, z, -1.388731625493765e-3f);
   pc = MPPI_FFMA(pc, z, 4.166664568298827e-2f);
   const float cr = MPPI_FFMA(MPPI_FMUL(pc, z), z, MPPI_FFMA(-0.5f, z, 1.0f));
-  switch (q & 3) {
-    case 0: *s_out = sr; *c_out = cr; break;
-    case 1: *s_out = cr; *c_out = -sr; break;
-    case 2: *s_out = -sr; *c_out = -cr; break;
-    default: *s_out = -cr; *c_out = sr; break;
+  /* quadrant fix-up, branch-free: q&3 = 0: (sr, cr)  1: (cr, -sr)  2: (-sr, -cr)  3: (-cr, sr) */
+  {
+    const float s0 = (q & 1) ? cr : sr;
+    const float c0 = (q & 1) ? sr : cr;
+    *s_out = (q & 2) ? -s0 : s0;
+    *c_out = ((q + 1) & 2) ? -c0 : c0;
   }
 }
 

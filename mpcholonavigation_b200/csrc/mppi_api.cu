@@ -108,11 +108,13 @@ struct mppi_handle
   bool spilled_traj{false}, spilled_cells{false}, have_rows{false};
   DevParams last;   // host copy of the last uploaded record
   int segments_override{0};
+  int stream_threads_override{0};
   bool stream_layout{false};   // large batches: time-major noise + thread-per-trajectory K2 + GEMV-style weighted sums
   int upd_blocks{0};
   // CUDA graphs of the steady-state cycle: [0] kernels + D2H (resident inputs), [1] H2D + kernels + D2H
   cudaGraphExec_t gexec[2]{nullptr, nullptr};
   size_t gkey_params[2]{0, 0}, gkey_costmap[2]{0, 0};
+  unsigned gkey_inst[2]{0, 0};
   bool use_graph{true};
   size_t costmap_bytes{0}, params_copy_bytes{0};
   int upd_rows{kUpdThreads};   // trajectories per block of the update kernel
@@ -262,7 +264,15 @@ mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, un
   p.goal_yaw = in->path_yaw[N - 1];
   p.size_x = in->costmap.size_x; p.size_y = in->costmap.size_y;
   p.res = in->costmap.resolution; p.ox = in->costmap.origin_x; p.oy = in->costmap.origin_y;
-  p.inv_res = 1.0 / p.res;
+  // fp32 filter of worldToMap (mppi_device.cuh world_to_cell_fast): operands and rigorous error bounds in cells
+  p.cell_oxf = static_cast<float>(p.ox);
+  p.cell_oyf = static_cast<float>(p.oy);
+  p.cell_invf = static_cast<float>(1.0 / p.res);
+  {
+    const double u = 5.9604644775390625e-08;   // 2^-24
+    p.cell_eps_x = static_cast<float>(((static_cast<double>(p.size_x) + 2.0) * 3.5 + std::fabs(p.ox) / p.res * 1.1) * u + 1.0e-6);
+    p.cell_eps_y = static_cast<float>(((static_cast<double>(p.size_y) + 2.0) * 3.5 + std::fabs(p.oy) / p.res * 1.1) * u + 1.0e-6);
+  }
 
   // path arrays behind the struct: x, y, yaw, arc-length prefix D (path_align_critic.cpp:83-90), PathAngle gate bytes
   float * tail = reinterpret_cast<float *>(h->h_params + sizeof(DevParams));
@@ -486,12 +496,64 @@ mppi_status enqueue_uploads(mppi_handle * h)
   return MPPI_OK;
 }
 
+// the exact set of features this cycle's record asks of the stream kernel (StreamFeature bits)
+unsigned stream_feature_need(const DevParams & p)
+{
+  unsigned need = 0;
+  if (p.holonomic) {need |= SF_HOL;}
+  if (p.model == MPPI_MODEL_ACKERMANN) {need |= SF_ACKER;}
+  if (p.constraint.on) {need |= SF_CON;}
+  if (p.forward.on) {need |= SF_FWD;}
+  if (p.twirl.on) {need |= SF_TWIRL;}
+  if (p.deadband.on) {need |= SF_DB;}
+  if (p.goal.on) {need |= SF_GOAL;}
+  if (p.goal_angle.on) {need |= SF_GANG;}
+  if (p.cost.on) {need |= SF_COST;}
+  if (p.obst.on) {need |= SF_OBST;}
+  if ((p.cost.on && p.cost_fp) || (p.obst.on && p.obst_fp)) {need |= SF_FOOTPRINT;}
+  if (p.want_cells || p.spill_traj) {need |= SF_SPILL;}
+  return need;
+}
+
+// Compiled instances of the stream kernel.  The exact ones are straight-line code for one feature set (the deployed
+// Omni critic list away from the goal, with and without footprint costs; the Obstacles-only benchmark config);
+// anything else runs the generic instance, which tests the per-cycle flags at run time.
+constexpr unsigned kSfOmniDefault = SF_HOL | SF_CON | SF_FWD | SF_TWIRL | SF_COST;
+constexpr unsigned kSfOmniDefaultFp = kSfOmniDefault | SF_FOOTPRINT;
+constexpr unsigned kSfObstaclesFp = SF_HOL | SF_OBST | SF_FOOTPRINT;
+
+unsigned pick_stream_instance(unsigned need)
+{
+  if (need == kSfOmniDefault || need == kSfOmniDefaultFp || need == kSfObstaclesFp) {return need;}
+  return SF_ALL;
+}
+
+int stream_block_threads(const mppi_handle * h)
+{
+  if (h->stream_threads_override > 0) {return h->stream_threads_override;}
+  // fewer threads per block below ~4 full blocks per SM: same number of warps, spread evenly over the 148 SMs
+  return h->B >= 148 * 4 * kStreamThreads ? kStreamThreads : 64;
+}
+
+template<unsigned F, bool kExact>
+void launch_stream_instance(mppi_handle * h, int mode)
+{
+  const int nthr = stream_block_threads(h);
+  const int Tp = ((h->T + kStreamChunk - 1) / kStreamChunk) * kStreamChunk;
+  const size_t smem = kHotBytes + sizeof(float) * 3 * Tp;
+  rollout_score_stream_kernel<F, kExact><<<(h->B + nthr - 1) / nthr, nthr, smem, h->stream>>>(
+    reinterpret_cast<const DevParams *>(h->d_params), h->d_costmap, make_bufs(h, mode));
+}
+
 mppi_status launch_rollout(mppi_handle * h, int mode)
 {
   if (mode == 0 && h->stream_layout) {
-    const size_t smem = kHotBytes + sizeof(float) * 3 * h->T;
-    rollout_score_stream_kernel<<<(h->B + kStreamThreads - 1) / kStreamThreads, kStreamThreads, smem, h->stream>>>(
-      reinterpret_cast<const DevParams *>(h->d_params), h->d_costmap, make_bufs(h, mode));
+    switch (pick_stream_instance(stream_feature_need(h->last))) {
+      case kSfOmniDefault: launch_stream_instance<kSfOmniDefault, true>(h, mode); break;
+      case kSfOmniDefaultFp: launch_stream_instance<kSfOmniDefaultFp, true>(h, mode); break;
+      case kSfObstaclesFp: launch_stream_instance<kSfObstaclesFp, true>(h, mode); break;
+      default: launch_stream_instance<SF_ALL, false>(h, mode); break;
+    }
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
     return MPPI_OK;
@@ -579,7 +641,10 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
   CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
   if (graph_ok) {
     const int slot = with_upload ? 1 : 0;
-    if (h->gexec[slot] && (h->gkey_params[slot] != h->params_copy_bytes || h->gkey_costmap[slot] != h->costmap_bytes)) {
+    const unsigned inst = h->stream_layout ? pick_stream_instance(stream_feature_need(h->last)) : 0u;
+    if (h->gexec[slot] && (h->gkey_params[slot] != h->params_copy_bytes || h->gkey_costmap[slot] != h->costmap_bytes ||
+      h->gkey_inst[slot] != inst))
+    {
       cudaGraphExecDestroy(h->gexec[slot]);
       h->gexec[slot] = nullptr;
     }
@@ -602,6 +667,7 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
         if (ie != cudaSuccess) {cudaGetLastError(); h->gexec[slot] = nullptr; h->use_graph = false;}
         h->gkey_params[slot] = h->params_copy_bytes;
         h->gkey_costmap[slot] = h->costmap_bytes;
+        h->gkey_inst[slot] = inst;
       }
     }
     if (h->gexec[slot]) {
@@ -792,6 +858,9 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   h->cur = h->base;
   std::memset(&h->robot, 0, sizeof(h->robot));
   if (const char * e = std::getenv("MPPI_SEGMENTS")) {h->segments_override = std::atoi(e);}
+  if (const char * e = std::getenv("MPPI_STREAM_THREADS")) {
+    h->stream_threads_override = std::max(32, std::min(kStreamThreads, (std::atoi(e) / 32) * 32));
+  }
   if (const char * e = std::getenv("MPPI_NO_GRAPH")) {h->use_graph = std::atoi(e) == 0;}
   {
     // batches too small to fill the GPU with one thread per trajectory keep the latency-oriented tile kernel
@@ -811,11 +880,16 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   CUDA_TRY(h, cudaEventCreate(&h->ev1));
   for (auto & e : h->pev) {CUDA_TRY(h, cudaEventCreate(&e));}
   const size_t B = h->B, T = h->T, plane = B * T * sizeof(float);
+  // kNoisePadRows zeroed rows behind every noise plane: the stream kernel prefetches past the horizon without a clamp
+  const size_t noise_plane = plane + static_cast<size_t>(kNoisePadRows) * B * sizeof(float);
+  if (h->stream_layout && (T + kNoisePadRows) * B >= (1ull << 32)) {
+    return bad("batch_size * time_steps too large for the 32-bit offsets of the stream layout");
+  }
   for (int i = 0; i < 3; ++i) {
-    CUDA_TRY(h, cudaMalloc(&h->d_noise[i], plane));
+    CUDA_TRY(h, cudaMalloc(&h->d_noise[i], noise_plane));
     CUDA_TRY(h, cudaMalloc(&h->d_samples[i], plane));
     CUDA_TRY(h, cudaMalloc(&h->d_spill[i], plane));
-    CUDA_TRY(h, cudaMemsetAsync(h->d_noise[i], 0, plane, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_noise[i], 0, noise_plane, h->stream));
   }
   CUDA_TRY(h, cudaMalloc(&h->d_cells, B * T * sizeof(int)));
   CUDA_TRY(h, cudaMalloc(&h->d_params, kParamsCapacity));

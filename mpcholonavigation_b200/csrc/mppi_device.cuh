@@ -85,7 +85,8 @@ struct DevParams
   // offsets (in floats) of the path arrays that follow this struct in the same buffer
   int off_path_x, off_path_y, off_path_yaw, off_path_D, off_gate;
   int fp_n;
-  double inv_res;                            // 1 / res, used only by the exactness-checked fast path of world_to_cell
+  float cell_oxf, cell_oyf, cell_invf;       // fp32 filter of worldToMap (world_to_cell_fast): fl32(ox), fl32(oy), fl32(1/res)
+  float cell_eps_x, cell_eps_y;              // and its error bounds in cells
   // ---- everything above is the "hot" part every CTA copies into shared memory (kHotBytes) ----
   double fp_x[MPPI_MAX_FOOTPRINT], fp_y[MPPI_MAX_FOOTPRINT];   // footprint polygon
   // obstacle-critic look-up tables indexed by the byte cost: [0] point cost, [1] footprint cost
@@ -131,36 +132,51 @@ __device__ __forceinline__ int world_to_cell(
   return static_cast<int>(my * size_x + mx);
 }
 
-// One coordinate of worldToMap with the IEEE division replaced by a multiplication where that is provably
-// harmless: q' = d * (1/res) is within a few ulp of the correctly rounded quotient q = d / res, so
-// trunc(q') == trunc(q) unless q' sits within `eps` of an integer; only then the true division is evaluated.
-// The result (cell index or off-map) is therefore identical to the reference arithmetic, bit for bit.
-__device__ __forceinline__ bool axis_cell_exact(double d, double res, double inv_res, unsigned size, unsigned & m)
+// worldToMap for a rollout pose, filtered: the cell is first computed in fp32,
+//   qf = fl32(fl32(xf - fl32(ox)) * fl32(1/res)),
+// whose distance to the reference's fp64 quotient Q = fl64(fl64(double(xf) - ox) / res) is bounded by
+//   |qf - Q| <= |Q| * 3.01 * 2^-24 + |ox| / res * 2^-24 * 1.001   (three fp32 roundings + the rounding of ox),
+// a bound the host evaluates per cycle as cell_eps_{x,y} (with margin, build_params).  If qf is farther than
+// that from every integer, floor(qf) == trunc(Q) and "qf < 0" == "wx < ox", so the fp32 answer IS the
+// reference's answer; otherwise (a pose within ~1e-4 cell of a cell edge, or outside the fp32 trick's range)
+// the reference's own fp64 arithmetic decides (world_to_cell_slow).  Bit-exact by construction, ~16 fp32
+// instructions instead of ~55 fp64/conversion instructions per pose.
+struct CellGrid
 {
-  // d >= 0 is guaranteed by the caller (wx >= ox)
-  double q = __dmul_rn(d, inv_res);
-  if (!(q < 2147483000.0)) {return false;}                 // far off-map (also catches NaN)
-  int qi = __double2int_rz(q);
-  const double frac = q - static_cast<double>(qi);
-  const double eps = __dmul_rn(q, 1.0e-14) + 1.0e-300;     // >> 4 ulp(q), << cell size
-  if (frac < eps || frac > 1.0 - eps) {
-    q = __ddiv_rn(d, res);                                 // rare: decide with the reference's own division
-    if (!(q < static_cast<double>(size))) {return false;}
-    qi = __double2int_rz(q);
-  }
-  m = static_cast<unsigned>(qi);
-  return m < size;
+  float oxf, oyf, invf, eps_x, eps_y;
+  unsigned size_x, size_y;
+};
+
+__device__ __noinline__ int world_to_cell_slow(float xf, float yf, const double * __restrict__ geom, unsigned size_x, unsigned size_y)
+{
+  // geom = &DevParams::res = {res, ox, oy}
+  unsigned mx, my;
+  return world_to_cell(static_cast<double>(xf), static_cast<double>(yf), geom[1], geom[2], geom[0], size_x, size_y, mx, my);
 }
 
-__device__ __forceinline__ int world_to_cell_fast(
-  float xf, float yf, double ox, double oy, double res, double inv_res, unsigned size_x, unsigned size_y)
+// round-to-nearest-even integer of q (|q| < 2^22) without conversion instructions: r = rint(q), i = int(r)
+__device__ __forceinline__ void rint_magic(float q, float & r, int & i)
 {
-  const double wx = xf, wy = yf;
-  if (wx < ox || wy < oy) {return -1;}
-  unsigned mx, my;
-  if (!axis_cell_exact(wx - ox, res, inv_res, size_x, mx)) {return -1;}
-  if (!axis_cell_exact(wy - oy, res, inv_res, size_y, my)) {return -1;}
-  return static_cast<int>(my * size_x + mx);
+  const float t = __fadd_rn(q, 12582912.0f);          // 1.5 * 2^23: the add rounds q to an integer
+  r = __fsub_rn(t, 12582912.0f);                      // exact
+  i = __float_as_int(t) - 0x4B400000;
+}
+
+__device__ __forceinline__ int world_to_cell_fast(float xf, float yf, const CellGrid & cg, const double * __restrict__ geom)
+{
+  const float qx = __fmul_rn(__fsub_rn(xf, cg.oxf), cg.invf);
+  const float qy = __fmul_rn(__fsub_rn(yf, cg.oyf), cg.invf);
+  float rx, ry;
+  int ix, iy;
+  rint_magic(qx, rx, ix);
+  rint_magic(qy, ry, iy);
+  const float dx = __fsub_rn(qx, rx), dy = __fsub_rn(qy, ry);   // exact, in [-0.5, 0.5]
+  // near a cell edge, outside the magic-number range, or NaN: the reference's fp64 arithmetic decides
+  const bool sure = fabsf(dx) > cg.eps_x && fabsf(dy) > cg.eps_y && fabsf(qx) < 4.0e6f && fabsf(qy) < 4.0e6f;
+  if (!sure) {return world_to_cell_slow(xf, yf, geom, cg.size_x, cg.size_y);}
+  const int mx = ix - (dx < 0.0f ? 1 : 0), my = iy - (dy < 0.0f ? 1 : 0);   // floor
+  if (static_cast<unsigned>(mx) >= cg.size_x || static_cast<unsigned>(my) >= cg.size_y) {return -1;}
+  return my * static_cast<int>(cg.size_x) + mx;
 }
 
 // FootprintCollisionChecker::lineCost over nav2_util::LineIterator (integer Bresenham, both ends included)

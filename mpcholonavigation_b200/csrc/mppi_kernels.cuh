@@ -20,6 +20,8 @@
 // summation order, and it is what makes the costmap cell indices bit-exact against the CPU oracle.
 // Everything else (sincos, costmap gathers, critic terms) is evaluated in parallel over (trajectory, t).
 #pragma once
+#include <type_traits>
+
 #include "mppi_device.cuh"
 
 namespace mppi
@@ -359,8 +361,9 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
     const bool cost_fp = p.cost_fp != 0, ob_fp = p.obst_fp != 0;
     const bool cost_near_goal = p.cost_near_goal != 0, ob_near_goal = p.obst_near_goal != 0, ob_rep_on = p.obst_repulsion_enabled != 0;
     const float cost_pic = p.cost_possibly_inscribed, ob_pic = p.obst_possibly_inscribed, cost_critical = p.cost_critical;
-    const double gx = p.goal_x, gy = p.goal_y, ox = p.ox, oy = p.oy, res = p.res, inv_res = p.inv_res;
+    const double gx = p.goal_x, gy = p.goal_y, ox = p.ox, oy = p.oy, res = p.res;
     const unsigned size_x = p.size_x, size_y = p.size_y;
+    const CellGrid cg = {p.cell_oxf, p.cell_oyf, p.cell_invf, p.cell_eps_x, p.cell_eps_y, size_x, size_y};
     const float goal_yaw = p.goal_yaw;
     const int step = p.sample_step;
     int next_sample = T, sample_k = 0;
@@ -381,7 +384,7 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
         a_gang += static_cast<float>(fabs(normalize_angle_d(static_cast<double>(__fsub_rn(goal_yaw, s_yaw[o])))));
       }
       if (need_cell) {
-        const int cell = world_to_cell_fast(px, py, ox, oy, res, inv_res, size_x, size_y);
+        const int cell = world_to_cell_fast(px, py, cg, &p.res);
         if (want_cells) {bufs.spill_cells[g] = cell;}
         if ((cost_on && !cost_hit) || (ob_on && !ob_hit)) {
           const int pose_cost = cell < 0 ? NO_INFORMATION : __ldg(cm + cell);
@@ -533,139 +536,229 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
 // ---------------------------------------------------------------------------------------------------
 // K2, stream variant (large batches): one thread owns one trajectory for the whole horizon and everything
 // lives in registers.  The noise planes are stored TIME-MAJOR [T][B] for this variant, so lane == trajectory
-// reads are coalesced straight from HBM/L2 with no shared-memory staging, no transposes and no barriers; the
-// next steps' noise is prefetched ahead of the dependent chain.  Arithmetic (order of the three cumulative
-// sums, non-contractable fp32 ops, fp64 index math) is identical to the tile variant and to the oracle.
+// reads are coalesced straight from HBM/L2 with no shared-memory staging, no transposes and no barriers.
+// The horizon is walked in chunks of kStreamChunk steps; inside a chunk the work is phased so that the
+// expensive, mutually independent parts (sincos of the lagged yaw, fp64 cell index, costmap byte gather)
+// of the chunk's steps are issued back to back (instruction-level parallelism within one thread), while the
+// three cumulative sums stay strictly sequential in t.  Arithmetic (order of the sums, non-contractable fp32
+// ops, fp64 index math) is identical to the tile variant and to the oracle.
+// The template mask removes whole critic families at compile time (smaller code, fewer registers); every
+// family that is compiled in is still gated by its per-cycle runtime flag.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kStreamThreads = 128;
-constexpr int kStreamPrefetch = 4;     // noise rows in flight per thread
+enum StreamFeature : unsigned
+{
+  SF_HOL = 1u,          // holonomic (Omni): vy terms
+  SF_ACKER = 2u,        // Ackermann term of the Constraint critic
+  SF_CON = 4u,          // ConstraintCritic
+  SF_FWD = 8u,          // PreferForwardCritic
+  SF_TWIRL = 16u,       // TwirlingCritic
+  SF_DB = 32u,          // VelocityDeadbandCritic
+  SF_GOAL = 64u,        // GoalCritic
+  SF_GANG = 128u,       // GoalAngleCritic
+  SF_COST = 256u,       // CostCritic
+  SF_OBST = 512u,       // ObstaclesCritic
+  SF_FOOTPRINT = 1024u, // footprint-cost mode of either costmap critic
+  SF_SPILL = 2048u,     // trajectories / cell indices written out
+  SF_ALL = 4095u
+};
 
-__global__ void __launch_bounds__(kStreamThreads, 4) rollout_score_stream_kernel(
+constexpr int kStreamThreads = 128;    // upper bound of the block size (the host may launch fewer threads per block)
+#ifndef MPPI_STREAM_CHUNK
+#define MPPI_STREAM_CHUNK 4
+#endif
+constexpr int kStreamChunk = MPPI_STREAM_CHUNK;   // steps per phase group == noise rows in flight per thread
+constexpr int kNoisePadRows = 8;       // rows allocated behind every noise plane so that the prefetch needs no clamp
+static_assert(kStreamChunk <= kNoisePadRows, "prefetch reads up to kStreamChunk rows past the horizon");
+#ifndef MPPI_STREAM_MIN_BLOCKS
+#define MPPI_STREAM_MIN_BLOCKS 4
+#endif
+
+// sqrt for cost terms (1e-4 tolerance): one MUFU instead of the IEEE sequence
+__device__ __forceinline__ float sqrt_approx(float v)
+{
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+// kExact: the mask IS the set of active features (no runtime flag tests inside the loop); otherwise the mask is an
+// upper bound and every feature is still gated by its per-cycle runtime flag (generic instance).
+template<unsigned F, bool kExact>
+__global__ void __launch_bounds__(kStreamThreads, MPPI_STREAM_MIN_BLOCKS) rollout_score_stream_kernel(
   const DevParams * __restrict__ P, const uint8_t * __restrict__ cm, DevBuffers bufs)
 {
   extern __shared__ float smem[];
   const int tid = threadIdx.x;
+  const int nthr = blockDim.x;
   float * s_hot = smem;
-  load_hot_params(s_hot, P, tid, kStreamThreads);
+  load_hot_params(s_hot, P, tid, nthr);
   __syncthreads();
   const DevParams & p = *reinterpret_cast<const DevParams *>(s_hot);
   const int T = p.T, B = p.B;
-  float * s_cs = s_hot + kHotFloats;   // [3][T]
-  for (int i = tid; i < 3 * T; i += kStreamThreads) {s_cs[i] = bufs.cs[i];}
+  const int Tp = ((T + kStreamChunk - 1) / kStreamChunk) * kStreamChunk;   // horizon padded to whole chunks
+  float * s_cs = s_hot + kHotFloats;   // [3][Tp], zero padded
+  for (int i = tid; i < 3 * Tp; i += nthr) {
+    const int plane = i / Tp, t = i - plane * Tp;
+    s_cs[i] = t < T ? bufs.cs[plane * T + t] : 0.0f;
+  }
   __syncthreads();
 
-  const int b = blockIdx.x * kStreamThreads + tid;
+  const int b = blockIdx.x * nthr + tid;
   const bool live = b < B;
-  const int bb = live ? b : B - 1;      // dead lanes shadow the last trajectory (no divergence, no stores)
-  const int hol = p.holonomic;
+  const unsigned bb = live ? b : B - 1;  // dead lanes shadow the last trajectory (no divergence, no stores)
   const float dt = p.dt;
-  const float * __restrict__ nvx = bufs.in_a + bb;
-  const float * __restrict__ nvy = bufs.in_b + bb;
-  const float * __restrict__ nwz = bufs.in_c + bb;
+  const float * __restrict__ nvx = bufs.in_a;
+  const float * __restrict__ nvy = bufs.in_b;
+  const float * __restrict__ nwz = bufs.in_c;
 
-  const bool con_on = p.constraint.on, fwd_on = p.forward.on, twirl_on = p.twirl.on, db_on = p.deadband.on;
-  const bool goal_on = p.goal.on, gang_on = p.goal_angle.on, cost_on = p.cost.on, ob_on = p.obst.on;
-  const bool want_cells = p.want_cells != 0, spill = p.spill_traj != 0;
+#define MPPI_SF(bit, flag) (((F & (bit)) != 0) && (kExact || (flag)))
+  const bool hol = MPPI_SF(SF_HOL, p.holonomic != 0);
+  const bool acker = MPPI_SF(SF_ACKER, p.model == MPPI_MODEL_ACKERMANN);
+  const bool con_on = MPPI_SF(SF_CON, p.constraint.on), fwd_on = MPPI_SF(SF_FWD, p.forward.on);
+  const bool twirl_on = MPPI_SF(SF_TWIRL, p.twirl.on), db_on = MPPI_SF(SF_DB, p.deadband.on);
+  const bool goal_on = MPPI_SF(SF_GOAL, p.goal.on), gang_on = MPPI_SF(SF_GANG, p.goal_angle.on);
+  const bool cost_on = MPPI_SF(SF_COST, p.cost.on), ob_on = MPPI_SF(SF_OBST, p.obst.on);
+  constexpr bool kFp = (F & SF_FOOTPRINT) != 0, kSpill = (F & SF_SPILL) != 0;
+  const bool cost_fp = kFp && p.cost_fp != 0, ob_fp = kFp && p.obst_fp != 0;
+  const bool want_cells = kSpill && p.want_cells != 0, spill = kSpill && p.spill_traj != 0;
+#undef MPPI_SF
   const bool need_cell = cost_on || ob_on || want_cells;
-  const bool acker = p.model == MPPI_MODEL_ACKERMANN;
   const bool track_unknown = p.track_unknown != 0;
-  const bool cost_fp = p.cost_fp != 0, ob_fp = p.obst_fp != 0;
   const bool cost_near_goal = p.cost_near_goal != 0, ob_near_goal = p.obst_near_goal != 0, ob_rep_on = p.obst_repulsion_enabled != 0;
   const float cost_pic = p.cost_possibly_inscribed, ob_pic = p.obst_possibly_inscribed, cost_critical = p.cost_critical;
   const float max_vel = p.max_vel, min_vel = p.min_vel, min_r = p.min_turning_r;
   const float db_vx = fabsf(p.db_vx), db_vy = fabsf(p.db_vy), db_wz = fabsf(p.db_wz);
-  const double x0 = p.pose_x, y0 = p.pose_y, ox = p.ox, oy = p.oy, res = p.res, inv_res = p.inv_res;
-  const unsigned size_x = p.size_x, size_y = p.size_y;
+  const double x0 = p.pose_x, y0 = p.pose_y;
+  const CellGrid cg = {p.cell_oxf, p.cell_oyf, p.cell_invf, p.cell_eps_x, p.cell_eps_y, p.size_x, p.size_y};
   const float yaw0 = p.yaw0, goal_yaw = p.goal_yaw;
   const int step = p.sample_step;
   const bool sample_yaw = p.sample_yaw != 0;
+  const bool step_is_chunk = step == kStreamChunk;
 
   float g_vx = 0.f, g_vy = 0.f, g_wz = 0.f, a_con = 0.f, a_fwd = 0.f, a_twirl = 0.f, a_db = 0.f;
   float a_goal = 0.f, a_gang = 0.f, cost_rep = 0.f, ob_traj = 0.f, ob_rep = 0.f;
   bool cost_hit = false, ob_hit = false;
   float vx = p.speed_vx, vy = hol ? p.speed_vy : 0.0f, wz = p.speed_wz;   // state velocities of step 0 = robot speed
-  float acc_yaw = 0.f, acc_x = 0.f, acc_y = 0.f, yaw_prev = yaw0;
-  float px = 0.f, py = 0.f;
+  // the running sums start at -0.0f: (-0) + x == x bit for bit, i.e. the first element of the cumsum is the term itself
+  float acc_yaw = -0.0f, acc_x = -0.0f, acc_y = -0.0f;
+  float yaw_prev = yaw0;                 // cos/sin of step 0 use yaw0 (p.cos0 / p.sin0 are mppi_det_sincosf(yaw0) as well)
+  float ex = 0.f, ey = 0.f;              // end pose
   int next_sample = step > 0 ? 0 : T, sample_k = 0;
 
-  // software pipeline of the noise rows
-  float qx[kStreamPrefetch], qy[kStreamPrefetch], qw[kStreamPrefetch];
+  // software pipeline of the noise rows: the chunk being processed was loaded one chunk ago.  32-bit element
+  // offsets (the host guarantees (T + pad) * B < 2^32): one IMAD.WIDE per load instead of 64-bit arithmetic.
+  float qx[kStreamChunk], qy[kStreamChunk], qw[kStreamChunk];
+  unsigned off = bb;                     // element offset of (row, trajectory) in the time-major planes
 #pragma unroll
-  for (int u = 0; u < kStreamPrefetch; ++u) {
-    const size_t off = static_cast<size_t>(min(u, T - 1)) * B;
-    qx[u] = __ldg(nvx + off); qy[u] = __ldg(nvy + off); qw[u] = __ldg(nwz + off);
+  for (int u = 0; u < kStreamChunk; ++u) {
+    qx[u] = __ldg(nvx + off); qw[u] = __ldg(nwz + off);
+    qy[u] = hol ? __ldg(nvy + off) : 0.0f;
+    off += B;
   }
-  size_t g = b;   // index of (t, b) in the time-major spills
-  for (int t0 = 0; t0 < T; t0 += kStreamPrefetch) {
-#pragma unroll
-    for (int u = 0; u < kStreamPrefetch; ++u) {
-      const int t = t0 + u;
-      if (t < T) {
-        // setNoisedControls (noise_generator.cpp:71-73)
-        const float csx = s_cs[t], csy = s_cs[T + t], csw = s_cs[2 * T + t];
-        const float cx = __fadd_rn(csx, qx[u]), cy = __fadd_rn(csy, qy[u]), cw = __fadd_rn(csw, qw[u]);
-        {   // refill this slot with the row kStreamPrefetch steps ahead
-          const size_t off = static_cast<size_t>(min(t + kStreamPrefetch, T - 1)) * B;
-          qx[u] = __ldg(nvx + off); qy[u] = __ldg(nvy + off); qw[u] = __ldg(nwz + off);
-        }
-        // gamma term (optimizer.cpp:365-380)
-        g_vx = __fadd_rn(g_vx, __fmul_rn(csx, __fsub_rn(cx, csx)));
-        g_wz = __fadd_rn(g_wz, __fmul_rn(csw, __fsub_rn(cw, csw)));
-        if (hol) {g_vy = __fadd_rn(g_vy, __fmul_rn(csy, __fsub_rn(cy, csy)));}
-        // velocity critics on the state velocities of step t
-        if (con_on) {
-          const float sgn = vx > 0.0f ? 1.0f : -1.0f;
-          const float vel_total = sgn * sqrtf(vx * vx + vy * vy);
-          float e = fmaxf(vel_total - max_vel, 0.0f) + fmaxf(min_vel - vel_total, 0.0f);
-          if (acker) {e += fmaxf(min_r - fabsf(vx) / fabsf(wz), 0.0f);}
-          a_con += e * dt;
-        }
-        if (fwd_on) {a_fwd += fmaxf(-vx, 0.0f) * dt;}
-        if (twirl_on) {a_twirl += fabsf(wz);}
-        if (db_on) {
-          float e = fmaxf(db_vx - fabsf(vx), 0.0f);
-          if (hol) {e += fmaxf(db_vy - fabsf(vy), 0.0f);}
-          e += fmaxf(db_wz - fabsf(wz), 0.0f);
-          a_db += e * dt;
-        }
-        // integrateStateVelocities (optimizer.cpp:319-342), sequential order
-        const float term = __fmul_rn(wz, dt);
-        acc_yaw = t == 0 ? term : __fadd_rn(acc_yaw, term);
-        const float yaw = __fadd_rn(acc_yaw, yaw0);
-        float sn, cn;
-        if (t == 0) {
-          sn = p.sin0; cn = p.cos0;
-        } else {
-          mppi_det_sincosf(yaw_prev, &sn, &cn);
-        }
-        float dx = __fmul_rn(vx, cn), dy = __fmul_rn(vx, sn);
-        if (hol) {
-          dx = __fsub_rn(dx, __fmul_rn(vy, sn));
-          dy = __fadd_rn(dy, __fmul_rn(vy, cn));
-        }
-        const float tx = __fmul_rn(dx, dt), ty = __fmul_rn(dy, dt);
-        acc_x = t == 0 ? tx : __fadd_rn(acc_x, tx);
-        acc_y = t == 0 ? ty : __fadd_rn(acc_y, ty);
-        px = static_cast<float>(x0 + static_cast<double>(acc_x));
-        py = static_cast<float>(y0 + static_cast<double>(acc_y));
+  unsigned g = b;   // index of (t, b) in the time-major spills
 
-        // position critics
-        if (goal_on) {
-          const float ddx = static_cast<float>(static_cast<double>(px) - p.goal_x);
-          const float ddy = static_cast<float>(static_cast<double>(py) - p.goal_y);
-          a_goal += sqrtf(ddx * ddx + ddy * ddy);
+  auto chunk = [&](auto tail_tag, const int t0) {
+      constexpr bool kTail = decltype(tail_tag)::value;   // the last, partial chunk: steps t >= T are masked
+      const float * cs_t = s_cs + t0;
+      // ---- phase A: noised controls of the chunk (noise_generator.cpp:71-73), then refill the pipeline
+      float cx[kStreamChunk], cy[kStreamChunk], cw[kStreamChunk];
+#pragma unroll
+      for (int u = 0; u < kStreamChunk; ++u) {
+        cx[u] = __fadd_rn(cs_t[u], qx[u]);
+        cy[u] = hol ? __fadd_rn(cs_t[Tp + u], qy[u]) : 0.0f;
+        cw[u] = __fadd_rn(cs_t[2 * Tp + u], qw[u]);
+      }
+      if (!kTail) {
+#pragma unroll
+        for (int u = 0; u < kStreamChunk; ++u) {
+          qx[u] = __ldg(nvx + off); qw[u] = __ldg(nwz + off);
+          qy[u] = hol ? __ldg(nvy + off) : 0.0f;
+          off += B;
         }
-        if (gang_on) {a_gang += static_cast<float>(fabs(normalize_angle_d(static_cast<double>(__fsub_rn(goal_yaw, yaw)))));}
-        if (need_cell) {
-          const int cell = world_to_cell_fast(px, py, ox, oy, res, inv_res, size_x, size_y);
-          if (want_cells && live) {bufs.spill_cells[g] = cell;}
-          if ((cost_on && !cost_hit) || (ob_on && !ob_hit)) {
-            const int pose_cost = cell < 0 ? NO_INFORMATION : __ldg(cm + cell);
+      }
+      // ---- phase B: yaw = cumsum(wz * dt) + yaw0 (optimizer.cpp:319-320), sequential; one add per step
+      float yw[kStreamChunk], sn[kStreamChunk], cn[kStreamChunk];
+#pragma unroll
+      for (int u = 0; u < kStreamChunk; ++u) {
+        const float swz = u == 0 ? wz : cw[u - 1];
+        acc_yaw = __fadd_rn(acc_yaw, __fmul_rn(swz, dt));
+        yw[u] = __fadd_rn(acc_yaw, yaw0);
+      }
+      // ---- phase C: cos/sin of the lagged yaw (optimizer.cpp:322-329): independent across the chunk
+#pragma unroll
+      for (int u = 0; u < kStreamChunk; ++u) {
+        mppi_det_sincosf(u == 0 ? yaw_prev : yw[u - 1], &sn[u], &cn[u]);
+      }
+      // ---- phase D: x = pose.x + cumsum(dx * dt) (optimizer.cpp:331-342), sequential; fp64 add of the pose
+      float px[kStreamChunk], py[kStreamChunk];
+#pragma unroll
+      for (int u = 0; u < kStreamChunk; ++u) {
+        const float svx = u == 0 ? vx : cx[u - 1];
+        float dx = __fmul_rn(svx, cn[u]), dy = __fmul_rn(svx, sn[u]);
+        if (hol) {
+          const float svy = u == 0 ? vy : cy[u - 1];
+          dx = __fsub_rn(dx, __fmul_rn(svy, sn[u]));
+          dy = __fadd_rn(dy, __fmul_rn(svy, cn[u]));
+        }
+        acc_x = __fadd_rn(acc_x, __fmul_rn(dx, dt));
+        acc_y = __fadd_rn(acc_y, __fmul_rn(dy, dt));
+        px[u] = static_cast<float>(x0 + static_cast<double>(acc_x));
+        py[u] = static_cast<float>(y0 + static_cast<double>(acc_y));
+      }
+      // ---- phase E: costmap cell of every pose of the chunk and its byte, loads issued together
+      int cell[kStreamChunk], pcost[kStreamChunk];
+      if (need_cell) {
+#pragma unroll
+        for (int u = 0; u < kStreamChunk; ++u) {cell[u] = world_to_cell_fast(px[u], py[u], cg, &p.res);}
+#pragma unroll
+        for (int u = 0; u < kStreamChunk; ++u) {pcost[u] = cell[u] < 0 ? NO_INFORMATION : __ldg(cm + cell[u]);}
+      }
+      // ---- phase F: the critics, in step order (collision short-circuits are order dependent)
+#pragma unroll
+      for (int u = 0; u < kStreamChunk; ++u) {
+        const int t = t0 + u;
+        if (!kTail || t < T) {
+          const float svx = u == 0 ? vx : cx[u - 1];
+          const float svy = u == 0 ? vy : cy[u - 1];
+          const float swz = u == 0 ? wz : cw[u - 1];
+          const float yaw = yw[u];
+          // gamma term (optimizer.cpp:365-380)
+          const float csx = cs_t[u], csw = cs_t[2 * Tp + u];
+          g_vx = __fadd_rn(g_vx, __fmul_rn(csx, __fsub_rn(cx[u], csx)));
+          g_wz = __fadd_rn(g_wz, __fmul_rn(csw, __fsub_rn(cw[u], csw)));
+          if (hol) {
+            const float csy = cs_t[Tp + u];
+            g_vy = __fadd_rn(g_vy, __fmul_rn(csy, __fsub_rn(cy[u], csy)));
+          }
+          if (con_on) {   // constraint_critic.cpp:49-52
+            const float sgn = svx > 0.0f ? 1.0f : -1.0f;
+            const float vel_total = sgn * sqrt_approx(svx * svx + svy * svy);
+            float e = fmaxf(vel_total - max_vel, 0.0f) + fmaxf(min_vel - vel_total, 0.0f);
+            if (acker) {e += fmaxf(min_r - fabsf(svx) / fabsf(swz), 0.0f);}
+            a_con += e * dt;
+          }
+          if (fwd_on) {a_fwd += fmaxf(-svx, 0.0f) * dt;}       // prefer_forward_critic.cpp:42-46
+          if (twirl_on) {a_twirl += fabsf(swz);}               // twirling_critic.cpp:40-41
+          if (db_on) {                                         // velocity_deadband_critic.cpp:54-97
+            float e = fmaxf(db_vx - fabsf(svx), 0.0f);
+            if (hol) {e += fmaxf(db_vy - fabsf(svy), 0.0f);}
+            e += fmaxf(db_wz - fabsf(swz), 0.0f);
+            a_db += e * dt;
+          }
+          if (goal_on) {                                       // goal_critic.cpp:50-52
+            const float ddx = static_cast<float>(static_cast<double>(px[u]) - p.goal_x);
+            const float ddy = static_cast<float>(static_cast<double>(py[u]) - p.goal_y);
+            a_goal += sqrt_approx(ddx * ddx + ddy * ddy);
+          }
+          if (gang_on) {a_gang += static_cast<float>(fabs(normalize_angle_d(static_cast<double>(__fsub_rn(goal_yaw, yaw)))));}
+          if (need_cell) {
+            if (want_cells && live) {bufs.spill_cells[g] = cell[u];}
+            const int pose_cost = pcost[u];
             int fp_cost = -1;
-            if (cost_on && !cost_hit && pose_cost >= 1) {
+            if (cost_on && !cost_hit && pose_cost >= 1) {   // cost_critic.cpp:139-162
               int c = pose_cost;
-              if (cost_fp && (static_cast<float>(c) >= cost_pic || cost_pic < 1.0f)) {
-                fp_cost = footprint_cost_at_pose(P, p.fp_n, ox, oy, res, size_x, size_y, cm, px, py, yaw);
+              if (kFp && cost_fp && (static_cast<float>(c) >= cost_pic || cost_pic < 1.0f)) {
+                fp_cost = footprint_cost_at_pose(P, p.fp_n, p.ox, p.oy, p.res, cg.size_x, cg.size_y, cm, px[u], py[u], yaw);
                 c = fp_cost;
               }
               if (in_collision(c, cost_fp, track_unknown)) {
@@ -676,11 +769,11 @@ __global__ void __launch_bounds__(kStreamThreads, 4) rollout_score_stream_kernel
                 cost_rep += static_cast<float>(pose_cost);
               }
             }
-            if (ob_on && !ob_hit) {
+            if (ob_on && !ob_hit) {                         // obstacles_critic.cpp:145-170, :203-224
               int c = pose_cost;
               int using_fp = 0;
-              if (cell >= 0 && ob_fp && (static_cast<float>(c) >= ob_pic || ob_pic < 1.0f)) {
-                if (fp_cost < 0) {fp_cost = footprint_cost_at_pose(P, p.fp_n, ox, oy, res, size_x, size_y, cm, px, py, yaw);}
+              if (kFp && cell[u] >= 0 && ob_fp && (static_cast<float>(c) >= ob_pic || ob_pic < 1.0f)) {
+                if (fp_cost < 0) {fp_cost = footprint_cost_at_pose(P, p.fp_n, p.ox, p.oy, p.res, cg.size_x, cg.size_y, cm, px[u], py[u], yaw);}
                 c = fp_cost;
                 using_fp = 1;
               }
@@ -694,23 +787,32 @@ __global__ void __launch_bounds__(kStreamThreads, 4) rollout_score_stream_kernel
               }
             }
           }
-        }
-        if (live) {
-          if (t == next_sample) {
-            const size_t k = static_cast<size_t>(sample_k) * B + b;
-            bufs.samples_x[k] = px; bufs.samples_y[k] = py;
-            if (sample_yaw) {bufs.samples_yaw[k] = yaw;}
-            next_sample += step; sample_k++;
+          if (live) {
+            // every trajectory_point_step-th pose for PathAlign (K3); the usual step equals the chunk length
+            if (step_is_chunk ? (u == 0) : (t == next_sample)) {
+              const unsigned k = static_cast<unsigned>(sample_k) * B + b;
+              bufs.samples_x[k] = px[u]; bufs.samples_y[k] = py[u];
+              if (sample_yaw) {bufs.samples_yaw[k] = yaw;}
+              next_sample += step; sample_k++;
+            }
+            if (kSpill && spill) {bufs.spill_x[g] = px[u]; bufs.spill_y[g] = py[u]; bufs.spill_yaw[g] = yaw;}
           }
-          if (spill) {bufs.spill_x[g] = px; bufs.spill_y[g] = py; bufs.spill_yaw[g] = yaw;}
+          g += B;
+          if (kTail) {
+            if (t == T - 1) {ex = px[u]; ey = py[u];}
+          } else if (u == kStreamChunk - 1) {
+            ex = px[u]; ey = py[u];
+          }
         }
-        g += B;
-        // predict(): state velocities of step t+1 are the controls of step t (motion_models.hpp:53-66)
-        vx = cx; vy = hol ? cy : 0.0f; wz = cw;
-        yaw_prev = yaw;
       }
-    }
-  }
+      // predict(): state velocities of the next step are the controls of this one (motion_models.hpp:53-66)
+      vx = cx[kStreamChunk - 1]; vy = cy[kStreamChunk - 1]; wz = cw[kStreamChunk - 1];
+      yaw_prev = yw[kStreamChunk - 1];
+    };
+
+  const int T_full = (T / kStreamChunk) * kStreamChunk;
+  for (int t0 = 0; t0 < T_full; t0 += kStreamChunk) {chunk(std::false_type{}, t0);}
+  if (T_full < T) {chunk(std::true_type{}, T_full);}
 
   // furthest reached path point candidate (utils.hpp:292-319): first minimum over the whole path
   unsigned best_j = 0;
@@ -720,8 +822,8 @@ __global__ void __launch_bounds__(kStreamThreads, 4) rollout_score_stream_kernel
     float best = 3.402823466e+38f;
     const int N = p.N;
     for (int j = 0; j < N; ++j) {
-      const float dx = __fsub_rn(__ldg(path_x + j), px);
-      const float dy = __fsub_rn(__ldg(path_y + j), py);
+      const float dx = __fsub_rn(__ldg(path_x + j), ex);
+      const float dy = __fsub_rn(__ldg(path_y + j), ey);
       const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
       if (d < best) {best = d; best_j = j;}
     }
@@ -731,18 +833,18 @@ __global__ void __launch_bounds__(kStreamThreads, 4) rollout_score_stream_kernel
   const float Tf = static_cast<float>(T);
   float * rows = bufs.crit_rows;
   if (live) {
-    bufs.end_xy[b] = px; bufs.end_xy[B + b] = py;
-    if (p.constraint.on) {rows[static_cast<size_t>(p.constraint.idx) * B + b] = add_pow(0.0f, a_con * p.constraint.weight, p.constraint.power);}
-    if (p.forward.on) {rows[static_cast<size_t>(p.forward.idx) * B + b] = add_pow(0.0f, a_fwd * p.forward.weight, p.forward.power);}
-    if (p.twirl.on) {rows[static_cast<size_t>(p.twirl.idx) * B + b] = add_pow(0.0f, (a_twirl / Tf) * p.twirl.weight, p.twirl.power);}
-    if (p.deadband.on) {rows[static_cast<size_t>(p.deadband.idx) * B + b] = add_pow(0.0f, a_db * p.deadband.weight, p.deadband.power);}
-    if (p.goal.on) {rows[static_cast<size_t>(p.goal.idx) * B + b] = add_pow(0.0f, (a_goal / Tf) * p.goal.weight, p.goal.power);}
-    if (p.goal_angle.on) {rows[static_cast<size_t>(p.goal_angle.idx) * B + b] = add_pow(0.0f, (a_gang / Tf) * p.goal_angle.weight, p.goal_angle.power);}
-    if (p.cost.on) {
+    bufs.end_xy[b] = ex; bufs.end_xy[B + b] = ey;
+    if (con_on) {rows[static_cast<size_t>(p.constraint.idx) * B + b] = add_pow(0.0f, a_con * p.constraint.weight, p.constraint.power);}
+    if (fwd_on) {rows[static_cast<size_t>(p.forward.idx) * B + b] = add_pow(0.0f, a_fwd * p.forward.weight, p.forward.power);}
+    if (twirl_on) {rows[static_cast<size_t>(p.twirl.idx) * B + b] = add_pow(0.0f, (a_twirl / Tf) * p.twirl.weight, p.twirl.power);}
+    if (db_on) {rows[static_cast<size_t>(p.deadband.idx) * B + b] = add_pow(0.0f, a_db * p.deadband.weight, p.deadband.power);}
+    if (goal_on) {rows[static_cast<size_t>(p.goal.idx) * B + b] = add_pow(0.0f, (a_goal / Tf) * p.goal.weight, p.goal.power);}
+    if (gang_on) {rows[static_cast<size_t>(p.goal_angle.idx) * B + b] = add_pow(0.0f, (a_gang / Tf) * p.goal_angle.weight, p.goal_angle.power);}
+    if (cost_on) {
       const float rep = cost_hit ? p.cost_collision : cost_rep;
       rows[static_cast<size_t>(p.cost.idx) * B + b] = add_pow(0.0f, p.cost.weight * rep / Tf, p.cost.power);
     }
-    if (p.obst.on) {
+    if (ob_on) {
       const float raw = ob_hit ? p.obst_collision : ob_traj;
       const float v = (p.obst_critical_w * raw) + (p.obst_repulsion_w * ob_rep / Tf);
       rows[static_cast<size_t>(p.obst.idx) * B + b] = add_pow(0.0f, v, p.obst.power);
@@ -750,11 +852,11 @@ __global__ void __launch_bounds__(kStreamThreads, 4) rollout_score_stream_kernel
     const size_t gr = static_cast<size_t>(p.n_critics) * B + b;
     rows[gr] = g_vx; rows[gr + B] = g_vy; rows[gr + 2 * static_cast<size_t>(B)] = g_wz;
   }
-  if (p.cost.on) {
+  if (cost_on) {
     const unsigned ok = __ballot_sync(0xffffffffu, live && !cost_hit);
     if ((tid & 31) == 0 && ok) {atomicOr(&bufs.st->any_ok[p.cost.idx], 1u);}
   }
-  if (p.obst.on) {
+  if (ob_on) {
     const unsigned ok = __ballot_sync(0xffffffffu, live && !ob_hit);
     if ((tid & 31) == 0 && ok) {atomicOr(&bufs.st->any_ok[p.obst.idx], 1u);}
   }

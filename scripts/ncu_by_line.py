@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--launch", type=int, default=0, help="index among the launches of that kernel in the report")
     ap.add_argument("--sort", default="samples", choices=["samples", "inst"])
+    ap.add_argument("--mangled", default=None, help="substring of the mangled name (templates), default = kernel")
     a = ap.parse_args()
     out = subprocess.run(["ncu", "-i", a.report, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     # the CSV holds one block per profiled launch: "Kernel Name", header row, rows
@@ -69,7 +70,7 @@ def main():
     ithr = hdr.index("Thread Instructions Executed")
     stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_")]
     base = int(blk["rows"][0][ia], 16)
-    off2line = disasm_lines(a.kernel)
+    off2line = disasm_lines(a.mangled or a.kernel)
     per_line = defaultdict(lambda: [0, 0, 0, defaultdict(int)])
     tot_i = tot_s = tot_t = 0
     for r in blk["rows"]:
