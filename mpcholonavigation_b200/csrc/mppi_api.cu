@@ -127,7 +127,8 @@ struct mppi_handle
 namespace
 {
 
-constexpr size_t kParamsCapacity = sizeof(DevParams) + MPPI_MAX_PATH_POINTS * (4 * sizeof(float) + 1) + 64;
+// record + per path point: x, y, yaw, D (floats), PathAngle gate byte, validity byte, invalid-prefix uint16 (+ slack)
+constexpr size_t kParamsCapacity = sizeof(DevParams) + MPPI_MAX_PATH_POINTS * (4 * sizeof(float) + 4) + 256;
 
 #define CUDA_TRY(h, expr)                                                                          \
   do {                                                                                             \
@@ -228,7 +229,8 @@ void set_common(CriticCommon & c, const mppi_critic_desc * d, int idx, bool gate
 }
 
 // Fill the per-cycle record.  `in` may be null for integrate-only calls (mode 1).
-mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, unsigned preset_furthest, bool critics_active)
+mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, unsigned preset_furthest, bool critics_active,
+  const float * first_pose = nullptr)
 {
   DevParams & p = *reinterpret_cast<DevParams *>(h->h_params);
   std::memset(&p, 0, sizeof(p));
@@ -247,6 +249,7 @@ mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, un
   p.preset_furthest = preset_furthest;
   p.track_unknown = h->robot.track_unknown;
   p.want_cells = (h->want_mask & MPPI_WANT_CELLS) ? 1 : 0;
+  p.want_critic_rows = (h->want_mask & MPPI_WANT_CRITIC_COSTS) ? 1 : 0;
   p.fp_n = h->robot.footprint_size;
   for (int i = 0; i < p.fp_n; ++i) {p.fp_x[i] = h->robot.footprint_x[i]; p.fp_y[i] = h->robot.footprint_y[i];}
 
@@ -289,13 +292,67 @@ mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, un
     D[i] = D[i - 1] + curr_dist;
   }
   uint8_t * gate = reinterpret_cast<uint8_t *>(tail + 4 * N);
-  std::memset(gate, 0, N);
-  h->params_bytes = sizeof(DevParams) + sizeof(float) * 4 * N + ((N + 15) / 16) * 16;
+  const int n16 = ((N + 15) / 16) * 16;
+  p.off_valid_bytes = n16;
+  p.off_invalid_prefix_bytes = 2 * n16;
+  uint8_t * valid = gate + p.off_valid_bytes;
+  uint16_t * invalid_before = reinterpret_cast<uint16_t *>(gate + p.off_invalid_prefix_bytes);
+  std::memset(gate, 0, 2 * n16 + sizeof(uint16_t) * (N + 1));
+  h->params_bytes = sizeof(DevParams) + sizeof(float) * 4 * N + 2 * n16 + sizeof(uint16_t) * (N + 1);
   // copy size rounded up to 64 path points so that the captured graph survives small changes of the pruned path
   {
     const size_t n64 = std::min<size_t>(MPPI_MAX_PATH_POINTS, ((static_cast<size_t>(N) + 63) / 64) * 64);
-    h->params_copy_bytes = std::min(kParamsCapacity, sizeof(DevParams) + 17 * n64 + 64);
-    h->params_copy_bytes = std::max(h->params_copy_bytes, h->params_bytes);
+    h->params_copy_bytes = std::min(kParamsCapacity, sizeof(DevParams) + 20 * n64 + 128);
+    h->params_copy_bytes = std::max(h->params_copy_bytes, (h->params_bytes + 15) & ~static_cast<size_t>(15));
+  }
+  // utils::findPathCosts (utils.hpp:361-394): validity of every path point but the last, against the costmap the
+  // caller holds for this cycle; prefix counts of the invalid ones for PathAlign's occupancy gate
+  for (int j = 0; j < N; ++j) {
+    bool ok = false;
+    if (j < N - 1 && in->costmap.cells) {
+      const double wx = in->path_x[j], wy = in->path_y[j];
+      if (!(wx < p.ox || wy < p.oy)) {
+        const double qx = (wx - p.ox) / p.res, qy = (wy - p.oy) / p.res;
+        if (qx < static_cast<double>(p.size_x) && qy < static_cast<double>(p.size_y)) {
+          const unsigned mx = static_cast<unsigned>(qx), my = static_cast<unsigned>(qy);
+          if (mx < p.size_x && my < p.size_y) {
+            const int c = in->costmap.cells[static_cast<size_t>(my) * p.size_x + mx];
+            ok = !(c == LETHAL_OBSTACLE || c == INSCRIBED_INFLATED_OBSTACLE || (c == NO_INFORMATION && !h->robot.track_unknown));
+          }
+        }
+      }
+    }
+    valid[j] = ok ? 1 : 0;
+    invalid_before[j + 1] = static_cast<uint16_t>(invalid_before[j] + (ok ? 0 : 1));
+  }
+  // utils::findPathTrajectoryInitialPoint (utils.hpp:327-344): closest path point to trajectory 0's first pose.  In the
+  // rollout modes that pose is the same for every trajectory (state velocities of step 0 are the robot speed), so the
+  // host evaluates it with the kernels' own arithmetic (this TU's host pass is built with -ffp-contract=off).
+  {
+    float x00, y00;
+    if (first_pose) {
+      x00 = first_pose[0]; y00 = first_pose[1];
+    } else {
+      const float dt = cfg.model_dt;
+      const float vx0 = p.speed_vx, vy0 = holonomic(h) ? p.speed_vy : 0.0f;
+      float dx = vx0 * p.cos0, dy = vx0 * p.sin0;
+      if (holonomic(h)) {
+        const float a = vy0 * p.sin0, b2 = vy0 * p.cos0;
+        dx = dx - a; dy = dy + b2;
+      }
+      const float tx = dx * dt, ty = dy * dt;
+      x00 = static_cast<float>(rx + static_cast<double>(tx));
+      y00 = static_cast<float>(ry + static_cast<double>(ty));
+    }
+    float best = 3.402823466e+38f;
+    int best_j = 0;
+    for (int j = 0; j < N; ++j) {
+      const float dx = in->path_x[j] - x00, dy = in->path_y[j] - y00;
+      const float dxx = dx * dx, dyy = dy * dy;
+      const float d = dxx + dyy;
+      if (d < best) {best = d; best_j = j;}
+    }
+    p.closest_path_pt = best_j;
   }
 
   p.n_critics = critics_active ? static_cast<int>(h->critics.size()) : 0;
@@ -571,9 +628,18 @@ mppi_status launch_rollout(mppi_handle * h, int mode)
 
 mppi_status launch_update(mppi_handle * h, int mode, int iteration)
 {
-  const size_t smem = kHotBytes + sizeof(float) * (MPPI_MAX_PATH_POINTS + kUpdThreads + 32) + MPPI_MAX_PATH_POINTS + 16;
+  if (mode == 0 && h->stream_layout) {
+    // stream layout: totals + global minimum here, weights and weighted sums in weighted_sums_tm_kernel
+    const int grid = std::min((h->B + kUpdThreads - 1) / kUpdThreads, 148 * 8);
+    path_costs_tm_kernel<<<grid, kUpdThreads, k3_common_smem_bytes(), h->stream>>>(
+      reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, mode), iteration);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+    return MPPI_OK;
+  }
+  const size_t smem = k3_common_smem_bytes() + sizeof(float) * (kUpdThreads + 32);
   path_softmax_update_kernel<<<h->upd_blocks, kUpdThreads, smem, h->stream>>>(
-    reinterpret_cast<const DevParams *>(h->d_params), h->d_costmap, make_bufs(h, mode), h->nranks, iteration, h->upd_rows);
+    reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, mode), h->nranks, iteration, h->upd_rows);
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   return MPPI_OK;
@@ -1165,6 +1231,7 @@ mppi_status mppi_get_critic_costs(mppi_handle * h, int32_t index, float * costs)
 {
   if (!h || !costs) {return MPPI_E_CONFIG;}
   if (!h->have_rows) {return fail(h, MPPI_E_STATE, "no optimize has run yet");}
+  if (!h->last.want_critic_rows) {return fail(h, MPPI_E_STATE, "request the rows first: mppi_set_outputs(MPPI_WANT_CRITIC_COSTS)");}
   if (index < 0 || index >= static_cast<int>(h->critics.size())) {return fail(h, MPPI_E_CONFIG, "critic index out of range");}
   CUDA_TRY(h, cudaSetDevice(h->device));
   CUDA_TRY(h, cudaMemcpyAsync(costs, h->d_crit_rows + static_cast<size_t>(index) * h->B, h->B * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -1238,7 +1305,8 @@ mppi_status mppi_score_trajectories(
   }
   CUDA_TRY(h, cudaMemcpyAsync(h->d_costs, costs_inout, h->B * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   const unsigned preset = furthest_inout ? *furthest_inout : kUnset;
-  s = build_params(h, in, 2, preset, true);
+  const float first_pose[2] = {x[0], y[0]};   // trajectories(0, 0): utils::findPathTrajectoryInitialPoint
+  s = build_params(h, in, 2, preset, true, first_pose);
   if (s != MPPI_OK) {return s;}
   if ((s = stage_costmap(h, in->costmap)) != MPPI_OK) {return s;}
   if ((s = enqueue_uploads(h)) != MPPI_OK) {return s;}

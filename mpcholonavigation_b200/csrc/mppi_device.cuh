@@ -84,6 +84,11 @@ struct DevParams
   int noise_tm;                              // noise planes are stored time-major [T][B] (stream layout) instead of [B][T]
   // offsets (in floats) of the path arrays that follow this struct in the same buffer
   int off_path_x, off_path_y, off_path_yaw, off_path_D, off_gate;
+  // byte offsets, relative to the gate bytes, of the host-decided path validity (utils::findPathCosts, utils.hpp:361-394)
+  // and of its prefix counts: invalid_before[j] = number of invalid points among [0, j), uint16
+  int off_valid_bytes, off_invalid_prefix_bytes;
+  int closest_path_pt;                       // utils::findPathTrajectoryInitialPoint (utils.hpp:327-344), host decided
+  int want_critic_rows;                      // per-critic rows are read back by the caller: keep them fully defined
   int fp_n;
   float cell_oxf, cell_oyf, cell_invf;       // fp32 filter of worldToMap (world_to_cell_fast): fl32(ox), fl32(oy), fl32(1/res)
   float cell_eps_x, cell_eps_y;              // and its error bounds in cells

@@ -944,79 +944,51 @@ __device__ __forceinline__ void merge_partials(
   if (tid == 0) {dst[0] = m;}
 }
 
-__global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
-  const DevParams * __restrict__ Pg, const uint8_t * __restrict__ cm, DevBuffers bufs, int n_ranks, int iteration, int R)
+// The scalar decisions of one CriticManager::evalTrajectoriesScores pass (critic_manager.cpp:67-76), taken once per
+// block by one thread: which critic raised fail_flag, the furthest reached path point, and the path critics' gates.
+struct K3Decisions
 {
-  // R = trajectories owned by this block (multiple of 32, <= kUpdThreads): small batches use small R so that
-  // the update spreads over many SMs; the column sums always use all kUpdThreads threads
-  extern __shared__ float smem[];
-  const int tid = threadIdx.x;
+  int fail_at;        // index of the critic that raised fail_flag (critics after it are skipped); n_critics if none
+  int furthest, furthest_set;
+  int follow_idx;
+  int align_go, legacy_go, angle_go, angle_idx;
+};
+
+// shared-memory carve-up common to the K3 kernels: hot params | D[N] | valid[N]
+__host__ __device__ inline size_t k3_common_smem_bytes() {return kHotBytes + sizeof(float) * MPPI_MAX_PATH_POINTS + MPPI_MAX_PATH_POINTS;}
+
+struct K3Path
+{
+  const float * x, * y, * yaw;     // global (read through the read-only path)
+  const uint8_t * gate;            // PathAngle gate per candidate index (host decided)
+  const float * s_D;               // shared: arc-length prefix
+  const uint8_t * s_valid;         // shared: path point validity (utils::findPathCosts, host decided)
+};
+
+// copies the hot record, D and the validity bytes into shared memory and lets thread 0 take the decisions
+__device__ __forceinline__ void k3_preamble(
+  float * smem, const DevParams * __restrict__ Pg, DevState * st, int iteration, int tid, int nthr, K3Path & path, K3Decisions * dec)
+{
   float * s_hot = smem;
-  load_hot_params(s_hot, Pg, tid, kUpdThreads);
+  load_hot_params(s_hot, Pg, tid, nthr);
   __syncthreads();
-  const DevParams * P = reinterpret_cast<const DevParams *>(s_hot);   // hot fields only; arrays stay in global (Pg)
-  const int T = P->T, B = P->B, N = P->N, nc = P->n_critics;
-  const float * __restrict__ path_x = reinterpret_cast<const float *>(Pg + 1) + P->off_path_x;
-  const float * __restrict__ path_y = reinterpret_cast<const float *>(Pg + 1) + P->off_path_y;
-  const float * __restrict__ path_yaw = reinterpret_cast<const float *>(Pg + 1) + P->off_path_yaw;
-  const float * __restrict__ path_D = reinterpret_cast<const float *>(Pg + 1) + P->off_path_D;
-  const uint8_t * __restrict__ gate = reinterpret_cast<const uint8_t *>(reinterpret_cast<const float *>(Pg + 1) + P->off_gate);
-
-  float * s_D = s_hot + kHotFloats;                     // [N]
-  float * s_w = s_D + N;                                // [kUpdThreads]
-  float * s_red = s_w + kUpdThreads;                    // [32]
-  uint8_t * s_valid = reinterpret_cast<uint8_t *>(s_red + 32);   // [N]
-  __shared__ int sc_fail_at, sc_furthest, sc_furthest_set, sc_follow_idx, sc_align_go, sc_legacy_go, sc_angle_go, sc_angle_idx;
-  __shared__ int sc_closest;
-  __shared__ unsigned sc_last;
-
-  DevState * st = bufs.st;
+  const DevParams * P = reinterpret_cast<const DevParams *>(s_hot);
+  const int N = P->N, nc = P->n_critics;
+  const float * tail = reinterpret_cast<const float *>(Pg + 1);
+  path.x = tail + P->off_path_x; path.y = tail + P->off_path_y; path.yaw = tail + P->off_path_yaw;
+  path.gate = reinterpret_cast<const uint8_t *>(tail + P->off_gate);
+  const uint8_t * g_valid = path.gate + P->off_valid_bytes;
+  const uint16_t * g_invalid_before = reinterpret_cast<const uint16_t *>(path.gate + P->off_invalid_prefix_bytes);
+  float * s_D = s_hot + kHotFloats;
+  uint8_t * s_valid = reinterpret_cast<uint8_t *>(s_D + MPPI_MAX_PATH_POINTS);
+  path.s_D = s_D; path.s_valid = s_valid;
   const bool any_path_critic = (P->follow.on || P->align.on || P->legacy.on || P->angle.on);
-
-  // ---- phase 0a: path validity (utils.hpp:361-394) and the arc-length prefix into smem
   if (any_path_critic) {
-    for (int j = tid; j < N; j += kUpdThreads) {
-      s_D[j] = path_D[j];
-      bool ok = false;
-      if (j < N - 1) {
-        unsigned mx, my;
-        const int cell = world_to_cell(__ldg(path_x + j), __ldg(path_y + j), P->ox, P->oy, P->res, P->size_x, P->size_y, mx, my);
-        if (cell >= 0) {
-          const int c = __ldg(cm + cell);
-          ok = !(c == LETHAL_OBSTACLE || c == INSCRIBED_INFLATED_OBSTACLE || (c == NO_INFORMATION && !P->track_unknown));
-        }
-      }
-      s_valid[j] = ok ? 1 : 0;
-    }
+    const float * g_D = tail + P->off_path_D;
+    for (int j = tid; j < N; j += nthr) {s_D[j] = __ldg(g_D + j); s_valid[j] = __ldg(g_valid + j);}
   }
-  // closest path point to the start of the trajectories (utils.hpp:327-344): warp 0, first minimum wins
-  if (tid < 32) {
-    int cj = 0;
-    if ((P->align.on || P->legacy.on) && P->sample_step > 0) {
-      const float x0 = bufs.samples_x[0], y0 = bufs.samples_y[0];
-      float best = 3.402823466e+38f;
-      int best_j = 0x7fffffff;
-      for (int j = tid; j < N; j += 32) {
-        const float dx = __fsub_rn(__ldg(path_x + j), x0);
-        const float dy = __fsub_rn(__ldg(path_y + j), y0);
-        const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-        if (d < best) {best = d; best_j = j;}
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float od = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
-        if (od < best || (od == best && oj < best_j)) {best = od; best_j = oj;}
-      }
-      cj = best_j == 0x7fffffff ? 0 : best_j;
-    }
-    if (tid == 0) {sc_closest = cj;}
-  }
-  __syncthreads();
-
-  // ---- phase 0b: the scalar control flow of CriticManager::evalTrajectoriesScores, by one thread
   if (tid == 0) {
-    int fail_at = nc;   // index of the critic that raised fail_flag; critics after it are skipped
+    int fail_at = nc;
     if (iteration > 0 && st->fail_flag) {
       fail_at = -1;     // fail_flag is only cleared in prepare(): a failed iteration mutes the following ones
     } else {
@@ -1034,7 +1006,7 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
       fset = st->furthest_set; furthest = st->furthest;
     }
     auto runs = [&](const CriticCommon & c) {return c.on && c.idx <= fail_at;};
-    // critics in list order that call setPathFurthestPointIfNotSet
+    // the first critic in list order that calls setPathFurthestPointIfNotSet fixes it for the cycle
     for (int q = 0; q < nc && !fset; ++q) {
       if (q > fail_at) {break;}
       const int kind = P->kind_of[q];
@@ -1042,9 +1014,9 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
         (kind == MPPI_CRITIC_PATH_ALIGN && P->align.on) || (kind == MPPI_CRITIC_PATH_ALIGN_LEGACY && P->legacy.on);
       if (wants) {furthest = st->furthest_candidate; fset = 1;}
     }
-    sc_fail_at = fail_at;
-    sc_furthest = static_cast<int>(furthest);
-    sc_furthest_set = fset;
+    dec->fail_at = fail_at;
+    dec->furthest = static_cast<int>(furthest);
+    dec->furthest_set = fset;
     // PathFollow target (path_follow_critic.cpp:45-58)
     int fidx = 0;
     if (runs(P->follow)) {
@@ -1052,166 +1024,174 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
       fidx = min(static_cast<int>(furthest) + P->follow_offset, path_size);
       bool valid = false;
       while (!valid && fidx < path_size - 1) {
-        valid = s_valid[fidx] != 0;
+        valid = __ldg(g_valid + fidx) != 0;
         if (!valid) {fidx++;}
       }
     }
-    sc_follow_idx = fidx;
-    // PathAlign gates (path_align_critic.cpp:56-72)
+    dec->follow_idx = fidx;
+    // PathAlign gates (path_align_critic.cpp:56-72).  The reference counts invalid points from the closest point up
+    // to the furthest one and bails out as soon as count / range > ratio with count > 2; the count only grows and
+    // the range is fixed, so the final count decides: O(1) with the host's prefix counts.
     auto align_gate = [&](const CriticCommon & c, int offset, float max_ratio) -> int {
         if (!runs(c)) {return 0;}
         if (static_cast<int>(furthest) < offset) {return 0;}
-        const int closest = sc_closest;
-        unsigned invalid_ctr = 0;
+        const int closest = P->closest_path_pt;
         const float range = static_cast<float>(static_cast<long long>(furthest) - closest);
-        for (int i = closest; i < static_cast<int>(furthest); ++i) {
-          if (!s_valid[i]) {invalid_ctr++;}
-          if (static_cast<float>(invalid_ctr) / range > max_ratio && invalid_ctr > 2) {return 0;}
+        unsigned invalid_ctr = 0;
+        if (static_cast<int>(furthest) > closest) {
+          invalid_ctr = static_cast<unsigned>(g_invalid_before[furthest]) - static_cast<unsigned>(g_invalid_before[closest]);
         }
+        if (invalid_ctr > 2 && static_cast<float>(invalid_ctr) / range > max_ratio) {return 0;}
         return 1;
       };
-    sc_align_go = align_gate(P->align, P->align_offset, P->align_max_ratio) && furthest > 0u;
-    sc_legacy_go = align_gate(P->legacy, P->legacy_offset, P->legacy_max_ratio) && (N - 1) >= 1;
+    dec->align_go = align_gate(P->align, P->align_offset, P->align_max_ratio) && furthest > 0u;
+    dec->legacy_go = align_gate(P->legacy, P->legacy_offset, P->legacy_max_ratio) && (N - 1) >= 1;
     // PathAngle gate (path_angle_critic.cpp:73-83): decided per candidate index on the host
     int ago = 0, aidx = 0;
     if (runs(P->angle)) {
       aidx = min(static_cast<int>(furthest) + P->angle_offset, N - 1);
-      ago = gate[aidx] != 0;
+      ago = path.gate[aidx] != 0;
     }
-    sc_angle_go = ago; sc_angle_idx = aidx;
+    dec->angle_go = ago; dec->angle_idx = aidx;
   }
   __syncthreads();
+}
 
-  // ---- phase 1: one thread per trajectory: path critics + total in list order
-  const int b = blockIdx.x * R + tid;
-  const bool live = tid < R && b < B;
-  const int fail_at = sc_fail_at;
-  const int furthest = sc_furthest;
-  float total = 3.402823466e+38f;
-  if (live) {
-    total = (iteration == 0 && P->mode == 0) ? 0.0f : bufs.costs[b];
-    float * rows = bufs.crit_rows;
-    for (int q = 0; q < nc; ++q) {
-      if (q > fail_at) {break;}
-      const int kind = P->kind_of[q];
-      float term = 0.0f;
-      bool has = false;
-      switch (kind) {
-        case MPPI_CRITIC_PATH_FOLLOW:
-          if (P->follow.on) {    // path_follow_critic.cpp:60-70
-            const float dx = bufs.end_xy[b] - __ldg(path_x + sc_follow_idx);
-            const float dy = bufs.end_xy[B + b] - __ldg(path_y + sc_follow_idx);
-            term = add_pow(0.0f, P->follow.weight * sqrtf(dx * dx + dy * dy), P->follow.power);
-            has = true;
-          }
-          break;
-        case MPPI_CRITIC_PATH_ALIGN:
-          if (sc_align_go) {     // path_align_critic.cpp:92-135, sequential and in the reference's fp32 order
-            const int step = P->align_step;
-            float traj_d = 0.0f, summed = 0.0f, num = 0.0f;
-            int path_pt = 0;
-            float prev_x = bufs.samples_x[b], prev_y = bufs.samples_y[b];
-            int k = 1;
-            float nx = 0.0f, ny = 0.0f;   // one-deep prefetch of the next sampled pose (L2 latency off the serial chain)
-            if (step < T) {nx = bufs.samples_x[static_cast<size_t>(B) + b]; ny = bufs.samples_y[static_cast<size_t>(B) + b];}
-            for (int p = step; p < T; p += step, ++k) {
-              const float Tx = nx, Ty = ny;
-              if (p + step < T) {
-                nx = bufs.samples_x[static_cast<size_t>(k + 1) * B + b];
-                ny = bufs.samples_y[static_cast<size_t>(k + 1) * B + b];
-              }
-              float dx = __fsub_rn(Tx, prev_x), dy = __fsub_rn(Ty, prev_y);
-              traj_d = __fadd_rn(traj_d, __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
-              path_pt = find_closest_path_pt(s_D, furthest, traj_d, path_pt);
-              if (s_valid[path_pt]) {
-                dx = __fsub_rn(__ldg(path_x + path_pt), Tx);
-                dy = __fsub_rn(__ldg(path_y + path_pt), Ty);
-                num = __fadd_rn(num, 1.0f);
-                if (P->align_use_yaw) {
-                  const float Tyaw = bufs.samples_yaw[static_cast<size_t>(k) * B + b];
-                  const float dyaw = static_cast<float>(normalize_angle_d(static_cast<double>(Tyaw) - static_cast<double>(__ldg(path_yaw + path_pt))));
-                  summed = __fadd_rn(summed, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dyaw, dyaw))));
-                } else {
-                  summed = __fadd_rn(summed, __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
-                }
-              }
-              prev_x = Tx; prev_y = Ty;
+// One trajectory: the path critics, then the total in critic-list order (fail_flag short-circuit) and the gamma term.
+__device__ __forceinline__ float k3_trajectory_total(
+  int b, const DevParams * P, const K3Decisions & dec, const K3Path & path, const DevBuffers & bufs, int iteration)
+{
+  const int T = P->T, B = P->B, N = P->N, nc = P->n_critics;
+  const int fail_at = dec.fail_at, furthest = dec.furthest;
+  const float * s_D = path.s_D;
+  const uint8_t * s_valid = path.s_valid;
+  const float * __restrict__ path_x = path.x;
+  const float * __restrict__ path_y = path.y;
+  const float * __restrict__ path_yaw = path.yaw;
+  float total = (iteration == 0 && P->mode == 0) ? 0.0f : bufs.costs[b];
+  float * rows = bufs.crit_rows;
+  for (int q = 0; q < nc; ++q) {
+    if (q > fail_at) {break;}
+    const int kind = P->kind_of[q];
+    float term = 0.0f;
+    bool has = false;
+    switch (kind) {
+      case MPPI_CRITIC_PATH_FOLLOW:
+        if (P->follow.on) {    // path_follow_critic.cpp:60-70
+          const float dx = bufs.end_xy[b] - __ldg(path_x + dec.follow_idx);
+          const float dy = bufs.end_xy[B + b] - __ldg(path_y + dec.follow_idx);
+          term = add_pow(0.0f, P->follow.weight * sqrtf(dx * dx + dy * dy), P->follow.power);
+          has = true;
+        }
+        break;
+      case MPPI_CRITIC_PATH_ALIGN:
+        if (dec.align_go) {     // path_align_critic.cpp:92-135, sequential and in the reference's fp32 order
+          const int step = P->align_step;
+          float traj_d = 0.0f, summed = 0.0f, num = 0.0f;
+          int path_pt = 0;
+          float prev_x = bufs.samples_x[b], prev_y = bufs.samples_y[b];
+          int k = 1;
+          float nx = 0.0f, ny = 0.0f;   // one-deep prefetch of the next sampled pose (L2 latency off the serial chain)
+          if (step < T) {nx = bufs.samples_x[static_cast<size_t>(B) + b]; ny = bufs.samples_y[static_cast<size_t>(B) + b];}
+          for (int p = step; p < T; p += step, ++k) {
+            const float Tx = nx, Ty = ny;
+            if (p + step < T) {
+              nx = bufs.samples_x[static_cast<size_t>(k + 1) * B + b];
+              ny = bufs.samples_y[static_cast<size_t>(k + 1) * B + b];
             }
-            const float cost = num > 0.0f ? __fdiv_rn(summed, num) : 0.0f;
-            term = add_pow(0.0f, __fmul_rn(cost, P->align.weight), P->align.power);
-            has = true;
-          }
-          break;
-        case MPPI_CRITIC_PATH_ALIGN_LEGACY:
-          if (sc_legacy_go) {    // path_align_legacy_critic.cpp:97-128
-            const int step = P->legacy_step;
-            const int segs = N - 1;
-            float summed = 0.0f;
-            int k = 1;
-            for (int p = step; p < T; p += step, ++k) {
-              const float Tx = bufs.samples_x[static_cast<size_t>(k) * B + b];
-              const float Ty = bufs.samples_y[static_cast<size_t>(k) * B + b];
-              float Tyaw = 0.0f;
-              if (P->legacy_use_yaw) {Tyaw = bufs.samples_yaw[static_cast<size_t>(k) * B + b];}
-              float min_d = 3.402823466e+38f;
-              int min_s = 0;
-              for (int s = 0; s < segs - 1; ++s) {
-                const float dx = __fsub_rn(__ldg(path_x + s), Tx);
-                const float dy = __fsub_rn(__ldg(path_y + s), Ty);
-                float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-                if (P->legacy_use_yaw) {
-                  const float dyaw = static_cast<float>(normalize_angle_d(static_cast<double>(Tyaw) - static_cast<double>(__ldg(path_yaw + s))));
-                  d = __fadd_rn(d, __fmul_rn(dyaw, dyaw));
-                }
-                if (d < min_d) {min_d = d; min_s = s;}
+            float dx = __fsub_rn(Tx, prev_x), dy = __fsub_rn(Ty, prev_y);
+            traj_d = __fadd_rn(traj_d, __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
+            path_pt = find_closest_path_pt(s_D, furthest, traj_d, path_pt);
+            if (s_valid[path_pt]) {
+              dx = __fsub_rn(__ldg(path_x + path_pt), Tx);
+              dy = __fsub_rn(__ldg(path_y + path_pt), Ty);
+              num = __fadd_rn(num, 1.0f);
+              if (P->align_use_yaw) {
+                const float Tyaw = bufs.samples_yaw[static_cast<size_t>(k) * B + b];
+                const float dyaw = static_cast<float>(normalize_angle_d(static_cast<double>(Tyaw) - static_cast<double>(__ldg(path_yaw + path_pt))));
+                summed = __fadd_rn(summed, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dyaw, dyaw))));
+              } else {
+                summed = __fadd_rn(summed, __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
               }
-              if (min_s != 0 && s_valid[min_s]) {summed = __fadd_rn(summed, __fsqrt_rn(min_d));}
             }
-            const float evals = static_cast<float>(T / step);
-            term = add_pow(0.0f, __fmul_rn(__fdiv_rn(summed, evals), P->legacy.weight), P->legacy.power);
-            has = true;
+            prev_x = Tx; prev_y = Ty;
           }
-          break;
-        case MPPI_CRITIC_PATH_ANGLE:
-          if (sc_angle_go) {     // path_angle_critic.cpp:85-100
-            const float gx = __ldg(path_x + sc_angle_idx), gy = __ldg(path_y + sc_angle_idx);
-            float sum = 0.0f;
-            for (int t = 0; t < T; ++t) {
-              const size_t g = static_cast<size_t>(t) * B + b;
-              const float x = bufs.spill_x[g], y = bufs.spill_y[g], yaw = bufs.spill_yaw[g];
-              const float ybp = atan2f(__fsub_rn(gy, y), __fsub_rn(gx, x));
-              double v = fabs(normalize_angle_d(static_cast<double>(__fsub_rn(ybp, yaw))));
-              if (P->angle_reversing && !P->angle_forward_pref) {
-                const double corrected = v < 1.57079632679489661923 ? static_cast<double>(ybp) :
-                  normalize_angle_d(static_cast<double>(ybp) + 3.14159265358979323846);
-                v = fabs(normalize_angle_d(corrected - static_cast<double>(yaw)));
+          const float cost = num > 0.0f ? __fdiv_rn(summed, num) : 0.0f;
+          term = add_pow(0.0f, __fmul_rn(cost, P->align.weight), P->align.power);
+          has = true;
+        }
+        break;
+      case MPPI_CRITIC_PATH_ALIGN_LEGACY:
+        if (dec.legacy_go) {    // path_align_legacy_critic.cpp:97-128
+          const int step = P->legacy_step;
+          const int segs = N - 1;
+          float summed = 0.0f;
+          int k = 1;
+          for (int p = step; p < T; p += step, ++k) {
+            const float Tx = bufs.samples_x[static_cast<size_t>(k) * B + b];
+            const float Ty = bufs.samples_y[static_cast<size_t>(k) * B + b];
+            float Tyaw = 0.0f;
+            if (P->legacy_use_yaw) {Tyaw = bufs.samples_yaw[static_cast<size_t>(k) * B + b];}
+            float min_d = 3.402823466e+38f;
+            int min_s = 0;
+            for (int sgm = 0; sgm < segs - 1; ++sgm) {
+              const float dx = __fsub_rn(__ldg(path_x + sgm), Tx);
+              const float dy = __fsub_rn(__ldg(path_y + sgm), Ty);
+              float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+              if (P->legacy_use_yaw) {
+                const float dyaw = static_cast<float>(normalize_angle_d(static_cast<double>(Tyaw) - static_cast<double>(__ldg(path_yaw + sgm))));
+                d = __fadd_rn(d, __fmul_rn(dyaw, dyaw));
               }
-              sum += static_cast<float>(v);
+              if (d < min_d) {min_d = d; min_s = sgm;}
             }
-            term = add_pow(0.0f, (sum / static_cast<float>(T)) * P->angle.weight, P->angle.power);
-            has = true;
+            if (min_s != 0 && s_valid[min_s]) {summed = __fadd_rn(summed, __fsqrt_rn(min_d));}
           }
-          break;
-        case MPPI_CRITIC_CONSTRAINT: has = P->constraint.on; break;
-        case MPPI_CRITIC_COST: has = P->cost.on; break;
-        case MPPI_CRITIC_GOAL: has = P->goal.on; break;
-        case MPPI_CRITIC_GOAL_ANGLE: has = P->goal_angle.on; break;
-        case MPPI_CRITIC_OBSTACLES: has = P->obst.on; break;
-        case MPPI_CRITIC_PREFER_FORWARD: has = P->forward.on; break;
-        case MPPI_CRITIC_TWIRLING: has = P->twirl.on; break;
-        case MPPI_CRITIC_VELOCITY_DEADBAND: has = P->deadband.on; break;
-        default: break;
-      }
-      const bool from_k3 = kind == MPPI_CRITIC_PATH_FOLLOW || kind == MPPI_CRITIC_PATH_ALIGN ||
-        kind == MPPI_CRITIC_PATH_ALIGN_LEGACY || kind == MPPI_CRITIC_PATH_ANGLE;
-      if (from_k3) {
-        rows[static_cast<size_t>(q) * B + b] = term;   // always defined for the per-critic getter
-      } else if (has) {
-        term = rows[static_cast<size_t>(q) * B + b];
-      }
-      if (has) {total = __fadd_rn(total, term);}
+          const float evals = static_cast<float>(T / step);
+          term = add_pow(0.0f, __fmul_rn(__fdiv_rn(summed, evals), P->legacy.weight), P->legacy.power);
+          has = true;
+        }
+        break;
+      case MPPI_CRITIC_PATH_ANGLE:
+        if (dec.angle_go) {     // path_angle_critic.cpp:85-100
+          const float gx = __ldg(path_x + dec.angle_idx), gy = __ldg(path_y + dec.angle_idx);
+          float sum = 0.0f;
+          for (int t = 0; t < T; ++t) {
+            const size_t g = static_cast<size_t>(t) * B + b;
+            const float x = bufs.spill_x[g], y = bufs.spill_y[g], yaw = bufs.spill_yaw[g];
+            const float ybp = atan2f(__fsub_rn(gy, y), __fsub_rn(gx, x));
+            double v = fabs(normalize_angle_d(static_cast<double>(__fsub_rn(ybp, yaw))));
+            if (P->angle_reversing && !P->angle_forward_pref) {
+              const double corrected = v < 1.57079632679489661923 ? static_cast<double>(ybp) :
+                normalize_angle_d(static_cast<double>(ybp) + 3.14159265358979323846);
+              v = fabs(normalize_angle_d(corrected - static_cast<double>(yaw)));
+            }
+            sum += static_cast<float>(v);
+          }
+          term = add_pow(0.0f, (sum / static_cast<float>(T)) * P->angle.weight, P->angle.power);
+          has = true;
+        }
+        break;
+      case MPPI_CRITIC_CONSTRAINT: has = P->constraint.on; break;
+      case MPPI_CRITIC_COST: has = P->cost.on; break;
+      case MPPI_CRITIC_GOAL: has = P->goal.on; break;
+      case MPPI_CRITIC_GOAL_ANGLE: has = P->goal_angle.on; break;
+      case MPPI_CRITIC_OBSTACLES: has = P->obst.on; break;
+      case MPPI_CRITIC_PREFER_FORWARD: has = P->forward.on; break;
+      case MPPI_CRITIC_TWIRLING: has = P->twirl.on; break;
+      case MPPI_CRITIC_VELOCITY_DEADBAND: has = P->deadband.on; break;
+      default: break;
     }
-    // rows of critics that did not run read as zero for the getter
+    const bool from_k3 = kind == MPPI_CRITIC_PATH_FOLLOW || kind == MPPI_CRITIC_PATH_ALIGN ||
+      kind == MPPI_CRITIC_PATH_ALIGN_LEGACY || kind == MPPI_CRITIC_PATH_ANGLE;
+    if (from_k3) {
+      rows[static_cast<size_t>(q) * B + b] = term;   // always defined for the per-critic getter
+    } else if (has) {
+      term = rows[static_cast<size_t>(q) * B + b];
+    }
+    if (has) {total = __fadd_rn(total, term);}
+  }
+  if (P->want_critic_rows) {
+    // rows of critics that did not run read as zero for the per-critic getter (mppi_get_critic_costs)
     for (int q = 0; q < nc; ++q) {
       const int kind = P->kind_of[q];
       const bool from_k3 = kind == MPPI_CRITIC_PATH_FOLLOW || kind == MPPI_CRITIC_PATH_ALIGN ||
@@ -1230,15 +1210,101 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
       }
       if (q > fail_at || (!from_k3 && !on)) {rows[static_cast<size_t>(q) * B + b] = 0.0f;}
     }
-    if (P->mode == 0) {
-      // gamma term (optimizer.cpp:367-380): vx, then wz, then vy (holonomic)
-      const size_t g = static_cast<size_t>(nc) * B + b;
-      total = __fadd_rn(total, __fmul_rn(P->gamma_vx, rows[g]));
-      total = __fadd_rn(total, __fmul_rn(P->gamma_wz, rows[g + 2 * static_cast<size_t>(B)]));
-      if (P->holonomic) {total = __fadd_rn(total, __fmul_rn(P->gamma_vy, rows[g + B]));}
-    }
-    bufs.costs[b] = total;
   }
+  if (P->mode == 0) {
+    // gamma term (optimizer.cpp:367-380): vx, then wz, then vy (holonomic)
+    const size_t g = static_cast<size_t>(nc) * B + b;
+    total = __fadd_rn(total, __fmul_rn(P->gamma_vx, rows[g]));
+    total = __fadd_rn(total, __fmul_rn(P->gamma_wz, rows[g + 2 * static_cast<size_t>(B)]));
+    if (P->holonomic) {total = __fadd_rn(total, __fmul_rn(P->gamma_vy, rows[g + B]));}
+  }
+  bufs.costs[b] = total;
+  return total;
+}
+
+// flags of the pass, published by the last block to finish
+__device__ __forceinline__ void k3_publish_flags(const DevParams * P, DevState * st, const K3Decisions & dec, float * out)
+{
+  const int T = P->T;
+  st->fail_flag = dec.fail_at < P->n_critics ? 1 : 0;
+  st->furthest = static_cast<unsigned>(dec.furthest);
+  st->furthest_set = dec.furthest_set;
+  st->furthest_candidate = 0u;
+  for (int q = 0; q < kMaxCritics; ++q) {st->any_ok[q] = 0u;}
+  st->ticket = 0u;
+  out[3 * T] = __int_as_float(st->fail_flag);
+  out[3 * T + 1] = __uint_as_float(dec.furthest_set ? static_cast<unsigned>(dec.furthest) : kUnset);
+}
+
+// K3, stream layout: path critics + totals for every trajectory (grid-stride: the preamble is paid once per block,
+// not once per 128 trajectories) and the global minimum of the costs; the weighted sums follow in
+// weighted_sums_tm_kernel.
+__global__ void __launch_bounds__(kUpdThreads) path_costs_tm_kernel(const DevParams * __restrict__ Pg, DevBuffers bufs, int iteration)
+{
+  extern __shared__ float smem[];
+  __shared__ K3Decisions dec;
+  __shared__ float s_red[kUpdThreads / 32];
+  __shared__ unsigned sc_last;
+  const int tid = threadIdx.x;
+  K3Path path;
+  k3_preamble(smem, Pg, bufs.st, iteration, tid, kUpdThreads, path, &dec);
+  const DevParams * P = reinterpret_cast<const DevParams *>(smem);
+  const int B = P->B, T = P->T;
+  float m = 3.402823466e+38f;
+  for (int b = blockIdx.x * kUpdThreads + tid; b < B; b += gridDim.x * kUpdThreads) {
+    m = fminf(m, k3_trajectory_total(b, P, dec, path, bufs, iteration));
+  }
+  m = warp_min(m);
+  if ((tid & 31) == 0) {s_red[tid >> 5] = m;}
+  __syncthreads();
+  const int stride = 3 * T + 2;
+  if (tid == 0) {
+#pragma unroll
+    for (int w = 1; w < kUpdThreads / 32; ++w) {m = fminf(m, s_red[w]);}
+    bufs.partials[static_cast<size_t>(blockIdx.x) * stride] = m;
+    __threadfence();
+    sc_last = atomicAdd(&bufs.st->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!sc_last) {return;}
+  __threadfence();
+  float gm = 3.402823466e+38f;
+  for (int i = tid; i < static_cast<int>(gridDim.x); i += kUpdThreads) {gm = fminf(gm, bufs.partials[static_cast<size_t>(i) * stride]);}
+  gm = warp_min(gm);
+  __syncthreads();
+  if ((tid & 31) == 0) {s_red[tid >> 5] = gm;}
+  __syncthreads();
+  if (tid == 0) {
+    gm = s_red[0];
+    for (int w = 1; w < kUpdThreads / 32; ++w) {gm = fminf(gm, s_red[w]);}
+    bufs.st->global_min = gm;
+    k3_publish_flags(P, bufs.st, dec, bufs.out);
+  }
+}
+
+__global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
+  const DevParams * __restrict__ Pg, DevBuffers bufs, int n_ranks, int iteration, int R)
+{
+  // R = trajectories owned by this block (multiple of 32, <= kUpdThreads): small batches use small R so that
+  // the update spreads over many SMs; the column sums always use all kUpdThreads threads
+  extern __shared__ float smem[];
+  __shared__ K3Decisions dec;
+  __shared__ unsigned sc_last;
+  const int tid = threadIdx.x;
+  K3Path path;
+  k3_preamble(smem, Pg, bufs.st, iteration, tid, kUpdThreads, path, &dec);
+  const DevParams * P = reinterpret_cast<const DevParams *>(smem);   // hot fields only; arrays stay in global (Pg)
+  const int T = P->T, B = P->B, nc = P->n_critics;
+  float * s_w = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(smem) + k3_common_smem_bytes());   // [kUpdThreads]
+  float * s_red = s_w + kUpdThreads;                                                                       // [32]
+  DevState * st = bufs.st;
+  const int fail_at = dec.fail_at;
+
+  // ---- phase 1: one thread per trajectory: path critics + total in list order
+  const int b = blockIdx.x * R + tid;
+  const bool live = tid < R && b < B;
+  float total = 3.402823466e+38f;
+  if (live) {total = k3_trajectory_total(b, P, dec, path, bufs, iteration);}
 
   if (P->mode != 0) {
     // score mode: no control update; the last block publishes the flags
@@ -1246,17 +1312,7 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
     __syncthreads();
     if (tid == 0) {sc_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;}
     __syncthreads();
-    if (sc_last && tid == 0) {
-      st->fail_flag = fail_at < nc ? 1 : 0;
-      st->furthest = static_cast<unsigned>(sc_furthest);
-      st->furthest_set = sc_furthest_set;
-      st->furthest_candidate = 0u;
-      for (int q = 0; q < kMaxCritics; ++q) {st->any_ok[q] = 0u;}
-      st->ticket = 0u;
-      float * out = bufs.out;
-      out[3 * T] = __int_as_float(st->fail_flag);
-      out[3 * T + 1] = __uint_as_float(sc_furthest_set ? static_cast<unsigned>(sc_furthest) : kUnset);
-    }
+    if (sc_last && tid == 0) {k3_publish_flags(P, st, dec, bufs.out);}
     return;
   }
 
@@ -1269,38 +1325,6 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
 #pragma unroll
   for (int w = 1; w < kUpdThreads / 32; ++w) {m = fminf(m, s_red[w]);}
   __syncthreads();
-  if (P->noise_tm) {
-    // stream layout: the weighted sums run as a separate, layout-friendly kernel (weighted_sums_tm_kernel) once the
-    // global minimum is known.  Publish this block's minimum; the last block reduces them and the flags.
-    const int stride_tm = 3 * T + 2;
-    if (tid == 0) {bufs.partials[static_cast<size_t>(blockIdx.x) * stride_tm] = m;}
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {sc_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;}
-    __syncthreads();
-    if (!sc_last) {return;}
-    __threadfence();
-    float gm = 3.402823466e+38f;
-    for (int i = tid; i < static_cast<int>(gridDim.x); i += kUpdThreads) {gm = fminf(gm, bufs.partials[static_cast<size_t>(i) * stride_tm]);}
-    gm = warp_min(gm);
-    if ((tid & 31) == 0) {s_red[tid >> 5] = gm;}
-    __syncthreads();
-    if (tid == 0) {
-      gm = s_red[0];
-      for (int w = 1; w < kUpdThreads / 32; ++w) {gm = fminf(gm, s_red[w]);}
-      st->global_min = gm;
-      st->fail_flag = fail_at < nc ? 1 : 0;
-      st->furthest = static_cast<unsigned>(sc_furthest);
-      st->furthest_set = sc_furthest_set;
-      st->furthest_candidate = 0u;
-      for (int q = 0; q < kMaxCritics; ++q) {st->any_ok[q] = 0u;}
-      st->ticket = 0u;
-      float * out = bufs.out;
-      out[3 * T] = __int_as_float(st->fail_flag);
-      out[3 * T + 1] = __uint_as_float(sc_furthest_set ? static_cast<unsigned>(sc_furthest) : kUnset);
-    }
-    return;
-  }
   const float w_b = live ? expf(-(total - m) * inv_temp) : 0.0f;
   s_w[tid] = w_b;
   float ssum = warp_sum(w_b);
@@ -1384,17 +1408,7 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
   __syncthreads();
   if (!sc_last) {return;}
   __threadfence();
-  if (tid == 0) {
-    st->fail_flag = fail_at < nc ? 1 : 0;
-    st->furthest = static_cast<unsigned>(sc_furthest);
-    st->furthest_set = sc_furthest_set;
-    st->furthest_candidate = 0u;
-    for (int q = 0; q < kMaxCritics; ++q) {st->any_ok[q] = 0u;}
-    st->ticket = 0u;
-    float * out = bufs.out;
-    out[3 * T] = __int_as_float(st->fail_flag);
-    out[3 * T + 1] = __uint_as_float(sc_furthest_set ? static_cast<unsigned>(sc_furthest) : kUnset);
-  }
+  if (tid == 0) {k3_publish_flags(P, st, dec, bufs.out);}
   if (static_cast<int>(gridDim.x) > kLastBlockMergeMax) {return;}
   float * merged = bufs.rank_partial;   // [3T + 2]
   merge_partials(bufs.partials, gridDim.x, stride, T, inv_temp, merged, s_red, tid, kUpdThreads);
@@ -1493,54 +1507,51 @@ __global__ void __launch_bounds__(kWsThreads) weighted_sums_tm_kernel(const DevP
 // applies the clip, so no broadcast is needed afterwards.  One block owns kMergeT time steps (3 columns each)
 // and all its threads stride over the partials; `finalize` = 0 writes the merged record to dst instead.
 
+constexpr int kMergeCached = 2048;   // partial records whose rescale factors are cached in shared memory
+
 __global__ void __launch_bounds__(kUpdThreads) merge_finalize_kernel(
   const DevParams * __restrict__ Pg, const float * __restrict__ parts, int n, int stride, DevBuffers bufs, int finalize,
   float * __restrict__ dst)
 {
   __shared__ float s_red[kUpdThreads / 32];
   __shared__ float s_col[3 * kMergeT + 1];
-  __shared__ float s_m;
-  const int tid = threadIdx.x;
+  __shared__ float s_e[kMergeCached];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = Pg->T;
   const float inv_temp = 1.0f / Pg->temperature;
   // global minimum over the partials
   float m = 3.402823466e+38f;
   for (int i = tid; i < n; i += kUpdThreads) {m = fminf(m, __ldg(parts + static_cast<size_t>(i) * stride));}
   m = warp_min(m);
-  if ((tid & 31) == 0) {s_red[tid >> 5] = m;}
+  if (lane == 0) {s_red[warp] = m;}
   __syncthreads();
-  if (tid == 0) {
-    float mm = s_red[0];
-    for (int w = 1; w < kUpdThreads / 32; ++w) {mm = fminf(mm, s_red[w]);}
-    s_m = mm;
+  m = s_red[0];
+#pragma unroll
+  for (int w = 1; w < kUpdThreads / 32; ++w) {m = fminf(m, s_red[w]);}
+  // rescale factor of every record, once
+  for (int i = tid; i < min(n, kMergeCached); i += kUpdThreads) {
+    s_e[i] = expf(-(__ldg(parts + static_cast<size_t>(i) * stride) - m) * inv_temp);
   }
   __syncthreads();
-  m = s_m;
   const int t_first = blockIdx.x * kMergeT;
-  // column 0 = sum of weights, then (vx, vy, wz) of each owned time step
-  for (int k = 0; k < 3 * kMergeT + 1; ++k) {
+  // column 0 = sum of weights, then (vx, vy, wz) of each owned time step; one warp per column, lanes over the records
+  for (int k = warp; k < 3 * kMergeT + 1; k += kUpdThreads / 32) {
     int col;   // index into the record after the leading m: 0 = s, 1 + plane * T + t = W
     if (k == 0) {
       col = 0;
     } else {
       const int t = t_first + (k - 1) / 3, plane = (k - 1) % 3;
-      if (t >= T) {break;}
+      if (t >= T) {continue;}
       col = 1 + plane * T + t;
     }
     float acc = 0.0f;
-    for (int i = tid; i < n; i += kUpdThreads) {
+    for (int i = lane; i < n; i += 32) {
       const float * p = parts + static_cast<size_t>(i) * stride;
-      acc = fmaf(__ldg(p + 1 + col), expf(-(__ldg(p) - m) * inv_temp), acc);
+      const float e = i < kMergeCached ? s_e[i] : expf(-(__ldg(p) - m) * inv_temp);
+      acc = fmaf(__ldg(p + 1 + col), e, acc);
     }
     acc = warp_sum(acc);
-    __syncthreads();
-    if ((tid & 31) == 0) {s_red[tid >> 5] = acc;}
-    __syncthreads();
-    if (tid == 0) {
-      float a = 0.0f;
-      for (int w = 0; w < kUpdThreads / 32; ++w) {a += s_red[w];}
-      s_col[k] = a;
-    }
+    if (lane == 0) {s_col[k] = acc;}
   }
   __syncthreads();
   if (tid < kMergeT && t_first + tid < T) {

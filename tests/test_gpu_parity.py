@@ -234,6 +234,7 @@ def test_full_size_properties_config3(product_fns):
     free = scenarios.config3()
     free.cycle.costmap = np.zeros_like(free.cycle.costmap)
     g.set_control_sequence(*(np.zeros(56, np.float32),) * 3)
+    g.set_outputs(critic_costs=True)
     g.optimize(free.cycle)
     assert not g.get_critic_costs(0).any()
 
