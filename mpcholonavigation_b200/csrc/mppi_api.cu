@@ -66,6 +66,9 @@ struct mppi_handle
   mppi_config cfg;
   Constraints base, cur;
   std::vector<mppi_critic_desc> critics;
+  std::vector<uint8_t> scratch_gate;       // build_params scratch (no allocation in the steady state)
+  std::vector<uint16_t> scratch_prefix;
+  std::vector<int> scratch_next;
   mppi_robot_desc robot;
   int B{0}, T{0};
   int device{0};
@@ -117,7 +120,6 @@ struct mppi_handle
   unsigned gkey_inst[2]{0, 0};
   bool use_graph{true};
   size_t costmap_bytes{0}, params_copy_bytes{0};
-  int upd_rows{kUpdThreads};   // trajectories per block of the update kernel
   // sharding
   ncclComm_t comm{nullptr};
   int rank{0}, nranks{1};
@@ -279,7 +281,7 @@ mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, un
 
   // path arrays behind the struct: x, y, yaw, arc-length prefix D (path_align_critic.cpp:83-90), PathAngle gate bytes
   float * tail = reinterpret_cast<float *>(h->h_params + sizeof(DevParams));
-  p.off_path_x = 0; p.off_path_y = N; p.off_path_yaw = 2 * N; p.off_path_D = 3 * N; p.off_gate = 4 * N;
+  p.off_path_x = 0; p.off_path_y = N; p.off_path_yaw = 2 * N; p.off_path_D = 3 * N;
   std::memcpy(tail, in->path_x, sizeof(float) * N);
   std::memcpy(tail + N, in->path_y, sizeof(float) * N);
   std::memcpy(tail + 2 * N, in->path_yaw, sizeof(float) * N);
@@ -291,14 +293,17 @@ mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, un
     const float curr_dist = sqrtf(dx * dx + dy * dy);
     D[i] = D[i - 1] + curr_dist;
   }
-  uint8_t * gate = reinterpret_cast<uint8_t *>(tail + 4 * N);
+  // host-made tables behind the path arrays: valid[n16] | flags[n16] | follow_idx[N] (uint16); see DevParams
   const int n16 = ((N + 15) / 16) * 16;
-  p.off_valid_bytes = n16;
-  p.off_invalid_prefix_bytes = 2 * n16;
-  uint8_t * valid = gate + p.off_valid_bytes;
-  uint16_t * invalid_before = reinterpret_cast<uint16_t *>(gate + p.off_invalid_prefix_bytes);
-  std::memset(gate, 0, 2 * n16 + sizeof(uint16_t) * (N + 1));
-  h->params_bytes = sizeof(DevParams) + sizeof(float) * 4 * N + 2 * n16 + sizeof(uint16_t) * (N + 1);
+  uint8_t * valid = reinterpret_cast<uint8_t *>(tail + 4 * N);
+  uint8_t * flags = valid + n16;
+  uint16_t * follow_tab = reinterpret_cast<uint16_t *>(valid + 2 * n16);
+  std::memset(valid, 0, 2 * n16 + sizeof(uint16_t) * N);
+  std::vector<uint8_t> & gate = h->scratch_gate;              // PathAngle gate per candidate target index
+  std::vector<uint16_t> & invalid_before = h->scratch_prefix; // number of invalid points among [0, j)
+  gate.assign(N, 0);
+  invalid_before.assign(N + 1, 0);
+  h->params_bytes = sizeof(DevParams) + sizeof(float) * 4 * N + 2 * n16 + sizeof(uint16_t) * N;
   // copy size rounded up to 64 path points so that the captured graph survives small changes of the pruned path
   {
     const size_t n64 = std::min<size_t>(MPPI_MAX_PATH_POINTS, ((static_cast<size_t>(N) + 63) / 64) * 64);
@@ -472,6 +477,47 @@ mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, un
       }
     }
   }
+  // ---- everything K3 decides from the furthest reached path point alone, tabulated per candidate value f
+  //      (the device only knows f after K2; path_follow_critic.cpp:45-58, path_align_critic.cpp:56-72,
+  //       path_angle_critic.cpp:73-83)
+  {
+    p.obstacle_q[0] = p.obstacle_q[1] = -1;
+    p.first_path_q = -1;
+    int nob = 0;
+    for (int q = 0; q < p.n_critics; ++q) {
+      const int kind = p.kind_of[q];
+      const bool obstacle_like = (kind == MPPI_CRITIC_COST && p.cost.on) || (kind == MPPI_CRITIC_OBSTACLES && p.obst.on);
+      if (obstacle_like && nob < 2) {p.obstacle_q[nob++] = q;}
+      const bool path_like = (kind == MPPI_CRITIC_PATH_FOLLOW && p.follow.on) || (kind == MPPI_CRITIC_PATH_ANGLE && p.angle.on) ||
+        (kind == MPPI_CRITIC_PATH_ALIGN && p.align.on) || (kind == MPPI_CRITIC_PATH_ALIGN_LEGACY && p.legacy.on);
+      if (path_like && p.first_path_q < 0) {p.first_path_q = q;}
+    }
+    // first valid index at or after i (N if none)
+    std::vector<int> & next_valid = h->scratch_next;
+    next_valid.assign(N + 1, N);
+    for (int i = N - 1; i >= 0; --i) {next_valid[i] = valid[i] ? i : next_valid[i + 1];}
+    const int path_size = N - 1;
+    auto align_gate = [&](int f, int offset, float max_ratio) -> bool {
+        if (f < offset) {return false;}
+        const int closest = p.closest_path_pt;
+        const float range = static_cast<float>(static_cast<long long>(f) - closest);
+        unsigned invalid_ctr = 0;
+        if (f > closest) {invalid_ctr = static_cast<unsigned>(invalid_before[f]) - static_cast<unsigned>(invalid_before[closest]);}
+        // the reference bails out of its counting loop as soon as ctr / range > ratio with ctr > 2; the count only
+        // grows and the range is fixed, so the final count decides
+        return !(invalid_ctr > 2 && static_cast<float>(invalid_ctr) / range > max_ratio);
+      };
+    for (int f = 0; f < N; ++f) {
+      int fidx = std::min(f + p.follow_offset, path_size);
+      if (fidx < path_size - 1) {fidx = std::min(next_valid[fidx], path_size - 1);}
+      follow_tab[f] = static_cast<uint16_t>(std::max(fidx, 0));
+      unsigned fl = 0;
+      if (align_gate(f, p.align_offset, p.align_max_ratio) && f > 0) {fl |= 1u;}
+      if (align_gate(f, p.legacy_offset, p.legacy_max_ratio) && (N - 1) >= 1) {fl |= 2u;}
+      if (gate[std::min(f + p.angle_offset, N - 1)]) {fl |= 4u;}
+      flags[f] = static_cast<uint8_t>(fl);
+    }
+  }
   p.spill_traj = ((h->want_mask & MPPI_WANT_TRAJECTORIES) || any_gate_open || mode == 1) ? 1 : 0;
   p.noise_tm = (h->stream_layout && mode == 0) ? 1 : 0;
   p.need_furthest = (p.follow.idx >= 0 || p.angle.idx >= 0 || p.align.idx >= 0 || p.legacy.idx >= 0) ? 1 : 0;
@@ -620,7 +666,7 @@ mppi_status launch_rollout(mppi_handle * h, int mode)
   if (smem > 227 * 1024) {return fail(h, MPPI_E_CONFIG, "time_steps too large for the shared-memory tile");}
   const dim3 grid((h->B + kTile - 1) / kTile), block(kTile, S);
   rollout_score_kernel<<<grid, block, smem, h->stream>>>(
-    reinterpret_cast<const DevParams *>(h->d_params), h->d_costmap, make_bufs(h, mode));
+    reinterpret_cast<const DevParams *>(h->d_params), h->d_costmap, make_bufs(h, mode), h->B, h->T, mode);
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   return MPPI_OK;
@@ -637,9 +683,8 @@ mppi_status launch_update(mppi_handle * h, int mode, int iteration)
     h->launches++;
     return MPPI_OK;
   }
-  const size_t smem = k3_common_smem_bytes() + sizeof(float) * (kUpdThreads + 32);
-  path_softmax_update_kernel<<<h->upd_blocks, kUpdThreads, smem, h->stream>>>(
-    reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, mode), h->nranks, iteration, h->upd_rows);
+  path_softmax_update_kernel<<<h->upd_blocks, kUpdThreads, k3_tile_smem_bytes(h->T), h->stream>>>(
+    reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, mode), h->nranks, iteration, h->B, h->T, mode);
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   return MPPI_OK;
@@ -838,6 +883,15 @@ extern "C" {
 
 int32_t mppi_abi_version(void) {return MPPI_ABI_VERSION;}
 
+#ifdef MPPI_TRACE
+// tuning aid (only in -DMPPI_TRACE builds): copies the phase trace of the last kernels
+int32_t mppi_debug_get_trace(long long * out, int32_t n)
+{
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, mppi::g_trace, sizeof(long long) * std::min(n, 64)) == cudaSuccess ? 0 : 1;
+}
+#endif
+
 void mppi_config_default(mppi_config * c)
 {
   std::memset(c, 0, sizeof(*c));
@@ -941,6 +995,8 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   }
   CUDA_TRY(h, cudaSetDevice(h->device));
   CUDA_TRY(h, cudaFuncSetAttribute(rollout_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CUDA_TRY(h, cudaFuncSetAttribute(path_softmax_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    static_cast<int>(k3_tile_smem_bytes(MPPI_MAX_TIME_STEPS))));
   CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CUDA_TRY(h, cudaEventCreate(&h->ev0));
   CUDA_TRY(h, cudaEventCreate(&h->ev1));
@@ -964,9 +1020,7 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   CUDA_TRY(h, cudaMemsetAsync(h->d_crit_rows, 0, (kMaxCritics + kGammaRows) * B * sizeof(float), h->stream));
   CUDA_TRY(h, cudaMalloc(&h->d_end_xy, 2 * B * sizeof(float)));
   CUDA_TRY(h, cudaMalloc(&h->d_costs, B * sizeof(float)));
-  h->upd_rows = B <= 32 * kLastBlockMergeMax ? 32 : kUpdThreads;
-  if (const char * e = std::getenv("MPPI_UPDATE_ROWS")) {h->upd_rows = std::max(32, std::min(kUpdThreads, (std::atoi(e) / 32) * 32));}
-  h->upd_blocks = static_cast<int>((B + h->upd_rows - 1) / h->upd_rows);
+  h->upd_blocks = static_cast<int>((B + kUpdRows - 1) / kUpdRows);
   const size_t stride = 3 * T + 2;
   CUDA_TRY(h, cudaMalloc(&h->d_partials, h->upd_blocks * stride * sizeof(float)));
   CUDA_TRY(h, cudaMalloc(&h->d_rank_partial, stride * sizeof(float)));

@@ -22,6 +22,15 @@
 namespace mppi
 {
 
+// Optional phase trace (build with -DMPPI_TRACE; tuning aid, not part of the product build): SM clock at phase
+// boundaries as seen by thread 0 of block 0, read back with mppi_debug_get_trace().
+#ifdef MPPI_TRACE
+__device__ long long g_trace[64];
+#define MPPI_TRACE_AT(i) do {if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) {g_trace[i] = clock64();}} while (0)
+#else
+#define MPPI_TRACE_AT(i) do {} while (0)
+#endif
+
 constexpr int kTile = 32;          // trajectories per tile == warp width (lane = trajectory)
 constexpr int kPad = 33;           // smem row pitch of the time-major tile [T][33]: conflict-free both ways
 constexpr int kMaxCritics = MPPI_MAX_CRITICS;
@@ -83,10 +92,12 @@ struct DevParams
   int need_furthest;                         // some path critic may ask for the furthest reached path point
   int noise_tm;                              // noise planes are stored time-major [T][B] (stream layout) instead of [B][T]
   // offsets (in floats) of the path arrays that follow this struct in the same buffer
-  int off_path_x, off_path_y, off_path_yaw, off_path_D, off_gate;
-  // byte offsets, relative to the gate bytes, of the host-decided path validity (utils::findPathCosts, utils.hpp:361-394)
-  // and of its prefix counts: invalid_before[j] = number of invalid points among [0, j), uint16
-  int off_valid_bytes, off_invalid_prefix_bytes;
+  int off_path_x, off_path_y, off_path_yaw, off_path_D;
+  // host-made tables behind the path arrays (build_params): valid[n16] (utils::findPathCosts, utils.hpp:361-394),
+  // flags[n16] and follow_idx[N] (uint16), the last two indexed by the furthest reached path point: bit 0 PathAlign
+  // gate, bit 1 PathAlignLegacy gate, bit 2 PathAngle gate; PathFollow's target index
+  int obstacle_q[2];                         // list positions of the enabled obstacle-type critics (Cost / Obstacles), -1 if none
+  int first_path_q;                          // list position of the first enabled path critic, -1 if none
   int closest_path_pt;                       // utils::findPathTrajectoryInitialPoint (utils.hpp:327-344), host decided
   int want_critic_rows;                      // per-critic rows are read back by the caller: keep them fully defined
   int fp_n;

@@ -147,20 +147,18 @@ __global__ void __launch_bounds__(256) noise_philox_kernel(
 #define MPPI_K2_MIN_BLOCKS 3
 #endif
 __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
-  const DevParams * __restrict__ P, const uint8_t * __restrict__ cm, DevBuffers bufs)
+  const DevParams * __restrict__ P, const uint8_t * __restrict__ cm, DevBuffers bufs, const int B, const int T, const int mode)
 {
+  // B, T and mode also live in the record, but as launch arguments they cost no memory round trip: the noise rows,
+  // the control sequence and the record are all requested at once when the kernel starts
   extern __shared__ float smem[];
   const int S = blockDim.y;
   const int lane = threadIdx.x, seg = threadIdx.y;
   const int tid = seg * kTile + lane;
   const int nthreads = S * kTile;
 
-  // hot part of the per-cycle record -> shared memory (one coalesced round trip instead of scattered loads)
   float * s_hot = smem;
-  load_hot_params(s_hot, P, tid, nthreads);
-  __syncthreads();
   const DevParams & p = *reinterpret_cast<const DevParams *>(s_hot);
-  const int T = p.T, B = p.B, mode = p.mode;
   const int tplane = T * kPad;
   float * s_cs = s_hot + kHotFloats;             // [3][T]
   float * s_v0 = s_cs + 3 * T;                   // [3][32] initial velocities per trajectory
@@ -177,26 +175,52 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
   const int b0 = blockIdx.x * kTile;
   const int b = b0 + lane;
   const bool live = b < B;
+
+  MPPI_TRACE_AT(0);
+  // ---- P1: stage the tile.  Warp `seg` owns rows seg, seg+S, ...; lane walks t (coalesced 128 B rows).
+  if (mode == 0) {
+    // noise first (raw), in batches of 4 (row, 32-column) items = 12 loads in flight per lane; the control
+    // sequence is added once it and the record have landed (same barrier)
+    const int ncol = (T + 31) >> 5;
+    const int nitems = ((kTile - seg + S - 1) / S) * ncol;
+    for (int i0 = 0; i0 < nitems; i0 += 4) {
+      float va[4], vb[4], vc[4];
+      int oo[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u;
+        const int ri = i / ncol, ci = i - ri * ncol;
+        const int r = seg + ri * S, t = (ci << 5) + lane;
+        const bool ok = i < nitems && t < T && b0 + r < B;
+        oo[u] = ok ? t * kPad + r : -1;
+        va[u] = vb[u] = vc[u] = 0.0f;
+        if (ok) {
+          const size_t g = static_cast<size_t>(b0 + r) * T + t;
+          va[u] = __ldg(bufs.in_a + g); vb[u] = __ldg(bufs.in_b + g); vc[u] = __ldg(bufs.in_c + g);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (oo[u] >= 0) {s_cvx[oo[u]] = va[u]; s_cvy[oo[u]] = vb[u]; s_cwz[oo[u]] = vc[u];}
+      }
+    }
+  }
+  MPPI_TRACE_AT(1);
+  for (int i = tid; i < 3 * T; i += nthreads) {s_cs[i] = bufs.cs[i];}
+  // hot part of the per-cycle record -> shared memory (one coalesced round trip instead of scattered loads)
+  load_hot_params(s_hot, P, tid, nthreads);
+  __syncthreads();
+  MPPI_TRACE_AT(2);
   const int hol = p.holonomic;
   const float dt = p.dt;
-
-  // ---- P1: stage the tile.  Warp `seg` walks rows seg, seg+S, ...; lane walks t (coalesced 128 B rows).
-  for (int i = tid; i < 3 * T; i += nthreads) {s_cs[i] = bufs.cs[i];}
-  __syncthreads();
   if (mode == 0) {
+    // setNoisedControls: c = control_sequence + noise (noise_generator.cpp:71-73), in place on this warp's rows
     for (int r = seg; r < kTile; r += S) {
-      const int rb = b0 + r;
-      if (rb < B) {
-        const float * __restrict__ pa = bufs.in_a + static_cast<size_t>(rb) * T;
-        const float * __restrict__ pb = bufs.in_b + static_cast<size_t>(rb) * T;
-        const float * __restrict__ pc = bufs.in_c + static_cast<size_t>(rb) * T;
-        int o = lane * kPad + r;
-        for (int t = lane; t < T; t += 32, o += 32 * kPad) {
-          // setNoisedControls: c = control_sequence + noise (noise_generator.cpp:71-73)
-          s_cvx[o] = __fadd_rn(s_cs[t], __ldg(pa + t));
-          s_cvy[o] = __fadd_rn(s_cs[T + t], __ldg(pb + t));
-          s_cwz[o] = __fadd_rn(s_cs[2 * T + t], __ldg(pc + t));
-        }
+      int o = lane * kPad + r;
+      for (int t = lane; t < T; t += 32, o += 32 * kPad) {
+        s_cvx[o] = __fadd_rn(s_cs[t], s_cvx[o]);
+        s_cvy[o] = __fadd_rn(s_cs[T + t], s_cvy[o]);
+        s_cwz[o] = __fadd_rn(s_cs[2 * T + t], s_cwz[o]);
       }
     }
     // updateInitialStateVelocities (optimizer.cpp:258-267): v[:,0] = robot speed
@@ -231,6 +255,7 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
   }
   __syncthreads();
 
+  MPPI_TRACE_AT(3);
   // my segment of the horizon, and the state velocities just before it (read before anyone overwrites a plane)
   const int L = (T + S - 1) / S;
   const int t0 = min(T, seg * L), t1 = min(T, t0 + L);
@@ -262,6 +287,7 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
   }
   __syncthreads();
 
+  MPPI_TRACE_AT(4);
   // ---- P3: velocity critics + gamma term, then dx*dt / dy*dt with the one-step yaw lag written in place
   float acc[A_COUNT];
 #pragma unroll
@@ -321,6 +347,7 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
     acc[A_CON] = a_con; acc[A_FWD] = a_fwd; acc[A_TWIRL] = a_twirl; acc[A_DB] = a_db;
   }
 
+  MPPI_TRACE_AT(5);
   if (mode != 2) {
     __syncthreads();
     // ---- P4: x = pose.x (double) + cumsum(dx*dt) (float), sequential in t (optimizer.cpp:339-342)
@@ -352,6 +379,7 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
   }
   __syncthreads();
 
+  MPPI_TRACE_AT(6);
   // ---- P5: position critics + spills, parallel over (trajectory, segment of the horizon)
   if (live) {
     const bool goal_on = p.goal.on, gang_on = p.goal_angle.on, cost_on = p.cost.on, ob_on = p.obst.on;
@@ -445,6 +473,7 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
 #pragma unroll
   for (int k = 0; k < A_COUNT; ++k) {s_acc[(seg * A_COUNT + k) * kTile + lane] = acc[k];}
 
+  MPPI_TRACE_AT(7);
   // ---- furthest reached path point candidate: argmin over the path of the end pose (utils.hpp:292-319),
   //      path range split over the warps, combined in order so the first minimum wins
   const int N = p.N;
@@ -468,6 +497,7 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
   }
   __syncthreads();
 
+  MPPI_TRACE_AT(8);
   // ---- P6: combine the segments in order, finish the per-critic terms, publish
   if (seg == 0) {
     float tot[A_COUNT];
@@ -531,6 +561,7 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
       if (lane == 0) {atomicMax(&bufs.st->furthest_candidate, m);}
     }
   }
+  MPPI_TRACE_AT(9);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -935,6 +966,7 @@ __device__ __forceinline__ void merge_partials(
   __syncthreads();
   for (int c = tid; c < 3 * T + 1; c += nthr) {
     float acc = 0.0f;
+#pragma unroll 8
     for (int i = 0; i < n; ++i) {
       const float * p = parts + static_cast<size_t>(i) * stride;
       acc = fmaf(p[1 + c], p[0], acc);
@@ -954,48 +986,76 @@ struct K3Decisions
   int align_go, legacy_go, angle_go, angle_idx;
 };
 
-// shared-memory carve-up common to the K3 kernels: hot params | D[N] | valid[N]
-__host__ __device__ inline size_t k3_common_smem_bytes() {return kHotBytes + sizeof(float) * MPPI_MAX_PATH_POINTS + MPPI_MAX_PATH_POINTS;}
+// shared-memory carve-up common to the K3 kernels: hot | D[N] | path x[N] | path y[N] | valid[N] | flags[N] | follow_idx[N]
+__host__ __device__ inline size_t k3_common_smem_bytes()
+{
+  return kHotBytes + 3 * sizeof(float) * MPPI_MAX_PATH_POINTS + 2 * MPPI_MAX_PATH_POINTS + sizeof(uint16_t) * (MPPI_MAX_PATH_POINTS + 16);
+}
 
 struct K3Path
 {
   const float * x, * y, * yaw;     // global (read through the read-only path)
-  const uint8_t * gate;            // PathAngle gate per candidate index (host decided)
   const float * s_D;               // shared: arc-length prefix
+  const float * s_x, * s_y;        // shared copies of the path points (PathAlign's data-dependent look-ups)
   const uint8_t * s_valid;         // shared: path point validity (utils::findPathCosts, host decided)
 };
 
-// copies the hot record, D and the validity bytes into shared memory and lets thread 0 take the decisions
+// Copies the hot record, the path and its host-made tables into shared memory and lets thread 0 take the decisions.
+// Memory round trips are the cost here (a cold record is ~1 us away), so everything is requested in one wave.  The
+// decisions that depend on device results (which critic failed, the furthest reached point) are a handful of
+// table look-ups: everything that is a function of "furthest" alone was tabulated by the host (build_params).
 __device__ __forceinline__ void k3_preamble(
   float * smem, const DevParams * __restrict__ Pg, DevState * st, int iteration, int tid, int nthr, K3Path & path, K3Decisions * dec)
 {
+  __shared__ unsigned s_any_ok[kMaxCritics];
+  __shared__ unsigned s_state[4];   // furthest_candidate, furthest, furthest_set, fail_flag
   float * s_hot = smem;
+  const int N = Pg->N;              // read straight from the record: the path copies need not wait for the barrier
   load_hot_params(s_hot, Pg, tid, nthr);
-  __syncthreads();
+  if (tid < kMaxCritics) {s_any_ok[tid] = st->any_ok[tid];}
+  if (tid == 32) {s_state[0] = st->furthest_candidate; s_state[1] = st->furthest;}
+  if (tid == 33) {s_state[2] = static_cast<unsigned>(st->furthest_set); s_state[3] = static_cast<unsigned>(st->fail_flag);}
   const DevParams * P = reinterpret_cast<const DevParams *>(s_hot);
-  const int N = P->N, nc = P->n_critics;
   const float * tail = reinterpret_cast<const float *>(Pg + 1);
-  path.x = tail + P->off_path_x; path.y = tail + P->off_path_y; path.yaw = tail + P->off_path_yaw;
-  path.gate = reinterpret_cast<const uint8_t *>(tail + P->off_gate);
-  const uint8_t * g_valid = path.gate + P->off_valid_bytes;
-  const uint16_t * g_invalid_before = reinterpret_cast<const uint16_t *>(path.gate + P->off_invalid_prefix_bytes);
+  // record tail layout (build_params): x[N] y[N] yaw[N] D[N] | valid[n16] flags[n16] follow_idx[N] (uint16)
+  const int n16 = ((N + 15) / 16) * 16;
+  path.x = tail; path.y = tail + N; path.yaw = tail + 2 * N;
+  const uint8_t * g_valid = reinterpret_cast<const uint8_t *>(tail + 4 * N);
+  const uint8_t * g_flags = g_valid + n16;
+  const uint16_t * g_follow = reinterpret_cast<const uint16_t *>(g_valid + 2 * n16);
   float * s_D = s_hot + kHotFloats;
-  uint8_t * s_valid = reinterpret_cast<uint8_t *>(s_D + MPPI_MAX_PATH_POINTS);
-  path.s_D = s_D; path.s_valid = s_valid;
-  const bool any_path_critic = (P->follow.on || P->align.on || P->legacy.on || P->angle.on);
-  if (any_path_critic) {
-    const float * g_D = tail + P->off_path_D;
-    for (int j = tid; j < N; j += nthr) {s_D[j] = __ldg(g_D + j); s_valid[j] = __ldg(g_valid + j);}
+  float * s_px = s_D + MPPI_MAX_PATH_POINTS, * s_py = s_px + MPPI_MAX_PATH_POINTS;
+  uint8_t * s_valid = reinterpret_cast<uint8_t *>(s_py + MPPI_MAX_PATH_POINTS);
+  uint8_t * s_flags = s_valid + MPPI_MAX_PATH_POINTS;
+  uint16_t * s_follow = reinterpret_cast<uint16_t *>(s_flags + MPPI_MAX_PATH_POINTS);
+  path.s_D = s_D; path.s_x = s_px; path.s_y = s_py; path.s_valid = s_valid;
+  {
+    const float * g_D = tail + 3 * N;
+    for (int j = tid; j < N; j += nthr) {
+      s_D[j] = __ldg(g_D + j); s_px[j] = __ldg(path.x + j); s_py[j] = __ldg(path.y + j);
+      s_valid[j] = __ldg(g_valid + j); s_flags[j] = __ldg(g_flags + j); s_follow[j] = __ldg(g_follow + j);
+    }
   }
+  MPPI_TRACE_AT(24);
+  __syncthreads();
+  MPPI_TRACE_AT(25);
+#ifdef MPPI_TRACE
+  for (int rep = 0; rep < 2; ++rep) {
+  MPPI_TRACE_AT(27 + rep);
+#endif
   if (tid == 0) {
+    const int nc = P->n_critics;
+    // CriticManager::evalTrajectoriesScores (critic_manager.cpp:67-76): the first obstacle-type critic (list order)
+    // that saw no surviving trajectory raises fail_flag; critics after it are skipped
     int fail_at = nc;
-    if (iteration > 0 && st->fail_flag) {
+    if (iteration > 0 && s_state[3]) {
       fail_at = -1;     // fail_flag is only cleared in prepare(): a failed iteration mutes the following ones
     } else {
-      for (int q = 0; q < nc; ++q) {
-        const int kind = P->kind_of[q];
-        const bool obstacle_like = (kind == MPPI_CRITIC_COST && P->cost.on) || (kind == MPPI_CRITIC_OBSTACLES && P->obst.on);
-        if (obstacle_like && st->any_ok[q] == 0u) {fail_at = q; break;}
+      const int q0 = P->obstacle_q[0], q1 = P->obstacle_q[1];
+      if (q0 >= 0 && s_any_ok[q0] == 0u) {
+        fail_at = q0;
+      } else if (q1 >= 0 && s_any_ok[q1] == 0u) {
+        fail_at = q1;
       }
     }
     unsigned furthest;
@@ -1003,57 +1063,25 @@ __device__ __forceinline__ void k3_preamble(
     if (iteration == 0) {
       fset = P->preset_furthest != kUnset; furthest = fset ? P->preset_furthest : 0u;
     } else {
-      fset = st->furthest_set; furthest = st->furthest;
+      fset = static_cast<int>(s_state[2]); furthest = s_state[1];
     }
-    auto runs = [&](const CriticCommon & c) {return c.on && c.idx <= fail_at;};
-    // the first critic in list order that calls setPathFurthestPointIfNotSet fixes it for the cycle
-    for (int q = 0; q < nc && !fset; ++q) {
-      if (q > fail_at) {break;}
-      const int kind = P->kind_of[q];
-      const bool wants = (kind == MPPI_CRITIC_PATH_FOLLOW && P->follow.on) || (kind == MPPI_CRITIC_PATH_ANGLE && P->angle.on) ||
-        (kind == MPPI_CRITIC_PATH_ALIGN && P->align.on) || (kind == MPPI_CRITIC_PATH_ALIGN_LEGACY && P->legacy.on);
-      if (wants) {furthest = st->furthest_candidate; fset = 1;}
-    }
+    // the first enabled path critic in list order calls setPathFurthestPointIfNotSet (utils.hpp:350-355)
+    if (!fset && P->first_path_q >= 0 && P->first_path_q <= fail_at) {furthest = s_state[0]; fset = 1;}
+    const int f = min(static_cast<int>(furthest), N - 1);
+    const unsigned flags = s_flags[f];
     dec->fail_at = fail_at;
     dec->furthest = static_cast<int>(furthest);
     dec->furthest_set = fset;
-    // PathFollow target (path_follow_critic.cpp:45-58)
-    int fidx = 0;
-    if (runs(P->follow)) {
-      const int path_size = N - 1;
-      fidx = min(static_cast<int>(furthest) + P->follow_offset, path_size);
-      bool valid = false;
-      while (!valid && fidx < path_size - 1) {
-        valid = __ldg(g_valid + fidx) != 0;
-        if (!valid) {fidx++;}
-      }
-    }
-    dec->follow_idx = fidx;
-    // PathAlign gates (path_align_critic.cpp:56-72).  The reference counts invalid points from the closest point up
-    // to the furthest one and bails out as soon as count / range > ratio with count > 2; the count only grows and
-    // the range is fixed, so the final count decides: O(1) with the host's prefix counts.
-    auto align_gate = [&](const CriticCommon & c, int offset, float max_ratio) -> int {
-        if (!runs(c)) {return 0;}
-        if (static_cast<int>(furthest) < offset) {return 0;}
-        const int closest = P->closest_path_pt;
-        const float range = static_cast<float>(static_cast<long long>(furthest) - closest);
-        unsigned invalid_ctr = 0;
-        if (static_cast<int>(furthest) > closest) {
-          invalid_ctr = static_cast<unsigned>(g_invalid_before[furthest]) - static_cast<unsigned>(g_invalid_before[closest]);
-        }
-        if (invalid_ctr > 2 && static_cast<float>(invalid_ctr) / range > max_ratio) {return 0;}
-        return 1;
-      };
-    dec->align_go = align_gate(P->align, P->align_offset, P->align_max_ratio) && furthest > 0u;
-    dec->legacy_go = align_gate(P->legacy, P->legacy_offset, P->legacy_max_ratio) && (N - 1) >= 1;
-    // PathAngle gate (path_angle_critic.cpp:73-83): decided per candidate index on the host
-    int ago = 0, aidx = 0;
-    if (runs(P->angle)) {
-      aidx = min(static_cast<int>(furthest) + P->angle_offset, N - 1);
-      ago = path.gate[aidx] != 0;
-    }
-    dec->angle_go = ago; dec->angle_idx = aidx;
+    dec->follow_idx = (P->follow.on && P->follow.idx <= fail_at) ? s_follow[f] : 0;
+    dec->align_go = (P->align.on && P->align.idx <= fail_at && (flags & 1u)) ? 1 : 0;
+    dec->legacy_go = (P->legacy.on && P->legacy.idx <= fail_at && (flags & 2u)) ? 1 : 0;
+    dec->angle_go = (P->angle.on && P->angle.idx <= fail_at && (flags & 4u)) ? 1 : 0;
+    dec->angle_idx = min(static_cast<int>(furthest) + P->angle_offset, N - 1);
   }
+#ifdef MPPI_TRACE
+  }
+#endif
+  MPPI_TRACE_AT(26);
   __syncthreads();
 }
 
@@ -1070,6 +1098,24 @@ __device__ __forceinline__ float k3_trajectory_total(
   const float * __restrict__ path_yaw = path.yaw;
   float total = (iteration == 0 && P->mode == 0) ? 0.0f : bufs.costs[b];
   float * rows = bufs.crit_rows;
+  // every K2 row this trajectory will need, requested up front: one memory round trip instead of one per critic
+  float row_v[kMaxCritics];
+#pragma unroll
+  for (int q = 0; q < kMaxCritics; ++q) {
+    row_v[q] = 0.0f;
+    if (q < nc && q <= fail_at) {
+      const int kind = P->kind_of[q];
+      const bool from_k3 = kind == MPPI_CRITIC_PATH_FOLLOW || kind == MPPI_CRITIC_PATH_ALIGN ||
+        kind == MPPI_CRITIC_PATH_ALIGN_LEGACY || kind == MPPI_CRITIC_PATH_ANGLE;
+      if (!from_k3) {row_v[q] = rows[static_cast<size_t>(q) * B + b];}
+    }
+  }
+  float gam[3] = {0.0f, 0.0f, 0.0f};
+  if (P->mode == 0) {
+    const size_t g = static_cast<size_t>(nc) * B + b;
+    gam[0] = rows[g]; gam[1] = rows[g + B]; gam[2] = rows[g + 2 * static_cast<size_t>(B)];
+  }
+  const float end_x = bufs.end_xy[b], end_y = bufs.end_xy[B + b];
   for (int q = 0; q < nc; ++q) {
     if (q > fail_at) {break;}
     const int kind = P->kind_of[q];
@@ -1078,8 +1124,8 @@ __device__ __forceinline__ float k3_trajectory_total(
     switch (kind) {
       case MPPI_CRITIC_PATH_FOLLOW:
         if (P->follow.on) {    // path_follow_critic.cpp:60-70
-          const float dx = bufs.end_xy[b] - __ldg(path_x + dec.follow_idx);
-          const float dy = bufs.end_xy[B + b] - __ldg(path_y + dec.follow_idx);
+          const float dx = end_x - path.s_x[dec.follow_idx];
+          const float dy = end_y - path.s_y[dec.follow_idx];
           term = add_pow(0.0f, P->follow.weight * sqrtf(dx * dx + dy * dy), P->follow.power);
           has = true;
         }
@@ -1087,34 +1133,41 @@ __device__ __forceinline__ float k3_trajectory_total(
       case MPPI_CRITIC_PATH_ALIGN:
         if (dec.align_go) {     // path_align_critic.cpp:92-135, sequential and in the reference's fp32 order
           const int step = P->align_step;
+          const int n_s = (T + step - 1) / step;     // sampled poses p = 0, step, 2 step, ... < T
           float traj_d = 0.0f, summed = 0.0f, num = 0.0f;
           int path_pt = 0;
           float prev_x = bufs.samples_x[b], prev_y = bufs.samples_y[b];
-          int k = 1;
-          float nx = 0.0f, ny = 0.0f;   // one-deep prefetch of the next sampled pose (L2 latency off the serial chain)
-          if (step < T) {nx = bufs.samples_x[static_cast<size_t>(B) + b]; ny = bufs.samples_y[static_cast<size_t>(B) + b];}
-          for (int p = step; p < T; p += step, ++k) {
-            const float Tx = nx, Ty = ny;
-            if (p + step < T) {
-              nx = bufs.samples_x[static_cast<size_t>(k + 1) * B + b];
-              ny = bufs.samples_y[static_cast<size_t>(k + 1) * B + b];
+          constexpr int kBatch = 8;                  // sampled poses requested together (latency off the serial chain)
+          for (int k0 = 1; k0 < n_s; k0 += kBatch) {
+            float sx[kBatch], sy[kBatch], syaw[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+              const int k = min(k0 + u, n_s - 1);
+              sx[u] = bufs.samples_x[static_cast<size_t>(k) * B + b];
+              sy[u] = bufs.samples_y[static_cast<size_t>(k) * B + b];
+              syaw[u] = P->align_use_yaw ? bufs.samples_yaw[static_cast<size_t>(k) * B + b] : 0.0f;
             }
-            float dx = __fsub_rn(Tx, prev_x), dy = __fsub_rn(Ty, prev_y);
-            traj_d = __fadd_rn(traj_d, __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
-            path_pt = find_closest_path_pt(s_D, furthest, traj_d, path_pt);
-            if (s_valid[path_pt]) {
-              dx = __fsub_rn(__ldg(path_x + path_pt), Tx);
-              dy = __fsub_rn(__ldg(path_y + path_pt), Ty);
-              num = __fadd_rn(num, 1.0f);
-              if (P->align_use_yaw) {
-                const float Tyaw = bufs.samples_yaw[static_cast<size_t>(k) * B + b];
-                const float dyaw = static_cast<float>(normalize_angle_d(static_cast<double>(Tyaw) - static_cast<double>(__ldg(path_yaw + path_pt))));
-                summed = __fadd_rn(summed, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dyaw, dyaw))));
-              } else {
-                summed = __fadd_rn(summed, __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+              if (k0 + u < n_s) {
+                const float Tx = sx[u], Ty = sy[u];
+                float dx = __fsub_rn(Tx, prev_x), dy = __fsub_rn(Ty, prev_y);
+                traj_d = __fadd_rn(traj_d, __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
+                path_pt = find_closest_path_pt(s_D, furthest, traj_d, path_pt);
+                if (s_valid[path_pt]) {
+                  dx = __fsub_rn(path.s_x[path_pt], Tx);
+                  dy = __fsub_rn(path.s_y[path_pt], Ty);
+                  num = __fadd_rn(num, 1.0f);
+                  if (P->align_use_yaw) {
+                    const float dyaw = static_cast<float>(normalize_angle_d(static_cast<double>(syaw[u]) - static_cast<double>(__ldg(path_yaw + path_pt))));
+                    summed = __fadd_rn(summed, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dyaw, dyaw))));
+                  } else {
+                    summed = __fadd_rn(summed, __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
+                  }
+                }
+                prev_x = Tx; prev_y = Ty;
               }
             }
-            prev_x = Tx; prev_y = Ty;
           }
           const float cost = num > 0.0f ? __fdiv_rn(summed, num) : 0.0f;
           term = add_pow(0.0f, __fmul_rn(cost, P->align.weight), P->align.power);
@@ -1184,9 +1237,10 @@ __device__ __forceinline__ float k3_trajectory_total(
     const bool from_k3 = kind == MPPI_CRITIC_PATH_FOLLOW || kind == MPPI_CRITIC_PATH_ALIGN ||
       kind == MPPI_CRITIC_PATH_ALIGN_LEGACY || kind == MPPI_CRITIC_PATH_ANGLE;
     if (from_k3) {
-      rows[static_cast<size_t>(q) * B + b] = term;   // always defined for the per-critic getter
+      if (P->want_critic_rows) {rows[static_cast<size_t>(q) * B + b] = term;}   // for the per-critic getter
     } else if (has) {
-      term = rows[static_cast<size_t>(q) * B + b];
+#pragma unroll
+      for (int r = 0; r < kMaxCritics; ++r) {term = r == q ? row_v[r] : term;}   // register array: static indices only
     }
     if (has) {total = __fadd_rn(total, term);}
   }
@@ -1213,10 +1267,9 @@ __device__ __forceinline__ float k3_trajectory_total(
   }
   if (P->mode == 0) {
     // gamma term (optimizer.cpp:367-380): vx, then wz, then vy (holonomic)
-    const size_t g = static_cast<size_t>(nc) * B + b;
-    total = __fadd_rn(total, __fmul_rn(P->gamma_vx, rows[g]));
-    total = __fadd_rn(total, __fmul_rn(P->gamma_wz, rows[g + 2 * static_cast<size_t>(B)]));
-    if (P->holonomic) {total = __fadd_rn(total, __fmul_rn(P->gamma_vy, rows[g + B]));}
+    total = __fadd_rn(total, __fmul_rn(P->gamma_vx, gam[0]));
+    total = __fadd_rn(total, __fmul_rn(P->gamma_wz, gam[2]));
+    if (P->holonomic) {total = __fadd_rn(total, __fmul_rn(P->gamma_vy, gam[1]));}
   }
   bufs.costs[b] = total;
   return total;
@@ -1282,30 +1335,79 @@ __global__ void __launch_bounds__(kUpdThreads) path_costs_tm_kernel(const DevPar
   }
 }
 
-__global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
-  const DevParams * __restrict__ Pg, DevBuffers bufs, int n_ranks, int iteration, int R)
+// K3, tile layout (small and medium batches; latency matters more than throughput here).  One block owns
+// kUpdRows = 32 trajectories.  Warp 0 walks the per-trajectory critic totals (one lane per trajectory) while the
+// other warps stage the block's noise rows [32][3][T] into shared memory, so the weighted column sums that follow
+// the softmax run out of shared memory with all threads busy.  The last block to finish merges the per-block
+// online-softmax records and writes the new control sequence (up to kLastBlockMergeMax blocks; beyond that
+// merge_finalize_kernel does it in parallel).
+constexpr int kUpdRows = 32;
+__host__ __device__ inline size_t k3_tile_smem_bytes(int T)
 {
-  // R = trajectories owned by this block (multiple of 32, <= kUpdThreads): small batches use small R so that
-  // the update spreads over many SMs; the column sums always use all kUpdThreads threads
+  return k3_common_smem_bytes() + sizeof(float) * (static_cast<size_t>(kUpdRows) * 3 * T + kUpdRows + 8);
+}
+
+__global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
+  const DevParams * __restrict__ Pg, DevBuffers bufs, int n_ranks, int iteration, const int B0, const int T0, const int mode0)
+{
   extern __shared__ float smem[];
   __shared__ K3Decisions dec;
   __shared__ unsigned sc_last;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  MPPI_TRACE_AT(16);
+  // the noise rows do not depend on anything K3 decides: request them before the preamble's barriers
+  // (B0, T0, mode0 repeat the record's B, T, mode as launch arguments: no memory round trip before the first load)
+  float * s_tile = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(smem) + k3_common_smem_bytes());   // [32][3T]
+  float * s_w = s_tile + static_cast<size_t>(kUpdRows) * 3 * T0;                                             // [32]
+  float * s_stat = s_w + kUpdRows;                                                                           // [m, ssum]
+  const int rows_here = min(kUpdRows, B0 - static_cast<int>(blockIdx.x) * kUpdRows);
+  if (mode0 == 0 && warp > 0) {
+    const int nstage = kUpdThreads - 32, sid = tid - 32;
+    const size_t row0 = static_cast<size_t>(blockIdx.x) * kUpdRows * T0;
+    if ((T0 & 3) == 0) {
+      const int rs = T0 >> 2, per_plane = rows_here * rs;
+      for (int i = sid; i < 3 * per_plane; i += nstage) {
+        const int plane = i / per_plane, j = i - plane * per_plane;
+        const int r = j / rs, q4 = j - r * rs;
+        const float * src = (plane == 0 ? bufs.in_a : (plane == 1 ? bufs.in_b : bufs.in_c)) + row0;
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + j);
+        *reinterpret_cast<float4 *>(s_tile + (static_cast<size_t>(r) * 3 + plane) * T0 + 4 * q4) = v;
+      }
+    } else {
+      const int per_plane = rows_here * T0;
+      for (int i = sid; i < 3 * per_plane; i += nstage) {
+        const int plane = i / per_plane, j = i - plane * per_plane;
+        const int r = j / T0, t = j - r * T0;
+        const float * src = (plane == 0 ? bufs.in_a : (plane == 1 ? bufs.in_b : bufs.in_c)) + row0;
+        s_tile[(static_cast<size_t>(r) * 3 + plane) * T0 + t] = __ldg(src + j);
+      }
+    }
+  }
+  MPPI_TRACE_AT(17);
   K3Path path;
   k3_preamble(smem, Pg, bufs.st, iteration, tid, kUpdThreads, path, &dec);
   const DevParams * P = reinterpret_cast<const DevParams *>(smem);   // hot fields only; arrays stay in global (Pg)
-  const int T = P->T, B = P->B, nc = P->n_critics;
-  float * s_w = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(smem) + k3_common_smem_bytes());   // [kUpdThreads]
-  float * s_red = s_w + kUpdThreads;                                                                       // [32]
+  const int T = P->T, B = P->B;
   DevState * st = bufs.st;
-  const int fail_at = dec.fail_at;
 
-  // ---- phase 1: one thread per trajectory: path critics + total in list order
-  const int b = blockIdx.x * R + tid;
-  const bool live = tid < R && b < B;
-  float total = 3.402823466e+38f;
-  if (live) {total = k3_trajectory_total(b, P, dec, path, bufs, iteration);}
-
+  MPPI_TRACE_AT(18);
+  // ---- phase 1: warp 0, one lane per trajectory: path critics + total in list order; block-local softmax record
+  const float inv_temp = 1.0f / P->temperature;
+  if (warp == 0) {
+    const int b = blockIdx.x * kUpdRows + lane;
+    const bool live = b < B;
+    float total = 3.402823466e+38f;
+    if (live) {total = k3_trajectory_total(b, P, dec, path, bufs, iteration);}
+    if (P->mode == 0) {
+      // optimizer.cpp:382-391 on this block's rows: m = min, w = exp(-(c - m) / temperature), s = sum w
+      const float m = warp_min(total);
+      const float w_b = live ? expf(-(total - m) * inv_temp) : 0.0f;
+      const float ssum = warp_sum(w_b);
+      s_w[lane] = w_b;
+      if (lane == 0) {s_stat[0] = m; s_stat[1] = ssum;}
+    }
+  }
+  MPPI_TRACE_AT(19);
   if (P->mode != 0) {
     // score mode: no control update; the last block publishes the flags
     __threadfence();
@@ -1315,92 +1417,28 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
     if (sc_last && tid == 0) {k3_publish_flags(P, st, dec, bufs.out);}
     return;
   }
+  __syncthreads();
 
-  // ---- phase 2: softmax partial of this block (optimizer.cpp:382-391): m = min, w = exp(-(c-m)/T), s = sum w
-  const float inv_temp = 1.0f / P->temperature;
-  float m = warp_min(total);
-  if ((tid & 31) == 0) {s_red[tid >> 5] = m;}
-  __syncthreads();
-  m = s_red[0];
-#pragma unroll
-  for (int w = 1; w < kUpdThreads / 32; ++w) {m = fminf(m, s_red[w]);}
-  __syncthreads();
-  const float w_b = live ? expf(-(total - m) * inv_temp) : 0.0f;
-  s_w[tid] = w_b;
-  float ssum = warp_sum(w_b);
-  if ((tid & 31) == 0) {s_red[tid >> 5] = ssum;}
-  __syncthreads();
-  ssum = 0.0f;
-#pragma unroll
-  for (int w = 0; w < kUpdThreads / 32; ++w) {ssum += s_red[w];}
-
-  // ---- phase 3: weighted column sums over this block's rows, W[c][t] = sum_b w_b * (cs[t] + noise[b,t])
+  // ---- phase 2: weighted column sums over this block's rows from shared memory, W[c] = sum_r w_r * (cs[c] + noise[r][c])
   const int stride = 3 * T + 2;
   float * part = bufs.partials + static_cast<size_t>(blockIdx.x) * stride;
-  const int rows_here = min(R, B - blockIdx.x * R);
-  const size_t row0 = static_cast<size_t>(blockIdx.x) * R * T;
-  if ((T & 3) == 0) {
-    // 16-byte loads along t: one thread owns 4 consecutive columns of one plane, 4 rows in flight
-    const int rs = T >> 2;
-    for (int c4 = tid; c4 < (3 * T) >> 2; c4 += kUpdThreads) {
-      const int c = c4 << 2;
-      const int plane = c / T, t = c - plane * T;
-      const float4 * __restrict__ src =
-        reinterpret_cast<const float4 *>((plane == 0 ? bufs.in_a : (plane == 1 ? bufs.in_b : bufs.in_c)) + row0 + t);
-      const float4 cs4 = *reinterpret_cast<const float4 *>(bufs.cs + c);
-      float4 a[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {a[u] = make_float4(0.f, 0.f, 0.f, 0.f);}
-      int r = 0;
-      for (; r + 3 < rows_here; r += 4) {
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {v[u] = __ldg(src + static_cast<size_t>(r + u) * rs);}
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float w = s_w[r + u];
-          a[u].x = fmaf(w, __fadd_rn(cs4.x, v[u].x), a[u].x);
-          a[u].y = fmaf(w, __fadd_rn(cs4.y, v[u].y), a[u].y);
-          a[u].z = fmaf(w, __fadd_rn(cs4.z, v[u].z), a[u].z);
-          a[u].w = fmaf(w, __fadd_rn(cs4.w, v[u].w), a[u].w);
-        }
-      }
-      for (; r < rows_here; ++r) {
-        const float4 v = __ldg(src + static_cast<size_t>(r) * rs);
-        const float w = s_w[r];
-        a[0].x = fmaf(w, __fadd_rn(cs4.x, v.x), a[0].x);
-        a[0].y = fmaf(w, __fadd_rn(cs4.y, v.y), a[0].y);
-        a[0].z = fmaf(w, __fadd_rn(cs4.z, v.z), a[0].z);
-        a[0].w = fmaf(w, __fadd_rn(cs4.w, v.w), a[0].w);
-      }
-      part[2 + c] = (a[0].x + a[1].x) + (a[2].x + a[3].x);
-      part[3 + c] = (a[0].y + a[1].y) + (a[2].y + a[3].y);
-      part[4 + c] = (a[0].z + a[1].z) + (a[2].z + a[3].z);
-      part[5 + c] = (a[0].w + a[1].w) + (a[2].w + a[3].w);
+  for (int c = tid; c < 3 * T; c += kUpdThreads) {
+    const float cs_c = bufs.cs[c];
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    int r = 0;
+    for (; r + 3 < rows_here; r += 4) {
+      a0 = fmaf(s_w[r], __fadd_rn(cs_c, s_tile[static_cast<size_t>(r) * 3 * T + c]), a0);
+      a1 = fmaf(s_w[r + 1], __fadd_rn(cs_c, s_tile[static_cast<size_t>(r + 1) * 3 * T + c]), a1);
+      a2 = fmaf(s_w[r + 2], __fadd_rn(cs_c, s_tile[static_cast<size_t>(r + 2) * 3 * T + c]), a2);
+      a3 = fmaf(s_w[r + 3], __fadd_rn(cs_c, s_tile[static_cast<size_t>(r + 3) * 3 * T + c]), a3);
     }
-  } else {
-    for (int c = tid; c < 3 * T; c += kUpdThreads) {
-      const int plane = c / T, t = c - plane * T;
-      const float * __restrict__ src = (plane == 0 ? bufs.in_a : (plane == 1 ? bufs.in_b : bufs.in_c)) + row0 + t;
-      const float cs_t = bufs.cs[c];
-      float a[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {a[u] = 0.0f;}
-      int r = 0;
-      for (; r + 7 < rows_here; r += 8) {
-        float v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {v[u] = __ldg(src + static_cast<size_t>(r + u) * T);}
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {a[u] = fmaf(s_w[r + u], __fadd_rn(cs_t, v[u]), a[u]);}
-      }
-      for (; r < rows_here; ++r) {a[0] = fmaf(s_w[r], __fadd_rn(cs_t, __ldg(src + static_cast<size_t>(r) * T)), a[0]);}
-      part[2 + c] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
-    }
+    for (; r < rows_here; ++r) {a0 = fmaf(s_w[r], __fadd_rn(cs_c, s_tile[static_cast<size_t>(r) * 3 * T + c]), a0);}
+    part[2 + c] = (a0 + a1) + (a2 + a3);
   }
-  if (tid == 0) {part[0] = m; part[1] = ssum;}
+  if (tid == 0) {part[0] = s_stat[0]; part[1] = s_stat[1];}
 
-  // ---- phase 4: the last block to finish publishes the flags and, for small batches, merges all partials
+  MPPI_TRACE_AT(20);
+  // ---- phase 3: the last block to finish publishes the flags and, for small batches, merges all partials
   //      and writes the new control sequence (large batches: merge_finalize_kernel, launched by the host)
   __threadfence();
   __syncthreads();
@@ -1408,15 +1446,17 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
   __syncthreads();
   if (!sc_last) {return;}
   __threadfence();
+  MPPI_TRACE_AT(21);
   if (tid == 0) {k3_publish_flags(P, st, dec, bufs.out);}
   if (static_cast<int>(gridDim.x) > kLastBlockMergeMax) {return;}
   float * merged = bufs.rank_partial;   // [3T + 2]
-  merge_partials(bufs.partials, gridDim.x, stride, T, inv_temp, merged, s_red, tid, kUpdThreads);
+  merge_partials(bufs.partials, gridDim.x, stride, T, inv_temp, merged, s_tile, tid, kUpdThreads);
   if (n_ranks <= 1) {
     __threadfence_block();
     __syncthreads();
     finalize_controls(P, merged, bufs.cs, bufs.out, tid, kUpdThreads);
   }
+  MPPI_TRACE_AT(22);
 }
 
 // K3c (stream layout): softmax weights and weighted control sums over time-major noise [T][B]; a GEMV
