@@ -206,6 +206,17 @@ mppi_status mppi_shift_control_sequence(mppi_handle * h);
  * mirror because it throws): costs are zeroed, then iteration_count x {noised rollout, critics,
  * softmax update}.  Host buffers in, host buffers out. */
 mppi_status mppi_optimize(mppi_handle * h, const mppi_cycle_in * in, mppi_cycle_out * out);
+/* Optimizer::evalControl (optimizer.cpp:134-155) for one attempt: prepare() + optimize() and, if fail_flag stayed clear,
+ * utils::savitskyGolayFilter (utils.hpp:442-605), getControlFromSequenceAsTwist (optimizer.cpp:396-410) and, when
+ * shift_control_sequence != 0 (Optimizer::setOffset, optimizer.cpp:95-114), shiftControlSequence (:206-225) -- all on
+ * the device, so the warm-start sequence and the 4-deep control history never leave it.  cmd_out = (vx, vy, wz) of
+ * the returned twist (vy = 0 for non-holonomic models).  When out->fail_flag is set nothing after optimize() ran:
+ * the caller does what Optimizer::fallback does (mppi_reset, retry up to retry_attempt_limit, then throw). */
+mppi_status mppi_eval_control(mppi_handle * h, const mppi_cycle_in * in, int32_t shift_control_sequence,
+                              mppi_cycle_out * out, float cmd_out[3]);
+/* control_history_ (optimizer.hpp:251): [4][3] = (vx, vy, wz) of the last four commands, oldest first */
+mppi_status mppi_set_control_history(mppi_handle * h, const float hist12[12]);
+mppi_status mppi_get_control_history(mppi_handle * h, float hist12[12]);
 /* batched multi-robot form: n independent handles (possibly on several devices) launched back to back
  * and then joined, so their kernels overlap */
 mppi_status mppi_optimize_batch(mppi_handle ** hs, const mppi_cycle_in * ins, mppi_cycle_out * outs, int32_t n);

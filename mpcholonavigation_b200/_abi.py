@@ -171,6 +171,9 @@ SIGNATURES = {
     "get_control_sequence": (C.c_int, [H, f32p, f32p, f32p]),
     "shift_control_sequence": (C.c_int, [H]),
     "optimize": (C.c_int, [H, C.POINTER(CycleIn), C.POINTER(CycleOut)]),
+    "eval_control": (C.c_int, [H, C.POINTER(CycleIn), C.c_int32, C.POINTER(CycleOut), f32p]),
+    "set_control_history": (C.c_int, [H, f32p]),
+    "get_control_history": (C.c_int, [H, f32p]),
     "get_trajectories": (C.c_int, [H, f32p, f32p, f32p]),
     "get_cells": (C.c_int, [H, i32p]),
     "get_costs": (C.c_int, [H, f32p]),

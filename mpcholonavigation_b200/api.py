@@ -58,8 +58,18 @@ class Cycle:
     resolution: float = 0.1
     origin: Sequence[float] = (0.0, 0.0)
 
+    def packed(self):
+        """pack() once and keep the result: host buffers that a caller hands over unchanged every cycle (bench e2e leg).
+        Call again after modifying the cycle."""
+        self._packed = None
+        self._packed = self.pack()
+        return self
+
     def pack(self):
         """-> (CycleIn, keepalive list)"""
+        cached = getattr(self, "_packed", None)
+        if cached is not None:
+            return cached
         px, py, pyaw = _f32(self.path_x), _f32(self.path_y), _f32(self.path_yaw)
         assert px.shape == py.shape == pyaw.shape and px.ndim == 1
         cm = np.ascontiguousarray(self.costmap, dtype=np.uint8)
@@ -253,6 +263,25 @@ class Engine:
         self._check(self.f["optimize"](self.h, C.byref(cin), C.byref(out)))
         del keep
         return self._result(out, arrs)
+
+    def eval_control(self, cycle: Cycle, shift_control_sequence: bool):
+        """One attempt of Optimizer::evalControl (optimizer.cpp:134-155): optimize, Savitzky-Golay filter, command
+        extraction and control-sequence shift.  Returns ((vx, vy, wz) command, Result)."""
+        cin, keep = cycle.pack()
+        out, arrs = self._out()
+        cmd = np.zeros(3, np.float32)
+        self._check(self.f["eval_control"](self.h, C.byref(cin), int(bool(shift_control_sequence)), C.byref(out), _p(cmd)))
+        del keep
+        return cmd, self._result(out, arrs)
+
+    def set_control_history(self, hist):
+        hist = _f32(hist).reshape(12)
+        self._check(self.f["set_control_history"](self.h, _p(hist)))
+
+    def get_control_history(self):
+        hist = np.zeros(12, np.float32)
+        self._check(self.f["get_control_history"](self.h, _p(hist)))
+        return hist.reshape(4, 3)
 
     def upload_cycle(self, cycle: Cycle):
         cin, keep = cycle.pack()

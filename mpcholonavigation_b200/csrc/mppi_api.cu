@@ -115,9 +115,12 @@ struct mppi_handle
   bool stream_layout{false};   // large batches: time-major noise + thread-per-trajectory K2 + GEMV-style weighted sums
   int upd_blocks{0};
   // CUDA graphs of the steady-state cycle: [0] kernels + D2H (resident inputs), [1] H2D + kernels + D2H
-  cudaGraphExec_t gexec[2]{nullptr, nullptr};
-  size_t gkey_params[2]{0, 0}, gkey_costmap[2]{0, 0};
-  unsigned gkey_inst[2]{0, 0};
+  // captured graphs: slot = (with_upload ? 1 : 0) + 2 * tail_mode
+  cudaGraphExec_t gexec[6]{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t gkey_params[6]{0, 0, 0, 0, 0, 0}, gkey_costmap[6]{0, 0, 0, 0, 0, 0};
+  unsigned gkey_inst[6]{0, 0, 0, 0, 0, 0};
+  int tail_mode{0};            // 0: optimize only, 1: + evalControl tail, 2: + tail with shiftControlSequence
+  float * d_hist{nullptr};     // control_history_ [4][3] (vx, vy, wz), optimizer.hpp:251
   bool use_graph{true};
   size_t costmap_bytes{0}, params_copy_bytes{0};
   // sharding
@@ -736,8 +739,14 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
       h->launches++;
     }
   }
+  if (h->tail_mode) {
+    // evalControl's tail (Savitzky-Golay filter, command extraction, shift) stays on the device
+    eval_tail_kernel<<<1, 32, 0, h->stream>>>(h->d_cs, h->d_hist, h->d_out, h->T, holonomic(h) ? 1 : 0, h->tail_mode == 2 ? 1 : 0);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+  }
   if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[3], h->stream));}
-  CUDA_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(float) * (3 * h->T + 2), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(float) * (3 * h->T + 5), cudaMemcpyDeviceToHost, h->stream));
   return MPPI_OK;
 }
 
@@ -747,11 +756,11 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
 {
   const bool prof = h->profiling && h->cfg.iteration_count == 1;
   const bool graph_ok = h->use_graph && !prof && h->nranks == 1;
-  h->d2h_bytes = sizeof(float) * (3 * h->T + 2);
+  h->d2h_bytes = sizeof(float) * (3 * h->T + 5);
   h->h2d_bytes = with_upload ? h->params_copy_bytes + h->costmap_bytes : 0;
   CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
   if (graph_ok) {
-    const int slot = with_upload ? 1 : 0;
+    const int slot = (with_upload ? 1 : 0) + 2 * h->tail_mode;
     const unsigned inst = h->stream_layout ? pick_stream_instance(stream_feature_need(h->last)) : 0u;
     if (h->gexec[slot] && (h->gkey_params[slot] != h->params_copy_bytes || h->gkey_costmap[slot] != h->costmap_bytes ||
       h->gkey_inst[slot] != inst))
@@ -783,7 +792,8 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
     }
     if (h->gexec[slot]) {
       CUDA_TRY(h, cudaGraphLaunch(h->gexec[slot], h->stream));
-      h->launches += (h->stream_layout ? 4ull : (h->upd_blocks > kLastBlockMergeMax ? 3ull : 2ull)) * h->cfg.iteration_count;
+      h->launches += (h->stream_layout ? 4ull : (h->upd_blocks > kLastBlockMergeMax ? 3ull : 2ull)) * h->cfg.iteration_count +
+        (h->tail_mode ? 1ull : 0ull);
       CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
       return MPPI_OK;
     }
@@ -859,6 +869,7 @@ mppi_status do_reset(mppi_handle * h)
   const size_t T = h->T, B = h->B;
   h->cur = h->base;
   CUDA_TRY(h, cudaMemsetAsync(h->d_cs, 0, 3 * T * sizeof(float), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_hist, 0, 12 * sizeof(float), h->stream));   // control_history_ (optimizer.cpp:120-123)
   CUDA_TRY(h, cudaMemsetAsync(h->d_costs, 0, B * sizeof(float), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->d_st, 0, sizeof(DevState), h->stream));
   // NoiseGenerator::reset (noise_generator.cpp:76-95): redraw
@@ -948,7 +959,7 @@ void mppi_destroy(mppi_handle * h)
   for (float * p : h->d_inj) {cudaFree(p);}
   cudaFree(h->d_tmp); cudaFree(h->d_costmap); cudaFree(h->d_params); cudaFree(h->d_cs); cudaFree(h->d_crit_rows);
   cudaFree(h->d_end_xy); cudaFree(h->d_cells); cudaFree(h->d_costs); cudaFree(h->d_partials); cudaFree(h->d_rank_partial);
-  cudaFree(h->d_gathered); cudaFree(h->d_out); cudaFree(h->d_st);
+  cudaFree(h->d_gathered); cudaFree(h->d_out); cudaFree(h->d_st); cudaFree(h->d_hist);
   cudaFreeHost(h->h_params); cudaFreeHost(h->h_costmap); cudaFreeHost(h->h_out);
   if (h->ev0) {cudaEventDestroy(h->ev0);}
   if (h->ev1) {cudaEventDestroy(h->ev1);}
@@ -1024,11 +1035,12 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   const size_t stride = 3 * T + 2;
   CUDA_TRY(h, cudaMalloc(&h->d_partials, h->upd_blocks * stride * sizeof(float)));
   CUDA_TRY(h, cudaMalloc(&h->d_rank_partial, stride * sizeof(float)));
-  CUDA_TRY(h, cudaMalloc(&h->d_out, (stride + 2) * sizeof(float)));
-  CUDA_TRY(h, cudaMemsetAsync(h->d_out, 0, (stride + 2) * sizeof(float), h->stream));
+  CUDA_TRY(h, cudaMalloc(&h->d_out, (stride + 8) * sizeof(float)));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_out, 0, (stride + 8) * sizeof(float), h->stream));
+  CUDA_TRY(h, cudaMalloc(&h->d_hist, 12 * sizeof(float)));
   CUDA_TRY(h, cudaMalloc(&h->d_st, sizeof(DevState)));
   CUDA_TRY(h, cudaMallocHost(&h->h_params, kParamsCapacity));
-  CUDA_TRY(h, cudaMallocHost(&h->h_out, (stride + 2) * sizeof(float)));
+  CUDA_TRY(h, cudaMallocHost(&h->h_out, (stride + 8) * sizeof(float)));
   return do_reset(h);
 }
 
@@ -1232,6 +1244,39 @@ mppi_status mppi_optimize(mppi_handle * h, const mppi_cycle_in * in, mppi_cycle_
   mppi_status s = optimize_begin(h, in);
   if (s != MPPI_OK) {return s;}
   return finish_optimize(h, out);
+}
+
+// Optimizer::evalControl (optimizer.cpp:134-155) without the fallback loop: prepare + optimize, and, when the
+// optimisation did not fail, savitskyGolayFilter + getControlFromSequenceAsTwist + shiftControlSequence on the device.
+mppi_status mppi_eval_control(mppi_handle * h, const mppi_cycle_in * in, int32_t shift_control_sequence, mppi_cycle_out * out, float cmd_out[3])
+{
+  if (!h || !in) {return MPPI_E_CONFIG;}
+  if (h->nranks > 1) {return fail(h, MPPI_E_STATE, "mppi_eval_control on a sharded handle: use mppi_optimize + the host tail");}
+  h->tail_mode = shift_control_sequence ? 2 : 1;
+  mppi_status s = optimize_begin(h, in);
+  if (s == MPPI_OK) {s = finish_optimize(h, out);}
+  h->tail_mode = 0;
+  if (s != MPPI_OK) {return s;}
+  if (cmd_out) {std::memcpy(cmd_out, h->h_out + 3 * h->T + 2, 3 * sizeof(float));}
+  return MPPI_OK;
+}
+
+mppi_status mppi_set_control_history(mppi_handle * h, const float hist12[12])
+{
+  if (!h || !hist12) {return MPPI_E_CONFIG;}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_hist, hist12, 12 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return MPPI_OK;
+}
+
+mppi_status mppi_get_control_history(mppi_handle * h, float hist12[12])
+{
+  if (!h || !hist12) {return MPPI_E_CONFIG;}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, cudaMemcpyAsync(hist12, h->d_hist, 12 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return MPPI_OK;
 }
 
 mppi_status mppi_optimize_batch(mppi_handle ** hs, const mppi_cycle_in * ins, mppi_cycle_out * outs, int32_t n)

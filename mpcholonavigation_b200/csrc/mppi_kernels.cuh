@@ -1660,6 +1660,71 @@ __global__ void shift_control_sequence_kernel(float * __restrict__ cs, int T, in
   }
 }
 
+// The tail of Optimizer::evalControl (optimizer.cpp:147-152) on the device, so that the control sequence never
+// makes a host round trip between cycles: utils::savitskyGolayFilter (utils.hpp:442-605) with the 4-deep control
+// history, getControlFromSequenceAsTwist (optimizer.cpp:396-410) and shiftControlSequence (:206-225).
+// Skipped when the optimisation failed (fail_flag): the reference only reaches this code after fallback() returned
+// false.  One thread per plane; the filter is inherently sequential (already-filtered neighbours are reused) and
+// reproduces the reference's quirks: index num_sequences - 4 is never filtered, vy is filtered for every model.
+// out layout: [0, 3T) control sequence after the tail, [3T] fail flag, [3T+1] furthest, [3T+2, 3T+5) command.
+__global__ void eval_tail_kernel(float * __restrict__ cs, float * __restrict__ hist, float * __restrict__ out, int T, int holonomic, int shift)
+{
+  __shared__ float s[3][MPPI_MAX_TIME_STEPS];
+  const int plane = threadIdx.x;   // 0 vx, 1 vy, 2 wz
+  const bool failed = __float_as_int(out[3 * T]) != 0;
+  if (plane < 3 && !failed) {
+    float * v = s[plane];
+    for (int t = 0; t < T; ++t) {v[t] = cs[plane * T + t];}
+    const unsigned num_sequences = static_cast<unsigned>(T) - 1u;
+    float h0 = hist[0 * 3 + plane], h1 = hist[1 * 3 + plane], h2 = hist[2 * 3 + plane], h3 = hist[3 * 3 + plane];
+    if (num_sequences >= 20u) {
+      float f[9] = {-21.0f, 14.0f, 39.0f, 54.0f, 59.0f, 54.0f, 39.0f, 14.0f, -21.0f};
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {f[i] = __fdiv_rn(f[i], 231.0f);}
+      auto apply = [&](float d0, float d1, float d2, float d3, float d4, float d5, float d6, float d7, float d8) -> float {
+          float a = __fadd_rn(0.0f, __fmul_rn(d0, f[0]));
+          a = __fadd_rn(a, __fmul_rn(d1, f[1])); a = __fadd_rn(a, __fmul_rn(d2, f[2])); a = __fadd_rn(a, __fmul_rn(d3, f[3]));
+          a = __fadd_rn(a, __fmul_rn(d4, f[4])); a = __fadd_rn(a, __fmul_rn(d5, f[5])); a = __fadd_rn(a, __fmul_rn(d6, f[6]));
+          a = __fadd_rn(a, __fmul_rn(d7, f[7])); a = __fadd_rn(a, __fmul_rn(d8, f[8]));
+          return a;
+        };
+      unsigned idx = 0;
+      v[idx] = apply(h0, h1, h2, h3, v[idx], v[idx + 1], v[idx + 2], v[idx + 3], v[idx + 4]);
+      idx++;
+      v[idx] = apply(h1, h2, h3, v[idx - 1], v[idx], v[idx + 1], v[idx + 2], v[idx + 3], v[idx + 4]);
+      idx++;
+      v[idx] = apply(h2, h3, v[idx - 2], v[idx - 1], v[idx], v[idx + 1], v[idx + 2], v[idx + 3], v[idx + 4]);
+      idx++;
+      v[idx] = apply(h3, v[idx - 3], v[idx - 2], v[idx - 1], v[idx], v[idx + 1], v[idx + 2], v[idx + 3], v[idx + 4]);
+      for (idx = 4; idx != num_sequences - 4; idx++) {
+        v[idx] = apply(v[idx - 4], v[idx - 3], v[idx - 2], v[idx - 1], v[idx], v[idx + 1], v[idx + 2], v[idx + 3], v[idx + 4]);
+      }
+      idx++;   // the reference's extra increment: index num_sequences - 4 stays unfiltered
+      v[idx] = apply(v[idx - 4], v[idx - 3], v[idx - 2], v[idx - 1], v[idx], v[idx + 1], v[idx + 2], v[idx + 3], v[idx + 3]);
+      idx++;
+      v[idx] = apply(v[idx - 4], v[idx - 3], v[idx - 2], v[idx - 1], v[idx], v[idx + 1], v[idx + 2], v[idx + 2], v[idx + 2]);
+      idx++;
+      v[idx] = apply(v[idx - 4], v[idx - 3], v[idx - 2], v[idx - 1], v[idx], v[idx + 1], v[idx + 1], v[idx + 1], v[idx + 1]);
+      idx++;
+      v[idx] = apply(v[idx - 4], v[idx - 3], v[idx - 2], v[idx - 1], v[idx], v[idx], v[idx], v[idx], v[idx]);
+      // control history: drop the oldest, append the command of this cycle
+      const int offset = shift ? 1 : 0;
+      hist[0 * 3 + plane] = h1; hist[1 * 3 + plane] = h2; hist[2 * 3 + plane] = h3; hist[3 * 3 + plane] = v[offset];
+    }
+    // getControlFromSequenceAsTwist: index 1 when the sequence is shifted afterwards, else 0; vy only if holonomic
+    out[3 * T + 2 + plane] = (plane == 1 && !holonomic) ? 0.0f : v[shift ? 1 : 0];
+    if (shift && (plane != 1 || holonomic)) {
+      // shiftControlSequence: roll by -1, then last = second to last (the old last element)
+      const float last = v[T - 1];
+      for (int t = 0; t + 1 < T; ++t) {v[t] = v[t + 1];}
+      v[T - 1] = last;
+    }
+    for (int t = 0; t < T; ++t) {cs[plane * T + t] = v[t]; out[plane * T + t] = v[t];}
+  } else if (plane < 3) {
+    out[3 * T + 2 + plane] = 0.0f;
+  }
+}
+
 // Optimizer::getOptimizedTrajectory (optimizer.cpp:345-360, :275-311): one trajectory from the mean controls
 __global__ void optimized_trajectory_kernel(const float * __restrict__ cs, float * __restrict__ out_t3, int T, int holonomic,
   float dt, double pose_x, double pose_y, float yaw0)

@@ -501,6 +501,7 @@ struct Optimizer
   std::vector<int32_t> cells;
   CriticData data;
   uint64_t noise_stream{0};
+  float control_history[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};   // ref: inc/optimizer.hpp:251
   std::string err;
 
   bool isHolonomic() const {return cfg.motion_model == MPPI_MODEL_OMNI;}
@@ -524,6 +525,7 @@ struct Optimizer
     const size_t B = cfg.batch_size, T = cfg.time_steps;
     state.reset(B, T);
     cs.reset(T);
+    std::memset(control_history, 0, sizeof(control_history));   // optimizer.cpp:120-123
     constraints = base_constraints;
     costs.assign(B, 0.0f);
     traj.reset(B, T);
@@ -1288,6 +1290,8 @@ void oracle_critic_default(int32_t kind, mppi_critic_desc * d)
 int oracle_create(const mppi_config * cfg, Optimizer ** out)
 {
   if (!cfg || !out || cfg->batch_size <= 0 || cfg->time_steps <= 0) {return MPPI_E_CONFIG;}
+  // ref: Optimizer::setMotionModel optimizer.cpp:412-426 throws for anything but DiffDrive / Omni / Ackermann
+  if (cfg->motion_model < MPPI_MODEL_DIFF_DRIVE || cfg->motion_model > MPPI_MODEL_ACKERMANN) {return MPPI_E_CONFIG;}
   Optimizer * o = new Optimizer();
   o->cfg = *cfg;
   o->base_constraints = {cfg->vx_max, cfg->vx_min, cfg->vy_max, cfg->wz_max};
@@ -1383,6 +1387,49 @@ int oracle_shift_control_sequence(Optimizer * o)
   if (o->isHolonomic()) {roll(o->cs.vy);}
   return MPPI_OK;
 }
+
+static void oracle_shift_impl(Optimizer * o)
+{
+  auto roll = [](std::vector<float> & v) {
+      if (v.size() < 2) {return;}
+      std::rotate(v.begin(), v.begin() + 1, v.end());
+      v[v.size() - 1] = v[v.size() - 2];
+    };
+  roll(o->cs.vx); roll(o->cs.wz);
+  if (o->isHolonomic()) {roll(o->cs.vy);}
+}
+
+int oracle_optimize(Optimizer * o, const mppi_cycle_in * in, mppi_cycle_out * out);
+
+// ref: Optimizer::evalControl optimizer.cpp:134-155, one attempt (the fallback loop is the caller's): optimize(); if it
+// did not fail: savitskyGolayFilter, getControlFromSequenceAsTwist (:396-410), shiftControlSequence (:206-225)
+int oracle_eval_control(Optimizer * o, const mppi_cycle_in * in, int32_t shift_control_sequence, mppi_cycle_out * out, float cmd_out[3])
+{
+  mppi_cycle_out tmp;
+  std::memset(&tmp, 0, sizeof(tmp));
+  oracle_optimize(o, in, &tmp);
+  float cmd[3] = {0.0f, 0.0f, 0.0f};
+  if (!tmp.fail_flag) {
+    oracle::savitskyGolayFilter(o->cs, o->control_history, shift_control_sequence != 0);
+    const unsigned offset = shift_control_sequence ? 1 : 0;
+    cmd[0] = o->cs.vx[offset]; cmd[2] = o->cs.wz[offset];
+    cmd[1] = o->isHolonomic() ? o->cs.vy[offset] : 0.0f;
+    if (shift_control_sequence) {oracle_shift_impl(o);}
+  }
+  const size_t T = o->cfg.time_steps;
+  if (out) {
+    if (out->control_vx) {std::memcpy(out->control_vx, o->cs.vx.data(), T * 4);}
+    if (out->control_vy) {std::memcpy(out->control_vy, o->cs.vy.data(), T * 4);}
+    if (out->control_wz) {std::memcpy(out->control_wz, o->cs.wz.data(), T * 4);}
+    out->fail_flag = tmp.fail_flag;
+    out->furthest_reached_path_point = tmp.furthest_reached_path_point;
+    out->device_ms = 0.0f;
+  }
+  if (cmd_out) {std::memcpy(cmd_out, cmd, sizeof(cmd));}
+  return MPPI_OK;
+}
+int oracle_set_control_history(Optimizer * o, const float hist12[12]) {std::memcpy(o->control_history, hist12, 48); return MPPI_OK;}
+int oracle_get_control_history(Optimizer * o, float hist12[12]) {std::memcpy(hist12, o->control_history, 48); return MPPI_OK;}
 
 int oracle_optimize(Optimizer * o, const mppi_cycle_in * in, mppi_cycle_out * out)
 {

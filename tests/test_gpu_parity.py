@@ -367,3 +367,44 @@ def test_tile_and_stream_agree_at_full_size(product_fns, monkeypatch):
     np.testing.assert_allclose(ka, kb, rtol=1e-4, atol=2e-5)
     np.testing.assert_allclose(ra.vx, rb.vx, rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(ra.wz, rb.wz, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("shift", [False, True])
+@pytest.mark.parametrize("layout", ["tile", "stream"])
+def test_eval_control_tail_on_device(product_fns, oracle_fns, monkeypatch, shift, layout):
+    """mppi_eval_control: optimize + Savitzky-Golay filter with the control history + command + shift, all on the
+    device (utils.hpp:442-605, optimizer.cpp:147-152,206-225,396-410) against the oracle, 12 free-running cycles."""
+    monkeypatch.setenv("MPPI_STREAM_MIN_BATCH", "64" if layout == "stream" else "1000000000")
+    sc = scenarios.config1(batch=512)
+    g, o = _pair(product_fns, oracle_fns, sc, sc.noise())
+    hist = np.arange(12, dtype=np.float32).reshape(4, 3) * 0.01
+    g.set_control_history(hist)
+    o.set_control_history(hist)
+    for cycle in range(12):
+        cg, rg = g.eval_control(sc.cycle, shift)
+        co, ro = o.eval_control(sc.cycle, shift)
+        np.testing.assert_allclose(cg, co, rtol=RTOL, atol=ATOL, err_msg=f"cycle {cycle}: command")
+        for name, a, b in (("vx", rg.vx, ro.vx), ("vy", rg.vy, ro.vy), ("wz", rg.wz, ro.wz)):
+            np.testing.assert_allclose(a, b, rtol=RTOL, atol=ATOL, err_msg=f"cycle {cycle}: control {name}")
+        np.testing.assert_allclose(g.get_control_history(), o.get_control_history(), rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(np.stack(g.get_control_sequence()), np.stack(o.get_control_sequence()), rtol=RTOL, atol=ATOL)
+        # keep both sides on the same warm start so that the comparison stays point-wise
+        g.set_control_sequence(*o.get_control_sequence())
+        g.set_control_history(o.get_control_history())
+    assert np.abs(co).max() > 0.01
+
+
+def test_eval_control_skips_the_tail_on_failure(product_fns, oracle_fns):
+    """all trajectories collide: fail_flag is data, the filter / shift must not run (the reference resets instead)"""
+    sc = scenarios.config1(batch=256)
+    sc.cycle.costmap = np.full_like(sc.cycle.costmap, 254)
+    g, o = _pair(product_fns, oracle_fns, sc, sc.noise())
+    hist = np.ones((4, 3), np.float32)
+    for e in (g, o):
+        e.set_control_history(hist)
+    cg, rg = g.eval_control(sc.cycle, True)
+    co, ro = o.eval_control(sc.cycle, True)
+    assert rg.fail_flag and ro.fail_flag
+    np.testing.assert_array_equal(cg, np.zeros(3, np.float32))
+    np.testing.assert_array_equal(g.get_control_history(), hist)
+    np.testing.assert_allclose(np.stack(g.get_control_sequence()), np.stack(o.get_control_sequence()), rtol=RTOL, atol=ATOL)

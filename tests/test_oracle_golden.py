@@ -298,3 +298,34 @@ def test_det_sincos_vs_libm(oracle_fns):
     assert worst < 1.2e-7
     oracle_fns["det_sincosf"](0.0, C.byref(s), C.byref(c))
     assert s.value == 0.0 and c.value == 1.0
+
+
+def test_eval_control_is_optimize_then_filter_twist_shift(oracle_fns):
+    """Optimizer::evalControl (optimizer.cpp:134-155) = optimize, savitskyGolayFilter, command at `offset`, shift"""
+    from mpcholonavigation_b200 import _abi as abi, scenarios
+    sc = scenarios.config1(batch=128)
+    noise = sc.noise()
+    for shift in (False, True):
+        a, b = (Engine(oracle_fns, **sc.cfg) for _ in range(2))
+        for e in (a, b):
+            e.set_robot(sc.robot)
+            e.set_critics(sc.critics)
+            e.set_noise(*noise)
+        hist = np.zeros((4, 3), np.float32)
+        for cycle in range(4):
+            cmd, ra = a.eval_control(sc.cycle, shift)
+            rb = b.optimize(sc.cycle)
+            vx, vy, wz = rb.vx.copy(), rb.vy.copy(), rb.wz.copy()
+            h = hist.reshape(12).copy()
+            oracle_fns["savitsky_golay"](vx.ctypes.data_as(abi.f32p), vy.ctypes.data_as(abi.f32p), wz.ctypes.data_as(abi.f32p),
+                                         len(vx), h.ctypes.data_as(abi.f32p), int(shift))
+            hist = h.reshape(4, 3)
+            off = 1 if shift else 0
+            np.testing.assert_array_equal(cmd, np.array([vx[off], vy[off], wz[off]], np.float32))
+            if shift:
+                vx, vy, wz = (np.concatenate([v[1:], v[-1:]]) for v in (vx, vy, wz))
+            b.set_control_sequence(vx, vy, wz)
+            np.testing.assert_array_equal(np.stack(a.get_control_sequence()), np.stack([vx, vy, wz]))
+            np.testing.assert_array_equal(a.get_control_history(), hist)
+        a.close()
+        b.close()
