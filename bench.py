@@ -192,6 +192,8 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps (steady-state number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="sharded workload: exchanges fused into the kernels over peer memory (default) or NCCL collectives")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -236,14 +238,22 @@ def main():
     if sharded and world > 1:
         import ctypes as C
         from mpcholonavigation_b200 import abi
-        uid = torch.zeros(abi.NCCL_UNIQUE_ID_BYTES, dtype=torch.uint8)
-        if rank == 0:
-            buf = (C.c_uint8 * abi.NCCL_UNIQUE_ID_BYTES)()
-            assert fns["comm_get_unique_id"](buf) == 0
-            uid = torch.tensor(list(buf), dtype=torch.uint8)
-        uid = uid.cuda()
-        dist.broadcast(uid, 0)
-        e.comm_init(bytes(uid.cpu().tolist()), rank, world)
+        if args.exchange == "nccl":
+            uid = torch.zeros(abi.NCCL_UNIQUE_ID_BYTES, dtype=torch.uint8)
+            if rank == 0:
+                buf = (C.c_uint8 * abi.NCCL_UNIQUE_ID_BYTES)()
+                assert fns["comm_get_unique_id"](buf) == 0
+                uid = torch.tensor(list(buf), dtype=torch.uint8)
+            uid = uid.cuda()
+            dist.broadcast(uid, 0)
+            e.comm_init(bytes(uid.cpu().tolist()), rank, world)
+        else:
+            # exchanges over peer-mapped mailboxes (CUDA IPC, NVLink), fused into K3 and the merge kernel
+            mine_h = torch.tensor(list(e.comm_mailbox_handle()), dtype=torch.uint8, device="cuda")
+            all_h = [torch.zeros_like(mine_h) for _ in range(world)]
+            dist.all_gather(all_h, mine_h)
+            e.comm_connect_peers([bytes(t.cpu().tolist()) for t in all_h], rank, world)
+            dist.barrier()
 
     B_local = cfg["batch_size"]
     iters = cfg.get("iteration_count", 1)
@@ -339,7 +349,7 @@ def main():
             "config": {"workload": sc.name, "batch_size": B_total, "time_steps": T, "iteration_count": iters,
                        "critics": [c[0] for c in sc.critics], "costmap": list(sc.cycle.costmap.shape), "path_points": N,
                        "noise": noise_kind, "per_rank_batch": B_local,
-                       "parallelism": ("sharded over ranks, 2 NCCL exchanges" if sharded and world > 1 else
+                       "parallelism": (f"sharded over ranks, 2 exchanges ({'in-kernel over NVLink peer memory' if args.exchange == 'peer' else 'NCCL all-reduce + all-gather'})" if sharded and world > 1 else
                                        ("independent robots, one per rank" if world > 1 else "single GPU")),
                        "l2": "cold: 256 MiB written between timed steps" if flush is not None else "warm (no flush)"},
             "clocks": clocks,

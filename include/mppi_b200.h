@@ -275,6 +275,14 @@ mppi_status mppi_optimize_sharded(mppi_handle ** hs, int32_t n, const mppi_cycle
 #define MPPI_NCCL_UNIQUE_ID_BYTES 128
 mppi_status mppi_comm_get_unique_id(uint8_t id_out[MPPI_NCCL_UNIQUE_ID_BYTES]);
 mppi_status mppi_comm_init(mppi_handle * h, const uint8_t id[MPPI_NCCL_UNIQUE_ID_BYTES], int32_t rank, int32_t nranks);
+/* one process per GPU, NO NCCL: the two exchanges go through small mailboxes in peer-mapped HBM (CUDA IPC over NVLink /
+ * NVSwitch) and are fused into the kernels on either side of them (remote stores + system-scope flags; consumers spin
+ * on local memory, bounded).  Every rank: mppi_comm_get_mailbox_handle -> all-gather the 64-byte handles by any means
+ * (MPI, torch.distributed, a file) -> mppi_comm_connect_peers(all handles in rank order).  Needs peer access between
+ * the GPUs; MPPI_E_NCCL from mppi_optimize means a rank never arrived (time-out), not a hang. */
+#define MPPI_IPC_HANDLE_BYTES 64
+mppi_status mppi_comm_get_mailbox_handle(mppi_handle * h, uint8_t handle_out[MPPI_IPC_HANDLE_BYTES]);
+mppi_status mppi_comm_connect_peers(mppi_handle * h, const uint8_t * handles /* [nranks][64] */, int32_t rank, int32_t nranks);
 mppi_status mppi_comm_destroy(mppi_handle * h);
 
 #ifdef __cplusplus

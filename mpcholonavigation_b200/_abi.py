@@ -36,6 +36,7 @@ MAX_FOOTPRINT = 32
 MAX_TIME_STEPS = 256
 MAX_PATH_POINTS = 1024
 NCCL_UNIQUE_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 UINT32_MAX = 0xFFFFFFFF
 
 WANT_TRAJECTORIES, WANT_CELLS, WANT_CRITIC_COSTS = 1, 2, 4
@@ -196,6 +197,8 @@ PRODUCT_ONLY = {
     "get_profile": (C.c_int, [H, f32p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "comm_get_unique_id": (C.c_int, [u8p]),
     "comm_init": (C.c_int, [H, u8p, C.c_int32, C.c_int32]),
+    "comm_get_mailbox_handle": (C.c_int, [H, u8p]),
+    "comm_connect_peers": (C.c_int, [H, u8p, C.c_int32, C.c_int32]),
     "comm_destroy": (C.c_int, [H]),
 }
 

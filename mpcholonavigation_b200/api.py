@@ -309,6 +309,19 @@ class Engine:
         buf = (C.c_uint8 * abi.NCCL_UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
         self._check(self.f["comm_init"](self.h, buf, rank, nranks))
 
+    def comm_mailbox_handle(self) -> bytes:
+        """peer-memory exchange, step 1: this rank's 64-byte CUDA IPC handle (all-gather these over any transport)"""
+        buf = (C.c_uint8 * abi.IPC_HANDLE_BYTES)()
+        self._check(self.f["comm_get_mailbox_handle"](self.h, buf))
+        return bytes(buf)
+
+    def comm_connect_peers(self, handles, rank: int, nranks: int):
+        """peer-memory exchange, step 2: handles = the nranks handles in rank order"""
+        blob = b"".join(handles)
+        assert len(blob) == abi.IPC_HANDLE_BYTES * nranks
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self._check(self.f["comm_connect_peers"](self.h, buf, rank, nranks))
+
     # -- introspection ----------------------------------------------------------------------
     def set_outputs(self, trajectories=False, cells=False, critic_costs=False):
         mask = (abi.WANT_TRAJECTORIES if trajectories else 0) | (abi.WANT_CELLS if cells else 0) | \

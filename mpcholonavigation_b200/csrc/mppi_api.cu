@@ -120,6 +120,11 @@ struct mppi_handle
   size_t gkey_params[6]{0, 0, 0, 0, 0, 0}, gkey_costmap[6]{0, 0, 0, 0, 0, 0};
   unsigned gkey_inst[6]{0, 0, 0, 0, 0, 0};
   int tail_mode{0};            // 0: optimize only, 1: + evalControl tail, 2: + tail with shiftControlSequence
+  // peer-memory exchange (one process per GPU; mppi_comm_get_mailbox_handle / mppi_comm_connect_peers)
+  unsigned * d_mailbox{nullptr};          // this rank's mailbox (kBoxWords words)
+  unsigned * d_seq{nullptr};              // completed exchange rounds (survives mppi_reset: tags never repeat)
+  unsigned * peer_box[kMaxRanks]{};       // mailboxes of all ranks as mapped here; [rank] == d_mailbox
+  bool peer_mode{false};
   float * d_hist{nullptr};     // control_history_ [4][3] (vx, vy, wz), optimizer.hpp:251
   bool use_graph{true};
   size_t costmap_bytes{0}, params_copy_bytes{0};
@@ -562,6 +567,10 @@ DevBuffers make_bufs(mppi_handle * h, int mode)
   b.spill_x = h->d_spill[0]; b.spill_y = h->d_spill[1]; b.spill_yaw = h->d_spill[2];
   b.spill_cells = h->d_cells;
   b.costs = h->d_costs; b.partials = h->d_partials; b.rank_partial = h->d_rank_partial; b.out = h->d_out; b.st = h->d_st;
+  for (int r = 0; r < kMaxRanks; ++r) {b.peer.box[r] = h->peer_mode ? h->peer_box[r] : nullptr;}
+  b.peer.seq = h->d_seq;
+  b.peer.rank = h->rank;
+  b.peer.nranks = h->peer_mode ? h->nranks : 1;
   return b;
 }
 
@@ -702,41 +711,49 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
     mppi_status s = launch_rollout(h, 0);
     if (s != MPPI_OK) {return s;}
     if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[1], h->stream));}
-    if (h->nranks > 1) {
+    if (h->nranks > 1 && !h->peer_mode) {
       // exchange 1: furthest path point candidate + "some trajectory survived" flags, one MAX all-reduce
+      // (peer mode: the same exchange happens inside K3's preamble over the mapped mailboxes)
       NCCL_TRY(h, g_nccl.AllReduce(h->d_st, h->d_st, 1 + kMaxCritics, ncclUint32, ncclMax, h->comm, h->stream));
     }
     s = launch_update(h, 0, it);
     if (s != MPPI_OK) {return s;}
     const bool many = h->upd_blocks > kLastBlockMergeMax;
     const int merge_grid = (h->T + kMergeT - 1) / kMergeT;
+    const DevParams * dp = reinterpret_cast<const DevParams *>(h->d_params);
+    const int chunks = (h->B + kWsChunk - 1) / kWsChunk;
     if (h->stream_layout) {
       // K3 published costs + global minimum; weights and weighted control sums over the time-major noise
-      const int chunks = (h->B + kWsChunk - 1) / kWsChunk;
       const int gy = weighted_sums_row_groups(h->T, chunks);
-      weighted_sums_tm_kernel<<<dim3(chunks, gy), kWsThreads, 0, h->stream>>>(reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, 0));
-      CUDA_TRY(h, cudaGetLastError());
-      merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
-        reinterpret_cast<const DevParams *>(h->d_params), h->d_partials, chunks, stride, make_bufs(h, 0),
-        h->nranks > 1 ? 0 : 1, h->d_rank_partial);
-      CUDA_TRY(h, cudaGetLastError());
-      h->launches += 2;
-    } else if (many) {
-      // too many block partials for a serial merge in K3's last block: merge them in parallel
-      merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
-        reinterpret_cast<const DevParams *>(h->d_params), h->d_partials, h->upd_blocks, stride, make_bufs(h, 0),
-        h->nranks > 1 ? 0 : 1, h->d_rank_partial);
+      weighted_sums_tm_kernel<<<dim3(chunks, gy), kWsThreads, 0, h->stream>>>(dp, make_bufs(h, 0));
       CUDA_TRY(h, cudaGetLastError());
       h->launches++;
     }
-    if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[2], h->stream));}
-    if (h->nranks > 1) {
-      // exchange 2: per-rank (min, sum, weighted control sums); merged redundantly on every rank
-      NCCL_TRY(h, g_nccl.AllGather(h->d_rank_partial, h->d_gathered, stride, ncclFloat32, h->comm, h->stream));
-      merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
-        reinterpret_cast<const DevParams *>(h->d_params), h->d_gathered, h->nranks, stride, make_bufs(h, 0), 1, nullptr);
+    if (h->nranks > 1 && h->peer_mode) {
+      // exchange 2 over peer memory, fused with the local merge before it and the cross-rank merge after it
+      if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[2], h->stream));}
+      const bool merged_in_k3 = !h->stream_layout && !many;   // K3's last block already merged into rank_partial
+      merge_exchange_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
+        dp, merged_in_k3 ? h->d_rank_partial : h->d_partials, merged_in_k3 ? 1 : (h->stream_layout ? chunks : h->upd_blocks), stride,
+        make_bufs(h, 0));
       CUDA_TRY(h, cudaGetLastError());
       h->launches++;
+    } else {
+      if (h->stream_layout || many) {
+        // too many partial records for a serial merge in K3's last block (or the stream layout): merge in parallel
+        merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
+          dp, h->d_partials, h->stream_layout ? chunks : h->upd_blocks, stride, make_bufs(h, 0), h->nranks > 1 ? 0 : 1, h->d_rank_partial);
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches++;
+      }
+      if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[2], h->stream));}
+      if (h->nranks > 1) {
+        // exchange 2: per-rank (min, sum, weighted control sums); merged redundantly on every rank
+        NCCL_TRY(h, g_nccl.AllGather(h->d_rank_partial, h->d_gathered, stride, ncclFloat32, h->comm, h->stream));
+        merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(dp, h->d_gathered, h->nranks, stride, make_bufs(h, 0), 1, nullptr);
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches++;
+      }
     }
   }
   if (h->tail_mode) {
@@ -746,7 +763,7 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
     h->launches++;
   }
   if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[3], h->stream));}
-  CUDA_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(float) * (3 * h->T + 5), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(float) * (3 * h->T + 6), cudaMemcpyDeviceToHost, h->stream));
   return MPPI_OK;
 }
 
@@ -755,8 +772,8 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
 mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
 {
   const bool prof = h->profiling && h->cfg.iteration_count == 1;
-  const bool graph_ok = h->use_graph && !prof && h->nranks == 1;
-  h->d2h_bytes = sizeof(float) * (3 * h->T + 5);
+  const bool graph_ok = h->use_graph && !prof && (h->nranks == 1 || h->peer_mode);   // NCCL calls are not captured
+  h->d2h_bytes = sizeof(float) * (3 * h->T + 6);
   h->h2d_bytes = with_upload ? h->params_copy_bytes + h->costmap_bytes : 0;
   CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
   if (graph_ok) {
@@ -828,6 +845,11 @@ mppi_status finish_optimize(mppi_handle * h, mppi_cycle_out * out)
     out->device_ms = ms;
   }
   cudaEventElapsedTime(&h->prof_ms[3], h->ev0, h->ev1);
+  if (h->peer_mode) {
+    uint32_t comm_error;
+    std::memcpy(&comm_error, h->h_out + 3 * T + 5, 4);
+    if (comm_error) {return fail(h, MPPI_E_NCCL, "peer-memory exchange timed out: a rank did not arrive");}
+  }
   if (h->profiling && h->cfg.iteration_count == 1) {
     cudaEventElapsedTime(&h->prof_ms[0], h->pev[0], h->pev[1]);
     // with sharding the span pev[1]..pev[2] also holds exchange 1; K3 alone is not separable there
@@ -953,13 +975,18 @@ void mppi_destroy(mppi_handle * h)
   if (h->stream) {cudaStreamSynchronize(h->stream);}
   drop_graphs(h);
   if (h->comm && g_nccl.CommDestroy) {g_nccl.CommDestroy(h->comm);}
+  if (h->peer_mode) {
+    for (int r = 0; r < h->nranks; ++r) {
+      if (r != h->rank && h->peer_box[r]) {cudaIpcCloseMemHandle(h->peer_box[r]);}
+    }
+  }
   for (float * p : h->d_noise) {cudaFree(p);}
   for (float * p : h->d_samples) {cudaFree(p);}
   for (float * p : h->d_spill) {cudaFree(p);}
   for (float * p : h->d_inj) {cudaFree(p);}
   cudaFree(h->d_tmp); cudaFree(h->d_costmap); cudaFree(h->d_params); cudaFree(h->d_cs); cudaFree(h->d_crit_rows);
   cudaFree(h->d_end_xy); cudaFree(h->d_cells); cudaFree(h->d_costs); cudaFree(h->d_partials); cudaFree(h->d_rank_partial);
-  cudaFree(h->d_gathered); cudaFree(h->d_out); cudaFree(h->d_st); cudaFree(h->d_hist);
+  cudaFree(h->d_gathered); cudaFree(h->d_out); cudaFree(h->d_st); cudaFree(h->d_hist); cudaFree(h->d_seq); cudaFree(h->d_mailbox);
   cudaFreeHost(h->h_params); cudaFreeHost(h->h_costmap); cudaFreeHost(h->h_out);
   if (h->ev0) {cudaEventDestroy(h->ev0);}
   if (h->ev1) {cudaEventDestroy(h->ev1);}
@@ -1038,6 +1065,8 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   CUDA_TRY(h, cudaMalloc(&h->d_out, (stride + 8) * sizeof(float)));
   CUDA_TRY(h, cudaMemsetAsync(h->d_out, 0, (stride + 8) * sizeof(float), h->stream));
   CUDA_TRY(h, cudaMalloc(&h->d_hist, 12 * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->d_seq, sizeof(unsigned)));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_seq, 0, sizeof(unsigned), h->stream));
   CUDA_TRY(h, cudaMalloc(&h->d_st, sizeof(DevState)));
   CUDA_TRY(h, cudaMallocHost(&h->h_params, kParamsCapacity));
   CUDA_TRY(h, cudaMallocHost(&h->h_out, (stride + 8) * sizeof(float)));
@@ -1251,7 +1280,7 @@ mppi_status mppi_optimize(mppi_handle * h, const mppi_cycle_in * in, mppi_cycle_
 mppi_status mppi_eval_control(mppi_handle * h, const mppi_cycle_in * in, int32_t shift_control_sequence, mppi_cycle_out * out, float cmd_out[3])
 {
   if (!h || !in) {return MPPI_E_CONFIG;}
-  if (h->nranks > 1) {return fail(h, MPPI_E_STATE, "mppi_eval_control on a sharded handle: use mppi_optimize + the host tail");}
+  if (h->nranks > 1 && !h->peer_mode) {return fail(h, MPPI_E_STATE, "mppi_eval_control on an NCCL-sharded handle: use mppi_optimize + the host tail");}
   h->tail_mode = shift_control_sequence ? 2 : 1;
   mppi_status s = optimize_begin(h, in);
   if (s == MPPI_OK) {s = finish_optimize(h, out);}
@@ -1575,9 +1604,59 @@ mppi_status mppi_comm_init(mppi_handle * h, const uint8_t id[MPPI_NCCL_UNIQUE_ID
   return MPPI_OK;
 }
 
+// ---- peer-memory exchange: no NCCL, the exchanges ride inside K3 and the merge kernel (mppi_device.cuh PeerComm) ----
+mppi_status mppi_comm_get_mailbox_handle(mppi_handle * h, uint8_t handle_out[MPPI_IPC_HANDLE_BYTES])
+{
+  static_assert(sizeof(cudaIpcMemHandle_t) == MPPI_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+  if (!h || !handle_out) {return MPPI_E_CONFIG;}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (!h->d_mailbox) {
+    CUDA_TRY(h, cudaMalloc(&h->d_mailbox, sizeof(unsigned) * kBoxWords));
+    CUDA_TRY(h, cudaMemset(h->d_mailbox, 0, sizeof(unsigned) * kBoxWords));
+  }
+  cudaIpcMemHandle_t ipc;
+  CUDA_TRY(h, cudaIpcGetMemHandle(&ipc, h->d_mailbox));
+  std::memcpy(handle_out, &ipc, sizeof(ipc));
+  return MPPI_OK;
+}
+
+mppi_status mppi_comm_connect_peers(mppi_handle * h, const uint8_t * handles, int32_t rank, int32_t nranks)
+{
+  if (!h || !handles || nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) {return MPPI_E_CONFIG;}
+  if (!h->d_mailbox) {return fail(h, MPPI_E_STATE, "mppi_comm_get_mailbox_handle first");}
+  if (h->comm) {return fail(h, MPPI_E_STATE, "handle is bound to an NCCL communicator");}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  drop_graphs(h);
+  for (int r = 0; r < nranks; ++r) {
+    if (r == rank) {h->peer_box[r] = h->d_mailbox; continue;}
+    cudaIpcMemHandle_t ipc;
+    std::memcpy(&ipc, handles + static_cast<size_t>(r) * MPPI_IPC_HANDLE_BYTES, sizeof(ipc));
+    void * p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(h, MPPI_E_CUDA, std::string("cudaIpcOpenMemHandle (peer access between the GPUs of the box is required): ") + cudaGetErrorString(e));
+    }
+    h->peer_box[r] = static_cast<unsigned *>(p);
+  }
+  h->rank = rank; h->nranks = nranks; h->peer_mode = nranks > 1;
+  return MPPI_OK;
+}
+
 mppi_status mppi_comm_destroy(mppi_handle * h)
 {
   if (!h) {return MPPI_E_CONFIG;}
+  if (h->peer_mode) {
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    drop_graphs(h);
+    for (int r = 0; r < h->nranks; ++r) {
+      if (r != h->rank && h->peer_box[r]) {cudaIpcCloseMemHandle(h->peer_box[r]);}
+      h->peer_box[r] = nullptr;
+    }
+    h->peer_mode = false;
+  }
   if (h->comm) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);

@@ -120,6 +120,60 @@ __device__ __forceinline__ void load_hot_params(float * s_hot, const DevParams *
   for (int i = tid; i < kHotBytes / 16; i += nthreads) {dst[i] = __ldg(src + i);}
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Peer-memory exchange between the ranks of a sharded problem (one process per GPU, NVLink / NVSwitch).
+// Every rank owns a small MAILBOX in its own HBM and maps the mailboxes of all peers (CUDA IPC).  A rank PUSHES its
+// contribution into slot [its rank] of every mailbox with plain remote stores, fences, then writes the cycle tag
+// into the slot's flag with a system-scope release store; consumers spin on flags in their LOCAL memory only.
+// No NCCL call, no extra kernel, no host involvement: exchange 1 rides at the start of K3, exchange 2 inside the
+// merge kernel.  Spins are bounded: a peer that never arrives raises comm_error instead of hanging.
+//   mailbox words:  x1   [kMaxRanks][kX1Words]   word 0 = tag, words 1..17 = furthest candidate + survivor flags
+//                   x2f  [kMaxRanks] (padded)     tag of the record below
+//                   x2   [kMaxRanks][kX2Stride]   (m, s, W[3T]) softmax record of the rank
+// ---------------------------------------------------------------------------------------------------
+constexpr int kMaxRanks = 16;
+constexpr int kX1Words = 32;
+constexpr int kX2Stride = ((3 * MPPI_MAX_TIME_STEPS + 2 + 15) / 16) * 16;
+constexpr int kBoxX1 = 0;
+constexpr int kBoxX2Flag = kMaxRanks * kX1Words;
+constexpr int kBoxX2 = kBoxX2Flag + 32;
+constexpr int kBoxWords = kBoxX2 + kMaxRanks * kX2Stride;
+constexpr long long kSpinLimitCycles = 4000000000LL;   // ~2 s at 1.965 GHz
+
+struct PeerComm
+{
+  unsigned * box[kMaxRanks];   // box[r] = mailbox of rank r as mapped into this process; box[rank] is local memory
+  unsigned * seq;              // local: number of completed exchange rounds; the tag of the current round is *seq + 1
+  int rank, nranks;            // nranks <= 1: not sharded over peer memory
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned * p, unsigned v)
+{
+  asm volatile ("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned * p)
+{
+  unsigned v;
+  asm volatile ("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned * p)
+{
+  unsigned v;
+  asm volatile ("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// bounded spin on a flag in local memory
+__device__ __forceinline__ bool wait_tag(const unsigned * p, unsigned tag)
+{
+  const long long t0 = clock64();
+  while (ld_acquire_sys(p) != tag) {
+    if (clock64() - t0 > kSpinLimitCycles) {return false;}
+    __nanosleep(32);
+  }
+  return true;
+}
+
 // Persistent per-optimize state shared between kernels (device memory, 1 record per handle).
 struct DevState
 {
@@ -130,6 +184,7 @@ struct DevState
   int fail_flag;
   unsigned ticket;                      // last-block election of the update kernel
   float global_min;                     // stream layout: min over all costs, published by K3's last block
+  unsigned comm_error;                  // a peer-memory exchange timed out (sticky until reset)
 };
 
 // ---------------------------------------------------------------------------------------------------

@@ -50,6 +50,7 @@ struct DevBuffers
   float * rank_partial; // [3T + 2] (+ fail flag / furthest packed after it for the exchange)
   float * out;          // [3T + 4]: new control sequence, fail flag, furthest (as bit patterns)
   DevState * st;
+  PeerComm peer;        // sharded over peer memory when peer.nranks > 1
 };
 
 // accumulator slots of the per-segment partials
@@ -1005,7 +1006,8 @@ struct K3Path
 // decisions that depend on device results (which critic failed, the furthest reached point) are a handful of
 // table look-ups: everything that is a function of "furthest" alone was tabulated by the host (build_params).
 __device__ __forceinline__ void k3_preamble(
-  float * smem, const DevParams * __restrict__ Pg, DevState * st, int iteration, int tid, int nthr, K3Path & path, K3Decisions * dec)
+  float * smem, const DevParams * __restrict__ Pg, DevState * st, const PeerComm & pc, int iteration, int tid, int nthr, K3Path & path,
+  K3Decisions * dec)
 {
   __shared__ unsigned s_any_ok[kMaxCritics];
   __shared__ unsigned s_state[4];   // furthest_candidate, furthest, furthest_set, fail_flag
@@ -1015,6 +1017,31 @@ __device__ __forceinline__ void k3_preamble(
   if (tid < kMaxCritics) {s_any_ok[tid] = st->any_ok[tid];}
   if (tid == 32) {s_state[0] = st->furthest_candidate; s_state[1] = st->furthest;}
   if (tid == 33) {s_state[2] = static_cast<unsigned>(st->furthest_set); s_state[3] = static_cast<unsigned>(st->fail_flag);}
+  if (pc.nranks > 1) {
+    // ---- exchange 1 over peer memory: element-wise MAX of (furthest candidate, survivor flags) across the ranks.
+    //      Block 0 pushes this rank's 17 words into every mailbox; every block then waits on its LOCAL mailbox.
+    const unsigned tag = ld_volatile_u32(pc.seq) + 1u;
+    constexpr int kWords = 1 + kMaxCritics;
+    if (blockIdx.x == 0) {
+      if (tid < kWords) {
+        const unsigned v = tid == 0 ? st->furthest_candidate : st->any_ok[tid - 1];
+        for (int r = 0; r < pc.nranks; ++r) {pc.box[r][kBoxX1 + pc.rank * kX1Words + 1 + tid] = v;}
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (tid < pc.nranks) {st_release_sys(pc.box[tid] + kBoxX1 + pc.rank * kX1Words, tag);}
+    }
+    const unsigned * local = pc.box[pc.rank];
+    bool ok = true;
+    if (tid < pc.nranks) {ok = wait_tag(local + kBoxX1 + tid * kX1Words, tag);}
+    if (!ok) {st->comm_error = 1u;}
+    __syncthreads();
+    if (tid < kWords) {
+      unsigned m = 0u;
+      for (int r = 0; r < pc.nranks; ++r) {m = max(m, ld_volatile_u32(local + kBoxX1 + r * kX1Words + 1 + tid));}
+      if (tid == 0) {s_state[0] = m;} else {s_any_ok[tid - 1] = m;}
+    }
+  }
   const DevParams * P = reinterpret_cast<const DevParams *>(s_hot);
   const float * tail = reinterpret_cast<const float *>(Pg + 1);
   // record tail layout (build_params): x[N] y[N] yaw[N] D[N] | valid[n16] flags[n16] follow_idx[N] (uint16)
@@ -1300,7 +1327,7 @@ __global__ void __launch_bounds__(kUpdThreads) path_costs_tm_kernel(const DevPar
   __shared__ unsigned sc_last;
   const int tid = threadIdx.x;
   K3Path path;
-  k3_preamble(smem, Pg, bufs.st, iteration, tid, kUpdThreads, path, &dec);
+  k3_preamble(smem, Pg, bufs.st, bufs.peer, iteration, tid, kUpdThreads, path, &dec);
   const DevParams * P = reinterpret_cast<const DevParams *>(smem);
   const int B = P->B, T = P->T;
   float m = 3.402823466e+38f;
@@ -1385,7 +1412,7 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
   }
   MPPI_TRACE_AT(17);
   K3Path path;
-  k3_preamble(smem, Pg, bufs.st, iteration, tid, kUpdThreads, path, &dec);
+  k3_preamble(smem, Pg, bufs.st, bufs.peer, iteration, tid, kUpdThreads, path, &dec);
   const DevParams * P = reinterpret_cast<const DevParams *>(smem);   // hot fields only; arrays stay in global (Pg)
   const int T = P->T, B = P->B;
   DevState * st = bufs.st;
@@ -1620,6 +1647,102 @@ __global__ void __launch_bounds__(kUpdThreads) merge_finalize_kernel(
       bufs.cs[t] = vx; bufs.cs[T + t] = vy; bufs.cs[2 * T + t] = wz;
       bufs.out[t] = vx; bufs.out[T + t] = vy; bufs.out[2 * T + t] = wz;
     }
+  }
+}
+
+// K4p: exchange 2 over peer memory, fused with the merges on both sides of it.  Every block merges its columns of the
+// rank's partial records (like merge_finalize_kernel) and PUSHES the merged slice into slot [rank] of every rank's
+// mailbox; the last block to finish publishes the tag, waits for the tags of all ranks in its local mailbox, merges
+// the nranks records and writes the new control sequence.  Every rank ends with the same sequence; no broadcast.
+__global__ void __launch_bounds__(kUpdThreads) merge_exchange_finalize_kernel(
+  const DevParams * __restrict__ Pg, const float * __restrict__ parts, int n, int stride, DevBuffers bufs)
+{
+  __shared__ float s_red[kUpdThreads / 32];
+  __shared__ float s_col[3 * kMergeT + 1];
+  __shared__ float s_e[kMergeCached];
+  __shared__ unsigned sc_last;
+  const PeerComm & pc = bufs.peer;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = Pg->T;
+  const float inv_temp = 1.0f / Pg->temperature;
+  const unsigned tag = ld_volatile_u32(pc.seq) + 1u;
+  // ---- local merge of this rank's partial records (identical to merge_finalize_kernel)
+  float m = 3.402823466e+38f;
+  for (int i = tid; i < n; i += kUpdThreads) {m = fminf(m, __ldg(parts + static_cast<size_t>(i) * stride));}
+  m = warp_min(m);
+  if (lane == 0) {s_red[warp] = m;}
+  __syncthreads();
+  m = s_red[0];
+#pragma unroll
+  for (int w = 1; w < kUpdThreads / 32; ++w) {m = fminf(m, s_red[w]);}
+  for (int i = tid; i < min(n, kMergeCached); i += kUpdThreads) {
+    s_e[i] = expf(-(__ldg(parts + static_cast<size_t>(i) * stride) - m) * inv_temp);
+  }
+  __syncthreads();
+  const int t_first = blockIdx.x * kMergeT;
+  for (int k = warp; k < 3 * kMergeT + 1; k += kUpdThreads / 32) {
+    int col;
+    if (k == 0) {
+      col = 0;
+    } else {
+      const int t = t_first + (k - 1) / 3, plane = (k - 1) % 3;
+      if (t >= T) {continue;}
+      col = 1 + plane * T + t;
+    }
+    float acc = 0.0f;
+    for (int i = lane; i < n; i += 32) {
+      const float * p = parts + static_cast<size_t>(i) * stride;
+      const float e = i < kMergeCached ? s_e[i] : expf(-(__ldg(p) - m) * inv_temp);
+      acc = fmaf(__ldg(p + 1 + col), e, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {s_col[k] = acc;}
+  }
+  __syncthreads();
+  // ---- push the merged slice into every rank's mailbox (remote stores over NVLink; slot = this rank)
+  if (tid < kMergeT && t_first + tid < T) {
+    const int t = t_first + tid;
+    for (int r = 0; r < pc.nranks; ++r) {
+      float * rec = reinterpret_cast<float *>(pc.box[r] + kBoxX2 + pc.rank * kX2Stride);
+      if (blockIdx.x == 0 && tid == 0) {rec[0] = m; rec[1] = s_col[0];}
+      rec[2 + t] = s_col[1 + 3 * tid]; rec[2 + T + t] = s_col[2 + 3 * tid]; rec[2 + 2 * T + t] = s_col[3 + 3 * tid];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {sc_last = atomicAdd(&bufs.st->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;}
+  __syncthreads();
+  if (!sc_last) {return;}
+  // ---- last block: publish, wait for every rank, merge the nranks records, finalize
+  __threadfence_system();
+  if (tid < pc.nranks) {st_release_sys(pc.box[tid] + kBoxX2Flag + pc.rank, tag);}
+  const unsigned * local = pc.box[pc.rank];
+  bool ok = true;
+  if (tid < pc.nranks) {ok = wait_tag(local + kBoxX2Flag + tid, tag);}
+  if (!ok) {bufs.st->comm_error = 1u;}
+  __syncthreads();
+  float * merged = s_e;   // [3T + 2] (3 * 256 + 2 <= kMergeCached)
+  {
+    float gm = 3.402823466e+38f;
+    for (int r = 0; r < pc.nranks; ++r) {gm = fminf(gm, __uint_as_float(ld_volatile_u32(local + kBoxX2 + r * kX2Stride)));}
+    for (int c = tid; c < 3 * T + 1; c += kUpdThreads) {
+      float acc = 0.0f;
+      for (int r = 0; r < pc.nranks; ++r) {
+        const unsigned * rec = local + kBoxX2 + r * kX2Stride;
+        const float e = expf(-(__uint_as_float(ld_volatile_u32(rec)) - gm) * inv_temp);
+        acc = fmaf(__uint_as_float(ld_volatile_u32(rec + 1 + c)), e, acc);
+      }
+      merged[1 + c] = acc;
+    }
+    if (tid == 0) {merged[0] = gm;}
+  }
+  __syncthreads();
+  finalize_controls(Pg, merged, bufs.cs, bufs.out, tid, kUpdThreads);
+  if (tid == 0) {
+    bufs.st->ticket = 0u;
+    bufs.out[3 * T + 5] = __uint_as_float(bufs.st->comm_error);
+    __threadfence();
+    *pc.seq = tag;   // round complete on this rank
   }
 }
 

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Correctness of the NCCL-sharded optimize(): launch with torchrun, one rank per GPU.
+"""Correctness of the sharded optimize(), one rank per GPU (launch with torchrun): CHECK_EXCHANGE=peer (default, exchanges over
+peer-mapped mailboxes fused into the kernels) or CHECK_EXCHANGE=nccl (all-reduce + all-gather baseline).
 
 Each rank owns B/world trajectories (Philox noise by global index).  Rank 0 additionally solves the same
 problem in-process (mppi_optimize_sharded with `world` shards on its own GPU) and the control sequences of all
@@ -34,19 +35,27 @@ def main():
         return e
 
     e = make(b0, b1, local)
-    uid = torch.zeros(abi.NCCL_UNIQUE_ID_BYTES, dtype=torch.uint8)
-    if rank == 0:
-        buf = (C.c_uint8 * abi.NCCL_UNIQUE_ID_BYTES)()
-        assert fns["comm_get_unique_id"](buf) == 0
-        uid = torch.tensor(list(buf), dtype=torch.uint8)
-    uid = uid.cuda()
-    dist.broadcast(uid, 0)
-    e.comm_init(bytes(uid.cpu().tolist()), rank, world)
+    exchange = os.environ.get("CHECK_EXCHANGE", "peer")
+    if exchange == "nccl":
+        uid = torch.zeros(abi.NCCL_UNIQUE_ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_uint8 * abi.NCCL_UNIQUE_ID_BYTES)()
+            assert fns["comm_get_unique_id"](buf) == 0
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        e.comm_init(bytes(uid.cpu().tolist()), rank, world)
+    else:
+        mine_h = torch.tensor(list(e.comm_mailbox_handle()), dtype=torch.uint8, device="cuda")
+        all_h = [torch.zeros_like(mine_h) for _ in range(world)]
+        dist.all_gather(all_h, mine_h)
+        e.comm_connect_peers([bytes(t.cpu().tolist()) for t in all_h], rank, world)
+        dist.barrier()
     ref = None
     if rank == 0:
         ref = [make(*sharding.shard_bounds(B, r, world), local) for r in range(world)]
     ok = True
-    for cycle in range(4):
+    for cycle in range(int(os.environ.get("CHECK_CYCLES", "6"))):
         r = e.optimize(sc.cycle)
         mine = torch.tensor(np.concatenate([r.vx, r.vy, r.wz]), device="cuda")
         allv = [torch.zeros_like(mine) for _ in range(world)]
@@ -60,6 +69,10 @@ def main():
                 ok = ok and good
                 print(f"cycle {cycle} rank {k}: max abs diff vs in-process reference {np.abs(got - want).max():.3e} "
                       f"{'OK' if good else 'MISMATCH'}  device_ms={r.device_ms:.3f} furthest={r.furthest_reached_path_point}")
+    if rank == 0:
+        print("exchange:", exchange)
+    dist.barrier()
+    e.close()
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:
