@@ -64,11 +64,19 @@ MPPI_HD void mppi_det_sincosf(float x, float * s_out, float * c_out)
   float r;
   int32_t q;
   if (fabsf(x) <= 1.0e5f) {
+#if defined(__CUDA_ARCH__)
+    /* rintf + float->int without conversion instructions: adding 1.5 * 2^23 rounds (to nearest even, like rintf) the
+     * product to an integer that sits in the low mantissa bits; |x * 2/pi| < 2^16 here.  Same kf, same q. */
+    const float tm = __fadd_rn(MPPI_FMUL(x, MPPI_TWO_OVER_PI_F), 12582912.0f);
+    const float kf = __fsub_rn(tm, 12582912.0f);
+    q = __float_as_int(tm) - 0x4B400000;
+#else
     const float kf = rintf(MPPI_FMUL(x, MPPI_TWO_OVER_PI_F));
+    q = (int32_t)kf;
+#endif
     r = MPPI_FFMA(-kf, MPPI_PIO2_C1, x);
     r = MPPI_FFMA(-kf, MPPI_PIO2_C2, r);
     r = MPPI_FFMA(-kf, MPPI_PIO2_C3, r);
-    q = (int32_t)kf;
   } else if (fabsf(x) <= 2.0e9f) {
     const double xd = (double)x;
     const double kd = rint(MPPI_DMUL(xd, MPPI_TWO_OVER_PI_D));

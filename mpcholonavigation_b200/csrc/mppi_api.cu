@@ -276,6 +276,7 @@ mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, un
   p.N = N;
   p.goal_yaw = in->path_yaw[N - 1];
   p.size_x = in->costmap.size_x; p.size_y = in->costmap.size_y;
+  if (p.size_x >= (1u << 22) || p.size_y >= (1u << 22)) {return fail(h, MPPI_E_CONFIG, "costmap side must be < 2^22 cells");}
   p.res = in->costmap.resolution; p.ox = in->costmap.origin_x; p.oy = in->costmap.origin_y;
   // fp32 filter of worldToMap (mppi_device.cuh world_to_cell_fast): operands and rigorous error bounds in cells
   p.cell_oxf = static_cast<float>(p.ox);
@@ -677,8 +678,24 @@ mppi_status launch_rollout(mppi_handle * h, int mode)
   const size_t smem = rollout_smem_bytes(h->T, S, mode);
   if (smem > 227 * 1024) {return fail(h, MPPI_E_CONFIG, "time_steps too large for the shared-memory tile");}
   const dim3 grid((h->B + kTile - 1) / kTile), block(kTile, S);
-  rollout_score_kernel<<<grid, block, smem, h->stream>>>(
-    reinterpret_cast<const DevParams *>(h->d_params), h->d_costmap, make_bufs(h, mode), h->B, h->T, mode);
+  const DevParams * dp = reinterpret_cast<const DevParams *>(h->d_params);
+  const unsigned inst = mode == 0 ? pick_stream_instance(stream_feature_need(h->last)) : SF_ALL;
+#define MPPI_LAUNCH_TILE(F, EXACT, MODE) \
+  rollout_score_kernel<F, EXACT, MODE><<<grid, block, smem, h->stream>>>(dp, h->d_costmap, make_bufs(h, mode), h->B, h->T)
+  if (mode == 1) {
+    MPPI_LAUNCH_TILE(SF_ALL, false, 1);
+  } else if (mode == 2) {
+    MPPI_LAUNCH_TILE(SF_ALL, false, 2);
+  } else if (inst == kSfOmniDefault) {
+    MPPI_LAUNCH_TILE(kSfOmniDefault, true, 0);
+  } else if (inst == kSfOmniDefaultFp) {
+    MPPI_LAUNCH_TILE(kSfOmniDefaultFp, true, 0);
+  } else if (inst == kSfObstaclesFp) {
+    MPPI_LAUNCH_TILE(kSfObstaclesFp, true, 0);
+  } else {
+    MPPI_LAUNCH_TILE(SF_ALL, false, 0);
+  }
+#undef MPPI_LAUNCH_TILE
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   return MPPI_OK;
@@ -778,7 +795,7 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
   CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
   if (graph_ok) {
     const int slot = (with_upload ? 1 : 0) + 2 * h->tail_mode;
-    const unsigned inst = h->stream_layout ? pick_stream_instance(stream_feature_need(h->last)) : 0u;
+    const unsigned inst = pick_stream_instance(stream_feature_need(h->last));   // the K2 instance is baked into the graph
     if (h->gexec[slot] && (h->gkey_params[slot] != h->params_copy_bytes || h->gkey_costmap[slot] != h->costmap_bytes ||
       h->gkey_inst[slot] != inst))
     {
@@ -1022,7 +1039,7 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   if (const char * e = std::getenv("MPPI_NO_GRAPH")) {h->use_graph = std::atoi(e) == 0;}
   {
     // batches too small to fill the GPU with one thread per trajectory keep the latency-oriented tile kernel
-    long long stream_min = 32768;   // measured cross-over on B200 (profiles/): below it the tile kernel wins
+    long long stream_min = 8192;    // measured cross-over on B200 (profiles/): below it the tile kernel wins
     if (const char * e = std::getenv("MPPI_STREAM_MIN_BATCH")) {stream_min = std::atoll(e);}
     h->stream_layout = cfg->batch_size >= stream_min;
   }
@@ -1032,7 +1049,15 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
     return MPPI_E_CUDA;
   }
   CUDA_TRY(h, cudaSetDevice(h->device));
-  CUDA_TRY(h, cudaFuncSetAttribute(rollout_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  {
+    const int big = 227 * 1024;
+    CUDA_TRY(h, cudaFuncSetAttribute(rollout_score_kernel<SF_ALL, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(h, cudaFuncSetAttribute(rollout_score_kernel<SF_ALL, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(h, cudaFuncSetAttribute(rollout_score_kernel<SF_ALL, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(h, cudaFuncSetAttribute(rollout_score_kernel<kSfOmniDefault, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(h, cudaFuncSetAttribute(rollout_score_kernel<kSfOmniDefaultFp, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(h, cudaFuncSetAttribute(rollout_score_kernel<kSfObstaclesFp, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  }
   CUDA_TRY(h, cudaFuncSetAttribute(path_softmax_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
     static_cast<int>(k3_tile_smem_bytes(MPPI_MAX_TIME_STEPS))));
   CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));

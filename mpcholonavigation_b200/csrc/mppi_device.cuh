@@ -214,7 +214,7 @@ __device__ __forceinline__ int world_to_cell(
 // instructions instead of ~55 fp64/conversion instructions per pose.
 struct CellGrid
 {
-  float oxf, oyf, invf, eps_x, eps_y;
+  float oxf, oyf, invf, half_minus_eps_x, half_minus_eps_y;   // 0.5 - error bound in cells (<= 0: always the slow path)
   unsigned size_x, size_y;
 };
 
@@ -225,27 +225,28 @@ __device__ __noinline__ int world_to_cell_slow(float xf, float yf, const double 
   return world_to_cell(static_cast<double>(xf), static_cast<double>(yf), geom[1], geom[2], geom[0], size_x, size_y, mx, my);
 }
 
-// round-to-nearest-even integer of q (|q| < 2^22) without conversion instructions: r = rint(q), i = int(r)
-__device__ __forceinline__ void rint_magic(float q, float & r, int & i)
+// floor of q without conversion instructions: adding 1.5 * 2^23 with round-down leaves floor(q) in the low mantissa
+// bits (exact for |q| < 2^22; beyond that the decoded integer is >= 2^22 in magnitude, i.e. off any map).
+// frac = q - floor(q) is exact.
+__device__ __forceinline__ void floor_magic(float q, int & i, float & frac)
 {
-  const float t = __fadd_rn(q, 12582912.0f);          // 1.5 * 2^23: the add rounds q to an integer
-  r = __fsub_rn(t, 12582912.0f);                      // exact
+  const float t = __fadd_rd(q, 12582912.0f);
   i = __float_as_int(t) - 0x4B400000;
+  frac = __fsub_rn(q, __fsub_rn(t, 12582912.0f));
 }
 
 __device__ __forceinline__ int world_to_cell_fast(float xf, float yf, const CellGrid & cg, const double * __restrict__ geom)
 {
   const float qx = __fmul_rn(__fsub_rn(xf, cg.oxf), cg.invf);
   const float qy = __fmul_rn(__fsub_rn(yf, cg.oyf), cg.invf);
-  float rx, ry;
-  int ix, iy;
-  rint_magic(qx, rx, ix);
-  rint_magic(qy, ry, iy);
-  const float dx = __fsub_rn(qx, rx), dy = __fsub_rn(qy, ry);   // exact, in [-0.5, 0.5]
-  // near a cell edge, outside the magic-number range, or NaN: the reference's fp64 arithmetic decides
-  const bool sure = fabsf(dx) > cg.eps_x && fabsf(dy) > cg.eps_y && fabsf(qx) < 4.0e6f && fabsf(qy) < 4.0e6f;
+  int mx, my;
+  float fx, fy;
+  floor_magic(qx, mx, fx);
+  floor_magic(qy, my, fy);
+  // farther than the error bound from both edges of the cell on both axes?  (NaN and out-of-range fail the test or
+  // decode to an off-map index; either way the answer below is the reference's)
+  const bool sure = fabsf(__fsub_rn(fx, 0.5f)) < cg.half_minus_eps_x && fabsf(__fsub_rn(fy, 0.5f)) < cg.half_minus_eps_y;
   if (!sure) {return world_to_cell_slow(xf, yf, geom, cg.size_x, cg.size_y);}
-  const int mx = ix - (dx < 0.0f ? 1 : 0), my = iy - (dy < 0.0f ? 1 : 0);   // floor
   if (static_cast<unsigned>(mx) >= cg.size_x || static_cast<unsigned>(my) >= cg.size_y) {return -1;}
   return my * static_cast<int>(cg.size_x) + mx;
 }
@@ -340,6 +341,14 @@ __device__ __forceinline__ float add_pow(float total, float value, unsigned powe
 {
   if (power == 1u) {return __fadd_rn(total, value);}
   return static_cast<float>(static_cast<double>(total) + pow(static_cast<double>(value), static_cast<double>(power)));
+}
+
+// sqrt for cost terms (1e-4 tolerance): one MUFU instead of the IEEE sequence
+__device__ __forceinline__ float sqrt_approx(float v)
+{
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
 }
 
 __device__ __forceinline__ float warp_min(float v)

@@ -141,15 +141,43 @@ __global__ void __launch_bounds__(256) noise_philox_kernel(
   }
 }
 
+// Compile-time feature sets of the K2 kernels.  An EXACT instance (kExact) is straight-line code for one set of active
+// features (no per-cycle flag tests, no dead critic code: smaller, fewer registers, fewer instruction-cache misses);
+// the generic instance (SF_ALL, !kExact) tests the per-cycle flags of the record at run time.  The host picks the exact
+// instance when the cycle's record asks for precisely that set (launch_rollout), else the generic one.
+enum StreamFeature : unsigned
+{
+  SF_HOL = 1u,          // holonomic (Omni): vy terms
+  SF_ACKER = 2u,        // Ackermann term of the Constraint critic
+  SF_CON = 4u,          // ConstraintCritic
+  SF_FWD = 8u,          // PreferForwardCritic
+  SF_TWIRL = 16u,       // TwirlingCritic
+  SF_DB = 32u,          // VelocityDeadbandCritic
+  SF_GOAL = 64u,        // GoalCritic
+  SF_GANG = 128u,       // GoalAngleCritic
+  SF_COST = 256u,       // CostCritic
+  SF_OBST = 512u,       // ObstaclesCritic
+  SF_FOOTPRINT = 1024u, // footprint-cost mode of either costmap critic
+  SF_SPILL = 2048u,     // trajectories / cell indices written out
+  SF_ALL = 4095u
+};
+#define MPPI_SF(bit, flag) (((F & (bit)) != 0) && (kExact || (flag)))
+
 // ---------------------------------------------------------------------------------------------------
 // K2
 // ---------------------------------------------------------------------------------------------------
 #ifndef MPPI_K2_MIN_BLOCKS
 #define MPPI_K2_MIN_BLOCKS 3
 #endif
+#ifndef MPPI_TILE_CHUNK
+#define MPPI_TILE_CHUNK 1
+#endif
+constexpr int kTileChunk = MPPI_TILE_CHUNK;   // steps whose independent work is issued together inside a segment
+template<unsigned F, bool kExact, int kMode>
 __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
-  const DevParams * __restrict__ P, const uint8_t * __restrict__ cm, DevBuffers bufs, const int B, const int T, const int mode)
+  const DevParams * __restrict__ P, const uint8_t * __restrict__ cm, DevBuffers bufs, const int B, const int T)
 {
+  constexpr int mode = kMode;   // 0 rollout from noise, 1 injected state (integrate), 2 injected state + trajectories
   // B, T and mode also live in the record, but as launch arguments they cost no memory round trip: the noise rows,
   // the control sequence and the record are all requested at once when the kernel starts
   extern __shared__ float smem[];
@@ -212,7 +240,13 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
   load_hot_params(s_hot, P, tid, nthreads);
   __syncthreads();
   MPPI_TRACE_AT(2);
-  const int hol = p.holonomic;
+  const bool hol = MPPI_SF(SF_HOL, p.holonomic != 0);
+  const bool acker = MPPI_SF(SF_ACKER, p.model == MPPI_MODEL_ACKERMANN);
+  const bool con_on = MPPI_SF(SF_CON, p.constraint.on), fwd_on = MPPI_SF(SF_FWD, p.forward.on);
+  const bool twirl_on = MPPI_SF(SF_TWIRL, p.twirl.on), db_on = MPPI_SF(SF_DB, p.deadband.on);
+  const bool goal_on = MPPI_SF(SF_GOAL, p.goal.on), gang_on = MPPI_SF(SF_GANG, p.goal_angle.on);
+  const bool cost_on = MPPI_SF(SF_COST, p.cost.on), ob_on = MPPI_SF(SF_OBST, p.obst.on);
+  constexpr bool kFp = (F & SF_FOOTPRINT) != 0, kSpill = (F & SF_SPILL) != 0;
   const float dt = p.dt;
   if (mode == 0) {
     // setNoisedControls: c = control_sequence + noise (noise_generator.cpp:71-73), in place on this warp's rows
@@ -294,55 +328,71 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
 #pragma unroll
   for (int k = 0; k < A_COUNT; ++k) {acc[k] = 0.0f;}
   if (live) {
-    const bool con_on = p.constraint.on, fwd_on = p.forward.on, twirl_on = p.twirl.on, db_on = p.deadband.on;
-    const bool acker = p.model == MPPI_MODEL_ACKERMANN;
     const float max_vel = p.max_vel, min_vel = p.min_vel, min_r = p.min_turning_r;
     const float db_vx = fabsf(p.db_vx), db_vy = fabsf(p.db_vy), db_wz = fabsf(p.db_wz);
     float g_vx = 0.0f, g_vy = 0.0f, g_wz = 0.0f, a_con = 0.0f, a_fwd = 0.0f, a_twirl = 0.0f, a_db = 0.0f;
-    int o = t0 * kPad + lane;
-    for (int t = t0; t < t1; ++t, o += kPad) {
-      const float cx = s_cvx[o], cy = s_cvy[o], cw = s_cwz[o];   // controls of step t (state velocities of t+1)
-      const float vx = pvx, vy = pvy, wz = pwz;                   // state velocities of step t
-      if (mode == 0) {
-        // gamma term of updateControlSequence (optimizer.cpp:365-380): sum_t cs[t] * (c[b,t] - cs[t])
-        const float csx = s_cs[t], csy = s_cs[T + t], csw = s_cs[2 * T + t];
-        g_vx = __fadd_rn(g_vx, __fmul_rn(csx, __fsub_rn(cx, csx)));
-        g_wz = __fadd_rn(g_wz, __fmul_rn(csw, __fsub_rn(cw, csw)));
-        if (hol) {g_vy = __fadd_rn(g_vy, __fmul_rn(csy, __fsub_rn(cy, csy)));}
-      }
-      if (con_on) {   // constraint_critic.cpp:49-52
-        const float sgn = vx > 0.0f ? 1.0f : -1.0f;
-        const float vel_total = sgn * sqrtf(vx * vx + vy * vy);
-        float e = fmaxf(vel_total - max_vel, 0.0f) + fmaxf(min_vel - vel_total, 0.0f);
-        if (acker) {e += fmaxf(min_r - fabsf(vx) / fabsf(wz), 0.0f);}
-        a_con += e * dt;
-      }
-      if (fwd_on) {a_fwd += fmaxf(-vx, 0.0f) * dt;}           // prefer_forward_critic.cpp:42-46
-      if (twirl_on) {a_twirl += fabsf(wz);}                   // twirling_critic.cpp:40-41
-      if (db_on) {                                            // velocity_deadband_critic.cpp:54-97
-        float e = fmaxf(db_vx - fabsf(vx), 0.0f);
-        if (hol) {e += fmaxf(db_vy - fabsf(vy), 0.0f);}
-        e += fmaxf(db_wz - fabsf(wz), 0.0f);
-        a_db += e * dt;
+    // steps of the segment in chunks of kTileChunk: the sincos chains of a chunk are independent and overlap (ILP)
+    constexpr int kC = kTileChunk;
+    for (int tc = t0; tc < t1; tc += kC) {
+      float cx[kC], cy[kC], cw[kC], sn[kC], cn[kC];
+#pragma unroll
+      for (int u = 0; u < kC; ++u) {
+        const int o = min(tc + u, t1 - 1) * kPad + lane;
+        cx[u] = s_cvx[o]; cy[u] = s_cvy[o]; cw[u] = s_cwz[o];   // controls of step t (state velocities of t+1)
       }
       if (mode != 2) {
         // integrateStateVelocities (optimizer.cpp:322-337): cos/sin of yaw[t-1]
-        float sn, cn;
-        if (t == 0) {
-          sn = p.sin0; cn = p.cos0;
-        } else {
-          mppi_det_sincosf(s_yaw[o - kPad], &sn, &cn);
+#pragma unroll
+        for (int u = 0; u < kC; ++u) {
+          const int t = min(tc + u, t1 - 1);
+          if (t == 0) {
+            sn[u] = p.sin0; cn[u] = p.cos0;
+          } else {
+            mppi_det_sincosf(s_yaw[(t - 1) * kPad + lane], &sn[u], &cn[u]);
+          }
         }
-        float dx = __fmul_rn(vx, cn);
-        float dy = __fmul_rn(vx, sn);
-        if (hol) {
-          dx = __fsub_rn(dx, __fmul_rn(vy, sn));
-          dy = __fadd_rn(dy, __fmul_rn(vy, cn));
-        }
-        s_x[o] = __fmul_rn(dx, dt);    // in place over the control planes: (cx, cy) already live in registers
-        s_y[o] = __fmul_rn(dy, dt);
       }
-      pvx = cx; pvy = use_vy ? cy : 0.0f; pwz = cw;
+#pragma unroll
+      for (int u = 0; u < kC; ++u) {
+        const int t = tc + u;
+        if (t < t1) {
+          const int o = t * kPad + lane;
+          const float vx = pvx, vy = pvy, wz = pwz;                   // state velocities of step t
+          if (mode == 0) {
+            // gamma term of updateControlSequence (optimizer.cpp:365-380): sum_t cs[t] * (c[b,t] - cs[t])
+            const float csx = s_cs[t], csy = s_cs[T + t], csw = s_cs[2 * T + t];
+            g_vx = fmaf(csx, __fsub_rn(cx[u], csx), g_vx);
+            g_wz = fmaf(csw, __fsub_rn(cw[u], csw), g_wz);
+            if (hol) {g_vy = fmaf(csy, __fsub_rn(cy[u], csy), g_vy);}
+          }
+          if (con_on) {   // constraint_critic.cpp:49-52
+            const float sgn = vx > 0.0f ? 1.0f : -1.0f;
+            const float vel_total = sgn * sqrt_approx(vx * vx + vy * vy);
+            float e = fmaxf(vel_total - max_vel, 0.0f) + fmaxf(min_vel - vel_total, 0.0f);
+            if (acker) {e += fmaxf(min_r - fabsf(vx) / fabsf(wz), 0.0f);}
+            a_con += e * dt;
+          }
+          if (fwd_on) {a_fwd += fmaxf(-vx, 0.0f) * dt;}           // prefer_forward_critic.cpp:42-46
+          if (twirl_on) {a_twirl += fabsf(wz);}                   // twirling_critic.cpp:40-41
+          if (db_on) {                                            // velocity_deadband_critic.cpp:54-97
+            float e = fmaxf(db_vx - fabsf(vx), 0.0f);
+            if (hol) {e += fmaxf(db_vy - fabsf(vy), 0.0f);}
+            e += fmaxf(db_wz - fabsf(wz), 0.0f);
+            a_db += e * dt;
+          }
+          if (mode != 2) {
+            float dx = __fmul_rn(vx, cn[u]);
+            float dy = __fmul_rn(vx, sn[u]);
+            if (hol) {
+              dx = __fsub_rn(dx, __fmul_rn(vy, sn[u]));
+              dy = __fadd_rn(dy, __fmul_rn(vy, cn[u]));
+            }
+            s_x[o] = __fmul_rn(dx, dt);    // in place over the control planes: (cx, cy) already live in registers
+            s_y[o] = __fmul_rn(dy, dt);
+          }
+          pvx = cx[u]; pvy = use_vy ? cy[u] : 0.0f; pwz = cw[u];
+        }
+      }
     }
     acc[A_GVX] = g_vx; acc[A_GVY] = g_vy; acc[A_GWZ] = g_wz;
     acc[A_CON] = a_con; acc[A_FWD] = a_fwd; acc[A_TWIRL] = a_twirl; acc[A_DB] = a_db;
@@ -383,16 +433,15 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
   MPPI_TRACE_AT(6);
   // ---- P5: position critics + spills, parallel over (trajectory, segment of the horizon)
   if (live) {
-    const bool goal_on = p.goal.on, gang_on = p.goal_angle.on, cost_on = p.cost.on, ob_on = p.obst.on;
-    const bool want_cells = p.want_cells != 0, spill = p.spill_traj != 0;
+    const bool want_cells = kSpill && p.want_cells != 0, spill = kSpill && p.spill_traj != 0;
     const bool need_cell = cost_on || ob_on || want_cells;
     const bool track_unknown = p.track_unknown != 0;
-    const bool cost_fp = p.cost_fp != 0, ob_fp = p.obst_fp != 0;
+    const bool cost_fp = kFp && p.cost_fp != 0, ob_fp = kFp && p.obst_fp != 0;
     const bool cost_near_goal = p.cost_near_goal != 0, ob_near_goal = p.obst_near_goal != 0, ob_rep_on = p.obst_repulsion_enabled != 0;
     const float cost_pic = p.cost_possibly_inscribed, ob_pic = p.obst_possibly_inscribed, cost_critical = p.cost_critical;
     const double gx = p.goal_x, gy = p.goal_y, ox = p.ox, oy = p.oy, res = p.res;
     const unsigned size_x = p.size_x, size_y = p.size_y;
-    const CellGrid cg = {p.cell_oxf, p.cell_oyf, p.cell_invf, p.cell_eps_x, p.cell_eps_y, size_x, size_y};
+    const CellGrid cg = {p.cell_oxf, p.cell_oyf, p.cell_invf, 0.5f - p.cell_eps_x, 0.5f - p.cell_eps_y, size_x, size_y};
     const float goal_yaw = p.goal_yaw;
     const int step = p.sample_step;
     int next_sample = T, sample_k = 0;
@@ -400,67 +449,89 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
     const bool sample_yaw = p.sample_yaw != 0;
     bool cost_hit = false, ob_hit = false;
     float a_goal = 0.0f, a_gang = 0.0f, cost_rep = 0.0f, ob_traj = 0.0f, ob_rep = 0.0f;
-    int o = t0 * kPad + lane;
     size_t g = static_cast<size_t>(t0) * B + b;
-    for (int t = t0; t < t1; ++t, o += kPad, g += B) {
-      const float px = s_x[o], py = s_y[o];
-      if (goal_on) {                                               // goal_critic.cpp:50-52
-        const float dx = static_cast<float>(static_cast<double>(px) - gx);
-        const float dy = static_cast<float>(static_cast<double>(py) - gy);
-        a_goal += sqrtf(dx * dx + dy * dy);
-      }
-      if (gang_on) {                                               // goal_angle_critic.cpp:47-49
-        a_gang += static_cast<float>(fabs(normalize_angle_d(static_cast<double>(__fsub_rn(goal_yaw, s_yaw[o])))));
+    // steps of the segment in chunks of kTileChunk: the cell indices are computed and their costmap bytes requested
+    // together (one memory round trip per chunk instead of one per step); the collision logic stays in step order
+    constexpr int kC = kTileChunk;
+    for (int tc = t0; tc < t1; tc += kC) {
+      float pxs[kC], pys[kC];
+      int cells[kC], pcs[kC];
+#pragma unroll
+      for (int u = 0; u < kC; ++u) {
+        const int oo = min(tc + u, t1 - 1) * kPad + lane;
+        pxs[u] = s_x[oo]; pys[u] = s_y[oo];
       }
       if (need_cell) {
-        const int cell = world_to_cell_fast(px, py, cg, &p.res);
-        if (want_cells) {bufs.spill_cells[g] = cell;}
-        if ((cost_on && !cost_hit) || (ob_on && !ob_hit)) {
-          const int pose_cost = cell < 0 ? NO_INFORMATION : __ldg(cm + cell);
-          int fp_cost = -1;
-          if (cost_on && !cost_hit && pose_cost >= 1) {            // cost_critic.cpp:139-162
-            int c = pose_cost;
-            if (cost_fp && (static_cast<float>(c) >= cost_pic || cost_pic < 1.0f)) {
-              fp_cost = footprint_cost_at_pose(P, p.fp_n, ox, oy, res, size_x, size_y, cm, px, py, s_yaw[o]);
-              c = fp_cost;
+#pragma unroll
+        for (int u = 0; u < kC; ++u) {cells[u] = world_to_cell_fast(pxs[u], pys[u], cg, &p.res);}
+#pragma unroll
+        for (int u = 0; u < kC; ++u) {pcs[u] = cells[u] < 0 ? NO_INFORMATION : __ldg(cm + cells[u]);}
+      }
+#pragma unroll
+      for (int u = 0; u < kC; ++u) {
+        const int t = tc + u;
+        if (t >= t1) {break;}
+        const int o = t * kPad + lane;
+        const float px = pxs[u], py = pys[u];
+        if (goal_on) {                                               // goal_critic.cpp:50-52
+          const float dx = static_cast<float>(static_cast<double>(px) - gx);
+          const float dy = static_cast<float>(static_cast<double>(py) - gy);
+          a_goal += sqrt_approx(dx * dx + dy * dy);
+        }
+        if (gang_on) {                                               // goal_angle_critic.cpp:47-49
+          a_gang += static_cast<float>(fabs(normalize_angle_d(static_cast<double>(__fsub_rn(goal_yaw, s_yaw[o])))));
+        }
+        if (need_cell) {
+          const int cell = cells[u];
+          if (want_cells) {bufs.spill_cells[g] = cell;}
+          if ((cost_on && !cost_hit) || (ob_on && !ob_hit)) {
+            const int pose_cost = pcs[u];
+            int fp_cost = -1;
+            if (cost_on && !cost_hit && pose_cost >= 1) {            // cost_critic.cpp:139-162
+              int c = pose_cost;
+              if (cost_fp && (static_cast<float>(c) >= cost_pic || cost_pic < 1.0f)) {
+                fp_cost = footprint_cost_at_pose(P, p.fp_n, ox, oy, res, size_x, size_y, cm, px, py, s_yaw[o]);
+                c = fp_cost;
+              }
+              if (in_collision(c, cost_fp, track_unknown)) {
+                cost_hit = true;
+              } else if (pose_cost >= INSCRIBED_INFLATED_OBSTACLE) {
+                cost_rep += cost_critical;
+              } else if (!cost_near_goal) {
+                cost_rep += static_cast<float>(pose_cost);
+              }
             }
-            if (in_collision(c, cost_fp, track_unknown)) {
-              cost_hit = true;
-            } else if (pose_cost >= INSCRIBED_INFLATED_OBSTACLE) {
-              cost_rep += cost_critical;
-            } else if (!cost_near_goal) {
-              cost_rep += static_cast<float>(pose_cost);
-            }
-          }
-          if (ob_on && !ob_hit) {                                  // obstacles_critic.cpp:145-170, :203-224
-            int c = pose_cost;
-            int using_fp = 0;
-            if (cell >= 0 && ob_fp && (static_cast<float>(c) >= ob_pic || ob_pic < 1.0f)) {
-              if (fp_cost < 0) {fp_cost = footprint_cost_at_pose(P, p.fp_n, ox, oy, res, size_x, size_y, cm, px, py, s_yaw[o]);}
-              c = fp_cost;
-              using_fp = 1;
-            }
-            if (c >= 1) {
-              if (in_collision(c, ob_fp, track_unknown)) {
-                ob_hit = true;
-              } else if (ob_rep_on) {
-                ob_traj += __ldg(&P->obst_lut_crit[using_fp][c]);
-                if (!ob_near_goal) {ob_rep += __ldg(&P->obst_lut_rep[using_fp][c]);}
+            if (ob_on && !ob_hit) {                                  // obstacles_critic.cpp:145-170, :203-224
+              int c = pose_cost;
+              int using_fp = 0;
+              if (cell >= 0 && ob_fp && (static_cast<float>(c) >= ob_pic || ob_pic < 1.0f)) {
+                if (fp_cost < 0) {fp_cost = footprint_cost_at_pose(P, p.fp_n, ox, oy, res, size_x, size_y, cm, px, py, s_yaw[o]);}
+                c = fp_cost;
+                using_fp = 1;
+              }
+              if (c >= 1) {
+                if (in_collision(c, ob_fp, track_unknown)) {
+                  ob_hit = true;
+                } else if (ob_rep_on) {
+                  ob_traj += __ldg(&P->obst_lut_crit[using_fp][c]);
+                  if (!ob_near_goal) {ob_rep += __ldg(&P->obst_lut_rep[using_fp][c]);}
+                }
               }
             }
           }
         }
-      }
-      // spills for the path critics of K3
-      if (t == next_sample) {
-        const size_t k = static_cast<size_t>(sample_k) * B + b;
-        bufs.samples_x[k] = px;
-        bufs.samples_y[k] = py;
-        if (sample_yaw) {bufs.samples_yaw[k] = s_yaw[o];}
-        next_sample += step; sample_k++;
-      }
-      if (spill) {
-        bufs.spill_x[g] = px; bufs.spill_y[g] = py; bufs.spill_yaw[g] = s_yaw[o];
+        // spills for the path critics of K3
+        if (t == next_sample) {
+          const size_t k = static_cast<size_t>(sample_k) * B + b;
+          bufs.samples_x[k] = px;
+          bufs.samples_y[k] = py;
+          if (sample_yaw) {bufs.samples_yaw[k] = s_yaw[o];}
+          next_sample += step; sample_k++;
+        }
+        if (spill) {
+          bufs.spill_x[g] = px; bufs.spill_y[g] = py; bufs.spill_yaw[g] = s_yaw[o];
+        }
+        g += B;
       }
     }
     if (t1 == T && t0 < t1) {
@@ -522,17 +593,17 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
     const float Tf = static_cast<float>(T);
     float * rows = bufs.crit_rows;
     if (live) {
-      if (p.constraint.on) {rows[static_cast<size_t>(p.constraint.idx) * B + b] = add_pow(0.0f, tot[A_CON] * p.constraint.weight, p.constraint.power);}
-      if (p.forward.on) {rows[static_cast<size_t>(p.forward.idx) * B + b] = add_pow(0.0f, tot[A_FWD] * p.forward.weight, p.forward.power);}
-      if (p.twirl.on) {rows[static_cast<size_t>(p.twirl.idx) * B + b] = add_pow(0.0f, (tot[A_TWIRL] / Tf) * p.twirl.weight, p.twirl.power);}
-      if (p.deadband.on) {rows[static_cast<size_t>(p.deadband.idx) * B + b] = add_pow(0.0f, tot[A_DB] * p.deadband.weight, p.deadband.power);}
-      if (p.goal.on) {rows[static_cast<size_t>(p.goal.idx) * B + b] = add_pow(0.0f, (tot[A_GOAL] / Tf) * p.goal.weight, p.goal.power);}
-      if (p.goal_angle.on) {rows[static_cast<size_t>(p.goal_angle.idx) * B + b] = add_pow(0.0f, (tot[A_GANG] / Tf) * p.goal_angle.weight, p.goal_angle.power);}
-      if (p.cost.on) {   // cost_critic.cpp:159-166
+      if (con_on) {rows[static_cast<size_t>(p.constraint.idx) * B + b] = add_pow(0.0f, tot[A_CON] * p.constraint.weight, p.constraint.power);}
+      if (fwd_on) {rows[static_cast<size_t>(p.forward.idx) * B + b] = add_pow(0.0f, tot[A_FWD] * p.forward.weight, p.forward.power);}
+      if (twirl_on) {rows[static_cast<size_t>(p.twirl.idx) * B + b] = add_pow(0.0f, (tot[A_TWIRL] / Tf) * p.twirl.weight, p.twirl.power);}
+      if (db_on) {rows[static_cast<size_t>(p.deadband.idx) * B + b] = add_pow(0.0f, tot[A_DB] * p.deadband.weight, p.deadband.power);}
+      if (goal_on) {rows[static_cast<size_t>(p.goal.idx) * B + b] = add_pow(0.0f, (tot[A_GOAL] / Tf) * p.goal.weight, p.goal.power);}
+      if (gang_on) {rows[static_cast<size_t>(p.goal_angle.idx) * B + b] = add_pow(0.0f, (tot[A_GANG] / Tf) * p.goal_angle.weight, p.goal_angle.power);}
+      if (cost_on) {   // cost_critic.cpp:159-166
         const float rep = cost_collided ? p.cost_collision : tot[A_COST_REP];
         rows[static_cast<size_t>(p.cost.idx) * B + b] = add_pow(0.0f, p.cost.weight * rep / Tf, p.cost.power);
       }
-      if (p.obst.on) {   // obstacles_critic.cpp:169-176
+      if (ob_on) {   // obstacles_critic.cpp:169-176
         const float raw = ob_collided ? p.obst_collision : tot[A_OB_TRAJ];
         const float v = (p.obst_critical_w * raw) + (p.obst_repulsion_w * tot[A_OB_REP] / Tf);
         rows[static_cast<size_t>(p.obst.idx) * B + b] = add_pow(0.0f, v, p.obst.power);
@@ -543,11 +614,11 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
       }
     }
     // fail_flag inputs: did any trajectory of this tile survive?
-    if (p.cost.on) {
+    if (cost_on) {
       const unsigned ok = __ballot_sync(0xffffffffu, live && !cost_collided);
       if (lane == 0 && ok) {atomicOr(&bufs.st->any_ok[p.cost.idx], 1u);}
     }
-    if (p.obst.on) {
+    if (ob_on) {
       const unsigned ok = __ballot_sync(0xffffffffu, live && !ob_collided);
       if (lane == 0 && ok) {atomicOr(&bufs.st->any_ok[p.obst.idx], 1u);}
     }
@@ -577,22 +648,6 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
 // The template mask removes whole critic families at compile time (smaller code, fewer registers); every
 // family that is compiled in is still gated by its per-cycle runtime flag.
 // ---------------------------------------------------------------------------------------------------
-enum StreamFeature : unsigned
-{
-  SF_HOL = 1u,          // holonomic (Omni): vy terms
-  SF_ACKER = 2u,        // Ackermann term of the Constraint critic
-  SF_CON = 4u,          // ConstraintCritic
-  SF_FWD = 8u,          // PreferForwardCritic
-  SF_TWIRL = 16u,       // TwirlingCritic
-  SF_DB = 32u,          // VelocityDeadbandCritic
-  SF_GOAL = 64u,        // GoalCritic
-  SF_GANG = 128u,       // GoalAngleCritic
-  SF_COST = 256u,       // CostCritic
-  SF_OBST = 512u,       // ObstaclesCritic
-  SF_FOOTPRINT = 1024u, // footprint-cost mode of either costmap critic
-  SF_SPILL = 2048u,     // trajectories / cell indices written out
-  SF_ALL = 4095u
-};
 
 constexpr int kStreamThreads = 128;    // upper bound of the block size (the host may launch fewer threads per block)
 #ifndef MPPI_STREAM_CHUNK
@@ -604,14 +659,6 @@ static_assert(kStreamChunk <= kNoisePadRows, "prefetch reads up to kStreamChunk 
 #ifndef MPPI_STREAM_MIN_BLOCKS
 #define MPPI_STREAM_MIN_BLOCKS 4
 #endif
-
-// sqrt for cost terms (1e-4 tolerance): one MUFU instead of the IEEE sequence
-__device__ __forceinline__ float sqrt_approx(float v)
-{
-  float r;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-  return r;
-}
 
 // kExact: the mask IS the set of active features (no runtime flag tests inside the loop); otherwise the mask is an
 // upper bound and every feature is still gated by its per-cycle runtime flag (generic instance).
@@ -643,7 +690,6 @@ __global__ void __launch_bounds__(kStreamThreads, MPPI_STREAM_MIN_BLOCKS) rollou
   const float * __restrict__ nvy = bufs.in_b;
   const float * __restrict__ nwz = bufs.in_c;
 
-#define MPPI_SF(bit, flag) (((F & (bit)) != 0) && (kExact || (flag)))
   const bool hol = MPPI_SF(SF_HOL, p.holonomic != 0);
   const bool acker = MPPI_SF(SF_ACKER, p.model == MPPI_MODEL_ACKERMANN);
   const bool con_on = MPPI_SF(SF_CON, p.constraint.on), fwd_on = MPPI_SF(SF_FWD, p.forward.on);
@@ -653,7 +699,6 @@ __global__ void __launch_bounds__(kStreamThreads, MPPI_STREAM_MIN_BLOCKS) rollou
   constexpr bool kFp = (F & SF_FOOTPRINT) != 0, kSpill = (F & SF_SPILL) != 0;
   const bool cost_fp = kFp && p.cost_fp != 0, ob_fp = kFp && p.obst_fp != 0;
   const bool want_cells = kSpill && p.want_cells != 0, spill = kSpill && p.spill_traj != 0;
-#undef MPPI_SF
   const bool need_cell = cost_on || ob_on || want_cells;
   const bool track_unknown = p.track_unknown != 0;
   const bool cost_near_goal = p.cost_near_goal != 0, ob_near_goal = p.obst_near_goal != 0, ob_rep_on = p.obst_repulsion_enabled != 0;
@@ -661,7 +706,7 @@ __global__ void __launch_bounds__(kStreamThreads, MPPI_STREAM_MIN_BLOCKS) rollou
   const float max_vel = p.max_vel, min_vel = p.min_vel, min_r = p.min_turning_r;
   const float db_vx = fabsf(p.db_vx), db_vy = fabsf(p.db_vy), db_wz = fabsf(p.db_wz);
   const double x0 = p.pose_x, y0 = p.pose_y;
-  const CellGrid cg = {p.cell_oxf, p.cell_oyf, p.cell_invf, p.cell_eps_x, p.cell_eps_y, p.size_x, p.size_y};
+  const CellGrid cg = {p.cell_oxf, p.cell_oyf, p.cell_invf, 0.5f - p.cell_eps_x, 0.5f - p.cell_eps_y, p.size_x, p.size_y};
   const float yaw0 = p.yaw0, goal_yaw = p.goal_yaw;
   const int step = p.sample_step;
   const bool sample_yaw = p.sample_yaw != 0;
@@ -756,11 +801,11 @@ __global__ void __launch_bounds__(kStreamThreads, MPPI_STREAM_MIN_BLOCKS) rollou
           const float yaw = yw[u];
           // gamma term (optimizer.cpp:365-380)
           const float csx = cs_t[u], csw = cs_t[2 * Tp + u];
-          g_vx = __fadd_rn(g_vx, __fmul_rn(csx, __fsub_rn(cx[u], csx)));
-          g_wz = __fadd_rn(g_wz, __fmul_rn(csw, __fsub_rn(cw[u], csw)));
+          g_vx = fmaf(csx, __fsub_rn(cx[u], csx), g_vx);
+          g_wz = fmaf(csw, __fsub_rn(cw[u], csw), g_wz);
           if (hol) {
             const float csy = cs_t[Tp + u];
-            g_vy = __fadd_rn(g_vy, __fmul_rn(csy, __fsub_rn(cy[u], csy)));
+            g_vy = fmaf(csy, __fsub_rn(cy[u], csy), g_vy);
           }
           if (con_on) {   // constraint_critic.cpp:49-52
             const float sgn = svx > 0.0f ? 1.0f : -1.0f;
@@ -905,14 +950,16 @@ constexpr int kUpdThreads = 128;
 constexpr int kMergeT = 4;               // time steps owned by one block of merge_finalize_kernel
 constexpr int kLastBlockMergeMax = 64;   // K3's last block merges up to this many partials itself
 
-// utils::findClosestPathPt (utils.hpp:665-675) on the prefix D[0..n); out-of-range clamps to n-1
-__device__ __forceinline__ int find_closest_path_pt(const float * D, int n, float dist, int init)
+// utils::findClosestPathPt (utils.hpp:665-675) on the prefix D[0..n); out-of-range clamps to n-1.
+// PathAlign calls this with non-decreasing distances, so std::lower_bound over the WHOLE prefix (`cursor`, kept by the
+// caller across calls) only ever moves forward: a scan that advances a few entries per call, O(n + calls) per
+// trajectory in total.  lower_bound over [init, n) -- what the reference evaluates -- is max(cursor, init).
+__device__ __forceinline__ int find_closest_path_pt(const float * D, int n, float dist, int init, int & cursor)
 {
-  int lo = init, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (D[mid] < dist) {lo = mid + 1;} else {hi = mid;}
-  }
+  int c = cursor;
+  while (c < n && D[c] < dist) {++c;}
+  cursor = c;
+  const int lo = max(c, init);
   if (lo == init) {return 0;}
   if (lo == n) {return n - 1;}
   if (__fsub_rn(dist, D[lo - 1]) < __fsub_rn(D[lo], dist)) {return lo - 1;}
@@ -1162,7 +1209,7 @@ __device__ __forceinline__ float k3_trajectory_total(
           const int step = P->align_step;
           const int n_s = (T + step - 1) / step;     // sampled poses p = 0, step, 2 step, ... < T
           float traj_d = 0.0f, summed = 0.0f, num = 0.0f;
-          int path_pt = 0;
+          int path_pt = 0, cursor = 0;
           float prev_x = bufs.samples_x[b], prev_y = bufs.samples_y[b];
           constexpr int kBatch = 8;                  // sampled poses requested together (latency off the serial chain)
           for (int k0 = 1; k0 < n_s; k0 += kBatch) {
@@ -1180,16 +1227,17 @@ __device__ __forceinline__ float k3_trajectory_total(
                 const float Tx = sx[u], Ty = sy[u];
                 float dx = __fsub_rn(Tx, prev_x), dy = __fsub_rn(Ty, prev_y);
                 traj_d = __fadd_rn(traj_d, __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
-                path_pt = find_closest_path_pt(s_D, furthest, traj_d, path_pt);
+                path_pt = find_closest_path_pt(s_D, furthest, traj_d, path_pt, cursor);
                 if (s_valid[path_pt]) {
                   dx = __fsub_rn(path.s_x[path_pt], Tx);
                   dy = __fsub_rn(path.s_y[path_pt], Ty);
                   num = __fadd_rn(num, 1.0f);
+                  // the distance itself only feeds the cost (1e-4 tolerance): one MUFU instead of the IEEE sequence
                   if (P->align_use_yaw) {
                     const float dyaw = static_cast<float>(normalize_angle_d(static_cast<double>(syaw[u]) - static_cast<double>(__ldg(path_yaw + path_pt))));
-                    summed = __fadd_rn(summed, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dyaw, dyaw))));
+                    summed += sqrt_approx(dx * dx + dy * dy + dyaw * dyaw);
                   } else {
-                    summed = __fadd_rn(summed, __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
+                    summed += sqrt_approx(dx * dx + dy * dy);
                   }
                 }
                 prev_x = Tx; prev_y = Ty;
