@@ -706,8 +706,13 @@ mppi_status launch_update(mppi_handle * h, int mode, int iteration)
   if (mode == 0 && h->stream_layout) {
     // stream layout: totals + global minimum here, weights and weighted sums in weighted_sums_tm_kernel
     const int grid = std::min((h->B + kUpdThreads - 1) / kUpdThreads, 148 * 8);
-    path_costs_tm_kernel<<<grid, kUpdThreads, k3_common_smem_bytes(), h->stream>>>(
-      reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, mode), iteration);
+    if (h->B >= 131072) {
+      path_costs_tm_kernel<8><<<grid, kUpdThreads, k3_common_smem_bytes(), h->stream>>>(
+        reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, mode), iteration);
+    } else {
+      path_costs_tm_kernel<5><<<grid, kUpdThreads, k3_common_smem_bytes(), h->stream>>>(
+        reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, mode), iteration);
+    }
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
     return MPPI_OK;

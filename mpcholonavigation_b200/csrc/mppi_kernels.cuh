@@ -308,16 +308,20 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
 
   // ---- P2: yaw = cumsum(wz * dt) + yaw0, sequential in t (optimizer.cpp:319-320)
   if (mode != 2 && seg == 0 && live) {
+    // chunks of 8: the eight loads are independent (pipelined), only the eight adds form the carried chain
     const float yaw0 = p.yaw0;
-    float acc = 0.0f;
+    float acc = -0.0f;                       // (-0) + x == x bit for bit: the first element of the cumsum is the term itself
     float wz = s_v0[2 * kTile + lane];
-    int o = lane;
-#pragma unroll 4
-    for (int t = 0; t < T; ++t, o += kPad) {
-      const float term = __fmul_rn(wz, dt);
-      acc = t == 0 ? term : __fadd_rn(acc, term);
-      wz = s_cwz[o];
-      s_yaw[o] = __fadd_rn(acc, yaw0);
+    for (int tc = 0; tc < T; tc += 8) {
+      float w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {w[u] = s_cwz[min(tc + u, T - 1) * kPad + lane];}
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        acc = __fadd_rn(acc, __fmul_rn(wz, dt));
+        wz = w[u];
+        if (tc + u < T) {s_yaw[(tc + u) * kPad + lane] = __fadd_rn(acc, yaw0);}
+      }
     }
   }
   __syncthreads();
@@ -404,28 +408,22 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
     // ---- P4: x = pose.x (double) + cumsum(dx*dt) (float), sequential in t (optimizer.cpp:339-342)
     if (live && seg < 2) {
       const bool do_x = seg == 0, do_y = (S > 1) ? (seg == 1) : true;
-      if (do_x) {
-        const double x0 = p.pose_x;
-        float a = 0.0f;
-        int o = lane;
-#pragma unroll 4
-        for (int t = 0; t < T; ++t, o += kPad) {
-          const float v = s_x[o];
-          a = t == 0 ? v : __fadd_rn(a, v);
-          s_x[o] = static_cast<float>(x0 + static_cast<double>(a));
-        }
-      }
-      if (do_y) {
-        const double y0 = p.pose_y;
-        float a = 0.0f;
-        int o = lane;
-#pragma unroll 4
-        for (int t = 0; t < T; ++t, o += kPad) {
-          const float v = s_y[o];
-          a = t == 0 ? v : __fadd_rn(a, v);
-          s_y[o] = static_cast<float>(y0 + static_cast<double>(a));
-        }
-      }
+      // one plane per warp (x: warp 0, y: warp 1), chunks of 8 as above; the fp64 pose add is off the carried chain
+      auto scan_plane = [&](float * plane, const double origin) {
+          float a = -0.0f;
+          for (int tc = 0; tc < T; tc += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {v[u] = plane[min(tc + u, T - 1) * kPad + lane];}
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              a = __fadd_rn(a, v[u]);
+              if (tc + u < T) {plane[(tc + u) * kPad + lane] = static_cast<float>(origin + static_cast<double>(a));}
+            }
+          }
+        };
+      if (do_x) {scan_plane(s_x, p.pose_x);}
+      if (do_y) {scan_plane(s_y, p.pose_y);}
     }
   }
   __syncthreads();
@@ -1367,7 +1365,10 @@ __device__ __forceinline__ void k3_publish_flags(const DevParams * P, DevState *
 // K3, stream layout: path critics + totals for every trajectory (grid-stride: the preamble is paid once per block,
 // not once per 128 trajectories) and the global minimum of the costs; the weighted sums follow in
 // weighted_sums_tm_kernel.
-__global__ void __launch_bounds__(kUpdThreads) path_costs_tm_kernel(const DevParams * __restrict__ Pg, DevBuffers bufs, int iteration)
+// kMinBlocks trades registers for occupancy: 8 resident blocks (64 registers, a few spills) win once the batch keeps every
+// SM oversubscribed, 5 (96 registers) below that (measured on B200, profiles/).
+template<int kMinBlocks>
+__global__ void __launch_bounds__(kUpdThreads, kMinBlocks) path_costs_tm_kernel(const DevParams * __restrict__ Pg, DevBuffers bufs, int iteration)
 {
   extern __shared__ float smem[];
   __shared__ K3Decisions dec;

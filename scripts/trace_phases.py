@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mpcholonavigation_b200 import Engine, load_product, scenarios  # noqa: E402
 
 fns = load_product(sys.argv[1])
-sc = scenarios.config1()
+sc = scenarios.config1(batch=int(sys.argv[2])) if len(sys.argv) > 2 else scenarios.config1()
 e = Engine(fns, **sc.cfg)
 e.set_robot(sc.robot); e.set_critics(sc.critics); e.set_noise(*sc.noise())
 e.upload_cycle(sc.cycle)
@@ -26,6 +26,7 @@ for _ in range(20):
 a = np.median(np.stack(acc), axis=0)
 k2 = a[0:10] - a[0]
 k3 = a[16:23] - a[16]
+print("B =", e.B)
 print("K2 phase starts (cycles from kernel start, block 0):", " ".join("%d" % v for v in k2))
 print("K3 phase starts (cycles from kernel start, block 0):", " ".join("%d" % v for v in k3))
 print("K3 preamble: issue-done %d, barrier-1 %d, decisions-done %d" % tuple(a[24:27] - a[16]))
