@@ -126,6 +126,9 @@ struct mppi_handle
   unsigned * peer_box[kMaxRanks]{};       // mailboxes of all ranks as mapped here; [rank] == d_mailbox
   bool peer_mode{false};
   float * d_hist{nullptr};     // control_history_ [4][3] (vx, vy, wz), optimizer.hpp:251
+  unsigned long long * d_epoch{nullptr};   // regenerate_noises: Philox stream index of the next draw (device copy of noise_stream)
+  cudaEvent_t ev_result{nullptr};          // regenerate_noises: result is in host memory (the redraw may still be running)
+  bool capturing{false};
   bool use_graph{true};
   size_t costmap_bytes{0}, params_copy_bytes{0};
   // sharding
@@ -661,6 +664,8 @@ void launch_stream_instance(mppi_handle * h, int mode)
     reinterpret_cast<const DevParams *>(h->d_params), h->d_costmap, make_bufs(h, mode));
 }
 
+mppi_status launch_regenerate(mppi_handle * h);
+
 mppi_status launch_rollout(mppi_handle * h, int mode)
 {
   if (mode == 0 && h->stream_layout) {
@@ -777,6 +782,9 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
         h->launches++;
       }
     }
+    if (h->cfg.regenerate_noises && it + 1 < h->cfg.iteration_count) {
+      if ((s = launch_regenerate(h)) != MPPI_OK) {return s;}
+    }
   }
   if (h->tail_mode) {
     // evalControl's tail (Savitzky-Golay filter, command extraction, shift) stays on the device
@@ -786,6 +794,15 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
   }
   if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[3], h->stream));}
   CUDA_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(float) * (3 * h->T + 6), cudaMemcpyDeviceToHost, h->stream));
+  if (h->cfg.regenerate_noises) {
+    // the result is complete here; the redraw for the next cycle runs behind it, off the caller's critical path
+    if (h->capturing) {
+      CUDA_TRY(h, cudaEventRecordWithFlags(h->ev_result, h->stream, cudaEventRecordExternal));
+    } else {
+      CUDA_TRY(h, cudaEventRecord(h->ev_result, h->stream));
+    }
+    return launch_regenerate(h);
+  }
   return MPPI_OK;
 }
 
@@ -811,9 +828,11 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
       cudaGraph_t graph = nullptr;
       const uint64_t launches_before = h->launches;
       CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      h->capturing = true;
       mppi_status s = MPPI_OK;
       if (with_upload) {s = enqueue_uploads(h);}
       if (s == MPPI_OK) {s = enqueue_kernels(h, false);}
+      h->capturing = false;
       const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
       h->launches = launches_before;   // capture launched nothing
       if (s != MPPI_OK || ce != cudaSuccess || !graph) {
@@ -847,7 +866,12 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
 
 mppi_status finish_optimize(mppi_handle * h, mppi_cycle_out * out)
 {
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->cfg.regenerate_noises) {
+    h->noise_stream += static_cast<uint64_t>(h->cfg.iteration_count);   // host mirror of d_epoch
+    CUDA_TRY(h, cudaEventSynchronize(h->ev_result));
+  } else {
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  }
   const int T = h->T;
   h->spilled_traj = h->last.spill_traj != 0;
   h->spilled_cells = h->last.want_cells != 0;
@@ -863,10 +887,10 @@ mppi_status finish_optimize(mppi_handle * h, mppi_cycle_out * out)
     out->fail_flag = ff;
     out->furthest_reached_path_point = fu;
     float ms = 0.0f;
-    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    cudaEventElapsedTime(&ms, h->ev0, h->cfg.regenerate_noises ? h->ev_result : h->ev1);
     out->device_ms = ms;
   }
-  cudaEventElapsedTime(&h->prof_ms[3], h->ev0, h->ev1);
+  cudaEventElapsedTime(&h->prof_ms[3], h->ev0, h->cfg.regenerate_noises ? h->ev_result : h->ev1);
   if (h->peer_mode) {
     uint32_t comm_error;
     std::memcpy(&comm_error, h->h_out + 3 * T + 5, 4);
@@ -908,6 +932,29 @@ mppi_status fetch_time_major(mppi_handle * h, const V * d_src, V * host_dst)
   return MPPI_OK;
 }
 
+mppi_status sync_epoch(mppi_handle * h)
+{
+  const unsigned long long e = h->noise_stream;
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_epoch, &e, sizeof(e), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return MPPI_OK;
+}
+
+// regenerate_noises (noise_generator.cpp:54-63,97-105): redraw the noise once the current set has been consumed.  The
+// stream index comes from device memory (d_epoch) so that a captured graph draws a new set at every replay.
+mppi_status launch_regenerate(mppi_handle * h)
+{
+  const long long total = static_cast<long long>(h->B) * ((h->T + 3) / 4);
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 16));
+  noise_philox_kernel<<<std::max(blocks, 1), 256, 0, h->stream>>>(
+    h->d_noise[0], h->d_noise[1], h->d_noise[2], h->B, h->T, h->cfg.vx_std, h->cfg.vy_std, h->cfg.wz_std,
+    holonomic(h) ? 1 : 0, h->cfg.seed, 0, static_cast<uint64_t>(h->cfg.shard_offset), h->stream_layout ? 1 : 0, h->d_epoch);
+  advance_epoch_kernel<<<1, 1, 0, h->stream>>>(h->d_epoch);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches += 2;
+  return MPPI_OK;
+}
+
 mppi_status do_reset(mppi_handle * h)
 {
   const size_t T = h->T, B = h->B;
@@ -922,13 +969,13 @@ mppi_status do_reset(mppi_handle * h)
   const int blocks = static_cast<int>(std::min<long long>((total + threads - 1) / threads, 148LL * 16));
   noise_philox_kernel<<<std::max(blocks, 1), threads, 0, h->stream>>>(
     h->d_noise[0], h->d_noise[1], h->d_noise[2], h->B, h->T, h->cfg.vx_std, h->cfg.vy_std, h->cfg.wz_std,
-    holonomic(h) ? 1 : 0, h->cfg.seed, h->noise_stream, static_cast<uint64_t>(h->cfg.shard_offset), h->stream_layout ? 1 : 0);
+    holonomic(h) ? 1 : 0, h->cfg.seed, h->noise_stream, static_cast<uint64_t>(h->cfg.shard_offset), h->stream_layout ? 1 : 0, nullptr);
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   h->noise_stream++;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->cycle_uploaded = false;
-  return MPPI_OK;
+  return sync_epoch(h);
 }
 
 }  // namespace
@@ -1008,7 +1055,8 @@ void mppi_destroy(mppi_handle * h)
   for (float * p : h->d_inj) {cudaFree(p);}
   cudaFree(h->d_tmp); cudaFree(h->d_costmap); cudaFree(h->d_params); cudaFree(h->d_cs); cudaFree(h->d_crit_rows);
   cudaFree(h->d_end_xy); cudaFree(h->d_cells); cudaFree(h->d_costs); cudaFree(h->d_partials); cudaFree(h->d_rank_partial);
-  cudaFree(h->d_gathered); cudaFree(h->d_out); cudaFree(h->d_st); cudaFree(h->d_hist); cudaFree(h->d_seq); cudaFree(h->d_mailbox);
+  cudaFree(h->d_gathered); cudaFree(h->d_out); cudaFree(h->d_st); cudaFree(h->d_hist); cudaFree(h->d_seq); cudaFree(h->d_epoch);
+  if (h->ev_result) {cudaEventDestroy(h->ev_result);} cudaFree(h->d_mailbox);
   cudaFreeHost(h->h_params); cudaFreeHost(h->h_costmap); cudaFreeHost(h->h_out);
   if (h->ev0) {cudaEventDestroy(h->ev0);}
   if (h->ev1) {cudaEventDestroy(h->ev1);}
@@ -1095,6 +1143,8 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   CUDA_TRY(h, cudaMalloc(&h->d_out, (stride + 8) * sizeof(float)));
   CUDA_TRY(h, cudaMemsetAsync(h->d_out, 0, (stride + 8) * sizeof(float), h->stream));
   CUDA_TRY(h, cudaMalloc(&h->d_hist, 12 * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->d_epoch, sizeof(unsigned long long)));
+  CUDA_TRY(h, cudaEventCreate(&h->ev_result));
   CUDA_TRY(h, cudaMalloc(&h->d_seq, sizeof(unsigned)));
   CUDA_TRY(h, cudaMemsetAsync(h->d_seq, 0, sizeof(unsigned), h->stream));
   CUDA_TRY(h, cudaMalloc(&h->d_st, sizeof(DevState)));
@@ -1194,12 +1244,12 @@ mppi_status mppi_generate_noise(mppi_handle * h, uint64_t stream)
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 16));
   noise_philox_kernel<<<std::max(blocks, 1), 256, 0, h->stream>>>(
     h->d_noise[0], h->d_noise[1], h->d_noise[2], h->B, h->T, h->cfg.vx_std, h->cfg.vy_std, h->cfg.wz_std,
-    holonomic(h) ? 1 : 0, h->cfg.seed, stream, static_cast<uint64_t>(h->cfg.shard_offset), h->stream_layout ? 1 : 0);
+    holonomic(h) ? 1 : 0, h->cfg.seed, stream, static_cast<uint64_t>(h->cfg.shard_offset), h->stream_layout ? 1 : 0, nullptr);
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   h->noise_stream = stream + 1;   // a later reset() draws the next stream
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  return MPPI_OK;
+  return sync_epoch(h);
 }
 
 mppi_status mppi_get_noise(mppi_handle * h, float * vx, float * vy, float * wz)

@@ -102,8 +102,10 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float & z0, f
 
 __global__ void __launch_bounds__(256) noise_philox_kernel(
   float * __restrict__ nvx, float * __restrict__ nvy, float * __restrict__ nwz, int B, int T, float sx, float sy, float sw,
-  int holonomic, uint64_t seed, uint64_t stream, uint64_t shard_offset, int time_major)
+  int holonomic, uint64_t seed, uint64_t stream, uint64_t shard_offset, int time_major, const unsigned long long * __restrict__ d_epoch)
 {
+  // regenerate_noises: the Philox stream index lives in device memory so that a captured graph draws a new set per replay
+  if (d_epoch) {stream = *d_epoch;}
   const int quads = (T + 3) >> 2;
   const long long total = static_cast<long long>(B) * quads;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -162,6 +164,8 @@ enum StreamFeature : unsigned
   SF_ALL = 4095u
 };
 #define MPPI_SF(bit, flag) (((F & (bit)) != 0) && (kExact || (flag)))
+
+__global__ void advance_epoch_kernel(unsigned long long * d_epoch) {*d_epoch += 1ull;}
 
 // ---------------------------------------------------------------------------------------------------
 // K2

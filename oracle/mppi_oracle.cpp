@@ -1235,6 +1235,13 @@ struct Optimizer
       integrateStateVelocities(traj, state, cfg.model_dt, isHolonomic());
       evalTrajectoriesScores(data);
       updateControlSequence();
+      // ref: NoiseGenerator::generateNextNoises noise_generator.cpp:54-63 + noiseThread :97-105: with regenerate_noises the
+      // side thread redraws once the current set has been consumed.  The reference races that thread against the next
+      // iteration; the deterministic restatement is "every iteration consumes a fresh set" (Philox stream + 1 each time).
+      if (cfg.regenerate_noises) {
+        generateNoisedControls();
+        noise_stream++;
+      }
     }
     computeCells();
   }

@@ -408,3 +408,27 @@ def test_eval_control_skips_the_tail_on_failure(product_fns, oracle_fns):
     np.testing.assert_array_equal(cg, np.zeros(3, np.float32))
     np.testing.assert_array_equal(g.get_control_history(), hist)
     np.testing.assert_allclose(np.stack(g.get_control_sequence()), np.stack(o.get_control_sequence()), rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("layout", ["tile", "stream"])
+def test_regenerate_noises_draws_a_fresh_set_every_iteration(product_fns, oracle_fns, monkeypatch, layout):
+    """regenerate_noises (noise_generator.cpp:35,54-63,97-105): every iteration consumes a fresh Philox stream; the
+    redraw runs behind the result copy (and inside the captured graph, driven by a device-side epoch)"""
+    monkeypatch.setenv("MPPI_STREAM_MIN_BATCH", "64" if layout == "stream" else "1000000000")
+    sc = scenarios.config1(batch=384)
+    g, o = _pair(product_fns, oracle_fns, sc, None, regenerate_noises=1, seed=11, iteration_count=2)
+    for e in (g, o):
+        e.generate_noise(5)
+    prev = None
+    for cycle in range(5):
+        rg, ro = g.optimize(sc.cycle), o.optimize(sc.cycle)
+        for name, a, b in (("vx", rg.vx, ro.vx), ("vy", rg.vy, ro.vy), ("wz", rg.wz, ro.wz)):
+            np.testing.assert_allclose(a, b, rtol=RTOL, atol=2e-6, err_msg=f"cycle {cycle}: control {name}")
+        ng, no = g.get_noise(), o.get_noise()
+        np.testing.assert_allclose(ng[0], no[0], rtol=0, atol=4e-6)     # the set drawn for the NEXT cycle
+        assert prev is None or not np.array_equal(prev, ng[0])
+        prev = ng[0]
+        g.set_control_sequence(ro.vx, ro.vy, ro.wz)
+    # a reset continues the stream sequence identically on both sides
+    g.reset(); o.reset()
+    np.testing.assert_allclose(g.get_noise()[2], o.get_noise()[2], rtol=0, atol=4e-6)
