@@ -121,9 +121,9 @@ struct mppi_handle
   unsigned gkey_inst[6]{0, 0, 0, 0, 0, 0};
   int tail_mode{0};            // 0: optimize only, 1: + evalControl tail, 2: + tail with shiftControlSequence
   // peer-memory exchange (one process per GPU; mppi_comm_get_mailbox_handle / mppi_comm_connect_peers)
-  unsigned * d_mailbox{nullptr};          // this rank's mailbox (kBoxWords words)
+  uint2 * d_mailbox{nullptr};             // this rank's mailbox (kBoxPackets packets)
   unsigned * d_seq{nullptr};              // completed exchange rounds (survives mppi_reset: tags never repeat)
-  unsigned * peer_box[kMaxRanks]{};       // mailboxes of all ranks as mapped here; [rank] == d_mailbox
+  uint2 * peer_box[kMaxRanks]{};          // mailboxes of all ranks as mapped here; [rank] == d_mailbox
   bool peer_mode{false};
   float * d_hist{nullptr};     // control_history_ [4][3] (vx, vy, wz), optimizer.hpp:251
   unsigned long long * d_epoch{nullptr};   // regenerate_noises: Philox stream index of the next draw (device copy of noise_stream)
@@ -1718,7 +1718,7 @@ mppi_status mppi_comm_connect_peers(mppi_handle * h, const uint8_t * handles, in
       cudaGetLastError();
       return fail(h, MPPI_E_CUDA, std::string("cudaIpcOpenMemHandle (peer access between the GPUs of the box is required): ") + cudaGetErrorString(e));
     }
-    h->peer_box[r] = static_cast<unsigned *>(p);
+    h->peer_box[r] = static_cast<uint2 *>(p);
   }
   h->rank = rank; h->nranks = nranks; h->peer_mode = nranks > 1;
   return MPPI_OK;

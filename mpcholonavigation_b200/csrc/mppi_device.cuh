@@ -122,56 +122,58 @@ __device__ __forceinline__ void load_hot_params(float * s_hot, const DevParams *
 
 // ---------------------------------------------------------------------------------------------------
 // Peer-memory exchange between the ranks of a sharded problem (one process per GPU, NVLink / NVSwitch).
-// Every rank owns a small MAILBOX in its own HBM and maps the mailboxes of all peers (CUDA IPC).  A rank PUSHES its
-// contribution into slot [its rank] of every mailbox with plain remote stores, fences, then writes the cycle tag
-// into the slot's flag with a system-scope release store; consumers spin on flags in their LOCAL memory only.
-// No NCCL call, no extra kernel, no host involvement: exchange 1 rides at the start of K3, exchange 2 inside the
-// merge kernel.  Spins are bounded: a peer that never arrives raises comm_error instead of hanging.
-//   mailbox words:  x1   [kMaxRanks][kX1Words]   word 0 = tag, words 1..17 = furthest candidate + survivor flags
-//                   x2f  [kMaxRanks] (padded)     tag of the record below
-//                   x2   [kMaxRanks][kX2Stride]   (m, s, W[3T]) softmax record of the rank
+// Every rank owns a small MAILBOX in its own HBM and maps the mailboxes of all peers (CUDA IPC).  Data travels as
+// 8-byte PACKETS {value, tag}: one aligned 8-byte store is delivered whole, so a packet whose tag equals the tag of
+// the current round IS its own arrival flag (the "LL" idea of NCCL's low-latency protocol).  A rank pushes its
+// contribution into slot [its rank] of every mailbox with plain remote stores; consumers spin on packets in their
+// LOCAL memory.  No fences, no separate flags, no NCCL call, no extra kernel, no host involvement: one one-way NVLink
+// latency per exchange.  Exchange 1 rides at the start of K3, exchange 2 inside the merge kernel.
+// Spins are bounded: a peer that never arrives raises comm_error instead of hanging.  Tags are the round counter
+// (*seq + 1, 32 bit, never reset): a stale packet of an older round can never match.
+//   mailbox packets:  x1 [kMaxRanks][kX1Words]   words 0..16 = furthest candidate + survivor flags
+//                     x2 [kMaxRanks][kX2Stride]  (m, s, W[3T]) softmax record of the rank
 // ---------------------------------------------------------------------------------------------------
 constexpr int kMaxRanks = 16;
 constexpr int kX1Words = 32;
 constexpr int kX2Stride = ((3 * MPPI_MAX_TIME_STEPS + 2 + 15) / 16) * 16;
-constexpr int kBoxX1 = 0;
-constexpr int kBoxX2Flag = kMaxRanks * kX1Words;
-constexpr int kBoxX2 = kBoxX2Flag + 32;
-constexpr int kBoxWords = kBoxX2 + kMaxRanks * kX2Stride;
-constexpr long long kSpinLimitCycles = 4000000000LL;   // ~2 s at 1.965 GHz
+constexpr int kBoxX1 = 0;                                   // in packets
+constexpr int kBoxX2 = kMaxRanks * kX1Words;
+constexpr int kBoxPackets = kBoxX2 + kMaxRanks * kX2Stride;
+constexpr int kBoxWords = 2 * kBoxPackets;                  // the allocation, in 32-bit words
+constexpr long long kSpinLimitCycles = 4000000000LL;        // ~2 s at 1.965 GHz
 
 struct PeerComm
 {
-  unsigned * box[kMaxRanks];   // box[r] = mailbox of rank r as mapped into this process; box[rank] is local memory
+  uint2 * box[kMaxRanks];      // box[r] = mailbox of rank r as mapped into this process; box[rank] is local memory
   unsigned * seq;              // local: number of completed exchange rounds; the tag of the current round is *seq + 1
   int rank, nranks;            // nranks <= 1: not sharded over peer memory
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned * p, unsigned v)
-{
-  asm volatile ("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned * p)
-{
-  unsigned v;
-  asm volatile ("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned * p)
 {
   unsigned v;
   asm volatile ("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// bounded spin on a flag in local memory
-__device__ __forceinline__ bool wait_tag(const unsigned * p, unsigned tag)
+__device__ __forceinline__ void st_packet(uint2 * p, unsigned value, unsigned tag)
+{
+  asm volatile ("st.volatile.global.v2.u32 [%0], {%1, %2};" :: "l"(p), "r"(value), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 ld_packet(const uint2 * p)
+{
+  uint2 v;
+  asm volatile ("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+// bounded spin on a packet in local memory; returns false (and value 0) on time-out
+__device__ __forceinline__ bool poll_packet(const uint2 * p, unsigned tag, unsigned & value)
 {
   const long long t0 = clock64();
-  while (ld_acquire_sys(p) != tag) {
-    if (clock64() - t0 > kSpinLimitCycles) {return false;}
-    __nanosleep(32);
+  for (;;) {
+    const uint2 v = ld_packet(p);
+    if (v.y == tag) {value = v.x; return true;}
+    if (clock64() - t0 > kSpinLimitCycles) {value = 0u; return false;}
   }
-  return true;
 }
 
 // Persistent per-optimize state shared between kernels (device memory, 1 record per handle).

@@ -1068,27 +1068,27 @@ __device__ __forceinline__ void k3_preamble(
   if (tid == 33) {s_state[2] = static_cast<unsigned>(st->furthest_set); s_state[3] = static_cast<unsigned>(st->fail_flag);}
   if (pc.nranks > 1) {
     // ---- exchange 1 over peer memory: element-wise MAX of (furthest candidate, survivor flags) across the ranks.
-    //      Block 0 pushes this rank's 17 words into every mailbox; every block then waits on its LOCAL mailbox.
+    //      Block 0 pushes this rank's 17 words as packets into every mailbox; every block polls its LOCAL mailbox.
+    __shared__ unsigned s_x1[1 + kMaxCritics];
     const unsigned tag = ld_volatile_u32(pc.seq) + 1u;
     constexpr int kWords = 1 + kMaxCritics;
-    if (blockIdx.x == 0) {
-      if (tid < kWords) {
-        const unsigned v = tid == 0 ? st->furthest_candidate : st->any_ok[tid - 1];
-        for (int r = 0; r < pc.nranks; ++r) {pc.box[r][kBoxX1 + pc.rank * kX1Words + 1 + tid] = v;}
-      }
-      __threadfence_system();
-      __syncthreads();
-      if (tid < pc.nranks) {st_release_sys(pc.box[tid] + kBoxX1 + pc.rank * kX1Words, tag);}
+    if (tid < kWords) {s_x1[tid] = 0u;}
+    if (blockIdx.x == 0 && tid < kWords) {
+      const unsigned v = tid == 0 ? st->furthest_candidate : st->any_ok[tid - 1];
+#pragma unroll 1
+      for (int r = 0; r < pc.nranks; ++r) {st_packet(pc.box[r] + kBoxX1 + pc.rank * kX1Words + tid, v, tag);}
     }
-    const unsigned * local = pc.box[pc.rank];
-    bool ok = true;
-    if (tid < pc.nranks) {ok = wait_tag(local + kBoxX1 + tid * kX1Words, tag);}
-    if (!ok) {st->comm_error = 1u;}
+    __syncthreads();
+    const uint2 * local = pc.box[pc.rank];
+    for (int i = tid; i < kWords * pc.nranks; i += nthr) {
+      const int r = i / kWords, w = i - r * kWords;
+      unsigned v;
+      if (!poll_packet(local + kBoxX1 + r * kX1Words + w, tag, v)) {st->comm_error = 1u;}
+      atomicMax(&s_x1[w], v);
+    }
     __syncthreads();
     if (tid < kWords) {
-      unsigned m = 0u;
-      for (int r = 0; r < pc.nranks; ++r) {m = max(m, ld_volatile_u32(local + kBoxX1 + r * kX1Words + 1 + tid));}
-      if (tid == 0) {s_state[0] = m;} else {s_any_ok[tid - 1] = m;}
+      if (tid == 0) {s_state[0] = s_x1[0];} else {s_any_ok[tid - 1] = s_x1[tid];}
     }
   }
   const DevParams * P = reinterpret_cast<const DevParams *>(s_hot);
@@ -1713,7 +1713,6 @@ __global__ void __launch_bounds__(kUpdThreads) merge_exchange_finalize_kernel(
   __shared__ float s_red[kUpdThreads / 32];
   __shared__ float s_col[3 * kMergeT + 1];
   __shared__ float s_e[kMergeCached];
-  __shared__ unsigned sc_last;
   const PeerComm & pc = bufs.peer;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = Pg->T;
@@ -1752,50 +1751,84 @@ __global__ void __launch_bounds__(kUpdThreads) merge_exchange_finalize_kernel(
     if (lane == 0) {s_col[k] = acc;}
   }
   __syncthreads();
-  // ---- push the merged slice into every rank's mailbox (remote stores over NVLink; slot = this rank)
+  // ---- push this block's merged values as packets into every rank's mailbox (remote stores over NVLink, slot = rank):
+  //      record index 0 = m, 1 = s (block 0 only), 2 + plane * T + t = W
+  if (tid < 3 * kMergeT + 1) {
+    int idx = -1;
+    if (tid == 0) {
+      idx = blockIdx.x == 0 ? 1 : -1;
+    } else {
+      const int t = t_first + (tid - 1) / 3, plane = (tid - 1) % 3;
+      if (t < T) {idx = 2 + plane * T + t;}
+    }
+    if (idx >= 0) {
+      const unsigned bits = __float_as_uint(s_col[tid]);
+#pragma unroll 1
+      for (int r = 0; r < pc.nranks; ++r) {st_packet(pc.box[r] + kBoxX2 + pc.rank * kX2Stride + idx, bits, tag);}
+    }
+  } else if (tid == 32 && blockIdx.x == 0) {
+    const unsigned bits = __float_as_uint(m);
+#pragma unroll 1
+    for (int r = 0; r < pc.nranks; ++r) {st_packet(pc.box[r] + kBoxX2 + pc.rank * kX2Stride, bits, tag);}
+  }
+  // ---- every block polls, in its LOCAL mailbox, the packets it needs from every rank: m, s and its own columns
+  __shared__ float s_in[kMaxRanks][3 * kMergeT + 2];
+  const uint2 * local = pc.box[pc.rank];
+  constexpr int kNeed = 3 * kMergeT + 2;
+  for (int i = tid; i < kNeed * pc.nranks; i += kUpdThreads) {
+    const int r = i / kNeed, k = i - r * kNeed;   // k: 0 = m, 1 = s, 2.. = columns (t, plane)
+    int idx = k;
+    bool want = true;
+    if (k >= 2) {
+      const int t = t_first + (k - 2) / 3, plane = (k - 2) % 3;
+      want = t < T;
+      idx = 2 + plane * T + t;
+    }
+    unsigned bits = 0u;
+    if (want && !poll_packet(local + kBoxX2 + r * kX2Stride + idx, tag, bits)) {bufs.st->comm_error = 1u;}
+    s_in[r][k] = __uint_as_float(bits);
+  }
+  __syncthreads();
+  // ---- cross-rank merge of this block's time steps, cs = W / sum, applyControlSequenceConstraints (optimizer.cpp:237-249)
   if (tid < kMergeT && t_first + tid < T) {
     const int t = t_first + tid;
-    for (int r = 0; r < pc.nranks; ++r) {
-      float * rec = reinterpret_cast<float *>(pc.box[r] + kBoxX2 + pc.rank * kX2Stride);
-      if (blockIdx.x == 0 && tid == 0) {rec[0] = m; rec[1] = s_col[0];}
-      rec[2 + t] = s_col[1 + 3 * tid]; rec[2 + T + t] = s_col[2 + 3 * tid]; rec[2 + 2 * T + t] = s_col[3 + 3 * tid];
-    }
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (tid == 0) {sc_last = atomicAdd(&bufs.st->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;}
-  __syncthreads();
-  if (!sc_last) {return;}
-  // ---- last block: publish, wait for every rank, merge the nranks records, finalize
-  __threadfence_system();
-  if (tid < pc.nranks) {st_release_sys(pc.box[tid] + kBoxX2Flag + pc.rank, tag);}
-  const unsigned * local = pc.box[pc.rank];
-  bool ok = true;
-  if (tid < pc.nranks) {ok = wait_tag(local + kBoxX2Flag + tid, tag);}
-  if (!ok) {bufs.st->comm_error = 1u;}
-  __syncthreads();
-  float * merged = s_e;   // [3T + 2] (3 * 256 + 2 <= kMergeCached)
-  {
     float gm = 3.402823466e+38f;
-    for (int r = 0; r < pc.nranks; ++r) {gm = fminf(gm, __uint_as_float(ld_volatile_u32(local + kBoxX2 + r * kX2Stride)));}
-    for (int c = tid; c < 3 * T + 1; c += kUpdThreads) {
-      float acc = 0.0f;
-      for (int r = 0; r < pc.nranks; ++r) {
-        const unsigned * rec = local + kBoxX2 + r * kX2Stride;
-        const float e = expf(-(__uint_as_float(ld_volatile_u32(rec)) - gm) * inv_temp);
-        acc = fmaf(__uint_as_float(ld_volatile_u32(rec + 1 + c)), e, acc);
-      }
-      merged[1 + c] = acc;
+    for (int r = 0; r < pc.nranks; ++r) {gm = fminf(gm, s_in[r][0]);}
+    float ssum = 0.0f, wvx = 0.0f, wvy = 0.0f, wwz = 0.0f;
+    for (int r = 0; r < pc.nranks; ++r) {
+      const float e = expf(-(s_in[r][0] - gm) * inv_temp);
+      ssum = fmaf(s_in[r][1], e, ssum);
+      wvx = fmaf(s_in[r][2 + 3 * tid], e, wvx);
+      wvy = fmaf(s_in[r][3 + 3 * tid], e, wvy);
+      wwz = fmaf(s_in[r][4 + 3 * tid], e, wwz);
     }
-    if (tid == 0) {merged[0] = gm;}
+    float vx = wvx / ssum, wz = wwz / ssum, vy = bufs.cs[T + t];
+    if (Pg->holonomic) {
+      vy = wvy / ssum;
+      vy = fminf(fmaxf(vy, -Pg->c_vy), Pg->c_vy);
+    }
+    vx = fminf(fmaxf(vx, Pg->c_vx_min), Pg->c_vx_max);
+    wz = fminf(fmaxf(wz, -Pg->c_wz), Pg->c_wz);
+    if (Pg->model == MPPI_MODEL_ACKERMANN) {   // motion_models.hpp:110-117
+      const float rr = Pg->min_turning_r;
+      if (fabsf(vx) / fabsf(wz) < rr) {
+        const float sgn = wz > 0.0f ? 1.0f : (wz < 0.0f ? -1.0f : 0.0f);
+        wz = sgn * fabsf(vx) / rr;
+      }
+    }
+    bufs.cs[t] = vx; bufs.cs[T + t] = vy; bufs.cs[2 * T + t] = wz;
+    bufs.out[t] = vx; bufs.out[T + t] = vy; bufs.out[2 * T + t] = wz;
   }
+  // ---- the last block to finish closes the round on this rank
+  __threadfence();
   __syncthreads();
-  finalize_controls(Pg, merged, bufs.cs, bufs.out, tid, kUpdThreads);
   if (tid == 0) {
-    bufs.st->ticket = 0u;
-    bufs.out[3 * T + 5] = __uint_as_float(bufs.st->comm_error);
-    __threadfence();
-    *pc.seq = tag;   // round complete on this rank
+    if (atomicAdd(&bufs.st->ticket, 1u) == gridDim.x - 1) {
+      bufs.st->ticket = 0u;
+      bufs.out[3 * T + 5] = __uint_as_float(bufs.st->comm_error);
+      __threadfence();
+      *pc.seq = tag;
+    }
   }
 }
 
