@@ -235,6 +235,12 @@ mppi_status mppi_optimize_resident(mppi_handle * h, mppi_cycle_out * out);
 mppi_status mppi_set_outputs(mppi_handle * h, uint32_t want_mask);
 /* ref: Optimizer::getGeneratedTrajectories optimizer.cpp:455-458 */
 mppi_status mppi_get_trajectories(mppi_handle * h, float * x, float * y, float * yaw);
+/* ref: the only consumer of the candidate trajectories, TrajectoryVisualizer::add (trajectory_visualizer.cpp:86-108), draws
+ * x(i, j), y(i, j) for i = 0, trajectory_step, ... and j = 0, time_step, ... ("TrajectoryVisualizer.trajectory_step" 5,
+ * ".time_step" 3): K2 materialises exactly that lattice.  (0, 0) switches it off.  Outputs are
+ * [ceil(B / trajectory_step)][ceil(T / time_step)] row-major. */
+mppi_status mppi_set_visualization(mppi_handle * h, int32_t trajectory_step, int32_t time_step);
+mppi_status mppi_get_visualization(mppi_handle * h, float * x, float * y);
 mppi_status mppi_get_cells(mppi_handle * h, int32_t * cells);
 /* total costs_[B] after the last iteration (before they are consumed by the softmax: includes gamma term) */
 mppi_status mppi_get_costs(mppi_handle * h, float * costs);

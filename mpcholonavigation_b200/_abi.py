@@ -193,6 +193,8 @@ PRODUCT_ONLY = {
     "upload_cycle": (C.c_int, [H, C.POINTER(CycleIn)]),
     "optimize_resident": (C.c_int, [H, C.POINTER(CycleOut)]),
     "set_outputs": (C.c_int, [H, C.c_uint32]),
+    "set_visualization": (C.c_int, [H, C.c_int32, C.c_int32]),
+    "get_visualization": (C.c_int, [H, f32p, f32p]),
     "set_profiling": (C.c_int, [H, C.c_int32]),
     "get_profile": (C.c_int, [H, f32p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "comm_get_unique_id": (C.c_int, [u8p]),

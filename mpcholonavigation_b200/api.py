@@ -329,6 +329,17 @@ class Engine:
         if "set_outputs" in self.f:
             self._check(self.f["set_outputs"](self.h, mask))
 
+    def set_visualization(self, trajectory_step, time_step):
+        self._check(self.f["set_visualization"](self.h, int(trajectory_step), int(time_step)))
+        self._vis = (int(trajectory_step), int(time_step))
+
+    def get_visualization(self):
+        ts, s = self._vis
+        nb, nt = -(-self.B // ts), -(-self.T // s)
+        x, y = np.empty((nb, nt), np.float32), np.empty((nb, nt), np.float32)
+        self._check(self.f["get_visualization"](self.h, _p(x), _p(y)))
+        return x, y
+
     def get_trajectories(self):
         x, y, yaw = self._planes()
         self._check(self.f["get_trajectories"](self.h, _p(x), _p(y), _p(yaw)))

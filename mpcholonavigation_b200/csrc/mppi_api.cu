@@ -125,6 +125,10 @@ struct mppi_handle
   unsigned * d_seq{nullptr};              // completed exchange rounds (survives mppi_reset: tags never repeat)
   uint2 * peer_box[kMaxRanks]{};          // mailboxes of all ranks as mapped here; [rank] == d_mailbox
   bool peer_mode{false};
+  int vis_b_step{0}, vis_t_step{0};       // mppi_set_visualization
+  float * d_vis{nullptr};
+  size_t vis_capacity{0};
+  bool vis_valid{false};
   float * d_hist{nullptr};     // control_history_ [4][3] (vx, vy, wz), optimizer.hpp:251
   unsigned long long * d_epoch{nullptr};   // regenerate_noises: Philox stream index of the next draw (device copy of noise_stream)
   cudaEvent_t ev_result{nullptr};          // regenerate_noises: result is in host memory (the redraw may still be running)
@@ -263,6 +267,8 @@ mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, un
   p.track_unknown = h->robot.track_unknown;
   p.want_cells = (h->want_mask & MPPI_WANT_CELLS) ? 1 : 0;
   p.want_critic_rows = (h->want_mask & MPPI_WANT_CRITIC_COSTS) ? 1 : 0;
+  p.vis_b_step = h->vis_b_step; p.vis_t_step = h->vis_t_step;
+  p.vis_nb = h->vis_b_step > 0 ? (h->B + h->vis_b_step - 1) / h->vis_b_step : 0;
   p.fp_n = h->robot.footprint_size;
   for (int i = 0; i < p.fp_n; ++i) {p.fp_x[i] = h->robot.footprint_x[i]; p.fp_y[i] = h->robot.footprint_y[i];}
 
@@ -570,6 +576,7 @@ DevBuffers make_bufs(mppi_handle * h, int mode)
   b.end_xy = h->d_end_xy;
   b.spill_x = h->d_spill[0]; b.spill_y = h->d_spill[1]; b.spill_yaw = h->d_spill[2];
   b.spill_cells = h->d_cells;
+  b.vis_xy = h->d_vis;
   b.costs = h->d_costs; b.partials = h->d_partials; b.rank_partial = h->d_rank_partial; b.out = h->d_out; b.st = h->d_st;
   for (int r = 0; r < kMaxRanks; ++r) {b.peer.box[r] = h->peer_mode ? h->peer_box[r] : nullptr;}
   b.peer.seq = h->d_seq;
@@ -630,7 +637,7 @@ unsigned stream_feature_need(const DevParams & p)
   if (p.cost.on) {need |= SF_COST;}
   if (p.obst.on) {need |= SF_OBST;}
   if ((p.cost.on && p.cost_fp) || (p.obst.on && p.obst_fp)) {need |= SF_FOOTPRINT;}
-  if (p.want_cells || p.spill_traj) {need |= SF_SPILL;}
+  if (p.want_cells || p.spill_traj || p.vis_b_step > 0) {need |= SF_SPILL;}
   return need;
 }
 
@@ -875,6 +882,7 @@ mppi_status finish_optimize(mppi_handle * h, mppi_cycle_out * out)
   const int T = h->T;
   h->spilled_traj = h->last.spill_traj != 0;
   h->spilled_cells = h->last.want_cells != 0;
+  h->vis_valid = h->last.vis_b_step > 0;
   h->have_rows = true;
   if (out) {
     if (out->control_vx) {std::memcpy(out->control_vx, h->h_out, sizeof(float) * T);}
@@ -1053,6 +1061,8 @@ void mppi_destroy(mppi_handle * h)
   for (float * p : h->d_samples) {cudaFree(p);}
   for (float * p : h->d_spill) {cudaFree(p);}
   for (float * p : h->d_inj) {cudaFree(p);}
+  cudaFree(h->d_vis);
+  cudaFree(h->d_vis);
   cudaFree(h->d_tmp); cudaFree(h->d_costmap); cudaFree(h->d_params); cudaFree(h->d_cs); cudaFree(h->d_crit_rows);
   cudaFree(h->d_end_xy); cudaFree(h->d_cells); cudaFree(h->d_costs); cudaFree(h->d_partials); cudaFree(h->d_rank_partial);
   cudaFree(h->d_gathered); cudaFree(h->d_out); cudaFree(h->d_st); cudaFree(h->d_hist); cudaFree(h->d_seq); cudaFree(h->d_epoch);
@@ -1416,6 +1426,47 @@ mppi_status mppi_get_trajectories(mppi_handle * h, float * x, float * y, float *
   if ((s = fetch_time_major<float>(h, h->d_spill[0], x)) != MPPI_OK) {return s;}
   if ((s = fetch_time_major<float>(h, h->d_spill[1], y)) != MPPI_OK) {return s;}
   return fetch_time_major<float>(h, h->d_spill[2], yaw);
+}
+
+// The TrajectoryVisualizer (trajectory_visualizer.cpp:86-108) draws every trajectory_step-th candidate at every
+// time_step-th step: materialise exactly that lattice in K2 (a few percent of the traffic of the full planes).
+mppi_status mppi_set_visualization(mppi_handle * h, int32_t trajectory_step, int32_t time_step)
+{
+  if (!h || trajectory_step < 0 || time_step < 0 || (trajectory_step == 0) != (time_step == 0)) {return MPPI_E_CONFIG;}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  drop_graphs(h);
+  h->vis_b_step = trajectory_step; h->vis_t_step = time_step; h->vis_valid = false;
+  if (trajectory_step > 0) {
+    const size_t nb = (h->B + trajectory_step - 1) / trajectory_step, nt = (h->T + time_step - 1) / time_step;
+    if (2 * nb * nt > h->vis_capacity) {
+      cudaFree(h->d_vis);
+      h->d_vis = nullptr; h->vis_capacity = 0;
+      CUDA_TRY(h, cudaMalloc(&h->d_vis, 2 * nb * nt * sizeof(float)));
+      h->vis_capacity = 2 * nb * nt;
+    }
+  }
+  return MPPI_OK;
+}
+
+// x, y: [ceil(B / trajectory_step)][ceil(T / time_step)] row-major = trajectories.x(i * trajectory_step, j * time_step)
+mppi_status mppi_get_visualization(mppi_handle * h, float * x, float * y)
+{
+  if (!h || !x || !y) {return MPPI_E_CONFIG;}
+  if (!h->vis_valid) {return fail(h, MPPI_E_STATE, "mppi_set_visualization before optimize");}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const int nb = (h->B + h->vis_b_step - 1) / h->vis_b_step, nt = (h->T + h->vis_t_step - 1) / h->vis_t_step;
+  mppi_status s = ensure_tmp(h);
+  if (s != MPPI_OK) {return s;}
+  const dim3 grid((nb + 31) / 32, (nt + 31) / 32), block(32, 8);
+  float * dst[2] = {x, y};
+  for (int k = 0; k < 2; ++k) {
+    transpose_tb_to_bt_kernel<float><<<grid, block, 0, h->stream>>>(h->d_vis + static_cast<size_t>(k) * nt * nb, h->d_tmp, nt, nb);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaMemcpyAsync(dst[k], h->d_tmp, static_cast<size_t>(nb) * nt * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  return MPPI_OK;
 }
 
 mppi_status mppi_get_cells(mppi_handle * h, int32_t * cells)

@@ -89,6 +89,7 @@ struct DevParams
   int sample_step, n_samples, sample_yaw;    // PathAlign samples: p = 0, step, 2 step ... < T
   int spill_traj;                            // write x,y,yaw time-major (PathAngle may fire / requested)
   int want_cells;
+  int vis_b_step, vis_t_step, vis_nb;        // visualiser feed: every vis_b_step-th trajectory x every vis_t_step-th step (0: off)
   int need_furthest;                         // some path critic may ask for the furthest reached path point
   int noise_tm;                              // noise planes are stored time-major [T][B] (stream layout) instead of [B][T]
   // offsets (in floats) of the path arrays that follow this struct in the same buffer

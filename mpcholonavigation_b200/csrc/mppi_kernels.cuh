@@ -45,6 +45,7 @@ struct DevBuffers
   float * spill_y;
   float * spill_yaw;
   int * spill_cells;    // [T][B]
+  float * vis_xy;       // [2][ceil(T / vis_t_step)][ceil(B / vis_b_step)] sub-sampled x, y for the TrajectoryVisualizer
   float * costs;        // [B]
   float * partials;     // [blocks][3T + 2]
   float * rank_partial; // [3T + 2] (+ fail flag / furthest packed after it for the exchange)
@@ -533,6 +534,12 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
         if (spill) {
           bufs.spill_x[g] = px; bufs.spill_y[g] = py; bufs.spill_yaw[g] = s_yaw[o];
         }
+        if (kSpill && p.vis_b_step > 0 && t % p.vis_t_step == 0 && b % p.vis_b_step == 0) {
+          // TrajectoryVisualizer::add (trajectory_visualizer.cpp:86-108) reads only this lattice of the candidates
+          const int nt = (T + p.vis_t_step - 1) / p.vis_t_step;
+          const size_t k = static_cast<size_t>(t / p.vis_t_step) * p.vis_nb + b / p.vis_b_step;
+          bufs.vis_xy[k] = px; bufs.vis_xy[static_cast<size_t>(nt) * p.vis_nb + k] = py;
+        }
         g += B;
       }
     }
@@ -875,6 +882,11 @@ __global__ void __launch_bounds__(kStreamThreads, MPPI_STREAM_MIN_BLOCKS) rollou
               next_sample += step; sample_k++;
             }
             if (kSpill && spill) {bufs.spill_x[g] = px[u]; bufs.spill_y[g] = py[u]; bufs.spill_yaw[g] = yaw;}
+            if (kSpill && p.vis_b_step > 0 && t % p.vis_t_step == 0 && b % p.vis_b_step == 0) {
+              const int nt = (T + p.vis_t_step - 1) / p.vis_t_step;
+              const size_t k = static_cast<size_t>(t / p.vis_t_step) * p.vis_nb + b / p.vis_b_step;
+              bufs.vis_xy[k] = px[u]; bufs.vis_xy[static_cast<size_t>(nt) * p.vis_nb + k] = py[u];
+            }
           }
           g += B;
           if (kTail) {

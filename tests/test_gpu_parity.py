@@ -432,3 +432,26 @@ def test_regenerate_noises_draws_a_fresh_set_every_iteration(product_fns, oracle
     # a reset continues the stream sequence identically on both sides
     g.reset(); o.reset()
     np.testing.assert_allclose(g.get_noise()[2], o.get_noise()[2], rtol=0, atol=4e-6)
+
+
+@pytest.mark.parametrize("layout", ["tile", "stream"])
+def test_visualizer_lattice(product_fns, oracle_fns, monkeypatch, layout):
+    """mppi_set_visualization: K2 materialises only x(i * trajectory_step, j * time_step), the lattice
+    TrajectoryVisualizer::add reads (trajectory_visualizer.cpp:86-108), bit-identical to the full planes"""
+    monkeypatch.setenv("MPPI_STREAM_MIN_BATCH", "64" if layout == "stream" else "1000000000")
+    sc = scenarios.config1(batch=333)
+    g, o = _pair(product_fns, oracle_fns, sc, sc.noise())
+    g.set_outputs()                      # nothing else materialised
+    g.set_visualization(5, 3)
+    for _ in range(3):
+        rg, ro = g.optimize(sc.cycle), o.optimize(sc.cycle)
+        g.set_control_sequence(ro.vx, ro.vy, ro.wz)
+    x, y = g.get_visualization()
+    ox, oy, _ = o.get_trajectories()
+    assert x.shape == (67, 19)
+    assert np.array_equal(x, ox[::5, ::3]) and np.array_equal(y, oy[::5, ::3])
+    np.testing.assert_allclose(rg.vx, ro.vx, rtol=RTOL, atol=ATOL)
+    g.set_visualization(0, 0)
+    g.optimize(sc.cycle)
+    with pytest.raises(Exception):
+        g.get_visualization()
