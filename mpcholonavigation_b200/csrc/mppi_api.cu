@@ -112,6 +112,10 @@ struct mppi_handle
   DevParams last;   // host copy of the last uploaded record
   int segments_override{0};
   int stream_threads_override{0};
+  bool fused_enabled{true};    // small batches: one cooperative launch per iteration (tile_fused_kernel); MPPI_FUSED=0 disables
+  int fused_key_N{-1};         // path size the cached decision below was taken for (the shared-memory size depends on it)
+  bool fused_fits{false};      // the whole grid is co-resident (a cooperative launch needs that)
+  int num_sms{0};
   bool stream_layout{false};   // large batches: time-major noise + thread-per-trajectory K2 + GEMV-style weighted sums
   int upd_blocks{0};
   // CUDA graphs of the steady-state cycle: [0] kernels + D2H (resident inputs), [1] H2D + kernels + D2H
@@ -673,6 +677,64 @@ void launch_stream_instance(mppi_handle * h, int mode)
 
 mppi_status launch_regenerate(mppi_handle * h);
 
+constexpr int kFusedSmemMax = 226 * 1024;
+
+template<unsigned F, bool kExact>
+cudaError_t fused_occupancy(int threads, size_t smem, int * blocks_per_sm)
+{
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, tile_fused_kernel<F, kExact>, threads, smem);
+}
+
+// Does this cycle run as ONE cooperative launch of tile_fused_kernel?  Single rank, tile layout, and the whole grid
+// co-resident (checked once per path size with the occupancy API; the generic instance is the largest one).
+bool use_fused(mppi_handle * h)
+{
+  if (!h->fused_enabled || h->stream_layout || h->nranks > 1) {return false;}
+  const int N = h->last.N;
+  if (h->fused_key_N != N) {
+    h->fused_key_N = N;
+    h->fused_fits = false;
+    const int S = pick_segments(h);
+    const int grid = (h->B + kTile - 1) / kTile;
+    const size_t smem = fused_smem_bytes(h->T, S, N, grid);
+    int per_sm = 0;
+    if (smem <= static_cast<size_t>(kFusedSmemMax) && fused_occupancy<SF_ALL, false>(kTile * S, smem, &per_sm) == cudaSuccess) {
+      h->fused_fits = static_cast<long long>(per_sm) * h->num_sms >= grid;
+    }
+    cudaGetLastError();
+  }
+  return h->fused_fits;
+}
+
+template<unsigned F, bool kExact>
+cudaError_t launch_fused_instance(mppi_handle * h, int iteration)
+{
+  const int S = pick_segments(h);
+  const dim3 grid((h->B + kTile - 1) / kTile), block(kTile, S);
+  int N = h->last.N;
+  const size_t smem = fused_smem_bytes(h->T, S, N, grid.x);
+  const DevParams * dp = reinterpret_cast<const DevParams *>(h->d_params);
+  const uint8_t * cm = h->d_costmap;
+  DevBuffers bufs = make_bufs(h, 0);
+  int B = h->B, T = h->T;
+  void * args[] = {&dp, &cm, &bufs, &B, &T, &N, &iteration};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&tile_fused_kernel<F, kExact>), grid, block, args, smem, h->stream);
+}
+
+mppi_status launch_fused(mppi_handle * h, int iteration)
+{
+  cudaError_t e;
+  switch (pick_stream_instance(stream_feature_need(h->last))) {
+    case kSfOmniDefault: e = launch_fused_instance<kSfOmniDefault, true>(h, iteration); break;
+    case kSfOmniDefaultFp: e = launch_fused_instance<kSfOmniDefaultFp, true>(h, iteration); break;
+    case kSfObstaclesFp: e = launch_fused_instance<kSfObstaclesFp, true>(h, iteration); break;
+    default: e = launch_fused_instance<SF_ALL, false>(h, iteration); break;
+  }
+  CUDA_TRY(h, e);
+  h->launches++;
+  return MPPI_OK;
+}
+
 mppi_status launch_rollout(mppi_handle * h, int mode)
 {
   if (mode == 0 && h->stream_layout) {
@@ -740,8 +802,22 @@ mppi_status launch_update(mppi_handle * h, int mode, int iteration)
 mppi_status enqueue_kernels(mppi_handle * h, bool prof)
 {
   const int stride = 3 * h->T + 2;
+  const bool fused = use_fused(h);
   for (int it = 0; it < h->cfg.iteration_count; ++it) {
     if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[0], h->stream));}
+    if (fused) {
+      // small batches: rollout, critics, softmax update and merge in one cooperative launch (pev: all of it counts as K2)
+      mppi_status s = launch_fused(h, it);
+      if (s != MPPI_OK) {return s;}
+      if (prof) {
+        CUDA_TRY(h, cudaEventRecord(h->pev[1], h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->pev[2], h->stream));
+      }
+      if (h->cfg.regenerate_noises && it + 1 < h->cfg.iteration_count) {
+        if ((s = launch_regenerate(h)) != MPPI_OK) {return s;}
+      }
+      continue;
+    }
     mppi_status s = launch_rollout(h, 0);
     if (s != MPPI_OK) {return s;}
     if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[1], h->stream));}
@@ -857,8 +933,8 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
     }
     if (h->gexec[slot]) {
       CUDA_TRY(h, cudaGraphLaunch(h->gexec[slot], h->stream));
-      h->launches += (h->stream_layout ? 4ull : (h->upd_blocks > kLastBlockMergeMax ? 3ull : 2ull)) * h->cfg.iteration_count +
-        (h->tail_mode ? 1ull : 0ull);
+      h->launches += (use_fused(h) ? 1ull : (h->stream_layout ? 4ull : (h->upd_blocks > kLastBlockMergeMax ? 3ull : 2ull))) *
+        h->cfg.iteration_count + (h->tail_mode ? 1ull : 0ull);
       CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
       return MPPI_OK;
     }
@@ -1100,6 +1176,7 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
     h->stream_threads_override = std::max(32, std::min(kStreamThreads, (std::atoi(e) / 32) * 32));
   }
   if (const char * e = std::getenv("MPPI_NO_GRAPH")) {h->use_graph = std::atoi(e) == 0;}
+  if (const char * e = std::getenv("MPPI_FUSED")) {h->fused_enabled = std::atoi(e) != 0;}
   {
     // batches too small to fill the GPU with one thread per trajectory keep the latency-oriented tile kernel
     long long stream_min = 8192;    // measured cross-over on B200 (profiles/): below it the tile kernel wins
@@ -1120,6 +1197,17 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
     CUDA_TRY(h, cudaFuncSetAttribute(rollout_score_kernel<kSfOmniDefault, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(h, cudaFuncSetAttribute(rollout_score_kernel<kSfOmniDefaultFp, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(h, cudaFuncSetAttribute(rollout_score_kernel<kSfObstaclesFp, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  }
+  {
+    const int big = kFusedSmemMax;   // the kernel also has a little static shared memory
+    CUDA_TRY(h, cudaFuncSetAttribute(tile_fused_kernel<SF_ALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(h, cudaFuncSetAttribute(tile_fused_kernel<kSfOmniDefault, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(h, cudaFuncSetAttribute(tile_fused_kernel<kSfOmniDefaultFp, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(h, cudaFuncSetAttribute(tile_fused_kernel<kSfObstaclesFp, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    int coop = 0;
+    CUDA_TRY(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+    CUDA_TRY(h, cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+    if (!coop) {h->fused_enabled = false;}
   }
   CUDA_TRY(h, cudaFuncSetAttribute(path_softmax_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
     static_cast<int>(k3_tile_smem_bytes(MPPI_MAX_TIME_STEPS))));

@@ -65,11 +65,66 @@ enum Acc
 // Rollout modes keep 4 planes (x and y are built IN PLACE over the vx / vy control planes once the velocity
 // critics have consumed them); the score mode (caller-provided trajectories) needs x and y beside the state: 6.
 __host__ __device__ inline int rollout_planes(int mode) {return mode == 2 ? 6 : 4;}
+__host__ __device__ inline size_t rollout_smem_floats(int T, int S, int planes)
+{
+  return static_cast<size_t>(kHotFloats) + 3 * T + 3 * kTile + static_cast<size_t>(planes) * T * kPad +
+         static_cast<size_t>(S) * A_COUNT * kTile + 2 * static_cast<size_t>(S) * kTile;
+}
 __host__ __device__ inline size_t rollout_smem_bytes(int T, int S, int mode)
 {
-  return sizeof(float) * (static_cast<size_t>(kHotFloats) + 3 * T + 3 * kTile + static_cast<size_t>(rollout_planes(mode)) * T * kPad +
-         static_cast<size_t>(S) * A_COUNT * kTile + 2 * static_cast<size_t>(S) * kTile);
+  return sizeof(float) * rollout_smem_floats(T, S, rollout_planes(mode));
 }
+
+// The fused small-batch kernel (tile_fused_kernel, below) keeps going where K2 stops: what K2 leaves in shared memory
+// and registers is handed over in this record instead of through global memory.
+struct FusedShared
+{
+  float * rows;       // [kMaxCritics + kGammaRows][32] per-critic contributions of this tile + the three gamma sums
+  float * term;       // [4][32] path critic terms: follow, align, legacy, angle
+  float * w;          // [32] softmax weights of the tile
+  float * stat;       // [8]  m, sum of weights
+  float * D, * px, * py;        // [N] arc-length prefix and points of the path
+  uint8_t * valid, * flags;     // [n16]
+  uint16_t * follow;            // [N]
+  float * e;          // [G] rescale factors of the merge
+  float * red;        // [32] block reductions
+};
+__host__ __device__ inline size_t fused_extra_floats(int N, int G)
+{
+  const int n16 = ((N + 15) / 16) * 16;
+  return static_cast<size_t>(kMaxCritics + kGammaRows) * kTile + 4 * kTile + kTile + 8 + 3 * static_cast<size_t>(n16) +
+         n16 / 2 /* valid + flags bytes */ + n16 / 2 /* follow uint16 */ + static_cast<size_t>(((G + 31) / 32) * 32) + 32;
+}
+__host__ __device__ inline size_t fused_smem_bytes(int T, int S, int N, int G)
+{
+  return sizeof(float) * (rollout_smem_floats(T, S, 6) + fused_extra_floats(N, G));
+}
+__device__ __forceinline__ FusedShared fused_carve(float * base, int N, int G)
+{
+  const int n16 = ((N + 15) / 16) * 16;
+  FusedShared f;
+  f.rows = base;
+  f.term = f.rows + (kMaxCritics + kGammaRows) * kTile;
+  f.w = f.term + 4 * kTile;
+  f.stat = f.w + kTile;
+  f.D = f.stat + 8;
+  f.px = f.D + n16;
+  f.py = f.px + n16;
+  f.valid = reinterpret_cast<uint8_t *>(f.py + n16);
+  f.flags = f.valid + n16;
+  f.follow = reinterpret_cast<uint16_t *>(f.flags + n16);
+  f.e = reinterpret_cast<float *>(f.follow + n16);
+  f.red = f.e + ((G + 31) / 32) * 32;
+  return f;
+}
+// what the K2 body hands to the fused tail
+struct FusedCtx
+{
+  FusedShared fs;
+  const float * s_hot, * s_cs;
+  const float * s_cvx, * s_cvy, * s_cwz, * s_yaw, * s_x, * s_y;   // time-major tile planes [T][33]
+  int N, iteration;
+};
 
 // ---------------------------------------------------------------------------------------------------
 // K1: Philox4x32-10 + Box-Muller.  One thread = one trajectory x one quad of time steps x 3 planes;
@@ -178,11 +233,12 @@ __global__ void advance_epoch_kernel(unsigned long long * d_epoch) {*d_epoch += 
 #define MPPI_TILE_CHUNK 1
 #endif
 constexpr int kTileChunk = MPPI_TILE_CHUNK;   // steps whose independent work is issued together inside a segment
-template<unsigned F, bool kExact, int kMode>
-__global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
-  const DevParams * __restrict__ P, const uint8_t * __restrict__ cm, DevBuffers bufs, const int B, const int T)
+template<unsigned F, bool kExact, int kMode, bool kFused>
+__device__ __forceinline__ void rollout_tile_body(
+  const DevParams * __restrict__ P, const uint8_t * __restrict__ cm, const DevBuffers & bufs, const int B, const int T, FusedCtx * fx)
 {
   constexpr int mode = kMode;   // 0 rollout from noise, 1 injected state (integrate), 2 injected state + trajectories
+  static_assert(!kFused || kMode == 0, "the fused kernel only exists for the rollout-from-noise mode");
   // B, T and mode also live in the record, but as launch arguments they cost no memory round trip: the noise rows,
   // the control sequence and the record are all requested at once when the kernel starts
   extern __shared__ float smem[];
@@ -200,11 +256,19 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
   float * s_cvy = s_cvx + tplane;                // controls vy  -> (rollout modes) y
   float * s_cwz = s_cvy + tplane;                // controls wz
   float * s_yaw = s_cwz + tplane;
-  float * s_x = mode == 2 ? s_yaw + tplane : s_cvx;
-  float * s_y = mode == 2 ? s_x + tplane : s_cvy;
-  float * s_acc = s_yaw + tplane * (mode == 2 ? 3 : 1);   // [S][A_COUNT][32]
+  constexpr bool kSixPlanes = mode == 2 || kFused;   // x and y beside the controls (the fused tail re-reads the controls)
+  float * s_x = kSixPlanes ? s_yaw + tplane : s_cvx;
+  float * s_y = kSixPlanes ? s_x + tplane : s_cvy;
+  float * s_acc = s_yaw + tplane * (kSixPlanes ? 3 : 1);   // [S][A_COUNT][32]
   float * s_amin_d = s_acc + S * A_COUNT * kTile;         // [S][32]
   int * s_amin_j = reinterpret_cast<int *>(s_amin_d + S * kTile);
+  FusedShared fs = {};
+  if (kFused) {
+    fs = fused_carve(reinterpret_cast<float *>(s_amin_j + S * kTile), fx->N, gridDim.x);
+    fx->fs = fs;
+    fx->s_hot = s_hot; fx->s_cs = s_cs; fx->s_cvx = s_cvx; fx->s_cvy = s_cvy; fx->s_cwz = s_cwz; fx->s_yaw = s_yaw;
+    fx->s_x = s_x; fx->s_y = s_y;
+  }
 
   const int b0 = blockIdx.x * kTile;
   const int b = b0 + lane;
@@ -240,6 +304,17 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
     }
   }
   MPPI_TRACE_AT(1);
+  if (kFused) {
+    // the path and its host-made tables (record tail, build_params): x[N] y[N] yaw[N] D[N] | valid[n16] flags[n16] follow[N]
+    const int N = fx->N, n16 = ((N + 15) / 16) * 16;
+    const float * tail = reinterpret_cast<const float *>(P + 1);
+    const uint8_t * g_valid = reinterpret_cast<const uint8_t *>(tail + 4 * N);
+    const uint16_t * g_follow = reinterpret_cast<const uint16_t *>(g_valid + 2 * n16);
+    for (int j = tid; j < N; j += nthreads) {
+      fs.D[j] = __ldg(tail + 3 * N + j); fs.px[j] = __ldg(tail + j); fs.py[j] = __ldg(tail + N + j);
+      fs.valid[j] = __ldg(g_valid + j); fs.flags[j] = __ldg(g_valid + n16 + j); fs.follow[j] = __ldg(g_follow + j);
+    }
+  }
   for (int i = tid; i < 3 * T; i += nthreads) {s_cs[i] = bufs.cs[i];}
   // hot part of the per-cycle record -> shared memory (one coalesced round trip instead of scattered loads)
   load_hot_params(s_hot, P, tid, nthreads);
@@ -523,8 +598,8 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
             }
           }
         }
-        // spills for the path critics of K3
-        if (t == next_sample) {
+        // spills for the path critics of K3 (the fused tail reads the poses straight from the tile)
+        if (!kFused && t == next_sample) {
           const size_t k = static_cast<size_t>(sample_k) * B + b;
           bufs.samples_x[k] = px;
           bufs.samples_y[k] = py;
@@ -543,7 +618,7 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
         g += B;
       }
     }
-    if (t1 == T && t0 < t1) {
+    if (!kFused && t1 == T && t0 < t1) {
       bufs.end_xy[b] = s_x[(T - 1) * kPad + lane];
       bufs.end_xy[B + b] = s_y[(T - 1) * kPad + lane];
     }
@@ -601,25 +676,30 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
     }
     const float Tf = static_cast<float>(T);
     float * rows = bufs.crit_rows;
+    // a row goes to global memory for K3 (and the per-critic getter); the fused tail takes it from shared memory
+    const bool rows_to_global = !kFused || p.want_critic_rows != 0;
+    auto put = [&](int q, float v) {
+        if (kFused) {fs.rows[q * kTile + lane] = v;}
+        if (rows_to_global) {rows[static_cast<size_t>(q) * B + b] = v;}
+      };
     if (live) {
-      if (con_on) {rows[static_cast<size_t>(p.constraint.idx) * B + b] = add_pow(0.0f, tot[A_CON] * p.constraint.weight, p.constraint.power);}
-      if (fwd_on) {rows[static_cast<size_t>(p.forward.idx) * B + b] = add_pow(0.0f, tot[A_FWD] * p.forward.weight, p.forward.power);}
-      if (twirl_on) {rows[static_cast<size_t>(p.twirl.idx) * B + b] = add_pow(0.0f, (tot[A_TWIRL] / Tf) * p.twirl.weight, p.twirl.power);}
-      if (db_on) {rows[static_cast<size_t>(p.deadband.idx) * B + b] = add_pow(0.0f, tot[A_DB] * p.deadband.weight, p.deadband.power);}
-      if (goal_on) {rows[static_cast<size_t>(p.goal.idx) * B + b] = add_pow(0.0f, (tot[A_GOAL] / Tf) * p.goal.weight, p.goal.power);}
-      if (gang_on) {rows[static_cast<size_t>(p.goal_angle.idx) * B + b] = add_pow(0.0f, (tot[A_GANG] / Tf) * p.goal_angle.weight, p.goal_angle.power);}
+      if (con_on) {put(p.constraint.idx, add_pow(0.0f, tot[A_CON] * p.constraint.weight, p.constraint.power));}
+      if (fwd_on) {put(p.forward.idx, add_pow(0.0f, tot[A_FWD] * p.forward.weight, p.forward.power));}
+      if (twirl_on) {put(p.twirl.idx, add_pow(0.0f, (tot[A_TWIRL] / Tf) * p.twirl.weight, p.twirl.power));}
+      if (db_on) {put(p.deadband.idx, add_pow(0.0f, tot[A_DB] * p.deadband.weight, p.deadband.power));}
+      if (goal_on) {put(p.goal.idx, add_pow(0.0f, (tot[A_GOAL] / Tf) * p.goal.weight, p.goal.power));}
+      if (gang_on) {put(p.goal_angle.idx, add_pow(0.0f, (tot[A_GANG] / Tf) * p.goal_angle.weight, p.goal_angle.power));}
       if (cost_on) {   // cost_critic.cpp:159-166
         const float rep = cost_collided ? p.cost_collision : tot[A_COST_REP];
-        rows[static_cast<size_t>(p.cost.idx) * B + b] = add_pow(0.0f, p.cost.weight * rep / Tf, p.cost.power);
+        put(p.cost.idx, add_pow(0.0f, p.cost.weight * rep / Tf, p.cost.power));
       }
       if (ob_on) {   // obstacles_critic.cpp:169-176
         const float raw = ob_collided ? p.obst_collision : tot[A_OB_TRAJ];
         const float v = (p.obst_critical_w * raw) + (p.obst_repulsion_w * tot[A_OB_REP] / Tf);
-        rows[static_cast<size_t>(p.obst.idx) * B + b] = add_pow(0.0f, v, p.obst.power);
+        put(p.obst.idx, add_pow(0.0f, v, p.obst.power));
       }
       if (mode == 0) {
-        const size_t g = static_cast<size_t>(p.n_critics) * B + b;
-        rows[g] = tot[A_GVX]; rows[g + B] = tot[A_GVY]; rows[g + 2 * static_cast<size_t>(B)] = tot[A_GWZ];
+        put(p.n_critics, tot[A_GVX]); put(p.n_critics + 1, tot[A_GVY]); put(p.n_critics + 2, tot[A_GWZ]);
       }
     }
     // fail_flag inputs: did any trajectory of this tile survive?
@@ -643,6 +723,13 @@ __global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
     }
   }
   MPPI_TRACE_AT(9);
+}
+
+template<unsigned F, bool kExact, int kMode>
+__global__ void __launch_bounds__(256, MPPI_K2_MIN_BLOCKS) rollout_score_kernel(
+  const DevParams * __restrict__ P, const uint8_t * __restrict__ cm, DevBuffers bufs, const int B, const int T)
+{
+  rollout_tile_body<F, kExact, kMode, false>(P, cm, bufs, B, T, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1062,6 +1149,48 @@ struct K3Path
   const uint8_t * s_valid;         // shared: path point validity (utils::findPathCosts, host decided)
 };
 
+// The decisions themselves (one thread).  any_ok / state = {furthest_candidate, furthest, furthest_set, fail_flag} are this
+// pass's reductions over all trajectories (after exchange 1 when sharded); flags / follow are the host-made tables indexed
+// by the furthest reached path point (build_params).
+__device__ __forceinline__ void k3_decide(
+  const DevParams * P, int N, const unsigned * any_ok, const unsigned * state, const uint8_t * s_flags, const uint16_t * s_follow,
+  int iteration, K3Decisions * dec)
+{
+  const int nc = P->n_critics;
+  // CriticManager::evalTrajectoriesScores (critic_manager.cpp:67-76): the first obstacle-type critic (list order)
+  // that saw no surviving trajectory raises fail_flag; critics after it are skipped
+  int fail_at = nc;
+  if (iteration > 0 && state[3]) {
+    fail_at = -1;     // fail_flag is only cleared in prepare(): a failed iteration mutes the following ones
+  } else {
+    const int q0 = P->obstacle_q[0], q1 = P->obstacle_q[1];
+    if (q0 >= 0 && any_ok[q0] == 0u) {
+      fail_at = q0;
+    } else if (q1 >= 0 && any_ok[q1] == 0u) {
+      fail_at = q1;
+    }
+  }
+  unsigned furthest;
+  int fset;
+  if (iteration == 0) {
+    fset = P->preset_furthest != kUnset; furthest = fset ? P->preset_furthest : 0u;
+  } else {
+    fset = static_cast<int>(state[2]); furthest = state[1];
+  }
+  // the first enabled path critic in list order calls setPathFurthestPointIfNotSet (utils.hpp:350-355)
+  if (!fset && P->first_path_q >= 0 && P->first_path_q <= fail_at) {furthest = state[0]; fset = 1;}
+  const int f = min(static_cast<int>(furthest), N - 1);
+  const unsigned flags = s_flags[f];
+  dec->fail_at = fail_at;
+  dec->furthest = static_cast<int>(furthest);
+  dec->furthest_set = fset;
+  dec->follow_idx = (P->follow.on && P->follow.idx <= fail_at) ? s_follow[f] : 0;
+  dec->align_go = (P->align.on && P->align.idx <= fail_at && (flags & 1u)) ? 1 : 0;
+  dec->legacy_go = (P->legacy.on && P->legacy.idx <= fail_at && (flags & 2u)) ? 1 : 0;
+  dec->angle_go = (P->angle.on && P->angle.idx <= fail_at && (flags & 4u)) ? 1 : 0;
+  dec->angle_idx = min(static_cast<int>(furthest) + P->angle_offset, N - 1);
+}
+
 // Copies the hot record, the path and its host-made tables into shared memory and lets thread 0 take the decisions.
 // Memory round trips are the cost here (a cold record is ~1 us away), so everything is requested in one wave.  The
 // decisions that depend on device results (which critic failed, the furthest reached point) are a handful of
@@ -1127,48 +1256,7 @@ __device__ __forceinline__ void k3_preamble(
   MPPI_TRACE_AT(24);
   __syncthreads();
   MPPI_TRACE_AT(25);
-#ifdef MPPI_TRACE
-  for (int rep = 0; rep < 2; ++rep) {
-  MPPI_TRACE_AT(27 + rep);
-#endif
-  if (tid == 0) {
-    const int nc = P->n_critics;
-    // CriticManager::evalTrajectoriesScores (critic_manager.cpp:67-76): the first obstacle-type critic (list order)
-    // that saw no surviving trajectory raises fail_flag; critics after it are skipped
-    int fail_at = nc;
-    if (iteration > 0 && s_state[3]) {
-      fail_at = -1;     // fail_flag is only cleared in prepare(): a failed iteration mutes the following ones
-    } else {
-      const int q0 = P->obstacle_q[0], q1 = P->obstacle_q[1];
-      if (q0 >= 0 && s_any_ok[q0] == 0u) {
-        fail_at = q0;
-      } else if (q1 >= 0 && s_any_ok[q1] == 0u) {
-        fail_at = q1;
-      }
-    }
-    unsigned furthest;
-    int fset;
-    if (iteration == 0) {
-      fset = P->preset_furthest != kUnset; furthest = fset ? P->preset_furthest : 0u;
-    } else {
-      fset = static_cast<int>(s_state[2]); furthest = s_state[1];
-    }
-    // the first enabled path critic in list order calls setPathFurthestPointIfNotSet (utils.hpp:350-355)
-    if (!fset && P->first_path_q >= 0 && P->first_path_q <= fail_at) {furthest = s_state[0]; fset = 1;}
-    const int f = min(static_cast<int>(furthest), N - 1);
-    const unsigned flags = s_flags[f];
-    dec->fail_at = fail_at;
-    dec->furthest = static_cast<int>(furthest);
-    dec->furthest_set = fset;
-    dec->follow_idx = (P->follow.on && P->follow.idx <= fail_at) ? s_follow[f] : 0;
-    dec->align_go = (P->align.on && P->align.idx <= fail_at && (flags & 1u)) ? 1 : 0;
-    dec->legacy_go = (P->legacy.on && P->legacy.idx <= fail_at && (flags & 2u)) ? 1 : 0;
-    dec->angle_go = (P->angle.on && P->angle.idx <= fail_at && (flags & 4u)) ? 1 : 0;
-    dec->angle_idx = min(static_cast<int>(furthest) + P->angle_offset, N - 1);
-  }
-#ifdef MPPI_TRACE
-  }
-#endif
+  if (tid == 0) {k3_decide(P, N, s_any_ok, s_state, s_flags, s_follow, iteration, dec);}
   MPPI_TRACE_AT(26);
   __syncthreads();
 }
@@ -1549,6 +1637,395 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
     finalize_controls(P, merged, bufs.cs, bufs.out, tid, kUpdThreads);
   }
   MPPI_TRACE_AT(22);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fused small-batch kernel: K2, the furthest-point / survivor reduction, K3 and the merge in ONE cooperative launch.
+// At the default 1000 x 56 the two-kernel cycle is bound by what surrounds the arithmetic: a launch boundary, a second
+// cold start (record, path tables, noise rows requested again), K2's results making a round trip through global memory,
+// and a serial per-trajectory walk of the path critics by one warp per block.  Here a block keeps its tile of 32
+// trajectories in shared memory from the first noise load to the block's softmax record:
+//   K2 body (rollout_tile_body, six planes: the noised controls survive beside x, y, yaw)
+//   grid barrier 1   = exchange 1 inside the GPU: furthest-point candidate and survivor flags of ALL tiles are in
+//   decisions          (k3_decide, one thread)
+//   path critics       one WARP per trajectory, lane = sampled pose (PathAlign, PathAlignLegacy) or time step (PathAngle);
+//                      the two carried dependences of PathAlign (integrated distance, previous path point) run as
+//                      shuffle chains of one add / one compare per sample, everything else is lane-parallel
+//   totals, weights    warp 0, lane = trajectory, critic-list order with the fail_flag short-circuit + gamma term
+//   weighted sums      all threads over the 3T columns, out of the tile
+//   grid barrier 2   = the softmax records of all tiles are in
+//   merge + clip       block t owns time steps t, t + G, ...: one warp per column over the records, redundant min
+// The barriers count arrivals in DevState::bar (64 bit, monotone); the launch is cooperative, so all blocks are
+// co-resident and the bounded spin never fires in normal operation.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long * p)
+{
+  unsigned long long v;
+  asm volatile ("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void grid_barrier(DevState * st, unsigned nblocks, bool leader)
+{
+  __syncthreads();
+  if (leader) {
+    __threadfence();
+    const unsigned long long old = atomicAdd(&st->bar, 1ull);
+    const unsigned long long target = (old / nblocks + 1ull) * nblocks;
+    const long long t0 = clock64();
+    while (ld_acquire_u64(&st->bar) < target) {
+      if (clock64() - t0 > kSpinLimitCycles) {st->comm_error = 1u; break;}
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// PathAlignCritic::score (path_align_critic.cpp:92-135) for trajectory r of the tile, by one warp; lane = sampled pose.
+__device__ __forceinline__ float path_align_warp(
+  const DevParams * P, const FusedCtx & fx, int r, int furthest, const float * __restrict__ path_yaw, int lane)
+{
+  const int T = P->T, step = P->align_step;
+  const int n_s = (T + step - 1) / step;     // sampled poses p = 0, step, 2 step, ... < T
+  const int n = furthest;                    // the arc-length prefix D[0, n) is searched
+  const float * D = fx.fs.D;
+  float carry_d = 0.0f, summed = 0.0f;
+  int carry_pt = 0, num = 0;
+  for (int k0 = 1; k0 < n_s; k0 += 32) {
+    const int k = k0 + lane;
+    const bool act = k < n_s;
+    const int o = (act ? k : k0) * step * kPad + r;       // idle lanes shadow a valid sample
+    const float Tx = fx.s_x[o], Ty = fx.s_y[o];
+    const float dxp = __fsub_rn(Tx, fx.s_x[o - step * kPad]), dyp = __fsub_rn(Ty, fx.s_y[o - step * kPad]);
+    const float d = act ? __fsqrt_rn(__fadd_rn(__fmul_rn(dxp, dxp), __fmul_rn(dyp, dyp))) : 0.0f;
+    const int cnt = min(32, n_s - k0);
+    // traj_integrated_distance: the reference's sequential fp32 sum, every lane follows the same chain
+    float acc = carry_d, mine = 0.0f;
+    for (int j = 0; j < cnt; ++j) {
+      acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, d, j));
+      if (lane == j) {mine = acc;}
+    }
+    carry_d = acc;
+    // utils::findClosestPathPt (utils.hpp:665-675) = lower_bound over [init, n) with init = the previous answer.
+    // c = lower_bound over the whole prefix does not depend on init: the answer is 0 when c <= init, else
+    // g = n - 1 (c == n) or the nearer of c - 1 and c.
+    int lo = 0, hi = n;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (D[mid] < mine) {lo = mid + 1;} else {hi = mid;}
+    }
+    const int c = lo;
+    int g = 0;
+    if (c > 0) {
+      if (c >= n) {
+        g = n - 1;
+      } else {
+        g = __fsub_rn(mine, D[c - 1]) < __fsub_rn(D[c], mine) ? c - 1 : c;
+      }
+    }
+    int prev = carry_pt, res = 0;
+    for (int j = 0; j < cnt; ++j) {
+      const int cj = __shfl_sync(0xffffffffu, c, j), gj = __shfl_sync(0xffffffffu, g, j);
+      const int cur = cj <= prev ? 0 : gj;
+      if (lane == j) {res = cur;}
+      prev = cur;
+    }
+    carry_pt = prev;
+    const bool ok = act && fx.fs.valid[res] != 0;
+    float term = 0.0f;
+    if (ok) {
+      const float dx = __fsub_rn(fx.fs.px[res], Tx), dy = __fsub_rn(fx.fs.py[res], Ty);
+      // the distance itself only feeds the cost (1e-4 tolerance): one MUFU instead of the IEEE sequence
+      if (P->align_use_yaw) {
+        const float dyaw = static_cast<float>(normalize_angle_d(static_cast<double>(fx.s_yaw[o]) - static_cast<double>(__ldg(path_yaw + res))));
+        term = sqrt_approx(dx * dx + dy * dy + dyaw * dyaw);
+      } else {
+        term = sqrt_approx(dx * dx + dy * dy);
+      }
+    }
+    num += __popc(__ballot_sync(0xffffffffu, ok));
+    summed += warp_sum(term);
+  }
+  const float cost = num > 0 ? __fdiv_rn(summed, static_cast<float>(num)) : 0.0f;
+  return add_pow(0.0f, __fmul_rn(cost, P->align.weight), P->align.power);
+}
+
+// PathAlignLegacyCritic::score (path_align_legacy_critic.cpp:97-128) for trajectory r, by one warp; lane = sampled pose
+__device__ __forceinline__ float path_align_legacy_warp(
+  const DevParams * P, const FusedCtx & fx, int r, const float * __restrict__ path_yaw, int lane)
+{
+  const int T = P->T, step = P->legacy_step, segs = P->N - 1;
+  float summed = 0.0f;
+  for (int p0 = step; p0 < T; p0 += 32 * step) {
+    const int p = p0 + lane * step;
+    float contrib = 0.0f;
+    if (p < T) {
+      const int o = p * kPad + r;
+      const float Tx = fx.s_x[o], Ty = fx.s_y[o];
+      const float Tyaw = P->legacy_use_yaw ? fx.s_yaw[o] : 0.0f;
+      float min_d = 3.402823466e+38f;
+      int min_s = 0;
+      for (int sgm = 0; sgm < segs - 1; ++sgm) {
+        const float dx = __fsub_rn(fx.fs.px[sgm], Tx);
+        const float dy = __fsub_rn(fx.fs.py[sgm], Ty);
+        float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        if (P->legacy_use_yaw) {
+          const float dyaw = static_cast<float>(normalize_angle_d(static_cast<double>(Tyaw) - static_cast<double>(__ldg(path_yaw + sgm))));
+          d = __fadd_rn(d, __fmul_rn(dyaw, dyaw));
+        }
+        if (d < min_d) {min_d = d; min_s = sgm;}
+      }
+      if (min_s != 0 && fx.fs.valid[min_s]) {contrib = __fsqrt_rn(min_d);}
+    }
+    summed += warp_sum(contrib);
+  }
+  const float evals = static_cast<float>(T / step);
+  return add_pow(0.0f, __fmul_rn(__fdiv_rn(summed, evals), P->legacy.weight), P->legacy.power);
+}
+
+// PathAngleCritic::score (path_angle_critic.cpp:85-100) for trajectory r, by one warp; lane = time step
+__device__ __forceinline__ float path_angle_warp(const DevParams * P, const FusedCtx & fx, int r, int angle_idx, int lane)
+{
+  const int T = P->T;
+  const float gx = fx.fs.px[angle_idx], gy = fx.fs.py[angle_idx];
+  float sum = 0.0f;
+  for (int t = lane; t < T; t += 32) {
+    const int o = t * kPad + r;
+    const float x = fx.s_x[o], y = fx.s_y[o], yaw = fx.s_yaw[o];
+    const float ybp = atan2f(__fsub_rn(gy, y), __fsub_rn(gx, x));
+    double v = fabs(normalize_angle_d(static_cast<double>(__fsub_rn(ybp, yaw))));
+    if (P->angle_reversing && !P->angle_forward_pref) {
+      const double corrected = v < 1.57079632679489661923 ? static_cast<double>(ybp) :
+        normalize_angle_d(static_cast<double>(ybp) + 3.14159265358979323846);
+      v = fabs(normalize_angle_d(corrected - static_cast<double>(yaw)));
+    }
+    sum += static_cast<float>(v);
+  }
+  sum = warp_sum(sum);
+  return add_pow(0.0f, (sum / static_cast<float>(T)) * P->angle.weight, P->angle.power);
+}
+
+template<unsigned F, bool kExact>
+__global__ void __launch_bounds__(256, 2) tile_fused_kernel(
+  const DevParams * __restrict__ Pg, const uint8_t * __restrict__ cm, DevBuffers bufs, const int B, const int T, const int N,
+  const int iteration)
+{
+  __shared__ K3Decisions dec;
+  FusedCtx fx;
+  fx.N = N; fx.iteration = iteration;
+  rollout_tile_body<F, kExact, 0, true>(Pg, cm, bufs, B, T, &fx);
+
+  const int S = blockDim.y, lane = threadIdx.x, seg = threadIdx.y;
+  const int tid = seg * kTile + lane, nthr = S * kTile;
+  const FusedShared & fs = fx.fs;
+  const DevParams * P = reinterpret_cast<const DevParams *>(fx.s_hot);   // hot fields only
+  DevState * st = bufs.st;
+  const int G = gridDim.x;
+  const int b0 = blockIdx.x * kTile;
+  const int rows_here = min(kTile, B - b0);
+  const float * __restrict__ path_yaw = reinterpret_cast<const float *>(Pg + 1) + 2 * N;
+
+  // ---- exchange 1 inside the GPU: every tile's furthest-point candidate and survivor flags are in after this barrier
+  grid_barrier(st, G, tid == 0);
+  MPPI_TRACE_AT(10);
+  if (tid == 0) {
+    unsigned any_ok[kMaxCritics], state[4];
+#pragma unroll
+    for (int q = 0; q < kMaxCritics; ++q) {any_ok[q] = ld_volatile_u32(&st->any_ok[q]);}
+    state[0] = ld_volatile_u32(&st->furthest_candidate);
+    state[1] = ld_volatile_u32(&st->furthest);
+    state[2] = ld_volatile_u32(reinterpret_cast<const unsigned *>(&st->furthest_set));
+    state[3] = ld_volatile_u32(reinterpret_cast<const unsigned *>(&st->fail_flag));
+    k3_decide(P, N, any_ok, state, fs.flags, fs.follow, iteration, &dec);
+  }
+  __syncthreads();
+  MPPI_TRACE_AT(11);
+
+  // ---- path critics that need more than the end pose: one warp per trajectory
+  if (dec.align_go || dec.legacy_go || dec.angle_go) {
+    for (int r = seg; r < rows_here; r += S) {
+      if (dec.align_go) {
+        const float v = path_align_warp(P, fx, r, dec.furthest, path_yaw, lane);
+        if (lane == 0) {fs.term[1 * kTile + r] = v;}
+      }
+      if (dec.legacy_go) {
+        const float v = path_align_legacy_warp(P, fx, r, path_yaw, lane);
+        if (lane == 0) {fs.term[2 * kTile + r] = v;}
+      }
+      if (dec.angle_go) {
+        const float v = path_angle_warp(P, fx, r, dec.angle_idx, lane);
+        if (lane == 0) {fs.term[3 * kTile + r] = v;}
+      }
+    }
+  }
+  __syncthreads();
+  MPPI_TRACE_AT(12);
+
+  // ---- totals in critic-list order with the fail_flag short-circuit (critic_manager.cpp:67-76), gamma term,
+  //      block-local softmax record (optimizer.cpp:362-391); warp 0, lane = trajectory
+  const float inv_temp = 1.0f / P->temperature;
+  if (seg == 0) {
+    const int b = b0 + lane;
+    const bool live = b < B;
+    const int nc = P->n_critics, fail_at = dec.fail_at;
+    float total = 3.402823466e+38f;
+    if (live) {
+      total = iteration == 0 ? 0.0f : bufs.costs[b];
+      float * rows = bufs.crit_rows;
+      for (int q = 0; q < nc; ++q) {
+        if (q > fail_at) {break;}
+        const int kind = P->kind_of[q];
+        float term = 0.0f;
+        bool has = false, from_path = true;
+        switch (kind) {
+          case MPPI_CRITIC_PATH_FOLLOW:
+            if (P->follow.on) {    // path_follow_critic.cpp:60-70
+              const float dx = fx.s_x[(T - 1) * kPad + lane] - fs.px[dec.follow_idx];
+              const float dy = fx.s_y[(T - 1) * kPad + lane] - fs.py[dec.follow_idx];
+              term = add_pow(0.0f, P->follow.weight * sqrtf(dx * dx + dy * dy), P->follow.power);
+              has = true;
+            }
+            break;
+          case MPPI_CRITIC_PATH_ALIGN: if (dec.align_go) {term = fs.term[1 * kTile + lane]; has = true;} break;
+          case MPPI_CRITIC_PATH_ALIGN_LEGACY: if (dec.legacy_go) {term = fs.term[2 * kTile + lane]; has = true;} break;
+          case MPPI_CRITIC_PATH_ANGLE: if (dec.angle_go) {term = fs.term[3 * kTile + lane]; has = true;} break;
+          case MPPI_CRITIC_CONSTRAINT: has = P->constraint.on; from_path = false; break;
+          case MPPI_CRITIC_COST: has = P->cost.on; from_path = false; break;
+          case MPPI_CRITIC_GOAL: has = P->goal.on; from_path = false; break;
+          case MPPI_CRITIC_GOAL_ANGLE: has = P->goal_angle.on; from_path = false; break;
+          case MPPI_CRITIC_OBSTACLES: has = P->obst.on; from_path = false; break;
+          case MPPI_CRITIC_PREFER_FORWARD: has = P->forward.on; from_path = false; break;
+          case MPPI_CRITIC_TWIRLING: has = P->twirl.on; from_path = false; break;
+          case MPPI_CRITIC_VELOCITY_DEADBAND: has = P->deadband.on; from_path = false; break;
+          default: from_path = false; break;
+        }
+        if (from_path) {
+          if (P->want_critic_rows) {rows[static_cast<size_t>(q) * B + b] = term;}   // for the per-critic getter
+        } else if (has) {
+          term = fs.rows[q * kTile + lane];
+        }
+        if (has) {total = __fadd_rn(total, term);}
+      }
+      if (P->want_critic_rows) {
+        // rows of critics that did not run read as zero for the per-critic getter (mppi_get_critic_costs)
+        for (int q = 0; q < nc; ++q) {
+          const int kind = P->kind_of[q];
+          const bool from_path = kind == MPPI_CRITIC_PATH_FOLLOW || kind == MPPI_CRITIC_PATH_ALIGN ||
+            kind == MPPI_CRITIC_PATH_ALIGN_LEGACY || kind == MPPI_CRITIC_PATH_ANGLE;
+          bool on = false;
+          switch (kind) {
+            case MPPI_CRITIC_CONSTRAINT: on = P->constraint.on; break;
+            case MPPI_CRITIC_COST: on = P->cost.on; break;
+            case MPPI_CRITIC_GOAL: on = P->goal.on; break;
+            case MPPI_CRITIC_GOAL_ANGLE: on = P->goal_angle.on; break;
+            case MPPI_CRITIC_OBSTACLES: on = P->obst.on; break;
+            case MPPI_CRITIC_PREFER_FORWARD: on = P->forward.on; break;
+            case MPPI_CRITIC_TWIRLING: on = P->twirl.on; break;
+            case MPPI_CRITIC_VELOCITY_DEADBAND: on = P->deadband.on; break;
+            default: break;
+          }
+          if (q > fail_at || (!from_path && !on)) {rows[static_cast<size_t>(q) * B + b] = 0.0f;}
+        }
+      }
+      // gamma term (optimizer.cpp:367-380): vx, then wz, then vy (holonomic)
+      total = __fadd_rn(total, __fmul_rn(P->gamma_vx, fs.rows[nc * kTile + lane]));
+      total = __fadd_rn(total, __fmul_rn(P->gamma_wz, fs.rows[(nc + 2) * kTile + lane]));
+      if (P->holonomic) {total = __fadd_rn(total, __fmul_rn(P->gamma_vy, fs.rows[(nc + 1) * kTile + lane]));}
+      bufs.costs[b] = total;
+    }
+    // optimizer.cpp:382-391 on this tile: m = min, w = exp(-(c - m) / temperature), s = sum w
+    const float m = warp_min(total);
+    const float w_b = live ? expf(-(total - m) * inv_temp) : 0.0f;
+    const float ssum = warp_sum(w_b);
+    fs.w[lane] = w_b;
+    if (lane == 0) {fs.stat[0] = m; fs.stat[1] = ssum;}
+  }
+  __syncthreads();
+  MPPI_TRACE_AT(13);
+
+  // ---- weighted column sums of the tile, W[c] = sum_r w_r * c[r][c], out of the noised controls still in the tile
+  const int stride = 3 * T + 2;
+  float * part = bufs.partials + static_cast<size_t>(blockIdx.x) * stride;
+  for (int c = tid; c < 3 * T; c += nthr) {
+    const int plane = c / T, t = c - plane * T;
+    const float * col = (plane == 0 ? fx.s_cvx : (plane == 1 ? fx.s_cvy : fx.s_cwz)) + t * kPad;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    int r = 0;
+    for (; r + 3 < rows_here; r += 4) {
+      a0 = fmaf(fs.w[r], col[r], a0);
+      a1 = fmaf(fs.w[r + 1], col[r + 1], a1);
+      a2 = fmaf(fs.w[r + 2], col[r + 2], a2);
+      a3 = fmaf(fs.w[r + 3], col[r + 3], a3);
+    }
+    for (; r < rows_here; ++r) {a0 = fmaf(fs.w[r], col[r], a0);}
+    part[2 + c] = (a0 + a1) + (a2 + a3);
+  }
+  if (tid == 0) {part[0] = fs.stat[0]; part[1] = fs.stat[1];}
+
+  // ---- exchange 2 inside the GPU: every tile's softmax record is in after this barrier
+  grid_barrier(st, G, tid == 0);
+  MPPI_TRACE_AT(14);
+  if (blockIdx.x == 0 && tid == 0) {k3_publish_flags(P, st, dec, bufs.out);}
+  if (static_cast<int>(blockIdx.x) >= T) {return;}   // owns no time step
+  // global minimum and the rescale factor of every record (redundant per block: G loads)
+  const float * parts = bufs.partials;
+  float m = 3.402823466e+38f;
+  for (int i = tid; i < G; i += nthr) {
+    const float mi = __ldcg(parts + static_cast<size_t>(i) * stride);
+    fs.e[i] = mi;
+    m = fminf(m, mi);
+  }
+  m = warp_min(m);
+  if (lane == 0) {fs.red[seg] = m;}
+  __syncthreads();
+  m = fs.red[0];
+  for (int w = 1; w < S; ++w) {m = fminf(m, fs.red[w]);}
+  __syncthreads();
+  for (int i = tid; i < G; i += nthr) {fs.e[i] = expf(-(fs.e[i] - m) * inv_temp);}
+  __syncthreads();
+  // column 0 = sum of the weights; then (vx, vy, wz) of every owned time step: one warp per column, lanes over the records
+  const int n_own = (T - static_cast<int>(blockIdx.x) + G - 1) / G;
+  float * col_out = fs.red + 8;   // [1 + 3 n_own] <= 24 entries for n_own <= 7; larger counts loop in rounds below
+  for (int t_base = 0; t_base < n_own; t_base += 7) {
+    const int n_now = min(7, n_own - t_base);
+    for (int k = seg; k < 1 + 3 * n_now; k += S) {
+      int col;
+      if (k == 0) {
+        col = 0;
+      } else {
+        const int t = static_cast<int>(blockIdx.x) + (t_base + (k - 1) / 3) * G, plane = (k - 1) % 3;
+        col = 1 + plane * T + t;
+      }
+      float acc = 0.0f;
+      for (int i = lane; i < G; i += 32) {acc = fmaf(__ldcg(parts + static_cast<size_t>(i) * stride + 1 + col), fs.e[i], acc);}
+      acc = warp_sum(acc);
+      if (lane == 0) {col_out[k] = acc;}
+    }
+    __syncthreads();
+    if (tid < n_now) {
+      // cs = W / sum, then applyControlSequenceConstraints (optimizer.cpp:237-249)
+      const int t = static_cast<int>(blockIdx.x) + (t_base + tid) * G;
+      const float ssum = col_out[0];
+      float vx = col_out[1 + 3 * tid] / ssum, wz = col_out[3 + 3 * tid] / ssum, vy = fx.s_cs[T + t];
+      if (P->holonomic) {
+        vy = col_out[2 + 3 * tid] / ssum;
+        vy = fminf(fmaxf(vy, -P->c_vy), P->c_vy);
+      }
+      vx = fminf(fmaxf(vx, P->c_vx_min), P->c_vx_max);
+      wz = fminf(fmaxf(wz, -P->c_wz), P->c_wz);
+      if (P->model == MPPI_MODEL_ACKERMANN) {   // motion_models.hpp:110-117
+        const float rr = P->min_turning_r;
+        if (fabsf(vx) / fabsf(wz) < rr) {
+          const float sgn = wz > 0.0f ? 1.0f : (wz < 0.0f ? -1.0f : 0.0f);
+          wz = sgn * fabsf(vx) / rr;
+        }
+      }
+      bufs.cs[t] = vx; bufs.cs[T + t] = vy; bufs.cs[2 * T + t] = wz;
+      bufs.out[t] = vx; bufs.out[T + t] = vy; bufs.out[2 * T + t] = wz;
+    }
+    __syncthreads();
+  }
+  MPPI_TRACE_AT(15);
 }
 
 // K3c (stream layout): softmax weights and weighted control sums over time-major noise [T][B]; a GEMV

@@ -24,11 +24,11 @@ for _ in range(20):
     assert lib.mppi_debug_get_trace(buf, 64) == 0
     acc.append(np.array(buf[:], dtype=np.int64))
 a = np.median(np.stack(acc), axis=0)
-k2 = a[0:10] - a[0]
+k2 = a[0:16] - a[0]
 k3 = a[16:23] - a[16]
 print("B =", e.B)
-print("K2 phase starts (cycles from kernel start, block 0):", " ".join("%d" % v for v in k2))
+print("K2 / fused phase starts (cycles from kernel start, block 0; 10.. = fused tail: barrier 1 passed, decisions,")
+print("   path critics, totals, [weighted sums + barrier 2], merge done):", " ".join("%d" % v for v in k2))
 print("K3 phase starts (cycles from kernel start, block 0):", " ".join("%d" % v for v in k3))
 print("K3 preamble: issue-done %d, barrier-1 %d, decisions-done %d" % tuple(a[24:27] - a[16]))
-print("K3 decisions rep0 start %d, rep1 start %d, end %d" % (a[27]-a[16], a[28]-a[16], a[26]-a[16]))
 print("K2 end -> K3 start gap (cycles, only meaningful if both blocks ran on the same SM):", int(a[16] - a[9]))
