@@ -266,6 +266,10 @@ mppi_status mppi_score_trajectories(mppi_handle * h, const mppi_cycle_in * in,
 /* ---- measurement hooks (bench.py: roofline of the dominant kernel, launch count) ---- */
 /* when enabled, CUDA events bracket each kernel of optimize() on the handle's stream (adds ~1 us per event) */
 mppi_status mppi_set_profiling(mppi_handle * h, int32_t enable);
+/* device_ms of mppi_cycle_out costs two event records and an event read-back per call (~5 us of host time); the
+ * controller does not need it (the reference has no such output): enable = 0 switches it off, device_ms then reads 0.
+ * Default: on. */
+mppi_status mppi_set_timing(mppi_handle * h, int32_t enable);
 /* last optimize(), summed over iteration_count: ms_out[0] K2 rollout_score, [1] K3 path_softmax_update,
  * [2] exchanges + K4 merge (sharded only), [3] whole device span incl. copies.  kernel_launches_total counts every
  * kernel this handle has launched since create; h2d/d2h are the bytes copied by the last mppi_optimize(). */

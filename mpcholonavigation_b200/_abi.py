@@ -196,6 +196,7 @@ PRODUCT_ONLY = {
     "set_visualization": (C.c_int, [H, C.c_int32, C.c_int32]),
     "get_visualization": (C.c_int, [H, f32p, f32p]),
     "set_profiling": (C.c_int, [H, C.c_int32]),
+    "set_timing": (C.c_int, [H, C.c_int32]),
     "get_profile": (C.c_int, [H, f32p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "comm_get_unique_id": (C.c_int, [u8p]),
     "comm_init": (C.c_int, [H, u8p, C.c_int32, C.c_int32]),

@@ -297,6 +297,10 @@ class Engine:
     def set_profiling(self, enable=True):
         self._check(self.f["set_profiling"](self.h, int(bool(enable))))
 
+    def set_timing(self, enable=True):
+        """device_ms of every cycle (two event records + a read-back per call); off: device_ms reads 0"""
+        self._check(self.f["set_timing"](self.h, int(bool(enable))))
+
     def get_profile(self):
         ms = np.zeros(4, np.float32)
         n, h2d, d2h = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)

@@ -11,6 +11,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <time.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -76,11 +78,15 @@ struct mppi_handle
   cudaEvent_t ev0{nullptr}, ev1{nullptr};
   cudaEvent_t pev[4]{nullptr, nullptr, nullptr, nullptr};   // profiling: before K2, after K2, after K3, after exchange 2
   bool profiling{false};
+  bool timing{true};           // bracket every cycle with two events and report device_ms (mppi_set_timing)
   float prof_ms[4]{0.f, 0.f, 0.f, 0.f};
   uint64_t launches{0};
   uint64_t h2d_bytes{0}, d2h_bytes{0};
   // device
   float * d_noise[3]{nullptr, nullptr, nullptr};
+  // one upload buffer per side, [cycle record (kParamsCapacity reserved) | costmap]: the record is copied alone
+  // (resident costmap) or record + costmap in ONE async copy: the costmap is staged right behind the bytes of the record
+  // that are copied (d_costmap = d_params + params_copy_bytes rounded up to 256)
   uint8_t * d_costmap{nullptr};
   size_t costmap_capacity{0};
   char * d_params{nullptr};
@@ -112,6 +118,13 @@ struct mppi_handle
   DevParams last;   // host copy of the last uploaded record
   int segments_override{0};
   int stream_threads_override{0};
+  // fused small-batch kernel: packet buffers of the in-GPU exchanges, launch epoch (device + host mirror), result packets
+  uint2 * d_pk{nullptr};                  // [G] exchange-1 packets, then [G][3T + 2] record packets
+  unsigned * d_fepoch{nullptr};           // completed fused launches (never reset: tags do not repeat)
+  uint32_t fepoch_host{0};                // host mirror of *d_fepoch once everything enqueued has run
+  uint2 * h_res{nullptr};                 // pinned + mapped: [3T + 8] result packets written by the kernels
+  bool wait_packets{false};               // the cycle in flight delivers its result as packets (no D2H copy, no stream sync)
+  uint64_t host_ns[8]{0, 0, 0, 0, 0, 0, 0, 0};   // host-side time of the steady-state call by phase (mppi_debug_get_host_ns)
   bool fused_enabled{true};    // small batches: one cooperative launch per iteration (tile_fused_kernel); MPPI_FUSED=0 disables
   int fused_key_N{-1};         // path size the cached decision below was taken for (the shared-memory size depends on it)
   bool fused_fits{false};      // the whole grid is co-resident (a cooperative launch needs that)
@@ -168,6 +181,13 @@ constexpr size_t kParamsCapacity = sizeof(DevParams) + MPPI_MAX_PATH_POINTS * (4
       return MPPI_E_NCCL;                                                                          \
     }                                                                                              \
   } while (0)
+
+inline uint64_t now_ns()
+{
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return static_cast<uint64_t>(ts.tv_sec) * 1000000000ull + static_cast<uint64_t>(ts.tv_nsec);
+}
 
 mppi_status fail(mppi_handle * h, mppi_status s, const std::string & msg)
 {
@@ -586,6 +606,9 @@ DevBuffers make_bufs(mppi_handle * h, int mode)
   b.peer.seq = h->d_seq;
   b.peer.rank = h->rank;
   b.peer.nranks = h->peer_mode ? h->nranks : 1;
+  b.pk_x1 = h->d_pk;
+  b.pk_rec = h->d_pk ? h->d_pk + h->upd_blocks : nullptr;
+  b.epoch = h->d_fepoch;
   return b;
 }
 
@@ -604,16 +627,23 @@ mppi_status stage_costmap(mppi_handle * h, const mppi_costmap & cm)
   if (bytes == 0 || !cm.cells) {return fail(h, MPPI_E_CONFIG, "empty costmap");}
   if (!(cm.resolution > 0.0)) {return fail(h, MPPI_E_CONFIG, "costmap resolution must be > 0");}
   if (bytes > h->costmap_capacity) {
-    // grow (outside the steady state: the costmap size only changes on reconfiguration)
+    // grow (outside the steady state: the costmap size only changes on reconfiguration); the record staged by
+    // build_params moves with the buffer
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     drop_graphs(h);
-    if (h->d_costmap) {cudaFree(h->d_costmap);}
-    if (h->h_costmap) {cudaFreeHost(h->h_costmap);}
-    h->d_costmap = nullptr; h->h_costmap = nullptr; h->costmap_capacity = 0;
-    CUDA_TRY(h, cudaMalloc(&h->d_costmap, bytes));
-    CUDA_TRY(h, cudaMallocHost(&h->h_costmap, bytes));
+    char * d_new = nullptr, * h_new = nullptr;
+    CUDA_TRY(h, cudaMalloc(&d_new, kParamsCapacity + 256 + bytes));
+    CUDA_TRY(h, cudaMallocHost(&h_new, kParamsCapacity + 256 + bytes));
+    std::memcpy(h_new, h->h_params, kParamsCapacity);
+    CUDA_TRY(h, cudaMemcpy(d_new, h->d_params, kParamsCapacity, cudaMemcpyDeviceToDevice));
+    cudaFree(h->d_params);
+    cudaFreeHost(h->h_params);
+    h->d_params = d_new; h->h_params = h_new;
     h->costmap_capacity = bytes;
   }
+  const size_t off = (h->params_copy_bytes + 255) & ~static_cast<size_t>(255);
+  h->d_costmap = reinterpret_cast<uint8_t *>(h->d_params + off);
+  h->h_costmap = reinterpret_cast<uint8_t *>(h->h_params + off);
   std::memcpy(h->h_costmap, cm.cells, bytes);
   h->costmap_bytes = bytes;
   return MPPI_OK;
@@ -621,8 +651,9 @@ mppi_status stage_costmap(mppi_handle * h, const mppi_costmap & cm)
 
 mppi_status enqueue_uploads(mppi_handle * h)
 {
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_params, h->h_params, h->params_copy_bytes, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_costmap, h->h_costmap, h->costmap_bytes, cudaMemcpyHostToDevice, h->stream));
+  // record + costmap, contiguous on both sides (stage_costmap): one copy
+  const size_t off = (h->params_copy_bytes + 255) & ~static_cast<size_t>(255);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_params, h->h_params, off + h->costmap_bytes, cudaMemcpyHostToDevice, h->stream));
   return MPPI_OK;
 }
 
@@ -685,12 +716,19 @@ cudaError_t fused_occupancy(int threads, size_t smem, int * blocks_per_sm)
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, tile_fused_kernel<F, kExact>, threads, smem);
 }
 
+// path capacity of the fused kernel's shared memory: rounded up to 64 points like the record copy (build_params), so that
+// the captured graph survives small changes of the pruned path
+int fused_path_capacity(const mppi_handle * h)
+{
+  return std::min(MPPI_MAX_PATH_POINTS, ((h->last.N + 63) / 64) * 64);
+}
+
 // Does this cycle run as ONE cooperative launch of tile_fused_kernel?  Single rank, tile layout, and the whole grid
 // co-resident (checked once per path size with the occupancy API; the generic instance is the largest one).
 bool use_fused(mppi_handle * h)
 {
   if (!h->fused_enabled || h->stream_layout || h->nranks > 1) {return false;}
-  const int N = h->last.N;
+  const int N = fused_path_capacity(h);
   if (h->fused_key_N != N) {
     h->fused_key_N = N;
     h->fused_fits = false;
@@ -707,28 +745,28 @@ bool use_fused(mppi_handle * h)
 }
 
 template<unsigned F, bool kExact>
-cudaError_t launch_fused_instance(mppi_handle * h, int iteration)
+cudaError_t launch_fused_instance(mppi_handle * h, int iteration, uint2 * host_res)
 {
   const int S = pick_segments(h);
   const dim3 grid((h->B + kTile - 1) / kTile), block(kTile, S);
-  int N = h->last.N;
+  int N = fused_path_capacity(h);
   const size_t smem = fused_smem_bytes(h->T, S, N, grid.x);
   const DevParams * dp = reinterpret_cast<const DevParams *>(h->d_params);
   const uint8_t * cm = h->d_costmap;
   DevBuffers bufs = make_bufs(h, 0);
   int B = h->B, T = h->T;
-  void * args[] = {&dp, &cm, &bufs, &B, &T, &N, &iteration};
+  void * args[] = {&dp, &cm, &bufs, &B, &T, &N, &iteration, &host_res};
   return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&tile_fused_kernel<F, kExact>), grid, block, args, smem, h->stream);
 }
 
-mppi_status launch_fused(mppi_handle * h, int iteration)
+mppi_status launch_fused(mppi_handle * h, int iteration, uint2 * host_res)
 {
   cudaError_t e;
   switch (pick_stream_instance(stream_feature_need(h->last))) {
-    case kSfOmniDefault: e = launch_fused_instance<kSfOmniDefault, true>(h, iteration); break;
-    case kSfOmniDefaultFp: e = launch_fused_instance<kSfOmniDefaultFp, true>(h, iteration); break;
-    case kSfObstaclesFp: e = launch_fused_instance<kSfObstaclesFp, true>(h, iteration); break;
-    default: e = launch_fused_instance<SF_ALL, false>(h, iteration); break;
+    case kSfOmniDefault: e = launch_fused_instance<kSfOmniDefault, true>(h, iteration, host_res); break;
+    case kSfOmniDefaultFp: e = launch_fused_instance<kSfOmniDefaultFp, true>(h, iteration, host_res); break;
+    case kSfObstaclesFp: e = launch_fused_instance<kSfObstaclesFp, true>(h, iteration, host_res); break;
+    default: e = launch_fused_instance<SF_ALL, false>(h, iteration, host_res); break;
   }
   CUDA_TRY(h, e);
   h->launches++;
@@ -807,7 +845,9 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
     if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[0], h->stream));}
     if (fused) {
       // small batches: rollout, critics, softmax update and merge in one cooperative launch (pev: all of it counts as K2)
-      mppi_status s = launch_fused(h, it);
+      // the launch that completes the result writes it to pinned host memory itself (packets), unless the tail follows
+      const bool last = it + 1 == h->cfg.iteration_count;
+      mppi_status s = launch_fused(h, it, last && !h->tail_mode ? h->h_res : nullptr);
       if (s != MPPI_OK) {return s;}
       if (prof) {
         CUDA_TRY(h, cudaEventRecord(h->pev[1], h->stream));
@@ -871,12 +911,15 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
   }
   if (h->tail_mode) {
     // evalControl's tail (Savitzky-Golay filter, command extraction, shift) stays on the device
-    eval_tail_kernel<<<1, 32, 0, h->stream>>>(h->d_cs, h->d_hist, h->d_out, h->T, holonomic(h) ? 1 : 0, h->tail_mode == 2 ? 1 : 0);
+    eval_tail_kernel<<<1, 32, 0, h->stream>>>(h->d_cs, h->d_hist, h->d_out, h->T, holonomic(h) ? 1 : 0, h->tail_mode == 2 ? 1 : 0,
+      fused ? h->h_res : nullptr, h->d_fepoch);
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
   }
   if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[3], h->stream));}
-  CUDA_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(float) * (3 * h->T + 6), cudaMemcpyDeviceToHost, h->stream));
+  if (!fused) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(float) * (3 * h->T + 6), cudaMemcpyDeviceToHost, h->stream));
+  }
   if (h->cfg.regenerate_noises) {
     // the result is complete here; the redraw for the next cycle runs behind it, off the caller's critical path
     if (h->capturing) {
@@ -895,9 +938,14 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
 {
   const bool prof = h->profiling && h->cfg.iteration_count == 1;
   const bool graph_ok = h->use_graph && !prof && (h->nranks == 1 || h->peer_mode);   // NCCL calls are not captured
-  h->d2h_bytes = sizeof(float) * (3 * h->T + 6);
-  h->h2d_bytes = with_upload ? h->params_copy_bytes + h->costmap_bytes : 0;
-  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+  h->wait_packets = use_fused(h);
+  if (h->wait_packets) {h->fepoch_host += static_cast<uint32_t>(h->cfg.iteration_count);}
+  h->d2h_bytes = h->wait_packets ? sizeof(uint2) * (3 * h->T + 2 + (h->tail_mode ? 3 : 0)) : sizeof(float) * (3 * h->T + 6);
+  h->h2d_bytes = with_upload ? ((h->params_copy_bytes + 255) & ~static_cast<size_t>(255)) + h->costmap_bytes : 0;
+  const uint64_t t_a = now_ns();
+  if (h->timing) {CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));}
+  const uint64_t t_b = now_ns();
+  h->host_ns[2] += t_b - t_a;
   if (graph_ok) {
     const int slot = (with_upload ? 1 : 0) + 2 * h->tail_mode;
     const unsigned inst = pick_stream_instance(stream_feature_need(h->last));   // the K2 instance is baked into the graph
@@ -933,9 +981,12 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
     }
     if (h->gexec[slot]) {
       CUDA_TRY(h, cudaGraphLaunch(h->gexec[slot], h->stream));
+      const uint64_t t_c = now_ns();
+      h->host_ns[3] += t_c - t_b;
       h->launches += (use_fused(h) ? 1ull : (h->stream_layout ? 4ull : (h->upd_blocks > kLastBlockMergeMax ? 3ull : 2ull))) *
         h->cfg.iteration_count + (h->tail_mode ? 1ull : 0ull);
-      CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+      if (h->timing) {CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));}
+      h->host_ns[4] += now_ns() - t_c;
       return MPPI_OK;
     }
   }
@@ -943,18 +994,64 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
   if (with_upload) {s = enqueue_uploads(h);}
   if (s != MPPI_OK) {return s;}
   if ((s = enqueue_kernels(h, prof)) != MPPI_OK) {return s;}
-  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+  if (h->timing) {CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));}
+  return MPPI_OK;
+}
+
+// The fused kernel (or the tail kernel behind it) writes the result straight into pinned host memory as packets
+// {value, tag}; a packet whose tag is the tag of the last launch enqueued is complete.  Polling them replaces the D2H
+// copy node and the stream synchronisation.  The stream is queried every few thousand polls so that a failed launch
+// surfaces as an error instead of a hang.
+mppi_status wait_result_packets(mppi_handle * h)
+{
+  const int n = 3 * h->T + 2 + (h->tail_mode ? 3 : 0);
+  const uint32_t tag = h->fepoch_host;
+  const uint64_t * pk = reinterpret_cast<const uint64_t *>(h->h_res);
+  uint32_t * dst = reinterpret_cast<uint32_t *>(h->h_out);
+  uint64_t spins = 0;
+  bool drained = false;
+  for (int i = 0; i < n; ++i) {
+    for (;;) {
+      const uint64_t v = __atomic_load_n(pk + i, __ATOMIC_ACQUIRE);
+      if (static_cast<uint32_t>(v >> 32) == tag) {dst[i] = static_cast<uint32_t>(v); break;}
+      if ((++spins & 4095u) == 0u) {
+        if (drained) {
+          // everything enqueued has run and the packet is still missing: resynchronise the epoch mirror and report
+          cudaMemcpy(&h->fepoch_host, h->d_fepoch, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+          return fail(h, MPPI_E_CUDA, "fused kernel finished without delivering its result packets");
+        }
+        const cudaError_t q = cudaStreamQuery(h->stream);
+        if (q == cudaSuccess) {
+          drained = true;
+        } else if (q != cudaErrorNotReady) {
+          return fail(h, MPPI_E_CUDA, std::string("cudaStreamQuery: ") + cudaGetErrorString(q));
+        }
+      }
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
+    }
+  }
   return MPPI_OK;
 }
 
 mppi_status finish_optimize(mppi_handle * h, mppi_cycle_out * out)
 {
+  const uint64_t t_a = now_ns();
   if (h->cfg.regenerate_noises) {
     h->noise_stream += static_cast<uint64_t>(h->cfg.iteration_count);   // host mirror of d_epoch
+  }
+  if (h->wait_packets) {
+    mppi_status ws = wait_result_packets(h);
+    if (ws != MPPI_OK) {return ws;}
+    if (h->timing) {CUDA_TRY(h, cudaEventSynchronize(h->cfg.regenerate_noises ? h->ev_result : h->ev1));}
+  } else if (h->cfg.regenerate_noises) {
     CUDA_TRY(h, cudaEventSynchronize(h->ev_result));
   } else {
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   }
+  const uint64_t t_b = now_ns();
+  h->host_ns[5] += t_b - t_a;
   const int T = h->T;
   h->spilled_traj = h->last.spill_traj != 0;
   h->spilled_cells = h->last.want_cells != 0;
@@ -970,11 +1067,13 @@ mppi_status finish_optimize(mppi_handle * h, mppi_cycle_out * out)
     std::memcpy(&fu, h->h_out + 3 * T + 1, 4);
     out->fail_flag = ff;
     out->furthest_reached_path_point = fu;
-    float ms = 0.0f;
-    cudaEventElapsedTime(&ms, h->ev0, h->cfg.regenerate_noises ? h->ev_result : h->ev1);
-    out->device_ms = ms;
   }
-  cudaEventElapsedTime(&h->prof_ms[3], h->ev0, h->cfg.regenerate_noises ? h->ev_result : h->ev1);
+  // device time of the cycle (events around everything enqueued for it), only when asked for: reading two events back
+  // costs several microseconds of host time
+  float ms = 0.0f;
+  if (h->timing) {cudaEventElapsedTime(&ms, h->ev0, h->cfg.regenerate_noises ? h->ev_result : h->ev1);}
+  h->prof_ms[3] = ms;
+  if (out) {out->device_ms = ms;}
   if (h->peer_mode) {
     uint32_t comm_error;
     std::memcpy(&comm_error, h->h_out + 3 * T + 5, 4);
@@ -986,6 +1085,8 @@ mppi_status finish_optimize(mppi_handle * h, mppi_cycle_out * out)
     cudaEventElapsedTime(&h->prof_ms[1], h->pev[1], h->pev[2]);
     cudaEventElapsedTime(&h->prof_ms[2], h->pev[2], h->pev[3]);
   }
+  h->host_ns[6] += now_ns() - t_b;
+  h->host_ns[7] += 1;
   return MPPI_OK;
 }
 
@@ -1139,11 +1240,12 @@ void mppi_destroy(mppi_handle * h)
   for (float * p : h->d_inj) {cudaFree(p);}
   cudaFree(h->d_vis);
   cudaFree(h->d_vis);
-  cudaFree(h->d_tmp); cudaFree(h->d_costmap); cudaFree(h->d_params); cudaFree(h->d_cs); cudaFree(h->d_crit_rows);
+  cudaFree(h->d_tmp); cudaFree(h->d_params); cudaFree(h->d_cs); cudaFree(h->d_crit_rows);
   cudaFree(h->d_end_xy); cudaFree(h->d_cells); cudaFree(h->d_costs); cudaFree(h->d_partials); cudaFree(h->d_rank_partial);
   cudaFree(h->d_gathered); cudaFree(h->d_out); cudaFree(h->d_st); cudaFree(h->d_hist); cudaFree(h->d_seq); cudaFree(h->d_epoch);
   if (h->ev_result) {cudaEventDestroy(h->ev_result);} cudaFree(h->d_mailbox);
-  cudaFreeHost(h->h_params); cudaFreeHost(h->h_costmap); cudaFreeHost(h->h_out);
+  cudaFreeHost(h->h_params); cudaFreeHost(h->h_out); cudaFreeHost(h->h_res);
+  cudaFree(h->d_pk); cudaFree(h->d_fepoch);
   if (h->ev0) {cudaEventDestroy(h->ev0);}
   if (h->ev1) {cudaEventDestroy(h->ev1);}
   for (auto & e : h->pev) {if (e) {cudaEventDestroy(e);}}
@@ -1228,7 +1330,7 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
     CUDA_TRY(h, cudaMemsetAsync(h->d_noise[i], 0, noise_plane, h->stream));
   }
   CUDA_TRY(h, cudaMalloc(&h->d_cells, B * T * sizeof(int)));
-  CUDA_TRY(h, cudaMalloc(&h->d_params, kParamsCapacity));
+  CUDA_TRY(h, cudaMalloc(&h->d_params, kParamsCapacity + 256));
   CUDA_TRY(h, cudaMalloc(&h->d_cs, 3 * T * sizeof(float)));
   CUDA_TRY(h, cudaMalloc(&h->d_crit_rows, (kMaxCritics + kGammaRows) * B * sizeof(float)));
   CUDA_TRY(h, cudaMemsetAsync(h->d_crit_rows, 0, (kMaxCritics + kGammaRows) * B * sizeof(float), h->stream));
@@ -1246,7 +1348,16 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   CUDA_TRY(h, cudaMalloc(&h->d_seq, sizeof(unsigned)));
   CUDA_TRY(h, cudaMemsetAsync(h->d_seq, 0, sizeof(unsigned), h->stream));
   CUDA_TRY(h, cudaMalloc(&h->d_st, sizeof(DevState)));
-  CUDA_TRY(h, cudaMallocHost(&h->h_params, kParamsCapacity));
+  if (!h->stream_layout) {
+    const size_t n_pk = static_cast<size_t>(h->upd_blocks) * (1 + stride);
+    CUDA_TRY(h, cudaMalloc(&h->d_pk, n_pk * sizeof(uint2)));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_pk, 0, n_pk * sizeof(uint2), h->stream));
+  }
+  CUDA_TRY(h, cudaMalloc(&h->d_fepoch, sizeof(unsigned)));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_fepoch, 0, sizeof(unsigned), h->stream));
+  CUDA_TRY(h, cudaHostAlloc(&h->h_res, (stride + 8) * sizeof(uint2), cudaHostAllocMapped | cudaHostAllocPortable));
+  std::memset(h->h_res, 0, (stride + 8) * sizeof(uint2));
+  CUDA_TRY(h, cudaMallocHost(&h->h_params, kParamsCapacity + 256));
   CUDA_TRY(h, cudaMallocHost(&h->h_out, (stride + 8) * sizeof(float)));
   return do_reset(h);
 }
@@ -1438,10 +1549,14 @@ mppi_status mppi_optimize_resident(mppi_handle * h, mppi_cycle_out * out)
 static mppi_status optimize_begin(mppi_handle * h, const mppi_cycle_in * in)
 {
   if (!h || !in) {return MPPI_E_CONFIG;}
+  const uint64_t t_a = now_ns();
   CUDA_TRY(h, cudaSetDevice(h->device));
   mppi_status s = build_params(h, in, 0, kUnset, true);
   if (s != MPPI_OK) {return s;}
+  const uint64_t t_b = now_ns();
   if ((s = stage_costmap(h, in->costmap)) != MPPI_OK) {return s;}
+  h->host_ns[0] += t_b - t_a;
+  h->host_ns[1] += now_ns() - t_b;
   h->cycle_uploaded = true;
   return enqueue_optimize(h, true);
 }
@@ -1675,6 +1790,24 @@ mppi_status mppi_score_trajectories(
   return MPPI_OK;
 }
 
+// tuning aid: accumulated host time (ns) of the steady-state call by phase, and the number of calls [7]:
+// [0] build_params, [1] stage_costmap, [2] event record, [3] graph launch, [4] event record, [5] wait for the result,
+// [6] copy-out + event read-back.  reset != 0 clears the counters.
+mppi_status mppi_debug_get_host_ns(mppi_handle * h, uint64_t out8[8], int32_t reset)
+{
+  if (!h || !out8) {return MPPI_E_CONFIG;}
+  for (int i = 0; i < 8; ++i) {out8[i] = h->host_ns[i]; if (reset) {h->host_ns[i] = 0;}}
+  return MPPI_OK;
+}
+
+mppi_status mppi_set_timing(mppi_handle * h, int32_t enable)
+{
+  if (!h) {return MPPI_E_CONFIG;}
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->timing = enable != 0;
+  return MPPI_OK;
+}
+
 mppi_status mppi_set_profiling(mppi_handle * h, int32_t enable)
 {
   if (!h) {return MPPI_E_CONFIG;}
@@ -1785,6 +1918,7 @@ mppi_status mppi_optimize_sharded(mppi_handle ** hs, int32_t n, const mppi_cycle
       cudaEventRecord(h->ev1, h->stream);
     }
     h->cycle_uploaded = true;
+    h->wait_packets = false;   // this path copies its result back (no fused kernel here)
   }
   mppi_status first = s;
   for (int i = 0; i < n; ++i) {

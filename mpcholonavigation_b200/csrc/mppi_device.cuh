@@ -188,8 +188,6 @@ struct DevState
   unsigned ticket;                      // last-block election of the update kernel
   float global_min;                     // stream layout: min over all costs, published by K3's last block
   unsigned comm_error;                  // a peer-memory exchange timed out (sticky until reset)
-  unsigned long long bar;               // arrivals at the grid barriers of the fused small-batch kernel (monotone; a
-                                        // multiple of the grid size whenever no fused kernel is running)
 };
 
 // ---------------------------------------------------------------------------------------------------

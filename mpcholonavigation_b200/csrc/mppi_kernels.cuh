@@ -52,6 +52,11 @@ struct DevBuffers
   float * out;          // [3T + 4]: new control sequence, fail flag, furthest (as bit patterns)
   DevState * st;
   PeerComm peer;        // sharded over peer memory when peer.nranks > 1
+  // fused small-batch kernel: the exchanges between the tiles of one launch travel as self-validating packets
+  // {value, tag of the launch} (the protocol of the peer exchange above, inside one GPU)
+  uint2 * pk_x1;        // [G]            per tile: furthest-point candidate | survivor flags << 16
+  uint2 * pk_rec;       // [G][3T + 2]    per tile: softmax record (m, s, W[3T])
+  unsigned * epoch;     // completed fused launches of this handle; the tag of the running launch is *epoch + 1
 };
 
 // accumulator slots of the per-segment partials
@@ -123,7 +128,8 @@ struct FusedCtx
   FusedShared fs;
   const float * s_hot, * s_cs;
   const float * s_cvx, * s_cvy, * s_cwz, * s_yaw, * s_x, * s_y;   // time-major tile planes [T][33]
-  int N, iteration;
+  int n_cap, iteration;   // n_cap: path capacity the shared-memory carve-up was sized for (>= the record's N)
+  unsigned tag;           // tag of this launch's packets
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -264,7 +270,7 @@ __device__ __forceinline__ void rollout_tile_body(
   int * s_amin_j = reinterpret_cast<int *>(s_amin_d + S * kTile);
   FusedShared fs = {};
   if (kFused) {
-    fs = fused_carve(reinterpret_cast<float *>(s_amin_j + S * kTile), fx->N, gridDim.x);
+    fs = fused_carve(reinterpret_cast<float *>(s_amin_j + S * kTile), fx->n_cap, gridDim.x);
     fx->fs = fs;
     fx->s_hot = s_hot; fx->s_cs = s_cs; fx->s_cvx = s_cvx; fx->s_cvy = s_cvy; fx->s_cwz = s_cwz; fx->s_yaw = s_yaw;
     fx->s_x = s_x; fx->s_y = s_y;
@@ -306,7 +312,7 @@ __device__ __forceinline__ void rollout_tile_body(
   MPPI_TRACE_AT(1);
   if (kFused) {
     // the path and its host-made tables (record tail, build_params): x[N] y[N] yaw[N] D[N] | valid[n16] flags[n16] follow[N]
-    const int N = fx->N, n16 = ((N + 15) / 16) * 16;
+    const int N = min(__ldg(&P->N), fx->n_cap), n16 = ((N + 15) / 16) * 16;
     const float * tail = reinterpret_cast<const float *>(P + 1);
     const uint8_t * g_valid = reinterpret_cast<const uint8_t *>(tail + 4 * N);
     const uint16_t * g_follow = reinterpret_cast<const uint16_t *>(g_valid + 2 * n16);
@@ -702,15 +708,10 @@ __device__ __forceinline__ void rollout_tile_body(
         put(p.n_critics, tot[A_GVX]); put(p.n_critics + 1, tot[A_GVY]); put(p.n_critics + 2, tot[A_GWZ]);
       }
     }
-    // fail_flag inputs: did any trajectory of this tile survive?
-    if (cost_on) {
-      const unsigned ok = __ballot_sync(0xffffffffu, live && !cost_collided);
-      if (lane == 0 && ok) {atomicOr(&bufs.st->any_ok[p.cost.idx], 1u);}
-    }
-    if (ob_on) {
-      const unsigned ok = __ballot_sync(0xffffffffu, live && !ob_collided);
-      if (lane == 0 && ok) {atomicOr(&bufs.st->any_ok[p.obst.idx], 1u);}
-    }
+    // fail_flag inputs: did any trajectory of this tile survive?  + this tile's furthest-point candidate
+    unsigned cost_ok = 0u, ob_ok = 0u, cand = 0u;
+    if (cost_on) {cost_ok = __ballot_sync(0xffffffffu, live && !cost_collided);}
+    if (ob_on) {ob_ok = __ballot_sync(0xffffffffu, live && !ob_collided);}
     if (need_furthest) {
       float best = s_amin_d[lane];
       int best_j = s_amin_j[lane];
@@ -718,8 +719,17 @@ __device__ __forceinline__ void rollout_tile_body(
         const float d = s_amin_d[s * kTile + lane];
         if (d < best) {best = d; best_j = s_amin_j[s * kTile + lane];}
       }
-      const unsigned m = warp_max_u(live ? static_cast<unsigned>(best_j) : 0u);
-      if (lane == 0) {atomicMax(&bufs.st->furthest_candidate, m);}
+      cand = warp_max_u(live ? static_cast<unsigned>(best_j) : 0u);
+    }
+    if (kFused) {
+      // exchange 1 inside the GPU: one self-validating packet per tile (path indices are < MPPI_MAX_PATH_POINTS <= 2^16)
+      if (lane == 0) {
+        st_packet(bufs.pk_x1 + blockIdx.x, cand | (cost_ok ? 0x10000u : 0u) | (ob_ok ? 0x20000u : 0u), fx->tag);
+      }
+    } else if (lane == 0) {
+      if (cost_ok) {atomicOr(&bufs.st->any_ok[p.cost.idx], 1u);}
+      if (ob_ok) {atomicOr(&bufs.st->any_ok[p.obst.idx], 1u);}
+      if (need_furthest) {atomicMax(&bufs.st->furthest_candidate, cand);}
     }
   }
   MPPI_TRACE_AT(9);
@@ -1646,41 +1656,21 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
 // and a serial per-trajectory walk of the path critics by one warp per block.  Here a block keeps its tile of 32
 // trajectories in shared memory from the first noise load to the block's softmax record:
 //   K2 body (rollout_tile_body, six planes: the noised controls survive beside x, y, yaw)
-//   grid barrier 1   = exchange 1 inside the GPU: furthest-point candidate and survivor flags of ALL tiles are in
+//   exchange 1         inside the GPU: one packet per tile (furthest-point candidate, survivor flags), collected by warp 0
 //   decisions          (k3_decide, one thread)
 //   path critics       one WARP per trajectory, lane = sampled pose (PathAlign, PathAlignLegacy) or time step (PathAngle);
 //                      the two carried dependences of PathAlign (integrated distance, previous path point) run as
 //                      shuffle chains of one add / one compare per sample, everything else is lane-parallel
 //   totals, weights    warp 0, lane = trajectory, critic-list order with the fail_flag short-circuit + gamma term
 //   weighted sums      all threads over the 3T columns, out of the tile
-//   grid barrier 2   = the softmax records of all tiles are in
-//   merge + clip       block t owns time steps t, t + G, ...: one warp per column over the records, redundant min
-// The barriers count arrivals in DevState::bar (64 bit, monotone); the launch is cooperative, so all blocks are
-// co-resident and the bounded spin never fires in normal operation.
+//   exchange 2         inside the GPU: the tile's softmax record leaves as packets
+//   merge + clip       block t owns time steps t, t + G, ...: one warp per column over the records, redundant min;
+//                      the result goes to device memory AND, as packets, straight into pinned host memory
+// Both exchanges use the self-validating {value, tag} packets of the peer exchange (mppi_device.cuh): a packet whose tag
+// equals the tag of this launch (*epoch + 1) is its own arrival flag, so there is no grid barrier, no fence and no atomic
+// on the critical path.  The launch is cooperative: all blocks are co-resident, the bounded polls never time out in
+// normal operation.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long * p)
-{
-  unsigned long long v;
-  asm volatile ("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__device__ __forceinline__ void grid_barrier(DevState * st, unsigned nblocks, bool leader)
-{
-  __syncthreads();
-  if (leader) {
-    __threadfence();
-    const unsigned long long old = atomicAdd(&st->bar, 1ull);
-    const unsigned long long target = (old / nblocks + 1ull) * nblocks;
-    const long long t0 = clock64();
-    while (ld_acquire_u64(&st->bar) < target) {
-      if (clock64() - t0 > kSpinLimitCycles) {st->comm_error = 1u; break;}
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
-
 // PathAlignCritic::score (path_align_critic.cpp:92-135) for trajectory r of the tile, by one warp; lane = sampled pose.
 __device__ __forceinline__ float path_align_warp(
   const DevParams * P, const FusedCtx & fx, int r, int furthest, const float * __restrict__ path_yaw, int lane)
@@ -1805,14 +1795,33 @@ __device__ __forceinline__ float path_angle_warp(const DevParams * P, const Fuse
   return add_pow(0.0f, (sum / static_cast<float>(T)) * P->angle.weight, P->angle.power);
 }
 
+__device__ __forceinline__ unsigned warp_or_u(unsigned v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {v |= __shfl_xor_sync(0xffffffffu, v, o);}
+  return v;
+}
+
+// result packet for the host: pinned, mapped memory written straight from the kernel, {value, tag of the launch};
+// the host polls the tags (finish_optimize), so no copy node, no stream synchronisation
+__device__ __forceinline__ void put_result(float * out, uint2 * host_res, int idx, float v, unsigned tag)
+{
+  out[idx] = v;
+  if (host_res) {st_packet(host_res + idx, __float_as_uint(v), tag);}
+}
+
 template<unsigned F, bool kExact>
 __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
-  const DevParams * __restrict__ Pg, const uint8_t * __restrict__ cm, DevBuffers bufs, const int B, const int T, const int N,
-  const int iteration)
+  const DevParams * __restrict__ Pg, const uint8_t * __restrict__ cm, DevBuffers bufs, const int B, const int T, const int n_cap,
+  const int iteration, uint2 * host_res)
 {
+  // n_cap (path capacity, a multiple of 64) sizes the shared memory; the path size itself comes from the record, so a
+  // captured graph survives the small changes of the pruned path from cycle to cycle
   __shared__ K3Decisions dec;
   FusedCtx fx;
-  fx.N = N; fx.iteration = iteration;
+  fx.n_cap = n_cap; fx.iteration = iteration;
+  const unsigned tag = ld_volatile_u32(bufs.epoch) + 1u;
+  fx.tag = tag;
   rollout_tile_body<F, kExact, 0, true>(Pg, cm, bufs, B, T, &fx);
 
   const int S = blockDim.y, lane = threadIdx.x, seg = threadIdx.y;
@@ -1823,20 +1832,33 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
   const int G = gridDim.x;
   const int b0 = blockIdx.x * kTile;
   const int rows_here = min(kTile, B - b0);
+  const int N = P->N;
   const float * __restrict__ path_yaw = reinterpret_cast<const float *>(Pg + 1) + 2 * N;
 
-  // ---- exchange 1 inside the GPU: every tile's furthest-point candidate and survivor flags are in after this barrier
-  grid_barrier(st, G, tid == 0);
-  MPPI_TRACE_AT(10);
-  if (tid == 0) {
-    unsigned any_ok[kMaxCritics], state[4];
+  // ---- exchange 1 inside the GPU: warp 0 collects every tile's packet (furthest-point candidate, survivor flags)
+  if (seg == 0) {
+    unsigned cand = 0u, flags = 0u;
+    for (int i = lane; i < G; i += 32) {
+      unsigned v;
+      if (!poll_packet(bufs.pk_x1 + i, tag, v)) {st->comm_error = 1u;}
+      cand = max(cand, v & 0xffffu);
+      flags |= v >> 16;
+    }
+    cand = warp_max_u(cand);
+    flags = warp_or_u(flags);
+    MPPI_TRACE_AT(10);
+    if (lane == 0) {
+      unsigned any_ok[kMaxCritics], state[4];
 #pragma unroll
-    for (int q = 0; q < kMaxCritics; ++q) {any_ok[q] = ld_volatile_u32(&st->any_ok[q]);}
-    state[0] = ld_volatile_u32(&st->furthest_candidate);
-    state[1] = ld_volatile_u32(&st->furthest);
-    state[2] = ld_volatile_u32(reinterpret_cast<const unsigned *>(&st->furthest_set));
-    state[3] = ld_volatile_u32(reinterpret_cast<const unsigned *>(&st->fail_flag));
-    k3_decide(P, N, any_ok, state, fs.flags, fs.follow, iteration, &dec);
+      for (int q = 0; q < kMaxCritics; ++q) {
+        any_ok[q] = (q == P->cost.idx && (flags & 1u)) || (q == P->obst.idx && (flags & 2u)) ? 1u : 0u;
+      }
+      state[0] = cand;
+      state[1] = st->furthest;                                  // written by the previous iteration's launch
+      state[2] = static_cast<unsigned>(st->furthest_set);
+      state[3] = static_cast<unsigned>(st->fail_flag);
+      k3_decide(P, N, any_ok, state, fs.flags, fs.follow, iteration, &dec);
+    }
   }
   __syncthreads();
   MPPI_TRACE_AT(11);
@@ -1943,9 +1965,12 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
   __syncthreads();
   MPPI_TRACE_AT(13);
 
-  // ---- weighted column sums of the tile, W[c] = sum_r w_r * c[r][c], out of the noised controls still in the tile
+  // ---- weighted column sums of the tile, W[c] = sum_r w_r * c[r][c], out of the noised controls still in the tile;
+  //      the record leaves as packets (exchange 2 inside the GPU)
   const int stride = 3 * T + 2;
-  float * part = bufs.partials + static_cast<size_t>(blockIdx.x) * stride;
+  uint2 * part = bufs.pk_rec + static_cast<size_t>(blockIdx.x) * stride;
+  if (tid == 0) {st_packet(part, __float_as_uint(fs.stat[0]), tag);}
+  if (tid == 32 || (S == 1 && tid == 1)) {st_packet(part + 1, __float_as_uint(fs.stat[1]), tag);}
   for (int c = tid; c < 3 * T; c += nthr) {
     const int plane = c / T, t = c - plane * T;
     const float * col = (plane == 0 ? fx.s_cvx : (plane == 1 ? fx.s_cvy : fx.s_cwz)) + t * kPad;
@@ -1958,20 +1983,27 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
       a3 = fmaf(fs.w[r + 3], col[r + 3], a3);
     }
     for (; r < rows_here; ++r) {a0 = fmaf(fs.w[r], col[r], a0);}
-    part[2 + c] = (a0 + a1) + (a2 + a3);
+    st_packet(part + 2 + c, __float_as_uint((a0 + a1) + (a2 + a3)), tag);
   }
-  if (tid == 0) {part[0] = fs.stat[0]; part[1] = fs.stat[1];}
-
-  // ---- exchange 2 inside the GPU: every tile's softmax record is in after this barrier
-  grid_barrier(st, G, tid == 0);
   MPPI_TRACE_AT(14);
-  if (blockIdx.x == 0 && tid == 0) {k3_publish_flags(P, st, dec, bufs.out);}
+
+  // ---- merge + clip: block t owns time steps t, t + G, ...  It needs m and s of every record and its own columns;
+  //      the polls return as soon as the packets of this launch are there (no barrier)
+  if (blockIdx.x == 0 && tid == 0) {
+    k3_publish_flags(P, st, dec, bufs.out);
+    if (host_res) {
+      st_packet(host_res + 3 * T, static_cast<unsigned>(st->fail_flag), tag);
+      st_packet(host_res + 3 * T + 1, dec.furthest_set ? static_cast<unsigned>(dec.furthest) : kUnset, tag);
+    }
+    *bufs.epoch = tag;     // every block read the epoch before block 0 can get here (it needs a packet of every block)
+  }
   if (static_cast<int>(blockIdx.x) >= T) {return;}   // owns no time step
-  // global minimum and the rescale factor of every record (redundant per block: G loads)
-  const float * parts = bufs.partials;
+  const uint2 * recs = bufs.pk_rec;
   float m = 3.402823466e+38f;
   for (int i = tid; i < G; i += nthr) {
-    const float mi = __ldcg(parts + static_cast<size_t>(i) * stride);
+    unsigned bits;
+    if (!poll_packet(recs + static_cast<size_t>(i) * stride, tag, bits)) {st->comm_error = 1u;}
+    const float mi = __uint_as_float(bits);
     fs.e[i] = mi;
     m = fminf(m, mi);
   }
@@ -1985,7 +2017,7 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
   __syncthreads();
   // column 0 = sum of the weights; then (vx, vy, wz) of every owned time step: one warp per column, lanes over the records
   const int n_own = (T - static_cast<int>(blockIdx.x) + G - 1) / G;
-  float * col_out = fs.red + 8;   // [1 + 3 n_own] <= 24 entries for n_own <= 7; larger counts loop in rounds below
+  float * col_out = fs.red + 8;   // [1 + 3 * 7]
   for (int t_base = 0; t_base < n_own; t_base += 7) {
     const int n_now = min(7, n_own - t_base);
     for (int k = seg; k < 1 + 3 * n_now; k += S) {
@@ -1997,7 +2029,11 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
         col = 1 + plane * T + t;
       }
       float acc = 0.0f;
-      for (int i = lane; i < G; i += 32) {acc = fmaf(__ldcg(parts + static_cast<size_t>(i) * stride + 1 + col), fs.e[i], acc);}
+      for (int i = lane; i < G; i += 32) {
+        unsigned bits;
+        if (!poll_packet(recs + static_cast<size_t>(i) * stride + 1 + col, tag, bits)) {st->comm_error = 1u;}
+        acc = fmaf(__uint_as_float(bits), fs.e[i], acc);
+      }
       acc = warp_sum(acc);
       if (lane == 0) {col_out[k] = acc;}
     }
@@ -2021,7 +2057,9 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
         }
       }
       bufs.cs[t] = vx; bufs.cs[T + t] = vy; bufs.cs[2 * T + t] = wz;
-      bufs.out[t] = vx; bufs.out[T + t] = vy; bufs.out[2 * T + t] = wz;
+      put_result(bufs.out, host_res, t, vx, tag);
+      put_result(bufs.out, host_res, T + t, vy, tag);
+      put_result(bufs.out, host_res, 2 * T + t, wz, tag);
     }
     __syncthreads();
   }
@@ -2365,7 +2403,8 @@ __global__ void shift_control_sequence_kernel(float * __restrict__ cs, int T, in
 // false.  One thread per plane; the filter is inherently sequential (already-filtered neighbours are reused) and
 // reproduces the reference's quirks: index num_sequences - 4 is never filtered, vy is filtered for every model.
 // out layout: [0, 3T) control sequence after the tail, [3T] fail flag, [3T+1] furthest, [3T+2, 3T+5) command.
-__global__ void eval_tail_kernel(float * __restrict__ cs, float * __restrict__ hist, float * __restrict__ out, int T, int holonomic, int shift)
+__global__ void eval_tail_kernel(float * __restrict__ cs, float * __restrict__ hist, float * __restrict__ out, int T, int holonomic, int shift,
+  uint2 * host_res, const unsigned * epoch)
 {
   __shared__ float s[3][MPPI_MAX_TIME_STEPS];
   const int plane = threadIdx.x;   // 0 vx, 1 vy, 2 wz
@@ -2420,6 +2459,13 @@ __global__ void eval_tail_kernel(float * __restrict__ cs, float * __restrict__ h
     for (int t = 0; t < T; ++t) {cs[plane * T + t] = v[t]; out[plane * T + t] = v[t];}
   } else if (plane < 3) {
     out[3 * T + 2 + plane] = 0.0f;
+  }
+  if (host_res) {
+    // after the fused kernel: the whole result (sequence, flags, command) goes to pinned host memory as packets tagged
+    // with the launch the fused kernel just completed (tile_fused_kernel, put_result)
+    __syncwarp();
+    const unsigned tag = *epoch;
+    for (int i = threadIdx.x; i < 3 * T + 5; i += 32) {st_packet(host_res + i, __float_as_uint(out[i]), tag);}
   }
 }
 

@@ -45,3 +45,18 @@ print("device (events)            p50 %.1f us" % np.percentile(dev, 50))
 cmd = np.zeros(3, np.float32)
 ev = fns["eval_control"]
 print("raw ctypes mppi_eval_control(shift) p50 %.1f us" % p50(lambda: ev(h, C.byref(cin), 1, C.byref(out), cmd.ctypes.data_as(abi.f32p))))
+
+fns["set_timing"](h, 0)
+print("timing off: raw ctypes mppi_optimize   p50 %.1f us" % p50(lambda: f(h, C.byref(cin), C.byref(out))))
+print("timing off: raw ctypes resident        p50 %.1f us" % p50(lambda: g(h, C.byref(out))))
+print("timing off: raw ctypes mppi_eval_control(shift) p50 %.1f us" % p50(lambda: ev(h, C.byref(cin), 1, C.byref(out), cmd.ctypes.data_as(abi.f32p))))
+lib = fns["_lib"]
+buf = (C.c_uint64 * 8)()
+lib.mppi_debug_get_host_ns.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32]
+lib.mppi_debug_get_host_ns(h, buf, 1)
+for _ in range(500):
+    f(h, C.byref(cin), C.byref(out))
+lib.mppi_debug_get_host_ns(h, buf, 1)
+n = max(1, buf[7])
+names = ["build_params", "stage_costmap", "event0", "graph launch", "event1", "wait result", "copy-out+elapsed"]
+print("mppi_optimize host phases (us/call): " + ", ".join("%s %.2f" % (nm, buf[i] / n / 1e3) for i, nm in enumerate(names)))
