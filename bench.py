@@ -294,6 +294,7 @@ def main():
     # (the ctypes argument struct is marshalled once: the caller's buffers are plain host memory that does not change
     #  between cycles; every call still copies the record + costmap H2D and the result D2H inside the timed region)
     host_cycle = sc.cycle.packed()
+    e.set_timing(False)   # the controller does not read device_ms: no event records / read-back on the production path
     for _ in range(args.warmup):
         e.optimize(host_cycle)
     barrier()
@@ -304,6 +305,7 @@ def main():
         e.optimize(host_cycle)
         e2e_ms.append((time.perf_counter() - t0) * 1e3)
     barrier()
+    e.set_timing(True)
     clocks = sampler.stop()
     prof = e.get_profile()
     h2d, d2h = prof["h2d_bytes"], prof["d2h_bytes"]
@@ -346,8 +348,10 @@ def main():
             traffic = json.load(open(tpath)).get(sc.name)
         # the dominant kernel (largest share of the step) carries the roofline; the other one is reported beside it
         stream_layout = B_local >= 8192
-        k2_name = "rollout_score_stream_kernel" if stream_layout else "rollout_score_kernel"
-        k3_name = "path_costs_tm_kernel+weighted_sums_tm_kernel+merge_finalize_kernel" if stream_layout else "path_softmax_update_kernel"
+        fused = (not stream_layout) and k3_ms == 0.0   # the library reports K3 = 0 when the fused kernel ran
+        k2_name = "rollout_score_stream_kernel" if stream_layout else ("tile_fused_kernel" if fused else "rollout_score_kernel")
+        k3_name = ("path_costs_tm_kernel+weighted_sums_tm_kernel+merge_finalize_kernel" if stream_layout else
+                   ("(fused into tile_fused_kernel)" if fused else "path_softmax_update_kernel"))
         dom_name, dom_ms, oth_name, oth_ms = (k2_name, k2_ms, k3_name, k3_ms) if k2_ms >= k3_ms else (k3_name, k3_ms, k2_name, k2_ms)
         achieved = alg / (dom_ms * 1e-3) / 1e9
         line = {
@@ -367,17 +371,20 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "p50_ms": pct(e2e_ms, 50)},
             "gpu_launches": int(launches),
-            "kernels_ms": {"K2_rollout_score": k2_ms, "K3_path_softmax_update": k3_ms,
+            "kernels_ms": {("fused_rollout_score_update" if fused else "K2_rollout_score"): k2_ms, "K3_path_softmax_update": k3_ms,
                            "exchange_and_merge": float(np.mean(xch))},
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel_share_of_step": dom_ms / max(k2_ms + k3_ms + float(np.mean(xch)), 1e-9),
                          "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
-                         "other_kernel": {"kernel": oth_name, "ms": oth_ms, "achieved": alg / (oth_ms * 1e-3) / 1e9},
+                         "other_kernel": {"kernel": oth_name, "ms": oth_ms, "achieved": (alg / (oth_ms * 1e-3) / 1e9) if oth_ms > 0 else None},
                          "step_achieved": alg / ((k2_ms + k3_ms) * 1e-3) / 1e9,
-                         "note": "algorithmic bytes of one optimize() (SURVEY 8d: 12 B per rollout step, noise read once) over the "
-                                 "kernel's CUDA-event duration; the implementation reads the noise twice (K2 and the weighted sums), "
-                                 "so its ceiling is 0.5; small configs are L2-resident and latency-bound"},
+                         "note": ("algorithmic bytes of one optimize() (SURVEY 8d: 12 B per rollout step, noise read once) over the "
+                                  "kernel's CUDA-event duration; " +
+                                  ("the fused small-batch kernel reads the noise once and keeps the tile in shared memory; "
+                                   "the config is L2-resident, single-wave and latency-bound" if fused else
+                                   "the implementation reads the noise twice (K2 and the weighted sums), so its ceiling is "
+                                   "0.5; small configs are L2-resident and latency-bound"))},
             "timed_region_s": region_s,
         }
         if not args.no_cpu_baseline:

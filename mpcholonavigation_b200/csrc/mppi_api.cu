@@ -123,8 +123,10 @@ struct mppi_handle
   unsigned * d_fepoch{nullptr};           // completed fused launches (never reset: tags do not repeat)
   uint32_t fepoch_host{0};                // host mirror of *d_fepoch once everything enqueued has run
   uint2 * h_res{nullptr};                 // pinned + mapped: [3T + 8] result packets written by the kernels
+  bool zero_copy_now{false};              // this cycle's fused kernel pulls the upload out of pinned host memory itself
   bool wait_packets{false};               // the cycle in flight delivers its result as packets (no D2H copy, no stream sync)
   uint64_t host_ns[8]{0, 0, 0, 0, 0, 0, 0, 0};   // host-side time of the steady-state call by phase (mppi_debug_get_host_ns)
+  bool zero_copy_enabled{true};   // MPPI_ZERO_COPY=0 disables
   bool fused_enabled{true};    // small batches: one cooperative launch per iteration (tile_fused_kernel); MPPI_FUSED=0 disables
   int fused_key_N{-1};         // path size the cached decision below was taken for (the shared-memory size depends on it)
   bool fused_fits{false};      // the whole grid is co-resident (a cooperative launch needs that)
@@ -136,6 +138,7 @@ struct mppi_handle
   cudaGraphExec_t gexec[6]{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t gkey_params[6]{0, 0, 0, 0, 0, 0}, gkey_costmap[6]{0, 0, 0, 0, 0, 0};
   unsigned gkey_inst[6]{0, 0, 0, 0, 0, 0};
+  int gkey_fused[6]{0, 0, 0, 0, 0, 0};   // fused kernel: shared-memory key (path capacity, PathAlign samples); -1 = two-kernel path
   int tail_mode{0};            // 0: optimize only, 1: + evalControl tail, 2: + tail with shiftControlSequence
   // peer-memory exchange (one process per GPU; mppi_comm_get_mailbox_handle / mppi_comm_connect_peers)
   uint2 * d_mailbox{nullptr};             // this rank's mailbox (kBoxPackets packets)
@@ -533,6 +536,23 @@ mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, un
       const bool path_like = (kind == MPPI_CRITIC_PATH_FOLLOW && p.follow.on) || (kind == MPPI_CRITIC_PATH_ANGLE && p.angle.on) ||
         (kind == MPPI_CRITIC_PATH_ALIGN && p.align.on) || (kind == MPPI_CRITIC_PATH_ALIGN_LEGACY && p.legacy.on);
       if (path_like && p.first_path_q < 0) {p.first_path_q = q;}
+      unsigned char src = 0;
+      switch (kind) {
+        case MPPI_CRITIC_PATH_FOLLOW: src = p.follow.on ? 2 : 0; break;
+        case MPPI_CRITIC_PATH_ALIGN: src = p.align.on ? 3 : 0; break;
+        case MPPI_CRITIC_PATH_ALIGN_LEGACY: src = p.legacy.on ? 4 : 0; break;
+        case MPPI_CRITIC_PATH_ANGLE: src = p.angle.on ? 5 : 0; break;
+        case MPPI_CRITIC_CONSTRAINT: src = p.constraint.on ? 1 : 0; break;
+        case MPPI_CRITIC_COST: src = p.cost.on ? 1 : 0; break;
+        case MPPI_CRITIC_GOAL: src = p.goal.on ? 1 : 0; break;
+        case MPPI_CRITIC_GOAL_ANGLE: src = p.goal_angle.on ? 1 : 0; break;
+        case MPPI_CRITIC_OBSTACLES: src = p.obst.on ? 1 : 0; break;
+        case MPPI_CRITIC_PREFER_FORWARD: src = p.forward.on ? 1 : 0; break;
+        case MPPI_CRITIC_TWIRLING: src = p.twirl.on ? 1 : 0; break;
+        case MPPI_CRITIC_VELOCITY_DEADBAND: src = p.deadband.on ? 1 : 0; break;
+        default: break;
+      }
+      p.src_base[q] = src;
     }
     // first valid index at or after i (N if none)
     std::vector<int> & next_valid = h->scratch_next;
@@ -606,8 +626,9 @@ DevBuffers make_bufs(mppi_handle * h, int mode)
   b.peer.seq = h->d_seq;
   b.peer.rank = h->rank;
   b.peer.nranks = h->peer_mode ? h->nranks : 1;
-  b.pk_x1 = h->d_pk;
-  b.pk_rec = h->d_pk ? h->d_pk + h->upd_blocks : nullptr;
+  b.pk_up = h->d_pk;
+  b.pk_x1 = h->d_pk ? h->d_pk + h->upd_blocks : nullptr;
+  b.pk_rec = h->d_pk ? h->d_pk + 2 * h->upd_blocks : nullptr;
   b.epoch = h->d_fepoch;
   return b;
 }
@@ -633,7 +654,7 @@ mppi_status stage_costmap(mppi_handle * h, const mppi_costmap & cm)
     drop_graphs(h);
     char * d_new = nullptr, * h_new = nullptr;
     CUDA_TRY(h, cudaMalloc(&d_new, kParamsCapacity + 256 + bytes));
-    CUDA_TRY(h, cudaMallocHost(&h_new, kParamsCapacity + 256 + bytes));
+    CUDA_TRY(h, cudaHostAlloc(&h_new, kParamsCapacity + 256 + bytes, cudaHostAllocMapped | cudaHostAllocPortable));
     std::memcpy(h_new, h->h_params, kParamsCapacity);
     CUDA_TRY(h, cudaMemcpy(d_new, h->d_params, kParamsCapacity, cudaMemcpyDeviceToDevice));
     cudaFree(h->d_params);
@@ -649,11 +670,15 @@ mppi_status stage_costmap(mppi_handle * h, const mppi_costmap & cm)
   return MPPI_OK;
 }
 
+// bytes of [record | costmap], contiguous on both sides (stage_costmap)
+size_t upload_bytes(const mppi_handle * h)
+{
+  return ((h->params_copy_bytes + 255) & ~static_cast<size_t>(255)) + h->costmap_bytes;
+}
+
 mppi_status enqueue_uploads(mppi_handle * h)
 {
-  // record + costmap, contiguous on both sides (stage_costmap): one copy
-  const size_t off = (h->params_copy_bytes + 255) & ~static_cast<size_t>(255);
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_params, h->h_params, off + h->costmap_bytes, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_params, h->h_params, upload_bytes(h), cudaMemcpyHostToDevice, h->stream));
   return MPPI_OK;
 }
 
@@ -709,6 +734,7 @@ void launch_stream_instance(mppi_handle * h, int mode)
 mppi_status launch_regenerate(mppi_handle * h);
 
 constexpr int kFusedSmemMax = 226 * 1024;
+constexpr size_t kZeroCopyMaxBytes = 96 * 1024;   // larger uploads (big costmaps) go through the copy engine
 
 template<unsigned F, bool kExact>
 cudaError_t fused_occupancy(int threads, size_t smem, int * blocks_per_sm)
@@ -723,18 +749,26 @@ int fused_path_capacity(const mppi_handle * h)
   return std::min(MPPI_MAX_PATH_POINTS, ((h->last.N + 63) / 64) * 64);
 }
 
+// sampled poses of PathAlign the fused kernel keeps scratch for (0 when the critic is not in the list)
+int fused_align_samples(const mppi_handle * h)
+{
+  const DevParams & p = h->last;
+  return (p.align.idx >= 0 && p.align_step >= 1) ? (h->T + p.align_step - 1) / p.align_step : 0;
+}
+
 // Does this cycle run as ONE cooperative launch of tile_fused_kernel?  Single rank, tile layout, and the whole grid
 // co-resident (checked once per path size with the occupancy API; the generic instance is the largest one).
 bool use_fused(mppi_handle * h)
 {
   if (!h->fused_enabled || h->stream_layout || h->nranks > 1) {return false;}
   const int N = fused_path_capacity(h);
-  if (h->fused_key_N != N) {
-    h->fused_key_N = N;
+  const int key = N + 4096 * fused_align_samples(h);
+  if (h->fused_key_N != key) {
+    h->fused_key_N = key;
     h->fused_fits = false;
     const int S = pick_segments(h);
     const int grid = (h->B + kTile - 1) / kTile;
-    const size_t smem = fused_smem_bytes(h->T, S, N, grid);
+    const size_t smem = fused_smem_bytes(h->T, S, N, grid, fused_align_samples(h));
     int per_sm = 0;
     if (smem <= static_cast<size_t>(kFusedSmemMax) && fused_occupancy<SF_ALL, false>(kTile * S, smem, &per_sm) == cudaSuccess) {
       h->fused_fits = static_cast<long long>(per_sm) * h->num_sms >= grid;
@@ -745,28 +779,31 @@ bool use_fused(mppi_handle * h)
 }
 
 template<unsigned F, bool kExact>
-cudaError_t launch_fused_instance(mppi_handle * h, int iteration, uint2 * host_res)
+cudaError_t launch_fused_instance(mppi_handle * h, int iteration, uint2 * host_res, bool zero_copy)
 {
   const int S = pick_segments(h);
   const dim3 grid((h->B + kTile - 1) / kTile), block(kTile, S);
   int N = fused_path_capacity(h);
-  const size_t smem = fused_smem_bytes(h->T, S, N, grid.x);
+  const size_t smem = fused_smem_bytes(h->T, S, N, grid.x, fused_align_samples(h));
   const DevParams * dp = reinterpret_cast<const DevParams *>(h->d_params);
   const uint8_t * cm = h->d_costmap;
   DevBuffers bufs = make_bufs(h, 0);
   int B = h->B, T = h->T;
-  void * args[] = {&dp, &cm, &bufs, &B, &T, &N, &iteration, &host_res};
+  // zero-copy upload: the kernel pulls [record | costmap] out of the pinned staging buffer itself (first iteration only)
+  const uint4 * up_host = zero_copy ? reinterpret_cast<const uint4 *>(h->h_params) : nullptr;
+  int up_vecs = zero_copy ? static_cast<int>((upload_bytes(h) + 15) / 16) : 0;
+  void * args[] = {&dp, &cm, &bufs, &B, &T, &N, &iteration, &host_res, &up_host, &up_vecs};
   return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&tile_fused_kernel<F, kExact>), grid, block, args, smem, h->stream);
 }
 
-mppi_status launch_fused(mppi_handle * h, int iteration, uint2 * host_res)
+mppi_status launch_fused(mppi_handle * h, int iteration, uint2 * host_res, bool zero_copy)
 {
   cudaError_t e;
   switch (pick_stream_instance(stream_feature_need(h->last))) {
-    case kSfOmniDefault: e = launch_fused_instance<kSfOmniDefault, true>(h, iteration, host_res); break;
-    case kSfOmniDefaultFp: e = launch_fused_instance<kSfOmniDefaultFp, true>(h, iteration, host_res); break;
-    case kSfObstaclesFp: e = launch_fused_instance<kSfObstaclesFp, true>(h, iteration, host_res); break;
-    default: e = launch_fused_instance<SF_ALL, false>(h, iteration, host_res); break;
+    case kSfOmniDefault: e = launch_fused_instance<kSfOmniDefault, true>(h, iteration, host_res, zero_copy); break;
+    case kSfOmniDefaultFp: e = launch_fused_instance<kSfOmniDefaultFp, true>(h, iteration, host_res, zero_copy); break;
+    case kSfObstaclesFp: e = launch_fused_instance<kSfObstaclesFp, true>(h, iteration, host_res, zero_copy); break;
+    default: e = launch_fused_instance<SF_ALL, false>(h, iteration, host_res, zero_copy); break;
   }
   CUDA_TRY(h, e);
   h->launches++;
@@ -847,7 +884,7 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
       // small batches: rollout, critics, softmax update and merge in one cooperative launch (pev: all of it counts as K2)
       // the launch that completes the result writes it to pinned host memory itself (packets), unless the tail follows
       const bool last = it + 1 == h->cfg.iteration_count;
-      mppi_status s = launch_fused(h, it, last && !h->tail_mode ? h->h_res : nullptr);
+      mppi_status s = launch_fused(h, it, last && !h->tail_mode ? h->h_res : nullptr, h->zero_copy_now && it == 0);
       if (s != MPPI_OK) {return s;}
       if (prof) {
         CUDA_TRY(h, cudaEventRecord(h->pev[1], h->stream));
@@ -939,18 +976,30 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
   const bool prof = h->profiling && h->cfg.iteration_count == 1;
   const bool graph_ok = h->use_graph && !prof && (h->nranks == 1 || h->peer_mode);   // NCCL calls are not captured
   h->wait_packets = use_fused(h);
+  h->zero_copy_now = with_upload && h->wait_packets && h->zero_copy_enabled && upload_bytes(h) <= kZeroCopyMaxBytes;
   if (h->wait_packets) {h->fepoch_host += static_cast<uint32_t>(h->cfg.iteration_count);}
   h->d2h_bytes = h->wait_packets ? sizeof(uint2) * (3 * h->T + 2 + (h->tail_mode ? 3 : 0)) : sizeof(float) * (3 * h->T + 6);
-  h->h2d_bytes = with_upload ? ((h->params_copy_bytes + 255) & ~static_cast<size_t>(255)) + h->costmap_bytes : 0;
+  // zero-copy: every tile also reads the hot part of the record over PCIe
+  h->h2d_bytes = with_upload ? upload_bytes(h) + (h->zero_copy_now ? static_cast<size_t>(h->upd_blocks) * kHotBytes : 0) : 0;
   const uint64_t t_a = now_ns();
   if (h->timing) {CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));}
   const uint64_t t_b = now_ns();
   h->host_ns[2] += t_b - t_a;
   if (graph_ok) {
+    // the upload stays OUT of the graph: a copy node in a captured graph measured ~8 us slower than the same
+    // cudaMemcpyAsync issued on the stream in front of the graph launch (profiles/, host phases)
+    // Small uploads behind the fused kernel are not copied at all: the kernel reads the pinned staging buffer
+    // (zero_copy_now, slot 1); the copy engine -> kernel hand-over alone costs more than the PCIe reads.
+    if (with_upload && !h->zero_copy_now) {
+      const mppi_status us = enqueue_uploads(h);
+      if (us != MPPI_OK) {return us;}
+      with_upload = false;
+    }
     const int slot = (with_upload ? 1 : 0) + 2 * h->tail_mode;
     const unsigned inst = pick_stream_instance(stream_feature_need(h->last));   // the K2 instance is baked into the graph
+    const int fkey = h->wait_packets ? h->fused_key_N : -1;   // wait_packets == use_fused(h), evaluated above
     if (h->gexec[slot] && (h->gkey_params[slot] != h->params_copy_bytes || h->gkey_costmap[slot] != h->costmap_bytes ||
-      h->gkey_inst[slot] != inst))
+      h->gkey_inst[slot] != inst || h->gkey_fused[slot] != fkey))
     {
       cudaGraphExecDestroy(h->gexec[slot]);
       h->gexec[slot] = nullptr;
@@ -961,7 +1010,7 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
       CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
       h->capturing = true;
       mppi_status s = MPPI_OK;
-      if (with_upload) {s = enqueue_uploads(h);}
+      if (with_upload && !h->zero_copy_now) {s = enqueue_uploads(h);}
       if (s == MPPI_OK) {s = enqueue_kernels(h, false);}
       h->capturing = false;
       const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
@@ -977,6 +1026,7 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
         h->gkey_params[slot] = h->params_copy_bytes;
         h->gkey_costmap[slot] = h->costmap_bytes;
         h->gkey_inst[slot] = inst;
+        h->gkey_fused[slot] = fkey;
       }
     }
     if (h->gexec[slot]) {
@@ -991,7 +1041,7 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
     }
   }
   mppi_status s = MPPI_OK;
-  if (with_upload) {s = enqueue_uploads(h);}
+  if (with_upload && !h->zero_copy_now) {s = enqueue_uploads(h);}
   if (s != MPPI_OK) {return s;}
   if ((s = enqueue_kernels(h, prof)) != MPPI_OK) {return s;}
   if (h->timing) {CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));}
@@ -1084,6 +1134,7 @@ mppi_status finish_optimize(mppi_handle * h, mppi_cycle_out * out)
     // with sharding the span pev[1]..pev[2] also holds exchange 1; K3 alone is not separable there
     cudaEventElapsedTime(&h->prof_ms[1], h->pev[1], h->pev[2]);
     cudaEventElapsedTime(&h->prof_ms[2], h->pev[2], h->pev[3]);
+    if (h->wait_packets) {h->prof_ms[1] = 0.0f; h->prof_ms[2] = 0.0f;}   // fused kernel: everything is in [0]
   }
   h->host_ns[6] += now_ns() - t_b;
   h->host_ns[7] += 1;
@@ -1279,6 +1330,7 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   }
   if (const char * e = std::getenv("MPPI_NO_GRAPH")) {h->use_graph = std::atoi(e) == 0;}
   if (const char * e = std::getenv("MPPI_FUSED")) {h->fused_enabled = std::atoi(e) != 0;}
+  if (const char * e = std::getenv("MPPI_ZERO_COPY")) {h->zero_copy_enabled = std::atoi(e) != 0;}
   {
     // batches too small to fill the GPU with one thread per trajectory keep the latency-oriented tile kernel
     long long stream_min = 8192;    // measured cross-over on B200 (profiles/): below it the tile kernel wins
@@ -1349,7 +1401,7 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   CUDA_TRY(h, cudaMemsetAsync(h->d_seq, 0, sizeof(unsigned), h->stream));
   CUDA_TRY(h, cudaMalloc(&h->d_st, sizeof(DevState)));
   if (!h->stream_layout) {
-    const size_t n_pk = static_cast<size_t>(h->upd_blocks) * (1 + stride);
+    const size_t n_pk = static_cast<size_t>(h->upd_blocks) * (2 + stride);
     CUDA_TRY(h, cudaMalloc(&h->d_pk, n_pk * sizeof(uint2)));
     CUDA_TRY(h, cudaMemsetAsync(h->d_pk, 0, n_pk * sizeof(uint2), h->stream));
   }
@@ -1357,7 +1409,7 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   CUDA_TRY(h, cudaMemsetAsync(h->d_fepoch, 0, sizeof(unsigned), h->stream));
   CUDA_TRY(h, cudaHostAlloc(&h->h_res, (stride + 8) * sizeof(uint2), cudaHostAllocMapped | cudaHostAllocPortable));
   std::memset(h->h_res, 0, (stride + 8) * sizeof(uint2));
-  CUDA_TRY(h, cudaMallocHost(&h->h_params, kParamsCapacity + 256));
+  CUDA_TRY(h, cudaHostAlloc(&h->h_params, kParamsCapacity + 256, cudaHostAllocMapped | cudaHostAllocPortable));
   CUDA_TRY(h, cudaMallocHost(&h->h_out, (stride + 8) * sizeof(float)));
   return do_reset(h);
 }

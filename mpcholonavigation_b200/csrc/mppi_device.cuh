@@ -104,6 +104,9 @@ struct DevParams
   int fp_n;
   float cell_oxf, cell_oyf, cell_invf;       // fp32 filter of worldToMap (world_to_cell_fast): fl32(ox), fl32(oy), fl32(1/res)
   float cell_eps_x, cell_eps_y;              // and its error bounds in cells
+  // where the term of list position q comes from when the critic runs (fused kernel): 0 nothing (absent / disabled / gated
+  // off by the host), 1 K2's row, 2 PathFollow, 3 PathAlign, 4 PathAlignLegacy, 5 PathAngle
+  unsigned char src_base[kMaxCritics];
   // ---- everything above is the "hot" part every CTA copies into shared memory (kHotBytes) ----
   double fp_x[MPPI_MAX_FOOTPRINT], fp_y[MPPI_MAX_FOOTPRINT];   // footprint polygon
   // obstacle-critic look-up tables indexed by the byte cost: [0] point cost, [1] footprint cost
@@ -344,6 +347,18 @@ __device__ __forceinline__ float add_pow(float total, float value, unsigned powe
 {
   if (power == 1u) {return __fadd_rn(total, value);}
   return static_cast<float>(static_cast<double>(total) + pow(static_cast<double>(value), static_cast<double>(power)));
+}
+
+// the same, with the power != 1 branch out of line: for code that runs once per launch (tile / fused kernels), where the
+// inlined double-precision pow only makes the instruction footprint larger (these kernels stall on instruction fetch)
+__device__ __noinline__ float add_pow_slow(float total, float value, unsigned power)
+{
+  return static_cast<float>(static_cast<double>(total) + pow(static_cast<double>(value), static_cast<double>(power)));
+}
+__device__ __forceinline__ float add_pow_c(float total, float value, unsigned power)
+{
+  if (power == 1u) {return __fadd_rn(total, value);}
+  return add_pow_slow(total, value, power);
 }
 
 // sqrt for cost terms (1e-4 tolerance): one MUFU instead of the IEEE sequence

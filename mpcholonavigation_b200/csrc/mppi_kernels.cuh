@@ -54,6 +54,7 @@ struct DevBuffers
   PeerComm peer;        // sharded over peer memory when peer.nranks > 1
   // fused small-batch kernel: the exchanges between the tiles of one launch travel as self-validating packets
   // {value, tag of the launch} (the protocol of the peer exchange above, inside one GPU)
+  uint2 * pk_up;        // [G]            per tile: "my slice of the upload is in device memory"
   uint2 * pk_x1;        // [G]            per tile: furthest-point candidate | survivor flags << 16
   uint2 * pk_rec;       // [G][3T + 2]    per tile: softmax record (m, s, W[3T])
   unsigned * epoch;     // completed fused launches of this handle; the tag of the running launch is *epoch + 1
@@ -93,16 +94,21 @@ struct FusedShared
   uint16_t * follow;            // [N]
   float * e;          // [G] rescale factors of the merge
   float * red;        // [32] block reductions
+  float * ap;         // [8][2][32] PathAlign: per-warp partial (sum, count) of every trajectory
+  float * ad;         // [n_s][32]  PathAlign: segment length -> integrated distance of every sampled pose; behind it
+                      // [n_s][32]  int: lower bound | candidate << 16 -> chosen path point
 };
-__host__ __device__ inline size_t fused_extra_floats(int N, int G)
+// n_s: sampled poses of PathAlign (0 when the critic is not in the list)
+__host__ __device__ inline size_t fused_extra_floats(int N, int G, int n_s)
 {
   const int n16 = ((N + 15) / 16) * 16;
   return static_cast<size_t>(kMaxCritics + kGammaRows) * kTile + 4 * kTile + kTile + 8 + 3 * static_cast<size_t>(n16) +
-         n16 / 2 /* valid + flags bytes */ + n16 / 2 /* follow uint16 */ + static_cast<size_t>(((G + 31) / 32) * 32) + 32;
+         n16 / 2 /* valid + flags bytes */ + n16 / 2 /* follow uint16 */ + static_cast<size_t>(((G + 31) / 32) * 32) + 32 +
+         8 * 2 * kTile + 2 * static_cast<size_t>(n_s) * kTile;
 }
-__host__ __device__ inline size_t fused_smem_bytes(int T, int S, int N, int G)
+__host__ __device__ inline size_t fused_smem_bytes(int T, int S, int N, int G, int n_s)
 {
-  return sizeof(float) * (rollout_smem_floats(T, S, 6) + fused_extra_floats(N, G));
+  return sizeof(float) * (rollout_smem_floats(T, S, 6) + fused_extra_floats(N, G, n_s));
 }
 __device__ __forceinline__ FusedShared fused_carve(float * base, int N, int G)
 {
@@ -120,6 +126,8 @@ __device__ __forceinline__ FusedShared fused_carve(float * base, int N, int G)
   f.follow = reinterpret_cast<uint16_t *>(f.flags + n16);
   f.e = reinterpret_cast<float *>(f.follow + n16);
   f.red = f.e + ((G + 31) / 32) * 32;
+  f.ap = f.red + 32;
+  f.ad = f.ap + 8 * 2 * kTile;
   return f;
 }
 // what the K2 body hands to the fused tail
@@ -130,6 +138,12 @@ struct FusedCtx
   const float * s_cvx, * s_cvy, * s_cwz, * s_yaw, * s_x, * s_y;   // time-major tile planes [T][33]
   int n_cap, iteration;   // n_cap: path capacity the shared-memory carve-up was sized for (>= the record's N)
   unsigned tag;           // tag of this launch's packets
+  // zero-copy upload: the cycle's record + costmap sit in pinned host memory (up_host, up_vecs 16-byte vectors, laid
+  // out like the device buffer that starts at the record); every tile reads the hot part of the record straight from
+  // there and copies one slice of the whole into device memory, where the cold parts and the costmap are read once all
+  // tiles have signalled (before the first costmap access).  nullptr: the buffers are already resident.
+  const uint4 * up_host;
+  int up_vecs;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -274,6 +288,7 @@ __device__ __forceinline__ void rollout_tile_body(
     fx->fs = fs;
     fx->s_hot = s_hot; fx->s_cs = s_cs; fx->s_cvx = s_cvx; fx->s_cvy = s_cvy; fx->s_cwz = s_cwz; fx->s_yaw = s_yaw;
     fx->s_x = s_x; fx->s_y = s_y;
+    if (tid == 0) {reinterpret_cast<unsigned *>(fs.stat)[7] = 0u;}   // exchange-1 word of this tile, gathered in P6
   }
 
   const int b0 = blockIdx.x * kTile;
@@ -281,51 +296,95 @@ __device__ __forceinline__ void rollout_tile_body(
   const bool live = b < B;
 
   MPPI_TRACE_AT(0);
-  // ---- P1: stage the tile.  Warp `seg` owns rows seg, seg+S, ...; lane walks t (coalesced 128 B rows).
+  // ---- P1: stage the tile.  Everything this block needs from global memory is REQUESTED before anything is consumed
+  //      (the first touch of global memory costs ~1 us even on an L2 hit, so dependent waves are what to avoid): the hot
+  //      part of the record and the control sequence go to registers first, then the noise rows, then all of it is
+  //      stored to shared memory.
+  const bool zero_copy = kFused && fx->up_host != nullptr;
+  const float4 * hot_src = zero_copy ? reinterpret_cast<const float4 *>(fx->up_host) : reinterpret_cast<const float4 *>(P);
+  float4 hot_v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tid < kHotBytes / 16) {hot_v = __ldg(hot_src + tid);}
+  // zero-copy upload: this tile's slice of [record | costmap], two vectors per thread in flight, the rest (large
+  // costmaps) in a plain loop behind the staging
+  uint4 up_v[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+  int up_begin = 0, up_end = 0;
+  if (kFused) {
+    if (zero_copy) {
+      const int per = (fx->up_vecs + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+      up_begin = min(fx->up_vecs, static_cast<int>(blockIdx.x) * per);
+      up_end = min(fx->up_vecs, up_begin + per);
+      if (up_begin + tid < up_end) {up_v[0] = __ldg(fx->up_host + up_begin + tid);}
+      if (up_begin + nthreads + tid < up_end) {up_v[1] = __ldg(fx->up_host + up_begin + nthreads + tid);}
+    }
+  }
+  float cs_v[2] = {0.0f, 0.0f};
+  if (tid < 3 * T) {cs_v[0] = bufs.cs[tid];}
+  if (tid + nthreads < 3 * T) {cs_v[1] = bufs.cs[tid + nthreads];}
   if (mode == 0) {
-    // noise first (raw), in batches of 4 (row, 32-column) items = 12 loads in flight per lane; the control
-    // sequence is added once it and the record have landed (same barrier)
+    // Warp `seg` owns rows seg, seg+S, ...; lane walks t (coalesced 128 B rows).  A batch = kCols 32-step columns x 4
+    // rows (fused: 2 x 4 covers the tile in one wave for T <= 64 with 8 warps; the two-kernel instances run at 3 blocks
+    // per SM and keep fewer loads in flight).  The control sequence of the batch's columns rides in the same wave, so
+    // setNoisedControls (noise_generator.cpp:71-73), c = control_sequence + noise, happens on the way into the tile.
+    constexpr int kCols = kFused ? 2 : 1, kRows = 4;
     const int ncol = (T + 31) >> 5;
-    const int nitems = ((kTile - seg + S - 1) / S) * ncol;
-    for (int i0 = 0; i0 < nitems; i0 += 4) {
-      float va[4], vb[4], vc[4];
-      int oo[4];
+    const int nri = (kTile - seg + S - 1) / S;
+    for (int ri0 = 0; ri0 < nri; ri0 += kRows) {
+      for (int ci0 = 0; ci0 < ncol; ci0 += kCols) {
+        float ca[kCols], cb[kCols], cc[kCols];
+        float va[kCols][kRows], vb[kCols][kRows], vc[kCols][kRows];
+        int oo[kCols][kRows];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u;
-        const int ri = i / ncol, ci = i - ri * ncol;
-        const int r = seg + ri * S, t = (ci << 5) + lane;
-        const bool ok = i < nitems && t < T && b0 + r < B;
-        oo[u] = ok ? t * kPad + r : -1;
-        va[u] = vb[u] = vc[u] = 0.0f;
-        if (ok) {
-          const size_t g = static_cast<size_t>(b0 + r) * T + t;
-          va[u] = __ldg(bufs.in_a + g); vb[u] = __ldg(bufs.in_b + g); vc[u] = __ldg(bufs.in_c + g);
+        for (int c = 0; c < kCols; ++c) {
+          const int t = ((ci0 + c) << 5) + lane;
+          const bool okc = ci0 + c < ncol && t < T;
+          ca[c] = cb[c] = cc[c] = 0.0f;
+          if (okc) {ca[c] = bufs.cs[t]; cb[c] = bufs.cs[T + t]; cc[c] = bufs.cs[2 * T + t];}
+#pragma unroll
+          for (int rr = 0; rr < kRows; ++rr) {
+            const int r = seg + (ri0 + rr) * S;
+            const bool ok = okc && ri0 + rr < nri && b0 + r < B;
+            oo[c][rr] = ok ? t * kPad + r : -1;
+            va[c][rr] = vb[c][rr] = vc[c][rr] = 0.0f;
+            if (ok) {
+              const size_t g = static_cast<size_t>(b0 + r) * T + t;
+              va[c][rr] = __ldg(bufs.in_a + g); vb[c][rr] = __ldg(bufs.in_b + g); vc[c][rr] = __ldg(bufs.in_c + g);
+            }
+          }
         }
-      }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (oo[u] >= 0) {s_cvx[oo[u]] = va[u]; s_cvy[oo[u]] = vb[u]; s_cwz[oo[u]] = vc[u];}
+        for (int c = 0; c < kCols; ++c) {
+#pragma unroll
+          for (int rr = 0; rr < kRows; ++rr) {
+            if (oo[c][rr] >= 0) {
+              s_cvx[oo[c][rr]] = __fadd_rn(ca[c], va[c][rr]);
+              s_cvy[oo[c][rr]] = __fadd_rn(cb[c], vb[c][rr]);
+              s_cwz[oo[c][rr]] = __fadd_rn(cc[c], vc[c][rr]);
+            }
+          }
+        }
       }
     }
   }
   MPPI_TRACE_AT(1);
   if (kFused) {
-    // the path and its host-made tables (record tail, build_params): x[N] y[N] yaw[N] D[N] | valid[n16] flags[n16] follow[N]
-    const int N = min(__ldg(&P->N), fx->n_cap), n16 = ((N + 15) / 16) * 16;
-    const float * tail = reinterpret_cast<const float *>(P + 1);
-    const uint8_t * g_valid = reinterpret_cast<const uint8_t *>(tail + 4 * N);
-    const uint16_t * g_follow = reinterpret_cast<const uint16_t *>(g_valid + 2 * n16);
-    for (int j = tid; j < N; j += nthreads) {
-      fs.D[j] = __ldg(tail + 3 * N + j); fs.px[j] = __ldg(tail + j); fs.py[j] = __ldg(tail + N + j);
-      fs.valid[j] = __ldg(g_valid + j); fs.flags[j] = __ldg(g_valid + n16 + j); fs.follow[j] = __ldg(g_follow + j);
+    if (zero_copy) {
+      uint4 * dst = reinterpret_cast<uint4 *>(const_cast<DevParams *>(P));
+      if (up_begin + tid < up_end) {dst[up_begin + tid] = up_v[0];}
+      if (up_begin + nthreads + tid < up_end) {dst[up_begin + nthreads + tid] = up_v[1];}
+      for (int i = up_begin + 2 * nthreads + tid; i < up_end; i += nthreads) {dst[i] = __ldg(fx->up_host + i);}
+      __threadfence();   // the slice is visible device-wide before the tile's flag (sent after the barrier below)
     }
   }
-  for (int i = tid; i < 3 * T; i += nthreads) {s_cs[i] = bufs.cs[i];}
-  // hot part of the per-cycle record -> shared memory (one coalesced round trip instead of scattered loads)
-  load_hot_params(s_hot, P, tid, nthreads);
+  if (tid < kHotBytes / 16) {reinterpret_cast<float4 *>(s_hot)[tid] = hot_v;}
+  for (int i = tid + nthreads; i < kHotBytes / 16; i += nthreads) {reinterpret_cast<float4 *>(s_hot)[i] = __ldg(hot_src + i);}
+  if (tid < 3 * T) {s_cs[tid] = cs_v[0];}
+  if (tid + nthreads < 3 * T) {s_cs[tid + nthreads] = cs_v[1];}
+  for (int i = tid + 2 * nthreads; i < 3 * T; i += nthreads) {s_cs[i] = bufs.cs[i];}
   __syncthreads();
   MPPI_TRACE_AT(2);
+  if (kFused) {
+    if (zero_copy && tid == 0) {st_packet(bufs.pk_up + blockIdx.x, 1u, fx->tag);}
+  }
   const bool hol = MPPI_SF(SF_HOL, p.holonomic != 0);
   const bool acker = MPPI_SF(SF_ACKER, p.model == MPPI_MODEL_ACKERMANN);
   const bool con_on = MPPI_SF(SF_CON, p.constraint.on), fwd_on = MPPI_SF(SF_FWD, p.forward.on);
@@ -335,16 +394,8 @@ __device__ __forceinline__ void rollout_tile_body(
   constexpr bool kFp = (F & SF_FOOTPRINT) != 0, kSpill = (F & SF_SPILL) != 0;
   const float dt = p.dt;
   if (mode == 0) {
-    // setNoisedControls: c = control_sequence + noise (noise_generator.cpp:71-73), in place on this warp's rows
-    for (int r = seg; r < kTile; r += S) {
-      int o = lane * kPad + r;
-      for (int t = lane; t < T; t += 32, o += 32 * kPad) {
-        s_cvx[o] = __fadd_rn(s_cs[t], s_cvx[o]);
-        s_cvy[o] = __fadd_rn(s_cs[T + t], s_cvy[o]);
-        s_cwz[o] = __fadd_rn(s_cs[2 * T + t], s_cwz[o]);
-      }
-    }
-    // updateInitialStateVelocities (optimizer.cpp:258-267): v[:,0] = robot speed
+    // updateInitialStateVelocities (optimizer.cpp:258-267): v[:,0] = robot speed.  Written and read by warp 0 only
+    // (yaw scan, first segment), lane to lane: no barrier
     if (seg == 0) {
       s_v0[lane] = p.speed_vx; s_v0[kTile + lane] = hol ? p.speed_vy : 0.0f; s_v0[2 * kTile + lane] = p.speed_wz;
     }
@@ -373,8 +424,8 @@ __device__ __forceinline__ void rollout_tile_body(
       const int o = (T - 1) * kPad + lane;
       s_cvx[o] = 0.0f; s_cvy[o] = 0.0f; s_cwz[o] = 0.0f;
     }
+    __syncthreads();
   }
-  __syncthreads();
 
   MPPI_TRACE_AT(3);
   // my segment of the horizon, and the state velocities just before it (read before anyone overwrites a plane)
@@ -511,10 +562,35 @@ __device__ __forceinline__ void rollout_tile_body(
       if (do_x) {scan_plane(s_x, p.pose_x);}
       if (do_y) {scan_plane(s_y, p.pose_y);}
     }
+    if (kFused) {
+      // zero-copy upload: a warp that has no scan to do collects the flags of all tiles; behind the barrier below the
+      // device copies of the record and the costmap are complete
+      if (zero_copy && seg == min(2, S - 1)) {
+        for (int i = lane; i < static_cast<int>(gridDim.x); i += 32) {
+          unsigned v;
+          if (!poll_packet(bufs.pk_up + i, fx->tag, v)) {bufs.st->comm_error = 1u;}
+        }
+      }
+    }
   }
   __syncthreads();
 
   MPPI_TRACE_AT(6);
+  // fused: the path and its host-made tables (record tail, build_params: x[N] y[N] yaw[N] D[N] | valid[n16] flags[n16]
+  // follow[N]) are requested now and committed to shared memory behind the position critics, when they have long arrived
+  float pt_f[3] = {0.0f, 0.0f, 0.0f};
+  unsigned pt_b = 0u;
+  if (kFused) {
+    const int N = min(p.N, fx->n_cap), n16 = ((N + 15) / 16) * 16;
+    const float * tail = reinterpret_cast<const float *>(P + 1);
+    const uint8_t * g_valid = reinterpret_cast<const uint8_t *>(tail + 4 * N);
+    const uint16_t * g_follow = reinterpret_cast<const uint16_t *>(g_valid + 2 * n16);
+    if (tid < N) {
+      pt_f[0] = __ldg(tail + 3 * N + tid); pt_f[1] = __ldg(tail + tid); pt_f[2] = __ldg(tail + N + tid);
+      pt_b = __ldg(g_valid + tid) | (static_cast<unsigned>(__ldg(g_valid + n16 + tid)) << 8) |
+        (static_cast<unsigned>(__ldg(g_follow + tid)) << 16);
+    }
+  }
   // ---- P5: position critics + spills, parallel over (trajectory, segment of the horizon)
   if (live) {
     const bool want_cells = kSpill && p.want_cells != 0, spill = kSpill && p.spill_traj != 0;
@@ -634,6 +710,22 @@ __device__ __forceinline__ void rollout_tile_body(
   }
 #pragma unroll
   for (int k = 0; k < A_COUNT; ++k) {s_acc[(seg * A_COUNT + k) * kTile + lane] = acc[k];}
+  if (kFused) {
+    const int N = min(p.N, fx->n_cap), n16 = ((N + 15) / 16) * 16;
+    if (tid < N) {
+      fs.D[tid] = pt_f[0]; fs.px[tid] = pt_f[1]; fs.py[tid] = pt_f[2];
+      fs.valid[tid] = static_cast<uint8_t>(pt_b & 0xffu); fs.flags[tid] = static_cast<uint8_t>((pt_b >> 8) & 0xffu);
+      fs.follow[tid] = static_cast<uint16_t>(pt_b >> 16);
+    }
+    // paths longer than the block: plain loop (rare)
+    const float * tail = reinterpret_cast<const float *>(P + 1);
+    const uint8_t * g_valid = reinterpret_cast<const uint8_t *>(tail + 4 * N);
+    const uint16_t * g_follow = reinterpret_cast<const uint16_t *>(g_valid + 2 * n16);
+    for (int j = tid + nthreads; j < N; j += nthreads) {
+      fs.D[j] = __ldg(tail + 3 * N + j); fs.px[j] = __ldg(tail + j); fs.py[j] = __ldg(tail + N + j);
+      fs.valid[j] = __ldg(g_valid + j); fs.flags[j] = __ldg(g_valid + n16 + j); fs.follow[j] = __ldg(g_follow + j);
+    }
+  }
 
   MPPI_TRACE_AT(7);
   // ---- furthest reached path point candidate: argmin over the path of the end pose (utils.hpp:292-319),
@@ -660,76 +752,98 @@ __device__ __forceinline__ void rollout_tile_body(
   __syncthreads();
 
   MPPI_TRACE_AT(8);
-  // ---- P6: combine the segments in order, finish the per-critic terms, publish
-  if (seg == 0) {
-    float tot[A_COUNT];
-#pragma unroll
-    for (int k = 0; k < A_COUNT; ++k) {tot[k] = 0.0f;}
-    bool cost_collided = false, ob_collided = false;
-    for (int s = 0; s < S; ++s) {
-      const float * a = s_acc + static_cast<size_t>(s) * A_COUNT * kTile + lane;
-#pragma unroll
-      for (int k = 0; k <= A_GWZ; ++k) {tot[k] = s == 0 ? a[k * kTile] : __fadd_rn(tot[k], a[k * kTile]);}
-      if (!cost_collided) {
-        tot[A_COST_REP] += a[A_COST_REP * kTile];
-        cost_collided = a[A_COST_HIT * kTile] != 0.0f;
-      }
-      if (!ob_collided) {
-        tot[A_OB_TRAJ] += a[A_OB_TRAJ * kTile];
-        tot[A_OB_REP] += a[A_OB_REP * kTile];
-        ob_collided = a[A_OB_HIT * kTile] != 0.0f;
-      }
-    }
+  // ---- P6: combine the segments in order and finish the per-critic terms: accumulator k (and the critic row it feeds)
+  //      by warp k mod S, lane = trajectory; the collision flags gate the sums they belong to.  The furthest-point
+  //      candidate is combined by the last warp.  Nothing here is serial over the critics.
+  {
     const float Tf = static_cast<float>(T);
     float * rows = bufs.crit_rows;
     // a row goes to global memory for K3 (and the per-critic getter); the fused tail takes it from shared memory
     const bool rows_to_global = !kFused || p.want_critic_rows != 0;
     auto put = [&](int q, float v) {
-        if (kFused) {fs.rows[q * kTile + lane] = v;}
-        if (rows_to_global) {rows[static_cast<size_t>(q) * B + b] = v;}
+        if (live) {
+          if (kFused) {fs.rows[q * kTile + lane] = v;}
+          if (rows_to_global) {rows[static_cast<size_t>(q) * B + b] = v;}
+        }
       };
-    if (live) {
-      if (con_on) {put(p.constraint.idx, add_pow(0.0f, tot[A_CON] * p.constraint.weight, p.constraint.power));}
-      if (fwd_on) {put(p.forward.idx, add_pow(0.0f, tot[A_FWD] * p.forward.weight, p.forward.power));}
-      if (twirl_on) {put(p.twirl.idx, add_pow(0.0f, (tot[A_TWIRL] / Tf) * p.twirl.weight, p.twirl.power));}
-      if (db_on) {put(p.deadband.idx, add_pow(0.0f, tot[A_DB] * p.deadband.weight, p.deadband.power));}
-      if (goal_on) {put(p.goal.idx, add_pow(0.0f, (tot[A_GOAL] / Tf) * p.goal.weight, p.goal.power));}
-      if (gang_on) {put(p.goal_angle.idx, add_pow(0.0f, (tot[A_GANG] / Tf) * p.goal_angle.weight, p.goal_angle.power));}
-      if (cost_on) {   // cost_critic.cpp:159-166
-        const float rep = cost_collided ? p.cost_collision : tot[A_COST_REP];
-        put(p.cost.idx, add_pow(0.0f, p.cost.weight * rep / Tf, p.cost.power));
-      }
-      if (ob_on) {   // obstacles_critic.cpp:169-176
-        const float raw = ob_collided ? p.obst_collision : tot[A_OB_TRAJ];
-        const float v = (p.obst_critical_w * raw) + (p.obst_repulsion_w * tot[A_OB_REP] / Tf);
-        put(p.obst.idx, add_pow(0.0f, v, p.obst.power));
-      }
-      if (mode == 0) {
-        put(p.n_critics, tot[A_GVX]); put(p.n_critics + 1, tot[A_GVY]); put(p.n_critics + 2, tot[A_GWZ]);
+    const float * a0 = s_acc + lane;   // [s][k][32]
+    unsigned my_flags = 0u;            // fused: bit 16 = a trajectory of this tile survived the Cost critic, bit 17 = Obstacles
+    for (int k = seg; k < A_COUNT; k += S) {
+      if (k == A_COST_HIT || k == A_OB_REP || k == A_OB_HIT) {continue;}   // combined with the sums they gate
+      if (k <= A_GWZ) {
+        float t = a0[k * kTile];
+        for (int s = 1; s < S; ++s) {t = __fadd_rn(t, a0[(s * A_COUNT + k) * kTile]);}
+        switch (k) {
+          case A_CON: if (con_on) {put(p.constraint.idx, add_pow_c(0.0f, t * p.constraint.weight, p.constraint.power));} break;
+          case A_FWD: if (fwd_on) {put(p.forward.idx, add_pow_c(0.0f, t * p.forward.weight, p.forward.power));} break;
+          case A_TWIRL: if (twirl_on) {put(p.twirl.idx, add_pow_c(0.0f, (t / Tf) * p.twirl.weight, p.twirl.power));} break;
+          case A_DB: if (db_on) {put(p.deadband.idx, add_pow_c(0.0f, t * p.deadband.weight, p.deadband.power));} break;
+          case A_GOAL: if (goal_on) {put(p.goal.idx, add_pow_c(0.0f, (t / Tf) * p.goal.weight, p.goal.power));} break;
+          case A_GANG: if (gang_on) {put(p.goal_angle.idx, add_pow_c(0.0f, (t / Tf) * p.goal_angle.weight, p.goal_angle.power));} break;
+          case A_GVX: if (mode == 0) {put(p.n_critics, t);} break;
+          case A_GVY: if (mode == 0) {put(p.n_critics + 1, t);} break;
+          default: if (mode == 0) {put(p.n_critics + 2, t);} break;   // A_GWZ
+        }
+      } else if (k == A_COST_REP) {
+        if (cost_on) {   // cost_critic.cpp:159-166
+          float t = 0.0f;
+          bool hit = false;
+          for (int s = 0; s < S && !hit; ++s) {
+            t += a0[(s * A_COUNT + A_COST_REP) * kTile];
+            hit = a0[(s * A_COUNT + A_COST_HIT) * kTile] != 0.0f;
+          }
+          const float rep = hit ? p.cost_collision : t;
+          put(p.cost.idx, add_pow_c(0.0f, p.cost.weight * rep / Tf, p.cost.power));
+          // fail_flag input: did any trajectory of this tile survive?
+          const unsigned ok = __ballot_sync(0xffffffffu, live && !hit);
+          if (kFused) {
+            if (ok) {my_flags |= 0x10000u;}
+          } else if (lane == 0 && ok) {
+            atomicOr(&bufs.st->any_ok[p.cost.idx], 1u);
+          }
+        }
+      } else {   // A_OB_TRAJ (+ A_OB_REP, A_OB_HIT)
+        if (ob_on) {   // obstacles_critic.cpp:169-176
+          float t = 0.0f, rp = 0.0f;
+          bool hit = false;
+          for (int s = 0; s < S && !hit; ++s) {
+            t += a0[(s * A_COUNT + A_OB_TRAJ) * kTile];
+            rp += a0[(s * A_COUNT + A_OB_REP) * kTile];
+            hit = a0[(s * A_COUNT + A_OB_HIT) * kTile] != 0.0f;
+          }
+          const float raw = hit ? p.obst_collision : t;
+          put(p.obst.idx, add_pow_c(0.0f, (p.obst_critical_w * raw) + (p.obst_repulsion_w * rp / Tf), p.obst.power));
+          const unsigned ok = __ballot_sync(0xffffffffu, live && !hit);
+          if (kFused) {
+            if (ok) {my_flags |= 0x20000u;}
+          } else if (lane == 0 && ok) {
+            atomicOr(&bufs.st->any_ok[p.obst.idx], 1u);
+          }
+        }
       }
     }
-    // fail_flag inputs: did any trajectory of this tile survive?  + this tile's furthest-point candidate
-    unsigned cost_ok = 0u, ob_ok = 0u, cand = 0u;
-    if (cost_on) {cost_ok = __ballot_sync(0xffffffffu, live && !cost_collided);}
-    if (ob_on) {ob_ok = __ballot_sync(0xffffffffu, live && !ob_collided);}
-    if (need_furthest) {
+    // this tile's furthest-point candidate: the segments' minima combined in order so the first minimum wins
+    if (seg == S - 1 && need_furthest) {
       float best = s_amin_d[lane];
       int best_j = s_amin_j[lane];
       for (int s = 1; s < S; ++s) {
         const float d = s_amin_d[s * kTile + lane];
         if (d < best) {best = d; best_j = s_amin_j[s * kTile + lane];}
       }
-      cand = warp_max_u(live ? static_cast<unsigned>(best_j) : 0u);
+      const unsigned cand = warp_max_u(live ? static_cast<unsigned>(best_j) : 0u);
+      if (kFused) {
+        my_flags |= cand;   // path indices are < MPPI_MAX_PATH_POINTS <= 2^16
+      } else if (lane == 0) {
+        atomicMax(&bufs.st->furthest_candidate, cand);
+      }
     }
     if (kFused) {
-      // exchange 1 inside the GPU: one self-validating packet per tile (path indices are < MPPI_MAX_PATH_POINTS <= 2^16)
-      if (lane == 0) {
-        st_packet(bufs.pk_x1 + blockIdx.x, cand | (cost_ok ? 0x10000u : 0u) | (ob_ok ? 0x20000u : 0u), fx->tag);
-      }
-    } else if (lane == 0) {
-      if (cost_ok) {atomicOr(&bufs.st->any_ok[p.cost.idx], 1u);}
-      if (ob_ok) {atomicOr(&bufs.st->any_ok[p.obst.idx], 1u);}
-      if (need_furthest) {atomicMax(&bufs.st->furthest_candidate, cand);}
+      // exchange 1 inside the GPU: one self-validating packet per tile {candidate | survivor flags << 16, tag}, put
+      // together from the warps that own the pieces
+      unsigned * s_x1 = reinterpret_cast<unsigned *>(fs.stat) + 7;   // zeroed at kernel start
+      if (lane == 0 && my_flags) {atomicOr(s_x1, my_flags);}
+      __syncthreads();         // also publishes fs.rows to the tail
+      if (tid == 0) {st_packet(bufs.pk_x1 + blockIdx.x, *s_x1, fx->tag);}
     }
   }
   MPPI_TRACE_AT(9);
@@ -1671,40 +1785,68 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
 // on the critical path.  The launch is cooperative: all blocks are co-resident, the bounded polls never time out in
 // normal operation.
 // ---------------------------------------------------------------------------------------------------
-// PathAlignCritic::score (path_align_critic.cpp:92-135) for trajectory r of the tile, by one warp; lane = sampled pose.
-__device__ __forceinline__ float path_align_warp(
-  const DevParams * P, const FusedCtx & fx, int r, int furthest, const float * __restrict__ path_yaw, int lane)
+// PathAlignCritic::score (path_align_critic.cpp:92-135) for the 32 trajectories of the tile, by the whole block:
+// lane = trajectory (every instruction serves 32 trajectories), and the sampled poses are dealt to the warps wherever the
+// reference's loop carries nothing from one sample to the next.  The two carried dependences (the integrated distance
+// and the previous path point) are walked by warp 0 alone: one add / one compare per sample.
+//   A  all warps   segment length of every sampled pose (one IEEE sqrt each)
+//   B  warp 0      traj_integrated_distance: the reference's sequential fp32 sum
+//   -- independent of the furthest reached point up to here: runs while exchange 1 is in flight --
+//   C  all warps   c = lower_bound(D[0, n), distance); utils::findClosestPathPt (utils.hpp:665-675) searches [init, n)
+//                  with init = the previous answer: the answer is 0 when c <= init, else g = n - 1 (c == n) or the
+//                  nearer of c - 1 and c.  c and g do not depend on init.
+//   D  warp 0      the chain over init
+//   E  all warps   distance to the chosen path point where it is valid
+//   F  warp 0      mean over the valid samples, cost
+__device__ __forceinline__ void path_align_distances(
+  const DevParams * P, const FusedCtx & fx, int lane, int seg, int S)
 {
   const int T = P->T, step = P->align_step;
   const int n_s = (T + step - 1) / step;     // sampled poses p = 0, step, 2 step, ... < T
+  float * ad = fx.fs.ad;
+  for (int k = 1 + seg; k < n_s; k += S) {
+    const int o = k * step * kPad + lane;
+    const float dxp = __fsub_rn(fx.s_x[o], fx.s_x[o - step * kPad]), dyp = __fsub_rn(fx.s_y[o], fx.s_y[o - step * kPad]);
+    ad[k * kTile + lane] = __fsqrt_rn(__fadd_rn(__fmul_rn(dxp, dxp), __fmul_rn(dyp, dyp)));
+  }
+  __syncthreads();
+  if (seg == 0) {
+    float acc = 0.0f;
+    for (int k0 = 1; k0 < n_s; k0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {v[u] = ad[min(k0 + u, n_s - 1) * kTile + lane];}
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (k0 + u < n_s) {
+          acc = __fadd_rn(acc, v[u]);
+          ad[(k0 + u) * kTile + lane] = acc;
+        }
+      }
+    }
+  }
+}
+
+// phases C..F; the value returned to the lanes of warp 0 is the critic's term of trajectory `lane`.  Starts with a barrier
+// of its own only where a phase needs the previous one (the caller has synchronised after the decisions).
+__device__ __forceinline__ float path_align_finish(
+  const DevParams * P, const FusedCtx & fx, int furthest, const float * __restrict__ path_yaw, int lane, int seg, int S)
+{
+  const int T = P->T, step = P->align_step;
+  const int n_s = (T + step - 1) / step;
   const int n = furthest;                    // the arc-length prefix D[0, n) is searched
   const float * D = fx.fs.D;
-  float carry_d = 0.0f, summed = 0.0f;
-  int carry_pt = 0, num = 0;
-  for (int k0 = 1; k0 < n_s; k0 += 32) {
-    const int k = k0 + lane;
-    const bool act = k < n_s;
-    const int o = (act ? k : k0) * step * kPad + r;       // idle lanes shadow a valid sample
-    const float Tx = fx.s_x[o], Ty = fx.s_y[o];
-    const float dxp = __fsub_rn(Tx, fx.s_x[o - step * kPad]), dyp = __fsub_rn(Ty, fx.s_y[o - step * kPad]);
-    const float d = act ? __fsqrt_rn(__fadd_rn(__fmul_rn(dxp, dxp), __fmul_rn(dyp, dyp))) : 0.0f;
-    const int cnt = min(32, n_s - k0);
-    // traj_integrated_distance: the reference's sequential fp32 sum, every lane follows the same chain
-    float acc = carry_d, mine = 0.0f;
-    for (int j = 0; j < cnt; ++j) {
-      acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, d, j));
-      if (lane == j) {mine = acc;}
+  const float * ad = fx.fs.ad;
+  int * ac = reinterpret_cast<int *>(fx.fs.ad + n_s * kTile);
+  int top = 1;                               // largest power of two <= max(n, 1)
+  while (top * 2 <= n) {top *= 2;}
+  for (int k = 1 + seg; k < n_s; k += S) {
+    const float mine = ad[k * kTile + lane];
+    int c = 0;                               // number of prefix entries below the distance = lower_bound
+    for (int bit = top; bit > 0; bit >>= 1) {
+      const int probe = c + bit;
+      if (probe <= n && D[probe - 1] < mine) {c = probe;}
     }
-    carry_d = acc;
-    // utils::findClosestPathPt (utils.hpp:665-675) = lower_bound over [init, n) with init = the previous answer.
-    // c = lower_bound over the whole prefix does not depend on init: the answer is 0 when c <= init, else
-    // g = n - 1 (c == n) or the nearer of c - 1 and c.
-    int lo = 0, hi = n;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (D[mid] < mine) {lo = mid + 1;} else {hi = mid;}
-    }
-    const int c = lo;
     int g = 0;
     if (c > 0) {
       if (c >= n) {
@@ -1713,35 +1855,56 @@ __device__ __forceinline__ float path_align_warp(
         g = __fsub_rn(mine, D[c - 1]) < __fsub_rn(D[c], mine) ? c - 1 : c;
       }
     }
-    int prev = carry_pt, res = 0;
-    for (int j = 0; j < cnt; ++j) {
-      const int cj = __shfl_sync(0xffffffffu, c, j), gj = __shfl_sync(0xffffffffu, g, j);
-      const int cur = cj <= prev ? 0 : gj;
-      if (lane == j) {res = cur;}
-      prev = cur;
+    ac[k * kTile + lane] = c | (g << 16);    // both < 2^16
+  }
+  __syncthreads();
+  if (seg == 0) {
+    int prev = 0;
+    for (int k0 = 1; k0 < n_s; k0 += 8) {
+      int v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {v[u] = ac[min(k0 + u, n_s - 1) * kTile + lane];}
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (k0 + u < n_s) {
+          prev = (v[u] & 0xffff) <= prev ? 0 : (v[u] >> 16);
+          ac[(k0 + u) * kTile + lane] = prev;
+        }
+      }
     }
-    carry_pt = prev;
-    const bool ok = act && fx.fs.valid[res] != 0;
-    float term = 0.0f;
-    if (ok) {
-      const float dx = __fsub_rn(fx.fs.px[res], Tx), dy = __fsub_rn(fx.fs.py[res], Ty);
+  }
+  __syncthreads();
+  float psum = 0.0f, pnum = 0.0f;
+  for (int k = 1 + seg; k < n_s; k += S) {
+    const int res = ac[k * kTile + lane];
+    if (fx.fs.valid[res]) {
+      const int o = k * step * kPad + lane;
+      const float dx = __fsub_rn(fx.fs.px[res], fx.s_x[o]), dy = __fsub_rn(fx.fs.py[res], fx.s_y[o]);
+      pnum += 1.0f;
       // the distance itself only feeds the cost (1e-4 tolerance): one MUFU instead of the IEEE sequence
       if (P->align_use_yaw) {
         const float dyaw = static_cast<float>(normalize_angle_d(static_cast<double>(fx.s_yaw[o]) - static_cast<double>(__ldg(path_yaw + res))));
-        term = sqrt_approx(dx * dx + dy * dy + dyaw * dyaw);
+        psum += sqrt_approx(dx * dx + dy * dy + dyaw * dyaw);
       } else {
-        term = sqrt_approx(dx * dx + dy * dy);
+        psum += sqrt_approx(dx * dx + dy * dy);
       }
     }
-    num += __popc(__ballot_sync(0xffffffffu, ok));
-    summed += warp_sum(term);
   }
-  const float cost = num > 0 ? __fdiv_rn(summed, static_cast<float>(num)) : 0.0f;
-  return add_pow(0.0f, __fmul_rn(cost, P->align.weight), P->align.power);
+  fx.fs.ap[(seg * 2) * kTile + lane] = psum;
+  fx.fs.ap[(seg * 2 + 1) * kTile + lane] = pnum;
+  __syncthreads();
+  float term = 0.0f;
+  if (seg == 0) {
+    float summed = 0.0f, num = 0.0f;
+    for (int w = 0; w < S; ++w) {summed += fx.fs.ap[(w * 2) * kTile + lane]; num += fx.fs.ap[(w * 2 + 1) * kTile + lane];}
+    const float cost = num > 0.0f ? __fdiv_rn(summed, num) : 0.0f;
+    term = add_pow_c(0.0f, __fmul_rn(cost, P->align.weight), P->align.power);
+  }
+  return term;
 }
 
 // PathAlignLegacyCritic::score (path_align_legacy_critic.cpp:97-128) for trajectory r, by one warp; lane = sampled pose
-__device__ __forceinline__ float path_align_legacy_warp(
+__device__ __noinline__ float path_align_legacy_warp(
   const DevParams * P, const FusedCtx & fx, int r, const float * __restrict__ path_yaw, int lane)
 {
   const int T = P->T, step = P->legacy_step, segs = P->N - 1;
@@ -1770,11 +1933,11 @@ __device__ __forceinline__ float path_align_legacy_warp(
     summed += warp_sum(contrib);
   }
   const float evals = static_cast<float>(T / step);
-  return add_pow(0.0f, __fmul_rn(__fdiv_rn(summed, evals), P->legacy.weight), P->legacy.power);
+  return add_pow_c(0.0f, __fmul_rn(__fdiv_rn(summed, evals), P->legacy.weight), P->legacy.power);
 }
 
 // PathAngleCritic::score (path_angle_critic.cpp:85-100) for trajectory r, by one warp; lane = time step
-__device__ __forceinline__ float path_angle_warp(const DevParams * P, const FusedCtx & fx, int r, int angle_idx, int lane)
+__device__ __noinline__ float path_angle_warp(const DevParams * P, const FusedCtx & fx, int r, int angle_idx, int lane)
 {
   const int T = P->T;
   const float gx = fx.fs.px[angle_idx], gy = fx.fs.py[angle_idx];
@@ -1792,7 +1955,7 @@ __device__ __forceinline__ float path_angle_warp(const DevParams * P, const Fuse
     sum += static_cast<float>(v);
   }
   sum = warp_sum(sum);
-  return add_pow(0.0f, (sum / static_cast<float>(T)) * P->angle.weight, P->angle.power);
+  return add_pow_c(0.0f, (sum / static_cast<float>(T)) * P->angle.weight, P->angle.power);
 }
 
 __device__ __forceinline__ unsigned warp_or_u(unsigned v)
@@ -1813,13 +1976,15 @@ __device__ __forceinline__ void put_result(float * out, uint2 * host_res, int id
 template<unsigned F, bool kExact>
 __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
   const DevParams * __restrict__ Pg, const uint8_t * __restrict__ cm, DevBuffers bufs, const int B, const int T, const int n_cap,
-  const int iteration, uint2 * host_res)
+  const int iteration, uint2 * host_res, const uint4 * up_host, const int up_vecs)
 {
   // n_cap (path capacity, a multiple of 64) sizes the shared memory; the path size itself comes from the record, so a
   // captured graph survives the small changes of the pruned path from cycle to cycle
   __shared__ K3Decisions dec;
+  __shared__ signed char s_src[kMaxCritics];
   FusedCtx fx;
   fx.n_cap = n_cap; fx.iteration = iteration;
+  fx.up_host = up_host; fx.up_vecs = up_vecs;
   const unsigned tag = ld_volatile_u32(bufs.epoch) + 1u;
   fx.tag = tag;
   rollout_tile_body<F, kExact, 0, true>(Pg, cm, bufs, B, T, &fx);
@@ -1835,6 +2000,9 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
   const int N = P->N;
   const float * __restrict__ path_yaw = reinterpret_cast<const float *>(Pg + 1) + 2 * N;
 
+  // PathAlign, the part that does not depend on the furthest reached point: done while exchange 1 is in flight
+  if (P->align.on) {path_align_distances(P, fx, lane, seg, S);}
+
   // ---- exchange 1 inside the GPU: warp 0 collects every tile's packet (furthest-point candidate, survivor flags)
   if (seg == 0) {
     unsigned cand = 0u, flags = 0u;
@@ -1847,29 +2015,64 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
     cand = warp_max_u(cand);
     flags = warp_or_u(flags);
     MPPI_TRACE_AT(10);
-    if (lane == 0) {
-      unsigned any_ok[kMaxCritics], state[4];
-#pragma unroll
-      for (int q = 0; q < kMaxCritics; ++q) {
-        any_ok[q] = (q == P->cost.idx && (flags & 1u)) || (q == P->obst.idx && (flags & 2u)) ? 1u : 0u;
+    // the decisions (k3_decide's logic on this launch's reductions), by every lane of warp 0 redundantly; lane q also
+    // derives where the term of list position q comes from
+    {
+      const int nc = P->n_critics;
+      int fail_at = nc;
+      unsigned furthest = 0u;
+      int fset = 0;
+      if (iteration == 0) {
+        fset = P->preset_furthest != kUnset; furthest = fset ? P->preset_furthest : 0u;
+      } else {
+        // carried over from the previous iteration's launch (critic_manager.cpp: fail_flag is only cleared in prepare())
+        fset = st->furthest_set; furthest = st->furthest;
+        if (st->fail_flag) {fail_at = -1;}
       }
-      state[0] = cand;
-      state[1] = st->furthest;                                  // written by the previous iteration's launch
-      state[2] = static_cast<unsigned>(st->furthest_set);
-      state[3] = static_cast<unsigned>(st->fail_flag);
-      k3_decide(P, N, any_ok, state, fs.flags, fs.follow, iteration, &dec);
+      if (fail_at == nc) {
+        // the first obstacle-type critic (list order) that saw no surviving trajectory raises fail_flag
+        const int q0 = P->obstacle_q[0], q1 = P->obstacle_q[1];
+        const bool ok0 = q0 == P->cost.idx ? (flags & 1u) != 0u : (flags & 2u) != 0u;
+        const bool ok1 = q1 == P->cost.idx ? (flags & 1u) != 0u : (flags & 2u) != 0u;
+        if (q0 >= 0 && !ok0) {
+          fail_at = q0;
+        } else if (q1 >= 0 && !ok1) {
+          fail_at = q1;
+        }
+      }
+      // the first enabled path critic in list order calls setPathFurthestPointIfNotSet (utils.hpp:350-355)
+      if (!fset && P->first_path_q >= 0 && P->first_path_q <= fail_at) {furthest = cand; fset = 1;}
+      const int f = min(static_cast<int>(furthest), N - 1);
+      const unsigned gates = fs.flags[f];
+      const int align_go = (P->align.on && P->align.idx <= fail_at && (gates & 1u)) ? 1 : 0;
+      const int legacy_go = (P->legacy.on && P->legacy.idx <= fail_at && (gates & 2u)) ? 1 : 0;
+      const int angle_go = (P->angle.on && P->angle.idx <= fail_at && (gates & 4u)) ? 1 : 0;
+      if (lane == 0) {
+        dec.fail_at = fail_at;
+        dec.furthest = static_cast<int>(furthest);
+        dec.furthest_set = fset;
+        dec.follow_idx = (P->follow.on && P->follow.idx <= fail_at) ? fs.follow[f] : 0;
+        dec.align_go = align_go; dec.legacy_go = legacy_go; dec.angle_go = angle_go;
+        dec.angle_idx = min(static_cast<int>(furthest) + P->angle_offset, N - 1);
+      }
+      if (lane < nc) {
+        int src = lane <= fail_at ? P->src_base[lane] : 0;
+        if ((src == 3 && !align_go) || (src == 4 && !legacy_go) || (src == 5 && !angle_go)) {src = 0;}
+        s_src[lane] = static_cast<signed char>(src);
+      }
     }
   }
   __syncthreads();
   MPPI_TRACE_AT(11);
 
-  // ---- path critics that need more than the end pose: one warp per trajectory
-  if (dec.align_go || dec.legacy_go || dec.angle_go) {
+  // ---- path critics that need more than the end pose.  PathAlign: the whole block, lane = trajectory
+  if (dec.align_go) {
+    const float v = path_align_finish(P, fx, dec.furthest, path_yaw, lane, seg, S);
+    if (seg == 0) {fs.term[1 * kTile + lane] = v;}
+  }
+  // PathAlignLegacy, PathAngle: one warp per trajectory
+  if (dec.legacy_go || dec.angle_go) {
     for (int r = seg; r < rows_here; r += S) {
-      if (dec.align_go) {
-        const float v = path_align_warp(P, fx, r, dec.furthest, path_yaw, lane);
-        if (lane == 0) {fs.term[1 * kTile + r] = v;}
-      }
       if (dec.legacy_go) {
         const float v = path_align_legacy_warp(P, fx, r, path_yaw, lane);
         if (lane == 0) {fs.term[2 * kTile + r] = v;}
@@ -1884,69 +2087,38 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
   MPPI_TRACE_AT(12);
 
   // ---- totals in critic-list order with the fail_flag short-circuit (critic_manager.cpp:67-76), gamma term,
-  //      block-local softmax record (optimizer.cpp:362-391); warp 0, lane = trajectory
+  //      block-local softmax record (optimizer.cpp:362-391); warp 0, lane = trajectory.  s_src (made with the decisions)
+  //      says where the term of list position q comes from: 0 nothing, 1 K2's row, 2.. the path critic terms.
   const float inv_temp = 1.0f / P->temperature;
   if (seg == 0) {
     const int b = b0 + lane;
     const bool live = b < B;
-    const int nc = P->n_critics, fail_at = dec.fail_at;
+    const int nc = P->n_critics;
     float total = 3.402823466e+38f;
     if (live) {
       total = iteration == 0 ? 0.0f : bufs.costs[b];
-      float * rows = bufs.crit_rows;
+      if (P->follow.on && P->follow.idx <= dec.fail_at) {    // path_follow_critic.cpp:60-70
+        const float dx = fx.s_x[(T - 1) * kPad + lane] - fs.px[dec.follow_idx];
+        const float dy = fx.s_y[(T - 1) * kPad + lane] - fs.py[dec.follow_idx];
+        fs.term[lane] = add_pow_c(0.0f, P->follow.weight * sqrtf(dx * dx + dy * dy), P->follow.power);
+      }
       for (int q = 0; q < nc; ++q) {
-        if (q > fail_at) {break;}
-        const int kind = P->kind_of[q];
-        float term = 0.0f;
-        bool has = false, from_path = true;
-        switch (kind) {
-          case MPPI_CRITIC_PATH_FOLLOW:
-            if (P->follow.on) {    // path_follow_critic.cpp:60-70
-              const float dx = fx.s_x[(T - 1) * kPad + lane] - fs.px[dec.follow_idx];
-              const float dy = fx.s_y[(T - 1) * kPad + lane] - fs.py[dec.follow_idx];
-              term = add_pow(0.0f, P->follow.weight * sqrtf(dx * dx + dy * dy), P->follow.power);
-              has = true;
-            }
-            break;
-          case MPPI_CRITIC_PATH_ALIGN: if (dec.align_go) {term = fs.term[1 * kTile + lane]; has = true;} break;
-          case MPPI_CRITIC_PATH_ALIGN_LEGACY: if (dec.legacy_go) {term = fs.term[2 * kTile + lane]; has = true;} break;
-          case MPPI_CRITIC_PATH_ANGLE: if (dec.angle_go) {term = fs.term[3 * kTile + lane]; has = true;} break;
-          case MPPI_CRITIC_CONSTRAINT: has = P->constraint.on; from_path = false; break;
-          case MPPI_CRITIC_COST: has = P->cost.on; from_path = false; break;
-          case MPPI_CRITIC_GOAL: has = P->goal.on; from_path = false; break;
-          case MPPI_CRITIC_GOAL_ANGLE: has = P->goal_angle.on; from_path = false; break;
-          case MPPI_CRITIC_OBSTACLES: has = P->obst.on; from_path = false; break;
-          case MPPI_CRITIC_PREFER_FORWARD: has = P->forward.on; from_path = false; break;
-          case MPPI_CRITIC_TWIRLING: has = P->twirl.on; from_path = false; break;
-          case MPPI_CRITIC_VELOCITY_DEADBAND: has = P->deadband.on; from_path = false; break;
-          default: from_path = false; break;
-        }
-        if (from_path) {
-          if (P->want_critic_rows) {rows[static_cast<size_t>(q) * B + b] = term;}   // for the per-critic getter
-        } else if (has) {
-          term = fs.rows[q * kTile + lane];
-        }
-        if (has) {total = __fadd_rn(total, term);}
+        const int src = s_src[q];
+        if (src == 0) {continue;}
+        const float term = src == 1 ? fs.rows[q * kTile + lane] : fs.term[(src - 2) * kTile + lane];
+        total = __fadd_rn(total, term);
       }
       if (P->want_critic_rows) {
-        // rows of critics that did not run read as zero for the per-critic getter (mppi_get_critic_costs)
+        // per-critic getter (mppi_get_critic_costs): path critic rows come from here, rows of critics that did not
+        // run read as zero
+        float * rows = bufs.crit_rows;
         for (int q = 0; q < nc; ++q) {
-          const int kind = P->kind_of[q];
-          const bool from_path = kind == MPPI_CRITIC_PATH_FOLLOW || kind == MPPI_CRITIC_PATH_ALIGN ||
-            kind == MPPI_CRITIC_PATH_ALIGN_LEGACY || kind == MPPI_CRITIC_PATH_ANGLE;
-          bool on = false;
-          switch (kind) {
-            case MPPI_CRITIC_CONSTRAINT: on = P->constraint.on; break;
-            case MPPI_CRITIC_COST: on = P->cost.on; break;
-            case MPPI_CRITIC_GOAL: on = P->goal.on; break;
-            case MPPI_CRITIC_GOAL_ANGLE: on = P->goal_angle.on; break;
-            case MPPI_CRITIC_OBSTACLES: on = P->obst.on; break;
-            case MPPI_CRITIC_PREFER_FORWARD: on = P->forward.on; break;
-            case MPPI_CRITIC_TWIRLING: on = P->twirl.on; break;
-            case MPPI_CRITIC_VELOCITY_DEADBAND: on = P->deadband.on; break;
-            default: break;
+          const int src = s_src[q];
+          if (src >= 2) {
+            rows[static_cast<size_t>(q) * B + b] = fs.term[(src - 2) * kTile + lane];
+          } else if (src == 0) {
+            rows[static_cast<size_t>(q) * B + b] = 0.0f;
           }
-          if (q > fail_at || (!from_path && !on)) {rows[static_cast<size_t>(q) * B + b] = 0.0f;}
         }
       }
       // gamma term (optimizer.cpp:367-380): vx, then wz, then vy (holonomic)
@@ -1999,22 +2171,25 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
   }
   if (static_cast<int>(blockIdx.x) >= T) {return;}   // owns no time step
   const uint2 * recs = bufs.pk_rec;
+  const bool small = G <= 32;   // one record per lane: every warp rescales on its own, one memory round trip in all
   float m = 3.402823466e+38f;
-  for (int i = tid; i < G; i += nthr) {
-    unsigned bits;
-    if (!poll_packet(recs + static_cast<size_t>(i) * stride, tag, bits)) {st->comm_error = 1u;}
-    const float mi = __uint_as_float(bits);
-    fs.e[i] = mi;
-    m = fminf(m, mi);
+  if (!small) {
+    for (int i = tid; i < G; i += nthr) {
+      unsigned bits;
+      if (!poll_packet(recs + static_cast<size_t>(i) * stride, tag, bits)) {st->comm_error = 1u;}
+      const float mi = __uint_as_float(bits);
+      fs.e[i] = mi;
+      m = fminf(m, mi);
+    }
+    m = warp_min(m);
+    if (lane == 0) {fs.red[seg] = m;}
+    __syncthreads();
+    m = fs.red[0];
+    for (int w = 1; w < S; ++w) {m = fminf(m, fs.red[w]);}
+    __syncthreads();
+    for (int i = tid; i < G; i += nthr) {fs.e[i] = expf(-(fs.e[i] - m) * inv_temp);}
+    __syncthreads();
   }
-  m = warp_min(m);
-  if (lane == 0) {fs.red[seg] = m;}
-  __syncthreads();
-  m = fs.red[0];
-  for (int w = 1; w < S; ++w) {m = fminf(m, fs.red[w]);}
-  __syncthreads();
-  for (int i = tid; i < G; i += nthr) {fs.e[i] = expf(-(fs.e[i] - m) * inv_temp);}
-  __syncthreads();
   // column 0 = sum of the weights; then (vx, vy, wz) of every owned time step: one warp per column, lanes over the records
   const int n_own = (T - static_cast<int>(blockIdx.x) + G - 1) / G;
   float * col_out = fs.red + 8;   // [1 + 3 * 7]
@@ -2029,10 +2204,26 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
         col = 1 + plane * T + t;
       }
       float acc = 0.0f;
-      for (int i = lane; i < G; i += 32) {
-        unsigned bits;
-        if (!poll_packet(recs + static_cast<size_t>(i) * stride + 1 + col, tag, bits)) {st->comm_error = 1u;}
-        acc = fmaf(__uint_as_float(bits), fs.e[i], acc);
+      if (small) {
+        // lane = record: its minimum and its entry of this column are polled together
+        float mi = 3.402823466e+38f, wi = 0.0f;
+        if (lane < G) {
+          const uint2 * pm = recs + static_cast<size_t>(lane) * stride;
+          const long long t0 = clock64();
+          for (;;) {
+            const uint2 a = ld_packet(pm), w = ld_packet(pm + 1 + col);
+            if (a.y == tag && w.y == tag) {mi = __uint_as_float(a.x); wi = __uint_as_float(w.x); break;}
+            if (clock64() - t0 > kSpinLimitCycles) {st->comm_error = 1u; mi = 0.0f; break;}
+          }
+        }
+        const float mm = warp_min(mi);
+        acc = lane < G ? wi * expf(-(mi - mm) * inv_temp) : 0.0f;
+      } else {
+        for (int i = lane; i < G; i += 32) {
+          unsigned bits;
+          if (!poll_packet(recs + static_cast<size_t>(i) * stride + 1 + col, tag, bits)) {st->comm_error = 1u;}
+          acc = fmaf(__uint_as_float(bits), fs.e[i], acc);
+        }
       }
       acc = warp_sum(acc);
       if (lane == 0) {col_out[k] = acc;}
