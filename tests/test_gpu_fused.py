@@ -1,0 +1,135 @@
+"""The fused small-batch kernel (tile_fused_kernel: K2 + exchange 1 + K3 + merge in one cooperative launch, zero-copy
+upload, result packets in pinned host memory) against the CPU oracle and against the two-kernel path it replaces.
+
+The parity suite (test_gpu_parity.py) already runs through the fused kernel wherever it applies (single rank, tile
+layout); these cases pin what is specific to it: the exact instances (no outputs requested), the in-GPU packet
+exchanges with more than 32 tiles, path sizes that change from cycle to cycle (captured graph must survive), paths
+longer than the block, the zero-copy upload, multi-iteration launches, and optimize_resident after a zero-copy cycle.
+"""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from mpcholonavigation_b200 import Engine, scenarios
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-4, 1e-6
+
+
+def _engine(fns, sc, noise, **kw):
+    e = Engine(fns, **{**sc.cfg, **kw})
+    e.set_robot(sc.robot)
+    e.set_critics(sc.critics)
+    e.set_noise(*noise)
+    return e
+
+
+def _close(ra, rb, rtol=RTOL, atol=ATOL, label=""):
+    for name in ("vx", "vy", "wz"):
+        np.testing.assert_allclose(getattr(ra, name), getattr(rb, name), rtol=rtol, atol=atol, err_msg=f"{label} {name}")
+    assert ra.fail_flag == rb.fail_flag, label
+    assert ra.furthest_reached_path_point == rb.furthest_reached_path_point, label
+
+
+@pytest.mark.parametrize("batch,steps", [(1000, 56), (2016, 56), (4100, 33), (1000, 100), (37, 56)])
+def test_exact_instance_against_oracle_and_two_kernel_path(product_fns, oracle_fns, monkeypatch, batch, steps):
+    """No outputs requested -> the exact feature-set instance runs (what bench.py times).  1000: 32 tiles (one record
+    per lane in the merge), 2016 / 4100: 63 / 129 tiles (general merge), 37: a ragged second tile.  Free running for 12
+    cycles: fused == two-kernel path == oracle within the control tolerance, costs of all trajectories included."""
+    sc = scenarios.config1(batch=batch, steps=steps)
+    noise = sc.noise()
+    fused = _engine(product_fns, sc, noise)
+    monkeypatch.setenv("MPPI_FUSED", "0")
+    two = _engine(product_fns, sc, noise)
+    monkeypatch.delenv("MPPI_FUSED")
+    orc = _engine(oracle_fns, sc, noise)
+    for cycle in range(12):
+        rf, rt, ro = fused.optimize(sc.cycle), two.optimize(sc.cycle), orc.optimize(sc.cycle)
+        _close(rf, ro, label=f"fused vs oracle, cycle {cycle}")
+        _close(rf, rt, label=f"fused vs two-kernel, cycle {cycle}")
+        np.testing.assert_allclose(fused.get_costs(), orc.get_costs(), rtol=RTOL, atol=2e-5)
+        np.testing.assert_allclose(fused.get_costs(), two.get_costs(), rtol=RTOL, atol=2e-5)
+        for e in (fused, two):
+            e.set_control_sequence(ro.vx, ro.vy, ro.wz)
+    assert fused.get_profile()["kernel_launches"] < two.get_profile()["kernel_launches"]   # 1 launch per cycle, not 2
+    for e in (fused, two, orc):
+        e.close()
+
+
+def test_path_size_changes_between_cycles(product_fns, oracle_fns):
+    """The pruned path changes length every cycle.  Within a 64-point bucket the captured graph is replayed (the path
+    size comes from the record, not from a kernel argument); 300 points: longer than the block (loop path)."""
+    sc = scenarios.config1()
+    noise = sc.noise()
+    g, o = _engine(product_fns, sc, noise), _engine(oracle_fns, sc, noise)
+    pose = sc.cycle.pose
+    for n_path in (40, 37, 52, 64, 65, 120, 300, 41, 2, 40):
+        px, py, pyaw = scenarios.straight_path(pose[0], pose[1], 0.0, n_path, 0.05 if n_path < 100 else 0.008)
+        cyc = dataclasses.replace(sc.cycle, path_x=px, path_y=py, path_yaw=pyaw, goal=(float(px[-1]), float(py[-1])))
+        rg, ro = g.optimize(cyc), o.optimize(cyc)
+        _close(rg, ro, label=f"N={n_path}")
+        np.testing.assert_allclose(g.get_costs(), o.get_costs(), rtol=RTOL, atol=2e-5, err_msg=f"N={n_path}")
+        g.set_control_sequence(ro.vx, ro.vy, ro.wz)
+    g.close(); o.close()
+
+
+def test_zero_copy_upload_is_bitwise_the_copy_engine_path(product_fns, monkeypatch):
+    """record + costmap pulled out of pinned staging by the kernel itself vs one cudaMemcpyAsync: identical bits;
+    and the device copies the zero-copy cycle leaves behind are complete (optimize_resident reproduces the cycle)."""
+    sc = scenarios.config1()
+    noise = sc.noise()
+    zc = _engine(product_fns, sc, noise)
+    monkeypatch.setenv("MPPI_ZERO_COPY", "0")
+    cp = _engine(product_fns, sc, noise)
+    monkeypatch.delenv("MPPI_ZERO_COPY")
+    for cycle in range(6):
+        ra, rb = zc.optimize(sc.cycle), cp.optimize(sc.cycle)
+        for name in ("vx", "vy", "wz"):
+            assert np.array_equal(getattr(ra, name), getattr(rb, name)), f"cycle {cycle} {name}"
+        assert np.array_equal(zc.get_costs(), cp.get_costs())
+    assert zc.get_profile()["h2d_bytes"] > 0
+    # same warm start, resident inputs: the record and the costmap the tiles copied into device memory are all there
+    before = zc.get_control_sequence()
+    r1 = zc.optimize(sc.cycle)
+    zc.set_control_sequence(*before)
+    r2 = zc.optimize_resident()
+    for name in ("vx", "vy", "wz"):
+        assert np.array_equal(getattr(r1, name), getattr(r2, name)), name
+    zc.close(); cp.close()
+
+
+def test_timing_off_and_multi_iteration(product_fns, oracle_fns):
+    """mppi_set_timing(0): no events, device_ms reads 0, same result; iteration_count = 3: three fused launches whose
+    costs and furthest point carry over (optimizer.cpp:157-164), result packets only from the last one."""
+    sc = scenarios.config1()
+    sc.cfg["iteration_count"] = 3
+    noise = sc.noise()
+    g, o = _engine(product_fns, sc, noise), _engine(oracle_fns, sc, noise)
+    g.set_timing(False)
+    for cycle in range(5):
+        rg, ro = g.optimize(sc.cycle), o.optimize(sc.cycle)
+        assert rg.device_ms == 0.0
+        _close(rg, ro, label=f"cycle {cycle}")
+        np.testing.assert_allclose(g.get_costs(), o.get_costs(), rtol=RTOL, atol=3e-5)
+        g.set_control_sequence(ro.vx, ro.vy, ro.wz)
+    g.set_timing(True)
+    assert g.optimize(sc.cycle).device_ms > 0.0
+    g.close(); o.close()
+
+
+def test_costmap_resize_and_large_costmap_fall_back_to_the_copy_engine(product_fns, oracle_fns):
+    """100x100 (zero-copy) -> 400x400 (160 KB: above the zero-copy bound, copy engine; staging buffers regrow) -> back"""
+    noise = None
+    g = o = None
+    for map_size in (100, 400, 100):
+        sc = scenarios.config1(map_size=map_size, pose=(2.5, 2.5, 0.0))
+        if g is None:
+            noise = sc.noise()
+            g, o = _engine(product_fns, sc, noise), _engine(oracle_fns, sc, noise)
+        for cycle in range(3):
+            rg, ro = g.optimize(sc.cycle), o.optimize(sc.cycle)
+            _close(rg, ro, label=f"map {map_size} cycle {cycle}")
+            g.set_control_sequence(ro.vx, ro.vy, ro.wz)
+    g.close(); o.close()
