@@ -55,6 +55,9 @@ def pick_scenario(workload, rank, world):
         return scenarios.config3(), "injected"
     if workload == "sharded_262144x100":
         return scenarios.config4(), "philox"
+    if workload == "robots_256":
+        sc = scenarios.config5_robot(rank)   # CPU arm: the robots are independent and the reference runs them one by one
+        return sc, "injected"
     raise SystemExit(f"unknown workload {workload}")
 
 
@@ -183,6 +186,128 @@ def cpu_baseline(sc, noise_kind, budget_s=12.0):
                       f"oracle port, reference-flags build; host has {os.cpu_count()} cpus"}
 
 
+def run_robots(args, rank, world, local_rank, fns, torch, dist):
+    """configs[4]: 256 independent robots x (2000 x 56), 256 / world per rank, no data-path collective.  One handle
+    (own stream) per robot; a step = every robot of the rank runs one optimize(), launched back to back and joined
+    (mppi_optimize_batch[_resident]), so that their kernels overlap on the device."""
+    import ctypes as C
+    from mpcholonavigation_b200 import abi
+    n_total = 256
+    assert n_total % world == 0
+    n = n_total // world
+    robots = [scenarios.config5_robot(rank * n + i) for i in range(n)]
+    B, T = robots[0].cfg["batch_size"], robots[0].cfg["time_steps"]
+    engines = []
+    for sc in robots:
+        cfg = dict(sc.cfg); cfg["device"] = local_rank
+        e = Engine(fns, **cfg)
+        e.set_robot(sc.robot); e.set_critics(sc.critics); e.set_noise(*sc.noise())
+        e.upload_cycle(sc.cycle)
+        engines.append(e)
+    hs = (abi.H * n)(*[e.h for e in engines])
+    ins = (abi.CycleIn * n)()
+    outs = (abi.CycleOut * n)()
+    keep = []
+    for i, sc in enumerate(robots):
+        cin, k = sc.cycle.pack()
+        ins[i] = cin
+        arrs = [np.empty(T, np.float32) for _ in range(3)]
+        outs[i].control_vx, outs[i].control_vy, outs[i].control_wz = (a.ctypes.data_as(abi.f32p) for a in arrs)
+        keep.append((k, arrs))
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def flush_l2():
+        if flush is not None:
+            flush.zero_()
+            torch.cuda.synchronize()
+
+    steps = max(1, min(args.steps, 200))
+    span = C.c_float(0.0)
+    for _ in range(args.warmup):
+        assert fns["optimize_batch_resident"](hs, outs, n) == 0
+    launches0 = sum(e.get_profile()["kernel_launches"] for e in engines)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    dev_ms = []
+    t_region = time.perf_counter()
+    for _ in range(steps):
+        flush_l2()
+        assert fns["optimize_batch_resident"](hs, outs, n) == 0
+        assert fns["batch_span_ms"](hs, n, C.byref(span)) == 0
+        dev_ms.append(span.value)
+    barrier()
+    region_s = time.perf_counter() - t_region
+    launches = sum(e.get_profile()["kernel_launches"] for e in engines) - launches0
+    for e in engines:
+        e.set_timing(False)
+    for _ in range(args.warmup):
+        assert fns["optimize_batch"](hs, ins, outs, n) == 0
+    barrier()
+    e2e_ms = []
+    for _ in range(steps):
+        flush_l2()
+        t0 = time.perf_counter()
+        assert fns["optimize_batch"](hs, ins, outs, n) == 0
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    barrier()
+    clocks = sampler.stop()
+    h2d = sum(e.get_profile()["h2d_bytes"] for e in engines)
+    d2h = sum(e.get_profile()["d2h_bytes"] for e in engines)
+    dev_total, e2e_total = float(np.sum(dev_ms)), float(np.sum(e2e_ms))
+    if world > 1:
+        t = torch.tensor([dev_total, e2e_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_total, e2e_total = float(t[0]), float(t[1])
+    units = n_total * B * T * steps
+    if rank == 0:
+        sc0 = robots[0]
+        cells, N = int(sc0.cycle.costmap.size), len(sc0.cycle.path_x)
+        alg = n * algorithmic_bytes(B, T, N, cells)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst)"
+        else:
+            peak, peak_src = 6650.0, "fallback of B200_PROFILING.md"
+        step_ms = dev_total / steps
+        achieved = alg / (step_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": units / (dev_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "robots_256", "robots": n_total, "robots_per_rank": n, "batch_size": B, "time_steps": T,
+                       "critics": [c[0] for c in sc0.critics], "costmap": list(sc0.cycle.costmap.shape), "path_points": N,
+                       "noise": "injected", "parallelism": "independent robots, one handle and stream each, no exchange",
+                       "l2": "cold: 256 MiB written between timed steps" if flush is not None else "warm (no flush)"},
+            "clocks": clocks,
+            "latency_ms": {"device_p50": pct(dev_ms, 50), "device_p90": pct(dev_ms, 90), "e2e_p50": pct(e2e_ms, 50),
+                           "e2e_p90": pct(e2e_ms, 90), "per_robot_e2e_p50": pct(e2e_ms, 50) / n},
+            "e2e": {"value": units / (e2e_total * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "p50_ms": pct(e2e_ms, 50)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "tile_fused_kernel x %d concurrent launches (whole step)" % n,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": alg // n, "peak_source": peak_src,
+                         "note": "algorithmic bytes of the rank's robots (SURVEY 8d) over the device span of the step: "
+                                 "first start event to latest end event across the robots' streams"},
+            "timed_region_s": region_s,
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(robots[0], "injected", 12.0)
+        print(json.dumps(line), flush=True)
+    for e in engines:
+        e.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -217,6 +342,9 @@ def main():
 
     from mpcholonavigation_b200 import load_product
     fns = load_product()
+    if args.workload == "robots_256":
+        run_robots(args, rank, world, local_rank, fns, torch, dist)
+        return
     sharded = args.workload == "sharded_262144x100"
     sc, noise_kind = pick_scenario(args.workload, rank, world)
     cfg = dict(sc.cfg)

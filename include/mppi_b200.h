@@ -220,6 +220,11 @@ mppi_status mppi_get_control_history(mppi_handle * h, float hist12[12]);
 /* batched multi-robot form: n independent handles (possibly on several devices) launched back to back
  * and then joined, so their kernels overlap */
 mppi_status mppi_optimize_batch(mppi_handle ** hs, const mppi_cycle_in * ins, mppi_cycle_out * outs, int32_t n);
+/* The same over inputs already resident on the device (mppi_upload_cycle on every handle).  Measurement hook. */
+mppi_status mppi_optimize_batch_resident(mppi_handle ** handles, mppi_cycle_out * outs, int32_t n);
+/* Device time of the last batch call over these handles (one device, timing on): first start event to latest end
+ * event; the handles run concurrently on their own streams, so their device_ms overlap. */
+mppi_status mppi_batch_span_ms(mppi_handle ** handles, int32_t n, float * ms_out);
 
 /* Split-phase form for data already resident on the device (bench "value" leg, CUDA-graph replay):
  * upload once, then run the device part only. */

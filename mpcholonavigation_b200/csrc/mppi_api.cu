@@ -1672,6 +1672,56 @@ mppi_status mppi_optimize_batch(mppi_handle ** hs, const mppi_cycle_in * ins, mp
   return first;
 }
 
+// the same over inputs that are already resident (mppi_upload_cycle on every handle): the measurement leg of the
+// multi-robot workload
+mppi_status mppi_optimize_batch_resident(mppi_handle ** hs, mppi_cycle_out * outs, int32_t n)
+{
+  if (!hs || n < 0) {return MPPI_E_CONFIG;}
+  mppi_status first = MPPI_OK;
+  std::vector<char> launched(n, 0);
+  for (int i = 0; i < n; ++i) {
+    mppi_handle * h = hs[i];
+    mppi_status s = MPPI_OK;
+    if (!h) {
+      s = MPPI_E_CONFIG;
+    } else if (!h->cycle_uploaded) {
+      s = fail(h, MPPI_E_STATE, "mppi_optimize_batch_resident before mppi_upload_cycle");
+    } else if (cudaSetDevice(h->device) != cudaSuccess) {
+      s = fail(h, MPPI_E_CUDA, "cudaSetDevice");
+    } else {
+      s = enqueue_optimize(h, false);
+    }
+    launched[i] = s == MPPI_OK;
+    if (s != MPPI_OK && first == MPPI_OK) {first = s;}
+  }
+  for (int i = 0; i < n; ++i) {
+    if (!launched[i]) {continue;}
+    cudaSetDevice(hs[i]->device);
+    const mppi_status s = finish_optimize(hs[i], outs ? &outs[i] : nullptr);
+    if (s != MPPI_OK && first == MPPI_OK) {first = s;}
+  }
+  return first;
+}
+
+// device time of the last batch call over these handles (same device, timing on): from the first handle's start event
+// to the latest end event.  The handles run on their own streams, so the per-handle device_ms overlap.
+mppi_status mppi_batch_span_ms(mppi_handle ** hs, int32_t n, float * ms_out)
+{
+  if (!hs || n < 1 || !ms_out || !hs[0]) {return MPPI_E_CONFIG;}
+  float span = 0.0f;
+  for (int i = 0; i < n; ++i) {
+    if (!hs[i] || !hs[i]->timing) {return MPPI_E_STATE;}
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, hs[0]->ev0, hs[i]->ev1) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(hs[i], MPPI_E_STATE, "mppi_batch_span_ms: no completed batch call to read");
+    }
+    span = std::max(span, ms);
+  }
+  *ms_out = span;
+  return MPPI_OK;
+}
+
 mppi_status mppi_get_trajectories(mppi_handle * h, float * x, float * y, float * yaw)
 {
   if (!h || !x || !y || !yaw) {return MPPI_E_CONFIG;}
