@@ -205,6 +205,12 @@ def run_robots(args, rank, world, local_rank, fns, torch, dist):
         e.upload_cycle(sc.cycle)
         engines.append(e)
     hs = (abi.H * n)(*[e.h for e in engines])
+    # MPPI_BATCH_BIND=1: the rank's robots as one bound group (tile_fused_batch_kernel, one launch per 16 robots).  Measured
+    # on one B200 (profiles/README.md): device span 1.70 ms against 2.03 ms, but end to end 2.25 ms against 2.03 ms because
+    # the host's record building overlaps less with the device; the default stays one launch per robot.
+    bound = os.environ.get("MPPI_BATCH_BIND", "0") != "0" and n > 1
+    if bound:
+        assert fns["batch_bind"](hs, n) == 0   # one kernel launch per step for all robots of the rank
     ins = (abi.CycleIn * n)()
     outs = (abi.CycleOut * n)()
     keep = []
@@ -231,6 +237,10 @@ def run_robots(args, rank, world, local_rank, fns, torch, dist):
     span = C.c_float(0.0)
     for _ in range(args.warmup):
         assert fns["optimize_batch_resident"](hs, outs, n) == 0
+    if bound and rank == 0:
+        msg = fns["last_error"](engines[0].h)
+        if msg:
+            print("note:", msg.decode(), file=sys.stderr, flush=True)
     launches0 = sum(e.get_profile()["kernel_launches"] for e in engines)
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -283,7 +293,9 @@ def run_robots(args, rank, world, local_rank, fns, torch, dist):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "robots_256", "robots": n_total, "robots_per_rank": n, "batch_size": B, "time_steps": T,
                        "critics": [c[0] for c in sc0.critics], "costmap": list(sc0.cycle.costmap.shape), "path_points": N,
-                       "noise": "injected", "parallelism": "independent robots, one handle and stream each, no exchange",
+                       "noise": "injected", "parallelism": ("independent robots, one handle each, bound into one group per rank: ONE launch per step "
+                                       "(blocks draw tickets), no exchange" if bound else
+                                       "independent robots, one handle and stream each, no exchange"),
                        "l2": "cold: 256 MiB written between timed steps" if flush is not None else "warm (no flush)"},
             "clocks": clocks,
             "latency_ms": {"device_p50": pct(dev_ms, 50), "device_p90": pct(dev_ms, 90), "e2e_p50": pct(e2e_ms, 50),
@@ -291,7 +303,8 @@ def run_robots(args, rank, world, local_rank, fns, torch, dist):
             "e2e": {"value": units / (e2e_total * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "p50_ms": pct(e2e_ms, 50)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "tile_fused_kernel x %d concurrent launches (whole step)" % n,
+            "roofline": {"bound": "hbm", "kernel": ("tile_fused_batch_kernel (%d robots per launch)" % n if bound else
+                                                    "tile_fused_kernel x %d concurrent launches (whole step)" % n),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "algorithmic_bytes_per_launch": alg // n, "peak_source": peak_src,
                          "note": "algorithmic bytes of the rank's robots (SURVEY 8d) over the device span of the step: "

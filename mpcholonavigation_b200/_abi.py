@@ -191,6 +191,8 @@ PRODUCT_ONLY = {
     "optimize_batch": (C.c_int, [C.POINTER(H), C.POINTER(CycleIn), C.POINTER(CycleOut), C.c_int32]),
     "optimize_sharded": (C.c_int, [C.POINTER(H), C.c_int32, C.POINTER(CycleIn), C.POINTER(CycleOut)]),
     "optimize_batch_resident": (C.c_int, [C.POINTER(H), C.POINTER(CycleOut), C.c_int32]),
+    "batch_bind": (C.c_int, [C.POINTER(H), C.c_int32]),
+    "batch_unbind": (C.c_int, [H]),
     "batch_span_ms": (C.c_int, [C.POINTER(H), C.c_int32, f32p]),
     "upload_cycle": (C.c_int, [H, C.POINTER(CycleIn)]),
     "optimize_resident": (C.c_int, [H, C.POINTER(CycleOut)]),

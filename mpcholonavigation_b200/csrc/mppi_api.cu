@@ -125,8 +125,20 @@ struct mppi_handle
   uint2 * h_res{nullptr};                 // pinned + mapped: [3T + 8] result packets written by the kernels
   bool zero_copy_now{false};              // this cycle's fused kernel pulls the upload out of pinned host memory itself
   bool wait_packets{false};               // the cycle in flight delivers its result as packets (no D2H copy, no stream sync)
+  // multi-robot batch (mppi_batch_bind): the bound handles share the leader's stream, so that ONE launch can serve all
+  // of them (tile_fused_batch_kernel) and every later operation on any of them is still ordered behind it
+  mppi_handle * batch_leader{nullptr};    // non-null for every bound handle (the leader points to itself)
+  cudaStream_t own_stream{nullptr};       // a follower's own stream while it borrows the leader's
+  mppi_handle * ev_src{nullptr};          // whose ev0 / ev1 bracket the cycle in flight (the leader's after a batched launch)
+  std::vector<mppi_handle *> batch_group; // leader only, in bind order
+  FusedJob * h_jobs{nullptr};             // leader only: job table, pinned ...
+  FusedJob * d_jobs{nullptr};             // ... and its device copy (re-sent only when an entry changes)
+  std::vector<char> jobs_sent;            // what the device copy holds
+  unsigned * d_ticket{nullptr};           // leader only: ticket counter of the batch kernel (never reset)
+  uint32_t ticket_base{0};                // tickets drawn by all earlier batched launches
   uint64_t host_ns[8]{0, 0, 0, 0, 0, 0, 0, 0};   // host-side time of the steady-state call by phase (mppi_debug_get_host_ns)
   bool zero_copy_enabled{true};   // MPPI_ZERO_COPY=0 disables
+  bool coop_launch{true};
   bool fused_enabled{true};    // small batches: one cooperative launch per iteration (tile_fused_kernel); MPPI_FUSED=0 disables
   int fused_key_N{-1};         // path size the cached decision below was taken for (the shared-memory size depends on it)
   bool fused_fits{false};      // the whole grid is co-resident (a cooperative launch needs that)
@@ -793,6 +805,9 @@ cudaError_t launch_fused_instance(mppi_handle * h, int iteration, uint2 * host_r
   const uint4 * up_host = zero_copy ? reinterpret_cast<const uint4 *>(h->h_params) : nullptr;
   int up_vecs = zero_copy ? static_cast<int>((upload_bytes(h) + 15) / 16) : 0;
   void * args[] = {&dp, &cm, &bufs, &B, &T, &N, &iteration, &host_res, &up_host, &up_vecs};
+  if (!h->coop_launch) {   // experiment switch (MPPI_COOP=0): plain launch, no co-residency guarantee
+    return cudaLaunchKernel(reinterpret_cast<const void *>(&tile_fused_kernel<F, kExact>), grid, block, args, smem, h->stream);
+  }
   return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&tile_fused_kernel<F, kExact>), grid, block, args, smem, h->stream);
 }
 
@@ -975,6 +990,7 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
 {
   const bool prof = h->profiling && h->cfg.iteration_count == 1;
   const bool graph_ok = h->use_graph && !prof && (h->nranks == 1 || h->peer_mode);   // NCCL calls are not captured
+  h->ev_src = nullptr;
   h->wait_packets = use_fused(h);
   h->zero_copy_now = with_upload && h->wait_packets && h->zero_copy_enabled && upload_bytes(h) <= kZeroCopyMaxBytes;
   if (h->wait_packets) {h->fepoch_host += static_cast<uint32_t>(h->cfg.iteration_count);}
@@ -1094,7 +1110,7 @@ mppi_status finish_optimize(mppi_handle * h, mppi_cycle_out * out)
   if (h->wait_packets) {
     mppi_status ws = wait_result_packets(h);
     if (ws != MPPI_OK) {return ws;}
-    if (h->timing) {CUDA_TRY(h, cudaEventSynchronize(h->cfg.regenerate_noises ? h->ev_result : h->ev1));}
+    if (h->timing) {CUDA_TRY(h, cudaEventSynchronize(h->cfg.regenerate_noises ? h->ev_result : (h->ev_src ? h->ev_src : h)->ev1));}
   } else if (h->cfg.regenerate_noises) {
     CUDA_TRY(h, cudaEventSynchronize(h->ev_result));
   } else {
@@ -1121,7 +1137,10 @@ mppi_status finish_optimize(mppi_handle * h, mppi_cycle_out * out)
   // device time of the cycle (events around everything enqueued for it), only when asked for: reading two events back
   // costs several microseconds of host time
   float ms = 0.0f;
-  if (h->timing) {cudaEventElapsedTime(&ms, h->ev0, h->cfg.regenerate_noises ? h->ev_result : h->ev1);}
+  if (h->timing) {
+    const mppi_handle * es = h->ev_src ? h->ev_src : h;
+    cudaEventElapsedTime(&ms, es->ev0, h->cfg.regenerate_noises ? h->ev_result : es->ev1);
+  }
   h->prof_ms[3] = ms;
   if (out) {out->device_ms = ms;}
   if (h->peer_mode) {
@@ -1214,6 +1233,165 @@ mppi_status do_reset(mppi_handle * h)
   return sync_epoch(h);
 }
 
+// ---- multi-robot batch -----------------------------------------------------------------------------
+void batch_unbind_group(mppi_handle * leader)
+{
+  if (!leader) {return;}
+  cudaSetDevice(leader->device);
+  cudaStreamSynchronize(leader->stream);
+  std::vector<mppi_handle *> group = leader->batch_group;
+  for (mppi_handle * m : group) {
+    if (m != leader && m->own_stream) {m->stream = m->own_stream; m->own_stream = nullptr;}
+    m->batch_leader = nullptr;
+    m->ev_src = nullptr;
+    drop_graphs(m);
+  }
+  leader->batch_group.clear();
+  leader->jobs_sent.clear();
+  if (leader->h_jobs) {cudaFreeHost(leader->h_jobs); leader->h_jobs = nullptr;}
+  if (leader->d_jobs) {cudaFree(leader->d_jobs); leader->d_jobs = nullptr;}
+  if (leader->d_ticket) {cudaFree(leader->d_ticket); leader->d_ticket = nullptr;}
+  leader->ticket_base = 0;
+}
+
+// is hs[0..n) exactly a bound group, in bind order?
+bool batch_is_group(mppi_handle ** hs, int n)
+{
+  if (n < 2 || !hs[0] || hs[0]->batch_leader != hs[0] || static_cast<int>(hs[0]->batch_group.size()) != n) {return false;}
+  for (int i = 0; i < n; ++i) {
+    if (hs[i] != hs[0]->batch_group[i]) {return false;}
+  }
+  return true;
+}
+
+constexpr int kBatchChunk = 16;   // robots per launch: the host prepares the next chunk's records while this one runs
+
+template<unsigned F, bool kExact>
+cudaError_t launch_batch_instance(mppi_handle * leader, int c0, int n, int G, dim3 block, size_t smem)
+{
+  tile_fused_batch_kernel<F, kExact><<<dim3(static_cast<unsigned>(n) * G), block, smem, leader->stream>>>(
+    leader->d_jobs + c0, G, leader->d_ticket, leader->ticket_base);
+  return cudaGetLastError();
+}
+
+// One launch for the members [c0, c0 + n) of a bound group (their records are built, uploads staged).  Returns
+// MPPI_E_STATE without having launched anything when they do not qualify this cycle: the caller then runs them one by
+// one (they share a stream, so that is correct, only slower).  `first` / `last`: this is the first / last chunk of the
+// call (the leader's events bracket the whole call).
+mppi_status batch_launch(mppi_handle * L, mppi_handle ** hs, int c0, int n, bool with_upload, bool first, bool last)
+{
+  // the exact instance when every member asks for the same one, else the generic instance (it tests the per-cycle flags)
+  unsigned inst = pick_stream_instance(stream_feature_need(hs[0]->last));
+  for (int i = 1; i < n; ++i) {
+    if (pick_stream_instance(stream_feature_need(hs[i]->last)) != inst) {inst = SF_ALL; break;}
+  }
+  const int S = pick_segments(L);
+  const int G = (L->B + kTile - 1) / kTile;
+  const int n_cap = fused_path_capacity(hs[0]), n_s = fused_align_samples(hs[0]);
+  for (int i = 0; i < n; ++i) {
+    mppi_handle * h = hs[i];
+    const char * why = nullptr;
+    if (!use_fused(h)) {why = "fused kernel not applicable";}
+    else if (h->tail_mode != 0 || h->cfg.iteration_count != 1 || h->profiling) {why = "tail / iteration_count / profiling";}
+    else if (fused_path_capacity(h) != n_cap || fused_align_samples(h) != n_s) {why = "different path capacity / PathAlign samples";}
+    if (why) {
+      L->err = std::string("batched launch not used: member ") + std::to_string(c0 + i) + ": " + why;
+      return MPPI_E_STATE;
+    }
+  }
+  const size_t smem = fused_smem_bytes(L->T, S, n_cap, G, n_s);
+  for (int i = 0; i < n; ++i) {
+    mppi_handle * h = hs[i];
+    h->wait_packets = true;
+    h->ev_src = L;
+    h->zero_copy_now = with_upload && h->zero_copy_enabled && upload_bytes(h) <= kZeroCopyMaxBytes;
+    if (with_upload && !h->zero_copy_now) {
+      const mppi_status us = enqueue_uploads(h);
+      if (us != MPPI_OK) {return us;}
+    }
+    FusedJob & j = L->h_jobs[c0 + i];
+    std::memset(&j, 0, sizeof(j));
+    j.Pg = reinterpret_cast<const DevParams *>(h->d_params);
+    j.cm = h->d_costmap;
+    j.bufs = make_bufs(h, 0);
+    j.B = h->B; j.T = h->T; j.n_cap = n_cap; j.iteration = 0;
+    j.host_res = h->h_res;
+    j.up_host = h->zero_copy_now ? reinterpret_cast<const uint4 *>(h->h_params) : nullptr;
+    j.up_vecs = h->zero_copy_now ? static_cast<int>((upload_bytes(h) + 15) / 16) : 0;
+  }
+  // the device copy of the job table is re-sent only where it changed (pointers and sizes are the same every cycle)
+  const size_t off = sizeof(FusedJob) * static_cast<size_t>(c0), bytes = sizeof(FusedJob) * static_cast<size_t>(n);
+  if (std::memcmp(L->jobs_sent.data() + off, L->h_jobs + c0, bytes) != 0) {
+    CUDA_TRY(L, cudaMemcpyAsync(L->d_jobs + c0, L->h_jobs + c0, bytes, cudaMemcpyHostToDevice, L->stream));
+    std::memcpy(L->jobs_sent.data() + off, L->h_jobs + c0, bytes);
+  }
+  if (first && L->timing) {CUDA_TRY(L, cudaEventRecord(L->ev0, L->stream));}
+  const dim3 block(kTile, S);
+  cudaError_t e;
+  switch (inst) {
+    case kSfOmniDefault: e = launch_batch_instance<kSfOmniDefault, true>(L, c0, n, G, block, smem); break;
+    case kSfOmniDefaultFp: e = launch_batch_instance<kSfOmniDefaultFp, true>(L, c0, n, G, block, smem); break;
+    case kSfObstaclesFp: e = launch_batch_instance<kSfObstaclesFp, true>(L, c0, n, G, block, smem); break;
+    default: e = launch_batch_instance<SF_ALL, false>(L, c0, n, G, block, smem); break;
+  }
+  CUDA_TRY(L, e);
+  if (last && L->timing) {CUDA_TRY(L, cudaEventRecord(L->ev1, L->stream));}
+  L->ticket_base += static_cast<uint32_t>(n) * static_cast<uint32_t>(G);
+  L->launches++;
+  for (int i = 0; i < n; ++i) {
+    mppi_handle * h = hs[i];
+    h->fepoch_host += 1u;
+    h->d2h_bytes = sizeof(uint2) * (3 * h->T + 2);
+    h->h2d_bytes = with_upload ? upload_bytes(h) + (h->zero_copy_now ? static_cast<size_t>(h->upd_blocks) * kHotBytes : 0) : 0;
+  }
+  return MPPI_OK;
+}
+
+// The whole group, in chunks of kBatchChunk robots: records of a chunk are built (ins != nullptr) and the chunk is
+// launched while the device still works on the previous ones.  Members of a chunk that does not qualify run one by one.
+mppi_status batch_run_group(mppi_handle ** hs, const mppi_cycle_in * ins, mppi_cycle_out * outs, int n)
+{
+  mppi_handle * L = hs[0];
+  CUDA_TRY(L, cudaSetDevice(L->device));
+  mppi_status first = MPPI_OK;
+  std::vector<char> pending(n, 0);
+  // resident inputs: nothing to prepare on the host, one launch for the whole group
+  const int chunk = ins ? kBatchChunk : n;
+  for (int c0 = 0; c0 < n; c0 += chunk) {
+    const int cn = std::min(chunk, n - c0);
+    mppi_status s = MPPI_OK;
+    for (int i = c0; i < c0 + cn && s == MPPI_OK; ++i) {
+      if (ins) {
+        s = build_params(hs[i], &ins[i], 0, kUnset, true);
+        if (s == MPPI_OK) {s = stage_costmap(hs[i], ins[i].costmap);}
+        if (s == MPPI_OK) {hs[i]->cycle_uploaded = true;}
+      } else if (!hs[i]->cycle_uploaded) {
+        s = fail(hs[i], MPPI_E_STATE, "mppi_optimize_batch_resident before mppi_upload_cycle");
+      }
+    }
+    if (s == MPPI_OK) {s = batch_launch(L, hs + c0, c0, cn, ins != nullptr, c0 == 0, c0 + cn == n);}
+    if (s == MPPI_OK) {
+      for (int i = c0; i < c0 + cn; ++i) {pending[i] = 1;}
+    } else if (s == MPPI_E_STATE) {
+      // this chunk does not qualify: one by one on the shared stream (records are built already)
+      if (c0 == 0 && L->timing) {cudaEventRecord(L->ev0, L->stream);}
+      for (int i = c0; i < c0 + cn; ++i) {
+        mppi_status f = hs[i]->cycle_uploaded ? enqueue_optimize(hs[i], ins != nullptr) : MPPI_E_STATE;
+        if (f == MPPI_OK) {pending[i] = 1;} else if (first == MPPI_OK) {first = f;}
+      }
+      if (c0 + cn == n && L->timing) {cudaEventRecord(L->ev1, L->stream);}
+    } else if (first == MPPI_OK) {
+      first = s;
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    if (!pending[i]) {continue;}
+    const mppi_status f = finish_optimize(hs[i], outs ? &outs[i] : nullptr);
+    if (f != MPPI_OK && first == MPPI_OK) {first = f;}
+  }
+  return first;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -1278,6 +1456,7 @@ void mppi_destroy(mppi_handle * h)
   if (!h) {return;}
   cudaSetDevice(h->device);
   if (h->stream) {cudaStreamSynchronize(h->stream);}
+  if (h->batch_leader) {batch_unbind_group(h->batch_leader);}   // a group does not survive the loss of a member
   drop_graphs(h);
   if (h->comm && g_nccl.CommDestroy) {g_nccl.CommDestroy(h->comm);}
   if (h->peer_mode) {
@@ -1331,6 +1510,7 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   if (const char * e = std::getenv("MPPI_NO_GRAPH")) {h->use_graph = std::atoi(e) == 0;}
   if (const char * e = std::getenv("MPPI_FUSED")) {h->fused_enabled = std::atoi(e) != 0;}
   if (const char * e = std::getenv("MPPI_ZERO_COPY")) {h->zero_copy_enabled = std::atoi(e) != 0;}
+  if (const char * e = std::getenv("MPPI_COOP")) {h->coop_launch = std::atoi(e) != 0;}
   {
     // batches too small to fill the GPU with one thread per trajectory keep the latency-oriented tile kernel
     long long stream_min = 8192;    // measured cross-over on B200 (profiles/): below it the tile kernel wins
@@ -1358,6 +1538,10 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
     CUDA_TRY(h, cudaFuncSetAttribute(tile_fused_kernel<kSfOmniDefault, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(h, cudaFuncSetAttribute(tile_fused_kernel<kSfOmniDefaultFp, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(h, cudaFuncSetAttribute(tile_fused_kernel<kSfObstaclesFp, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(h, cudaFuncSetAttribute(tile_fused_batch_kernel<SF_ALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(h, cudaFuncSetAttribute(tile_fused_batch_kernel<kSfOmniDefault, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(h, cudaFuncSetAttribute(tile_fused_batch_kernel<kSfOmniDefaultFp, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(h, cudaFuncSetAttribute(tile_fused_batch_kernel<kSfObstaclesFp, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     int coop = 0;
     CUDA_TRY(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
     CUDA_TRY(h, cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
@@ -1653,9 +1837,53 @@ mppi_status mppi_get_control_history(mppi_handle * h, float hist12[12])
   return MPPI_OK;
 }
 
+// Multi-robot server: bind n handles of one device (same batch_size / time_steps, tile layout, not sharded) into a
+// group.  They share the first handle's stream from here on, and mppi_optimize_batch[_resident] over exactly this group
+// (same order) becomes ONE kernel launch for all robots.  Everything else keeps working on bound handles.
+mppi_status mppi_batch_bind(mppi_handle ** hs, int32_t n)
+{
+  if (!hs || n < 1 || !hs[0]) {return MPPI_E_CONFIG;}
+  mppi_handle * L = hs[0];
+  for (int i = 0; i < n; ++i) {
+    mppi_handle * h = hs[i];
+    if (!h) {return MPPI_E_CONFIG;}
+    if (h->device != L->device || h->B != L->B || h->T != L->T) {return fail(L, MPPI_E_CONFIG, "mppi_batch_bind: handles must share device, batch_size and time_steps");}
+    if (h->stream_layout || h->nranks > 1 || h->cfg.regenerate_noises) {return fail(L, MPPI_E_CONFIG, "mppi_batch_bind: tile-layout, unsharded handles without regenerate_noises only");}
+    for (int k = 0; k < i; ++k) {if (hs[k] == h) {return fail(L, MPPI_E_CONFIG, "mppi_batch_bind: duplicate handle");}}
+  }
+  for (int i = 0; i < n; ++i) {
+    if (hs[i]->batch_leader) {batch_unbind_group(hs[i]->batch_leader);}
+  }
+  CUDA_TRY(L, cudaSetDevice(L->device));
+  CUDA_TRY(L, cudaHostAlloc(&L->h_jobs, sizeof(FusedJob) * static_cast<size_t>(n), cudaHostAllocDefault));
+  CUDA_TRY(L, cudaMalloc(&L->d_jobs, sizeof(FusedJob) * static_cast<size_t>(n)));
+  CUDA_TRY(L, cudaMalloc(&L->d_ticket, sizeof(unsigned)));
+  CUDA_TRY(L, cudaMemsetAsync(L->d_ticket, 0, sizeof(unsigned), L->stream));
+  L->ticket_base = 0;
+  L->jobs_sent.assign(sizeof(FusedJob) * static_cast<size_t>(n), 0);
+  std::memset(L->h_jobs, 0, sizeof(FusedJob) * static_cast<size_t>(n));
+  L->batch_group.assign(hs, hs + n);
+  for (int i = 0; i < n; ++i) {
+    mppi_handle * h = hs[i];
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    drop_graphs(h);
+    h->batch_leader = L;
+    if (h != L) {h->own_stream = h->stream; h->stream = L->stream;}
+  }
+  return MPPI_OK;
+}
+
+mppi_status mppi_batch_unbind(mppi_handle * any_member)
+{
+  if (!any_member) {return MPPI_E_CONFIG;}
+  batch_unbind_group(any_member->batch_leader);
+  return MPPI_OK;
+}
+
 mppi_status mppi_optimize_batch(mppi_handle ** hs, const mppi_cycle_in * ins, mppi_cycle_out * outs, int32_t n)
 {
   if (!hs || !ins || n < 0) {return MPPI_E_CONFIG;}
+  if (batch_is_group(hs, n)) {return batch_run_group(hs, ins, outs, n);}
   mppi_status first = MPPI_OK;
   std::vector<char> launched(n, 0);
   for (int i = 0; i < n; ++i) {
@@ -1677,6 +1905,7 @@ mppi_status mppi_optimize_batch(mppi_handle ** hs, const mppi_cycle_in * ins, mp
 mppi_status mppi_optimize_batch_resident(mppi_handle ** hs, mppi_cycle_out * outs, int32_t n)
 {
   if (!hs || n < 0) {return MPPI_E_CONFIG;}
+  if (batch_is_group(hs, n)) {return batch_run_group(hs, nullptr, outs, n);}
   mppi_status first = MPPI_OK;
   std::vector<char> launched(n, 0);
   for (int i = 0; i < n; ++i) {
@@ -1712,7 +1941,9 @@ mppi_status mppi_batch_span_ms(mppi_handle ** hs, int32_t n, float * ms_out)
   for (int i = 0; i < n; ++i) {
     if (!hs[i] || !hs[i]->timing) {return MPPI_E_STATE;}
     float ms = 0.0f;
-    if (cudaEventElapsedTime(&ms, hs[0]->ev0, hs[i]->ev1) != cudaSuccess) {
+    const mppi_handle * e0 = hs[0]->ev_src ? hs[0]->ev_src : hs[0];
+    const mppi_handle * e1 = hs[i]->ev_src ? hs[i]->ev_src : hs[i];
+    if (cudaEventElapsedTime(&ms, e0->ev0, e1->ev1) != cudaSuccess) {
       cudaGetLastError();
       return fail(hs[i], MPPI_E_STATE, "mppi_batch_span_ms: no completed batch call to read");
     }

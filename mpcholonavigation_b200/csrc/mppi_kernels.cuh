@@ -137,6 +137,8 @@ struct FusedCtx
   const float * s_hot, * s_cs;
   const float * s_cvx, * s_cvy, * s_cwz, * s_yaw, * s_x, * s_y;   // time-major tile planes [T][33]
   int n_cap, iteration;   // n_cap: path capacity the shared-memory carve-up was sized for (>= the record's N)
+  int tile, ntiles;       // this block's tile of the problem and the number of tiles (blockIdx.x / gridDim.x for a launch
+                          // of one problem; ticket-derived when one launch serves several robots)
   unsigned tag;           // tag of this launch's packets
   // zero-copy upload: the cycle's record + costmap sit in pinned host memory (up_host, up_vecs 16-byte vectors, laid
   // out like the device buffer that starts at the record); every tile reads the hot part of the record straight from
@@ -265,6 +267,8 @@ __device__ __forceinline__ void rollout_tile_body(
   const int S = blockDim.y;
   const int lane = threadIdx.x, seg = threadIdx.y;
   const int tid = seg * kTile + lane;
+  const int tile = kFused ? fx->tile : static_cast<int>(blockIdx.x);
+  const int ntiles = kFused ? fx->ntiles : static_cast<int>(gridDim.x);
   const int nthreads = S * kTile;
 
   float * s_hot = smem;
@@ -284,14 +288,14 @@ __device__ __forceinline__ void rollout_tile_body(
   int * s_amin_j = reinterpret_cast<int *>(s_amin_d + S * kTile);
   FusedShared fs = {};
   if (kFused) {
-    fs = fused_carve(reinterpret_cast<float *>(s_amin_j + S * kTile), fx->n_cap, gridDim.x);
+    fs = fused_carve(reinterpret_cast<float *>(s_amin_j + S * kTile), fx->n_cap, ntiles);
     fx->fs = fs;
     fx->s_hot = s_hot; fx->s_cs = s_cs; fx->s_cvx = s_cvx; fx->s_cvy = s_cvy; fx->s_cwz = s_cwz; fx->s_yaw = s_yaw;
     fx->s_x = s_x; fx->s_y = s_y;
     if (tid == 0) {reinterpret_cast<unsigned *>(fs.stat)[7] = 0u;}   // exchange-1 word of this tile, gathered in P6
   }
 
-  const int b0 = blockIdx.x * kTile;
+  const int b0 = tile * kTile;
   const int b = b0 + lane;
   const bool live = b < B;
 
@@ -310,8 +314,8 @@ __device__ __forceinline__ void rollout_tile_body(
   int up_begin = 0, up_end = 0;
   if (kFused) {
     if (zero_copy) {
-      const int per = (fx->up_vecs + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-      up_begin = min(fx->up_vecs, static_cast<int>(blockIdx.x) * per);
+      const int per = (fx->up_vecs + ntiles - 1) / ntiles;
+      up_begin = min(fx->up_vecs, tile * per);
       up_end = min(fx->up_vecs, up_begin + per);
       if (up_begin + tid < up_end) {up_v[0] = __ldg(fx->up_host + up_begin + tid);}
       if (up_begin + nthreads + tid < up_end) {up_v[1] = __ldg(fx->up_host + up_begin + nthreads + tid);}
@@ -383,7 +387,7 @@ __device__ __forceinline__ void rollout_tile_body(
   __syncthreads();
   MPPI_TRACE_AT(2);
   if (kFused) {
-    if (zero_copy && tid == 0) {st_packet(bufs.pk_up + blockIdx.x, 1u, fx->tag);}
+    if (zero_copy && tid == 0) {st_packet(bufs.pk_up + tile, 1u, fx->tag);}
   }
   const bool hol = MPPI_SF(SF_HOL, p.holonomic != 0);
   const bool acker = MPPI_SF(SF_ACKER, p.model == MPPI_MODEL_ACKERMANN);
@@ -566,7 +570,7 @@ __device__ __forceinline__ void rollout_tile_body(
       // zero-copy upload: a warp that has no scan to do collects the flags of all tiles; behind the barrier below the
       // device copies of the record and the costmap are complete
       if (zero_copy && seg == min(2, S - 1)) {
-        for (int i = lane; i < static_cast<int>(gridDim.x); i += 32) {
+        for (int i = lane; i < ntiles; i += 32) {
           unsigned v;
           if (!poll_packet(bufs.pk_up + i, fx->tag, v)) {bufs.st->comm_error = 1u;}
         }
@@ -843,7 +847,7 @@ __device__ __forceinline__ void rollout_tile_body(
       unsigned * s_x1 = reinterpret_cast<unsigned *>(fs.stat) + 7;   // zeroed at kernel start
       if (lane == 0 && my_flags) {atomicOr(s_x1, my_flags);}
       __syncthreads();         // also publishes fs.rows to the tail
-      if (tid == 0) {st_packet(bufs.pk_x1 + blockIdx.x, *s_x1, fx->tag);}
+      if (tid == 0) {st_packet(bufs.pk_x1 + tile, *s_x1, fx->tag);}
     }
   }
   MPPI_TRACE_AT(9);
@@ -1973,10 +1977,14 @@ __device__ __forceinline__ void put_result(float * out, uint2 * host_res, int id
   if (host_res) {st_packet(host_res + idx, __float_as_uint(v), tag);}
 }
 
+#ifndef MPPI_FUSED_MIN_BLOCKS
+#define MPPI_FUSED_MIN_BLOCKS 2
+#endif
+// the work of one block on tile `tile` of `G` of one problem (see the header comment above)
 template<unsigned F, bool kExact>
-__global__ void __launch_bounds__(256, 2) tile_fused_kernel(
-  const DevParams * __restrict__ Pg, const uint8_t * __restrict__ cm, DevBuffers bufs, const int B, const int T, const int n_cap,
-  const int iteration, uint2 * host_res, const uint4 * up_host, const int up_vecs)
+__device__ __forceinline__ void tile_fused_body(
+  const DevParams * __restrict__ Pg, const uint8_t * __restrict__ cm, const DevBuffers & bufs, const int B, const int T, const int n_cap,
+  const int iteration, uint2 * host_res, const uint4 * up_host, const int up_vecs, const int tile, const int G)
 {
   // n_cap (path capacity, a multiple of 64) sizes the shared memory; the path size itself comes from the record, so a
   // captured graph survives the small changes of the pruned path from cycle to cycle
@@ -1985,6 +1993,7 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
   FusedCtx fx;
   fx.n_cap = n_cap; fx.iteration = iteration;
   fx.up_host = up_host; fx.up_vecs = up_vecs;
+  fx.tile = tile; fx.ntiles = G;
   const unsigned tag = ld_volatile_u32(bufs.epoch) + 1u;
   fx.tag = tag;
   rollout_tile_body<F, kExact, 0, true>(Pg, cm, bufs, B, T, &fx);
@@ -1994,8 +2003,7 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
   const FusedShared & fs = fx.fs;
   const DevParams * P = reinterpret_cast<const DevParams *>(fx.s_hot);   // hot fields only
   DevState * st = bufs.st;
-  const int G = gridDim.x;
-  const int b0 = blockIdx.x * kTile;
+  const int b0 = tile * kTile;
   const int rows_here = min(kTile, B - b0);
   const int N = P->N;
   const float * __restrict__ path_yaw = reinterpret_cast<const float *>(Pg + 1) + 2 * N;
@@ -2140,7 +2148,7 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
   // ---- weighted column sums of the tile, W[c] = sum_r w_r * c[r][c], out of the noised controls still in the tile;
   //      the record leaves as packets (exchange 2 inside the GPU)
   const int stride = 3 * T + 2;
-  uint2 * part = bufs.pk_rec + static_cast<size_t>(blockIdx.x) * stride;
+  uint2 * part = bufs.pk_rec + static_cast<size_t>(tile) * stride;
   if (tid == 0) {st_packet(part, __float_as_uint(fs.stat[0]), tag);}
   if (tid == 32 || (S == 1 && tid == 1)) {st_packet(part + 1, __float_as_uint(fs.stat[1]), tag);}
   for (int c = tid; c < 3 * T; c += nthr) {
@@ -2161,7 +2169,7 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
 
   // ---- merge + clip: block t owns time steps t, t + G, ...  It needs m and s of every record and its own columns;
   //      the polls return as soon as the packets of this launch are there (no barrier)
-  if (blockIdx.x == 0 && tid == 0) {
+  if (tile == 0 && tid == 0) {
     k3_publish_flags(P, st, dec, bufs.out);
     if (host_res) {
       st_packet(host_res + 3 * T, static_cast<unsigned>(st->fail_flag), tag);
@@ -2169,7 +2177,7 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
     }
     *bufs.epoch = tag;     // every block read the epoch before block 0 can get here (it needs a packet of every block)
   }
-  if (static_cast<int>(blockIdx.x) >= T) {return;}   // owns no time step
+  if (tile >= T) {return;}   // owns no time step
   const uint2 * recs = bufs.pk_rec;
   const bool small = G <= 32;   // one record per lane: every warp rescales on its own, one memory round trip in all
   float m = 3.402823466e+38f;
@@ -2191,7 +2199,7 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
     __syncthreads();
   }
   // column 0 = sum of the weights; then (vx, vy, wz) of every owned time step: one warp per column, lanes over the records
-  const int n_own = (T - static_cast<int>(blockIdx.x) + G - 1) / G;
+  const int n_own = (T - tile + G - 1) / G;
   float * col_out = fs.red + 8;   // [1 + 3 * 7]
   for (int t_base = 0; t_base < n_own; t_base += 7) {
     const int n_now = min(7, n_own - t_base);
@@ -2200,7 +2208,7 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
       if (k == 0) {
         col = 0;
       } else {
-        const int t = static_cast<int>(blockIdx.x) + (t_base + (k - 1) / 3) * G, plane = (k - 1) % 3;
+        const int t = tile + (t_base + (k - 1) / 3) * G, plane = (k - 1) % 3;
         col = 1 + plane * T + t;
       }
       float acc = 0.0f;
@@ -2231,7 +2239,7 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
     __syncthreads();
     if (tid < n_now) {
       // cs = W / sum, then applyControlSequenceConstraints (optimizer.cpp:237-249)
-      const int t = static_cast<int>(blockIdx.x) + (t_base + tid) * G;
+      const int t = tile + (t_base + tid) * G;
       const float ssum = col_out[0];
       float vx = col_out[1 + 3 * tid] / ssum, wz = col_out[3 + 3 * tid] / ssum, vy = fx.s_cs[T + t];
       if (P->holonomic) {
@@ -2255,6 +2263,61 @@ __global__ void __launch_bounds__(256, 2) tile_fused_kernel(
     __syncthreads();
   }
   MPPI_TRACE_AT(15);
+}
+
+template<unsigned F, bool kExact>
+__global__ void __launch_bounds__(256, MPPI_FUSED_MIN_BLOCKS) tile_fused_kernel(
+  const DevParams * __restrict__ Pg, const uint8_t * __restrict__ cm, DevBuffers bufs, const int B, const int T, const int n_cap,
+  const int iteration, uint2 * host_res, const uint4 * up_host, const int up_vecs)
+{
+  tile_fused_body<F, kExact>(Pg, cm, bufs, B, T, n_cap, iteration, host_res, up_host, up_vecs, blockIdx.x, gridDim.x);
+}
+
+// One launch for several robots (independent problems of the same shape: BASELINE configs[4]).  Block r * G + tile works
+// on tile `tile` of robot r.  The tiles of one robot wait for each other (packet exchanges), and a grid this large is not
+// co-resident, so a block does not take its work from blockIdx: it draws a TICKET from a counter when it starts running.
+// Tickets are consecutive, so at any time at most one robot is incomplete (has tickets not yet drawn); every earlier robot
+// has all its blocks running or finished and therefore completes without waiting for anything that is not resident, which
+// frees the slots the incomplete robot's remaining blocks need: no deadlock whatever the dispatch order.  The counter is
+// never reset: the host passes the number of tickets drawn by earlier launches (base).
+struct __align__(16) FusedJob
+{
+  const DevParams * Pg;
+  const uint8_t * cm;
+  DevBuffers bufs;
+  int B, T, n_cap, iteration;
+  uint2 * host_res;
+  const uint4 * up_host;
+  int up_vecs, pad;
+};
+static_assert(sizeof(FusedJob) % 16 == 0, "jobs are copied as 16-byte vectors");
+
+template<unsigned F, bool kExact>
+__global__ void __launch_bounds__(256, MPPI_FUSED_MIN_BLOCKS) tile_fused_batch_kernel(
+  const FusedJob * __restrict__ jobs, const int G, unsigned * ticket_counter, const unsigned ticket_base)
+{
+  __shared__ __align__(16) FusedJob s_job;
+  __shared__ unsigned s_ticket;
+  const int tid = threadIdx.y * kTile + threadIdx.x, nthr = blockDim.y * kTile;
+  constexpr int kVecs = sizeof(FusedJob) / 16;
+  // the ticket is an atomic round trip; the job it will most likely name (in-order dispatch) is fetched meanwhile
+  if (tid == 0) {s_ticket = atomicAdd(ticket_counter, 1u) - ticket_base;}
+  int r = blockIdx.x / G;
+  for (int i = tid; i < kVecs; i += nthr) {
+    reinterpret_cast<uint4 *>(&s_job)[i] = __ldg(reinterpret_cast<const uint4 *>(jobs + r) + i);
+  }
+  __syncthreads();
+  const unsigned ticket = s_ticket;
+  if (static_cast<int>(ticket / G) != r) {
+    r = ticket / G;
+    __syncthreads();
+    for (int i = tid; i < kVecs; i += nthr) {
+      reinterpret_cast<uint4 *>(&s_job)[i] = __ldg(reinterpret_cast<const uint4 *>(jobs + r) + i);
+    }
+    __syncthreads();
+  }
+  tile_fused_body<F, kExact>(s_job.Pg, s_job.cm, s_job.bufs, s_job.B, s_job.T, s_job.n_cap, s_job.iteration, s_job.host_res,
+    s_job.up_host, s_job.up_vecs, static_cast<int>(ticket % G), G);
 }
 
 // K3c (stream layout): softmax weights and weighted control sums over time-major noise [T][B]; a GEMV

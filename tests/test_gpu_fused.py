@@ -133,3 +133,57 @@ def test_costmap_resize_and_large_costmap_fall_back_to_the_copy_engine(product_f
             _close(rg, ro, label=f"map {map_size} cycle {cycle}")
             g.set_control_sequence(ro.vx, ro.vy, ro.wz)
     g.close(); o.close()
+
+
+def test_bound_group_is_one_launch_and_bitwise_the_single_calls(product_fns, oracle_fns):
+    """mppi_batch_bind: mppi_optimize_batch over the bound group = ONE kernel launch (tile_fused_batch_kernel, blocks
+    draw tickets) with the same bits as one mppi_optimize per robot; a member keeps working on its own afterwards, and
+    the group dissolves when a member is destroyed."""
+    import ctypes as C
+    from mpcholonavigation_b200 import abi
+    n = 9
+    scs = [scenarios.config5_robot(r, batch=700) for r in range(n)]   # 22 tiles each: 198 blocks in one launch
+    T = scs[0].cfg["time_steps"]
+    single = [_engine(product_fns, sc, sc.noise()) for sc in scs]
+    group = [_engine(product_fns, sc, sc.noise()) for sc in scs]
+    orc = _engine(oracle_fns, scs[4], scs[4].noise())
+    hs = (abi.H * n)(*[e.h for e in group])
+    assert product_fns["batch_bind"](hs, n) == 0
+    ins = (abi.CycleIn * n)()
+    outs = (abi.CycleOut * n)()
+    keep, bufs = [], []
+    for i, sc in enumerate(scs):
+        cin, k = sc.cycle.pack()
+        ins[i] = cin
+        arrs = [np.empty(T, np.float32) for _ in range(3)]
+        outs[i].control_vx, outs[i].control_vy, outs[i].control_wz = (a.ctypes.data_as(abi.f32p) for a in arrs)
+        keep.append(k); bufs.append(arrs)
+    launches0 = sum(e.get_profile()["kernel_launches"] for e in group)
+    for cycle in range(6):
+        refs = [e.optimize(sc.cycle) for e, sc in zip(single, scs)]
+        ro = orc.optimize(scs[4].cycle)
+        call = product_fns["optimize_batch"] if cycle % 2 == 0 else None
+        if call is not None:
+            assert call(hs, ins, outs, n) == 0
+        else:
+            for e, sc in zip(group, scs):
+                e.upload_cycle(sc.cycle)
+            assert product_fns["optimize_batch_resident"](hs, outs, n) == 0
+        for i in range(n):
+            for a, name in zip(bufs[i], ("vx", "vy", "wz")):
+                assert np.array_equal(a, getattr(refs[i], name)), f"cycle {cycle} robot {i} {name}"
+            assert outs[i].fail_flag == refs[i].fail_flag
+        np.testing.assert_allclose(bufs[4][0], ro.vx, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(bufs[4][2], ro.wz, rtol=RTOL, atol=ATOL)
+        orc.set_control_sequence(*[b.copy() for b in bufs[4]])
+    assert sum(e.get_profile()["kernel_launches"] for e in group) - launches0 == 6   # one launch per cycle for 9 robots
+    # a bound member on its own (shares the leader's stream), then the group again, then without the leader
+    r_alone = group[3].optimize(scs[3].cycle)
+    r_ref = single[3].optimize(scs[3].cycle)
+    assert np.array_equal(r_alone.vx, r_ref.vx) and np.array_equal(r_alone.wz, r_ref.wz)
+    group[0].close()                                     # dissolves the group
+    r_after = group[5].optimize(scs[5].cycle)
+    r_ref5 = single[5].optimize(scs[5].cycle)
+    assert np.array_equal(r_after.vx, r_ref5.vx)
+    for e in single + group[1:] + [orc]:
+        e.close()
