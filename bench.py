@@ -321,7 +321,25 @@ def run_robots(args, rank, world, local_rank, fns, torch, dist):
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """stdout carries the ONE JSON line: whatever native libraries print there (NCCL's version line at communicator
+    creation, ...) is sent to stderr instead.  Returns the stream the JSON line is written to."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
+
+
 def main():
+    global print
+    _json_out = _claim_stdout()
+    _builtin_print = print
+
+    def print(*a, **kw):   # noqa: A001  (the JSON line goes to the real stdout; everything else is explicit about its file)
+        kw.setdefault("file", _json_out)
+        _builtin_print(*a, **kw)
+        kw["file"].flush()
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
@@ -351,6 +369,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from mpcholonavigation_b200 import load_product

@@ -147,10 +147,12 @@ struct mppi_handle
   int upd_blocks{0};
   // CUDA graphs of the steady-state cycle: [0] kernels + D2H (resident inputs), [1] H2D + kernels + D2H
   // captured graphs: slot = (with_upload ? 1 : 0) + 2 * tail_mode
-  cudaGraphExec_t gexec[6]{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t gkey_params[6]{0, 0, 0, 0, 0, 0}, gkey_costmap[6]{0, 0, 0, 0, 0, 0};
-  unsigned gkey_inst[6]{0, 0, 0, 0, 0, 0};
-  int gkey_fused[6]{0, 0, 0, 0, 0, 0};   // fused kernel: shared-memory key (path capacity, PathAlign samples); -1 = two-kernel path
+  // (+ 6 when the cycle is timed: the two event records are nodes of the graph, so that device_ms does not contain the
+  //  host's gap between recording an event and launching the graph)
+  cudaGraphExec_t gexec[12]{};
+  size_t gkey_params[12]{}, gkey_costmap[12]{};
+  unsigned gkey_inst[12]{};
+  int gkey_fused[12]{};   // fused kernel: shared-memory key (path capacity, PathAlign samples); -1 = two-kernel path
   int tail_mode{0};            // 0: optimize only, 1: + evalControl tail, 2: + tail with shiftControlSequence
   // peer-memory exchange (one process per GPU; mppi_comm_get_mailbox_handle / mppi_comm_connect_peers)
   uint2 * d_mailbox{nullptr};             // this rank's mailbox (kBoxPackets packets)
@@ -998,7 +1000,8 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
   // zero-copy: every tile also reads the hot part of the record over PCIe
   h->h2d_bytes = with_upload ? upload_bytes(h) + (h->zero_copy_now ? static_cast<size_t>(h->upd_blocks) * kHotBytes : 0) : 0;
   const uint64_t t_a = now_ns();
-  if (h->timing) {CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));}
+  bool ev0_recorded = false;
+  if (h->timing && !graph_ok) {CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream)); ev0_recorded = true;}
   const uint64_t t_b = now_ns();
   h->host_ns[2] += t_b - t_a;
   if (graph_ok) {
@@ -1011,7 +1014,7 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
       if (us != MPPI_OK) {return us;}
       with_upload = false;
     }
-    const int slot = (with_upload ? 1 : 0) + 2 * h->tail_mode;
+    const int slot = (with_upload ? 1 : 0) + 2 * h->tail_mode + (h->timing ? 6 : 0);
     const unsigned inst = pick_stream_instance(stream_feature_need(h->last));   // the K2 instance is baked into the graph
     const int fkey = h->wait_packets ? h->fused_key_N : -1;   // wait_packets == use_fused(h), evaluated above
     if (h->gexec[slot] && (h->gkey_params[slot] != h->params_copy_bytes || h->gkey_costmap[slot] != h->costmap_bytes ||
@@ -1026,8 +1029,11 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
       CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
       h->capturing = true;
       mppi_status s = MPPI_OK;
-      if (with_upload && !h->zero_copy_now) {s = enqueue_uploads(h);}
+      // (external event nodes: the host reads them back after the launch)
+      if (h->timing && cudaEventRecordWithFlags(h->ev0, h->stream, cudaEventRecordExternal) != cudaSuccess) {s = MPPI_E_CUDA;}
+      if (s == MPPI_OK && with_upload && !h->zero_copy_now) {s = enqueue_uploads(h);}
       if (s == MPPI_OK) {s = enqueue_kernels(h, false);}
+      if (s == MPPI_OK && h->timing && cudaEventRecordWithFlags(h->ev1, h->stream, cudaEventRecordExternal) != cudaSuccess) {s = MPPI_E_CUDA;}
       h->capturing = false;
       const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
       h->launches = launches_before;   // capture launched nothing
@@ -1051,11 +1057,11 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
       h->host_ns[3] += t_c - t_b;
       h->launches += (use_fused(h) ? 1ull : (h->stream_layout ? 4ull : (h->upd_blocks > kLastBlockMergeMax ? 3ull : 2ull))) *
         h->cfg.iteration_count + (h->tail_mode ? 1ull : 0ull);
-      if (h->timing) {CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));}
       h->host_ns[4] += now_ns() - t_c;
       return MPPI_OK;
     }
   }
+  if (h->timing && !ev0_recorded) {CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));}
   mppi_status s = MPPI_OK;
   if (with_upload && !h->zero_copy_now) {s = enqueue_uploads(h);}
   if (s != MPPI_OK) {return s;}
