@@ -1,0 +1,57 @@
+"""bench.py's output contract (the driver parses ONE JSON line from stdout).
+
+CPU: the reference arm (`--impl reference`, the oracle port on the host cores) runs here and must print exactly one
+line with the keys the driver reads.  GPU: the same for the default arm, plus the tier-specific objects (roofline,
+cpu_baseline, e2e, clocks, gpu_launches).
+"""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e"}
+
+
+def _run(*args, env=None):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
+                       timeout=600, env={**os.environ, **(env or {})})
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, f"stdout must carry exactly one line, got {len(lines)}: {r.stdout[:500]}"
+    return json.loads(lines[0])
+
+
+def test_reference_arm_prints_one_json_line():
+    d = _run("--impl", "reference", "--steps", "5", "--warmup", "3")
+    assert d["impl"] == "reference"
+    assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
+    assert d["metric"] == "rollout_steps_per_sec" and d["unit"] == "rollout-steps/s" and d["higher_is_better"] is True
+    assert d["config"]["workload"] == "omni_1000x56" and "model" not in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["value"] > 0 and d["vs_baseline"] is None
+
+
+def test_reference_arm_other_ranks_stay_silent():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2"],
+                       capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+@pytest.mark.gpu
+def test_default_arm_line_on_the_gpu():
+    d = _run("--steps", "30", "--warmup", "3")
+    assert BASE_KEYS | {"roofline", "cpu_baseline", "clocks", "gpu_launches", "latency_ms"} <= set(d)
+    assert d["n_gpus"] == 1 and d["steps"] == 30 and d["dtype"] == "f32" and d["scaling"] == "weak"
+    roof = d["roofline"]
+    assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and 0 < roof["frac"] < 1
+    assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9
+    assert d["gpu_launches"] == 30                      # one fused kernel per optimize()
+    assert d["e2e"]["h2d_bytes_per_step"] > 10000 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["e2e"]["value"] < d["value"]               # end to end includes the copies and the host
+    assert d["cpu_baseline"]["value"] < d["e2e"]["value"]
+    assert d["latency_ms"]["e2e_p50"] < 0.3             # north_star: 1000 x 56 under 0.3 ms per optimize()
