@@ -202,15 +202,17 @@ def run_robots(args, rank, world, local_rank, fns, torch, dist):
         cfg = dict(sc.cfg); cfg["device"] = local_rank
         e = Engine(fns, **cfg)
         e.set_robot(sc.robot); e.set_critics(sc.critics); e.set_noise(*sc.noise())
-        e.upload_cycle(sc.cycle)
         engines.append(e)
     hs = (abi.H * n)(*[e.h for e in engines])
-    # MPPI_BATCH_BIND=1: the rank's robots as one bound group (tile_fused_batch_kernel, one launch per 16 robots).  Measured
-    # on one B200 (profiles/README.md): device span 1.70 ms against 2.03 ms, but end to end 2.25 ms against 2.03 ms because
-    # the host's record building overlaps less with the device; the default stays one launch per robot.
-    bound = os.environ.get("MPPI_BATCH_BIND", "0") != "0" and n > 1
+    # the rank's robots as one bound group (mppi_batch_bind, stream layout: one strided upload and four kernel launches per
+    # 64 robots).  MPPI_BATCH_BIND=0: one fused launch per robot on its own stream; MPPI_BATCH_MODE=tile: the ticketed
+    # fused kernel.  Measured on one B200 (profiles/README.md): 0.68 / 1.5 ms (device span / end to end) bound in the stream
+    # layout, 1.70 / 2.25 ms bound in the tile layout, 2.03 / 2.03 ms unbound.
+    bound = os.environ.get("MPPI_BATCH_BIND", "1") != "0" and n > 1
     if bound:
-        assert fns["batch_bind"](hs, n) == 0   # one kernel launch per step for all robots of the rank
+        assert fns["batch_bind"](hs, n) == 0
+    for e, sc in zip(engines, robots):
+        e.upload_cycle(sc.cycle)
     ins = (abi.CycleIn * n)()
     outs = (abi.CycleOut * n)()
     keep = []
@@ -293,8 +295,9 @@ def run_robots(args, rank, world, local_rank, fns, torch, dist):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "robots_256", "robots": n_total, "robots_per_rank": n, "batch_size": B, "time_steps": T,
                        "critics": [c[0] for c in sc0.critics], "costmap": list(sc0.cycle.costmap.shape), "path_points": N,
-                       "noise": "injected", "parallelism": ("independent robots, one handle each, bound into one group per rank: ONE launch per step "
-                                       "(blocks draw tickets), no exchange" if bound else
+                       "noise": "injected", "parallelism": ("independent robots, one handle each, bound into one group per rank (%s), no exchange"
+                                       % ("tile layout, ticketed fused kernel" if os.environ.get("MPPI_BATCH_MODE") == "tile"
+                                          else "stream layout: one strided upload + four launches per 64 robots") if bound else
                                        "independent robots, one handle and stream each, no exchange"),
                        "l2": "cold: 256 MiB written between timed steps" if flush is not None else "warm (no flush)"},
             "clocks": clocks,
@@ -303,7 +306,10 @@ def run_robots(args, rank, world, local_rank, fns, torch, dist):
             "e2e": {"value": units / (e2e_total * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "p50_ms": pct(e2e_ms, 50)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": ("tile_fused_batch_kernel (%d robots per launch)" % n if bound else
+            "roofline": {"bound": "hbm", "kernel": ("rollout_score_stream_batch_kernel + path_costs_tm_batch_kernel + "
+                                                    "weighted_sums_tm_batch_kernel + merge_finalize_batch_kernel (%d robots, whole step)" % n
+                                                    if bound and os.environ.get("MPPI_BATCH_MODE") != "tile" else
+                                                    "tile_fused_batch_kernel (%d robots, whole step)" % n if bound else
                                                     "tile_fused_kernel x %d concurrent launches (whole step)" % n),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "algorithmic_bytes_per_launch": alg // n, "peak_source": peak_src,

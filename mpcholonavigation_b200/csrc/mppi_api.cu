@@ -136,6 +136,13 @@ struct mppi_handle
   std::vector<char> jobs_sent;            // what the device copy holds
   unsigned * d_ticket{nullptr};           // leader only: ticket counter of the batch kernel (never reset)
   uint32_t ticket_base{0};                // tickets drawn by all earlier batched launches
+  int batch_mode{0};                      // leader: 1 = tile layout, ticketed fused kernel; 2 = stream layout, four batched kernels
+  char * arena_h{nullptr};                // leader, mode 2: the [record | costmap] buffers of all members, one slice each,
+  char * arena_d{nullptr};                //   so that the whole group uploads with ONE strided copy
+  size_t arena_slice{0};
+  bool params_in_arena{false};            // member: h_params / d_params point into the leader's arena
+  uint32_t batch_tag{0};                  // leader, mode 2: counter behind the tag of the group's result packets
+  uint32_t result_tag{0};                 // tag the cycle in flight delivers its result packets with
   uint64_t host_ns[8]{0, 0, 0, 0, 0, 0, 0, 0};   // host-side time of the steady-state call by phase (mppi_debug_get_host_ns)
   bool zero_copy_enabled{true};   // MPPI_ZERO_COPY=0 disables
   bool coop_launch{true};
@@ -661,6 +668,9 @@ mppi_status stage_costmap(mppi_handle * h, const mppi_costmap & cm)
   const size_t bytes = static_cast<size_t>(cm.size_x) * cm.size_y;
   if (bytes == 0 || !cm.cells) {return fail(h, MPPI_E_CONFIG, "empty costmap");}
   if (!(cm.resolution > 0.0)) {return fail(h, MPPI_E_CONFIG, "costmap resolution must be > 0");}
+  if (bytes > h->costmap_capacity && h->params_in_arena) {
+    return fail(h, MPPI_E_CONFIG, "costmap larger than the slice of the bound group: mppi_batch_unbind first");
+  }
   if (bytes > h->costmap_capacity) {
     // grow (outside the steady state: the costmap size only changes on reconfiguration); the record staged by
     // build_params moves with the buffer
@@ -995,7 +1005,7 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
   h->ev_src = nullptr;
   h->wait_packets = use_fused(h);
   h->zero_copy_now = with_upload && h->wait_packets && h->zero_copy_enabled && upload_bytes(h) <= kZeroCopyMaxBytes;
-  if (h->wait_packets) {h->fepoch_host += static_cast<uint32_t>(h->cfg.iteration_count);}
+  if (h->wait_packets) {h->fepoch_host += static_cast<uint32_t>(h->cfg.iteration_count); h->result_tag = h->fepoch_host;}
   h->d2h_bytes = h->wait_packets ? sizeof(uint2) * (3 * h->T + 2 + (h->tail_mode ? 3 : 0)) : sizeof(float) * (3 * h->T + 6);
   // zero-copy: every tile also reads the hot part of the record over PCIe
   h->h2d_bytes = with_upload ? upload_bytes(h) + (h->zero_copy_now ? static_cast<size_t>(h->upd_blocks) * kHotBytes : 0) : 0;
@@ -1077,7 +1087,7 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
 mppi_status wait_result_packets(mppi_handle * h)
 {
   const int n = 3 * h->T + 2 + (h->tail_mode ? 3 : 0);
-  const uint32_t tag = h->fepoch_host;
+  const uint32_t tag = h->result_tag;
   const uint64_t * pk = reinterpret_cast<const uint64_t *>(h->h_res);
   uint32_t * dst = reinterpret_cast<uint32_t *>(h->h_out);
   uint64_t spins = 0;
@@ -1251,7 +1261,22 @@ void batch_unbind_group(mppi_handle * leader)
     m->batch_leader = nullptr;
     m->ev_src = nullptr;
     drop_graphs(m);
+    if (m->params_in_arena) {
+      // back to buffers of its own (the staged cycle does not survive: the next call uploads again)
+      const size_t bytes = kParamsCapacity + 256 + m->costmap_capacity;
+      m->h_params = nullptr; m->d_params = nullptr;
+      cudaHostAlloc(&m->h_params, bytes, cudaHostAllocMapped | cudaHostAllocPortable);
+      cudaMalloc(&m->d_params, bytes);
+      m->d_costmap = nullptr; m->h_costmap = nullptr;
+      m->params_in_arena = false;
+      m->cycle_uploaded = false;
+    }
+    if (m->h_res) {std::memset(m->h_res, 0, (3 * static_cast<size_t>(m->T) + 10) * sizeof(uint2));}   // tags of the group era
   }
+  if (leader->arena_h) {cudaFreeHost(leader->arena_h); leader->arena_h = nullptr;}
+  if (leader->arena_d) {cudaFree(leader->arena_d); leader->arena_d = nullptr;}
+  leader->arena_slice = 0;
+  leader->batch_mode = 0;
   leader->batch_group.clear();
   leader->jobs_sent.clear();
   if (leader->h_jobs) {cudaFreeHost(leader->h_jobs); leader->h_jobs = nullptr;}
@@ -1347,9 +1372,133 @@ mppi_status batch_launch(mppi_handle * L, mppi_handle ** hs, int c0, int n, bool
   for (int i = 0; i < n; ++i) {
     mppi_handle * h = hs[i];
     h->fepoch_host += 1u;
+    h->result_tag = h->fepoch_host;
     h->d2h_bytes = sizeof(uint2) * (3 * h->T + 2);
     h->h2d_bytes = with_upload ? upload_bytes(h) + (h->zero_copy_now ? static_cast<size_t>(h->upd_blocks) * kHotBytes : 0) : 0;
   }
+  return MPPI_OK;
+}
+
+// ---- mode 2: the group in the stream layout, four batched kernels for all robots -------------------------------
+// [B][T] -> [T][B] for the three noise planes of a handle that was created in the tile layout
+mppi_status to_stream_layout(mppi_handle * h)
+{
+  if (h->stream_layout) {return MPPI_OK;}
+  if ((static_cast<unsigned long long>(h->T) + kNoisePadRows) * static_cast<unsigned long long>(h->B) >= (1ull << 32)) {
+    return fail(h, MPPI_E_CONFIG, "batch_size * time_steps too large for the 32-bit offsets of the stream layout");
+  }
+  mppi_status s = ensure_tmp(h);
+  if (s != MPPI_OK) {return s;}
+  const size_t plane = static_cast<size_t>(h->B) * h->T * sizeof(float);
+  const dim3 grid((h->T + 31) / 32, (h->B + 31) / 32), block(32, 8);
+  for (int i = 0; i < 3; ++i) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_tmp, h->d_noise[i], plane, cudaMemcpyDeviceToDevice, h->stream));
+    transpose_tb_to_bt_kernel<float><<<grid, block, 0, h->stream>>>(h->d_tmp, h->d_noise[i], h->B, h->T);
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  drop_graphs(h);
+  h->stream_layout = true;
+  h->fused_key_N = -1;
+  return MPPI_OK;
+}
+
+constexpr int kStreamBatchChunk = 64;   // robots per upload + four launches: the host builds the next chunk's records meanwhile
+
+template<unsigned F, bool kExact>
+cudaError_t launch_stream_batch_instance(mppi_handle * L, const FusedJob * jobs, int n, int nthr, size_t smem)
+{
+  rollout_score_stream_batch_kernel<F, kExact><<<dim3((L->B + nthr - 1) / nthr, n), nthr, smem, L->stream>>>(jobs);
+  return cudaGetLastError();
+}
+
+// does every member qualify for the batched stream launch this cycle?
+bool batch_stream_ok(mppi_handle ** hs, int n)
+{
+  mppi_handle * L = hs[0];
+  for (int i = 0; i < n; ++i) {
+    const mppi_handle * h = hs[i];
+    if (!h->stream_layout || !h->params_in_arena || h->tail_mode != 0 || h->cfg.iteration_count != 1 || h->profiling ||
+      h->cfg.regenerate_noises || h->nranks > 1)
+    {
+      L->err = std::string("batched launch not used: member ") + std::to_string(i) + " does not qualify this cycle";
+      return false;
+    }
+  }
+  return true;
+}
+
+// One cycle of the members [c0, c0 + n) of a stream-layout group (records built): ONE strided upload, then K2 / K3a /
+// K3c / K4 launched once each with the robot as the last grid dimension; results as packets (tag) in each member's pinned
+// result buffer.  first / last: the leader's events bracket the whole call.
+mppi_status batch_stream_launch(mppi_handle * L, mppi_handle ** hs, int c0, int n, bool with_upload, uint32_t tag, bool first, bool last)
+{
+  unsigned inst = pick_stream_instance(stream_feature_need(hs[0]->last));
+  size_t max_used = 0;
+  for (int i = 0; i < n; ++i) {
+    if (pick_stream_instance(stream_feature_need(hs[i]->last)) != inst) {inst = SF_ALL;}
+    max_used = std::max(max_used, upload_bytes(hs[i]));
+  }
+  if (first && L->timing) {CUDA_TRY(L, cudaEventRecord(L->ev0, L->stream));}
+  if (with_upload) {
+    const size_t off = L->arena_slice * static_cast<size_t>(c0);
+    CUDA_TRY(L, cudaMemcpy2DAsync(L->arena_d + off, L->arena_slice, L->arena_h + off, L->arena_slice, max_used, n,
+      cudaMemcpyHostToDevice, L->stream));
+  }
+  for (int i = 0; i < n; ++i) {
+    mppi_handle * h = hs[i];
+    FusedJob & j = L->h_jobs[c0 + i];
+    std::memset(&j, 0, sizeof(j));
+    j.Pg = reinterpret_cast<const DevParams *>(h->d_params);
+    j.cm = h->d_costmap;
+    j.bufs = make_bufs(h, 0);
+    j.B = h->B; j.T = h->T;
+    j.host_res = h->h_res;
+    h->wait_packets = true;
+    h->zero_copy_now = false;
+    h->ev_src = L;
+    h->result_tag = tag;
+    h->d2h_bytes = sizeof(uint2) * (3 * h->T + 2);
+    h->h2d_bytes = with_upload ? upload_bytes(h) : 0;
+  }
+  const size_t off = sizeof(FusedJob) * static_cast<size_t>(c0), bytes = sizeof(FusedJob) * static_cast<size_t>(n);
+  if (std::memcmp(L->jobs_sent.data() + off, L->h_jobs + c0, bytes) != 0) {
+    CUDA_TRY(L, cudaMemcpyAsync(L->d_jobs + c0, L->h_jobs + c0, bytes, cudaMemcpyHostToDevice, L->stream));
+    std::memcpy(L->jobs_sent.data() + off, L->h_jobs + c0, bytes);
+  }
+  const FusedJob * jobs = L->d_jobs + c0;
+  const int T = L->T, B = L->B;
+  {
+    const int nthr = stream_block_threads(L);
+    const int Tp = ((T + kStreamChunk - 1) / kStreamChunk) * kStreamChunk;
+    const size_t smem = kHotBytes + sizeof(float) * 3 * Tp;
+    cudaError_t e;
+    switch (inst) {
+      case kSfOmniDefault: e = launch_stream_batch_instance<kSfOmniDefault, true>(L, jobs, n, nthr, smem); break;
+      case kSfOmniDefaultFp: e = launch_stream_batch_instance<kSfOmniDefaultFp, true>(L, jobs, n, nthr, smem); break;
+      case kSfObstaclesFp: e = launch_stream_batch_instance<kSfObstaclesFp, true>(L, jobs, n, nthr, smem); break;
+      default: e = launch_stream_batch_instance<SF_ALL, false>(L, jobs, n, nthr, smem); break;
+    }
+    CUDA_TRY(L, e);
+  }
+  {
+    const int grid = std::min((B + kUpdThreads - 1) / kUpdThreads, 148 * 8);
+    path_costs_tm_batch_kernel<<<dim3(grid, n), kUpdThreads, k3_common_smem_bytes(), L->stream>>>(jobs);
+    CUDA_TRY(L, cudaGetLastError());
+  }
+  const int chunks = (B + kWsChunk - 1) / kWsChunk;
+  {
+    const int gy = weighted_sums_row_groups(T, chunks * n);   // the rows are split less when many robots fill the machine
+    weighted_sums_tm_batch_kernel<<<dim3(chunks, gy, n), kWsThreads, 0, L->stream>>>(jobs);
+    CUDA_TRY(L, cudaGetLastError());
+  }
+  {
+    const int merge_grid = (T + kMergeT - 1) / kMergeT;
+    merge_finalize_batch_kernel<<<dim3(merge_grid, n), kUpdThreads, 0, L->stream>>>(jobs, chunks, 3 * T + 2, tag);
+    CUDA_TRY(L, cudaGetLastError());
+  }
+  if (last && L->timing) {CUDA_TRY(L, cudaEventRecord(L->ev1, L->stream));}
+  L->launches += 4;
   return MPPI_OK;
 }
 
@@ -1361,6 +1510,54 @@ mppi_status batch_run_group(mppi_handle ** hs, const mppi_cycle_in * ins, mppi_c
   CUDA_TRY(L, cudaSetDevice(L->device));
   mppi_status first = MPPI_OK;
   std::vector<char> pending(n, 0);
+  if (L->batch_mode == 2) {
+    // stream-layout group, in chunks: the records of a chunk are built, then the chunk is uploaded with one strided copy
+    // and launched (four kernels) while the host builds the next chunk
+    if (batch_stream_ok(hs, n)) {
+      const uint32_t tag = 0x80000000u | (++L->batch_tag);   // never a tag of the fused kernel's epochs
+      const int chunk = ins ? kStreamBatchChunk : n;
+      for (int c0 = 0; c0 < n; c0 += chunk) {
+        const int cn = std::min(chunk, n - c0);
+        mppi_status s = MPPI_OK;
+        for (int i = c0; i < c0 + cn && s == MPPI_OK; ++i) {
+          if (ins) {
+            s = build_params(hs[i], &ins[i], 0, kUnset, true);
+            if (s == MPPI_OK) {s = stage_costmap(hs[i], ins[i].costmap);}
+            if (s == MPPI_OK) {hs[i]->cycle_uploaded = true;}
+          } else if (!hs[i]->cycle_uploaded) {
+            s = fail(hs[i], MPPI_E_STATE, "mppi_optimize_batch_resident before mppi_upload_cycle");
+          }
+        }
+        if (s == MPPI_OK) {s = batch_stream_launch(L, hs + c0, c0, cn, ins != nullptr, tag, c0 == 0, c0 + cn == n);}
+        if (s == MPPI_OK) {
+          for (int i = c0; i < c0 + cn; ++i) {pending[i] = 1;}
+        } else if (first == MPPI_OK) {
+          first = s;
+        }
+      }
+      for (int i = 0; i < n; ++i) {
+        if (!pending[i]) {continue;}
+        const mppi_status f = finish_optimize(hs[i], outs ? &outs[i] : nullptr);
+        if (f != MPPI_OK && first == MPPI_OK) {first = f;}
+      }
+      return first;
+    }
+    if (L->timing) {cudaEventRecord(L->ev0, L->stream);}
+    for (int i = 0; i < n; ++i) {   // one by one on the shared stream
+      mppi_status f = MPPI_OK;
+      if (ins) {
+        f = build_params(hs[i], &ins[i], 0, kUnset, true);
+        if (f == MPPI_OK) {f = stage_costmap(hs[i], ins[i].costmap);}
+        if (f == MPPI_OK) {hs[i]->cycle_uploaded = true;}
+      } else if (!hs[i]->cycle_uploaded) {
+        f = fail(hs[i], MPPI_E_STATE, "mppi_optimize_batch_resident before mppi_upload_cycle");
+      }
+      if (f == MPPI_OK) {f = enqueue_optimize(hs[i], ins != nullptr);}
+      if (f == MPPI_OK) {f = finish_optimize(hs[i], outs ? &outs[i] : nullptr);}
+      if (f != MPPI_OK && first == MPPI_OK) {first = f;}
+    }
+    return first;
+  }
   // resident inputs: nothing to prepare on the host, one launch for the whole group
   const int chunk = ins ? kBatchChunk : n;
   for (int c0 = 0; c0 < n; c0 += chunk) {
@@ -1850,11 +2047,15 @@ mppi_status mppi_batch_bind(mppi_handle ** hs, int32_t n)
 {
   if (!hs || n < 1 || !hs[0]) {return MPPI_E_CONFIG;}
   mppi_handle * L = hs[0];
+  // mode 2 (default): the members move to the stream layout and the group runs as four batched kernels; mode 1
+  // (MPPI_BATCH_MODE=tile): the members stay in the tile layout, one ticketed fused kernel per 16 robots
+  int mode = 2;
+  if (const char * e = std::getenv("MPPI_BATCH_MODE")) {mode = std::strcmp(e, "tile") == 0 ? 1 : 2;}
   for (int i = 0; i < n; ++i) {
     mppi_handle * h = hs[i];
     if (!h) {return MPPI_E_CONFIG;}
     if (h->device != L->device || h->B != L->B || h->T != L->T) {return fail(L, MPPI_E_CONFIG, "mppi_batch_bind: handles must share device, batch_size and time_steps");}
-    if (h->stream_layout || h->nranks > 1 || h->cfg.regenerate_noises) {return fail(L, MPPI_E_CONFIG, "mppi_batch_bind: tile-layout, unsharded handles without regenerate_noises only");}
+    if ((mode == 1 && h->stream_layout) || h->nranks > 1 || h->cfg.regenerate_noises) {return fail(L, MPPI_E_CONFIG, "mppi_batch_bind: unsharded handles without regenerate_noises only (tile mode: tile layout only)");}
     for (int k = 0; k < i; ++k) {if (hs[k] == h) {return fail(L, MPPI_E_CONFIG, "mppi_batch_bind: duplicate handle");}}
   }
   for (int i = 0; i < n; ++i) {
@@ -1869,10 +2070,31 @@ mppi_status mppi_batch_bind(mppi_handle ** hs, int32_t n)
   L->jobs_sent.assign(sizeof(FusedJob) * static_cast<size_t>(n), 0);
   std::memset(L->h_jobs, 0, sizeof(FusedJob) * static_cast<size_t>(n));
   L->batch_group.assign(hs, hs + n);
+  L->batch_mode = mode;
+  L->batch_tag = 0;
+  if (mode == 2) {
+    size_t cap = 64 * 1024;
+    for (int i = 0; i < n; ++i) {cap = std::max(cap, hs[i]->costmap_capacity);}
+    L->arena_slice = (kParamsCapacity + 256 + cap + 255) & ~static_cast<size_t>(255);
+    CUDA_TRY(L, cudaHostAlloc(&L->arena_h, L->arena_slice * n, cudaHostAllocMapped | cudaHostAllocPortable));
+    CUDA_TRY(L, cudaMalloc(&L->arena_d, L->arena_slice * n));
+  }
   for (int i = 0; i < n; ++i) {
     mppi_handle * h = hs[i];
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     drop_graphs(h);
+    if (mode == 2) {
+      const mppi_status s = to_stream_layout(h);
+      if (s != MPPI_OK) {batch_unbind_group(L); return s;}
+      cudaFreeHost(h->h_params); cudaFree(h->d_params);
+      h->h_params = L->arena_h + L->arena_slice * i;
+      h->d_params = L->arena_d + L->arena_slice * i;
+      h->h_costmap = nullptr; h->d_costmap = nullptr;
+      h->costmap_capacity = L->arena_slice - kParamsCapacity - 256;
+      h->params_in_arena = true;
+      h->cycle_uploaded = false;
+      std::memset(h->h_res, 0, (3 * static_cast<size_t>(h->T) + 10) * sizeof(uint2));
+    }
     h->batch_leader = L;
     if (h != L) {h->own_stream = h->stream; h->stream = L->stream;}
   }

@@ -887,8 +887,8 @@ static_assert(kStreamChunk <= kNoisePadRows, "prefetch reads up to kStreamChunk 
 // kExact: the mask IS the set of active features (no runtime flag tests inside the loop); otherwise the mask is an
 // upper bound and every feature is still gated by its per-cycle runtime flag (generic instance).
 template<unsigned F, bool kExact>
-__global__ void __launch_bounds__(kStreamThreads, MPPI_STREAM_MIN_BLOCKS) rollout_score_stream_kernel(
-  const DevParams * __restrict__ P, const uint8_t * __restrict__ cm, DevBuffers bufs)
+__device__ __forceinline__ void rollout_score_stream_body(
+  const DevParams * __restrict__ P, const uint8_t * __restrict__ cm, const DevBuffers & bufs)
 {
   extern __shared__ float smem[];
   const int tid = threadIdx.x;
@@ -1170,6 +1170,13 @@ __global__ void __launch_bounds__(kStreamThreads, MPPI_STREAM_MIN_BLOCKS) rollou
     const unsigned m = warp_max_u(live ? best_j : 0u);
     if ((tid & 31) == 0) {atomicMax(&bufs.st->furthest_candidate, m);}
   }
+}
+
+template<unsigned F, bool kExact>
+__global__ void __launch_bounds__(kStreamThreads, MPPI_STREAM_MIN_BLOCKS) rollout_score_stream_kernel(
+  const DevParams * __restrict__ P, const uint8_t * __restrict__ cm, DevBuffers bufs)
+{
+  rollout_score_stream_body<F, kExact>(P, cm, bufs);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1599,8 +1606,7 @@ __device__ __forceinline__ void k3_publish_flags(const DevParams * P, DevState *
 // weighted_sums_tm_kernel.
 // kMinBlocks trades registers for occupancy: 8 resident blocks (64 registers, a few spills) win once the batch keeps every
 // SM oversubscribed, 5 (96 registers) below that (measured on B200, profiles/).
-template<int kMinBlocks>
-__global__ void __launch_bounds__(kUpdThreads, kMinBlocks) path_costs_tm_kernel(const DevParams * __restrict__ Pg, DevBuffers bufs, int iteration)
+__device__ __forceinline__ void path_costs_tm_body(const DevParams * __restrict__ Pg, const DevBuffers & bufs, int iteration)
 {
   extern __shared__ float smem[];
   __shared__ K3Decisions dec;
@@ -1641,6 +1647,12 @@ __global__ void __launch_bounds__(kUpdThreads, kMinBlocks) path_costs_tm_kernel(
     bufs.st->global_min = gm;
     k3_publish_flags(P, bufs.st, dec, bufs.out);
   }
+}
+
+template<int kMinBlocks>
+__global__ void __launch_bounds__(kUpdThreads, kMinBlocks) path_costs_tm_kernel(const DevParams * __restrict__ Pg, DevBuffers bufs, int iteration)
+{
+  path_costs_tm_body(Pg, bufs, iteration);
 }
 
 // K3, tile layout (small and medium batches; latency matters more than throughput here).  One block owns
@@ -2332,7 +2344,7 @@ constexpr int kWsThreads = 256;
 constexpr int kWsVec = 8;
 constexpr int kWsChunk = 32 * 4 * kWsVec;   // 1024 trajectories per block
 
-__global__ void __launch_bounds__(kWsThreads) weighted_sums_tm_kernel(const DevParams * __restrict__ Pg, DevBuffers bufs)
+__device__ __forceinline__ void weighted_sums_tm_body(const DevParams * __restrict__ Pg, const DevBuffers & bufs)
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = Pg->T, B = Pg->B;
@@ -2402,6 +2414,11 @@ __global__ void __launch_bounds__(kWsThreads) weighted_sums_tm_kernel(const DevP
   }
 }
 
+__global__ void __launch_bounds__(kWsThreads) weighted_sums_tm_kernel(const DevParams * __restrict__ Pg, DevBuffers bufs)
+{
+  weighted_sums_tm_body(Pg, bufs);
+}
+
 // K4: parallel merge of n partial records [m, s, W...] (online-softmax merge, SURVEY 8e exchange 2).
 // Used (a) after K3 when the batch produced more partials than one block should merge serially, and
 // (b) in sharded configurations on the all-gathered per-rank records; every rank merges redundantly and
@@ -2410,9 +2427,11 @@ __global__ void __launch_bounds__(kWsThreads) weighted_sums_tm_kernel(const DevP
 
 constexpr int kMergeCached = 2048;   // partial records whose rescale factors are cached in shared memory
 
-__global__ void __launch_bounds__(kUpdThreads) merge_finalize_kernel(
-  const DevParams * __restrict__ Pg, const float * __restrict__ parts, int n, int stride, DevBuffers bufs, int finalize,
-  float * __restrict__ dst)
+// host_res != nullptr (finalize only): the result also goes straight into pinned host memory as {value, tag} packets
+// (multi-robot groups: no copy node and no stream synchronisation per robot, see wait_result_packets)
+__device__ __forceinline__ void merge_finalize_body(
+  const DevParams * __restrict__ Pg, const float * __restrict__ parts, int n, int stride, const DevBuffers & bufs, int finalize,
+  float * __restrict__ dst, uint2 * host_res, unsigned tag)
 {
   __shared__ float s_red[kUpdThreads / 32];
   __shared__ float s_col[3 * kMergeT + 1];
@@ -2480,8 +2499,25 @@ __global__ void __launch_bounds__(kUpdThreads) merge_finalize_kernel(
       }
       bufs.cs[t] = vx; bufs.cs[T + t] = vy; bufs.cs[2 * T + t] = wz;
       bufs.out[t] = vx; bufs.out[T + t] = vy; bufs.out[2 * T + t] = wz;
+      if (host_res) {
+        st_packet(host_res + t, __float_as_uint(vx), tag);
+        st_packet(host_res + T + t, __float_as_uint(vy), tag);
+        st_packet(host_res + 2 * T + t, __float_as_uint(wz), tag);
+      }
     }
   }
+  if (host_res && finalize && blockIdx.x == 0 && tid == 0) {
+    // fail flag and furthest reached path point, published by the path-cost kernel in front of this one
+    st_packet(host_res + 3 * T, __float_as_uint(bufs.out[3 * T]), tag);
+    st_packet(host_res + 3 * T + 1, __float_as_uint(bufs.out[3 * T + 1]), tag);
+  }
+}
+
+__global__ void __launch_bounds__(kUpdThreads) merge_finalize_kernel(
+  const DevParams * __restrict__ Pg, const float * __restrict__ parts, int n, int stride, DevBuffers bufs, int finalize,
+  float * __restrict__ dst)
+{
+  merge_finalize_body(Pg, parts, n, stride, bufs, finalize, dst, nullptr, 0u);
 }
 
 // K4p: exchange 2 over peer memory, fused with the merges on both sides of it.  Every block merges its columns of the
@@ -2748,6 +2784,36 @@ __global__ void optimized_trajectory_kernel(const float * __restrict__ cs, float
     out_t3[3 * t + 2] = yaw;
     prev_yaw = yaw;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Multi-robot groups in the stream layout (BASELINE configs[4]): the four kernels of the large-batch path, launched
+// ONCE for all robots of a group; the robot is the last grid dimension and its buffers come from the job table.
+// Robots are independent problems (own record, costmap, noise, control sequence, state), so nothing else changes.
+// ---------------------------------------------------------------------------------------------------
+template<unsigned F, bool kExact>
+__global__ void __launch_bounds__(kStreamThreads, MPPI_STREAM_MIN_BLOCKS) rollout_score_stream_batch_kernel(const FusedJob * __restrict__ jobs)
+{
+  const FusedJob & j = jobs[blockIdx.y];
+  rollout_score_stream_body<F, kExact>(j.Pg, j.cm, j.bufs);
+}
+
+__global__ void __launch_bounds__(kUpdThreads, 5) path_costs_tm_batch_kernel(const FusedJob * __restrict__ jobs)
+{
+  const FusedJob & j = jobs[blockIdx.y];
+  path_costs_tm_body(j.Pg, j.bufs, 0);
+}
+
+__global__ void __launch_bounds__(kWsThreads) weighted_sums_tm_batch_kernel(const FusedJob * __restrict__ jobs)
+{
+  const FusedJob & j = jobs[blockIdx.z];
+  weighted_sums_tm_body(j.Pg, j.bufs);
+}
+
+__global__ void __launch_bounds__(kUpdThreads) merge_finalize_batch_kernel(const FusedJob * __restrict__ jobs, int n_parts, int stride, unsigned tag)
+{
+  const FusedJob & j = jobs[blockIdx.y];
+  merge_finalize_body(j.Pg, j.bufs.partials, n_parts, stride, j.bufs, 1, nullptr, j.host_res, tag);
 }
 
 }  // namespace mppi
