@@ -9,8 +9,8 @@ harness (benchmark/optimizer_benchmark.cpp:85-93): fixed robot pose, control seq
 
 workloads (BASELINE.json configs):
   omni_1000x56        configs[0]/[1]: Omni 1000 x 56, dt 0.05, default critic set, 100x100 costmap, 40-point path,
-                      reference-style injected noise.  DEFAULT at N=1; at N>1 every rank runs its own robot of this
-                      shape (independent scenarios, no data-path collective: weak scaling, configs[4] style).
+                      reference-style injected noise.  DEFAULT at N=1; at N>1 every rank runs this same problem
+                      with its own noise draw (replicas, no data-path collective: weak scaling).
   obstacles_16384x56  configs[2]: 16384 x 56, 400x400 costmap, ObstaclesCritic in footprint mode.
   sharded_262144x100  configs[3]: 262144 x 100 sharded over the ranks, Philox noise by global trajectory index,
                       NCCL exchanges of the furthest path point and of the softmax partials (strong scaling).
@@ -48,7 +48,10 @@ def algorithmic_bytes(B, T, N, cells, iterations=1):
 
 def pick_scenario(workload, rank, world):
     if workload == "omni_1000x56":
-        sc = scenarios.config1() if world == 1 else scenarios.config5_robot(rank, batch=1000)
+        # N > 1: every rank runs the SAME problem (configs[1]) with its own noise draw, so that the per-GPU work really is
+        # fixed as N grows (weak scaling).  Distinct maps per rank (the robots_256 workload) make the step as slow as the
+        # unluckiest robot: footprint checks near obstacles cost several times a free-space pose.
+        sc = scenarios.config1(noise_seed=1 + rank)
         sc.name = "omni_1000x56"
         return sc, "injected"
     if workload == "obstacles_16384x56":
@@ -528,7 +531,7 @@ def main():
                        "critics": [c[0] for c in sc.critics], "costmap": list(sc.cycle.costmap.shape), "path_points": N,
                        "noise": noise_kind, "per_rank_batch": B_local,
                        "parallelism": (f"sharded over ranks, 2 exchanges ({'in-kernel over NVLink peer memory' if args.exchange == 'peer' else 'NCCL all-reduce + all-gather'})" if sharded and world > 1 else
-                                       ("independent robots, one per rank" if world > 1 else "single GPU")),
+                                       ("replicas: the same problem on every rank, own noise draw, no exchange" if world > 1 else "single GPU")),
                        "l2": "cold: 256 MiB written between timed steps" if flush is not None else "warm (no flush)"},
             "clocks": clocks,
             "latency_ms": {"device_p50": pct(dev_ms, 50), "device_p90": pct(dev_ms, 90), "device_p99": pct(dev_ms, 99),
