@@ -650,6 +650,7 @@ DevBuffers make_bufs(mppi_handle * h, int mode)
   b.pk_up = h->d_pk;
   b.pk_x1 = h->d_pk ? h->d_pk + h->upd_blocks : nullptr;
   b.pk_rec = h->d_pk ? h->d_pk + 2 * h->upd_blocks : nullptr;
+  b.pk_out = h->d_pk ? h->d_pk + static_cast<size_t>(h->upd_blocks) * (2 + 3 * h->T + 2) : nullptr;
   b.epoch = h->d_fepoch;
   return b;
 }
@@ -803,7 +804,7 @@ bool use_fused(mppi_handle * h)
 }
 
 template<unsigned F, bool kExact>
-cudaError_t launch_fused_instance(mppi_handle * h, int iteration, uint2 * host_res, bool zero_copy)
+cudaError_t launch_fused_instance(mppi_handle * h, int iteration, uint2 * host_res, bool zero_copy, int tail_mode)
 {
   const int S = pick_segments(h);
   const dim3 grid((h->B + kTile - 1) / kTile), block(kTile, S);
@@ -816,21 +817,22 @@ cudaError_t launch_fused_instance(mppi_handle * h, int iteration, uint2 * host_r
   // zero-copy upload: the kernel pulls [record | costmap] out of the pinned staging buffer itself (first iteration only)
   const uint4 * up_host = zero_copy ? reinterpret_cast<const uint4 *>(h->h_params) : nullptr;
   int up_vecs = zero_copy ? static_cast<int>((upload_bytes(h) + 15) / 16) : 0;
-  void * args[] = {&dp, &cm, &bufs, &B, &T, &N, &iteration, &host_res, &up_host, &up_vecs};
+  float * hist = h->d_hist;
+  void * args[] = {&dp, &cm, &bufs, &B, &T, &N, &iteration, &host_res, &up_host, &up_vecs, &tail_mode, &hist};
   if (!h->coop_launch) {   // experiment switch (MPPI_COOP=0): plain launch, no co-residency guarantee
     return cudaLaunchKernel(reinterpret_cast<const void *>(&tile_fused_kernel<F, kExact>), grid, block, args, smem, h->stream);
   }
   return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&tile_fused_kernel<F, kExact>), grid, block, args, smem, h->stream);
 }
 
-mppi_status launch_fused(mppi_handle * h, int iteration, uint2 * host_res, bool zero_copy)
+mppi_status launch_fused(mppi_handle * h, int iteration, uint2 * host_res, bool zero_copy, int tail_mode)
 {
   cudaError_t e;
   switch (pick_stream_instance(stream_feature_need(h->last))) {
-    case kSfOmniDefault: e = launch_fused_instance<kSfOmniDefault, true>(h, iteration, host_res, zero_copy); break;
-    case kSfOmniDefaultFp: e = launch_fused_instance<kSfOmniDefaultFp, true>(h, iteration, host_res, zero_copy); break;
-    case kSfObstaclesFp: e = launch_fused_instance<kSfObstaclesFp, true>(h, iteration, host_res, zero_copy); break;
-    default: e = launch_fused_instance<SF_ALL, false>(h, iteration, host_res, zero_copy); break;
+    case kSfOmniDefault: e = launch_fused_instance<kSfOmniDefault, true>(h, iteration, host_res, zero_copy, tail_mode); break;
+    case kSfOmniDefaultFp: e = launch_fused_instance<kSfOmniDefaultFp, true>(h, iteration, host_res, zero_copy, tail_mode); break;
+    case kSfObstaclesFp: e = launch_fused_instance<kSfObstaclesFp, true>(h, iteration, host_res, zero_copy, tail_mode); break;
+    default: e = launch_fused_instance<SF_ALL, false>(h, iteration, host_res, zero_copy, tail_mode); break;
   }
   CUDA_TRY(h, e);
   h->launches++;
@@ -909,9 +911,10 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
     if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[0], h->stream));}
     if (fused) {
       // small batches: rollout, critics, softmax update and merge in one cooperative launch (pev: all of it counts as K2)
-      // the launch that completes the result writes it to pinned host memory itself (packets), unless the tail follows
+      // the launch that completes the result writes it to pinned host memory itself (packets) and, for
+      // mppi_eval_control, runs the evalControl tail on tile 0
       const bool last = it + 1 == h->cfg.iteration_count;
-      mppi_status s = launch_fused(h, it, last && !h->tail_mode ? h->h_res : nullptr, h->zero_copy_now && it == 0);
+      mppi_status s = launch_fused(h, it, last ? h->h_res : nullptr, h->zero_copy_now && it == 0, last ? h->tail_mode : 0);
       if (s != MPPI_OK) {return s;}
       if (prof) {
         CUDA_TRY(h, cudaEventRecord(h->pev[1], h->stream));
@@ -973,10 +976,10 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
       if ((s = launch_regenerate(h)) != MPPI_OK) {return s;}
     }
   }
-  if (h->tail_mode) {
-    // evalControl's tail (Savitzky-Golay filter, command extraction, shift) stays on the device
-    eval_tail_kernel<<<1, 32, 0, h->stream>>>(h->d_cs, h->d_hist, h->d_out, h->T, holonomic(h) ? 1 : 0, h->tail_mode == 2 ? 1 : 0,
-      fused ? h->h_res : nullptr, h->d_fepoch);
+  if (h->tail_mode && !fused) {
+    // evalControl's tail (Savitzky-Golay filter, command extraction, shift) stays on the device (the fused kernel runs it
+    // itself)
+    eval_tail_kernel<<<1, 32, 0, h->stream>>>(h->d_cs, h->d_hist, h->d_out, h->T, holonomic(h) ? 1 : 0, h->tail_mode == 2 ? 1 : 0);
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
   }
@@ -1066,7 +1069,7 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
       const uint64_t t_c = now_ns();
       h->host_ns[3] += t_c - t_b;
       h->launches += (use_fused(h) ? 1ull : (h->stream_layout ? 4ull : (h->upd_blocks > kLastBlockMergeMax ? 3ull : 2ull))) *
-        h->cfg.iteration_count + (h->tail_mode ? 1ull : 0ull);
+        h->cfg.iteration_count + (h->tail_mode && !use_fused(h) ? 1ull : 0ull);
       h->host_ns[4] += now_ns() - t_c;
       return MPPI_OK;
     }
@@ -1788,7 +1791,7 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   CUDA_TRY(h, cudaMemsetAsync(h->d_seq, 0, sizeof(unsigned), h->stream));
   CUDA_TRY(h, cudaMalloc(&h->d_st, sizeof(DevState)));
   if (!h->stream_layout) {
-    const size_t n_pk = static_cast<size_t>(h->upd_blocks) * (2 + stride);
+    const size_t n_pk = static_cast<size_t>(h->upd_blocks) * (2 + stride) + stride;
     CUDA_TRY(h, cudaMalloc(&h->d_pk, n_pk * sizeof(uint2)));
     CUDA_TRY(h, cudaMemsetAsync(h->d_pk, 0, n_pk * sizeof(uint2), h->stream));
   }

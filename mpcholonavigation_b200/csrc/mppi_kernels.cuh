@@ -57,6 +57,7 @@ struct DevBuffers
   uint2 * pk_up;        // [G]            per tile: "my slice of the upload is in device memory"
   uint2 * pk_x1;        // [G]            per tile: furthest-point candidate | survivor flags << 16
   uint2 * pk_rec;       // [G][3T + 2]    per tile: softmax record (m, s, W[3T])
+  uint2 * pk_out;       // [3T]           evalControl tail: the new sequence on its way from the owner tiles to tile 0
   unsigned * epoch;     // completed fused launches of this handle; the tag of the running launch is *epoch + 1
 };
 
@@ -376,7 +377,9 @@ __device__ __forceinline__ void rollout_tile_body(
       if (up_begin + tid < up_end) {dst[up_begin + tid] = up_v[0];}
       if (up_begin + nthreads + tid < up_end) {dst[up_begin + nthreads + tid] = up_v[1];}
       for (int i = up_begin + 2 * nthreads + tid; i < up_end; i += nthreads) {dst[i] = __ldg(fx->up_host + i);}
-      __threadfence();   // the slice is visible device-wide before the tile's flag (sent after the barrier below)
+      // (the fence that makes the slice visible device-wide, and the tile's flag behind it, wait until the yaw scan is
+      //  over: nothing reads the device copies before the position critics, and a fence here would sit on the path of
+      //  the first barrier)
     }
   }
   if (tid < kHotBytes / 16) {reinterpret_cast<float4 *>(s_hot)[tid] = hot_v;}
@@ -386,9 +389,6 @@ __device__ __forceinline__ void rollout_tile_body(
   for (int i = tid + 2 * nthreads; i < 3 * T; i += nthreads) {s_cs[i] = bufs.cs[i];}
   __syncthreads();
   MPPI_TRACE_AT(2);
-  if (kFused) {
-    if (zero_copy && tid == 0) {st_packet(bufs.pk_up + tile, 1u, fx->tag);}
-  }
   const bool hol = MPPI_SF(SF_HOL, p.holonomic != 0);
   const bool acker = MPPI_SF(SF_ACKER, p.model == MPPI_MODEL_ACKERMANN);
   const bool con_on = MPPI_SF(SF_CON, p.constraint.on), fwd_on = MPPI_SF(SF_FWD, p.forward.on);
@@ -465,7 +465,13 @@ __device__ __forceinline__ void rollout_tile_body(
       }
     }
   }
+  if (kFused) {
+    if (zero_copy) {__threadfence();}   // this thread's part of the upload slice is visible device-wide ...
+  }
   __syncthreads();
+  if (kFused) {
+    if (zero_copy && tid == 0) {st_packet(bufs.pk_up + tile, 1u, fx->tag);}   // ... before the tile's flag goes out
+  }
 
   MPPI_TRACE_AT(4);
   // ---- P3: velocity critics + gamma term, then dx*dt / dy*dt with the one-step yaw lag written in place
@@ -1779,6 +1785,60 @@ __global__ void __launch_bounds__(kUpdThreads) path_softmax_update_kernel(
   MPPI_TRACE_AT(22);
 }
 
+// The tail of Optimizer::evalControl (optimizer.cpp:147-152) for one plane (0 vx, 1 vy, 2 wz) of the control sequence,
+// v[T] in shared memory: utils::savitskyGolayFilter (utils.hpp:442-605) with the 4-deep control history (global, updated),
+// getControlFromSequenceAsTwist (optimizer.cpp:396-410; returned) and shiftControlSequence (:206-225).  One thread; the
+// filter is inherently sequential (already-filtered neighbours are reused) and reproduces the reference's quirks: index
+// num_sequences - 4 is never filtered, vy is filtered for every model.
+__device__ __forceinline__ float eval_tail_plane(float * v, float * __restrict__ hist, int plane, int T, int holonomic, int shift)
+{
+  const unsigned num_sequences = static_cast<unsigned>(T) - 1u;
+  float h0 = hist[0 * 3 + plane], h1 = hist[1 * 3 + plane], h2 = hist[2 * 3 + plane], h3 = hist[3 * 3 + plane];
+  if (num_sequences >= 20u) {
+    float f[9] = {-21.0f, 14.0f, 39.0f, 54.0f, 59.0f, 54.0f, 39.0f, 14.0f, -21.0f};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {f[i] = __fdiv_rn(f[i], 231.0f);}
+    auto apply = [&](float d0, float d1, float d2, float d3, float d4, float d5, float d6, float d7, float d8) -> float {
+        float a = __fadd_rn(0.0f, __fmul_rn(d0, f[0]));
+        a = __fadd_rn(a, __fmul_rn(d1, f[1])); a = __fadd_rn(a, __fmul_rn(d2, f[2])); a = __fadd_rn(a, __fmul_rn(d3, f[3]));
+        a = __fadd_rn(a, __fmul_rn(d4, f[4])); a = __fadd_rn(a, __fmul_rn(d5, f[5])); a = __fadd_rn(a, __fmul_rn(d6, f[6]));
+        a = __fadd_rn(a, __fmul_rn(d7, f[7])); a = __fadd_rn(a, __fmul_rn(d8, f[8]));
+        return a;
+      };
+    unsigned idx = 0;
+    v[idx] = apply(h0, h1, h2, h3, v[idx], v[idx + 1], v[idx + 2], v[idx + 3], v[idx + 4]);
+    idx++;
+    v[idx] = apply(h1, h2, h3, v[idx - 1], v[idx], v[idx + 1], v[idx + 2], v[idx + 3], v[idx + 4]);
+    idx++;
+    v[idx] = apply(h2, h3, v[idx - 2], v[idx - 1], v[idx], v[idx + 1], v[idx + 2], v[idx + 3], v[idx + 4]);
+    idx++;
+    v[idx] = apply(h3, v[idx - 3], v[idx - 2], v[idx - 1], v[idx], v[idx + 1], v[idx + 2], v[idx + 3], v[idx + 4]);
+    for (idx = 4; idx != num_sequences - 4; idx++) {
+      v[idx] = apply(v[idx - 4], v[idx - 3], v[idx - 2], v[idx - 1], v[idx], v[idx + 1], v[idx + 2], v[idx + 3], v[idx + 4]);
+    }
+    idx++;   // the reference's extra increment: index num_sequences - 4 stays unfiltered
+    v[idx] = apply(v[idx - 4], v[idx - 3], v[idx - 2], v[idx - 1], v[idx], v[idx + 1], v[idx + 2], v[idx + 3], v[idx + 3]);
+    idx++;
+    v[idx] = apply(v[idx - 4], v[idx - 3], v[idx - 2], v[idx - 1], v[idx], v[idx + 1], v[idx + 2], v[idx + 2], v[idx + 2]);
+    idx++;
+    v[idx] = apply(v[idx - 4], v[idx - 3], v[idx - 2], v[idx - 1], v[idx], v[idx + 1], v[idx + 1], v[idx + 1], v[idx + 1]);
+    idx++;
+    v[idx] = apply(v[idx - 4], v[idx - 3], v[idx - 2], v[idx - 1], v[idx], v[idx], v[idx], v[idx], v[idx]);
+    // control history: drop the oldest, append the command of this cycle
+    const int offset = shift ? 1 : 0;
+    hist[0 * 3 + plane] = h1; hist[1 * 3 + plane] = h2; hist[2 * 3 + plane] = h3; hist[3 * 3 + plane] = v[offset];
+  }
+  // getControlFromSequenceAsTwist: index 1 when the sequence is shifted afterwards, else 0; vy only if holonomic
+  const float cmd = (plane == 1 && !holonomic) ? 0.0f : v[shift ? 1 : 0];
+  if (shift && (plane != 1 || holonomic)) {
+    // shiftControlSequence: roll by -1, then last = second to last (the old last element)
+    const float last = v[T - 1];
+    for (int t = 0; t + 1 < T; ++t) {v[t] = v[t + 1];}
+    v[T - 1] = last;
+  }
+  return cmd;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Fused small-batch kernel: K2, the furthest-point / survivor reduction, K3 and the merge in ONE cooperative launch.
 // At the default 1000 x 56 the two-kernel cycle is bound by what surrounds the arithmetic: a launch boundary, a second
@@ -1996,7 +2056,8 @@ __device__ __forceinline__ void put_result(float * out, uint2 * host_res, int id
 template<unsigned F, bool kExact>
 __device__ __forceinline__ void tile_fused_body(
   const DevParams * __restrict__ Pg, const uint8_t * __restrict__ cm, const DevBuffers & bufs, const int B, const int T, const int n_cap,
-  const int iteration, uint2 * host_res, const uint4 * up_host, const int up_vecs, const int tile, const int G)
+  const int iteration, uint2 * host_res, const uint4 * up_host, const int up_vecs, const int tile, const int G,
+  const int tail_mode, float * __restrict__ hist)
 {
   // n_cap (path capacity, a multiple of 64) sizes the shared memory; the path size itself comes from the record, so a
   // captured graph survives the small changes of the pruned path from cycle to cycle
@@ -2181,6 +2242,9 @@ __device__ __forceinline__ void tile_fused_body(
 
   // ---- merge + clip: block t owns time steps t, t + G, ...  It needs m and s of every record and its own columns;
   //      the polls return as soon as the packets of this launch are there (no barrier)
+  // tail_mode != 0 (mppi_eval_control): the owners hand their time steps to tile 0 as packets instead of writing them out;
+  // tile 0 runs the evalControl tail on the whole sequence and delivers the result (below)
+  const bool tail = tail_mode != 0;
   if (tile == 0 && tid == 0) {
     k3_publish_flags(P, st, dec, bufs.out);
     if (host_res) {
@@ -2267,22 +2331,51 @@ __device__ __forceinline__ void tile_fused_body(
           wz = sgn * fabsf(vx) / rr;
         }
       }
-      bufs.cs[t] = vx; bufs.cs[T + t] = vy; bufs.cs[2 * T + t] = wz;
-      put_result(bufs.out, host_res, t, vx, tag);
-      put_result(bufs.out, host_res, T + t, vy, tag);
-      put_result(bufs.out, host_res, 2 * T + t, wz, tag);
+      if (tail) {
+        st_packet(bufs.pk_out + t, __float_as_uint(vx), tag);
+        st_packet(bufs.pk_out + T + t, __float_as_uint(vy), tag);
+        st_packet(bufs.pk_out + 2 * T + t, __float_as_uint(wz), tag);
+      } else {
+        bufs.cs[t] = vx; bufs.cs[T + t] = vy; bufs.cs[2 * T + t] = wz;
+        put_result(bufs.out, host_res, t, vx, tag);
+        put_result(bufs.out, host_res, T + t, vy, tag);
+        put_result(bufs.out, host_res, 2 * T + t, wz, tag);
+      }
     }
     __syncthreads();
   }
   MPPI_TRACE_AT(15);
+  if (tail && tile == 0) {
+    // ---- the tail of evalControl (Savitzky-Golay filter, command, shift) on the whole new sequence: exchange 3 inside the
+    //      GPU collects it from the owners; skipped when the optimisation failed (the reference only reaches this code
+    //      after fallback() returned false)
+    float * v = const_cast<float *>(fx.s_cvx);   // the tile planes are free now: [3][T]
+    for (int i = tid; i < 3 * T; i += nthr) {
+      unsigned bits;
+      if (!poll_packet(bufs.pk_out + i, tag, bits)) {st->comm_error = 1u;}
+      v[i] = __uint_as_float(bits);
+    }
+    __syncthreads();
+    const bool failed = dec.fail_at < P->n_critics;
+    if (tid < 3) {
+      float cmd = 0.0f;
+      if (!failed) {cmd = eval_tail_plane(v + tid * T, hist, tid, T, P->holonomic, tail_mode == 2 ? 1 : 0);}
+      put_result(bufs.out, host_res, 3 * T + 2 + tid, cmd, tag);
+    }
+    __syncthreads();
+    for (int i = tid; i < 3 * T; i += nthr) {
+      bufs.cs[i] = v[i];
+      put_result(bufs.out, host_res, i, v[i], tag);
+    }
+  }
 }
 
 template<unsigned F, bool kExact>
 __global__ void __launch_bounds__(256, MPPI_FUSED_MIN_BLOCKS) tile_fused_kernel(
   const DevParams * __restrict__ Pg, const uint8_t * __restrict__ cm, DevBuffers bufs, const int B, const int T, const int n_cap,
-  const int iteration, uint2 * host_res, const uint4 * up_host, const int up_vecs)
+  const int iteration, uint2 * host_res, const uint4 * up_host, const int up_vecs, const int tail_mode, float * hist)
 {
-  tile_fused_body<F, kExact>(Pg, cm, bufs, B, T, n_cap, iteration, host_res, up_host, up_vecs, blockIdx.x, gridDim.x);
+  tile_fused_body<F, kExact>(Pg, cm, bufs, B, T, n_cap, iteration, host_res, up_host, up_vecs, blockIdx.x, gridDim.x, tail_mode, hist);
 }
 
 // One launch for several robots (independent problems of the same shape: BASELINE configs[4]).  Block r * G + tile works
@@ -2329,7 +2422,7 @@ __global__ void __launch_bounds__(256, MPPI_FUSED_MIN_BLOCKS) tile_fused_batch_k
     __syncthreads();
   }
   tile_fused_body<F, kExact>(s_job.Pg, s_job.cm, s_job.bufs, s_job.B, s_job.T, s_job.n_cap, s_job.iteration, s_job.host_res,
-    s_job.up_host, s_job.up_vecs, static_cast<int>(ticket % G), G);
+    s_job.up_host, s_job.up_vecs, static_cast<int>(ticket % G), G, 0, nullptr);
 }
 
 // K3c (stream layout): softmax weights and weighted control sums over time-major noise [T][B]; a GEMV
@@ -2693,8 +2786,7 @@ __global__ void shift_control_sequence_kernel(float * __restrict__ cs, int T, in
 // false.  One thread per plane; the filter is inherently sequential (already-filtered neighbours are reused) and
 // reproduces the reference's quirks: index num_sequences - 4 is never filtered, vy is filtered for every model.
 // out layout: [0, 3T) control sequence after the tail, [3T] fail flag, [3T+1] furthest, [3T+2, 3T+5) command.
-__global__ void eval_tail_kernel(float * __restrict__ cs, float * __restrict__ hist, float * __restrict__ out, int T, int holonomic, int shift,
-  uint2 * host_res, const unsigned * epoch)
+__global__ void eval_tail_kernel(float * __restrict__ cs, float * __restrict__ hist, float * __restrict__ out, int T, int holonomic, int shift)
 {
   __shared__ float s[3][MPPI_MAX_TIME_STEPS];
   const int plane = threadIdx.x;   // 0 vx, 1 vy, 2 wz
@@ -2702,60 +2794,10 @@ __global__ void eval_tail_kernel(float * __restrict__ cs, float * __restrict__ h
   if (plane < 3 && !failed) {
     float * v = s[plane];
     for (int t = 0; t < T; ++t) {v[t] = cs[plane * T + t];}
-    const unsigned num_sequences = static_cast<unsigned>(T) - 1u;
-    float h0 = hist[0 * 3 + plane], h1 = hist[1 * 3 + plane], h2 = hist[2 * 3 + plane], h3 = hist[3 * 3 + plane];
-    if (num_sequences >= 20u) {
-      float f[9] = {-21.0f, 14.0f, 39.0f, 54.0f, 59.0f, 54.0f, 39.0f, 14.0f, -21.0f};
-#pragma unroll
-      for (int i = 0; i < 9; ++i) {f[i] = __fdiv_rn(f[i], 231.0f);}
-      auto apply = [&](float d0, float d1, float d2, float d3, float d4, float d5, float d6, float d7, float d8) -> float {
-          float a = __fadd_rn(0.0f, __fmul_rn(d0, f[0]));
-          a = __fadd_rn(a, __fmul_rn(d1, f[1])); a = __fadd_rn(a, __fmul_rn(d2, f[2])); a = __fadd_rn(a, __fmul_rn(d3, f[3]));
-          a = __fadd_rn(a, __fmul_rn(d4, f[4])); a = __fadd_rn(a, __fmul_rn(d5, f[5])); a = __fadd_rn(a, __fmul_rn(d6, f[6]));
-          a = __fadd_rn(a, __fmul_rn(d7, f[7])); a = __fadd_rn(a, __fmul_rn(d8, f[8]));
-          return a;
-        };
-      unsigned idx = 0;
-      v[idx] = apply(h0, h1, h2, h3, v[idx], v[idx + 1], v[idx + 2], v[idx + 3], v[idx + 4]);
-      idx++;
-      v[idx] = apply(h1, h2, h3, v[idx - 1], v[idx], v[idx + 1], v[idx + 2], v[idx + 3], v[idx + 4]);
-      idx++;
-      v[idx] = apply(h2, h3, v[idx - 2], v[idx - 1], v[idx], v[idx + 1], v[idx + 2], v[idx + 3], v[idx + 4]);
-      idx++;
-      v[idx] = apply(h3, v[idx - 3], v[idx - 2], v[idx - 1], v[idx], v[idx + 1], v[idx + 2], v[idx + 3], v[idx + 4]);
-      for (idx = 4; idx != num_sequences - 4; idx++) {
-        v[idx] = apply(v[idx - 4], v[idx - 3], v[idx - 2], v[idx - 1], v[idx], v[idx + 1], v[idx + 2], v[idx + 3], v[idx + 4]);
-      }
-      idx++;   // the reference's extra increment: index num_sequences - 4 stays unfiltered
-      v[idx] = apply(v[idx - 4], v[idx - 3], v[idx - 2], v[idx - 1], v[idx], v[idx + 1], v[idx + 2], v[idx + 3], v[idx + 3]);
-      idx++;
-      v[idx] = apply(v[idx - 4], v[idx - 3], v[idx - 2], v[idx - 1], v[idx], v[idx + 1], v[idx + 2], v[idx + 2], v[idx + 2]);
-      idx++;
-      v[idx] = apply(v[idx - 4], v[idx - 3], v[idx - 2], v[idx - 1], v[idx], v[idx + 1], v[idx + 1], v[idx + 1], v[idx + 1]);
-      idx++;
-      v[idx] = apply(v[idx - 4], v[idx - 3], v[idx - 2], v[idx - 1], v[idx], v[idx], v[idx], v[idx], v[idx]);
-      // control history: drop the oldest, append the command of this cycle
-      const int offset = shift ? 1 : 0;
-      hist[0 * 3 + plane] = h1; hist[1 * 3 + plane] = h2; hist[2 * 3 + plane] = h3; hist[3 * 3 + plane] = v[offset];
-    }
-    // getControlFromSequenceAsTwist: index 1 when the sequence is shifted afterwards, else 0; vy only if holonomic
-    out[3 * T + 2 + plane] = (plane == 1 && !holonomic) ? 0.0f : v[shift ? 1 : 0];
-    if (shift && (plane != 1 || holonomic)) {
-      // shiftControlSequence: roll by -1, then last = second to last (the old last element)
-      const float last = v[T - 1];
-      for (int t = 0; t + 1 < T; ++t) {v[t] = v[t + 1];}
-      v[T - 1] = last;
-    }
+    out[3 * T + 2 + plane] = eval_tail_plane(v, hist, plane, T, holonomic, shift);
     for (int t = 0; t < T; ++t) {cs[plane * T + t] = v[t]; out[plane * T + t] = v[t];}
   } else if (plane < 3) {
     out[3 * T + 2 + plane] = 0.0f;
-  }
-  if (host_res) {
-    // after the fused kernel: the whole result (sequence, flags, command) goes to pinned host memory as packets tagged
-    // with the launch the fused kernel just completed (tile_fused_kernel, put_result)
-    __syncwarp();
-    const unsigned tag = *epoch;
-    for (int i = threadIdx.x; i < 3 * T + 5; i += 32) {st_packet(host_res + i, __float_as_uint(out[i]), tag);}
   }
 }
 
