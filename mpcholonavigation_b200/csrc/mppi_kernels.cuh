@@ -311,15 +311,18 @@ __device__ __forceinline__ void rollout_tile_body(
   if (tid < kHotBytes / 16) {hot_v = __ldg(hot_src + tid);}
   // zero-copy upload: this tile's slice of [record | costmap], two vectors per thread in flight, the rest (large
   // costmaps) in a plain loop behind the staging
+  // (the copy is the business of the warps that have no scan to do: requested now, stored and fenced while warp 0 walks
+  //  the yaw scan, so that neither the PCIe latency nor the fence sits on the path of a barrier)
   uint4 up_v[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
   int up_begin = 0, up_end = 0;
+  const int up_tid = S > 1 ? tid - kTile : tid, up_n = S > 1 ? nthreads - kTile : nthreads;   // warp 0 sits out when it can
   if (kFused) {
-    if (zero_copy) {
+    if (zero_copy && up_tid >= 0) {
       const int per = (fx->up_vecs + ntiles - 1) / ntiles;
       up_begin = min(fx->up_vecs, tile * per);
       up_end = min(fx->up_vecs, up_begin + per);
-      if (up_begin + tid < up_end) {up_v[0] = __ldg(fx->up_host + up_begin + tid);}
-      if (up_begin + nthreads + tid < up_end) {up_v[1] = __ldg(fx->up_host + up_begin + nthreads + tid);}
+      if (up_begin + up_tid < up_end) {up_v[0] = __ldg(fx->up_host + up_begin + up_tid);}
+      if (up_begin + up_n + up_tid < up_end) {up_v[1] = __ldg(fx->up_host + up_begin + up_n + up_tid);}
     }
   }
   float cs_v[2] = {0.0f, 0.0f};
@@ -371,17 +374,6 @@ __device__ __forceinline__ void rollout_tile_body(
     }
   }
   MPPI_TRACE_AT(1);
-  if (kFused) {
-    if (zero_copy) {
-      uint4 * dst = reinterpret_cast<uint4 *>(const_cast<DevParams *>(P));
-      if (up_begin + tid < up_end) {dst[up_begin + tid] = up_v[0];}
-      if (up_begin + nthreads + tid < up_end) {dst[up_begin + nthreads + tid] = up_v[1];}
-      for (int i = up_begin + 2 * nthreads + tid; i < up_end; i += nthreads) {dst[i] = __ldg(fx->up_host + i);}
-      // (the fence that makes the slice visible device-wide, and the tile's flag behind it, wait until the yaw scan is
-      //  over: nothing reads the device copies before the position critics, and a fence here would sit on the path of
-      //  the first barrier)
-    }
-  }
   if (tid < kHotBytes / 16) {reinterpret_cast<float4 *>(s_hot)[tid] = hot_v;}
   for (int i = tid + nthreads; i < kHotBytes / 16; i += nthreads) {reinterpret_cast<float4 *>(s_hot)[i] = __ldg(hot_src + i);}
   if (tid < 3 * T) {s_cs[tid] = cs_v[0];}
@@ -466,7 +458,13 @@ __device__ __forceinline__ void rollout_tile_body(
     }
   }
   if (kFused) {
-    if (zero_copy) {__threadfence();}   // this thread's part of the upload slice is visible device-wide ...
+    if (zero_copy && up_tid >= 0) {
+      uint4 * dst = reinterpret_cast<uint4 *>(const_cast<DevParams *>(P));
+      if (up_begin + up_tid < up_end) {dst[up_begin + up_tid] = up_v[0];}
+      if (up_begin + up_n + up_tid < up_end) {dst[up_begin + up_n + up_tid] = up_v[1];}
+      for (int i = up_begin + 2 * up_n + up_tid; i < up_end; i += up_n) {dst[i] = __ldg(fx->up_host + i);}
+      __threadfence();   // this thread's part of the upload slice is visible device-wide ...
+    }
   }
   __syncthreads();
   if (kFused) {
