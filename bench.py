@@ -463,6 +463,12 @@ def main():
     # (the ctypes argument struct is marshalled once: the caller's buffers are plain host memory that does not change
     #  between cycles; every call still copies the record + costmap H2D and the result D2H inside the timed region)
     host_cycle = sc.cycle.packed()
+    cm_host = host_cycle.pack()[1][3]   # the caller's costmap buffer of the packed cycle
+    costmap_in_place = cm_host.nbytes > 96 * 1024
+    if costmap_in_place:
+        # large costmaps are handed over in place (the controller registers Costmap2D::getCharMap() once): pinned caller
+        # memory, copied H2D inside the timed region without the staging memcpy
+        e.register_costmap_memory(cm_host)
     e.set_timing(False)   # the controller does not read device_ms: no event records / read-back on the production path
     for _ in range(args.warmup):
         e.optimize(host_cycle)
@@ -530,6 +536,7 @@ def main():
             "config": {"workload": sc.name, "batch_size": B_total, "time_steps": T, "iteration_count": iters,
                        "critics": [c[0] for c in sc.critics], "costmap": list(sc.cycle.costmap.shape), "path_points": N,
                        "noise": noise_kind, "per_rank_batch": B_local,
+                       "costmap_memory": "registered as pinned, uploaded in place" if costmap_in_place else "staged (memcpy into pinned staging)",
                        "parallelism": (f"sharded over ranks, 2 exchanges ({'in-kernel over NVLink peer memory' if args.exchange == 'peer' else 'NCCL all-reduce + all-gather'})" if sharded and world > 1 else
                                        ("replicas: the same problem on every rank, own noise draw, no exchange" if world > 1 else "single GPU")),
                        "l2": "cold: 256 MiB written between timed steps" if flush is not None else "warm (no flush)"},

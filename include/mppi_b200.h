@@ -276,6 +276,13 @@ mppi_status mppi_score_trajectories(mppi_handle * h, const mppi_cycle_in * in,
                                     const float * x, const float * y, const float * yaw,
                                     float * costs_inout, uint32_t * furthest_inout, int32_t * fail_flag_out);
 
+/* Zero-copy costmap hand-off (ref: the reference reads Costmap2D::getCharMap() in place under the costmap mutex,
+ * controller.cpp:99-100).  Register the memory the caller's costmaps live in (cudaHostRegister) once; from then on a
+ * costmap inside such a range is copied to the device straight from the caller's buffer during the call, without the
+ * staging memcpy.  Costmaps small enough for the fused kernel's own upload (<= 96 KB) keep going through staging. */
+mppi_status mppi_register_costmap_memory(mppi_handle * h, const void * base, uint64_t bytes);
+mppi_status mppi_unregister_costmap_memory(mppi_handle * h, const void * base);
+
 /* ---- measurement hooks (bench.py: roofline of the dominant kernel, launch count) ---- */
 /* when enabled, CUDA events bracket each kernel of optimize() on the handle's stream (adds ~1 us per event) */
 mppi_status mppi_set_profiling(mppi_handle * h, int32_t enable);

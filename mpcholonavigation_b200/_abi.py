@@ -201,6 +201,8 @@ PRODUCT_ONLY = {
     "get_visualization": (C.c_int, [H, f32p, f32p]),
     "set_profiling": (C.c_int, [H, C.c_int32]),
     "set_timing": (C.c_int, [H, C.c_int32]),
+    "register_costmap_memory": (C.c_int, [H, C.c_void_p, C.c_uint64]),
+    "unregister_costmap_memory": (C.c_int, [H, C.c_void_p]),
     "get_profile": (C.c_int, [H, f32p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "comm_get_unique_id": (C.c_int, [u8p]),
     "comm_init": (C.c_int, [H, u8p, C.c_int32, C.c_int32]),

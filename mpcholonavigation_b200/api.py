@@ -297,6 +297,15 @@ class Engine:
     def set_profiling(self, enable=True):
         self._check(self.f["set_profiling"](self.h, int(bool(enable))))
 
+    def register_costmap_memory(self, array):
+        """pin the memory of a (C-contiguous uint8) costmap array: cycles whose costmap is this array are uploaded
+        straight from it (no staging memcpy).  Keep the array alive until unregister / close."""
+        assert array.dtype == np.uint8 and array.flags["C_CONTIGUOUS"]
+        self._check(self.f["register_costmap_memory"](self.h, array.ctypes.data, array.nbytes))
+
+    def unregister_costmap_memory(self, array):
+        self._check(self.f["unregister_costmap_memory"](self.h, array.ctypes.data))
+
     def set_timing(self, enable=True):
         """device_ms of every cycle (two event records + a read-back per call); off: device_ms reads 0"""
         self._check(self.f["set_timing"](self.h, int(bool(enable))))

@@ -143,6 +143,10 @@ struct mppi_handle
   bool params_in_arena{false};            // member: h_params / d_params point into the leader's arena
   uint32_t batch_tag{0};                  // leader, mode 2: counter behind the tag of the group's result packets
   uint32_t result_tag{0};                 // tag the cycle in flight delivers its result packets with
+  // caller memory registered as pinned (mppi_register_costmap_memory): a costmap inside such a range is copied to the
+  // device straight from the caller's buffer, without the staging memcpy
+  std::vector<std::pair<const char *, size_t>> pinned_ranges;
+  const uint8_t * costmap_direct{nullptr};   // this cycle's costmap source when it is copied directly
   uint64_t host_ns[8]{0, 0, 0, 0, 0, 0, 0, 0};   // host-side time of the steady-state call by phase (mppi_debug_get_host_ns)
   bool zero_copy_enabled{true};   // MPPI_ZERO_COPY=0 disables
   bool coop_launch{true};
@@ -662,6 +666,9 @@ void drop_graphs(mppi_handle * h)
   }
 }
 
+constexpr int kFusedSmemMax = 226 * 1024;
+constexpr size_t kZeroCopyMaxBytes = 96 * 1024;   // larger uploads (big costmaps) go through the copy engine
+
 // validate + stage the costmap into pinned memory (the caller's buffer is only valid during the call: it holds
 // the costmap mutex, controller.cpp:99-100); the async H2D copy itself is issued by enqueue_uploads
 mppi_status stage_costmap(mppi_handle * h, const mppi_costmap & cm)
@@ -690,8 +697,19 @@ mppi_status stage_costmap(mppi_handle * h, const mppi_costmap & cm)
   const size_t off = (h->params_copy_bytes + 255) & ~static_cast<size_t>(255);
   h->d_costmap = reinterpret_cast<uint8_t *>(h->d_params + off);
   h->h_costmap = reinterpret_cast<uint8_t *>(h->h_params + off);
-  std::memcpy(h->h_costmap, cm.cells, bytes);
   h->costmap_bytes = bytes;
+  // A costmap that lives in memory the caller registered as pinned is copied to the device from where it is (the
+  // reference reads Costmap2D::getCharMap() in place, controller.cpp:99-100) - unless the upload is small enough for the
+  // fused kernel to pull it out of the staging buffer itself, where the staging memcpy is the cheaper way.
+  h->costmap_direct = nullptr;
+  const bool small = !h->stream_layout && h->fused_enabled && h->zero_copy_enabled && h->nranks == 1 && off + bytes <= kZeroCopyMaxBytes;
+  if (!small && !h->params_in_arena) {
+    const char * c = reinterpret_cast<const char *>(cm.cells);
+    for (const auto & r : h->pinned_ranges) {
+      if (c >= r.first && c + bytes <= r.first + r.second) {h->costmap_direct = cm.cells; break;}
+    }
+  }
+  if (!h->costmap_direct) {std::memcpy(h->h_costmap, cm.cells, bytes);}
   return MPPI_OK;
 }
 
@@ -703,6 +721,13 @@ size_t upload_bytes(const mppi_handle * h)
 
 mppi_status enqueue_uploads(mppi_handle * h)
 {
+  if (h->costmap_direct) {
+    // record from the staging buffer, costmap straight from the caller's registered memory (both complete before the
+    // call returns: the result is ordered behind them on the stream)
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_params, h->h_params, h->params_copy_bytes, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_costmap, h->costmap_direct, h->costmap_bytes, cudaMemcpyHostToDevice, h->stream));
+    return MPPI_OK;
+  }
   CUDA_TRY(h, cudaMemcpyAsync(h->d_params, h->h_params, upload_bytes(h), cudaMemcpyHostToDevice, h->stream));
   return MPPI_OK;
 }
@@ -758,8 +783,6 @@ void launch_stream_instance(mppi_handle * h, int mode)
 
 mppi_status launch_regenerate(mppi_handle * h);
 
-constexpr int kFusedSmemMax = 226 * 1024;
-constexpr size_t kZeroCopyMaxBytes = 96 * 1024;   // larger uploads (big costmaps) go through the copy engine
 
 template<unsigned F, bool kExact>
 cudaError_t fused_occupancy(int threads, size_t smem, int * blocks_per_sm)
@@ -1663,6 +1686,7 @@ void mppi_destroy(mppi_handle * h)
   cudaSetDevice(h->device);
   if (h->stream) {cudaStreamSynchronize(h->stream);}
   if (h->batch_leader) {batch_unbind_group(h->batch_leader);}   // a group does not survive the loss of a member
+  for (const auto & r : h->pinned_ranges) {cudaHostUnregister(const_cast<char *>(r.first));}
   drop_graphs(h);
   if (h->comm && g_nccl.CommDestroy) {g_nccl.CommDestroy(h->comm);}
   if (h->peer_mode) {
@@ -2362,6 +2386,34 @@ mppi_status mppi_debug_get_host_ns(mppi_handle * h, uint64_t out8[8], int32_t re
   if (!h || !out8) {return MPPI_E_CONFIG;}
   for (int i = 0; i < 8; ++i) {out8[i] = h->host_ns[i]; if (reset) {h->host_ns[i] = 0;}}
   return MPPI_OK;
+}
+
+// Zero-copy costmap hand-off: the caller registers the memory its costmaps live in (Costmap2D::getCharMap()
+// of the controller's costmap, once, after configure) as pinned; from then on a costmap inside that range is copied to
+// the device straight from the caller's buffer while the call runs - no staging memcpy (160 KB at 400 x 400).
+mppi_status mppi_register_costmap_memory(mppi_handle * h, const void * base, uint64_t bytes)
+{
+  if (!h || !base || bytes == 0) {return MPPI_E_CONFIG;}
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, cudaHostRegister(const_cast<void *>(base), static_cast<size_t>(bytes), cudaHostRegisterPortable));
+  h->pinned_ranges.emplace_back(reinterpret_cast<const char *>(base), static_cast<size_t>(bytes));
+  return MPPI_OK;
+}
+
+mppi_status mppi_unregister_costmap_memory(mppi_handle * h, const void * base)
+{
+  if (!h || !base) {return MPPI_E_CONFIG;}
+  for (size_t i = 0; i < h->pinned_ranges.size(); ++i) {
+    if (h->pinned_ranges[i].first == reinterpret_cast<const char *>(base)) {
+      CUDA_TRY(h, cudaSetDevice(h->device));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      CUDA_TRY(h, cudaHostUnregister(const_cast<void *>(base)));
+      h->pinned_ranges.erase(h->pinned_ranges.begin() + static_cast<long>(i));
+      h->costmap_direct = nullptr;
+      return MPPI_OK;
+    }
+  }
+  return fail(h, MPPI_E_STATE, "mppi_unregister_costmap_memory: not a registered base address");
 }
 
 mppi_status mppi_set_timing(mppi_handle * h, int32_t enable)

@@ -201,3 +201,29 @@ def test_bound_group_against_the_single_calls(product_fns, oracle_fns, monkeypat
     np.testing.assert_allclose(r_after.vx, r_ref5.vx, rtol=RTOL, atol=ATOL)
     for e in single + group[1:] + [orc]:
         e.close()
+
+
+@pytest.mark.parametrize("batch", [1000, 16384])
+def test_registered_costmap_memory_is_uploaded_in_place(product_fns, batch):
+    """mppi_register_costmap_memory (SURVEY 8f-4, Costmap2D::getCharMap() handed over without a staging memcpy): a
+    400 x 400 costmap (160 KB, above the fused kernel's own upload bound) inside registered memory gives the same bits
+    as the staged copy, in the tile layout (fused kernel behind a copy) and in the stream layout; changing the map in
+    place is seen by the next cycle; unregistering falls back to staging."""
+    sc = scenarios.config3(batch=batch)
+    noise = sc.noise()
+    a, b = _engine(product_fns, sc, noise), _engine(product_fns, sc, noise)
+    cm = np.ascontiguousarray(sc.cycle.costmap)
+    cyc = dataclasses.replace(sc.cycle, costmap=cm)
+    b.register_costmap_memory(cm)
+    for cycle in range(4):
+        if cycle == 2:
+            cm[180:220, 230:260] = 254          # the world changed: same buffer, new content
+        ra, rb = a.optimize(cyc), b.optimize(cyc)
+        for name in ("vx", "vy", "wz"):
+            assert np.array_equal(getattr(ra, name), getattr(rb, name)), f"cycle {cycle} {name}"
+        assert np.array_equal(a.get_costs(), b.get_costs())
+        assert ra.fail_flag == rb.fail_flag
+    b.unregister_costmap_memory(cm)
+    ra, rb = a.optimize(cyc), b.optimize(cyc)
+    assert np.array_equal(ra.vx, rb.vx) and np.array_equal(ra.wz, rb.wz)
+    a.close(); b.close()
