@@ -227,3 +227,40 @@ def test_registered_costmap_memory_is_uploaded_in_place(product_fns, batch):
     ra, rb = a.optimize(cyc), b.optimize(cyc)
     assert np.array_equal(ra.vx, rb.vx) and np.array_equal(ra.wz, rb.wz)
     a.close(); b.close()
+
+
+def test_mixed_call_sequence_keeps_the_packet_tags_in_step(product_fns, oracle_fns):
+    """A long random mix of the entry points on ONE handle (optimize, evalControl with / without shift, resident cycles,
+    speed limits, resets, explicit shifts, moving robot): every call delivers its result through the packet path, so a
+    tag / epoch that got out of step would show up as a time-out or as a stale sequence.  Oracle after every call."""
+    sc = scenarios.config1(batch=500)
+    noise = sc.noise()
+    g, o = _engine(product_fns, sc, noise), _engine(oracle_fns, sc, noise)
+    rng = np.random.default_rng(7)
+    pose0 = sc.cycle.pose
+    for step in range(80):
+        op = rng.integers(0, 8)
+        dx = float(rng.uniform(-0.05, 0.25))
+        cyc = dataclasses.replace(sc.cycle, pose=(pose0[0] + dx, pose0[1] + float(rng.uniform(-0.03, 0.03)), float(rng.uniform(-0.3, 0.3))),
+                                  speed=(float(rng.uniform(0, 0.3)), 0.0, float(rng.uniform(-0.2, 0.2))))
+        if op <= 1:
+            rg, ro = g.optimize(cyc), o.optimize(cyc)
+        elif op <= 4:
+            shift = bool(op % 2)
+            (cg, rg), (co, ro) = g.eval_control(cyc, shift), o.eval_control(cyc, shift)
+            np.testing.assert_allclose(cg, co, rtol=RTOL, atol=ATOL, err_msg=f"step {step}: command")
+        elif op == 5:
+            g.upload_cycle(cyc)
+            rg, ro = g.optimize_resident(), o.optimize(cyc)
+        elif op == 6:
+            lim = float(rng.uniform(30, 100))
+            g.set_speed_limit(lim, True); o.set_speed_limit(lim, True)
+            rg, ro = g.optimize(cyc), o.optimize(cyc)
+        else:
+            g.reset(); o.reset()
+            g.set_noise(*noise); o.set_noise(*noise)   # reset redraws the noise: put the shared set back
+            rg, ro = g.optimize(cyc), o.optimize(cyc)
+        _close(rg, ro, label=f"step {step} op {op}")
+        g.set_control_sequence(ro.vx, ro.vy, ro.wz)
+        g.set_control_history(o.get_control_history())
+    g.close(); o.close()
