@@ -537,10 +537,30 @@ mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, un
       if (!reversing_allowed) {forward_preference = true;}
       p.angle_reversing = reversing_allowed; p.angle_forward_pref = forward_preference;
       if (p.angle.on) {
-        // path_angle_critic.cpp:79-83 for every index the furthest point could select
+        // path_angle_critic.cpp:79-83 for every index the furthest point could select.  The reference's test is
+        // posePointAngle(...) < max_angle (atan2f + fmod per point: most of this function's time at 40 points).  With
+        // forward_preference the angle A in [0, pi] is the one between the heading and the direction to the point, so
+        // "A < max" is "cos A > cos max": decided from a dot product wherever that is further than 1e-5 from the
+        // threshold (atan2f, the float roundings of the reference and the rounding of A to float move cos A by < 1e-6);
+        // the reference's own arithmetic decides the rest, so the gate is the reference's gate bit for bit.
+        const float thr = d->max_angle_to_furthest;
+        const bool fast = forward_preference && thr > 1.0e-3f && thr < 3.1f;
+        const float pose_xf = static_cast<float>(rx), pose_yf = static_cast<float>(ry), pose_yawf = static_cast<float>(in->pose_yaw);
+        const double ch = std::cos(static_cast<double>(pose_yawf)), sh = std::sin(static_cast<double>(pose_yawf));
+        const double ct = std::cos(static_cast<double>(thr));
         for (int j = 0; j < N; ++j) {
           const float gxj = in->path_x[j], gyj = in->path_y[j];
-          const bool open = !(pose_point_angle(rx, ry, in->pose_yaw, gxj, gyj, forward_preference) < d->max_angle_to_furthest);
+          int decided = -1;
+          if (fast) {
+            const double dxj = static_cast<double>(gxj - pose_xf), dyj = static_cast<double>(gyj - pose_yf);   // float differences, as atan2f gets them
+            const double dd = dxj * dxj + dyj * dyj;
+            if (dd > 1.0e-12) {
+              const double c = (dxj * ch + dyj * sh) / std::sqrt(dd);
+              if (c < ct - 1.0e-5) {decided = 1;} else if (c > ct + 1.0e-5) {decided = 0;}
+            }
+          }
+          const bool open = decided >= 0 ? decided == 1 :
+            !(pose_point_angle(rx, ry, in->pose_yaw, gxj, gyj, forward_preference) < thr);
           gate[j] = open ? 1 : 0;
           any_gate_open = any_gate_open || open;
         }
