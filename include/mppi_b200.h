@@ -164,7 +164,8 @@ typedef struct mppi_cycle_out {
   float * control_wz;
   int32_t fail_flag;         /* CriticData::fail_flag after the last iteration */
   uint32_t furthest_reached_path_point;  /* CriticData::furthest_reached_path_point, UINT32_MAX if unset */
-  float device_ms;           /* CUDA-event time of the kernels + copies of this call */
+  float device_ms;           /* CUDA-event time of the kernels of this call (and of the copies that are part of the
+                                captured cycle); 0 when mppi_set_timing(h, 0) */
 } mppi_cycle_out;
 
 typedef struct mppi_handle mppi_handle;
@@ -291,7 +292,8 @@ mppi_status mppi_set_profiling(mppi_handle * h, int32_t enable);
  * Default: on. */
 mppi_status mppi_set_timing(mppi_handle * h, int32_t enable);
 /* last optimize(), summed over iteration_count: ms_out[0] K2 rollout_score, [1] K3 path_softmax_update,
- * [2] exchanges + K4 merge (sharded only), [3] whole device span incl. copies.  kernel_launches_total counts every
+ * [2] exchanges + K4 merge (sharded only), [3] whole device span.  When the fused small-batch kernel ran (one launch
+ * for rollout, critics, update and merge) all of it is reported in [0] and [1] = [2] = 0.  kernel_launches_total counts every
  * kernel this handle has launched since create; h2d/d2h are the bytes copied by the last mppi_optimize(). */
 mppi_status mppi_get_profile(mppi_handle * h, float ms_out[4], uint64_t * kernel_launches_total,
                              uint64_t * h2d_bytes, uint64_t * d2h_bytes);
