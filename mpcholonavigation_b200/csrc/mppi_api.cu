@@ -150,6 +150,7 @@ struct mppi_handle
   uint64_t host_ns[8]{0, 0, 0, 0, 0, 0, 0, 0};   // host-side time of the steady-state call by phase (mppi_debug_get_host_ns)
   bool zero_copy_enabled{true};   // MPPI_ZERO_COPY=0 disables
   bool coop_launch{true};
+  bool packets_enabled{true};     // MPPI_STREAM_PACKETS=0: the stream layout copies its result back and synchronises
   bool fused_enabled{true};    // small batches: one cooperative launch per iteration (tile_fused_kernel); MPPI_FUSED=0 disables
   int fused_key_N{-1};         // path size the cached decision below was taken for (the shared-memory size depends on it)
   bool fused_fits{false};      // the whole grid is co-resident (a cooperative launch needs that)
@@ -810,6 +811,13 @@ cudaError_t fused_occupancy(int threads, size_t smem, int * blocks_per_sm)
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, tile_fused_kernel<F, kExact>, threads, smem);
 }
 
+// Stream layout, one rank, no evalControl tail: the merge kernel writes the result into pinned host memory as packets
+// tagged with the epoch the path-cost kernel advanced (no D2H copy node, no stream synchronisation).
+bool stream_packets(const mppi_handle * h)
+{
+  return h->stream_layout && h->nranks == 1 && h->tail_mode == 0 && h->d_fepoch != nullptr && h->packets_enabled;
+}
+
 // path capacity of the fused kernel's shared memory: rounded up to 64 points like the record copy (build_params), so that
 // the captured graph survives small changes of the pruned path
 int fused_path_capacity(const mppi_handle * h)
@@ -927,12 +935,14 @@ mppi_status launch_update(mppi_handle * h, int mode, int iteration)
   if (mode == 0 && h->stream_layout) {
     // stream layout: totals + global minimum here, weights and weighted sums in weighted_sums_tm_kernel
     const int grid = std::min((h->B + kUpdThreads - 1) / kUpdThreads, 148 * 8);
+    // the iteration that completes the result advances the packet epoch when the result leaves as packets
+    const int bump = (stream_packets(h) && iteration + 1 == h->cfg.iteration_count) ? 1 : 0;
     if (h->B >= 131072) {
       path_costs_tm_kernel<8><<<grid, kUpdThreads, k3_common_smem_bytes(), h->stream>>>(
-        reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, mode), iteration);
+        reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, mode), iteration, bump);
     } else {
       path_costs_tm_kernel<5><<<grid, kUpdThreads, k3_common_smem_bytes(), h->stream>>>(
-        reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, mode), iteration);
+        reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, mode), iteration, bump);
     }
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
@@ -1002,7 +1012,8 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
       if (h->stream_layout || many) {
         // too many partial records for a serial merge in K3's last block (or the stream layout): merge in parallel
         merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
-          dp, h->d_partials, h->stream_layout ? chunks : h->upd_blocks, stride, make_bufs(h, 0), h->nranks > 1 ? 0 : 1, h->d_rank_partial);
+          dp, h->d_partials, h->stream_layout ? chunks : h->upd_blocks, stride, make_bufs(h, 0), h->nranks > 1 ? 0 : 1, h->d_rank_partial,
+          (stream_packets(h) && it + 1 == h->cfg.iteration_count) ? h->h_res : nullptr);
         CUDA_TRY(h, cudaGetLastError());
         h->launches++;
       }
@@ -1010,7 +1021,7 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
       if (h->nranks > 1) {
         // exchange 2: per-rank (min, sum, weighted control sums); merged redundantly on every rank
         NCCL_TRY(h, g_nccl.AllGather(h->d_rank_partial, h->d_gathered, stride, ncclFloat32, h->comm, h->stream));
-        merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(dp, h->d_gathered, h->nranks, stride, make_bufs(h, 0), 1, nullptr);
+        merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(dp, h->d_gathered, h->nranks, stride, make_bufs(h, 0), 1, nullptr, nullptr);
         CUDA_TRY(h, cudaGetLastError());
         h->launches++;
       }
@@ -1027,7 +1038,7 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
     h->launches++;
   }
   if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[3], h->stream));}
-  if (!fused) {
+  if (!fused && !stream_packets(h)) {
     CUDA_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(float) * (3 * h->T + 6), cudaMemcpyDeviceToHost, h->stream));
   }
   if (h->cfg.regenerate_noises) {
@@ -1049,9 +1060,14 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
   const bool prof = h->profiling && h->cfg.iteration_count == 1;
   const bool graph_ok = h->use_graph && !prof && (h->nranks == 1 || h->peer_mode);   // NCCL calls are not captured
   h->ev_src = nullptr;
-  h->wait_packets = use_fused(h);
-  h->zero_copy_now = with_upload && h->wait_packets && h->zero_copy_enabled && upload_bytes(h) <= kZeroCopyMaxBytes;
-  if (h->wait_packets) {h->fepoch_host += static_cast<uint32_t>(h->cfg.iteration_count); h->result_tag = h->fepoch_host;}
+  const bool fused_now = use_fused(h);
+  h->wait_packets = fused_now || stream_packets(h);
+  h->zero_copy_now = with_upload && fused_now && h->zero_copy_enabled && upload_bytes(h) <= kZeroCopyMaxBytes;
+  if (h->wait_packets) {
+    // the fused kernel advances the epoch once per launch, the stream layout once per cycle
+    h->fepoch_host += fused_now ? static_cast<uint32_t>(h->cfg.iteration_count) : 1u;
+    h->result_tag = h->fepoch_host;
+  }
   h->d2h_bytes = h->wait_packets ? sizeof(uint2) * (3 * h->T + 2 + (h->tail_mode ? 3 : 0)) : sizeof(float) * (3 * h->T + 6);
   // zero-copy: every tile also reads the hot part of the record over PCIe
   h->h2d_bytes = with_upload ? upload_bytes(h) + (h->zero_copy_now ? static_cast<size_t>(h->upd_blocks) * kHotBytes : 0) : 0;
@@ -1072,7 +1088,7 @@ mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
     }
     const int slot = (with_upload ? 1 : 0) + 2 * h->tail_mode + (h->timing ? 6 : 0);
     const unsigned inst = pick_stream_instance(stream_feature_need(h->last));   // the K2 instance is baked into the graph
-    const int fkey = h->wait_packets ? h->fused_key_N : -1;   // wait_packets == use_fused(h), evaluated above
+    const int fkey = fused_now ? h->fused_key_N : -1;
     if (h->gexec[slot] && (h->gkey_params[slot] != h->params_copy_bytes || h->gkey_costmap[slot] != h->costmap_bytes ||
       h->gkey_inst[slot] != inst || h->gkey_fused[slot] != fkey))
     {
@@ -1215,7 +1231,7 @@ mppi_status finish_optimize(mppi_handle * h, mppi_cycle_out * out)
     // with sharding the span pev[1]..pev[2] also holds exchange 1; K3 alone is not separable there
     cudaEventElapsedTime(&h->prof_ms[1], h->pev[1], h->pev[2]);
     cudaEventElapsedTime(&h->prof_ms[2], h->pev[2], h->pev[3]);
-    if (h->wait_packets) {h->prof_ms[1] = 0.0f; h->prof_ms[2] = 0.0f;}   // fused kernel: everything is in [0]
+    if (use_fused(h)) {h->prof_ms[1] = 0.0f; h->prof_ms[2] = 0.0f;}   // fused kernel: everything is in [0]
   }
   h->host_ns[6] += now_ns() - t_b;
   h->host_ns[7] += 1;
@@ -1761,6 +1777,7 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   if (const char * e = std::getenv("MPPI_FUSED")) {h->fused_enabled = std::atoi(e) != 0;}
   if (const char * e = std::getenv("MPPI_ZERO_COPY")) {h->zero_copy_enabled = std::atoi(e) != 0;}
   if (const char * e = std::getenv("MPPI_COOP")) {h->coop_launch = std::atoi(e) != 0;}
+  if (const char * e = std::getenv("MPPI_STREAM_PACKETS")) {h->packets_enabled = std::atoi(e) != 0;}
   {
     // batches too small to fill the GPU with one thread per trajectory keep the latency-oriented tile kernel
     long long stream_min = 8192;    // measured cross-over on B200 (profiles/): below it the tile kernel wins
@@ -2522,11 +2539,11 @@ mppi_status mppi_optimize_sharded(mppi_handle ** hs, int32_t n, const mppi_cycle
         const int gy = weighted_sums_row_groups(T, chunks);
         weighted_sums_tm_kernel<<<dim3(chunks, gy), kWsThreads, 0, h->stream>>>(reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, 0));
         merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
-          reinterpret_cast<const DevParams *>(h->d_params), h->d_partials, chunks, stride, make_bufs(h, 0), 0, h->d_rank_partial);
+          reinterpret_cast<const DevParams *>(h->d_params), h->d_partials, chunks, stride, make_bufs(h, 0), 0, h->d_rank_partial, nullptr);
         h->launches += 2;
       } else if (h->upd_blocks > kLastBlockMergeMax) {
         merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
-          reinterpret_cast<const DevParams *>(h->d_params), h->d_partials, h->upd_blocks, stride, make_bufs(h, 0), 0, h->d_rank_partial);
+          reinterpret_cast<const DevParams *>(h->d_params), h->d_partials, h->upd_blocks, stride, make_bufs(h, 0), 0, h->d_rank_partial, nullptr);
         h->launches++;
       }
       if (cudaGetLastError() != cudaSuccess) {s = fail(h, MPPI_E_CUDA, "launch");  break;}
@@ -2540,7 +2557,7 @@ mppi_status mppi_optimize_sharded(mppi_handle ** hs, int32_t n, const mppi_cycle
       if (cudaMemcpyAsync(h->d_gathered, partial_host.data(), static_cast<size_t>(n) * stride * sizeof(float), cudaMemcpyHostToDevice,
           h->stream) != cudaSuccess) {s = fail(h, MPPI_E_CUDA, "exchange 2 H2D"); break;}
       merge_finalize_kernel<<<(T + kMergeT - 1) / kMergeT, kUpdThreads, 0, h->stream>>>(
-        reinterpret_cast<const DevParams *>(h->d_params), h->d_gathered, n, stride, make_bufs(h, 0), 1, nullptr);
+        reinterpret_cast<const DevParams *>(h->d_params), h->d_gathered, n, stride, make_bufs(h, 0), 1, nullptr, nullptr);
       h->launches++;
       if (cudaGetLastError() != cudaSuccess) {s = fail(h, MPPI_E_CUDA, "launch"); break;}
     }

@@ -1610,7 +1610,9 @@ __device__ __forceinline__ void k3_publish_flags(const DevParams * P, DevState *
 // weighted_sums_tm_kernel.
 // kMinBlocks trades registers for occupancy: 8 resident blocks (64 registers, a few spills) win once the batch keeps every
 // SM oversubscribed, 5 (96 registers) below that (measured on B200, profiles/).
-__device__ __forceinline__ void path_costs_tm_body(const DevParams * __restrict__ Pg, const DevBuffers & bufs, int iteration)
+// bump_epoch: the last block also advances the handle's packet epoch, so that the merge kernel behind this one can tag the
+// result packets it writes to pinned host memory (stream layout, unsharded: no copy node, no stream synchronisation)
+__device__ __forceinline__ void path_costs_tm_body(const DevParams * __restrict__ Pg, const DevBuffers & bufs, int iteration, int bump_epoch = 0)
 {
   extern __shared__ float smem[];
   __shared__ K3Decisions dec;
@@ -1650,13 +1652,15 @@ __device__ __forceinline__ void path_costs_tm_body(const DevParams * __restrict_
     for (int w = 1; w < kUpdThreads / 32; ++w) {gm = fminf(gm, s_red[w]);}
     bufs.st->global_min = gm;
     k3_publish_flags(P, bufs.st, dec, bufs.out);
+    if (bump_epoch) {*bufs.epoch += 1u;}
   }
 }
 
 template<int kMinBlocks>
-__global__ void __launch_bounds__(kUpdThreads, kMinBlocks) path_costs_tm_kernel(const DevParams * __restrict__ Pg, DevBuffers bufs, int iteration)
+__global__ void __launch_bounds__(kUpdThreads, kMinBlocks) path_costs_tm_kernel(
+  const DevParams * __restrict__ Pg, DevBuffers bufs, int iteration, int bump_epoch)
 {
-  path_costs_tm_body(Pg, bufs, iteration);
+  path_costs_tm_body(Pg, bufs, iteration, bump_epoch);
 }
 
 // K3, tile layout (small and medium batches; latency matters more than throughput here).  One block owns
@@ -2606,9 +2610,10 @@ __device__ __forceinline__ void merge_finalize_body(
 
 __global__ void __launch_bounds__(kUpdThreads) merge_finalize_kernel(
   const DevParams * __restrict__ Pg, const float * __restrict__ parts, int n, int stride, DevBuffers bufs, int finalize,
-  float * __restrict__ dst)
+  float * __restrict__ dst, uint2 * host_res)
 {
-  merge_finalize_body(Pg, parts, n, stride, bufs, finalize, dst, nullptr, 0u);
+  // host_res: the tag is the packet epoch the path-cost kernel in front of this one advanced
+  merge_finalize_body(Pg, parts, n, stride, bufs, finalize, dst, host_res, host_res ? ld_volatile_u32(bufs.epoch) : 0u);
 }
 
 // K4p: exchange 2 over peer memory, fused with the merges on both sides of it.  Every block merges its columns of the
