@@ -158,7 +158,7 @@ def run_reference(args, rank, world):
                                    f"oracle port (xtensor reference not buildable offline); host has {os.cpu_count()} cpus"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(sc, noise_kind, budget_s=12.0):
@@ -322,7 +322,7 @@ def run_robots(args, rank, world, local_rank, fns, torch, dist):
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(robots[0], "injected", 12.0)
-        print(json.dumps(line), flush=True)
+        emit(line)
     for e in engines:
         e.close()
     if world > 1:
@@ -330,25 +330,27 @@ def run_robots(args, rank, world, local_rank, fns, torch, dist):
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
 def _claim_stdout():
     """stdout carries the ONE JSON line: whatever native libraries print there (NCCL's version line at communicator
-    creation, ...) is sent to stderr instead.  Returns the stream the JSON line is written to."""
+    creation, ...) is sent to stderr instead; emit() writes the line to the real stdout."""
+    global _JSON_OUT
     sys.stdout.flush()
     keep = os.dup(1)
     os.dup2(2, 1)
-    return os.fdopen(keep, "w")
+    _JSON_OUT = os.fdopen(keep, "w")
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
-    global print
-    _json_out = _claim_stdout()
-    _builtin_print = print
-
-    def print(*a, **kw):   # noqa: A001  (the JSON line goes to the real stdout; everything else is explicit about its file)
-        kw.setdefault("file", _json_out)
-        _builtin_print(*a, **kw)
-        kw["file"].flush()
-
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
@@ -566,7 +568,7 @@ def main():
         if not args.no_cpu_baseline:
             budget = 12.0 if B_total * T <= 2_000_000 else 25.0
             line["cpu_baseline"] = cpu_baseline(pick_scenario(args.workload, 0, 1)[0], noise_kind, budget)
-        print(json.dumps(line), flush=True)
+        emit(line)
     e.close()
     if world > 1:
         dist.barrier()
