@@ -264,3 +264,30 @@ def test_mixed_call_sequence_keeps_the_packet_tags_in_step(product_fns, oracle_f
         g.set_control_sequence(ro.vx, ro.vy, ro.wz)
         g.set_control_history(o.get_control_history())
     g.close(); o.close()
+
+
+@pytest.mark.parametrize("batch,steps", [(1000, 56), (2000, 56), (96, 100)])
+def test_fused_kernel_is_deterministic(product_fns, batch, steps):
+    """The same cycle from the same warm start, 300 times (host buffers: zero-copy upload, packet exchanges between the
+    tiles, result packets): every repetition returns the bits of the first, controls and all trajectory costs.  A race
+    between tiles, or between a tile's warps in shared memory, would show up as a repetition that differs."""
+    sc = scenarios.config1(batch=batch, steps=steps)
+    e = _engine(product_fns, sc, sc.noise())
+    for _ in range(5):                       # a non-trivial warm start
+        e.optimize(sc.cycle)
+    start = e.get_control_sequence()
+    ref = None
+    for rep in range(300):
+        e.set_control_sequence(*start)
+        r = e.optimize(sc.cycle)
+        got = (r.vx.copy(), r.vy.copy(), r.wz.copy(), e.get_costs() if rep % 25 == 0 else None, r.fail_flag,
+               r.furthest_reached_path_point)
+        if ref is None:
+            ref = got
+            continue
+        for a, b in zip(got[:3], ref[:3]):
+            assert np.array_equal(a, b), f"repetition {rep} differs"
+        if got[3] is not None:
+            assert np.array_equal(got[3], ref[3]), f"repetition {rep}: costs differ"
+        assert got[4:] == ref[4:]
+    e.close()
