@@ -88,6 +88,10 @@ public:
     check(MPPI_ABI(create)(&settings_.base, &handle_), "create");   // throws on an invalid motion model (optimizer.cpp:421-424)
     check(MPPI_ABI(set_robot)(handle_, &robot), "set_robot");
     check(MPPI_ABI(set_critics)(handle_, critics.data(), static_cast<int32_t>(critics.size())), "set_critics");
+#ifndef MPPI_ABI_DECLARE_PREFIXED
+    // the controller never reads device_ms (the reference has no such output): no event records / read-back per cycle
+    check(mppi_set_timing(handle_, 0), "set_timing");
+#endif
     vx_.assign(settings_.base.time_steps, 0.0f); vy_ = vx_; wz_ = vx_;
   }
 
