@@ -563,7 +563,9 @@ mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, un
           const bool open = decided >= 0 ? decided == 1 :
             !(pose_point_angle(rx, ry, in->pose_yaw, gxj, gyj, forward_preference) < thr);
           gate[j] = open ? 1 : 0;
-          any_gate_open = any_gate_open || open;
+          // only indices the critic can select count (furthest + offset_from_furthest, clamped): the point under the robot
+          // (j = 0: atan2f(0, 0) = 0, i.e. the angle is the heading itself) must not force the trajectory spills
+          any_gate_open = any_gate_open || (open && j >= std::max(0, std::min(p.angle_offset, N - 1)));
         }
       }
     }
