@@ -11,6 +11,11 @@
 //                                  weighted control update, clip  (critic_manager.cpp:67-76, path_*_critic.cpp,
 //                                  optimizer.cpp:362-394,237-249)
 //  K4 merge_finalize_kernel        parallel merge of the softmax partials (large batches; cross-rank when sharded)
+//  KF tile_fused_kernel            small batches, one rank: K2's body, both grid-wide exchanges (as packets), the path critics,
+//                                  the update, the merge and the evalControl tail in ONE cooperative launch; zero-copy upload
+//                                  in, result packets out (the default 1000 x 56 path)
+//     tile_fused_batch_kernel      the same for several robots per launch (blocks draw tickets)
+//     *_batch_kernel (stream)      K2 / K3a / K3c / K4 of the stream layout with the robot as the last grid dimension
 //
 // Work shape of K2: one CTA owns a tile of 32 trajectories (lane == trajectory) and S warps split the
 // horizon into S contiguous segments.  The tile lives in shared memory time-major, [T][33] floats per
