@@ -108,9 +108,15 @@ public:
   {
     mppi_cycle_in in = prepare(robot_pose, robot_speed, plan, goal, goal_checker_xy_tolerance, costmap);
     float cmd[3];
-    do {
-      optimize(in, cmd);
-    } while (fallback(last_.fail_flag != 0));
+    optimize(in, cmd);
+    // The reference's `do {optimize();} while (fallback(critics_data_.fail_flag));` (optimizer.cpp:143-145) cannot recover:
+    // fail_flag is cleared in prepare() only (:198), which the loop does not repeat, so every retry's
+    // evalTrajectoriesScores breaks before its first critic (critic_manager.cpp:70-73), the flag stays set, and after
+    // retry_attempt_limit soft resets fallback() throws "Optimizer fail to compute path".  The retries' optimize()
+    // therefore only computes an update from all-zero costs that the next reset() wipes: the mirror keeps the resets and
+    // the throw (same observable behaviour, same state afterwards) and does not launch those cycles.
+    const bool fail = last_.fail_flag != 0;
+    while (fallback(fail)) {}
     return Twist{cmd[0], cmd[1], cmd[2]};
   }
 
@@ -137,7 +143,8 @@ public:
   }
 
   // ref: Optimizer::reset optimizer.cpp:116-132
-  void reset() {check(MPPI_ABI(reset)(handle_), "reset");}
+  void reset() {check(MPPI_ABI(reset)(handle_), "reset"); ++resets_;}
+  size_t resetCount() const {return resets_;}
 
   // ---- access for tests and for the shim -----------------------------------------------------------------------
   mppi_handle * handle() {return handle_;}
@@ -219,6 +226,7 @@ protected:
   OptimizerSettings settings_;
   mppi_handle * handle_{nullptr};
   bool shift_control_sequence_{false};
+  size_t resets_{0};
   mppi_cycle_out last_{};
   std::vector<float> vx_, vy_, wz_;
 };

@@ -100,6 +100,7 @@ struct mppi_handle
   float * d_partials{nullptr};
   float * d_rank_partial{nullptr};
   float * d_gathered{nullptr};
+  size_t gathered_capacity{0};   // records d_gathered holds (exchange 2: one (3T + 2)-float record per rank / shard)
   float * d_out{nullptr};
   DevState * d_st{nullptr};
   float * d_inj[6]{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // score / integrate scratch, lazy
@@ -679,6 +680,8 @@ DevBuffers make_bufs(mppi_handle * h, int mode)
   b.pk_rec = h->d_pk ? h->d_pk + 2 * h->upd_blocks : nullptr;
   b.pk_out = h->d_pk ? h->d_pk + static_cast<size_t>(h->upd_blocks) * (2 + 3 * h->T + 2) : nullptr;
   b.epoch = h->d_fepoch;
+  // sticky "a bounded poll gave up" word in pinned host memory, behind the result packets (raise_comm_error)
+  b.host_err = h->h_res ? reinterpret_cast<unsigned *>(h->h_res + 3 * static_cast<size_t>(h->T) + 9) : nullptr;
   return b;
 }
 
@@ -1057,7 +1060,33 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
 
 // One cycle on the handle's stream: [uploads], kernels, result copy; bracketed by ev0 / ev1.  The steady state
 // (single rank, no per-kernel profiling) replays a captured CUDA graph: one launch instead of five.
+mppi_status enqueue_optimize_impl(mppi_handle * h, bool with_upload);
+
+// The host mirrors the device's packet epoch (fepoch_host) and advances it when a cycle is enqueued.  If enqueueing fails
+// half-way, or a cycle ends with an error, the mirror is re-read from the device once the stream has drained: otherwise
+// every later cycle would wait for a tag that is never written.
+void resync_packet_epoch(mppi_handle * h)
+{
+  if (!h->d_fepoch) {return;}
+  cudaStreamSynchronize(h->stream);
+  uint32_t e = h->fepoch_host;
+  if (cudaMemcpy(&e, h->d_fepoch, sizeof(uint32_t), cudaMemcpyDeviceToHost) == cudaSuccess) {h->fepoch_host = e;}
+  cudaGetLastError();
+}
+
 mppi_status enqueue_optimize(mppi_handle * h, bool with_upload)
+{
+  const mppi_status s = enqueue_optimize_impl(h, with_upload);
+  if (s != MPPI_OK && h->wait_packets) {
+    const std::string keep = h->err;
+    resync_packet_epoch(h);
+    h->wait_packets = false;
+    h->err = keep;
+  }
+  return s;
+}
+
+mppi_status enqueue_optimize_impl(mppi_handle * h, bool with_upload)
 {
   const bool prof = h->profiling && h->cfg.iteration_count == 1;
   const bool graph_ok = h->use_graph && !prof && (h->nranks == 1 || h->peer_mode);   // NCCL calls are not captured
@@ -1190,6 +1219,15 @@ mppi_status finish_optimize(mppi_handle * h, mppi_cycle_out * out)
   if (h->wait_packets) {
     mppi_status ws = wait_result_packets(h);
     if (ws != MPPI_OK) {return ws;}
+    // a tile gave up waiting for another tile's packets (raise_comm_error): the result above is not to be trusted
+    volatile unsigned * host_err = reinterpret_cast<volatile unsigned *>(h->h_res + 3 * static_cast<size_t>(h->T) + 9);
+    if (*host_err != 0u) {
+      *host_err = 0u;
+      resync_packet_epoch(h);
+      cudaMemsetAsync(&h->d_st->comm_error, 0, sizeof(unsigned), h->stream);
+      return fail(h, h->nranks > 1 ? MPPI_E_NCCL : MPPI_E_CUDA,
+               "an in-kernel packet exchange timed out (a tile or rank never delivered): result discarded");
+    }
     if (h->timing) {CUDA_TRY(h, cudaEventSynchronize(h->cfg.regenerate_noises ? h->ev_result : (h->ev_src ? h->ev_src : h)->ev1));}
   } else if (h->cfg.regenerate_noises) {
     CUDA_TRY(h, cudaEventSynchronize(h->ev_result));
@@ -1237,6 +1275,18 @@ mppi_status finish_optimize(mppi_handle * h, mppi_cycle_out * out)
   }
   h->host_ns[6] += now_ns() - t_b;
   h->host_ns[7] += 1;
+  return MPPI_OK;
+}
+
+// room for `records` softmax records in d_gathered (grown outside the steady state: the shard count changes on reconfiguration)
+mppi_status ensure_gathered(mppi_handle * h, int records)
+{
+  if (h->d_gathered && h->gathered_capacity >= static_cast<size_t>(records)) {return MPPI_OK;}
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->d_gathered) {cudaFree(h->d_gathered); h->d_gathered = nullptr; h->gathered_capacity = 0;}
+  const size_t cap = static_cast<size_t>(std::max(records, 8));
+  CUDA_TRY(h, cudaMalloc(&h->d_gathered, cap * (3 * static_cast<size_t>(h->T) + 2) * sizeof(float)));
+  h->gathered_capacity = cap;
   return MPPI_OK;
 }
 
@@ -1740,7 +1790,7 @@ void mppi_destroy(mppi_handle * h)
   cudaFree(h->d_vis);
   cudaFree(h->d_tmp); cudaFree(h->d_params); cudaFree(h->d_cs); cudaFree(h->d_crit_rows);
   cudaFree(h->d_end_xy); cudaFree(h->d_cells); cudaFree(h->d_costs); cudaFree(h->d_partials); cudaFree(h->d_rank_partial);
-  cudaFree(h->d_gathered); cudaFree(h->d_out); cudaFree(h->d_st); cudaFree(h->d_hist); cudaFree(h->d_seq); cudaFree(h->d_epoch);
+  cudaFree(h->d_gathered); h->gathered_capacity = 0; cudaFree(h->d_out); cudaFree(h->d_st); cudaFree(h->d_hist); cudaFree(h->d_seq); cudaFree(h->d_epoch);
   if (h->ev_result) {cudaEventDestroy(h->ev_result);} cudaFree(h->d_mailbox);
   cudaFreeHost(h->h_params); cudaFreeHost(h->h_out); cudaFreeHost(h->h_res);
   cudaFree(h->d_pk); cudaFree(h->d_fepoch);
@@ -2486,7 +2536,7 @@ mppi_status mppi_get_profile(mppi_handle * h, float ms_out[4], uint64_t * kernel
 // and it lets the sharded code path run on a single GPU (two handles on one device) in the tests.
 mppi_status mppi_optimize_sharded(mppi_handle ** hs, int32_t n, const mppi_cycle_in * in, mppi_cycle_out * out)
 {
-  if (!hs || n < 1 || !in) {return MPPI_E_CONFIG;}
+  if (!hs || n < 1 || n > kMaxRanks || !in) {return MPPI_E_CONFIG;}
   for (int i = 0; i < n; ++i) {
     if (!hs[i]) {return MPPI_E_CONFIG;}
     if (hs[i]->T != hs[0]->T || hs[i]->cfg.iteration_count != hs[0]->cfg.iteration_count) {
@@ -2502,13 +2552,8 @@ mppi_status mppi_optimize_sharded(mppi_handle ** hs, int32_t n, const mppi_cycle
   auto on = [&](int i) {cudaSetDevice(hs[i]->device); return hs[i];};
   for (int i = 0; i < n && s == MPPI_OK; ++i) {
     mppi_handle * h = on(i);
-    h->nranks = n;   // K3 must not finalize on its own
-    if (!h->d_gathered) {
-      if (cudaMalloc(&h->d_gathered, static_cast<size_t>(std::max(n, 8)) * stride * sizeof(float)) != cudaSuccess) {
-        h->nranks = 1;
-        return fail(h, MPPI_E_CUDA, "cudaMalloc(d_gathered)");
-      }
-    }
+    h->nranks = n;   // K3 must not finalize on its own (restored to 1 on every exit path, below)
+    if ((s = ensure_gathered(h, n)) != MPPI_OK) {break;}
     if ((s = build_params(h, in, 0, kUnset, true)) != MPPI_OK) {break;}
     if ((s = stage_costmap(h, in->costmap)) != MPPI_OK) {break;}
     if ((s = enqueue_uploads(h)) != MPPI_OK) {break;}
@@ -2564,6 +2609,17 @@ mppi_status mppi_optimize_sharded(mppi_handle ** hs, int32_t n, const mppi_cycle
       if (cudaGetLastError() != cudaSuccess) {s = fail(h, MPPI_E_CUDA, "launch"); break;}
     }
   }
+  if (s != MPPI_OK) {
+    // nothing to deliver: drain what was enqueued and hand every shard back as a single-rank handle
+    for (int i = 0; i < n; ++i) {
+      mppi_handle * h = on(i);
+      cudaStreamSynchronize(h->stream);
+      h->nranks = 1;
+      h->wait_packets = false;
+    }
+    cudaGetLastError();
+    return s;
+  }
   for (int i = 0; i < n; ++i) {
     mppi_handle * h = on(i);
     if (s == MPPI_OK) {
@@ -2606,10 +2662,7 @@ mppi_status mppi_comm_init(mppi_handle * h, const uint8_t id[MPPI_NCCL_UNIQUE_ID
   std::memcpy(&uid, id, sizeof(uid));
   NCCL_TRY(h, g_nccl.CommInitRank(&h->comm, nranks, uid, rank));
   h->rank = rank; h->nranks = nranks;
-  if (!h->d_gathered) {
-    CUDA_TRY(h, cudaMalloc(&h->d_gathered, static_cast<size_t>(nranks) * (3 * h->T + 2) * sizeof(float)));
-  }
-  return MPPI_OK;
+  return ensure_gathered(h, nranks);
 }
 
 // ---- peer-memory exchange: no NCCL, the exchanges ride inside K3 and the merge kernel (mppi_device.cuh PeerComm) ----

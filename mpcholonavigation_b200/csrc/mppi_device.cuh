@@ -193,6 +193,17 @@ struct DevState
   unsigned comm_error;                  // a peer-memory exchange timed out (sticky until reset)
 };
 
+// Read-only data of a launch is loaded through the non-coherent path (ld.global.nc) -- EXCEPT in the fused kernels, whose
+// tiles write the device copy of [record | costmap] themselves (zero-copy upload) before other tiles read it in the same
+// launch: ld.global.nc is only defined for data that is read-only for the whole kernel, so there the loads are plain
+// (coherent) ones, ordered behind the upload flags by fences (rollout_tile_body).  kNc is a compile-time choice.
+template<bool kNc, typename V>
+__device__ __forceinline__ V ld_ro(const V * p)
+{
+  if (kNc) {return __ldg(p);}
+  return *p;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // nav2_costmap_2d::Costmap2D::worldToMap restated; all fp64, inputs are fp32 poses widened.
 // Returns the flat cell index my*size_x+mx or -1 (off-map).
@@ -258,7 +269,8 @@ __device__ __forceinline__ int world_to_cell_fast(float xf, float yf, const Cell
 }
 
 // FootprintCollisionChecker::lineCost over nav2_util::LineIterator (integer Bresenham, both ends included)
-__device__ __forceinline__ int line_cost(const uint8_t * __restrict__ cm, unsigned size_x, int x0, int y0, int x1, int y1)
+template<bool kNc>
+__device__ __forceinline__ int line_cost(const uint8_t * cm, unsigned size_x, int x0, int y0, int x1, int y1)
 {
   int deltax = abs(x1 - x0), deltay = abs(y1 - y0);
   int xinc1, xinc2, yinc1, yinc2;
@@ -273,7 +285,7 @@ __device__ __forceinline__ int line_cost(const uint8_t * __restrict__ cm, unsign
   int x = x0, y = y0;
   int cost = 0;
   for (int cur = 0; cur <= numpixels; ++cur) {
-    const int c = __ldg(cm + static_cast<unsigned>(y) * size_x + static_cast<unsigned>(x));
+    const int c = ld_ro<kNc>(cm + static_cast<unsigned>(y) * size_x + static_cast<unsigned>(x));
     if (c == LETHAL_OBSTACLE) {return c;}
     cost = max(cost, c);
     num += numadd;
@@ -284,17 +296,18 @@ __device__ __forceinline__ int line_cost(const uint8_t * __restrict__ cm, unsign
 }
 
 // FootprintCollisionChecker::footprintCostAtPose + footprintCost.  P is the record in GLOBAL memory (the polygon
-// is not part of the hot copy); the scalars come from the caller's registers.
+// is not part of the hot copy); the scalars come from the caller's registers.  kNc: see ld_ro.
+template<bool kNc>
 __device__ __noinline__ int footprint_cost_at_pose(
-  const DevParams * __restrict__ P, int n, double ox, double oy, double res, unsigned size_x, unsigned size_y,
-  const uint8_t * __restrict__ cm, float xf, float yf, float thf)
+  const DevParams * P, int n, double ox, double oy, double res, unsigned size_x, unsigned size_y,
+  const uint8_t * cm, float xf, float yf, float thf)
 {
   const double x = xf, y = yf, th = thf;
   double sin_th, cos_th;
   sincos(th, &sin_th, &cos_th);
   unsigned x0, y0, x1, y1;
   {
-    const double fx = __ldg(&P->fp_x[0]), fy = __ldg(&P->fp_y[0]);
+    const double fx = ld_ro<kNc>(&P->fp_x[0]), fy = ld_ro<kNc>(&P->fp_y[0]);
     const double wx = x + (__dmul_rn(fx, cos_th) - __dmul_rn(fy, sin_th));
     const double wy = y + (__dmul_rn(fx, sin_th) + __dmul_rn(fy, cos_th));
     if (world_to_cell(wx, wy, ox, oy, res, size_x, size_y, x0, y0) < 0) {return LETHAL_OBSTACLE;}
@@ -303,15 +316,15 @@ __device__ __noinline__ int footprint_cost_at_pose(
   x1 = x0; y1 = y0;
   int footprint_cost = 0;
   for (int i = 0; i + 1 < n; ++i) {
-    const double fx = __ldg(&P->fp_x[i + 1]), fy = __ldg(&P->fp_y[i + 1]);
+    const double fx = ld_ro<kNc>(&P->fp_x[i + 1]), fy = ld_ro<kNc>(&P->fp_y[i + 1]);
     const double wx = x + (__dmul_rn(fx, cos_th) - __dmul_rn(fy, sin_th));
     const double wy = y + (__dmul_rn(fx, sin_th) + __dmul_rn(fy, cos_th));
     if (world_to_cell(wx, wy, ox, oy, res, size_x, size_y, x1, y1) < 0) {return LETHAL_OBSTACLE;}
-    footprint_cost = max(line_cost(cm, size_x, x0, y0, x1, y1), footprint_cost);
+    footprint_cost = max(line_cost<kNc>(cm, size_x, x0, y0, x1, y1), footprint_cost);
     x0 = x1; y0 = y1;
     if (footprint_cost == LETHAL_OBSTACLE) {return footprint_cost;}
   }
-  return max(line_cost(cm, size_x, xstart, ystart, x1, y1), footprint_cost);
+  return max(line_cost<kNc>(cm, size_x, xstart, ystart, x1, y1), footprint_cost);
 }
 
 // CostCritic::inCollision / ObstaclesCritic::inCollision on a byte cost

@@ -64,7 +64,21 @@ struct DevBuffers
   uint2 * pk_rec;       // [G][3T + 2]    per tile: softmax record (m, s, W[3T])
   uint2 * pk_out;       // [3T]           evalControl tail: the new sequence on its way from the owner tiles to tile 0
   unsigned * epoch;     // completed fused launches of this handle; the tag of the running launch is *epoch + 1
+  unsigned * host_err;  // pinned host word (behind the result packets): a bounded poll gave up inside this handle's kernels
 };
+
+// A bounded poll timed out: sticky flag in device memory and, for the cycles whose result leaves as packets (no D2H of the
+// state), in pinned host memory too.  The system-scope fence orders the host word before every packet this block sends
+// afterwards, and the result packets are only sent once every tile's packets have arrived: the host reads the word after
+// the last result packet and cannot miss it.
+__device__ __forceinline__ void raise_comm_error(const DevBuffers & bufs)
+{
+  bufs.st->comm_error = 1u;
+  if (bufs.host_err) {
+    *reinterpret_cast<volatile unsigned *>(bufs.host_err) = 1u;
+    __threadfence_system();
+  }
+}
 
 // accumulator slots of the per-segment partials
 enum Acc
@@ -263,8 +277,11 @@ __global__ void advance_epoch_kernel(unsigned long long * d_epoch) {*d_epoch += 
 constexpr int kTileChunk = MPPI_TILE_CHUNK;   // steps whose independent work is issued together inside a segment
 template<unsigned F, bool kExact, int kMode, bool kFused>
 __device__ __forceinline__ void rollout_tile_body(
-  const DevParams * __restrict__ P, const uint8_t * __restrict__ cm, const DevBuffers & bufs, const int B, const int T, FusedCtx * fx)
+  const DevParams * P, const uint8_t * cm, const DevBuffers & bufs, const int B, const int T, FusedCtx * fx)
 {
+  // the fused kernels' tiles WRITE the device copy of [record | costmap] in this very launch (zero-copy upload): no
+  // non-coherent loads from either there (ld_ro); the two-kernel instances keep ld.global.nc
+  constexpr bool kNc = !kFused;
   constexpr int mode = kMode;   // 0 rollout from noise, 1 injected state (integrate), 2 injected state + trajectories
   static_assert(!kFused || kMode == 0, "the fused kernel only exists for the rollout-from-noise mode");
   // B, T and mode also live in the record, but as launch arguments they cost no memory round trip: the noise rows,
@@ -473,7 +490,9 @@ __device__ __forceinline__ void rollout_tile_body(
   }
   __syncthreads();
   if (kFused) {
-    if (zero_copy && tid == 0) {st_packet(bufs.pk_up + tile, 1u, fx->tag);}   // ... before the tile's flag goes out
+    // ... before the tile's flag goes out.  The flag's writer fences too: its fence is cumulative over what the barrier
+    // above made visible to it, which is what makes {slice stores, flag} a release in the PTX memory model
+    if (zero_copy && tid == 0) {__threadfence(); st_packet(bufs.pk_up + tile, 1u, fx->tag);}
   }
 
   MPPI_TRACE_AT(4);
@@ -581,8 +600,9 @@ __device__ __forceinline__ void rollout_tile_body(
       if (zero_copy && seg == min(2, S - 1)) {
         for (int i = lane; i < ntiles; i += 32) {
           unsigned v;
-          if (!poll_packet(bufs.pk_up + i, fx->tag, v)) {bufs.st->comm_error = 1u;}
+          if (!poll_packet(bufs.pk_up + i, fx->tag, v)) {raise_comm_error(bufs);}
         }
+        __threadfence();   // acquire side: the (coherent) loads of record tail and costmap behind the barrier below see the slices
       }
     }
   }
@@ -599,9 +619,9 @@ __device__ __forceinline__ void rollout_tile_body(
     const uint8_t * g_valid = reinterpret_cast<const uint8_t *>(tail + 4 * N);
     const uint16_t * g_follow = reinterpret_cast<const uint16_t *>(g_valid + 2 * n16);
     if (tid < N) {
-      pt_f[0] = __ldg(tail + 3 * N + tid); pt_f[1] = __ldg(tail + tid); pt_f[2] = __ldg(tail + N + tid);
-      pt_b = __ldg(g_valid + tid) | (static_cast<unsigned>(__ldg(g_valid + n16 + tid)) << 8) |
-        (static_cast<unsigned>(__ldg(g_follow + tid)) << 16);
+      pt_f[0] = ld_ro<kNc>(tail + 3 * N + tid); pt_f[1] = ld_ro<kNc>(tail + tid); pt_f[2] = ld_ro<kNc>(tail + N + tid);
+      pt_b = ld_ro<kNc>(g_valid + tid) | (static_cast<unsigned>(ld_ro<kNc>(g_valid + n16 + tid)) << 8) |
+        (static_cast<unsigned>(ld_ro<kNc>(g_follow + tid)) << 16);
     }
   }
   // ---- P5: position critics + spills, parallel over (trajectory, segment of the horizon)
@@ -638,7 +658,7 @@ __device__ __forceinline__ void rollout_tile_body(
 #pragma unroll
         for (int u = 0; u < kC; ++u) {cells[u] = world_to_cell_fast(pxs[u], pys[u], cg, &p.res);}
 #pragma unroll
-        for (int u = 0; u < kC; ++u) {pcs[u] = cells[u] < 0 ? NO_INFORMATION : __ldg(cm + cells[u]);}
+        for (int u = 0; u < kC; ++u) {pcs[u] = cells[u] < 0 ? NO_INFORMATION : ld_ro<kNc>(cm + cells[u]);}
       }
 #pragma unroll
       for (int u = 0; u < kC; ++u) {
@@ -663,7 +683,7 @@ __device__ __forceinline__ void rollout_tile_body(
             if (cost_on && !cost_hit && pose_cost >= 1) {            // cost_critic.cpp:139-162
               int c = pose_cost;
               if (cost_fp && (static_cast<float>(c) >= cost_pic || cost_pic < 1.0f)) {
-                fp_cost = footprint_cost_at_pose(P, p.fp_n, ox, oy, res, size_x, size_y, cm, px, py, s_yaw[o]);
+                fp_cost = footprint_cost_at_pose<kNc>(P, p.fp_n, ox, oy, res, size_x, size_y, cm, px, py, s_yaw[o]);
                 c = fp_cost;
               }
               if (in_collision(c, cost_fp, track_unknown)) {
@@ -678,7 +698,7 @@ __device__ __forceinline__ void rollout_tile_body(
               int c = pose_cost;
               int using_fp = 0;
               if (cell >= 0 && ob_fp && (static_cast<float>(c) >= ob_pic || ob_pic < 1.0f)) {
-                if (fp_cost < 0) {fp_cost = footprint_cost_at_pose(P, p.fp_n, ox, oy, res, size_x, size_y, cm, px, py, s_yaw[o]);}
+                if (fp_cost < 0) {fp_cost = footprint_cost_at_pose<kNc>(P, p.fp_n, ox, oy, res, size_x, size_y, cm, px, py, s_yaw[o]);}
                 c = fp_cost;
                 using_fp = 1;
               }
@@ -686,8 +706,8 @@ __device__ __forceinline__ void rollout_tile_body(
                 if (in_collision(c, ob_fp, track_unknown)) {
                   ob_hit = true;
                 } else if (ob_rep_on) {
-                  ob_traj += __ldg(&P->obst_lut_crit[using_fp][c]);
-                  if (!ob_near_goal) {ob_rep += __ldg(&P->obst_lut_rep[using_fp][c]);}
+                  ob_traj += ld_ro<kNc>(&P->obst_lut_crit[using_fp][c]);
+                  if (!ob_near_goal) {ob_rep += ld_ro<kNc>(&P->obst_lut_rep[using_fp][c]);}
                 }
               }
             }
@@ -735,8 +755,8 @@ __device__ __forceinline__ void rollout_tile_body(
     const uint8_t * g_valid = reinterpret_cast<const uint8_t *>(tail + 4 * N);
     const uint16_t * g_follow = reinterpret_cast<const uint16_t *>(g_valid + 2 * n16);
     for (int j = tid + nthreads; j < N; j += nthreads) {
-      fs.D[j] = __ldg(tail + 3 * N + j); fs.px[j] = __ldg(tail + j); fs.py[j] = __ldg(tail + N + j);
-      fs.valid[j] = __ldg(g_valid + j); fs.flags[j] = __ldg(g_valid + n16 + j); fs.follow[j] = __ldg(g_follow + j);
+      fs.D[j] = ld_ro<kNc>(tail + 3 * N + j); fs.px[j] = ld_ro<kNc>(tail + j); fs.py[j] = ld_ro<kNc>(tail + N + j);
+      fs.valid[j] = ld_ro<kNc>(g_valid + j); fs.flags[j] = ld_ro<kNc>(g_valid + n16 + j); fs.follow[j] = ld_ro<kNc>(g_follow + j);
     }
   }
 
@@ -746,16 +766,16 @@ __device__ __forceinline__ void rollout_tile_body(
   const int N = p.N;
   const bool need_furthest = p.need_furthest != 0;
   if (need_furthest) {
-    const float * __restrict__ path_x = reinterpret_cast<const float *>(P + 1) + p.off_path_x;
-    const float * __restrict__ path_y = reinterpret_cast<const float *>(P + 1) + p.off_path_y;
+    const float * path_x = reinterpret_cast<const float *>(P + 1) + p.off_path_x;
+    const float * path_y = reinterpret_cast<const float *>(P + 1) + p.off_path_y;
     const float ex = s_x[(T - 1) * kPad + lane], ey = s_y[(T - 1) * kPad + lane];
     const int per = (N + S - 1) / S;
     const int j0 = seg * per, j1 = min(N, j0 + per);
     float best = 3.402823466e+38f;
     int best_j = j0 < N ? j0 : 0;
     for (int j = j0; j < j1; ++j) {
-      const float dx = __fsub_rn(__ldg(path_x + j), ex);
-      const float dy = __fsub_rn(__ldg(path_y + j), ey);
+      const float dx = __fsub_rn(ld_ro<kNc>(path_x + j), ex);
+      const float dy = __fsub_rn(ld_ro<kNc>(path_y + j), ey);
       const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
       if (d < best) {best = d; best_j = j;}
     }
@@ -1068,7 +1088,7 @@ __device__ __forceinline__ void rollout_score_stream_body(
             if (cost_on && !cost_hit && pose_cost >= 1) {   // cost_critic.cpp:139-162
               int c = pose_cost;
               if (kFp && cost_fp && (static_cast<float>(c) >= cost_pic || cost_pic < 1.0f)) {
-                fp_cost = footprint_cost_at_pose(P, p.fp_n, p.ox, p.oy, p.res, cg.size_x, cg.size_y, cm, px[u], py[u], yaw);
+                fp_cost = footprint_cost_at_pose<true>(P, p.fp_n, p.ox, p.oy, p.res, cg.size_x, cg.size_y, cm, px[u], py[u], yaw);
                 c = fp_cost;
               }
               if (in_collision(c, cost_fp, track_unknown)) {
@@ -1083,7 +1103,7 @@ __device__ __forceinline__ void rollout_score_stream_body(
               int c = pose_cost;
               int using_fp = 0;
               if (kFp && cell[u] >= 0 && ob_fp && (static_cast<float>(c) >= ob_pic || ob_pic < 1.0f)) {
-                if (fp_cost < 0) {fp_cost = footprint_cost_at_pose(P, p.fp_n, p.ox, p.oy, p.res, cg.size_x, cg.size_y, cm, px[u], py[u], yaw);}
+                if (fp_cost < 0) {fp_cost = footprint_cost_at_pose<true>(P, p.fp_n, p.ox, p.oy, p.res, cg.size_x, cg.size_y, cm, px[u], py[u], yaw);}
                 c = fp_cost;
                 using_fp = 1;
               }
@@ -1913,7 +1933,7 @@ __device__ __forceinline__ void path_align_distances(
 // phases C..F; the value returned to the lanes of warp 0 is the critic's term of trajectory `lane`.  Starts with a barrier
 // of its own only where a phase needs the previous one (the caller has synchronised after the decisions).
 __device__ __forceinline__ float path_align_finish(
-  const DevParams * P, const FusedCtx & fx, int furthest, const float * __restrict__ path_yaw, int lane, int seg, int S)
+  const DevParams * P, const FusedCtx & fx, int furthest, const float * path_yaw, int lane, int seg, int S)
 {
   const int T = P->T, step = P->align_step;
   const int n_s = (T + step - 1) / step;
@@ -1966,7 +1986,7 @@ __device__ __forceinline__ float path_align_finish(
       pnum += 1.0f;
       // the distance itself only feeds the cost (1e-4 tolerance): one MUFU instead of the IEEE sequence
       if (P->align_use_yaw) {
-        const float dyaw = static_cast<float>(normalize_angle_d(static_cast<double>(fx.s_yaw[o]) - static_cast<double>(__ldg(path_yaw + res))));
+        const float dyaw = static_cast<float>(normalize_angle_d(static_cast<double>(fx.s_yaw[o]) - static_cast<double>(path_yaw[res])));
         psum += sqrt_approx(dx * dx + dy * dy + dyaw * dyaw);
       } else {
         psum += sqrt_approx(dx * dx + dy * dy);
@@ -1988,7 +2008,7 @@ __device__ __forceinline__ float path_align_finish(
 
 // PathAlignLegacyCritic::score (path_align_legacy_critic.cpp:97-128) for trajectory r, by one warp; lane = sampled pose
 __device__ __noinline__ float path_align_legacy_warp(
-  const DevParams * P, const FusedCtx & fx, int r, const float * __restrict__ path_yaw, int lane)
+  const DevParams * P, const FusedCtx & fx, int r, const float * path_yaw, int lane)
 {
   const int T = P->T, step = P->legacy_step, segs = P->N - 1;
   float summed = 0.0f;
@@ -2006,7 +2026,7 @@ __device__ __noinline__ float path_align_legacy_warp(
         const float dy = __fsub_rn(fx.fs.py[sgm], Ty);
         float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
         if (P->legacy_use_yaw) {
-          const float dyaw = static_cast<float>(normalize_angle_d(static_cast<double>(Tyaw) - static_cast<double>(__ldg(path_yaw + sgm))));
+          const float dyaw = static_cast<float>(normalize_angle_d(static_cast<double>(Tyaw) - static_cast<double>(path_yaw[sgm])));
           d = __fadd_rn(d, __fmul_rn(dyaw, dyaw));
         }
         if (d < min_d) {min_d = d; min_s = sgm;}
@@ -2062,7 +2082,7 @@ __device__ __forceinline__ void put_result(float * out, uint2 * host_res, int id
 // the work of one block on tile `tile` of `G` of one problem (see the header comment above)
 template<unsigned F, bool kExact>
 __device__ __forceinline__ void tile_fused_body(
-  const DevParams * __restrict__ Pg, const uint8_t * __restrict__ cm, const DevBuffers & bufs, const int B, const int T, const int n_cap,
+  const DevParams * Pg, const uint8_t * cm, const DevBuffers & bufs, const int B, const int T, const int n_cap,
   const int iteration, uint2 * host_res, const uint4 * up_host, const int up_vecs, const int tile, const int G,
   const int tail_mode, float * __restrict__ hist)
 {
@@ -2086,7 +2106,7 @@ __device__ __forceinline__ void tile_fused_body(
   const int b0 = tile * kTile;
   const int rows_here = min(kTile, B - b0);
   const int N = P->N;
-  const float * __restrict__ path_yaw = reinterpret_cast<const float *>(Pg + 1) + 2 * N;
+  const float * path_yaw = reinterpret_cast<const float *>(Pg + 1) + 2 * N;   // written in this launch (zero-copy): coherent loads
 
   // PathAlign, the part that does not depend on the furthest reached point: done while exchange 1 is in flight
   if (P->align.on) {path_align_distances(P, fx, lane, seg, S);}
@@ -2096,7 +2116,7 @@ __device__ __forceinline__ void tile_fused_body(
     unsigned cand = 0u, flags = 0u;
     for (int i = lane; i < G; i += 32) {
       unsigned v;
-      if (!poll_packet(bufs.pk_x1 + i, tag, v)) {st->comm_error = 1u;}
+      if (!poll_packet(bufs.pk_x1 + i, tag, v)) {raise_comm_error(bufs);}
       cand = max(cand, v & 0xffffu);
       flags |= v >> 16;
     }
@@ -2267,7 +2287,7 @@ __device__ __forceinline__ void tile_fused_body(
   if (!small) {
     for (int i = tid; i < G; i += nthr) {
       unsigned bits;
-      if (!poll_packet(recs + static_cast<size_t>(i) * stride, tag, bits)) {st->comm_error = 1u;}
+      if (!poll_packet(recs + static_cast<size_t>(i) * stride, tag, bits)) {raise_comm_error(bufs);}
       const float mi = __uint_as_float(bits);
       fs.e[i] = mi;
       m = fminf(m, mi);
@@ -2304,7 +2324,7 @@ __device__ __forceinline__ void tile_fused_body(
           for (;;) {
             const uint2 a = ld_packet(pm), w = ld_packet(pm + 1 + col);
             if (a.y == tag && w.y == tag) {mi = __uint_as_float(a.x); wi = __uint_as_float(w.x); break;}
-            if (clock64() - t0 > kSpinLimitCycles) {st->comm_error = 1u; mi = 0.0f; break;}
+            if (clock64() - t0 > kSpinLimitCycles) {raise_comm_error(bufs); mi = 0.0f; break;}
           }
         }
         const float mm = warp_min(mi);
@@ -2312,7 +2332,7 @@ __device__ __forceinline__ void tile_fused_body(
       } else {
         for (int i = lane; i < G; i += 32) {
           unsigned bits;
-          if (!poll_packet(recs + static_cast<size_t>(i) * stride + 1 + col, tag, bits)) {st->comm_error = 1u;}
+          if (!poll_packet(recs + static_cast<size_t>(i) * stride + 1 + col, tag, bits)) {raise_comm_error(bufs);}
           acc = fmaf(__uint_as_float(bits), fs.e[i], acc);
         }
       }
@@ -2359,7 +2379,7 @@ __device__ __forceinline__ void tile_fused_body(
     float * v = const_cast<float *>(fx.s_cvx);   // the tile planes are free now: [3][T]
     for (int i = tid; i < 3 * T; i += nthr) {
       unsigned bits;
-      if (!poll_packet(bufs.pk_out + i, tag, bits)) {st->comm_error = 1u;}
+      if (!poll_packet(bufs.pk_out + i, tag, bits)) {raise_comm_error(bufs);}
       v[i] = __uint_as_float(bits);
     }
     __syncthreads();
@@ -2377,9 +2397,10 @@ __device__ __forceinline__ void tile_fused_body(
   }
 }
 
+// (Pg, cm: no __restrict__ -- the tiles write both during the zero-copy upload)
 template<unsigned F, bool kExact>
 __global__ void __launch_bounds__(256, MPPI_FUSED_MIN_BLOCKS) tile_fused_kernel(
-  const DevParams * __restrict__ Pg, const uint8_t * __restrict__ cm, DevBuffers bufs, const int B, const int T, const int n_cap,
+  const DevParams * Pg, const uint8_t * cm, DevBuffers bufs, const int B, const int T, const int n_cap,
   const int iteration, uint2 * host_res, const uint4 * up_host, const int up_vecs, const int tail_mode, float * hist)
 {
   tile_fused_body<F, kExact>(Pg, cm, bufs, B, T, n_cap, iteration, host_res, up_host, up_vecs, blockIdx.x, gridDim.x, tail_mode, hist);
@@ -2703,7 +2724,7 @@ __global__ void __launch_bounds__(kUpdThreads) merge_exchange_finalize_kernel(
       idx = 2 + plane * T + t;
     }
     unsigned bits = 0u;
-    if (want && !poll_packet(local + kBoxX2 + r * kX2Stride + idx, tag, bits)) {bufs.st->comm_error = 1u;}
+    if (want && !poll_packet(local + kBoxX2 + r * kX2Stride + idx, tag, bits)) {raise_comm_error(bufs);}
     s_in[r][k] = __uint_as_float(bits);
   }
   __syncthreads();
@@ -2814,13 +2835,15 @@ __global__ void optimized_trajectory_kernel(const float * __restrict__ cs, float
   float dt, double pose_x, double pose_y, float yaw0)
 {
   if (threadIdx.x != 0 || blockIdx.x != 0) {return;}
-  float acc = 0.0f, accx = 0.0f, accy = 0.0f, prev_yaw = yaw0;
+  float acc = 0.0f, accx = 0.0f, accy = 0.0f;
   for (int t = 0; t < T; ++t) {
     const float term = __fmul_rn(cs[2 * T + t], dt);
     acc = t == 0 ? term : __fadd_rn(acc, term);
     const float yaw = __fadd_rn(acc, yaw0);
     float sn, cn;
-    mppi_det_sincosf(prev_yaw, &sn, &cn);
+    // optimizer.cpp:294-299: cos/sin[0] of the initial yaw, cos/sin[t >= 1] of yaws[t] itself -- this overload has no
+    // one-step lag, unlike the batch overload (:322-329)
+    mppi_det_sincosf(t == 0 ? yaw0 : yaw, &sn, &cn);
     float dx = __fmul_rn(cs[t], cn), dy = __fmul_rn(cs[t], sn);
     if (holonomic) {
       dx = __fsub_rn(dx, __fmul_rn(cs[T + t], sn));
@@ -2832,7 +2855,6 @@ __global__ void optimized_trajectory_kernel(const float * __restrict__ cs, float
     out_t3[3 * t] = static_cast<float>(pose_x + static_cast<double>(accx));
     out_t3[3 * t + 1] = static_cast<float>(pose_y + static_cast<double>(accy));
     out_t3[3 * t + 2] = yaw;
-    prev_yaw = yaw;
   }
 }
 

@@ -1499,7 +1499,9 @@ int oracle_get_optimized_trajectory(Optimizer * o, double pose_x, double pose_y,
   float accx = 0.0f, accy = 0.0f;
   for (size_t t = 0; t < T; ++t) {
     float yc, ys;
-    mppi_det_sincosf(t == 0 ? initial_yaw : yaws[t - 1], &ys, &yc);
+    // NOT the one-step lag of the batch overload (:322-329): this overload pairs cos/sin[1:] with yaws[1:]
+    // (`yaw_offseted = view(traj_yaws, range(1, _))`, optimizer.cpp:294-299), so step t >= 1 turns by its OWN yaw
+    mppi_det_sincosf(t == 0 ? initial_yaw : yaws[t], &ys, &yc);
     float dx = o->cs.vx[t] * yc, dy = o->cs.vx[t] * ys;
     if (o->isHolonomic()) {
       dx = dx - o->cs.vy[t] * ys;

@@ -208,6 +208,10 @@ static void testAllCollideThrows()
   mppi_b200::Path plan;
   plan.x = {2.0f, 2.5f}; plan.y = {2.0f, 2.0f}; plan.yaw = {0.0f, 0.0f};
   EXPECT_THROW(t.evalControl({2.0, 2.0, 0.0}, {0, 0, 0}, plan, {2.5, 2.0, 0.0}, -1.0, cm.view));
+  // the reference's retry loop never re-runs prepare(), so fail_flag survives the retries (critic_manager.cpp:70-73):
+  // retry_attempt_limit + 1 soft resets, then the throw -- on ANY map, even one that became free meanwhile
+  EXPECT_TRUE(t.resetCount() == s.retry_attempt_limit + 1);
+  EXPECT_TRUE(t.lastCycle().fail_flag != 0);
   // and the optimizer is usable again afterwards on a free map
   std::fill(cm.cells.begin(), cm.cells.end(), 0);
   EXPECT_NO_THROW(t.evalControl({2.0, 2.0, 0.0}, {0, 0, 0}, plan, {2.5, 2.0, 0.0}, -1.0, cm.view));

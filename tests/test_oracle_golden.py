@@ -329,3 +329,39 @@ def test_eval_control_is_optimize_then_filter_twist_shift(oracle_fns):
             np.testing.assert_array_equal(a.get_control_history(), hist)
         a.close()
         b.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# getOptimizedTrajectory (optimizer.cpp:345-360 -> integrateStateVelocities(xtensor2&, ...) :275-311)
+# ------------------------------------------------------------------------------------------------
+def test_optimized_trajectory_known_answer_and_second_opinion(oracle_fns):
+    """optimizer_unit_tests.cpp:243-248: a fresh Omni optimizer (zero sequence, 50 steps) returns a [50, 3] trajectory of
+    zeros.  Then an independent numpy restatement of optimizer.cpp:275-311 on a non-zero sequence: this overload pairs
+    cos/sin[1:] with yaws[1:] (`yaw_offseted = view(traj_yaws, range(1, _))`, :294-299) -- there is NO one-step lag,
+    unlike the batch overload (:322-329) that the rollout uses."""
+    e = Engine(oracle_fns, batch_size=1000, time_steps=50, model_dt=0.1, motion_model="Omni")
+    t = e.get_optimized_trajectory((0.0, 0.0, 0.0))
+    assert t.shape == (50, 3)
+    assert t[5, 0] == 0.0 and t[5, 1] == 0.0 and t[5, 2] == 0.0
+    rng = np.random.default_rng(3)
+    vx, vy, wz = (rng.uniform(-0.4, 0.5, 50).astype(np.float32) for _ in range(3))
+    e.set_control_sequence(vx, vy, wz)
+    pose = (1.25, -0.5, 0.3)
+    t = e.get_optimized_trajectory(pose)
+    dt = np.float32(0.1)
+    yaws = np.cumsum(wz * dt, dtype=np.float32) + np.float32(pose[2])
+    ang = yaws.copy()
+    ang[0] = np.float32(pose[2])                       # cos/sin[0] = cosf/sinf(initial_yaw); [1:] = cos/sin(yaws[1:])
+    c, s = np.cos(ang.astype(np.float64)), np.sin(ang.astype(np.float64))
+    dx = vx * c - vy * s
+    dy = vx * s + vy * c
+    x = pose[0] + np.cumsum((dx * dt).astype(np.float32), dtype=np.float32)
+    y = pose[1] + np.cumsum((dy * dt).astype(np.float32), dtype=np.float32)
+    np.testing.assert_array_equal(t[:, 2], yaws)
+    np.testing.assert_allclose(t[:, 0], x, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(t[:, 1], y, rtol=0, atol=2e-6)
+    # the lagged pairing (what the batch overload does) gives a visibly different curve: the test can tell them apart
+    lag = np.concatenate([[np.float32(pose[2])], yaws[:-1]]).astype(np.float64)
+    x_lag = pose[0] + np.cumsum(((vx * np.cos(lag) - vy * np.sin(lag)) * dt).astype(np.float32), dtype=np.float32)
+    assert np.abs(x_lag - x).max() > 1e-3
+    e.close()
