@@ -503,6 +503,13 @@ struct Optimizer
   uint64_t noise_stream{0};
   float control_history[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};   // ref: inc/optimizer.hpp:251
   std::string err;
+  // Test switch (oracle_set_wide_reductions): the softmax normaliser and the weighted control sums accumulate in double.
+  // The reference types these accumulators as float and leaves their ORDER to xtensor/xsimd under -ffast-math (xt::sum over
+  // [B], xt::sum(.., 0) over [B,T]; optimizer.cpp:384-391), so its own bits are not defined.  For the sizes the reference is
+  // used at (B ~ 1000) every order agrees to ~1e-6; at B = 262144 a float accumulator in index order drops the softmax tail
+  // below half an ulp of the running sum (3e-4 relative, larger than the parity tolerance), so the full-size test compares
+  // with this order-free value and reports the index-order float result beside it.
+  bool wide_reductions{false};
 
   bool isHolonomic() const {return cfg.motion_model == MPPI_MODEL_OMNI;}
 
@@ -646,17 +653,26 @@ struct Optimizer
     for (size_t b = 0; b < B; ++b) {cmin = std::min(cmin, costs[b]);}
     std::vector<float> softmaxes(B);
     float sum = 0.0f;
+    double wide_sum = 0.0;
     const float neg_inv_temp = -1 / cfg.temperature;
     for (size_t b = 0; b < B; ++b) {
       softmaxes[b] = expf(neg_inv_temp * (costs[b] - cmin));
       sum += softmaxes[b];
+      wide_sum += static_cast<double>(softmaxes[b]);
     }
+    if (wide_reductions) {sum = static_cast<float>(wide_sum);}
     for (size_t b = 0; b < B; ++b) {softmaxes[b] = softmaxes[b] / sum;}
     auto weighted = [&](const Plane & c, std::vector<float> & seq) {
         for (size_t t = 0; t < T; ++t) {
-          float acc = 0.0f;
-          for (size_t b = 0; b < B; ++b) {acc += c(b, t) * softmaxes[b];}
-          seq[t] = acc;
+          if (wide_reductions) {
+            double acc = 0.0;
+            for (size_t b = 0; b < B; ++b) {acc += static_cast<double>(c(b, t) * softmaxes[b]);}
+            seq[t] = static_cast<float>(acc);
+          } else {
+            float acc = 0.0f;
+            for (size_t b = 0; b < B; ++b) {acc += c(b, t) * softmaxes[b];}
+            seq[t] = acc;
+          }
         }
       };
     weighted(state.cvx, cs.vx);
@@ -1457,6 +1473,11 @@ int oracle_get_trajectories(Optimizer * o, float * x, float * y, float * yaw)
 {
   const size_t n = o->traj.x.v.size();
   std::memcpy(x, o->traj.x.v.data(), n * 4); std::memcpy(y, o->traj.y.v.data(), n * 4); std::memcpy(yaw, o->traj.yaws.v.data(), n * 4);
+  return MPPI_OK;
+}
+int oracle_set_wide_reductions(Optimizer * o, int32_t on)
+{
+  o->wide_reductions = on != 0;
   return MPPI_OK;
 }
 int oracle_get_state(Optimizer * o, float * vx, float * vy, float * wz, float * cvx, float * cvy, float * cwz)

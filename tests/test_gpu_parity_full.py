@@ -63,25 +63,51 @@ def test_config3_full_size_against_the_oracle(product_fns, oracle_fns):
     g.close(); o.close()
 
 
+def _controls_dev(ra, rb):
+    """largest relative deviation of the control sequences (floor 1e-6 absolute, the floor of the parity bar)"""
+    worst = 0.0
+    for name in ("vx", "vy", "wz"):
+        a, b = np.asarray(getattr(ra, name), np.float64), np.asarray(getattr(rb, name), np.float64)
+        worst = max(worst, float(np.max(np.maximum(np.abs(a - b) - ATOL, 0.0) / np.maximum(np.abs(b), 1e-12))))
+    return worst
+
+
 def test_config4_full_size_against_the_oracle(product_fns, oracle_fns):
     """BASELINE configs[3] on ONE GPU: 262144 x 100, default critic set, 400 x 400 map, N = 120.  The noise is drawn by the
-    Philox kernel and handed to the oracle (mppi_get_noise -> oracle set_noise), so both sides see identical bits."""
+    Philox kernel and handed to the oracle (mppi_get_noise -> oracle set_noise), so both sides see identical bits.
+
+    Cells, trajectories, per-critic costs and total costs: against the oracle as everywhere else.  Control sequence: the
+    reference types the softmax normaliser and the weighted sums as float and leaves their order to xtensor/xsimd under
+    -ffast-math (optimizer.cpp:384-391).  At 262144 trajectories a float accumulator in index order drops the softmax tail
+    (terms below half an ulp of the running sum): the literal index-order oracle itself sits ~3e-4 from the order-free value,
+    i.e. two legal evaluation orders of the reference differ by more than the 1e-4 bar.  The bar is therefore applied against
+    the oracle with order-free (double) accumulators; the index-order float oracle runs beside it and the test requires the
+    device result to be CLOSER to the order-free value than the index-order one is, and within 1e-3 of the latter."""
     sc = scenarios.config4()
     g = _engine(product_fns, sc, None, seed=3)
     g.generate_noise(0)
     noise = g.get_noise()
     o = _engine(oracle_fns, sc, noise)
+    oracle_fns["set_wide_reductions"](o.h, 1)
+    lit = _engine(oracle_fns, sc, noise, outputs=False)          # literal restatement: float accumulators, index order
+    report = []
     for cycle in range(2):
-        rg, ro = g.optimize(sc.cycle), o.optimize(sc.cycle)
+        rg, ro, rl = g.optimize(sc.cycle), o.optimize(sc.cycle), lit.optimize(sc.cycle)
         _compare(g, o, sc, rg, ro, f"config4 cycle {cycle}")
-        g.set_control_sequence(ro.vx, ro.vy, ro.wz)
+        d_dev, d_lit, d_dev_lit = _controls_dev(rg, ro), _controls_dev(rl, ro), _controls_dev(rg, rl)
+        report.append((cycle, d_dev, d_lit, d_dev_lit))
+        assert d_dev < d_lit or d_lit < 1e-5, (d_dev, d_lit)
+        assert d_dev_lit < 1e-3, d_dev_lit
+        for e in (g, lit):
+            e.set_control_sequence(ro.vx, ro.vy, ro.wz)
+    print("config4 control deviations (cycle, device vs order-free, index-order float vs order-free, device vs index-order):", report)
     # what bench.py times: nothing materialised (exact instance), same controls
     g.set_outputs()
     g.set_control_sequence(*(np.zeros(100, np.float32),) * 3)
     o.set_control_sequence(*(np.zeros(100, np.float32),) * 3)
     rg, ro = g.optimize(sc.cycle), o.optimize(sc.cycle)
     _compare(g, o, sc, rg, ro, "config4, no outputs", bitwise=False)
-    g.close(); o.close()
+    g.close(); o.close(); lit.close()
 
 
 @pytest.mark.parametrize("mode", ["stream", "tile"])
