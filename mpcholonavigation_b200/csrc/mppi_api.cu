@@ -98,9 +98,9 @@ struct mppi_handle
   int * d_cells{nullptr};
   float * d_costs{nullptr};
   float * d_partials{nullptr};
-  CUtensorMap noise_map[3];           // TMA descriptors of the time-major noise planes (stream layout, path_softmax_stream_kernel)
-  bool k3s_enabled{true};             // MPPI_K3S=0: the two-kernel path (path_costs_tm + weighted_sums_tm), kept for ragged batches
-  bool k3s_ok{false};                 // the fused path-critics + softmax + weighted-sums kernel can run (B % 4 == 0, descriptors made)
+  CUtensorMap noise_map[3];           // TMA descriptors of the time-major noise planes (stream layout, weighted_sums_tma_kernel)
+  bool ws_tma_enabled{true};             // MPPI_WS_TMA=0: the register-staged weighted-sums kernel (always used when B % 4 != 0)
+  bool ws_tma_ok{false};                 // the TMA-fed weighted-sums kernel can run (B % 4 == 0, descriptors made)
   float * d_rank_partial{nullptr};
   float * d_gathered{nullptr};
   size_t gathered_capacity{0};   // records d_gathered holds (exchange 2: one (3T + 2)-float record per rank / shard)
@@ -657,7 +657,7 @@ int pick_segments(const mppi_handle * h)
   return S;
 }
 
-// TMA descriptors of the time-major noise planes [T + pad][B] for path_softmax_stream_kernel: box = kPsRows rows x kPsChunk
+// TMA descriptors of the time-major noise planes [T + pad][B] for weighted_sums_tma_kernel: box = kPsRows rows x kPsBoxCols
 // columns, no swizzle (a warp reads one row with 16-byte vectors at consecutive lanes: conflict free as it lies), columns
 // beyond B are zero-filled by the TMA unit.  cuTensorMapEncodeTiled is a driver entry point; it is fetched through the
 // runtime (cudaGetDriverEntryPoint), so the library still links against nothing but the static runtime.
@@ -679,7 +679,7 @@ bool make_noise_maps(mppi_handle * h)
   for (int i = 0; i < 3; ++i) {
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(h->B), static_cast<cuuint64_t>(h->T + kNoisePadRows)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(h->B) * sizeof(float)};
-    const cuuint32_t box[2] = {static_cast<cuuint32_t>(kPsChunk), static_cast<cuuint32_t>(kPsRows)};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(kPsBoxCols), static_cast<cuuint32_t>(kPsRows)};
     const cuuint32_t estr[2] = {1, 1};
     if (encode(&h->noise_map[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->d_noise[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
@@ -970,6 +970,31 @@ mppi_status launch_rollout(mppi_handle * h, int mode)
   return MPPI_OK;
 }
 
+// K3c of the stream layout: the TMA-fed kernel whenever the descriptors exist (B % 4 == 0), else the register-staged one
+int weighted_sums_chunks(const mppi_handle * h)
+{
+  return h->ws_tma_ok ? (h->B + kPsChunk - 1) / kPsChunk : (h->B + kWsChunk - 1) / kWsChunk;
+}
+
+mppi_status launch_weighted_sums(mppi_handle * h)
+{
+  const DevParams * dp = reinterpret_cast<const DevParams *>(h->d_params);
+  const int chunks = weighted_sums_chunks(h);
+  if (h->ws_tma_ok) {
+    // row groups: about four waves of 3 resident blocks per SM (a short tail), at least two stages per block
+    const int stages = (holonomic(h) ? 3 : 2) * ((h->T + kPsRows - 1) / kPsRows);
+    const int gy = std::max(1, std::min(stages / 2, (12 * h->num_sms + chunks - 1) / chunks));
+    weighted_sums_tma_kernel<<<dim3(chunks, gy), kPsThreads, ps_smem_bytes(), h->stream>>>(
+      h->noise_map[0], h->noise_map[1], h->noise_map[2], dp, make_bufs(h, 0), h->T, h->B, holonomic(h) ? 1 : 0);
+  } else {
+    const int gy = weighted_sums_row_groups(h->T, chunks);
+    weighted_sums_tm_kernel<<<dim3(chunks, gy), kWsThreads, 0, h->stream>>>(dp, make_bufs(h, 0));
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
+  return MPPI_OK;
+}
+
 mppi_status launch_update(mppi_handle * h, int mode, int iteration)
 {
   if (mode == 0 && h->stream_layout) {
@@ -977,15 +1002,6 @@ mppi_status launch_update(mppi_handle * h, int mode, int iteration)
     const int grid = std::min((h->B + kUpdThreads - 1) / kUpdThreads, 148 * 8);
     // the iteration that completes the result advances the packet epoch when the result leaves as packets
     const int bump = (stream_packets(h) && iteration + 1 == h->cfg.iteration_count) ? 1 : 0;
-    if (h->k3s_ok) {
-      // path critics, totals, block-local softmax and the weighted control sums in one kernel (TMA ring over the noise)
-      path_softmax_stream_kernel<<<(h->B + kPsChunk - 1) / kPsChunk, kPsThreads, ps_smem_bytes(h->T), h->stream>>>(
-        h->noise_map[0], h->noise_map[1], h->noise_map[2], reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, mode),
-        iteration, bump, h->T, holonomic(h) ? 1 : 0);
-      CUDA_TRY(h, cudaGetLastError());
-      h->launches++;
-      return MPPI_OK;
-    }
     if (h->B >= 131072) {
       path_costs_tm_kernel<8><<<grid, kUpdThreads, k3_common_smem_bytes(), h->stream>>>(
         reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, mode), iteration, bump);
@@ -1040,13 +1056,11 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
     const bool many = h->upd_blocks > kLastBlockMergeMax;
     const int merge_grid = (h->T + kMergeT - 1) / kMergeT;
     const DevParams * dp = reinterpret_cast<const DevParams *>(h->d_params);
-    const int chunks = h->k3s_ok ? (h->B + kPsChunk - 1) / kPsChunk : (h->B + kWsChunk - 1) / kWsChunk;
-    if (h->stream_layout && !h->k3s_ok) {
+    const int chunks = weighted_sums_chunks(h);
+    if (h->stream_layout) {
       // K3 published costs + global minimum; weights and weighted control sums over the time-major noise
-      const int gy = weighted_sums_row_groups(h->T, chunks);
-      weighted_sums_tm_kernel<<<dim3(chunks, gy), kWsThreads, 0, h->stream>>>(dp, make_bufs(h, 0));
-      CUDA_TRY(h, cudaGetLastError());
-      h->launches++;
+      const mppi_status ws = launch_weighted_sums(h);
+      if (ws != MPPI_OK) {return ws;}
     }
     if (h->nranks > 1 && h->peer_mode) {
       // exchange 2 over peer memory, fused with the local merge before it and the cross-rank merge after it
@@ -1874,7 +1888,7 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   if (const char * e = std::getenv("MPPI_ZERO_COPY")) {h->zero_copy_enabled = std::atoi(e) != 0;}
   if (const char * e = std::getenv("MPPI_COOP")) {h->coop_launch = std::atoi(e) != 0;}
   if (const char * e = std::getenv("MPPI_STREAM_PACKETS")) {h->packets_enabled = std::atoi(e) != 0;}
-  if (const char * e = std::getenv("MPPI_K3S")) {h->k3s_enabled = std::atoi(e) != 0;}
+  if (const char * e = std::getenv("MPPI_WS_TMA")) {h->ws_tma_enabled = std::atoi(e) != 0;}
   {
     // batches too small to fill the GPU with one thread per trajectory keep the latency-oriented tile kernel
     long long stream_min = 8192;    // measured cross-over on B200 (profiles/): below it the tile kernel wins
@@ -1913,8 +1927,8 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   }
   CUDA_TRY(h, cudaFuncSetAttribute(path_softmax_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
     static_cast<int>(k3_tile_smem_bytes(MPPI_MAX_TIME_STEPS))));
-  CUDA_TRY(h, cudaFuncSetAttribute(path_softmax_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-    static_cast<int>(ps_smem_bytes(MPPI_MAX_TIME_STEPS))));
+  CUDA_TRY(h, cudaFuncSetAttribute(weighted_sums_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    static_cast<int>(ps_smem_bytes())));
   CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CUDA_TRY(h, cudaEventCreate(&h->ev0));
   CUDA_TRY(h, cudaEventCreate(&h->ev1));
@@ -1931,7 +1945,7 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
     CUDA_TRY(h, cudaMalloc(&h->d_spill[i], plane));
     CUDA_TRY(h, cudaMemsetAsync(h->d_noise[i], 0, noise_plane, h->stream));
   }
-  if (h->stream_layout && h->k3s_enabled) {h->k3s_ok = make_noise_maps(h);}
+  if (h->stream_layout && h->ws_tma_enabled) {h->ws_tma_ok = make_noise_maps(h);}
   CUDA_TRY(h, cudaMalloc(&h->d_cells, B * T * sizeof(int)));
   CUDA_TRY(h, cudaMalloc(&h->d_params, kParamsCapacity + 256));
   CUDA_TRY(h, cudaMalloc(&h->d_cs, 3 * T * sizeof(float)));
@@ -2630,12 +2644,8 @@ mppi_status mppi_optimize_sharded(mppi_handle ** hs, int32_t n, const mppi_cycle
       if ((s = launch_update(h, 0, it)) != MPPI_OK) {break;}
       const int merge_grid = (T + kMergeT - 1) / kMergeT;
       if (h->stream_layout) {
-        const int chunks = h->k3s_ok ? (h->B + kPsChunk - 1) / kPsChunk : (h->B + kWsChunk - 1) / kWsChunk;
-        if (!h->k3s_ok) {
-          const int gy = weighted_sums_row_groups(T, chunks);
-          weighted_sums_tm_kernel<<<dim3(chunks, gy), kWsThreads, 0, h->stream>>>(reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, 0));
-          h->launches++;
-        }
+        const int chunks = weighted_sums_chunks(h);
+        if ((s = launch_weighted_sums(h)) != MPPI_OK) {break;}
         merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
           reinterpret_cast<const DevParams *>(h->d_params), h->d_partials, chunks, stride, make_bufs(h, 0), 0, h->d_rank_partial, nullptr);
         h->launches++;

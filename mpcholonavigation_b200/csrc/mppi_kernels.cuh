@@ -2542,34 +2542,33 @@ __global__ void __launch_bounds__(kWsThreads) weighted_sums_tm_kernel(const DevP
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K3s (stream layout, B % 4 == 0): path critics + totals + block-local online softmax + weighted control sums in ONE
-// kernel; replaces path_costs_tm_kernel + weighted_sums_tm_kernel (one launch less, no global-minimum pass, no second
-// trip of the costs through global memory).  critic_manager.cpp:67-76, path_*_critic.cpp, optimizer.cpp:362-394.
+// K3c, Blackwell data path (stream layout, B % 4 == 0): the weighted control sums W[c] = sum_b w_b (cs[c] + noise[c][b])
+// with the noise streamed through shared memory by the TMA unit instead of per-lane 16-byte loads (optimizer.cpp:384-391).
 //
-// One block owns kPsChunk = 256 consecutive trajectories.  Warp 8 is the PRODUCER: from the first instruction on it
-// streams the block's columns of the three time-major noise planes through a ring of kPsStages shared-memory stages with
-// TMA (cp.async.bulk.tensor.2d, one box = 8 rows x 256 columns = 8 KB per instruction, completion on an mbarrier), so the
-// HBM stream of the GEMV is already in flight while warps 0..7 (the CONSUMERS, thread = trajectory) walk the path critics
-// and the totals, reduce the block minimum and turn the costs into weights.  The consumers then drain the ring: warp w
-// owns row w of every box, the weights of its 8 columns per lane sit in registers, one shuffle reduction per row.  Full /
-// empty mbarriers per stage, no __syncthreads in the steady state.  Out-of-range columns of the last chunk are zero-filled
-// by the TMA unit (their weights are zero as well).  The record written per block is [m_block, s_block, W[3T]] relative
-// to the BLOCK minimum; merge_finalize_kernel rescales (online-softmax merge), so no grid-wide minimum is needed.
-// Chunks are taken in DESCENDING column order: the columns the rollout kernel read last are the ones still in L2.
+// One block owns kPsChunk = 1024 consecutive trajectories (columns of the time-major planes) and a range of row groups
+// (gridDim.y).  The last warp is the PRODUCER: its first lane fills a ring of kPsStages stages with cp.async.bulk.tensor.2d
+// (a stage = 4 rows x 1024 columns = 16 KB as four boxes of 4 x 256, completion counted on the stage's `full` mbarrier)
+// before anything else happens in the block, and refills a stage as soon as the 4 consumer warps have released it (`empty`
+// mbarrier).  The CONSUMERS turn the block's 1024 costs into weights (32 per lane, in registers) while the first stages are in
+// flight, then drain the ring: warp w owns row w of every stage, eight conflict-free 16-byte shared loads per lane, 32 FMAs,
+// one shuffle reduction per row.  No __syncthreads in the steady state; 64 KB in flight per block whatever the consumers
+// do, which is what the register-staged version lacked (long-scoreboard 25 per issue at 41 % occupancy, profiles/r01b).  Columns beyond B
+// are zero-filled by the TMA unit (their weights are zero too).  Chunks are taken in DESCENDING column order: the columns the
+// rollout kernel read last are the ones still in L2.  The record per chunk is [m = global min, s, W[3T]] like the
+// register-staged kernel's, so merge_finalize_kernel is unchanged.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kPsChunk = 256;
-constexpr int kPsRows = 8;
+constexpr int kPsChunk = 1024;            // trajectories (columns) per block
+constexpr int kPsBoxCols = 256;           // columns per TMA box (the hardware limit of a box dimension)
+constexpr int kPsSub = kPsChunk / kPsBoxCols;
+constexpr int kPsRows = 4;                // rows per stage == consumer warps
 constexpr int kPsStages = 4;
-constexpr int kPsConsumers = 256;
+constexpr int kPsConsumers = 32 * kPsRows;
 constexpr int kPsThreads = kPsConsumers + 32;
-constexpr int kPsStageBytes = kPsRows * kPsChunk * 4;
+constexpr int kPsBoxBytes = kPsRows * kPsBoxCols * 4;
+constexpr int kPsStageBytes = kPsSub * kPsBoxBytes;
 constexpr int kPsSpinLimit = 1 << 22;     // bounded mbarrier waits (each try_wait suspends the thread for a while)
 
-__host__ __device__ inline size_t ps_smem_bytes(int T)
-{
-  // [stages][8][256] floats (128-byte aligned: it is the base of the dynamic window) | K3 common block | weights | W[3T]
-  return static_cast<size_t>(kPsStages) * kPsStageBytes + k3_common_smem_bytes() + sizeof(float) * (kPsChunk + 3 * T + 8);
-}
+__host__ __device__ inline size_t ps_smem_bytes() {return static_cast<size_t>(kPsStages) * kPsStageBytes + 128;}
 
 __device__ __forceinline__ unsigned smem_u32(const void * p) {return static_cast<unsigned>(__cvta_generic_to_shared(p));}
 __device__ __forceinline__ void mbar_init(uint64_t * bar, unsigned count)
@@ -2605,115 +2604,107 @@ __device__ __forceinline__ void tma_load_2d(void * dst, const CUtensorMap * map,
     :: "r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(col), "r"(row), "r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(kPsThreads, 3) path_softmax_stream_kernel(
+// one stage = kPsRows rows x kPsChunk columns as kPsSub boxes side by side (box q lands at q * kPsBoxBytes): the four boxes of
+// a stage ask for the same rows back to back, so DRAM sees 4 KB contiguous per row like the register-staged kernel
+__device__ __forceinline__ void ps_fill_stage(float * stage, const CUtensorMap * map, int b0, int t0, uint64_t * bar)
+{
+  mbar_arrive_expect_tx(bar, kPsStageBytes);
+#pragma unroll
+  for (int q = 0; q < kPsSub; ++q) {tma_load_2d(stage + q * (kPsBoxBytes / 4), map, b0 + q * kPsBoxCols, t0, bar);}
+}
+
+__global__ void __launch_bounds__(kPsThreads) weighted_sums_tma_kernel(
   const __grid_constant__ CUtensorMap tm_vx, const __grid_constant__ CUtensorMap tm_vy, const __grid_constant__ CUtensorMap tm_wz,
-  const DevParams * __restrict__ Pg, DevBuffers bufs, int iteration, int bump_epoch, const int T, const int holonomic)
+  const DevParams * __restrict__ Pg, DevBuffers bufs, const int T, const int B, const int holonomic)
 {
   extern __shared__ __align__(128) float ps_smem[];
-  float * smem = ps_smem;
   __shared__ __align__(8) uint64_t s_full[kPsStages], s_empty[kPsStages];
-  __shared__ K3Decisions dec;
-  __shared__ float s_red[2][kPsConsumers / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float * s_stage = smem;
-  float * s_common = smem + kPsStages * kPsStageBytes / 4;
-  float * s_w = s_common + k3_common_smem_bytes() / 4;
-  float * s_W = s_w + kPsChunk;
+  float * s_stage = ps_smem;
   const int chunk = static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x);
   const int b0 = chunk * kPsChunk;
+  // stages in ring order: plane vx, plane wz, [plane vy]; this block's share of them (gridDim.y row groups)
   const int boxes_per_plane = (T + kPsRows - 1) / kPsRows;
-  const int n_planes = holonomic ? 3 : 2;                       // planes in ring order: vx, wz, [vy]
-  const int n_boxes = n_planes * boxes_per_plane;
-  const bool producer = warp == kPsConsumers / 32;
+  const int n_all = (holonomic ? 3 : 2) * boxes_per_plane;
+  const int per_y = (n_all + static_cast<int>(gridDim.y) - 1) / static_cast<int>(gridDim.y);
+  const int box_begin = blockIdx.y * per_y, n_boxes = max(0, min(n_all, box_begin + per_y) - box_begin);
 
   if (tid == kPsConsumers) {
     for (int s = 0; s < kPsStages; ++s) {mbar_init(&s_full[s], 1u); mbar_init(&s_empty[s], kPsConsumers / 32);}
     asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
-    // the ring is filled before anything else happens in this block: the stream does not wait for the path critics
     for (int i = 0; i < min(kPsStages, n_boxes); ++i) {
-      const int pl = i / boxes_per_plane, t0 = (i - pl * boxes_per_plane) * kPsRows;
-      const CUtensorMap * map = pl == 0 ? &tm_vx : (pl == 1 ? &tm_wz : &tm_vy);
-      mbar_arrive_expect_tx(&s_full[i], kPsStageBytes);
-      tma_load_2d(s_stage + i * (kPsStageBytes / 4), map, b0, t0, &s_full[i]);
+      const int g = box_begin + i, pl = g / boxes_per_plane, t0 = (g - pl * boxes_per_plane) * kPsRows;
+      ps_fill_stage(s_stage + i * (kPsStageBytes / 4), pl == 0 ? &tm_vx : (pl == 1 ? &tm_wz : &tm_vy), b0, t0, &s_full[i]);
     }
   }
-  K3Path path;
-  k3_preamble(s_common, Pg, bufs.st, bufs.peer, iteration, tid, kPsThreads, path, &dec);   // ends with __syncthreads: barriers visible
-  const DevParams * P = reinterpret_cast<const DevParams *>(s_common);
+  __syncthreads();     // the barriers are initialised for everybody
 
-  if (producer) {
+  if (warp == kPsConsumers / 32) {
     if (lane == 0) {
       for (int i = kPsStages; i < n_boxes; ++i) {
         const int s = i % kPsStages;
-        const unsigned parity = ((i / kPsStages) - 1) & 1u;       // the consumers' release of the stage's previous use
-        if (!mbar_wait(&s_empty[s], parity)) {raise_comm_error(bufs); break;}
-        const int pl = i / boxes_per_plane, t0 = (i - pl * boxes_per_plane) * kPsRows;
-        const CUtensorMap * map = pl == 0 ? &tm_vx : (pl == 1 ? &tm_wz : &tm_vy);
-        mbar_arrive_expect_tx(&s_full[s], kPsStageBytes);
-        tma_load_2d(s_stage + s * (kPsStageBytes / 4), map, b0, t0, &s_full[s]);
+        if (!mbar_wait(&s_empty[s], ((i / kPsStages) - 1) & 1u)) {raise_comm_error(bufs); break;}   // the stage's previous use is drained
+        const int g = box_begin + i, pl = g / boxes_per_plane, t0 = (g - pl * boxes_per_plane) * kPsRows;
+        ps_fill_stage(s_stage + s * (kPsStageBytes / 4), pl == 0 ? &tm_vx : (pl == 1 ? &tm_wz : &tm_vy), b0, t0, &s_full[s]);
       }
     }
-  } else {
-    // ---- phase 1 (thread = trajectory): path critics, total in list order, gamma term (k3_trajectory_total)
-    const int B = P->B;
-    const int b = b0 + tid;
-    const bool live = b < B;
-    const float total = live ? k3_trajectory_total(b, P, dec, path, bufs, iteration) : 3.402823466e+38f;
-    float m = warp_min(total);
-    if (lane == 0) {s_red[0][warp] = m;}
-    asm volatile ("bar.sync 1, %0;" :: "n"(kPsConsumers) : "memory");
-    m = s_red[0][0];
+    return;
+  }
+  // ---- consumers: softmax weights of the chunk; lane owns columns q * 256 + j * 128 + 4 lane + {0..3}, q < 4, j < 2
+  const float inv_temp = 1.0f / Pg->temperature;
+  const float gm = bufs.st->global_min;
+  float w[kPsSub][2][4];
+  float ssum = 0.0f;
 #pragma unroll
-    for (int w = 1; w < kPsConsumers / 32; ++w) {m = fminf(m, s_red[0][w]);}
-    const float wgt = live ? expf(-(total - m) * (1.0f / P->temperature)) : 0.0f;
-    s_w[tid] = wgt;
-    const float ws = warp_sum(wgt);
-    if (lane == 0) {s_red[1][warp] = ws;}
-    asm volatile ("bar.sync 1, %0;" :: "n"(kPsConsumers) : "memory");
-    float ssum = 0.0f;
+  for (int q = 0; q < kPsSub; ++q) {
 #pragma unroll
-    for (int w = 0; w < kPsConsumers / 32; ++w) {ssum += s_red[1][w];}
-    // ---- phase 2: drain the ring; warp w owns row w of every box, lane owns columns 4 lane + {0..3} and 128 + 4 lane + {0..3}
-    const float4 w0 = *reinterpret_cast<const float4 *>(s_w + 4 * lane);
-    const float4 w1 = *reinterpret_cast<const float4 *>(s_w + 128 + 4 * lane);
-    bool ok = true;
-    for (int i = 0; i < n_boxes && ok; ++i) {
-      const int s = i % kPsStages;
-      ok = mbar_wait(&s_full[s], (i / kPsStages) & 1u);
-      if (!ok) {raise_comm_error(bufs); break;}
-      const int pl = i / boxes_per_plane, t = (i - pl * boxes_per_plane) * kPsRows + warp;
-      const float * row = s_stage + s * (kPsStageBytes / 4) + warp * kPsChunk;
-      const float4 v0 = *reinterpret_cast<const float4 *>(row + 4 * lane);
-      const float4 v1 = *reinterpret_cast<const float4 *>(row + 128 + 4 * lane);
-      __syncwarp();
-      if (lane == 0) {mbar_arrive(&s_empty[s]);}
-      float a0 = w0.x * v0.x, a1 = w1.x * v1.x;
-      a0 = fmaf(w0.y, v0.y, a0); a1 = fmaf(w1.y, v1.y, a1);
-      a0 = fmaf(w0.z, v0.z, a0); a1 = fmaf(w1.z, v1.z, a1);
-      a0 = fmaf(w0.w, v0.w, a0); a1 = fmaf(w1.w, v1.w, a1);
-      const float a = warp_sum(a0 + a1);
-      if (lane == 0 && t < T) {s_W[(pl == 0 ? 0 : (pl == 1 ? 2 : 1)) * T + t] = a;}   // record order: vx, vy, wz
-    }
-    asm volatile ("bar.sync 1, %0;" :: "n"(kPsConsumers) : "memory");
-    // ---- the block's record: W[c] = sum_b w_b (cs[c] + noise[c][b]) = cs[c] * s + sum_b w_b noise[c][b]
-    float * part = bufs.partials + static_cast<size_t>(chunk) * (3 * T + 2);
-    if (tid == 0) {part[0] = m; part[1] = ssum;}
-    for (int c = tid; c < 3 * T; c += kPsConsumers) {
-      const bool have = holonomic || c < T || c >= 2 * T;
-      part[2 + c] = have ? fmaf(bufs.cs[c], ssum, s_W[c]) : 0.0f;
+    for (int j = 0; j < 2; ++j) {
+      const int b = b0 + q * kPsBoxCols + j * 128 + 4 * lane;
+      float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      if (b + 3 < B) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(bufs.costs + b));
+        c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {if (b + e < B) {c[e] = __ldg(bufs.costs + b + e);}}
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        w[q][j][e] = b + e < B ? expf(-(c[e] - gm) * inv_temp) : 0.0f;
+        ssum += w[q][j][e];
+      }
     }
   }
-  // ---- the last block to finish publishes the flags of the pass (and advances the packet epoch for the merge kernel)
-  __shared__ unsigned sc_last;
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {sc_last = atomicAdd(&bufs.st->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;}
-  __syncthreads();
-  if (sc_last && tid == 0) {
-    __threadfence();
-    k3_publish_flags(P, bufs.st, dec, bufs.out);
-    if (bump_epoch) {*bufs.epoch += 1u;}
+  ssum = warp_sum(ssum);          // every warp holds the whole chunk: the same sum in every warp
+  float * part = bufs.partials + static_cast<size_t>(chunk) * (3 * T + 2);
+  if (blockIdx.y == 0 && tid == 0) {part[0] = gm; part[1] = ssum;}
+  for (int i = 0; i < n_boxes; ++i) {
+    const int s = i % kPsStages;
+    if (!mbar_wait(&s_full[s], (i / kPsStages) & 1u)) {raise_comm_error(bufs); break;}
+    const int g = box_begin + i, pl = g / boxes_per_plane, t = (g - pl * boxes_per_plane) * kPsRows + warp;
+    const float * row = s_stage + s * (kPsStageBytes / 4) + warp * kPsBoxCols + 4 * lane;
+    float4 v[kPsSub][2];
+#pragma unroll
+    for (int q = 0; q < kPsSub; ++q) {
+      v[q][0] = *reinterpret_cast<const float4 *>(row + q * (kPsBoxBytes / 4));
+      v[q][1] = *reinterpret_cast<const float4 *>(row + q * (kPsBoxBytes / 4) + 128);
+    }
+    __syncwarp();
+    if (lane == 0) {mbar_arrive(&s_empty[s]);}
+    float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+    for (int q = 0; q < kPsSub; ++q) {
+      a0 = fmaf(w[q][0][0], v[q][0].x, a0); a1 = fmaf(w[q][1][0], v[q][1].x, a1);
+      a0 = fmaf(w[q][0][1], v[q][0].y, a0); a1 = fmaf(w[q][1][1], v[q][1].y, a1);
+      a0 = fmaf(w[q][0][2], v[q][0].z, a0); a1 = fmaf(w[q][1][2], v[q][1].z, a1);
+      a0 = fmaf(w[q][0][3], v[q][0].w, a0); a1 = fmaf(w[q][1][3], v[q][1].w, a1);
+    }
+    const float a = warp_sum(a0 + a1);
+    if (lane == 0 && t < T) {
+      const int c = (pl == 0 ? 0 : (pl == 1 ? 2 : 1)) * T + t;       // record order: vx, vy, wz
+      part[2 + c] = fmaf(__ldg(bufs.cs + c), ssum, a);               // sum_b w_b (cs + noise) = cs * s + sum_b w_b noise
+    }
   }
 }
 
