@@ -79,6 +79,7 @@ protected:
   mppi_config active_{};                       // what the device handle was created with
   std::string motion_model_name_;
   bool regenerate_noises_{false};
+  bool visualize_{false}, visualize_active_{false};
   float ackermann_min_turning_r_{0.2f};
   mppi_b200::Optimizer core_;
   geometry_msgs::msg::Pose last_pose_;

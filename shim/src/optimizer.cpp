@@ -56,6 +56,9 @@ void Optimizer::getParams()
   getParam(settings_.retry_attempt_limit, "retry_attempt_limit", 1);
   getParam(motion_model_name_, "motion_model", std::string("DiffDrive"));
   setMotionModel(motion_model_name_);
+  // The controller's own "visualize" switch (controller.cpp:41): the reference always holds generated_trajectories_ on the
+  // host; on the device the [B][T] planes are only written when somebody will read them (getGeneratedTrajectories).
+  getParam(visualize_, "visualize", false);
   // any dynamic parameter change ends here (parameters_handler.cpp:66-68 -> optimizer.cpp:88): the reference resets; the
   // shim additionally re-packs what the device holds by value (critic table, create-time settings)
   parameters_handler_->addPostCallback([this]() {setMotionModel(motion_model_name_); configureDevice(false);});
@@ -90,12 +93,19 @@ void Optimizer::configureDevice(bool force_create)
     core_.initialize(settings_, critics, robot);   // mppi_create + set_robot + set_critics; throws like the reference
     active_ = settings_.base;
     ++reconfigures_;
+    visualize_active_ = false;
   } else {
     if (mppi_set_robot(core_.handle(), &robot) != MPPI_OK ||
       mppi_set_critics(core_.handle(), critics.data(), static_cast<int32_t>(critics.size())) != MPPI_OK)
     {
       throw std::runtime_error(std::string("critic table rejected: ") + mppi_last_error(core_.handle()));
     }
+  }
+  if (visualize_ != visualize_active_) {
+    if (mppi_set_outputs(core_.handle(), visualize_ ? MPPI_WANT_TRAJECTORIES : 0u) != MPPI_OK) {
+      throw std::runtime_error(std::string("mppi_set_outputs: ") + mppi_last_error(core_.handle()));
+    }
+    visualize_active_ = visualize_;
   }
   reset();
 }
@@ -147,6 +157,7 @@ geometry_msgs::msg::TwistStamped Optimizer::evalControl(
 
 GeneratedTrajectories & Optimizer::getGeneratedTrajectories()   // optimizer.cpp:455-458
 {
+  if (!visualize_active_) {throw std::runtime_error("getGeneratedTrajectories: the visualize parameter is false, trajectories are not materialised");}
   generated_.batch_size = settings_.base.batch_size;
   generated_.time_steps = settings_.base.time_steps;
   core_.getGeneratedTrajectories(generated_.x, generated_.y, generated_.yaws);

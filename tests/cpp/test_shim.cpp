@@ -329,9 +329,10 @@ static void test_cycles()
       Scene sc(1.0 + 0.02 * k, 1.5 - 0.004 * k, -0.01 * k, 0.05 * k);
       compare_cycle(opt, o, sc, world, false, "yaml config");
     }
-    // the visualisation feed (controller.cpp:118-123)
-    auto & traj = opt.getGeneratedTrajectories();
-    EXPECT_EQ(traj.x.size(), size_t(2000) * 56);
+    // the visualisation feed (controller.cpp:118-123): only materialised when "visualize" is true (the YAML says false)
+    bool threw = false;
+    try {opt.getGeneratedTrajectories();} catch (const std::runtime_error &) {threw = true;}
+    EXPECT_TRUE(threw);
     EXPECT_EQ(opt.getOptimizedTrajectory().size(), size_t(56) * 3);
     // setSpeedLimit (controller.cpp:130-133 -> optimizer.cpp:428-453): 50 % of the base constraints
     opt.setSpeedLimit(50.0, true);
@@ -375,6 +376,25 @@ static void test_cycles()
       threw = std::string(e.what()) == "Optimizer fail to compute path";
     }
     EXPECT_TRUE(threw);
+  }
+  // ---- visualize: true -> the candidate trajectories are materialised and the getters feed TrajectoryVisualizer::add
+  {
+    auto node4 = std::make_shared<Node>("controller_server");
+    load_yaml_overrides(*node4);
+    node4->set_override("FollowPath.visualize", true);
+    node4->set_override("FollowPath.batch_size", 512);
+    sortham::ParametersHandler handler4(node4);
+    sortham::Optimizer opt4;
+    opt4.initialize(node4, "FollowPath", world.ros, &handler4);
+    FixedGoalChecker checker;
+    Scene sc(1.0, 1.5, 0.0, 0.1);
+    opt4.evalControl(sc.pose, sc.speed, sc.plan, sc.goal, &checker);
+    auto & traj = opt4.getGeneratedTrajectories();
+    EXPECT_EQ(traj.x.size(), size_t(512) * 56);
+    EXPECT_NEAR(traj.x[0], 1.0, 0.05);                     // first pose of the first trajectory sits next to the robot
+    const auto best = opt4.getOptimizedTrajectory();
+    EXPECT_EQ(best.size(), size_t(56) * 3);
+    EXPECT_NEAR(best[0], 1.0, 0.05);
   }
   // ---- an unknown motion model throws at configure time like the reference (optimizer.cpp:421-424)
   {
