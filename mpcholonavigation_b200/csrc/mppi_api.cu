@@ -99,6 +99,8 @@ struct mppi_handle
   float * d_costs{nullptr};
   float * d_partials{nullptr};
   CUtensorMap noise_map[3];           // TMA descriptors of the time-major noise planes (stream layout, weighted_sums_tma_kernel)
+  bool pdl_enabled{true};             // MPPI_PDL=0: ordinary (fully serialised) launches of the stream layout's post-rollout kernels
+  int scan_mode{0};                   // MPPI_SCAN=warp: experiment, warp-shuffle prefix scans in the tile kernels (not the parity path)
   bool ws_tma_enabled{true};             // MPPI_WS_TMA=0: the register-staged weighted-sums kernel (always used when B % 4 != 0)
   bool ws_tma_ok{false};                 // the TMA-fed weighted-sums kernel can run (B % 4 == 0, descriptors made)
   float * d_rank_partial{nullptr};
@@ -634,6 +636,7 @@ mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, un
   }
   p.spill_traj = ((h->want_mask & MPPI_WANT_TRAJECTORIES) || any_gate_open || mode == 1) ? 1 : 0;
   p.noise_tm = (h->stream_layout && mode == 0) ? 1 : 0;
+  p.scan_mode = h->scan_mode;
   p.need_furthest = (p.follow.idx >= 0 || p.angle.idx >= 0 || p.align.idx >= 0 || p.legacy.idx >= 0) ? 1 : 0;
   h->last = p;
   return MPPI_OK;
@@ -970,6 +973,21 @@ mppi_status launch_rollout(mppi_handle * h, int mode)
   return MPPI_OK;
 }
 
+// Launch with (pdl) or without programmatic stream serialisation: with it the kernel may start while its predecessor on
+// the stream drains and synchronises inside (pdl_wait in mppi_kernels.cuh).  Captured into the cycle's CUDA graph like
+// any other launch (programmatic dependency edge).
+template<typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args... args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // K3c of the stream layout: the TMA-fed kernel whenever the descriptors exist (B % 4 == 0), else the register-staged one
 int weighted_sums_chunks(const mppi_handle * h)
 {
@@ -984,11 +1002,11 @@ mppi_status launch_weighted_sums(mppi_handle * h)
     // row groups: about four waves of 3 resident blocks per SM (a short tail), at least two stages per block
     const int stages = (holonomic(h) ? 3 : 2) * ((h->T + kPsRows - 1) / kPsRows);
     const int gy = std::max(1, std::min(stages / 2, (12 * h->num_sms + chunks - 1) / chunks));
-    weighted_sums_tma_kernel<<<dim3(chunks, gy), kPsThreads, ps_smem_bytes(), h->stream>>>(
-      h->noise_map[0], h->noise_map[1], h->noise_map[2], dp, make_bufs(h, 0), h->T, h->B, holonomic(h) ? 1 : 0);
+    CUDA_TRY(h, launch_kernel(weighted_sums_tma_kernel, dim3(chunks, gy), dim3(kPsThreads), ps_smem_bytes(), h->stream, h->pdl_enabled,
+      h->noise_map[0], h->noise_map[1], h->noise_map[2], dp, make_bufs(h, 0), h->T, h->B, holonomic(h) ? 1 : 0));
   } else {
     const int gy = weighted_sums_row_groups(h->T, chunks);
-    weighted_sums_tm_kernel<<<dim3(chunks, gy), kWsThreads, 0, h->stream>>>(dp, make_bufs(h, 0));
+    CUDA_TRY(h, launch_kernel(weighted_sums_tm_kernel, dim3(chunks, gy), dim3(kWsThreads), 0, h->stream, h->pdl_enabled, dp, make_bufs(h, 0)));
   }
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
@@ -1002,12 +1020,15 @@ mppi_status launch_update(mppi_handle * h, int mode, int iteration)
     const int grid = std::min((h->B + kUpdThreads - 1) / kUpdThreads, 148 * 8);
     // the iteration that completes the result advances the packet epoch when the result leaves as packets
     const int bump = (stream_packets(h) && iteration + 1 == h->cfg.iteration_count) ? 1 : 0;
+    // programmatic dependent launch behind the rollout kernel (not behind an NCCL all-reduce: that is a library launch)
+    const bool pdl = h->pdl_enabled && !(h->nranks > 1 && !h->peer_mode);
+    const DevParams * dp = reinterpret_cast<const DevParams *>(h->d_params);
     if (h->B >= 131072) {
-      path_costs_tm_kernel<8><<<grid, kUpdThreads, k3_common_smem_bytes(), h->stream>>>(
-        reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, mode), iteration, bump);
+      CUDA_TRY(h, launch_kernel(path_costs_tm_kernel<8>, dim3(grid), dim3(kUpdThreads), k3_common_smem_bytes(), h->stream, pdl,
+        dp, make_bufs(h, mode), iteration, bump));
     } else {
-      path_costs_tm_kernel<5><<<grid, kUpdThreads, k3_common_smem_bytes(), h->stream>>>(
-        reinterpret_cast<const DevParams *>(h->d_params), make_bufs(h, mode), iteration, bump);
+      CUDA_TRY(h, launch_kernel(path_costs_tm_kernel<5>, dim3(grid), dim3(kUpdThreads), k3_common_smem_bytes(), h->stream, pdl,
+        dp, make_bufs(h, mode), iteration, bump));
     }
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
@@ -1066,17 +1087,17 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
       // exchange 2 over peer memory, fused with the local merge before it and the cross-rank merge after it
       if (prof) {CUDA_TRY(h, cudaEventRecord(h->pev[2], h->stream));}
       const bool merged_in_k3 = !h->stream_layout && !many;   // K3's last block already merged into rank_partial
-      merge_exchange_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
-        dp, merged_in_k3 ? h->d_rank_partial : h->d_partials, merged_in_k3 ? 1 : (h->stream_layout ? chunks : h->upd_blocks), stride,
-        make_bufs(h, 0));
+      CUDA_TRY(h, launch_kernel(merge_exchange_finalize_kernel, dim3(merge_grid), dim3(kUpdThreads), 0, h->stream,
+        h->pdl_enabled && h->stream_layout, dp, merged_in_k3 ? h->d_rank_partial : h->d_partials,
+        merged_in_k3 ? 1 : (h->stream_layout ? chunks : h->upd_blocks), stride, make_bufs(h, 0)));
       CUDA_TRY(h, cudaGetLastError());
       h->launches++;
     } else {
       if (h->stream_layout || many) {
         // too many partial records for a serial merge in K3's last block (or the stream layout): merge in parallel
-        merge_finalize_kernel<<<merge_grid, kUpdThreads, 0, h->stream>>>(
+        CUDA_TRY(h, launch_kernel(merge_finalize_kernel, dim3(merge_grid), dim3(kUpdThreads), 0, h->stream, h->pdl_enabled && h->stream_layout,
           dp, h->d_partials, h->stream_layout ? chunks : h->upd_blocks, stride, make_bufs(h, 0), h->nranks > 1 ? 0 : 1, h->d_rank_partial,
-          (stream_packets(h) && it + 1 == h->cfg.iteration_count) ? h->h_res : nullptr);
+          (stream_packets(h) && it + 1 == h->cfg.iteration_count) ? h->h_res : nullptr));
         CUDA_TRY(h, cudaGetLastError());
         h->launches++;
       }
@@ -1888,6 +1909,8 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   if (const char * e = std::getenv("MPPI_ZERO_COPY")) {h->zero_copy_enabled = std::atoi(e) != 0;}
   if (const char * e = std::getenv("MPPI_COOP")) {h->coop_launch = std::atoi(e) != 0;}
   if (const char * e = std::getenv("MPPI_STREAM_PACKETS")) {h->packets_enabled = std::atoi(e) != 0;}
+  if (const char * e = std::getenv("MPPI_PDL")) {h->pdl_enabled = std::atoi(e) != 0;}
+  if (const char * e = std::getenv("MPPI_SCAN")) {h->scan_mode = std::strcmp(e, "warp") == 0 ? 1 : 0;}
   if (const char * e = std::getenv("MPPI_WS_TMA")) {h->ws_tma_enabled = std::atoi(e) != 0;}
   {
     // batches too small to fill the GPU with one thread per trajectory keep the latency-oriented tile kernel

@@ -33,6 +33,13 @@
 namespace mppi
 {
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// may start while its predecessor on the stream is still draining; it runs the part of its prologue that does not read the
+// predecessor's results (record and path tables into shared memory, mbarrier set-up, the first TMA loads of the static noise
+// planes) and then waits.  pdl_wait() returns at once in a kernel that was launched the ordinary way.
+__device__ __forceinline__ void pdl_launch_dependents() {asm volatile ("griddepcontrol.launch_dependents;" ::: "memory");}
+__device__ __forceinline__ void pdl_wait() {asm volatile ("griddepcontrol.wait;" ::: "memory");}
+
 struct DevBuffers
 {
   const float * in_a;   // mode 0: noise vx | mode 1,2: state vx      [B][T]
@@ -462,8 +469,32 @@ __device__ __forceinline__ void rollout_tile_body(
     if (!use_vy) {pvy = 0.0f;}
   }
 
+  // ---- P2 (experiment, MPPI_SCAN=warp): the same cumsum as a warp-shuffle inclusive scan ALONG THE HORIZON (lane = time
+  //      step, 32 steps per pass, carry between passes), trajectories dealt to the warps.  This is what north_star item (2)
+  //      names; it re-associates the fp32 sums, so poses - and with them costmap cells - can differ from the reference's
+  //      sequential order.  Measured and rejected for the parity path (profiles/r02_scan_experiment.json).
+  const bool warp_scan = mode == 0 && p.scan_mode != 0;
+  if (warp_scan) {
+    const float yaw0 = p.yaw0;
+    for (int r = seg; r < kTile && b0 + r < B; r += S) {
+      float carry = -0.0f;
+      for (int c0 = 0; c0 < T; c0 += 32) {
+        const int t = c0 + lane;
+        float term = 0.0f;
+        if (t < T) {term = __fmul_rn(t == 0 ? s_v0[2 * kTile + r] : s_cwz[(t - 1) * kPad + r], dt);}
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const float up = __shfl_up_sync(0xffffffffu, term, d);
+          if (lane >= d) {term = __fadd_rn(up, term);}
+        }
+        const float v = __fadd_rn(carry, term);
+        if (t < T) {s_yaw[t * kPad + r] = __fadd_rn(v, yaw0);}
+        carry = __shfl_sync(0xffffffffu, v, 31);
+      }
+    }
+  }
   // ---- P2: yaw = cumsum(wz * dt) + yaw0, sequential in t (optimizer.cpp:319-320)
-  if (mode != 2 && seg == 0 && live) {
+  if (mode != 2 && seg == 0 && live && !warp_scan) {
     // chunks of 8: the eight loads are independent (pipelined), only the eight adds form the carried chain
     const float yaw0 = p.yaw0;
     float acc = -0.0f;                       // (-0) + x == x bit for bit: the first element of the cumsum is the term itself
@@ -576,7 +607,30 @@ __device__ __forceinline__ void rollout_tile_body(
   if (mode != 2) {
     __syncthreads();
     // ---- P4: x = pose.x (double) + cumsum(dx*dt) (float), sequential in t (optimizer.cpp:339-342)
-    if (live && seg < 2) {
+    if (warp_scan) {
+      // experiment (see P2): x and y as warp-shuffle scans along the horizon
+      for (int r = seg; r < kTile && b0 + r < B; r += S) {
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+          float * plane = pl == 0 ? s_x : s_y;
+          const double origin = pl == 0 ? p.pose_x : p.pose_y;
+          float carry = -0.0f;
+          for (int c0 = 0; c0 < T; c0 += 32) {
+            const int t = c0 + lane;
+            float term = t < T ? plane[t * kPad + r] : 0.0f;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const float up = __shfl_up_sync(0xffffffffu, term, d);
+              if (lane >= d) {term = __fadd_rn(up, term);}
+            }
+            const float v = __fadd_rn(carry, term);
+            if (t < T) {plane[t * kPad + r] = static_cast<float>(origin + static_cast<double>(v));}
+            carry = __shfl_sync(0xffffffffu, v, 31);
+          }
+        }
+      }
+    }
+    if (live && seg < 2 && !warp_scan) {
       const bool do_x = seg == 0, do_y = (S > 1) ? (seg == 1) : true;
       // one plane per warp (x: warp 0, y: warp 1), chunks of 8 as above; the fp64 pose add is off the carried chain
       auto scan_plane = [&](float * plane, const double origin) {
@@ -923,6 +977,7 @@ __device__ __forceinline__ void rollout_score_stream_body(
   extern __shared__ float smem[];
   const int tid = threadIdx.x;
   const int nthr = blockDim.x;
+  pdl_launch_dependents();   // the path-cost kernel behind this one may stage its tables while this grid drains
   float * s_hot = smem;
   load_hot_params(s_hot, P, tid, nthr);
   __syncthreads();
@@ -1369,6 +1424,30 @@ __device__ __forceinline__ void k3_preamble(
   float * s_hot = smem;
   const int N = Pg->N;              // read straight from the record: the path copies need not wait for the barrier
   load_hot_params(s_hot, Pg, tid, nthr);
+  const DevParams * P = reinterpret_cast<const DevParams *>(s_hot);
+  const float * tail = reinterpret_cast<const float *>(Pg + 1);
+  // record tail layout (build_params): x[N] y[N] yaw[N] D[N] | valid[n16] flags[n16] follow_idx[N] (uint16)
+  const int n16 = ((N + 15) / 16) * 16;
+  path.x = tail; path.y = tail + N; path.yaw = tail + 2 * N;
+  const uint8_t * g_valid = reinterpret_cast<const uint8_t *>(tail + 4 * N);
+  const uint8_t * g_flags = g_valid + n16;
+  const uint16_t * g_follow = reinterpret_cast<const uint16_t *>(g_valid + 2 * n16);
+  float * s_D = s_hot + kHotFloats;
+  float * s_px = s_D + MPPI_MAX_PATH_POINTS, * s_py = s_px + MPPI_MAX_PATH_POINTS;
+  uint8_t * s_valid = reinterpret_cast<uint8_t *>(s_py + MPPI_MAX_PATH_POINTS);
+  uint8_t * s_flags = s_valid + MPPI_MAX_PATH_POINTS;
+  uint16_t * s_follow = reinterpret_cast<uint16_t *>(s_flags + MPPI_MAX_PATH_POINTS);
+  path.s_D = s_D; path.s_x = s_px; path.s_y = s_py; path.s_valid = s_valid;
+  {
+    const float * g_D = tail + 3 * N;
+    for (int j = tid; j < N; j += nthr) {
+      s_D[j] = __ldg(g_D + j); s_px[j] = __ldg(path.x + j); s_py[j] = __ldg(path.y + j);
+      s_valid[j] = __ldg(g_valid + j); s_flags[j] = __ldg(g_flags + j); s_follow[j] = __ldg(g_follow + j);
+    }
+  }
+  // everything above is the cycle's upload (complete before the rollout kernel started); what follows reads the rollout
+  // kernel's reductions: under a programmatic dependent launch this is where the block waits for it
+  pdl_wait();
   if (tid < kMaxCritics) {s_any_ok[tid] = st->any_ok[tid];}
   if (tid == 32) {s_state[0] = st->furthest_candidate; s_state[1] = st->furthest;}
   if (tid == 33) {s_state[2] = static_cast<unsigned>(st->furthest_set); s_state[3] = static_cast<unsigned>(st->fail_flag);}
@@ -1395,27 +1474,6 @@ __device__ __forceinline__ void k3_preamble(
     __syncthreads();
     if (tid < kWords) {
       if (tid == 0) {s_state[0] = s_x1[0];} else {s_any_ok[tid - 1] = s_x1[tid];}
-    }
-  }
-  const DevParams * P = reinterpret_cast<const DevParams *>(s_hot);
-  const float * tail = reinterpret_cast<const float *>(Pg + 1);
-  // record tail layout (build_params): x[N] y[N] yaw[N] D[N] | valid[n16] flags[n16] follow_idx[N] (uint16)
-  const int n16 = ((N + 15) / 16) * 16;
-  path.x = tail; path.y = tail + N; path.yaw = tail + 2 * N;
-  const uint8_t * g_valid = reinterpret_cast<const uint8_t *>(tail + 4 * N);
-  const uint8_t * g_flags = g_valid + n16;
-  const uint16_t * g_follow = reinterpret_cast<const uint16_t *>(g_valid + 2 * n16);
-  float * s_D = s_hot + kHotFloats;
-  float * s_px = s_D + MPPI_MAX_PATH_POINTS, * s_py = s_px + MPPI_MAX_PATH_POINTS;
-  uint8_t * s_valid = reinterpret_cast<uint8_t *>(s_py + MPPI_MAX_PATH_POINTS);
-  uint8_t * s_flags = s_valid + MPPI_MAX_PATH_POINTS;
-  uint16_t * s_follow = reinterpret_cast<uint16_t *>(s_flags + MPPI_MAX_PATH_POINTS);
-  path.s_D = s_D; path.s_x = s_px; path.s_y = s_py; path.s_valid = s_valid;
-  {
-    const float * g_D = tail + 3 * N;
-    for (int j = tid; j < N; j += nthr) {
-      s_D[j] = __ldg(g_D + j); s_px[j] = __ldg(path.x + j); s_py[j] = __ldg(path.y + j);
-      s_valid[j] = __ldg(g_valid + j); s_flags[j] = __ldg(g_flags + j); s_follow[j] = __ldg(g_follow + j);
     }
   }
   MPPI_TRACE_AT(24);
@@ -1645,6 +1703,7 @@ __device__ __forceinline__ void path_costs_tm_body(const DevParams * __restrict_
   __shared__ float s_red[kUpdThreads / 32];
   __shared__ unsigned sc_last;
   const int tid = threadIdx.x;
+  pdl_launch_dependents();   // the weighted-sums kernel may set up its ring and request its first noise rows meanwhile
   K3Path path;
   k3_preamble(smem, Pg, bufs.st, bufs.peer, iteration, tid, kUpdThreads, path, &dec);
   const DevParams * P = reinterpret_cast<const DevParams *>(smem);
@@ -2469,6 +2528,8 @@ constexpr int kWsChunk = 32 * 4 * kWsVec;   // 1024 trajectories per block
 __device__ __forceinline__ void weighted_sums_tm_body(const DevParams * __restrict__ Pg, const DevBuffers & bufs)
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
   const int T = Pg->T, B = Pg->B;
   const float inv_temp = 1.0f / Pg->temperature;
   const float gm = bufs.st->global_min;
@@ -2628,6 +2689,7 @@ __global__ void __launch_bounds__(kPsThreads) weighted_sums_tma_kernel(
   const int n_all = (holonomic ? 3 : 2) * boxes_per_plane;
   const int per_y = (n_all + static_cast<int>(gridDim.y) - 1) / static_cast<int>(gridDim.y);
   const int box_begin = blockIdx.y * per_y, n_boxes = max(0, min(n_all, box_begin + per_y) - box_begin);
+  pdl_launch_dependents();
 
   if (tid == kPsConsumers) {
     for (int s = 0; s < kPsStages; ++s) {mbar_init(&s_full[s], 1u); mbar_init(&s_empty[s], kPsConsumers / 32);}
@@ -2652,6 +2714,9 @@ __global__ void __launch_bounds__(kPsThreads) weighted_sums_tma_kernel(
     return;
   }
   // ---- consumers: softmax weights of the chunk; lane owns columns q * 256 + j * 128 + 4 lane + {0..3}, q < 4, j < 2
+  //      (the noise planes are static, the costs and their minimum are the path-cost kernel's: wait for it here, with the
+  //       first stages of the ring already in flight)
+  pdl_wait();
   const float inv_temp = 1.0f / Pg->temperature;
   const float gm = bufs.st->global_min;
   float w[kPsSub][2][4];
@@ -2807,6 +2872,7 @@ __global__ void __launch_bounds__(kUpdThreads) merge_finalize_kernel(
   float * __restrict__ dst, uint2 * host_res)
 {
   // host_res: the tag is the packet epoch the path-cost kernel in front of this one advanced
+  pdl_wait();
   merge_finalize_body(Pg, parts, n, stride, bufs, finalize, dst, host_res, host_res ? ld_volatile_u32(bufs.epoch) : 0u);
 }
 
@@ -2822,6 +2888,7 @@ __global__ void __launch_bounds__(kUpdThreads) merge_exchange_finalize_kernel(
   __shared__ float s_e[kMergeCached];
   const PeerComm & pc = bufs.peer;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait();
   const int T = Pg->T;
   const float inv_temp = 1.0f / Pg->temperature;
   const unsigned tag = ld_volatile_u32(pc.seq) + 1u;

@@ -47,11 +47,29 @@ def test_default_arm_line_on_the_gpu():
     d = _run("--steps", "30", "--warmup", "3")
     assert BASE_KEYS | {"roofline", "cpu_baseline", "clocks", "gpu_launches", "latency_ms"} <= set(d)
     assert d["n_gpus"] == 1 and d["steps"] == 30 and d["dtype"] == "f32" and d["scaling"] == "weak"
+    assert d["config"]["workload"] == "omni_1000x56"
     roof = d["roofline"]
-    assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and 0 < roof["frac"] < 1
+    assert roof["bound"] in ("hbm", "issue") and 0 < roof["frac"] < 1
     assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9
     assert d["gpu_launches"] == 30                      # one fused kernel per optimize()
     assert d["e2e"]["h2d_bytes_per_step"] > 10000 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert d["e2e"]["value"] < d["value"]               # end to end includes the copies and the host
     assert d["cpu_baseline"]["value"] < d["e2e"]["value"]
     assert d["latency_ms"]["e2e_p50"] < 0.3             # north_star: 1000 x 56 under 0.3 ms per optimize()
+    # the other BASELINE configs ride in the same line, measured in the same process, each with its in-run oracle check
+    for name in ("obstacles_16384x56", "sharded_262144x100", "robots_256"):
+        rec = d[name]
+        assert "error" not in rec, rec
+        assert rec["ms_per_step"] > 0 and rec["e2e"]["value"] > 0 and "roofline" in rec and "cpu_baseline" in rec
+    assert d["sharded_262144x100"]["parity"]["status"] == "ok"
+    assert d["robots_256"]["parity"]["status"] == "ok"
+
+
+def test_reference_arm_prints_the_same_config_object():
+    """same_config / warmup_match of the driver: the reference arm echoes the GPU arm's config and honours --warmup"""
+    import bench
+    from mpcholonavigation_b200 import scenarios
+    sc = scenarios.config1()
+    want = bench.make_config("omni_1000x56", sc, "injected", 1, "peer", True)
+    d = _run("--impl", "reference", "--steps", "3", "--warmup", "7")
+    assert d["config"] == want and d["warmup"] == 7
