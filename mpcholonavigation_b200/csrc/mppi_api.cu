@@ -137,6 +137,8 @@ struct mppi_handle
   cudaStream_t own_stream{nullptr};       // a follower's own stream while it borrows the leader's
   mppi_handle * ev_src{nullptr};          // whose ev0 / ev1 bracket the cycle in flight (the leader's after a batched launch)
   std::vector<mppi_handle *> batch_group; // leader only, in bind order
+  cudaStream_t copy_stream{nullptr};      // leader only (stream-layout group): the chunk uploads ride here, beside the previous chunk's kernels
+  cudaEvent_t ev_upload[8]{};             // leader only: upload of chunk c done (c modulo 8)
   FusedJob * h_jobs{nullptr};             // leader only: job table, pinned ...
   FusedJob * d_jobs{nullptr};             // ... and its device copy (re-sent only when an entry changes)
   std::vector<char> jobs_sent;            // what the device copy holds
@@ -1023,7 +1025,14 @@ mppi_status launch_update(mppi_handle * h, int mode, int iteration)
     // programmatic dependent launch behind the rollout kernel (not behind an NCCL all-reduce: that is a library launch)
     const bool pdl = h->pdl_enabled && !(h->nranks > 1 && !h->peer_mode);
     const DevParams * dp = reinterpret_cast<const DevParams *>(h->d_params);
-    if (h->B >= 131072) {
+    static const int k3a_blocks = std::getenv("MPPI_K3A_BLOCKS") ? std::atoi(std::getenv("MPPI_K3A_BLOCKS")) : 0;   // experiment
+    if (k3a_blocks == 6) {
+      CUDA_TRY(h, launch_kernel(path_costs_tm_kernel<6>, dim3(std::min(grid, 148 * 6)), dim3(kUpdThreads), k3_common_smem_bytes(), h->stream, pdl,
+        dp, make_bufs(h, mode), iteration, bump));
+    } else if (k3a_blocks == 4) {
+      CUDA_TRY(h, launch_kernel(path_costs_tm_kernel<4>, dim3(std::min(grid, 148 * 4)), dim3(kUpdThreads), k3_common_smem_bytes(), h->stream, pdl,
+        dp, make_bufs(h, mode), iteration, bump));
+    } else if (h->B >= 131072 && k3a_blocks != 5) {
       CUDA_TRY(h, launch_kernel(path_costs_tm_kernel<8>, dim3(grid), dim3(kUpdThreads), k3_common_smem_bytes(), h->stream, pdl,
         dp, make_bufs(h, mode), iteration, bump));
     } else {
@@ -1448,6 +1457,12 @@ void batch_unbind_group(mppi_handle * leader)
   if (!leader) {return;}
   cudaSetDevice(leader->device);
   cudaStreamSynchronize(leader->stream);
+  if (leader->copy_stream) {
+    cudaStreamSynchronize(leader->copy_stream);
+    cudaStreamDestroy(leader->copy_stream);
+    leader->copy_stream = nullptr;
+    for (auto & e : leader->ev_upload) {if (e) {cudaEventDestroy(e); e = nullptr;}}
+  }
   std::vector<mppi_handle *> group = leader->batch_group;
   for (mppi_handle * m : group) {
     if (m != leader && m->own_stream) {m->stream = m->own_stream; m->own_stream = nullptr;}
@@ -1634,9 +1649,14 @@ mppi_status batch_stream_launch(mppi_handle * L, mppi_handle ** hs, int c0, int 
   }
   if (first && L->timing) {CUDA_TRY(L, cudaEventRecord(L->ev0, L->stream));}
   if (with_upload) {
+    // the chunk's slices travel on the group's copy stream, i.e. beside the kernels of the previous chunk (the slices of
+    // different chunks are disjoint; the previous STEP's kernels are done: its results have been delivered)
     const size_t off = L->arena_slice * static_cast<size_t>(c0);
+    cudaEvent_t ev = L->ev_upload[(c0 / std::max(n, 1)) & 7];
     CUDA_TRY(L, cudaMemcpy2DAsync(L->arena_d + off, L->arena_slice, L->arena_h + off, L->arena_slice, max_used, n,
-      cudaMemcpyHostToDevice, L->stream));
+      cudaMemcpyHostToDevice, L->copy_stream));
+    CUDA_TRY(L, cudaEventRecord(ev, L->copy_stream));
+    CUDA_TRY(L, cudaStreamWaitEvent(L->stream, ev, 0));
   }
   for (int i = 0; i < n; ++i) {
     mppi_handle * h = hs[i];
@@ -2279,6 +2299,8 @@ mppi_status mppi_batch_bind(mppi_handle ** hs, int32_t n)
     L->arena_slice = (kParamsCapacity + 256 + cap + 255) & ~static_cast<size_t>(255);
     CUDA_TRY(L, cudaHostAlloc(&L->arena_h, L->arena_slice * n, cudaHostAllocMapped | cudaHostAllocPortable));
     CUDA_TRY(L, cudaMalloc(&L->arena_d, L->arena_slice * n));
+    CUDA_TRY(L, cudaStreamCreateWithFlags(&L->copy_stream, cudaStreamNonBlocking));
+    for (auto & e : L->ev_upload) {CUDA_TRY(L, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));}
   }
   for (int i = 0; i < n; ++i) {
     mppi_handle * h = hs[i];

@@ -254,6 +254,22 @@ __device__ __forceinline__ void floor_magic(float q, int & i, float & frac)
   frac = __fsub_rn(q, __fsub_rn(t, 12582912.0f));
 }
 
+// The fp32 half of world_to_cell_fast on its own: the candidate cell and whether it is certain.  The stream kernel
+// evaluates it for the four poses of a chunk and takes ONE branch to the fp64 path when any of them is uncertain
+// (~1e-4 of the poses), instead of one branch per pose.
+__device__ __forceinline__ int world_to_cell_try(float xf, float yf, const CellGrid & cg, bool & sure)
+{
+  const float qx = __fmul_rn(__fsub_rn(xf, cg.oxf), cg.invf);
+  const float qy = __fmul_rn(__fsub_rn(yf, cg.oyf), cg.invf);
+  int mx, my;
+  float fx, fy;
+  floor_magic(qx, mx, fx);
+  floor_magic(qy, my, fy);
+  sure = fabsf(__fsub_rn(fx, 0.5f)) < cg.half_minus_eps_x && fabsf(__fsub_rn(fy, 0.5f)) < cg.half_minus_eps_y;
+  if (static_cast<unsigned>(mx) >= cg.size_x || static_cast<unsigned>(my) >= cg.size_y) {return -1;}
+  return my * static_cast<int>(cg.size_x) + mx;
+}
+
 __device__ __forceinline__ int world_to_cell_fast(float xf, float yf, const CellGrid & cg, const double * __restrict__ geom)
 {
   const float qx = __fmul_rn(__fsub_rn(xf, cg.oxf), cg.invf);

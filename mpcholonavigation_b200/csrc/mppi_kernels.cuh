@@ -1093,11 +1093,25 @@ __device__ __forceinline__ void rollout_score_stream_body(
       }
       // ---- phase E: costmap cell of every pose of the chunk and its byte, loads issued together
       int cell[kStreamChunk], pcost[kStreamChunk];
+      bool costed = false;   // some pose of the chunk needs the obstacle-type critics' attention
       if (need_cell) {
+        bool all_sure = true;
 #pragma unroll
-        for (int u = 0; u < kStreamChunk; ++u) {cell[u] = world_to_cell_fast(px[u], py[u], cg, &p.res);}
+        for (int u = 0; u < kStreamChunk; ++u) {
+          bool sure;
+          cell[u] = world_to_cell_try(px[u], py[u], cg, sure);
+          all_sure = all_sure && sure;
+        }
+        if (!all_sure) {   // one branch per chunk: the reference's own fp64 arithmetic decides (bit-exact either way)
 #pragma unroll
-        for (int u = 0; u < kStreamChunk; ++u) {pcost[u] = cell[u] < 0 ? NO_INFORMATION : __ldg(cm + cell[u]);}
+          for (int u = 0; u < kStreamChunk; ++u) {cell[u] = world_to_cell_fast(px[u], py[u], cg, &p.res);}
+        }
+        int any = 0;
+#pragma unroll
+        for (int u = 0; u < kStreamChunk; ++u) {pcost[u] = cell[u] < 0 ? NO_INFORMATION : __ldg(cm + cell[u]); any |= pcost[u];}
+        // free space under every pose of the chunk (the common case): nothing for Cost / Obstacles to do - unless the
+        // Obstacles critic checks the footprint at every pose (no inflation layer: possibly_inscribed_cost < 1)
+        costed = any != 0 || want_cells || (ob_on && ob_fp && ob_pic < 1.0f);
       }
       // ---- phase F: the critics, in step order (collision short-circuits are order dependent)
 #pragma unroll
@@ -1137,7 +1151,7 @@ __device__ __forceinline__ void rollout_score_stream_body(
             a_goal += sqrt_approx(ddx * ddx + ddy * ddy);
           }
           if (gang_on) {a_gang += static_cast<float>(fabs(normalize_angle_d(static_cast<double>(__fsub_rn(goal_yaw, yaw)))));}
-          if (need_cell) {
+          if (costed) {
             if (want_cells && live) {bufs.spill_cells[g] = cell[u];}
             const int pose_cost = pcost[u];
             int fp_cost = -1;
