@@ -1,5 +1,9 @@
 """The two exchanges of a sharded optimize(), stated in numpy.
 
+SPECIFICATION / TEST SUPPORT, not product code: the product does these exchanges inside its kernels (NVLink peer
+mailboxes) or with NCCL (mppi_api.cu); tests/test_sharding_gloo.py runs this numpy statement at world_size 2 over gloo
+against the unsharded oracle, which is what the device protocol is checked against.
+
 Trajectories are independent through rollout and scoring, so a batch shards over ranks by trajectory index.
 Two data-dependent global scalars split the pipeline:
 
