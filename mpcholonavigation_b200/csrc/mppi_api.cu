@@ -722,6 +722,8 @@ DevBuffers make_bufs(mppi_handle * h, int mode)
   b.epoch = h->d_fepoch;
   // sticky "a bounded poll gave up" word in pinned host memory, behind the result packets (raise_comm_error)
   b.host_err = h->h_res ? reinterpret_cast<unsigned *>(h->h_res + 3 * static_cast<size_t>(h->T) + 9) : nullptr;
+  static const int k3_fast = std::getenv("MPPI_K3_FAST") ? std::atoi(std::getenv("MPPI_K3_FAST")) : 1;   // measurement switch
+  b.k3_fast = k3_fast;
   return b;
 }
 

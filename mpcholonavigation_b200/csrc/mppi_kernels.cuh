@@ -40,6 +40,12 @@ namespace mppi
 __device__ __forceinline__ void pdl_launch_dependents() {asm volatile ("griddepcontrol.launch_dependents;" ::: "memory");}
 __device__ __forceinline__ void pdl_wait() {asm volatile ("griddepcontrol.wait;" ::: "memory");}
 
+// shared-window addressing by 32-bit address (the tables a kernel reads with data-dependent indices: generic pointers make
+// the compiler rebuild the window base at every access)
+__device__ __forceinline__ unsigned smem_addr(const void * p) {return static_cast<unsigned>(__cvta_generic_to_shared(p));}
+__device__ __forceinline__ float lds_f32(unsigned a) {float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v;}
+__device__ __forceinline__ unsigned lds_u8(unsigned a) {unsigned v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v;}
+
 struct DevBuffers
 {
   const float * in_a;   // mode 0: noise vx | mode 1,2: state vx      [B][T]
@@ -73,6 +79,7 @@ struct DevBuffers
   uint2 * pk_out;       // [3T]           evalControl tail: the new sequence on its way from the owner tiles to tile 0
   unsigned * epoch;     // completed fused launches of this handle; the tag of the running launch is *epoch + 1
   unsigned * host_err;  // pinned host word (behind the result packets): a bounded poll gave up inside this handle's kernels
+  int k3_fast;          // the stream layout's path-cost kernel may take its lean per-trajectory total (MPPI_K3_FAST=0: never)
 };
 
 // A bounded poll timed out: sticky flag in device memory and, for the cycles whose result leaves as packets (no D2H of the
@@ -1689,6 +1696,121 @@ __device__ __forceinline__ float k3_trajectory_total(
   return total;
 }
 
+// out-of-line instance for path_costs_tm_body: the general total must not cost the lean one beside it registers
+__device__ __noinline__ float k3_trajectory_total_general(
+  int b, const DevParams * P, const K3Decisions & dec, const K3Path & path, const DevBuffers & bufs, int iteration)
+{
+  return k3_trajectory_total(b, P, dec, path, bufs, iteration);
+}
+
+// The same total for the usual case, at a third of the instructions: no per-critic rows requested, PathAlign without path
+// orientations, PathAlignLegacy / PathAngle not firing this pass (block-uniform conditions, decided once per block in
+// path_costs_tm_body).  `src` = where the term of list position q comes from this pass, one byte per position
+// (0 nothing, 1 K2's row, 2 PathFollow, 3 PathAlign), packed four to a word so that the unrolled loops index registers
+// statically.  PathAlign (path_align_critic.cpp:92-135): one monotone cursor is utils::findClosestPathPt's lower_bound
+// (utils.hpp:665-675) for every sample, the answer follows from the cursor and the previous answer by selects.
+__device__ __forceinline__ float k3_trajectory_total_fast(
+  int b, const DevParams * P, const K3Decisions & dec, const K3Path & path, const DevBuffers & bufs, int iteration, const unsigned (&src_w)[kMaxCritics / 4], const float inv_h)
+{
+  const int T = P->T, B = P->B;
+  const float * __restrict__ rows = bufs.crit_rows;
+  float row_v[kMaxCritics];
+#pragma unroll
+  for (int q = 0; q < kMaxCritics; ++q) {
+    const unsigned src = (src_w[q >> 2] >> (8 * (q & 3))) & 0xffu;
+    row_v[q] = src == 1u ? rows[static_cast<size_t>(q) * B + b] : 0.0f;
+  }
+  float total = iteration == 0 ? 0.0f : bufs.costs[b];
+  const size_t g = static_cast<size_t>(P->n_critics) * B + b;
+  const float gam0 = rows[g], gam1 = rows[g + B], gam2 = rows[g + 2 * static_cast<size_t>(B)];
+  float follow_term = 0.0f, align_term = 0.0f;
+  if (P->follow.on) {    // path_follow_critic.cpp:60-70
+    const float dx = bufs.end_xy[b] - path.s_x[dec.follow_idx];
+    const float dy = bufs.end_xy[B + b] - path.s_y[dec.follow_idx];
+    follow_term = add_pow(0.0f, P->follow.weight * sqrtf(dx * dx + dy * dy), P->follow.power);
+  }
+  if (dec.align_go) {
+    const int n = dec.furthest;
+    const int step = P->align_step;
+    const int n_s = (T + step - 1) / step;     // sampled poses p = 0, step, 2 step, ... < T
+    const float * __restrict__ sxp = bufs.samples_x + b;
+    const float * __restrict__ syp = bufs.samples_y + b;
+    // the path tables by shared-window address: D[j] at aD + 4 j, x[j] / y[j] one / two table pitches behind it, valid[j]
+    // at aV + j (k3_preamble's carve-up)
+    const unsigned aD = smem_addr(path.s_D), aV = smem_addr(path.s_valid);
+    constexpr unsigned kPitch = 4u * MPPI_MAX_PATH_POINTS;
+    const unsigned a_end = aD + 4u * static_cast<unsigned>(n), a_last = aD + 4u * static_cast<unsigned>(max(n - 1, 0));
+    unsigned a_c = aD;                         // address of D[c], c = lower_bound(D[0, n), distance): only ever moves forward
+    unsigned a_prev = aD;                      // address of D[previous answer]
+    float traj_d = 0.0f, summed = 0.0f, num = 0.0f;
+    float prev_x = sxp[0], prev_y = syp[0];
+    const float kInf = __int_as_float(0x7f800000);
+    auto sample = [&](const float Tx, const float Ty) {
+        const float ddx = __fsub_rn(Tx, prev_x), ddy = __fsub_rn(Ty, prev_y);
+        traj_d = __fadd_rn(traj_d, __fsqrt_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy))));
+        // lower_bound by a guess from the mean spacing of the path (exact for an evenly spaced path up to rounding), then
+        // corrected both ways against the table itself: D[c - 1] < distance <= D[c].  Any guess gives the same c; the two
+        // table entries that prove it are the ones the nearest-neighbour decision needs.
+        const unsigned a_g = aD + 4u * static_cast<unsigned>(__float2int_rd(__fmul_rn(traj_d, inv_h)) + 1);
+        const unsigned a_0 = a_c;              // lower_bound is monotone in the distance: never below the previous cursor
+        a_c = min(max(a_g, a_0), a_end);
+        float d_lo = a_c < a_end ? lds_f32(a_c) : kInf;                           // D[c]     (+inf at the end of the prefix)
+        float d_lm = a_c > aD ? lds_f32(a_c - 4u) : -kInf;                        // D[c - 1] (-inf in front of it)
+        while (d_lo < traj_d) {
+          a_c += 4u; d_lm = d_lo;
+          d_lo = a_c < a_end ? lds_f32(a_c) : kInf;
+        }
+        while (a_c > a_0 && d_lm >= traj_d) {
+          a_c -= 4u; d_lo = d_lm;
+          d_lm = a_c > aD ? lds_f32(a_c - 4u) : -kInf;
+        }
+        // findClosestPathPt over [init, n), init = the previous answer: 0 when the bound does not pass init, the last
+        // point when it runs off the prefix, else the nearer of the two neighbours
+        const unsigned a_near = __fsub_rn(traj_d, d_lm) < __fsub_rn(d_lo, traj_d) ? a_c - 4u : a_c;
+        const unsigned a_res = a_c <= a_prev ? aD : (a_c == a_end ? a_last : a_near);
+        a_prev = a_res;
+        const float ex = __fsub_rn(lds_f32(a_res + kPitch), Tx), ey = __fsub_rn(lds_f32(a_res + 2u * kPitch), Ty);
+        if (lds_u8(aV + ((a_res - aD) >> 2))) {
+          num = __fadd_rn(num, 1.0f);
+          // the distance itself only feeds the cost (1e-4 tolerance): one MUFU instead of the IEEE sequence
+          summed += sqrt_approx(ex * ex + ey * ey);
+        }
+        prev_x = Tx; prev_y = Ty;
+      };
+    constexpr int kBatch = 8;                  // sampled poses requested together (latency off the serial chain)
+    int k0 = 1;
+    unsigned o = static_cast<unsigned>(B);
+    for (; k0 + kBatch <= n_s; k0 += kBatch) {
+      float sx[kBatch], sy[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {sx[u] = sxp[o]; sy[u] = syp[o]; o += static_cast<unsigned>(B);}
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {sample(sx[u], sy[u]);}
+    }
+    for (; k0 < n_s; ++k0) {
+      const float Tx = sxp[o], Ty = syp[o];
+      o += static_cast<unsigned>(B);
+      sample(Tx, Ty);
+    }
+    const float cost = num > 0.0f ? __fdiv_rn(summed, num) : 0.0f;
+    align_term = add_pow(0.0f, __fmul_rn(cost, P->align.weight), P->align.power);
+  }
+#pragma unroll
+  for (int q = 0; q < kMaxCritics; ++q) {
+    const unsigned src = (src_w[q >> 2] >> (8 * (q & 3))) & 0xffu;
+    if (src != 0u) {
+      const float term = src == 1u ? row_v[q] : (src == 2u ? follow_term : align_term);
+      total = __fadd_rn(total, term);
+    }
+  }
+  // gamma term (optimizer.cpp:367-380): vx, then wz, then vy (holonomic)
+  total = __fadd_rn(total, __fmul_rn(P->gamma_vx, gam0));
+  total = __fadd_rn(total, __fmul_rn(P->gamma_wz, gam2));
+  if (P->holonomic) {total = __fadd_rn(total, __fmul_rn(P->gamma_vy, gam1));}
+  bufs.costs[b] = total;
+  return total;
+}
+
 // flags of the pass, published by the last block to finish
 __device__ __forceinline__ void k3_publish_flags(const DevParams * P, DevState * st, const K3Decisions & dec, float * out)
 {
@@ -1723,8 +1845,35 @@ __device__ __forceinline__ void path_costs_tm_body(const DevParams * __restrict_
   const DevParams * P = reinterpret_cast<const DevParams *>(smem);
   const int B = P->B, T = P->T;
   float m = 3.402823466e+38f;
-  for (int b = blockIdx.x * kUpdThreads + tid; b < B; b += gridDim.x * kUpdThreads) {
-    m = fminf(m, k3_trajectory_total(b, P, dec, path, bufs, iteration));
+  // block-uniform: the usual pass runs the lean total (k3_trajectory_total_fast), anything else the general one
+  const bool fast = bufs.k3_fast && P->mode == 0 && !P->want_critic_rows && !dec.legacy_go && !dec.angle_go && !(dec.align_go && P->align_use_yaw);
+  __shared__ unsigned s_srcw[kMaxCritics / 4];
+  if (tid < kMaxCritics / 4) {   // where the term of every list position comes from this pass, four positions to a word
+    unsigned v = 0u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = 4 * tid + i;
+      unsigned src = (q < P->n_critics && q <= dec.fail_at) ? P->src_base[q] : 0u;
+      if ((src == 3u && !dec.align_go) || src >= 4u) {src = 0u;}
+      v |= src << (8 * i);
+    }
+    s_srcw[tid] = v;
+  }
+  __syncthreads();
+  if (fast) {
+    unsigned src_w[kMaxCritics / 4];
+#pragma unroll
+    for (int w = 0; w < kMaxCritics / 4; ++w) {src_w[w] = s_srcw[w];}
+    // points per metre of the path: the start of the per-sample search in the arc-length prefix (efficiency only)
+    const float d_all = path.s_D[max(P->N - 1, 0)];
+    const float inv_h = d_all > 0.0f ? static_cast<float>(P->N - 1) / d_all : 0.0f;
+    for (int b = blockIdx.x * kUpdThreads + tid; b < B; b += gridDim.x * kUpdThreads) {
+      m = fminf(m, k3_trajectory_total_fast(b, P, dec, path, bufs, iteration, src_w, inv_h));
+    }
+  } else {
+    for (int b = blockIdx.x * kUpdThreads + tid; b < B; b += gridDim.x * kUpdThreads) {
+      m = fminf(m, k3_trajectory_total_general(b, P, dec, path, bufs, iteration));
+    }
   }
   m = warp_min(m);
   if ((tid & 31) == 0) {s_red[tid >> 5] = m;}
@@ -1757,7 +1906,7 @@ __device__ __forceinline__ void path_costs_tm_body(const DevParams * __restrict_
 
 template<int kMinBlocks>
 __global__ void __launch_bounds__(kUpdThreads, kMinBlocks) path_costs_tm_kernel(
-  const DevParams * __restrict__ Pg, DevBuffers bufs, int iteration, int bump_epoch)
+  const DevParams * __restrict__ Pg, const __grid_constant__ DevBuffers bufs, int iteration, int bump_epoch)
 {
   path_costs_tm_body(Pg, bufs, iteration, bump_epoch);
 }
