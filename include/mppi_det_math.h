@@ -58,25 +58,74 @@
 #define MPPI_PIO2_D2 6.123233995736766e-17 /* 0x1.1a62633145c07p-54 */
 #define MPPI_TWO_OVER_PI_D 0.6366197723675814
 
+/* v with its sign bit flipped where bit 31 of m is set (v -> -v exactly, zeros and NaNs included) */
+MPPI_HD float mppi_det_xor_sign(float v, uint32_t m)
+{
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(__float_as_uint(v) ^ (m & 0x80000000u));
+#else
+  union {float f; uint32_t u;} w;
+  w.f = v;
+  w.u ^= m & 0x80000000u;
+  return w.f;
+#endif
+}
+
+/* second half of the sincos: Cephes sinf/cosf kernels on the reduced argument |r| <= pi/4, then the quadrant */
+MPPI_HD void mppi_det_sincosf_reduced(float r, int32_t q, float * s_out, float * c_out)
+{
+  const float z = MPPI_FMUL(r, r);
+  float ps = MPPI_FFMA(-1.9515295891e-4f, z, 8.3321608736e-3f);
+  ps = MPPI_FFMA(ps, z, -1.6666654611e-1f);
+  const float sr = MPPI_FFMA(MPPI_FMUL(ps, z), r, r);
+  float pc = MPPI_FFMA(2.443315711809948e-5f, z, -1.388731625493765e-3f);
+  pc = MPPI_FFMA(pc, z, 4.166664568298827e-2f);
+  const float cr = MPPI_FFMA(MPPI_FMUL(pc, z), z, MPPI_FFMA(-0.5f, z, 1.0f));
+  /* quadrant fix-up, branch-free: q&3 = 0: (sr, cr)  1: (cr, -sr)  2: (-sr, -cr)  3: (-cr, sr).
+   * The swap is a select on bit 0; the signs are bit 1 of q (sine) and of q + 1 (cosine) moved onto the sign bit. */
+  {
+    const uint32_t uq = (uint32_t)q;
+    const float s0 = (uq & 1u) ? cr : sr;
+    const float c0 = (uq & 1u) ? sr : cr;
+    *s_out = mppi_det_xor_sign(s0, uq << 30);
+    *c_out = mppi_det_xor_sign(c0, (uq << 30) + 0x40000000u);
+  }
+}
+
+/* first half for |x| <= 1e5 (the caller guarantees the range): 3-term Cody-Waite reduction by pi/2 */
+MPPI_HD void mppi_det_reduce_small(float x, float * r_out, int32_t * q_out)
+{
+#if defined(__CUDA_ARCH__)
+  /* rintf + float->int without conversion instructions: adding 1.5 * 2^23 rounds (to nearest even, like rintf) the
+   * product to an integer that sits in the low mantissa bits; |x * 2/pi| < 2^16 here.  Same kf, same q. */
+  const float tm = __fadd_rn(MPPI_FMUL(x, MPPI_TWO_OVER_PI_F), 12582912.0f);
+  const float kf = __fsub_rn(tm, 12582912.0f);
+  *q_out = __float_as_int(tm) - 0x4B400000;
+#else
+  const float kf = rintf(MPPI_FMUL(x, MPPI_TWO_OVER_PI_F));
+  *q_out = (int32_t)kf;
+#endif
+  float r = MPPI_FFMA(-kf, MPPI_PIO2_C1, x);
+  r = MPPI_FFMA(-kf, MPPI_PIO2_C2, r);
+  *r_out = MPPI_FFMA(-kf, MPPI_PIO2_C3, r);
+}
+
+/* sin and cos of x for callers that have already checked |x| <= 1e5: the same bits as mppi_det_sincosf */
+MPPI_HD void mppi_det_sincosf_small(float x, float * s_out, float * c_out)
+{
+  float r;
+  int32_t q;
+  mppi_det_reduce_small(x, &r, &q);
+  mppi_det_sincosf_reduced(r, q, s_out, c_out);
+}
+
 /* sin and cos of x, both at once.  Deterministic across host and device. */
 MPPI_HD void mppi_det_sincosf(float x, float * s_out, float * c_out)
 {
   float r;
   int32_t q;
   if (fabsf(x) <= 1.0e5f) {
-#if defined(__CUDA_ARCH__)
-    /* rintf + float->int without conversion instructions: adding 1.5 * 2^23 rounds (to nearest even, like rintf) the
-     * product to an integer that sits in the low mantissa bits; |x * 2/pi| < 2^16 here.  Same kf, same q. */
-    const float tm = __fadd_rn(MPPI_FMUL(x, MPPI_TWO_OVER_PI_F), 12582912.0f);
-    const float kf = __fsub_rn(tm, 12582912.0f);
-    q = __float_as_int(tm) - 0x4B400000;
-#else
-    const float kf = rintf(MPPI_FMUL(x, MPPI_TWO_OVER_PI_F));
-    q = (int32_t)kf;
-#endif
-    r = MPPI_FFMA(-kf, MPPI_PIO2_C1, x);
-    r = MPPI_FFMA(-kf, MPPI_PIO2_C2, r);
-    r = MPPI_FFMA(-kf, MPPI_PIO2_C3, r);
+    mppi_det_reduce_small(x, &r, &q);
   } else if (fabsf(x) <= 2.0e9f) {
     const double xd = (double)x;
     const double kd = rint(MPPI_DMUL(xd, MPPI_TWO_OVER_PI_D));
@@ -89,21 +138,7 @@ MPPI_HD void mppi_det_sincosf(float x, float * s_out, float * c_out)
     r = 0.0f;
     q = 0;
   }
-  const float z = MPPI_FMUL(r, r);
-  /* Cephes sinf/cosf kernels on |r| <= pi/4 */
-  float ps = MPPI_FFMA(-1.9515295891e-4f, z, 8.3321608736e-3f);
-  ps = MPPI_FFMA(ps, z, -1.6666654611e-1f);
-  const float sr = MPPI_FFMA(MPPI_FMUL(ps, z), r, r);
-  float pc = MPPI_FFMA(2.443315711809948e-5f, z, -1.388731625493765e-3f);
-  pc = MPPI_FFMA(pc, z, 4.166664568298827e-2f);
-  const float cr = MPPI_FFMA(MPPI_FMUL(pc, z), z, MPPI_FFMA(-0.5f, z, 1.0f));
-  /* quadrant fix-up, branch-free: q&3 = 0: (sr, cr)  1: (cr, -sr)  2: (-sr, -cr)  3: (-cr, sr) */
-  {
-    const float s0 = (q & 1) ? cr : sr;
-    const float c0 = (q & 1) ? sr : cr;
-    *s_out = (q & 2) ? -s0 : s0;
-    *c_out = ((q + 1) & 2) ? -c0 : c0;
-  }
+  mppi_det_sincosf_reduced(r, q, s_out, c_out);
 }
 
 #endif  /* MPPI_DET_MATH_H_ */

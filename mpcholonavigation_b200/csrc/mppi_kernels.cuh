@@ -1036,7 +1036,8 @@ __device__ __forceinline__ void rollout_score_stream_body(
   float acc_yaw = -0.0f, acc_x = -0.0f, acc_y = -0.0f;
   float yaw_prev = yaw0;                 // cos/sin of step 0 use yaw0 (p.cos0 / p.sin0 are mppi_det_sincosf(yaw0) as well)
   float ex = 0.f, ey = 0.f;              // end pose
-  int next_sample = step > 0 ? 0 : T, sample_k = 0;
+  int next_sample = step > 0 ? 0 : T;
+  unsigned sample_o = 0u;               // element offset of the next PathAlign sample row
 
   // software pipeline of the noise rows: the chunk being processed was loaded one chunk ago.  32-bit element
   // offsets (the host guarantees (T + pad) * B < 2^32): one IMAD.WIDE per load instead of 64-bit arithmetic.
@@ -1050,16 +1051,28 @@ __device__ __forceinline__ void rollout_score_stream_body(
   }
   unsigned g = b;   // index of (t, b) in the time-major spills
 
-  auto chunk = [&](auto tail_tag, const int t0) {
+  auto chunk = [&](auto tail_tag, auto step_tag, const int t0) {
       constexpr bool kTail = decltype(tail_tag)::value;   // the last, partial chunk: steps t >= T are masked
+      constexpr bool kStepChunk = decltype(step_tag)::value;   // PathAlign samples every kStreamChunk-th pose (the usual step)
       const float * cs_t = s_cs + t0;
       // ---- phase A: noised controls of the chunk (noise_generator.cpp:71-73), then refill the pipeline
       float cx[kStreamChunk], cy[kStreamChunk], cw[kStreamChunk];
 #pragma unroll
       for (int u = 0; u < kStreamChunk; ++u) {
-        cx[u] = __fadd_rn(cs_t[u], qx[u]);
-        cy[u] = hol ? __fadd_rn(cs_t[Tp + u], qy[u]) : 0.0f;
-        cw[u] = __fadd_rn(cs_t[2 * Tp + u], qw[u]);
+        const float csx = cs_t[u], csw = cs_t[2 * Tp + u];
+        cx[u] = __fadd_rn(csx, qx[u]);
+        cw[u] = __fadd_rn(csw, qw[u]);
+        // gamma term (optimizer.cpp:365-380) while the control sequence is at hand; the padded steps of the last chunk
+        // carry a zero control sequence and zero noise rows: their terms are exact zeros
+        g_vx = fmaf(csx, __fsub_rn(cx[u], csx), g_vx);
+        g_wz = fmaf(csw, __fsub_rn(cw[u], csw), g_wz);
+        if (hol) {
+          const float csy = cs_t[Tp + u];
+          cy[u] = __fadd_rn(csy, qy[u]);
+          g_vy = fmaf(csy, __fsub_rn(cy[u], csy), g_vy);
+        } else {
+          cy[u] = 0.0f;
+        }
       }
       if (!kTail) {
 #pragma unroll
@@ -1078,9 +1091,16 @@ __device__ __forceinline__ void rollout_score_stream_body(
         yw[u] = __fadd_rn(acc_yaw, yaw0);
       }
       // ---- phase C: cos/sin of the lagged yaw (optimizer.cpp:322-329): independent across the chunk
+      //      one range test per chunk: yaw angles are small, the large-argument reduction is a branch never taken
+      bool small = true;
 #pragma unroll
-      for (int u = 0; u < kStreamChunk; ++u) {
-        mppi_det_sincosf(u == 0 ? yaw_prev : yw[u - 1], &sn[u], &cn[u]);
+      for (int u = 0; u < kStreamChunk; ++u) {small = small && fabsf(u == 0 ? yaw_prev : yw[u - 1]) <= 1.0e5f;}
+      if (small) {
+#pragma unroll
+        for (int u = 0; u < kStreamChunk; ++u) {mppi_det_sincosf_small(u == 0 ? yaw_prev : yw[u - 1], &sn[u], &cn[u]);}
+      } else {
+#pragma unroll
+        for (int u = 0; u < kStreamChunk; ++u) {mppi_det_sincosf(u == 0 ? yaw_prev : yw[u - 1], &sn[u], &cn[u]);}
       }
       // ---- phase D: x = pose.x + cumsum(dx * dt) (optimizer.cpp:331-342), sequential; fp64 add of the pose
       float px[kStreamChunk], py[kStreamChunk];
@@ -1120,7 +1140,7 @@ __device__ __forceinline__ void rollout_score_stream_body(
         // Obstacles critic checks the footprint at every pose (no inflation layer: possibly_inscribed_cost < 1)
         costed = any != 0 || want_cells || (ob_on && ob_fp && ob_pic < 1.0f);
       }
-      // ---- phase F: the critics, in step order (collision short-circuits are order dependent)
+      // ---- phase F1: the critics that do not look at the costmap; straight-line code, independent across the chunk
 #pragma unroll
       for (int u = 0; u < kStreamChunk; ++u) {
         const int t = t0 + u;
@@ -1128,15 +1148,6 @@ __device__ __forceinline__ void rollout_score_stream_body(
           const float svx = u == 0 ? vx : cx[u - 1];
           const float svy = u == 0 ? vy : cy[u - 1];
           const float swz = u == 0 ? wz : cw[u - 1];
-          const float yaw = yw[u];
-          // gamma term (optimizer.cpp:365-380)
-          const float csx = cs_t[u], csw = cs_t[2 * Tp + u];
-          g_vx = fmaf(csx, __fsub_rn(cx[u], csx), g_vx);
-          g_wz = fmaf(csw, __fsub_rn(cw[u], csw), g_wz);
-          if (hol) {
-            const float csy = cs_t[Tp + u];
-            g_vy = fmaf(csy, __fsub_rn(cy[u], csy), g_vy);
-          }
           if (con_on) {   // constraint_critic.cpp:49-52
             const float sgn = svx > 0.0f ? 1.0f : -1.0f;
             const float vel_total = sgn * sqrt_approx(svx * svx + svy * svy);
@@ -1157,9 +1168,18 @@ __device__ __forceinline__ void rollout_score_stream_body(
             const float ddy = static_cast<float>(static_cast<double>(py[u]) - p.goal_y);
             a_goal += sqrt_approx(ddx * ddx + ddy * ddy);
           }
-          if (gang_on) {a_gang += static_cast<float>(fabs(normalize_angle_d(static_cast<double>(__fsub_rn(goal_yaw, yaw)))));}
-          if (costed) {
-            if (want_cells && live) {bufs.spill_cells[g] = cell[u];}
+          if (gang_on) {a_gang += static_cast<float>(fabs(normalize_angle_d(static_cast<double>(__fsub_rn(goal_yaw, yw[u])))));}
+        }
+      }
+      // ---- phase F2: Cost / Obstacles, in step order (the collision short-circuits are order dependent); one branch
+      //      per chunk: skipped while every pose of the chunk sits in free space
+      if (costed) {
+#pragma unroll
+        for (int u = 0; u < kStreamChunk; ++u) {
+          const int t = t0 + u;
+          if (!kTail || t < T) {
+            const float yaw = yw[u];
+            if (want_cells && live) {bufs.spill_cells[g + static_cast<unsigned>(u) * static_cast<unsigned>(B)] = cell[u];}
             const int pose_cost = pcost[u];
             int fp_cost = -1;
             if (cost_on && !cost_hit && pose_cost >= 1) {   // cost_critic.cpp:139-162
@@ -1194,28 +1214,47 @@ __device__ __forceinline__ void rollout_score_stream_body(
               }
             }
           }
-          if (live) {
-            // every trajectory_point_step-th pose for PathAlign (K3); the usual step equals the chunk length
-            if (step_is_chunk ? (u == 0) : (t == next_sample)) {
-              const unsigned k = static_cast<unsigned>(sample_k) * B + b;
+        }
+      }
+      // ---- phase F3: what leaves the kernel per pose
+      if (live) {
+        if (kStepChunk) {
+          // every trajectory_point_step-th pose for PathAlign (K3); the usual step equals the chunk length: pose 0 of the chunk
+          const unsigned k = sample_o + b;
+          bufs.samples_x[k] = px[0]; bufs.samples_y[k] = py[0];
+          if (sample_yaw) {bufs.samples_yaw[k] = yw[0];}
+          sample_o += static_cast<unsigned>(B);
+        }
+#pragma unroll
+        for (int u = 0; u < kStreamChunk; ++u) {
+          const int t = t0 + u;
+          if (!kTail || t < T) {
+            if (!kStepChunk && t == next_sample) {
+              const unsigned k = sample_o + b;
               bufs.samples_x[k] = px[u]; bufs.samples_y[k] = py[u];
-              if (sample_yaw) {bufs.samples_yaw[k] = yaw;}
-              next_sample += step; sample_k++;
+              if (sample_yaw) {bufs.samples_yaw[k] = yw[u];}
+              next_sample += step; sample_o += static_cast<unsigned>(B);
             }
-            if (kSpill && spill) {bufs.spill_x[g] = px[u]; bufs.spill_y[g] = py[u]; bufs.spill_yaw[g] = yaw;}
-            if (kSpill && p.vis_b_step > 0 && t % p.vis_t_step == 0 && b % p.vis_b_step == 0) {
-              const int nt = (T + p.vis_t_step - 1) / p.vis_t_step;
-              const size_t k = static_cast<size_t>(t / p.vis_t_step) * p.vis_nb + b / p.vis_b_step;
-              bufs.vis_xy[k] = px[u]; bufs.vis_xy[static_cast<size_t>(nt) * p.vis_nb + k] = py[u];
+            if (kSpill) {
+              const unsigned gu = g + static_cast<unsigned>(u) * static_cast<unsigned>(B);
+              if (spill) {bufs.spill_x[gu] = px[u]; bufs.spill_y[gu] = py[u]; bufs.spill_yaw[gu] = yw[u];}
+              if (p.vis_b_step > 0 && t % p.vis_t_step == 0 && b % p.vis_b_step == 0) {
+                const int nt = (T + p.vis_t_step - 1) / p.vis_t_step;
+                const size_t k = static_cast<size_t>(t / p.vis_t_step) * p.vis_nb + b / p.vis_b_step;
+                bufs.vis_xy[k] = px[u]; bufs.vis_xy[static_cast<size_t>(nt) * p.vis_nb + k] = py[u];
+              }
             }
-          }
-          g += B;
-          if (kTail) {
-            if (t == T - 1) {ex = px[u]; ey = py[u];}
-          } else if (u == kStreamChunk - 1) {
-            ex = px[u]; ey = py[u];
           }
         }
+      }
+      g += static_cast<unsigned>(kStreamChunk) * static_cast<unsigned>(B);
+      if (kTail) {
+#pragma unroll
+        for (int u = 0; u < kStreamChunk; ++u) {
+          if (t0 + u == T - 1) {ex = px[u]; ey = py[u];}
+        }
+      } else {
+        ex = px[kStreamChunk - 1]; ey = py[kStreamChunk - 1];
       }
       // predict(): state velocities of the next step are the controls of this one (motion_models.hpp:53-66)
       vx = cx[kStreamChunk - 1]; vy = cy[kStreamChunk - 1]; wz = cw[kStreamChunk - 1];
@@ -1223,8 +1262,13 @@ __device__ __forceinline__ void rollout_score_stream_body(
     };
 
   const int T_full = (T / kStreamChunk) * kStreamChunk;
-  for (int t0 = 0; t0 < T_full; t0 += kStreamChunk) {chunk(std::false_type{}, t0);}
-  if (T_full < T) {chunk(std::true_type{}, T_full);}
+  if (step_is_chunk) {
+    for (int t0 = 0; t0 < T_full; t0 += kStreamChunk) {chunk(std::false_type{}, std::true_type{}, t0);}
+    if (T_full < T) {chunk(std::true_type{}, std::true_type{}, T_full);}
+  } else {
+    for (int t0 = 0; t0 < T_full; t0 += kStreamChunk) {chunk(std::false_type{}, std::false_type{}, t0);}
+    if (T_full < T) {chunk(std::true_type{}, std::false_type{}, T_full);}
+  }
 
   // furthest reached path point candidate (utils.hpp:292-319): first minimum over the whole path
   unsigned best_j = 0;
