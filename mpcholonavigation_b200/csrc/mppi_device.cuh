@@ -270,6 +270,22 @@ __device__ __forceinline__ int world_to_cell_try(float xf, float yf, const CellG
   return my * static_cast<int>(cg.size_x) + mx;
 }
 
+// The same for callers that send EVERYTHING unusual down one slow branch (the stream kernel's chunk): `plain` is set when
+// the fp32 cell is certain AND on the map; the return value is then the flat index and needs no off-map test.  Otherwise
+// the value is meaningless and world_to_cell_fast decides.
+__device__ __forceinline__ int world_to_cell_plain(float xf, float yf, const CellGrid & cg, bool & plain)
+{
+  const float qx = __fmul_rn(__fsub_rn(xf, cg.oxf), cg.invf);
+  const float qy = __fmul_rn(__fsub_rn(yf, cg.oyf), cg.invf);
+  int mx, my;
+  float fx, fy;
+  floor_magic(qx, mx, fx);
+  floor_magic(qy, my, fy);
+  plain = fabsf(__fsub_rn(fx, 0.5f)) < cg.half_minus_eps_x && fabsf(__fsub_rn(fy, 0.5f)) < cg.half_minus_eps_y &&
+    static_cast<unsigned>(mx) < cg.size_x && static_cast<unsigned>(my) < cg.size_y;
+  return my * static_cast<int>(cg.size_x) + mx;
+}
+
 __device__ __forceinline__ int world_to_cell_fast(float xf, float yf, const CellGrid & cg, const double * __restrict__ geom)
 {
   const float qx = __fmul_rn(__fsub_rn(xf, cg.oxf), cg.invf);

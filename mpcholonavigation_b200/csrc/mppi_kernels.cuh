@@ -992,9 +992,11 @@ __device__ __forceinline__ void rollout_score_stream_body(
   const int T = p.T, B = p.B;
   const int Tp = ((T + kStreamChunk - 1) / kStreamChunk) * kStreamChunk;   // horizon padded to whole chunks
   float * s_cs = s_hot + kHotFloats;   // [3][Tp], zero padded
-  for (int i = tid; i < 3 * Tp; i += nthr) {
-    const int plane = i / Tp, t = i - plane * Tp;
-    s_cs[i] = t < T ? bufs.cs[plane * T + t] : 0.0f;
+  for (int t = tid; t < Tp; t += nthr) {
+    const bool in = t < T;
+    s_cs[t] = in ? bufs.cs[t] : 0.0f;
+    s_cs[Tp + t] = in ? bufs.cs[T + t] : 0.0f;
+    s_cs[2 * Tp + t] = in ? bufs.cs[2 * T + t] : 0.0f;
   }
   __syncthreads();
 
@@ -1122,20 +1124,24 @@ __device__ __forceinline__ void rollout_score_stream_body(
       int cell[kStreamChunk], pcost[kStreamChunk];
       bool costed = false;   // some pose of the chunk needs the obstacle-type critics' attention
       if (need_cell) {
-        bool all_sure = true;
+        bool all_plain = true;
 #pragma unroll
         for (int u = 0; u < kStreamChunk; ++u) {
-          bool sure;
-          cell[u] = world_to_cell_try(px[u], py[u], cg, sure);
-          all_sure = all_sure && sure;
-        }
-        if (!all_sure) {   // one branch per chunk: the reference's own fp64 arithmetic decides (bit-exact either way)
-#pragma unroll
-          for (int u = 0; u < kStreamChunk; ++u) {cell[u] = world_to_cell_fast(px[u], py[u], cg, &p.res);}
+          bool plain;
+          cell[u] = world_to_cell_plain(px[u], py[u], cg, plain);
+          all_plain = all_plain && plain;
         }
         int any = 0;
+        if (all_plain) {   // every pose of the chunk certainly in its fp32 cell and on the map: the usual case
 #pragma unroll
-        for (int u = 0; u < kStreamChunk; ++u) {pcost[u] = cell[u] < 0 ? NO_INFORMATION : __ldg(cm + cell[u]); any |= pcost[u];}
+          for (int u = 0; u < kStreamChunk; ++u) {pcost[u] = __ldg(cm + static_cast<unsigned>(cell[u])); any |= pcost[u];}
+        } else {           // one branch per chunk: poses off the map, and the reference's own fp64 arithmetic where it decides
+#pragma unroll
+          for (int u = 0; u < kStreamChunk; ++u) {
+            cell[u] = world_to_cell_fast(px[u], py[u], cg, &p.res);
+            pcost[u] = cell[u] < 0 ? NO_INFORMATION : __ldg(cm + cell[u]); any |= pcost[u];
+          }
+        }
         // free space under every pose of the chunk (the common case): nothing for Cost / Obstacles to do - unless the
         // Obstacles critic checks the footprint at every pose (no inflation layer: possibly_inscribed_cost < 1)
         costed = any != 0 || want_cells || (ob_on && ob_fp && ob_pic < 1.0f);
