@@ -98,6 +98,7 @@ struct mppi_handle
   int * d_cells{nullptr};
   float * d_costs{nullptr};
   float * d_partials{nullptr};
+  unsigned * d_ws_done{nullptr};         // per row group of the weighted-sums kernel: blocks finished (last one merges)
   CUtensorMap noise_map[3];           // TMA descriptors of the time-major noise planes (stream layout, weighted_sums_tma_kernel)
   bool pdl_enabled{true};             // MPPI_PDL=0: ordinary (fully serialised) launches of the stream layout's post-rollout kernels
   int scan_mode{0};                   // MPPI_SCAN=warp: experiment, warp-shuffle prefix scans in the tile kernels (not the parity path)
@@ -998,7 +999,16 @@ int weighted_sums_chunks(const mppi_handle * h)
   return h->ws_tma_ok ? (h->B + kPsChunk - 1) / kPsChunk : (h->B + kWsChunk - 1) / kWsChunk;
 }
 
-mppi_status launch_weighted_sums(mppi_handle * h)
+// the TMA-fed weighted-sums kernel merges, normalises and clips itself (no merge kernel behind it): single rank, and no
+// coupling between the planes of a time step in the clip (Ackermann couples wz to vx)
+bool merge_in_weighted_sums(const mppi_handle * h)
+{
+  static const int enabled = std::getenv("MPPI_WS_MERGE") ? std::atoi(std::getenv("MPPI_WS_MERGE")) : 1;   // measurement switch
+  return enabled && h->stream_layout && h->ws_tma_ok && h->nranks == 1 && h->cfg.motion_model != MPPI_MODEL_ACKERMANN && h->d_ws_done;
+}
+
+// host_res: the result leaves as packets (only looked at when the kernel merges itself)
+mppi_status launch_weighted_sums(mppi_handle * h, uint2 * host_res = nullptr, bool allow_merge = false)
 {
   const DevParams * dp = reinterpret_cast<const DevParams *>(h->d_params);
   const int chunks = weighted_sums_chunks(h);
@@ -1006,8 +1016,10 @@ mppi_status launch_weighted_sums(mppi_handle * h)
     // row groups: about four waves of 3 resident blocks per SM (a short tail), at least two stages per block
     const int stages = (holonomic(h) ? 3 : 2) * ((h->T + kPsRows - 1) / kPsRows);
     const int gy = std::max(1, std::min(stages / 2, (12 * h->num_sms + chunks - 1) / chunks));
-    CUDA_TRY(h, launch_kernel(weighted_sums_tma_kernel, dim3(chunks, gy), dim3(kPsThreads), ps_smem_bytes(), h->stream, h->pdl_enabled,
-      h->noise_map[0], h->noise_map[1], h->noise_map[2], dp, make_bufs(h, 0), h->T, h->B, holonomic(h) ? 1 : 0));
+    static const int chunk_major = std::getenv("MPPI_WS_CHUNK_MAJOR") ? std::atoi(std::getenv("MPPI_WS_CHUNK_MAJOR")) : 0;   // experiment (profiles/README.md): slower
+    CUDA_TRY(h, launch_kernel(weighted_sums_tma_kernel, chunk_major ? dim3(gy, chunks) : dim3(chunks, gy), dim3(kPsThreads), ps_smem_bytes(), h->stream, h->pdl_enabled,
+      h->noise_map[0], h->noise_map[1], h->noise_map[2], dp, make_bufs(h, 0), h->T, h->B, holonomic(h) ? 1 : 0,
+      (allow_merge && merge_in_weighted_sums(h)) ? h->d_ws_done : nullptr, host_res, chunk_major));
   } else {
     const int gy = weighted_sums_row_groups(h->T, chunks);
     CUDA_TRY(h, launch_kernel(weighted_sums_tm_kernel, dim3(chunks, gy), dim3(kWsThreads), 0, h->stream, h->pdl_enabled, dp, make_bufs(h, 0)));
@@ -1091,7 +1103,7 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
     const int chunks = weighted_sums_chunks(h);
     if (h->stream_layout) {
       // K3 published costs + global minimum; weights and weighted control sums over the time-major noise
-      const mppi_status ws = launch_weighted_sums(h);
+      const mppi_status ws = launch_weighted_sums(h, (stream_packets(h) && it + 1 == h->cfg.iteration_count) ? h->h_res : nullptr, true);
       if (ws != MPPI_OK) {return ws;}
     }
     if (h->nranks > 1 && h->peer_mode) {
@@ -1104,7 +1116,9 @@ mppi_status enqueue_kernels(mppi_handle * h, bool prof)
       CUDA_TRY(h, cudaGetLastError());
       h->launches++;
     } else {
-      if (h->stream_layout || many) {
+      if (merge_in_weighted_sums(h)) {
+        // nothing to launch: the weighted-sums kernel's last block per row group merged, clipped and delivered
+      } else if (h->stream_layout || many) {
         // too many partial records for a serial merge in K3's last block (or the stream layout): merge in parallel
         CUDA_TRY(h, launch_kernel(merge_finalize_kernel, dim3(merge_grid), dim3(kUpdThreads), 0, h->stream, h->pdl_enabled && h->stream_layout,
           dp, h->d_partials, h->stream_layout ? chunks : h->upd_blocks, stride, make_bufs(h, 0), h->nranks > 1 ? 0 : 1, h->d_rank_partial,
@@ -1890,7 +1904,7 @@ void mppi_destroy(mppi_handle * h)
   cudaFree(h->d_vis);
   cudaFree(h->d_vis);
   cudaFree(h->d_tmp); cudaFree(h->d_params); cudaFree(h->d_cs); cudaFree(h->d_crit_rows);
-  cudaFree(h->d_end_xy); cudaFree(h->d_cells); cudaFree(h->d_costs); cudaFree(h->d_partials); cudaFree(h->d_rank_partial);
+  cudaFree(h->d_end_xy); cudaFree(h->d_cells); cudaFree(h->d_costs); cudaFree(h->d_partials); cudaFree(h->d_ws_done); cudaFree(h->d_rank_partial);
   cudaFree(h->d_gathered); h->gathered_capacity = 0; cudaFree(h->d_out); cudaFree(h->d_st); cudaFree(h->d_hist); cudaFree(h->d_seq); cudaFree(h->d_epoch);
   if (h->ev_result) {cudaEventDestroy(h->ev_result);} cudaFree(h->d_mailbox);
   cudaFreeHost(h->h_params); cudaFreeHost(h->h_out); cudaFreeHost(h->h_res);
@@ -2002,6 +2016,8 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   const size_t stride = 3 * T + 2;
   CUDA_TRY(h, cudaMalloc(&h->d_partials, h->upd_blocks * stride * sizeof(float)));
   CUDA_TRY(h, cudaMalloc(&h->d_rank_partial, stride * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->d_ws_done, 1024 * sizeof(unsigned)));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_ws_done, 0, 1024 * sizeof(unsigned), h->stream));
   CUDA_TRY(h, cudaMalloc(&h->d_out, (stride + 8) * sizeof(float)));
   CUDA_TRY(h, cudaMemsetAsync(h->d_out, 0, (stride + 8) * sizeof(float), h->stream));
   CUDA_TRY(h, cudaMalloc(&h->d_hist, 12 * sizeof(float)));

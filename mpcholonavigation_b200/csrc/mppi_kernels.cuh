@@ -2889,19 +2889,25 @@ __device__ __forceinline__ void ps_fill_stage(float * stage, const CUtensorMap *
 
 __global__ void __launch_bounds__(kPsThreads) weighted_sums_tma_kernel(
   const __grid_constant__ CUtensorMap tm_vx, const __grid_constant__ CUtensorMap tm_vy, const __grid_constant__ CUtensorMap tm_wz,
-  const DevParams * __restrict__ Pg, DevBuffers bufs, const int T, const int B, const int holonomic)
+  const DevParams * __restrict__ Pg, DevBuffers bufs, const int T, const int B, const int holonomic,
+  unsigned * __restrict__ done, uint2 * host_res, const int chunk_major)
 {
   extern __shared__ __align__(128) float ps_smem[];
   __shared__ __align__(8) uint64_t s_full[kPsStages], s_empty[kPsStages];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float * s_stage = ps_smem;
-  const int chunk = static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x);
+  // grid = (row groups, chunks), or (chunks, row groups) when `chunk_major` is 0.  Row group fastest: all row groups of a chunk
+  // are dispatched together, chunks in descending order - the rollout kernel went through the trajectories in ascending
+  // order, so the columns it read last (still in L2) are the ones read first here
+  const int n_chunks = static_cast<int>(chunk_major ? gridDim.y : gridDim.x), n_groups = static_cast<int>(chunk_major ? gridDim.x : gridDim.y);
+  const int group = static_cast<int>(chunk_major ? blockIdx.x : blockIdx.y);
+  const int chunk = n_chunks - 1 - static_cast<int>(chunk_major ? blockIdx.y : blockIdx.x);
   const int b0 = chunk * kPsChunk;
   // stages in ring order: plane vx, plane wz, [plane vy]; this block's share of them (gridDim.y row groups)
   const int boxes_per_plane = (T + kPsRows - 1) / kPsRows;
   const int n_all = (holonomic ? 3 : 2) * boxes_per_plane;
-  const int per_y = (n_all + static_cast<int>(gridDim.y) - 1) / static_cast<int>(gridDim.y);
-  const int box_begin = blockIdx.y * per_y, n_boxes = max(0, min(n_all, box_begin + per_y) - box_begin);
+  const int per_y = (n_all + n_groups - 1) / n_groups;
+  const int box_begin = group * per_y, n_boxes = max(0, min(n_all, box_begin + per_y) - box_begin);
   pdl_launch_dependents();
 
   if (tid == kPsConsumers) {
@@ -2956,7 +2962,9 @@ __global__ void __launch_bounds__(kPsThreads) weighted_sums_tma_kernel(
   }
   ssum = warp_sum(ssum);          // every warp holds the whole chunk: the same sum in every warp
   float * part = bufs.partials + static_cast<size_t>(chunk) * (3 * T + 2);
-  if (blockIdx.y == 0 && tid == 0) {part[0] = gm; part[1] = ssum;}
+  // every row group writes the head of the record (the same bits from every group: each holds the whole chunk's weights), so
+  // that the group that merges its own columns (below) depends on the blocks of its own group only
+  if ((group == 0 || done != nullptr) && tid == 0) {part[0] = gm; part[1] = ssum;}
   for (int i = 0; i < n_boxes; ++i) {
     const int s = i % kPsStages;
     if (!mbar_wait(&s_full[s], (i / kPsStages) & 1u)) {raise_comm_error(bufs); break;}
@@ -2981,9 +2989,70 @@ __global__ void __launch_bounds__(kPsThreads) weighted_sums_tma_kernel(
     const float a = warp_sum(a0 + a1);
     if (lane == 0 && t < T) {
       const int c = (pl == 0 ? 0 : (pl == 1 ? 2 : 1)) * T + t;       // record order: vx, vy, wz
-      part[2 + c] = fmaf(__ldg(bufs.cs + c), ssum, a);               // sum_b w_b (cs + noise) = cs * s + sum_b w_b noise
+      part[2 + c] = fmaf(bufs.cs[c], ssum, a);                       // sum_b w_b (cs + noise) = cs * s + sum_b w_b noise
     }
   }
+  if (done == nullptr) {return;}
+  // ---- merge + normalise + clip (optimizer.cpp:384-394, :237-249) without another kernel: the block that finishes a row
+  //      group LAST sums that group's columns over all chunks (every record carries the same minimum - the global one - so
+  //      the online-softmax merge is a plain sum, taken in the order merge_finalize_kernel takes it), divides by the
+  //      normaliser, clips and delivers its part of the new control sequence (device memory and, when asked, result packets
+  //      in pinned host memory).  Row groups finish at different times: their merges hide behind the other groups' streaming.
+  __shared__ unsigned s_last;
+  __threadfence();
+  asm volatile ("bar.sync 1, %0;" :: "n"(kPsConsumers) : "memory");
+  if (tid == 0) {s_last = atomicAdd(&done[group], 1u) == static_cast<unsigned>(n_chunks) - 1u ? 1u : 0u;}
+  asm volatile ("bar.sync 1, %0;" :: "n"(kPsConsumers) : "memory");
+  if (!s_last) {return;}
+  __threadfence();
+  const int stride = 3 * T + 2;
+  const float * parts = bufs.partials;
+  const unsigned tag = host_res ? ld_volatile_u32(bufs.epoch) : 0u;
+  // thread = column of the row group, all chunks in chunk order (four interleaved partial sums: a fixed order); the loads
+  // of a thread are independent, consecutive threads read consecutive words
+  for (int r = tid; r < n_boxes * kPsRows; r += kPsConsumers) {
+    const int g = box_begin + r / kPsRows, pl = g / boxes_per_plane, t = (g - pl * boxes_per_plane) * kPsRows + r % kPsRows;
+    if (t >= T) {continue;}
+    const int plane = pl == 0 ? 0 : (pl == 1 ? 2 : 1), c = plane * T + t;
+    float a[4] = {0.0f, 0.0f, 0.0f, 0.0f}, sw[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const float * p0 = parts + 2 + c;
+    int i = 0;
+    for (; i + 4 <= n_chunks; i += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[u] += __ldcg(p0 + static_cast<size_t>(i + u) * stride);
+        sw[u] += __ldcg(parts + static_cast<size_t>(i + u) * stride + 1);
+      }
+    }
+    for (; i < n_chunks; ++i) {a[0] += __ldcg(p0 + static_cast<size_t>(i) * stride); sw[0] += __ldcg(parts + static_cast<size_t>(i) * stride + 1);}
+    const float acc = (a[0] + a[1]) + (a[2] + a[3]), S = (sw[0] + sw[1]) + (sw[2] + sw[3]);
+    float v = acc / S;
+    if (plane == 0) {
+      v = fminf(fmaxf(v, Pg->c_vx_min), Pg->c_vx_max);
+    } else if (plane == 1) {
+      v = fminf(fmaxf(v, -Pg->c_vy), Pg->c_vy);
+    } else {
+      v = fminf(fmaxf(v, -Pg->c_wz), Pg->c_wz);
+    }
+    bufs.cs[c] = v; bufs.out[c] = v;
+    if (host_res) {st_packet(host_res + c, __float_as_uint(v), tag);}
+  }
+  if (group == 0) {
+    // what no row group owns: the lateral plane of a non-holonomic model (unchanged), the fail flag and the furthest
+    // reached path point (published by the path-cost kernel in front of this one)
+    if (!holonomic) {
+      for (int t = tid; t < T; t += kPsConsumers) {
+        const float vy = bufs.cs[T + t];
+        bufs.out[T + t] = vy;
+        if (host_res) {st_packet(host_res + T + t, __float_as_uint(vy), tag);}
+      }
+    }
+    if (host_res && tid == 0) {
+      st_packet(host_res + 3 * T, __float_as_uint(bufs.out[3 * T]), tag);
+      st_packet(host_res + 3 * T + 1, __float_as_uint(bufs.out[3 * T + 1]), tag);
+    }
+  }
+  if (tid == 0) {done[group] = 0u;}   // ready for the next launch (nobody else touches this group's counter any more)
 }
 
 // K4: parallel merge of n partial records [m, s, W...] (online-softmax merge, SURVEY 8e exchange 2).
