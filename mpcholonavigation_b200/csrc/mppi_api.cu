@@ -438,6 +438,16 @@ mppi_status build_params(mppi_handle * h, const mppi_cycle_in * in, int mode, un
       if (d < best) {best = d; best_j = j;}
     }
     p.closest_path_pt = best_j;
+    // longest segment and mean spacing of the path (double, from the fp32 coordinates the kernels read)
+    double hmax = 0.0, len = 0.0;
+    for (int j = 0; j + 1 < N; ++j) {
+      const double sx = static_cast<double>(in->path_x[j + 1]) - static_cast<double>(in->path_x[j]);
+      const double sy = static_cast<double>(in->path_y[j + 1]) - static_cast<double>(in->path_y[j]);
+      const double seg = std::sqrt(sx * sx + sy * sy);
+      hmax = std::max(hmax, seg); len += seg;
+    }
+    p.path_hmax_inv = (hmax > 0.0 && std::isfinite(hmax)) ? static_cast<float>(1.0 / (hmax * 1.00001)) : 0.0f;
+    p.path_hmean_inv = (len > 0.0 && std::isfinite(len)) ? static_cast<float>(static_cast<double>(N - 1) / len) : 0.0f;
   }
 
   p.n_critics = critics_active ? static_cast<int>(h->critics.size()) : 0;
@@ -1000,7 +1010,9 @@ int weighted_sums_chunks(const mppi_handle * h)
 }
 
 // the TMA-fed weighted-sums kernel merges, normalises and clips itself (no merge kernel behind it): single rank, and no
-// coupling between the planes of a time step in the clip (Ackermann couples wz to vx)
+// coupling between the planes of a time step in the clip (Ackermann couples wz to vx).  Sharded over peer memory, exchange 2
+// was tried in the same place (the last block of a row group pushing and polling its columns): 175 against 172 us per
+// step at 2 GPUs - the exposed part is the last row group's merge plus the rank skew either way - and left out.
 bool merge_in_weighted_sums(const mppi_handle * h)
 {
   static const int enabled = std::getenv("MPPI_WS_MERGE") ? std::atoi(std::getenv("MPPI_WS_MERGE")) : 1;   // measurement switch
@@ -2016,8 +2028,8 @@ mppi_status mppi_create(const mppi_config * cfg, mppi_handle ** out)
   const size_t stride = 3 * T + 2;
   CUDA_TRY(h, cudaMalloc(&h->d_partials, h->upd_blocks * stride * sizeof(float)));
   CUDA_TRY(h, cudaMalloc(&h->d_rank_partial, stride * sizeof(float)));
-  CUDA_TRY(h, cudaMalloc(&h->d_ws_done, 1024 * sizeof(unsigned)));
-  CUDA_TRY(h, cudaMemsetAsync(h->d_ws_done, 0, 1024 * sizeof(unsigned), h->stream));
+  CUDA_TRY(h, cudaMalloc(&h->d_ws_done, kWsDoneSlots * sizeof(unsigned)));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_ws_done, 0, kWsDoneSlots * sizeof(unsigned), h->stream));
   CUDA_TRY(h, cudaMalloc(&h->d_out, (stride + 8) * sizeof(float)));
   CUDA_TRY(h, cudaMemsetAsync(h->d_out, 0, (stride + 8) * sizeof(float), h->stream));
   CUDA_TRY(h, cudaMalloc(&h->d_hist, 12 * sizeof(float)));

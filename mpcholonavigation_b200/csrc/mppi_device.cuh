@@ -106,6 +106,10 @@ struct DevParams
   int fp_n;
   float cell_oxf, cell_oyf, cell_invf;       // fp32 filter of worldToMap (world_to_cell_fast): fl32(ox), fl32(oy), fl32(1/res)
   float cell_eps_x, cell_eps_y;              // and its error bounds in cells
+  // furthest-point search of the stream kernel (utils.hpp:292-319 restated as a scan that skips): 1 / (longest path
+  // segment, rounded up) bounds how fast the distance to the path can fall from one point to the next; (N - 1) / length
+  // places the first guess.  Zero: no skipping / no guess.
+  float path_hmax_inv, path_hmean_inv;
   // where the term of list position q comes from when the critic runs (fused kernel): 0 nothing (absent / disabled / gated
   // off by the host), 1 K2's row, 2 PathFollow, 3 PathAlign, 4 PathAlignLegacy, 5 PathAngle
   unsigned char src_base[kMaxCritics];

@@ -1281,13 +1281,32 @@ __device__ __forceinline__ void rollout_score_stream_body(
   if (p.need_furthest) {
     const float * __restrict__ path_x = reinterpret_cast<const float *>(P + 1) + p.off_path_x;
     const float * __restrict__ path_y = reinterpret_cast<const float *>(P + 1) + p.off_path_y;
-    float best = 3.402823466e+38f;
     const int N = p.N;
-    for (int j = 0; j < N; ++j) {
-      const float dx = __fsub_rn(__ldg(path_x + j), ex);
-      const float dy = __fsub_rn(__ldg(path_y + j), ey);
-      const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-      if (d < best) {best = d; best_j = j;}
+    auto dist2 = [&](int j) {
+        const float dx = __fsub_rn(__ldg(path_x + j), ex);
+        const float dy = __fsub_rn(__ldg(path_y + j), ey);
+        return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+      };
+    // The reference scans all N points for the first minimum of the squared distance.  Same answer from a scan that skips:
+    // along the path the distance to the end pose cannot fall faster than the path advances, so behind a point at distance
+    // r the next floor((r - r_best) / longest segment) points are farther than the best seen so far.  The margins (1e-5
+    // relative on both roots; 1 / hmax rounded down by the host) are orders above the rounding of the squared distances
+    // (3 fp32 operations) and of sqrt.approx (2^-22), so a skipped point is STRICTLY farther in the kernel's own arithmetic:
+    // it can be neither the minimum nor a tie.  A first guess (the point an arc as long as the trajectory's displacement
+    // beyond the robot's closest point) makes r_best small from the start; ties go to the lower index as in the reference.
+    const float gdx = ex - static_cast<float>(x0), gdy = ey - static_cast<float>(y0);
+    const int guess = p.closest_path_pt + __float2int_rn(fminf(sqrt_approx(gdx * gdx + gdy * gdy) * p.path_hmean_inv, 65536.0f));
+    best_j = static_cast<unsigned>(max(0, min(N - 1, guess)));
+    float best = N > 0 ? dist2(static_cast<int>(best_j)) : 3.402823466e+38f;
+    float r_best = sqrt_approx(best);
+    const float inv_h = p.path_hmax_inv;
+    int j = 0;
+    while (j < N) {
+      const float d = dist2(j);
+      const float r = sqrt_approx(d);
+      if (d < best || (d == best && j < static_cast<int>(best_j))) {best = d; best_j = static_cast<unsigned>(j); r_best = r;}
+      const float gap = r * 0.99999f - r_best * 1.00001f;
+      j += 1 + (gap > 0.0f ? __float2int_rz(fminf(gap * inv_h, 65536.0f)) : 0);
     }
   }
 
@@ -2840,6 +2859,7 @@ constexpr int kPsConsumers = 32 * kPsRows;
 constexpr int kPsThreads = kPsConsumers + 32;
 constexpr int kPsBoxBytes = kPsRows * kPsBoxCols * 4;
 constexpr int kPsStageBytes = kPsSub * kPsBoxBytes;
+constexpr int kWsDoneSlots = 1024;       // row-group counters of the fused merge; the last one counts finished row groups
 constexpr int kPsSpinLimit = 1 << 22;     // bounded mbarrier waits (each try_wait suspends the thread for a while)
 
 __host__ __device__ inline size_t ps_smem_bytes() {return static_cast<size_t>(kPsStages) * kPsStageBytes + 128;}

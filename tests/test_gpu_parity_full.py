@@ -310,3 +310,53 @@ def test_no_inflation_layer_in_footprint_mode(product_fns, oracle_fns, monkeypat
     c = o.get_critic_costs(1)
     assert (c > 200.0).any() and ((c > 0.0) & (c < 200.0)).any()    # collided (267.86) and merely costed trajectories
     g.close(); o.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# 1e. the stream layout's furthest-point scan (skips along the path) and lean per-trajectory total
+# ------------------------------------------------------------------------------------------------
+def _winding_paths(x0, y0):
+    """paths on which the distance to a pose is NOT unimodal along the path, with ties, repeated points, uneven spacing"""
+    out = {}
+    s = np.linspace(0.0, 1.0, 90)
+    # a loop that leaves the robot, comes back past it and leaves again: several local minima
+    out["loop"] = (x0 + 1.2 * np.sin(2 * np.pi * s) + 0.8 * s, y0 + 0.9 * (1 - np.cos(2 * np.pi * s)) * np.sign(0.5 - s + 1e-9))
+    # out and back along the SAME line: every distance appears twice (ties -> the first index must win)
+    leg = np.arange(30) * 0.05
+    out["out_and_back"] = (x0 + np.concatenate([leg, leg[::-1]]), np.full(60, y0))
+    # uneven spacing: repeated points (zero-length segments), then a 0.6 m jump, then dense points
+    xs = np.concatenate([np.zeros(4), np.arange(1, 12) * 0.03, 0.33 + 0.6 + np.arange(25) * 0.01, 1.2 + np.arange(10) * 0.2])
+    out["uneven"] = (x0 + xs, y0 + 0.1 * np.sin(5 * xs))
+    # a spiral around the robot
+    th = np.linspace(0.0, 5 * np.pi, 120)
+    out["spiral"] = (x0 + (0.1 + 0.09 * th) * np.cos(th), y0 + (0.1 + 0.09 * th) * np.sin(th))
+    return {k: (np.asarray(a, np.float32), np.asarray(b, np.float32)) for k, (a, b) in out.items()}
+
+
+@pytest.mark.parametrize("shape", ["loop", "out_and_back", "uneven", "spiral"])
+def test_stream_layout_on_winding_paths(product_fns, oracle_fns, monkeypatch, shape):
+    """utils::findPathFurthestReachedPoint (utils.hpp:292-319) is a first-minimum scan over ALL path points; the stream
+    kernel skips points that provably cannot win.  Paths with several local minima, exact ties, repeated points and uneven
+    spacing: furthest point, per-critic costs, total costs and controls against the oracle; then the same without
+    materialised outputs (the lean per-trajectory total of the path-cost kernel)."""
+    monkeypatch.setenv("MPPI_STREAM_MIN_BATCH", "1")
+    sc = scenarios.config1(batch=2048)
+    px, py = _winding_paths(sc.cycle.pose[0], sc.cycle.pose[1])[shape]
+    pyaw = np.arctan2(np.gradient(py.astype(np.float64)), np.gradient(px.astype(np.float64)) + 1e-12).astype(np.float32)
+    sc.cycle = dataclasses.replace(sc.cycle, path_x=px, path_y=py, path_yaw=pyaw, goal=(float(px[-1]) + 3.0, float(py[-1])),
+                                   costmap=np.zeros_like(sc.cycle.costmap), speed=(0.25, 0.05, 0.1))
+    noise = sc.noise()
+    g, o = _engine(product_fns, sc, noise), _engine(oracle_fns, sc, noise)
+    seen = set()
+    for cycle in range(5):
+        rg, ro = g.optimize(sc.cycle), o.optimize(sc.cycle)
+        _compare(g, o, sc, rg, ro, f"{shape} cycle {cycle}")
+        seen.add(ro.furthest_reached_path_point)
+        g.set_control_sequence(ro.vx, ro.vy, ro.wz)
+    assert None not in seen
+    g.set_outputs(); o.set_outputs()
+    for cycle in range(3):
+        rg, ro = g.optimize(sc.cycle), o.optimize(sc.cycle)
+        _compare(g, o, sc, rg, ro, f"{shape} lean cycle {cycle}", bitwise=False)
+        g.set_control_sequence(ro.vx, ro.vy, ro.wz)
+    g.close(); o.close()
