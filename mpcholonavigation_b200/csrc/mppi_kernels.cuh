@@ -1936,12 +1936,14 @@ __device__ __forceinline__ void path_costs_tm_body(const DevParams * __restrict_
     // points per metre of the path: the start of the per-sample search in the arc-length prefix (efficiency only)
     const float d_all = path.s_D[max(P->N - 1, 0)];
     const float inv_h = d_all > 0.0f ? static_cast<float>(P->N - 1) / d_all : 0.0f;
-    for (int b = blockIdx.x * kUpdThreads + tid; b < B; b += gridDim.x * kUpdThreads) {
-      m = fminf(m, k3_trajectory_total_fast(b, P, dec, path, bufs, iteration, src_w, inv_h));
+    for (int base = blockIdx.x * kUpdThreads; base < B; base += gridDim.x * kUpdThreads) {
+      const int b = base + tid;
+      if (b < B) {m = fminf(m, k3_trajectory_total_fast(b, P, dec, path, bufs, iteration, src_w, inv_h));}
     }
   } else {
-    for (int b = blockIdx.x * kUpdThreads + tid; b < B; b += gridDim.x * kUpdThreads) {
-      m = fminf(m, k3_trajectory_total_general(b, P, dec, path, bufs, iteration));
+    for (int base = blockIdx.x * kUpdThreads; base < B; base += gridDim.x * kUpdThreads) {
+      const int b = base + tid;
+      if (b < B) {m = fminf(m, k3_trajectory_total_general(b, P, dec, path, bufs, iteration));}
     }
   }
   m = warp_min(m);
@@ -2854,7 +2856,10 @@ constexpr int kPsChunk = 1024;            // trajectories (columns) per block
 constexpr int kPsBoxCols = 256;           // columns per TMA box (the hardware limit of a box dimension)
 constexpr int kPsSub = kPsChunk / kPsBoxCols;
 constexpr int kPsRows = 4;                // rows per stage == consumer warps
-constexpr int kPsStages = 4;
+#ifndef MPPI_PS_STAGES
+#define MPPI_PS_STAGES 4
+#endif
+constexpr int kPsStages = MPPI_PS_STAGES;
 constexpr int kPsConsumers = 32 * kPsRows;
 constexpr int kPsThreads = kPsConsumers + 32;
 constexpr int kPsBoxBytes = kPsRows * kPsBoxCols * 4;
@@ -2955,8 +2960,8 @@ __global__ void __launch_bounds__(kPsThreads) weighted_sums_tma_kernel(
   // ---- consumers: softmax weights of the chunk; lane owns columns q * 256 + j * 128 + 4 lane + {0..3}, q < 4, j < 2
   //      (the noise planes are static, the costs and their minimum are the path-cost kernel's: wait for it here, with the
   //       first stages of the ring already in flight)
-  pdl_wait();
   const float inv_temp = 1.0f / Pg->temperature;
+  pdl_wait();
   const float gm = bufs.st->global_min;
   float w[kPsSub][2][4];
   float ssum = 0.0f;
@@ -2967,15 +2972,23 @@ __global__ void __launch_bounds__(kPsThreads) weighted_sums_tma_kernel(
       const int b = b0 + q * kPsBoxCols + j * 128 + 4 * lane;
       float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
       if (b + 3 < B) {
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(bufs.costs + b));
+        const float4 v = __ldcg(reinterpret_cast<const float4 *>(bufs.costs + b));   // the lane's eight loads are all in flight before the first exponential
         c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
       } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {if (b + e < B) {c[e] = __ldg(bufs.costs + b + e);}}
+        for (int e = 0; e < 4; ++e) {if (b + e < B) {c[e] = __ldcg(bufs.costs + b + e);}}
       }
 #pragma unroll
+      for (int e = 0; e < 4; ++e) {w[q][j][e] = c[e];}
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kPsSub; ++q) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#pragma unroll
       for (int e = 0; e < 4; ++e) {
-        w[q][j][e] = b + e < B ? expf(-(c[e] - gm) * inv_temp) : 0.0f;
+        w[q][j][e] = b0 + q * kPsBoxCols + j * 128 + 4 * lane + e < B ? expf(-(w[q][j][e] - gm) * inv_temp) : 0.0f;
         ssum += w[q][j][e];
       }
     }
