@@ -2962,7 +2962,7 @@ __global__ void __launch_bounds__(kPsThreads) weighted_sums_tma_kernel(
   //       first stages of the ring already in flight)
   const float inv_temp = 1.0f / Pg->temperature;
   pdl_wait();
-  const float gm = bufs.st->global_min;
+  const float gm = __ldcg(&bufs.st->global_min);
   float w[kPsSub][2][4];
   float ssum = 0.0f;
 #pragma unroll
@@ -3022,7 +3022,7 @@ __global__ void __launch_bounds__(kPsThreads) weighted_sums_tma_kernel(
     const float a = warp_sum(a0 + a1);
     if (lane == 0 && t < T) {
       const int c = (pl == 0 ? 0 : (pl == 1 ? 2 : 1)) * T + t;       // record order: vx, vy, wz
-      part[2 + c] = fmaf(bufs.cs[c], ssum, a);                       // sum_b w_b (cs + noise) = cs * s + sum_b w_b noise
+      part[2 + c] = fmaf(__ldcg(bufs.cs + c), ssum, a);              // sum_b w_b (cs + noise) = cs * s + sum_b w_b noise
     }
   }
   if (done == nullptr) {return;}
