@@ -530,7 +530,8 @@ def run_workload(ctx, workload, steps, warmup, with_cpu_baseline, parity=None):
     stream_layout = B_local >= 8192
     fused = (not stream_layout) and k3_ms == 0.0   # the library reports K3 = 0 when the fused kernel ran
     k2_name = "rollout_score_stream_kernel" if stream_layout else ("tile_fused_kernel" if fused else "rollout_score_kernel")
-    k3_name = ("path_costs_tm_kernel+weighted_sums_tm_kernel+merge_finalize_kernel" if stream_layout else
+    k3_name = (("path_costs_tm_kernel+weighted_sums_tma_kernel (merge inside)" if world == 1 or not sharded else
+                "path_costs_tm_kernel+weighted_sums_tma_kernel") if stream_layout else
                ("(fused into tile_fused_kernel)" if fused else "path_softmax_update_kernel"))
     dom_name, dom_ms, oth_name, oth_ms = (k2_name, k2_ms, k3_name, k3_ms) if k2_ms >= k3_ms else (k3_name, k3_ms, k2_name, k2_ms)
     note = ("algorithmic bytes of one optimize() (SURVEY 8d: 12 B per rollout step, noise read once) over the kernel's "

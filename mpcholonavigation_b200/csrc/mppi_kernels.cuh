@@ -3050,6 +3050,16 @@ __global__ void __launch_bounds__(kPsThreads) weighted_sums_tma_kernel(
     float a[4] = {0.0f, 0.0f, 0.0f, 0.0f}, sw[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     const float * p0 = parts + 2 + c;
     int i = 0;
+    for (; i + 16 <= n_chunks; i += 16) {   // 32 loads of the thread in flight: the merge is a few L2 round trips
+      float va[16], vs[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        va[u] = __ldcg(p0 + static_cast<size_t>(i + u) * stride);
+        vs[u] = __ldcg(parts + static_cast<size_t>(i + u) * stride + 1);
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {a[u & 3] += va[u]; sw[u & 3] += vs[u];}
+    }
     for (; i + 4 <= n_chunks; i += 4) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {

@@ -35,6 +35,6 @@ for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "counters", "*.csv
         out[f"{k}@{size}"] = {"warp_inst": int(d.get("smsp__inst_executed.sum", 0)),
                               "dram_bytes": int(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0)),
                               "ncu_duration_us": d.get("gpu__time_duration.sum"),
-                              "source": f"profiles/r02_counters/{name}.csv"}
+                              "source": f"profiles/r02b_counters/{name}.csv"}
 json.dump(out, open(os.path.join(ROOT, "profiles", "ncu_kernel_counters.json"), "w"), indent=1)
 print(json.dumps(out, indent=1)[:3000])
