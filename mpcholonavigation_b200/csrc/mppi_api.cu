@@ -1025,9 +1025,12 @@ mppi_status launch_weighted_sums(mppi_handle * h, uint2 * host_res = nullptr, bo
   const DevParams * dp = reinterpret_cast<const DevParams *>(h->d_params);
   const int chunks = weighted_sums_chunks(h);
   if (h->ws_tma_ok) {
-    // row groups: about four waves of 3 resident blocks per SM (a short tail), at least two stages per block
+    // row groups: every block pays the same start-up (1024 costs -> weights) before its first row, so few fat blocks beat
+    // many thin ones: about 2.5 blocks per SM in all, never fewer than four row groups, at least two stages per block
+    // (measured on B200 at 32768 ... 262144 x 100: 12 / 6 / 4 / 4 row groups; three times as many cost 7 - 13 us per step)
     const int stages = (holonomic(h) ? 3 : 2) * ((h->T + kPsRows - 1) / kPsRows);
-    const int gy = std::max(1, std::min(stages / 2, (12 * h->num_sms + chunks - 1) / chunks));
+    const int target = (5 * h->num_sms) / 2;
+    const int gy = std::max(1, std::min(stages / 2, std::max(4, (target + chunks - 1) / chunks)));
     static const int chunk_major = std::getenv("MPPI_WS_CHUNK_MAJOR") ? std::atoi(std::getenv("MPPI_WS_CHUNK_MAJOR")) : 0;   // experiment (profiles/README.md): slower
     CUDA_TRY(h, launch_kernel(weighted_sums_tma_kernel, chunk_major ? dim3(gy, chunks) : dim3(chunks, gy), dim3(kPsThreads), ps_smem_bytes(), h->stream, h->pdl_enabled,
       h->noise_map[0], h->noise_map[1], h->noise_map[2], dp, make_bufs(h, 0), h->T, h->B, holonomic(h) ? 1 : 0,
