@@ -1031,10 +1031,9 @@ mppi_status launch_weighted_sums(mppi_handle * h, uint2 * host_res = nullptr, bo
     const int stages = (holonomic(h) ? 3 : 2) * ((h->T + kPsRows - 1) / kPsRows);
     const int target = (5 * h->num_sms) / 2;
     const int gy = std::max(1, std::min(stages / 2, std::max(4, (target + chunks - 1) / chunks)));
-    static const int chunk_major = std::getenv("MPPI_WS_CHUNK_MAJOR") ? std::atoi(std::getenv("MPPI_WS_CHUNK_MAJOR")) : 0;   // experiment (profiles/README.md): slower
-    CUDA_TRY(h, launch_kernel(weighted_sums_tma_kernel, chunk_major ? dim3(gy, chunks) : dim3(chunks, gy), dim3(kPsThreads), ps_smem_bytes(), h->stream, h->pdl_enabled,
+    CUDA_TRY(h, launch_kernel(weighted_sums_tma_kernel, dim3(chunks, gy), dim3(kPsThreads), ps_smem_bytes(), h->stream, h->pdl_enabled,
       h->noise_map[0], h->noise_map[1], h->noise_map[2], dp, make_bufs(h, 0), h->T, h->B, holonomic(h) ? 1 : 0,
-      (allow_merge && merge_in_weighted_sums(h)) ? h->d_ws_done : nullptr, host_res, chunk_major));
+      (allow_merge && merge_in_weighted_sums(h)) ? h->d_ws_done : nullptr, host_res));
   } else {
     const int gy = weighted_sums_row_groups(h->T, chunks);
     CUDA_TRY(h, launch_kernel(weighted_sums_tm_kernel, dim3(chunks, gy), dim3(kWsThreads), 0, h->stream, h->pdl_enabled, dp, make_bufs(h, 0)));

@@ -2848,9 +2848,12 @@ __global__ void __launch_bounds__(kWsThreads) weighted_sums_tm_kernel(const DevP
 // flight, then drain the ring: warp w owns row w of every stage, eight conflict-free 16-byte shared loads per lane, 32 FMAs,
 // one shuffle reduction per row.  No __syncthreads in the steady state; 64 KB in flight per block whatever the consumers
 // do, which is what the register-staged version lacked (long-scoreboard 25 per issue at 41 % occupancy, profiles/r01b).  Columns beyond B
-// are zero-filled by the TMA unit (their weights are zero too).  Chunks are taken in DESCENDING column order: the columns the
-// rollout kernel read last are the ones still in L2.  The record per chunk is [m = global min, s, W[3T]] like the
-// register-staged kernel's, so merge_finalize_kernel is unchanged.
+// are zero-filled by the TMA unit (their weights are zero too).  Chunks are taken in DESCENDING column order (the columns the
+// rollout kernel read last); at 262144 x 100 DRAM still delivers all 317 MB - the path-cost kernel's 65 MB in between
+// evict them - so the order is harmless, not a gain.  Every block pays the same start-up before its first row (1024 costs ->
+// 32 exponentials per lane, all eight loads of a lane in flight at once), so the host picks FEW row groups (about 2.5 blocks
+// per SM in all).  The record per chunk is [m = global min, s, W[3T]]; on one rank the block that finishes a row group last
+// merges that group's columns itself (below), otherwise merge_finalize_kernel / merge_exchange_finalize_kernel follow.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kPsChunk = 1024;            // trajectories (columns) per block
 constexpr int kPsBoxCols = 256;           // columns per TMA box (the hardware limit of a box dimension)
@@ -2915,18 +2918,16 @@ __device__ __forceinline__ void ps_fill_stage(float * stage, const CUtensorMap *
 __global__ void __launch_bounds__(kPsThreads) weighted_sums_tma_kernel(
   const __grid_constant__ CUtensorMap tm_vx, const __grid_constant__ CUtensorMap tm_vy, const __grid_constant__ CUtensorMap tm_wz,
   const DevParams * __restrict__ Pg, DevBuffers bufs, const int T, const int B, const int holonomic,
-  unsigned * __restrict__ done, uint2 * host_res, const int chunk_major)
+  unsigned * __restrict__ done, uint2 * host_res)
 {
   extern __shared__ __align__(128) float ps_smem[];
   __shared__ __align__(8) uint64_t s_full[kPsStages], s_empty[kPsStages];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float * s_stage = ps_smem;
-  // grid = (row groups, chunks), or (chunks, row groups) when `chunk_major` is 0.  Row group fastest: all row groups of a chunk
-  // are dispatched together, chunks in descending order - the rollout kernel went through the trajectories in ascending
-  // order, so the columns it read last (still in L2) are the ones read first here
-  const int n_chunks = static_cast<int>(chunk_major ? gridDim.y : gridDim.x), n_groups = static_cast<int>(chunk_major ? gridDim.x : gridDim.y);
-  const int group = static_cast<int>(chunk_major ? blockIdx.x : blockIdx.y);
-  const int chunk = n_chunks - 1 - static_cast<int>(chunk_major ? blockIdx.y : blockIdx.x);
+  // grid = (chunks, row groups); chunks in DESCENDING order (see above)
+  const int n_chunks = static_cast<int>(gridDim.x), n_groups = static_cast<int>(gridDim.y);
+  const int group = static_cast<int>(blockIdx.y);
+  const int chunk = n_chunks - 1 - static_cast<int>(blockIdx.x);
   const int b0 = chunk * kPsChunk;
   // stages in ring order: plane vx, plane wz, [plane vy]; this block's share of them (gridDim.y row groups)
   const int boxes_per_plane = (T + kPsRows - 1) / kPsRows;
