@@ -32,9 +32,9 @@ def _compare_cycle(g, o, sc, rg, ro, label):
     for name, a, b in zip("x y yaw".split(), g.get_trajectories(), o.get_trajectories()):
         assert np.array_equal(a, b), f"{label}: trajectory {name} differs in {np.count_nonzero(a != b)} places"
     for q in range(len(sc.critics)):
-        np.testing.assert_allclose(g.get_critic_costs(q), o.get_critic_costs(q), rtol=RTOL, atol=2e-5,
+        np.testing.assert_allclose(g.get_critic_costs(q), o.get_critic_costs(q), rtol=RTOL, atol=5e-6,
                                    err_msg=f"{label}: critic {q} {sc.critics[q][0]}")
-    np.testing.assert_allclose(g.get_costs(), o.get_costs(), rtol=RTOL, atol=2e-5, err_msg=f"{label}: total costs")
+    np.testing.assert_allclose(g.get_costs(), o.get_costs(), rtol=RTOL, atol=5e-6, err_msg=f"{label}: total costs")
     for name, a, b in (("vx", rg.vx, ro.vx), ("vy", rg.vy, ro.vy), ("wz", rg.wz, ro.wz)):
         np.testing.assert_allclose(a, b, rtol=RTOL, atol=ATOL, err_msg=f"{label}: control {name}")
     assert rg.fail_flag == ro.fail_flag
@@ -364,7 +364,7 @@ def test_tile_and_stream_agree_at_full_size(product_fns, monkeypatch):
     assert np.array_equal(ca, cb)
     for a, b in zip(ta, tb):
         assert np.array_equal(a, b)
-    np.testing.assert_allclose(ka, kb, rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(ka, kb, rtol=1e-4, atol=5e-6)
     np.testing.assert_allclose(ra.vx, rb.vx, rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(ra.wz, rb.wz, rtol=1e-4, atol=1e-6)
 

@@ -3,7 +3,7 @@ reduced cases never reach (round-1 verdict, items 1a-1d).
 
 Bars: cell indices and trajectories bit-exact; per-critic costs, total costs and the control sequence within 1e-4
 relative.  Absolute floors: 1e-6 on the controls; on costs the floor is COST_ATOL, justified in
-profiles/r02_parity_margins.txt (the only sums with cancellation are the gamma terms, whose operands are O(1)).
+profiles/r02b_parity_margins.txt (scripts/parity_margins.py) (the only sums with cancellation are the gamma terms, whose operands are O(1)).
 The oracle needs ~25 ms (16384 x 56), ~1 s (262144 x 100) and ~3 ms (2000 x 56) per cycle on one host core.
 """
 import ctypes as C
