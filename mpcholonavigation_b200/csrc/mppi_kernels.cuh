@@ -1772,12 +1772,14 @@ __device__ __noinline__ float k3_trajectory_total_general(
   return k3_trajectory_total(b, P, dec, path, bufs, iteration);
 }
 
-// The same total for the usual case, at a third of the instructions: no per-critic rows requested, PathAlign without path
+// The same total for the usual case, at 60 % of the instructions: no per-critic rows requested, PathAlign without path
 // orientations, PathAlignLegacy / PathAngle not firing this pass (block-uniform conditions, decided once per block in
 // path_costs_tm_body).  `src` = where the term of list position q comes from this pass, one byte per position
 // (0 nothing, 1 K2's row, 2 PathFollow, 3 PathAlign), packed four to a word so that the unrolled loops index registers
-// statically.  PathAlign (path_align_critic.cpp:92-135): one monotone cursor is utils::findClosestPathPt's lower_bound
-// (utils.hpp:665-675) for every sample, the answer follows from the cursor and the previous answer by selects.
+// statically.  PathAlign (path_align_critic.cpp:92-135): utils::findClosestPathPt's lower_bound (utils.hpp:665-675) is a
+// cursor that only moves forward from sample to sample, placed by a guess from the path's mean spacing (`inv_h`, points
+// per metre) and corrected both ways against the arc-length table; the answer follows from the cursor and the previous
+// answer by selects.  The tables are read by 32-bit shared-window addresses (lds_f32).
 __device__ __forceinline__ float k3_trajectory_total_fast(
   int b, const DevParams * P, const K3Decisions & dec, const K3Path & path, const DevBuffers & bufs, int iteration, const unsigned (&src_w)[kMaxCritics / 4], const float inv_h)
 {
