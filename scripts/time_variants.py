@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--workload", default="sharded_262144x100")
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--cycles", type=int, default=30)
+    ap.add_argument("--flush", action="store_true", help="cold L2: 256 MiB written between cycles (what bench.py does)")
     ap.add_argument("libs", nargs="*")
     a = ap.parse_args()
     kw = {"batch": a.batch} if a.batch else {}
@@ -26,6 +27,14 @@ def main():
                   "sharded_262144x100": (scenarios.config4, True)}[a.workload]
     sc = sc(**kw)
     noise = None if philox else sc.noise()
+    flush = lambda: None
+    if a.flush:
+        import torch
+        buf = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
+
+        def flush():
+            buf.zero_()
+            torch.cuda.synchronize()
     for lib in (a.libs or [None]):
         e = Engine(load_product(lib), **sc.cfg)
         e.set_robot(sc.robot)
@@ -37,10 +46,14 @@ def main():
         e.upload_cycle(sc.cycle)
         for _ in range(5):
             e.optimize_resident()
-        tot = [e.optimize_resident().device_ms for _ in range(a.cycles)]
+        tot = []
+        for _ in range(a.cycles):
+            flush()
+            tot.append(e.optimize_resident().device_ms)
         e.set_profiling(True)
         k = []
         for _ in range(a.cycles):
+            flush()
             e.optimize_resident()
             p = e.get_profile()
             k.append((p["k2_ms"], p["k3_ms"], p["exchange_ms"]))
