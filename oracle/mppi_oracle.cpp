@@ -510,6 +510,11 @@ struct Optimizer
   // below half an ulp of the running sum (3e-4 relative, larger than the parity tolerance), so the full-size test compares
   // with this order-free value and reports the index-order float result beside it.
   bool wide_reductions{false};
+  // Test switch (oracle_set_iteration_controls): behind the update of iteration `pin_iteration` the control sequence is
+  // replaced by the given one (the bits another implementation holds at that point), so that the NEXT iteration's rollout can
+  // be compared bit for bit although the two updates differ in the order of their batch reductions.
+  int pin_iteration{-1};
+  ControlSequence pin_cs;
 
   bool isHolonomic() const {return cfg.motion_model == MPPI_MODEL_OMNI;}
 
@@ -1251,6 +1256,7 @@ struct Optimizer
       integrateStateVelocities(traj, state, cfg.model_dt, isHolonomic());
       evalTrajectoriesScores(data);
       updateControlSequence();
+      if (i == pin_iteration) {cs = pin_cs;}
       // ref: NoiseGenerator::generateNextNoises noise_generator.cpp:54-63 + noiseThread :97-105: with regenerate_noises the
       // side thread redraws once the current set has been consumed.  The reference races that thread against the next
       // iteration; the deterministic restatement is "every iteration consumes a fresh set" (Philox stream + 1 each time).
@@ -1478,6 +1484,15 @@ int oracle_get_trajectories(Optimizer * o, float * x, float * y, float * yaw)
 int oracle_set_wide_reductions(Optimizer * o, int32_t on)
 {
   o->wide_reductions = on != 0;
+  return MPPI_OK;
+}
+int oracle_set_iteration_controls(Optimizer * o, int32_t iteration, const float * vx, const float * vy, const float * wz)
+{
+  o->pin_iteration = iteration;
+  if (iteration >= 0) {
+    const size_t T = o->cfg.time_steps;
+    o->pin_cs.vx.assign(vx, vx + T); o->pin_cs.vy.assign(vy, vy + T); o->pin_cs.wz.assign(wz, wz + T);
+  }
   return MPPI_OK;
 }
 int oracle_get_state(Optimizer * o, float * vx, float * vy, float * wz, float * cvx, float * cvy, float * cwz)

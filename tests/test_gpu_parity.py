@@ -152,6 +152,24 @@ def test_iteration_count_two(product_fns, oracle_fns):
     assert not np.allclose(g1.optimize(sc1.cycle).vx, rg.vx, rtol=1e-3)
 
 
+def test_iteration_count_two_second_rollout_is_bit_exact(product_fns, oracle_fns):
+    """iteration_count 2 with the oracle's second iteration started from the DEVICE's first update (test switch
+    oracle_set_iteration_controls): the second rollout - trajectories and cell indices of every (b, t) - is bit-equal,
+    the accumulated costs (quirk R20, optimizer.cpp:157-164) and the final control sequence meet the usual bars."""
+    sc1 = _all_critics_scenario(1)
+    noise = sc1.noise()
+    g1 = _pair(product_fns, oracle_fns, sc1, noise)[0]
+    r1 = g1.optimize(sc1.cycle)            # what the device holds behind its first iteration
+    sc = _all_critics_scenario(2)
+    g, o = _pair(product_fns, oracle_fns, sc, noise)
+    pin = [np.ascontiguousarray(a, dtype=np.float32) for a in (r1.vx, r1.vy, r1.wz)]
+    f32p = oracle_fns["_lib"].oracle_set_iteration_controls.argtypes[2]
+    assert oracle_fns["set_iteration_controls"](o.h, 0, *[a.ctypes.data_as(f32p) for a in pin]) == 0
+    rg, ro = g.optimize(sc.cycle), o.optimize(sc.cycle)
+    _compare_cycle(g, o, sc, rg, ro, "second iteration")
+    assert not np.allclose(r1.vx, rg.vx, rtol=1e-3)   # the second iteration moved the sequence
+
+
 def test_all_trajectories_collide_sets_fail_flag(product_fns, oracle_fns):
     sc = scenarios.config1(batch=128)
     sc.cycle.costmap = np.full_like(sc.cycle.costmap, 254)

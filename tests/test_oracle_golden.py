@@ -365,3 +365,31 @@ def test_optimized_trajectory_known_answer_and_second_opinion(oracle_fns):
     x_lag = pose[0] + np.cumsum(((vx * np.cos(lag) - vy * np.sin(lag)) * dt).astype(np.float32), dtype=np.float32)
     assert np.abs(x_lag - x).max() > 1e-3
     e.close()
+
+
+def test_iteration_controls_switch_of_the_oracle(oracle_fns):
+    """test switch oracle_set_iteration_controls (used by the iteration_count = 2 GPU parity test): pinning the oracle's own
+    first update reproduces the free-running two-iteration cycle bit for bit; pinning something else does not"""
+    from mpcholonavigation_b200 import scenarios
+    f32p = oracle_fns["_lib"].oracle_set_iteration_controls.argtypes[2]
+    sc = scenarios.config1(batch=128)
+    noise = sc.noise()
+
+    def engine(iterations):
+        e = Engine(oracle_fns, **{**sc.cfg, "iteration_count": iterations})
+        e.set_robot(sc.robot)
+        e.set_critics(sc.critics)
+        e.set_noise(*noise)
+        e.set_outputs(trajectories=True, cells=True, critic_costs=True)
+        return e
+
+    first = engine(1).optimize(sc.cycle)
+    free = engine(2)
+    r_free = free.optimize(sc.cycle)
+    for delta, same in ((0.0, True), (1e-3, False)):
+        pinned = engine(2)
+        pin = [np.ascontiguousarray(a + delta, dtype=np.float32) for a in (first.vx, first.vy, first.wz)]
+        assert oracle_fns["set_iteration_controls"](pinned.h, 0, *[a.ctypes.data_as(f32p) for a in pin]) == 0
+        r = pinned.optimize(sc.cycle)
+        assert np.array_equal(r.vx, r_free.vx) == same
+        assert np.array_equal(pinned.get_costs(), free.get_costs()) == same
