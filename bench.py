@@ -12,12 +12,15 @@ workloads (BASELINE.json configs):
                       reference-style injected noise.  THE headline line; at N>1 every rank runs this same problem
                       with its own noise draw (replicas, no data-path collective: weak scaling).
   obstacles_16384x56  configs[2]: 16384 x 56, 400x400 costmap, ObstaclesCritic in footprint mode.
+  obstacles_dense_16384x56  the same with the robot boxed in (rectangular footprint inside a ring of discs): the footprint
+                      branch is taken by ~14 % of the visited poses in every cycle (configs[2]'s literal geometry: 0.2 % of
+                      the first cycle, none afterwards; cpu_baseline.footprint_branch reports the counts for both).
   sharded_262144x100  configs[3]: 262144 x 100 sharded over the ranks, Philox noise by global trajectory index,
                       two exchanges (furthest path point; softmax partials) over NVLink peer memory or NCCL (strong scaling).
   robots_256          configs[4]: 256 robots x (2000 x 56), 256/N per rank, one bound group per rank, no exchange.
 
 Without --workload the ONE line printed is the omni_1000x56 line and it carries three nested records measured in the
-same process at the same N: "obstacles_16384x56" (N = 1 only), "sharded_262144x100" and "robots_256", each with
+same process at the same N: "obstacles_16384x56" and "obstacles_dense_16384x56" (N = 1 only), "sharded_262144x100" and "robots_256", each with
 ms_per_step, e2e, per-kernel ms, roofline and a "parity" object produced in the same run (every rank's result against
 the CPU oracle; "MISMATCH" makes the process exit non-zero after the line is printed).
 
@@ -66,6 +69,11 @@ def pick_scenario(workload, rank, world):
         return sc, "injected"
     if workload == "obstacles_16384x56":
         return scenarios.config3(), "injected"
+    if workload == "obstacles_dense_16384x56":
+        # configs[2] with the robot boxed in (rectangular footprint inside a ring of discs): the footprint branch of the
+        # critic is taken by ~13 % of the visited poses in every cycle; SURVEY 8d's literal geometry takes it in 0.2 % of the
+        # first cycle's poses and never once the control sequence has moved away (cpu_baseline.footprint_branch has both)
+        return scenarios.config3(dense=True), "injected"
     if workload == "sharded_262144x100":
         return scenarios.config4(), "philox"
     if workload == "robots_256":
@@ -238,6 +246,7 @@ def cpu_baseline(sc, noise_kind, budget_s=12.0):
     B, T = sc.cfg["batch_size"], sc.cfg["time_steps"]
     e = oracle_engine(sc, noise_kind)
     e.optimize(sc.cycle)
+    branch_cold = footprint_branch(e, B * T)
     n, t0 = 0, time.perf_counter()
     lat = []
     while True:
@@ -248,11 +257,33 @@ def cpu_baseline(sc, noise_kind, budget_s=12.0):
         if time.perf_counter() - t0 > budget_s or n >= 2000:
             break
     wall = time.perf_counter() - t0
+    branch = footprint_branch(e, B * T)
     e.close()
-    return {"value": B * T * sc.cfg.get("iteration_count", 1) * n / wall, "unit": UNIT, "cores": 1, "kind": "port",
-            "p50_ms": pct(lat, 50), "cpu_model": model, "pinned_core": core,
-            "sample": f"{n} optimize() calls of {sc.name} in {wall:.1f} s on 1 host thread pinned to core {core} of {ncpu} ({model}); "
-                      f"the reference is single-threaded; oracle port, reference-flags build"}
+    out = {"value": B * T * sc.cfg.get("iteration_count", 1) * n / wall, "unit": UNIT, "cores": 1, "kind": "port",
+           "p50_ms": pct(lat, 50), "cpu_model": model, "pinned_core": core,
+           "sample": f"{n} optimize() calls of {sc.name} in {wall:.1f} s on 1 host thread pinned to core {core} of {ncpu} ({model}); "
+                     f"the reference is single-threaded; oracle port, reference-flags build"}
+    if branch:
+        out["footprint_branch"] = {"first_cycle_zero_control_sequence": branch_cold, f"cycle_{n + 1}_warm_started": branch,
+                                   "note": "poses visited = poses of the batch before a trajectory's first collision (the "
+                                           "critics break there); counted by the CPU oracle"}
+    return out
+
+
+def footprint_branch(e, poses):
+    """the fraction of poses for which the obstacle-type critics leave the point cost for the footprint check
+    (cost_critic.cpp:204-209, obstacles_critic.cpp:214-220), counted by the CPU oracle in its last optimize()"""
+    import ctypes as C
+    if "get_counters" not in e.f:
+        return None
+    c = (C.c_uint64 * 4)()
+    e.f["get_counters"](e.h, c)
+    out = {}
+    for name, visited, fp in (("CostCritic", c[0], c[1]), ("ObstaclesCritic", c[2], c[3])):
+        if visited:
+            out[name] = {"poses_visited": int(visited), "footprint_checks": int(fp), "fraction_of_visited": fp / visited,
+                         "fraction_of_all_poses": fp / poses}
+    return out or None
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -273,21 +304,22 @@ def load_peaks():
     return peaks
 
 
-def kernel_counters(kernel, B_local, T):
-    """ncu counters of ONE launch of `kernel` at this launch size (profiles/ncu_kernel_counters.json), or None"""
+def kernel_counters(kernel, B_local, T, tag=""):
+    """ncu counters of ONE launch of `kernel` at this launch size (profiles/ncu_kernel_counters.json), or None; `tag`
+    selects the capture of a workload variant with the same launch size ("dense:")"""
     p = os.path.join(ROOT, "profiles", "ncu_kernel_counters.json")
     if not os.path.exists(p):
         return None
-    return json.load(open(p)).get(f"{kernel}@{B_local}x{T}")
+    return json.load(open(p)).get(f"{tag}{kernel}@{B_local}x{T}")
 
 
-def make_roofline(kernel, dur_ms, alg_bytes, B_local, T, peaks, note):
+def make_roofline(kernel, dur_ms, alg_bytes, B_local, T, peaks, note, tag=""):
     """the bound that binds: HBM (algorithmic bytes) or issue slots (warp instructions from the ncu capture of this launch size)"""
     hbm = alg_bytes / (dur_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": kernel, "achieved": hbm, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": hbm / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_launch": int(alg_bytes),
             "kernel_ms": dur_ms, "peak_source": peaks["hbm_src"], "note": note}
-    kc = kernel_counters(kernel, B_local, T)
+    kc = kernel_counters(kernel, B_local, T, tag)
     if kc:
         roof["traffic"] = kc.get("dram_bytes")
         roof["counters_source"] = kc.get("source")
@@ -434,6 +466,43 @@ def sharded_parity(ctx, batch=65536, cycles=2):
             "flags_equal": bad == 0.0, "oracle_s": t_oracle}
 
 
+def single_parity(ctx, workload, cycles=3):
+    """In-run check of a single-handle workload at its full size (N = 1 records): `cycles` optimize() calls from host
+    buffers against the CPU oracle on the same injected noise - control sequence, fail flag, furthest reached path point,
+    and the total cost of every trajectory; both sides continue from the oracle's control sequence."""
+    sc, noise_kind = pick_scenario(workload, 0, 1)
+    assert noise_kind == "injected"
+    cfg = dict(sc.cfg)
+    cfg["device"] = ctx.local_rank
+    e = Engine(ctx.fns, **cfg)
+    e.set_robot(sc.robot)
+    e.set_critics(sc.critics)
+    e.set_noise(*sc.noise())
+    o = oracle_engine(sc, "injected", fast=False)
+    worst, worst_abs, worst_cost, flags_ok, t_oracle = 0.0, 0.0, 0.0, True, 0.0
+    for _ in range(cycles):
+        rg = e.optimize(sc.cycle)
+        t0 = time.perf_counter()
+        ro = o.optimize(sc.cycle)
+        t_oracle += time.perf_counter() - t0
+        dev, ab = controls_deviation((rg.vx, rg.vy, rg.wz), (ro.vx, ro.vy, ro.wz))
+        worst, worst_abs = max(worst, dev), max(worst_abs, ab)
+        cg, co = np.asarray(e.get_costs(), np.float64), np.asarray(o.get_costs(), np.float64)
+        worst_cost = max(worst_cost, float(np.max(np.abs(cg - co) / (5e-6 + RTOL * np.abs(co)))))
+        flags_ok = (flags_ok and bool(rg.fail_flag) == bool(ro.fail_flag)
+                    and rg.furthest_reached_path_point == ro.furthest_reached_path_point)
+        e.set_control_sequence(ro.vx, ro.vy, ro.wz)
+    e.close()
+    o.close()
+    ok = worst <= 1.0 and worst_cost <= 1.0 and flags_ok
+    return {"status": "ok" if ok else "MISMATCH",
+            "checked": f"{sc.name} at full size, {cycles} cycles from host buffers against the CPU oracle: control sequence, "
+                       "fail flag, furthest point, total cost of every trajectory",
+            "tolerance": f"controls |d| <= {ATOL} + {RTOL} |ref|, costs |d| <= 5e-06 + {RTOL} |ref|",
+            "worst_violation_ratio": worst, "worst_cost_violation_ratio": worst_cost, "max_abs_dev": worst_abs,
+            "flags_equal": flags_ok, "oracle_s": t_oracle}
+
+
 def run_workload(ctx, workload, steps, warmup, with_cpu_baseline, parity=None):
     """one workload through one handle per rank (everything but robots_256); returns the JSON object on rank 0"""
     args, rank, world, fns = ctx.args, ctx.rank, ctx.world, ctx.fns
@@ -539,7 +608,7 @@ def run_workload(ctx, workload, steps, warmup, with_cpu_baseline, parity=None):
             ("the fused small-batch kernel reads the noise once and keeps the tile in shared memory; the config is "
              "L2-resident, single-wave and latency-bound" if fused else
              "the implementation reads the noise twice (rollout and weighted sums), so its HBM ceiling is 0.5"))
-    roof = make_roofline(dom_name, dom_ms, alg, B_local, T, ctx.peaks, note)
+    roof = make_roofline(dom_name, dom_ms, alg, B_local, T, ctx.peaks, note, "dense:" if "dense" in workload else "")
     roof["kernel_share_of_step"] = dom_ms / max(k2_ms + k3_ms + xch_ms, 1e-9)
     roof["other_kernel"] = {"kernel": oth_name, "ms": oth_ms, "achieved": (alg / (oth_ms * 1e-3) / 1e9) if oth_ms > 0 else None}
     roof["step_achieved_gbs"] = alg / ((dev_total / steps) * 1e-3) / 1e9
@@ -683,6 +752,22 @@ def run_robots(ctx, steps, warmup, with_cpu_baseline, check_parity):
     roof = make_roofline(kname, step_ms, alg, n * B, T, ctx.peaks,
                          "algorithmic bytes of the rank's robots (SURVEY 8d) over the device span of the step: first start "
                          "event to latest end event across the robots' launches (whole step, all kernels)")
+    kc = kernel_counters("robots_step", B, T) if bound and not tile else None
+    if kc:
+        # ncu counters of ONE step of a bound group (every launch of the step summed), scaled to this rank's robots
+        scale = n / kc["n_robots"]
+        roof["traffic"] = int(kc["dram_bytes"] * scale)
+        roof["counters_source"] = kc["source"]
+        roof["traffic_note"] = (f"sum over the {kc['launches']} launches of one step of {kc['n_robots']} robots"
+                                + ("" if scale == 1.0 else f", scaled by {n}/{kc['n_robots']}"))
+        if ctx.peaks["issue_gips"]:
+            gips = kc["warp_inst"] * scale / (step_ms * 1e-3) / 1e9
+            roof["issue"] = {"bound": "issue", "achieved": gips, "peak": ctx.peaks["issue_gips"], "unit": "G warp-inst/s",
+                             "frac": gips / ctx.peaks["issue_gips"], "warp_inst_per_step": int(kc["warp_inst"] * scale),
+                             "peak_source": ctx.peaks["sm_src"]}
+        roof["per_kernel_ncu"] = {k: {"share_of_ncu_time": v["ncu_duration_us"] / max(kc["ncu_duration_us"], 1e-9),
+                                      "dram_bytes": int(v["dram_bytes"] * scale), "warp_inst": int(v["warp_inst"] * scale)}
+                                  for k, v in kc["per_kernel"].items()}
     line = {
         "metric": METRIC, "value": units / (dev_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
@@ -775,13 +860,16 @@ def main():
         line = run_robots(ctx, max(1, min(args.steps, 200)), args.warmup, False, True)
     elif args.workload == "sharded_262144x100":
         line = run_workload(ctx, args.workload, args.steps, args.warmup, False, parity=sharded_parity(ctx))
+    elif args.workload.startswith("obstacles_"):
+        line = run_workload(ctx, args.workload, args.steps, args.warmup, False, parity=single_parity(ctx, args.workload))
     else:
         line = run_workload(ctx, args.workload, args.steps, args.warmup, False)
     extra = {}
     if nested:
         n_steps, n_warm = max(1, min(args.steps, 50)), max(3, min(args.warmup, 10))
         if world == 1:
-            extra["obstacles_16384x56"] = guarded("obstacles_16384x56", lambda: run_workload(ctx, "obstacles_16384x56", n_steps, n_warm, False))
+            for wl in ("obstacles_16384x56", "obstacles_dense_16384x56"):
+                extra[wl] = guarded(wl, lambda wl=wl: run_workload(ctx, wl, n_steps, n_warm, False, parity=single_parity(ctx, wl)))
         extra["sharded_262144x100"] = guarded("sharded_262144x100", lambda: run_workload(
             ctx, "sharded_262144x100", n_steps, n_warm, False, parity=sharded_parity(ctx)))
         extra["robots_256"] = guarded("robots_256", lambda: run_robots(ctx, min(n_steps, 30), n_warm, False, True))

@@ -145,17 +145,36 @@ def config1(batch=1000, steps=56, map_size=100, n_path=40, heading=0.0, map_seed
                     robot, cyc, noise_seed)
 
 
-def config3(batch=16384, steps=56, map_size=400, k_discs=120, map_seed=2, noise_seed=3):
-    """BASELINE configs[2]: 16384x56, 400x400 costmap @0.05 m, ObstaclesCritic alone in footprint mode."""
+def config3(batch=16384, steps=56, map_size=400, k_discs=120, map_seed=2, noise_seed=3, dense=False, ring=0.47):
+    """BASELINE configs[2]: 16384x56, 400x400 costmap @0.05 m, ObstaclesCritic alone in footprint mode.
+
+    dense=True is the same map with the robot boxed in: a 0.5 x 0.3 m rectangular footprint (inscribed radius 0.15 m,
+    circumscribed 0.29 m) inside a ring of eight discs `ring` metres away, so that the footprint branch of the critic
+    (obstacles_critic.cpp:214-220: point cost >= the cost at the circumscribed radius) is taken by a large share of the poses
+    in every cycle - with SURVEY 8d's literal geometry (a 16-gon whose circumscribed radius IS its inscribed radius, one
+    disc 0.5 m away) it is taken by 0.2 % of the poses of the first cycle and by none once the sequence has moved away."""
     res = 0.05
     centre = map_size * res / 2.0
     pose = (centre, centre, 0.0)
     px, py, pyaw = straight_path(pose[0], pose[1], 0.0, 40, 0.05)
     rng = np.random.default_rng(map_seed)
-    keep = [(pose[0], pose[1], 0.45)]
+    keep = [(pose[0], pose[1], 0.45 if not dense else 0.9)]
     discs = random_discs(rng, k_discs - 1, map_size, map_size, res, keep)
     # one disc placed 0.5 m from the robot so that many poses take the footprint branch
     discs.append((pose[0] / res + 0.5 / res * np.cos(0.6), pose[1] / res + 0.5 / res * np.sin(0.6), 3.0))
+    if dense:
+        discs.pop()
+        for k in range(8):
+            a = 2.0 * np.pi * (k + 0.5) / 8
+            discs.append((pose[0] / res + ring / res * np.cos(a), pose[1] / res + ring / res * np.sin(a), 2.0))
+        cm = inflated_disc_costmap(map_size, map_size, res, discs, inscribed_radius=0.15)
+        fp = np.array([[0.25, 0.15], [-0.25, 0.15], [-0.25, -0.15], [0.25, -0.15]])
+        robot = make_robot(fp, inscribed_radius=0.15, circumscribed_radius=float(np.hypot(0.25, 0.15)),
+                           inflation_layer_found=True, inflation_cost_scaling_factor=3.0, track_unknown=False)
+        critics = [("ObstaclesCritic", dict(consider_footprint=1, inflation_radius=0.55, cost_scaling_factor=3.0))]
+        cyc = Cycle(pose=pose, goal=(float(px[-1]), float(py[-1])), goal_checker_xy_tolerance=0.25, path_x=px, path_y=py,
+                    path_yaw=pyaw, costmap=cm, resolution=res, origin=(0.0, 0.0))
+        return Scenario("obstacles_fp_dense_%dx%d" % (batch, steps), _omni_cfg(batch, steps), critics, robot, cyc, noise_seed)
     cm = inflated_disc_costmap(map_size, map_size, res, discs)
     robot = make_robot(circle_footprint(0.25), inscribed_radius=0.25, circumscribed_radius=0.25,
                        inflation_layer_found=True, inflation_cost_scaling_factor=3.0, track_unknown=False)

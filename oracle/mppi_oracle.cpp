@@ -515,6 +515,11 @@ struct Optimizer
   // be compared bit for bit although the two updates differ in the order of their batch reductions.
   int pin_iteration{-1};
   ControlSequence pin_cs;
+  // Measurement aid (oracle_get_counters): how many poses the obstacle-type critics visited in the last optimize() and how
+  // many of them took the footprint branch (cost_critic.cpp:204-209, obstacles_critic.cpp:214-220) - the "branch fraction"
+  // SURVEY 8d asks for beside config 3's numbers.  [0] CostCritic visited, [1] CostCritic footprint, [2] Obstacles visited,
+  // [3] Obstacles footprint.
+  mutable uint64_t counters[4] = {0, 0, 0, 0};
 
   bool isHolonomic() const {return cfg.motion_model == MPPI_MODEL_OMNI;}
 
@@ -1089,10 +1094,12 @@ struct Optimizer
         } else {
           pose_cost = checker.pointCost(x_i, y_i);
         }
+        ++counters[0];
         if (pose_cost < 1.0f) {continue;}
         float cost = pose_cost;
         if (consider_footprint && (cost >= c.possibly_inscribed_cost || c.possibly_inscribed_cost < 1.0f)) {
           cost = static_cast<float>(checker.footprintCostAtPose(x, y, tr.yaws(i, j), robot));
+          ++counters[1];
         }
         if (inCollisionValue(cost, consider_footprint)) {
           trajectory_collide = true;
@@ -1139,6 +1146,7 @@ struct Optimizer
         float cost;
         bool using_footprint = false;
         unsigned int x_i, y_i;
+        ++counters[2];
         if (!costmap.worldToMap(x, y, x_i, y_i)) {
           cost = NO_INFORMATION;
         } else {
@@ -1146,6 +1154,7 @@ struct Optimizer
           if (consider_footprint && (cost >= c.possibly_inscribed_cost || c.possibly_inscribed_cost < 1.0f)) {
             cost = static_cast<float>(checker.footprintCostAtPose(x, y, tr.yaws(i, j), robot));
             using_footprint = true;
+            ++counters[3];
           }
         }
         if (cost < 1.0f) {continue;}
@@ -1247,6 +1256,7 @@ struct Optimizer
   void optimize(const mppi_cycle_in & in)
   {
     loadCycle(in);
+    counters[0] = counters[1] = counters[2] = counters[3] = 0;
     std::fill(costs.begin(), costs.end(), 0.0f);
     data = makeData(in, &state, &traj, &costs);
     for (int i = 0; i < cfg.iteration_count; ++i) {
@@ -1484,6 +1494,11 @@ int oracle_get_trajectories(Optimizer * o, float * x, float * y, float * yaw)
 int oracle_set_wide_reductions(Optimizer * o, int32_t on)
 {
   o->wide_reductions = on != 0;
+  return MPPI_OK;
+}
+int oracle_get_counters(Optimizer * o, uint64_t * out4)
+{
+  std::memcpy(out4, o->counters, sizeof(o->counters));
   return MPPI_OK;
 }
 int oracle_set_iteration_controls(Optimizer * o, int32_t iteration, const float * vx, const float * vy, const float * wz)

@@ -28,6 +28,8 @@ def main():
         sc, philox = scenarios.config1(**kw), False
     elif a.workload == "obstacles_16384x56":
         sc, philox = scenarios.config3(**kw), False
+    elif a.workload == "obstacles_dense_16384x56":
+        sc, philox = scenarios.config3(dense=True, **kw), False
     elif a.workload == "sharded_262144x100":
         sc, philox = scenarios.config4(**kw), True
     else:

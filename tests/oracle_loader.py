@@ -12,6 +12,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 EXTRA = {
     "get_state": (C.c_int, [abi.H] + [abi.f32p] * 6),
     "set_wide_reductions": (C.c_int, [abi.H, C.c_int32]),
+    "get_counters": (C.c_int, [abi.H, C.POINTER(C.c_uint64)]),
     "set_iteration_controls": (C.c_int, [abi.H, C.c_int32, abi.f32p, abi.f32p, abi.f32p]),
     "philox4x32_10": (None, [abi.u32p, abi.u32p, abi.u32p]),
     "det_sincosf": (None, [C.c_float, abi.f32p, abi.f32p]),

@@ -57,12 +57,16 @@ def test_default_arm_line_on_the_gpu():
     assert d["cpu_baseline"]["value"] < d["e2e"]["value"]
     assert d["latency_ms"]["e2e_p50"] < 0.3             # north_star: 1000 x 56 under 0.3 ms per optimize()
     # the other BASELINE configs ride in the same line, measured in the same process, each with its in-run oracle check
-    for name in ("obstacles_16384x56", "sharded_262144x100", "robots_256"):
+    for name in ("obstacles_16384x56", "obstacles_dense_16384x56", "sharded_262144x100", "robots_256"):
         rec = d[name]
         assert "error" not in rec, rec
         assert rec["ms_per_step"] > 0 and rec["e2e"]["value"] > 0 and "roofline" in rec and "cpu_baseline" in rec
-    assert d["sharded_262144x100"]["parity"]["status"] == "ok"
-    assert d["robots_256"]["parity"]["status"] == "ok"
+        assert rec["parity"]["status"] == "ok", rec["parity"]
+    # the footprint-branch fraction of config 3, counted by the CPU oracle of the same run
+    dense = d["obstacles_dense_16384x56"]["cpu_baseline"]["footprint_branch"]
+    warm = [v for k, v in dense.items() if k.startswith("cycle_")][0]["ObstaclesCritic"]
+    assert warm["fraction_of_visited"] > 0.08
+    assert "first_cycle_zero_control_sequence" in d["obstacles_16384x56"]["cpu_baseline"]["footprint_branch"]
 
 
 def test_reference_arm_prints_the_same_config_object():

@@ -63,6 +63,26 @@ def test_config3_full_size_against_the_oracle(product_fns, oracle_fns):
     g.close(); o.close()
 
 
+def test_config3_dense_footprint_branch_full_size(product_fns, oracle_fns):
+    """configs[2] with the robot boxed in (rectangular footprint inside a ring of discs, scenarios.config3(dense=True)):
+    the footprint branch of ObstaclesCritic (obstacles_critic.cpp:214-220) is taken by more than a tenth of the visited
+    poses in every cycle, more than half of the trajectories collide and break early - the geometry bench.py times as
+    obstacles_dense_16384x56."""
+    sc = scenarios.config3(dense=True)
+    noise = sc.noise()
+    g, o = _engine(product_fns, sc, noise), _engine(oracle_fns, sc, noise)
+    counters = (C.c_uint64 * 4)()
+    for cycle in range(4):
+        rg, ro = g.optimize(sc.cycle), o.optimize(sc.cycle)
+        _compare(g, o, sc, rg, ro, f"config3 dense cycle {cycle}")
+        g.set_control_sequence(ro.vx, ro.vy, ro.wz)
+        oracle_fns["get_counters"](o.h, counters)
+        assert counters[3] > 0.08 * counters[2] > 0, (cycle, list(counters))
+    c = o.get_critic_costs(0)
+    assert (c >= 1e4).sum() > 1000 and (c < 1e4).sum() > 1000
+    g.close(); o.close()
+
+
 def _controls_dev(ra, rb):
     """largest relative deviation of the control sequences (floor 1e-6 absolute, the floor of the parity bar)"""
     worst = 0.0
