@@ -306,7 +306,14 @@ __device__ __forceinline__ int world_to_cell_fast(float xf, float yf, const Cell
   return my * static_cast<int>(cg.size_x) + mx;
 }
 
-// FootprintCollisionChecker::lineCost over nav2_util::LineIterator (integer Bresenham, both ends included)
+// FootprintCollisionChecker::lineCost over nav2_util::LineIterator (integer Bresenham, both ends included).
+// The reference walks the cells one by one and returns LETHAL_OBSTACLE at the first lethal cell, otherwise the maximum of
+// all cells: the cost of a line is a function of the SET of its cells (lethal if any cell is, else the maximum), so the
+// cells are fetched kLineBatch at a time - the loads of a batch are in flight together instead of one L1/L2 round trip
+// per cell behind an exit test (the footprint checks of a boxed-in robot were 85 % of the stream rollout's time that
+// way) - and the walk stops behind the first batch that holds a lethal cell.  Cells past the end of the line are not
+// dereferenced.  The integer stepping is the reference's, cell for cell.
+constexpr int kLineBatch = 8;
 template<bool kNc>
 __device__ __forceinline__ int line_cost(const uint8_t * cm, unsigned size_x, int x0, int y0, int x1, int y1)
 {
@@ -320,21 +327,35 @@ __device__ __forceinline__ int line_cost(const uint8_t * cm, unsigned size_x, in
   } else {
     xinc2 = 0; yinc1 = 0; den = deltay; num = deltay / 2; numadd = deltax; numpixels = deltay;
   }
-  int x = x0, y = y0;
+  // flat index of the cell and its two increments (the minor step is taken when the error term overflows)
+  const int sx = static_cast<int>(size_x);
+  int idx = y0 * sx + x0;
+  const int inc1 = yinc1 * sx + xinc1, inc2 = yinc2 * sx + xinc2;
   int cost = 0;
-  for (int cur = 0; cur <= numpixels; ++cur) {
-    const int c = ld_ro<kNc>(cm + static_cast<unsigned>(y) * size_x + static_cast<unsigned>(x));
-    if (c == LETHAL_OBSTACLE) {return c;}
-    cost = max(cost, c);
-    num += numadd;
-    if (num >= den) {num -= den; x += xinc1; y += yinc1;}
-    x += xinc2; y += yinc2;
+  for (int cur = 0; cur <= numpixels; cur += kLineBatch) {
+    int c[kLineBatch];
+#pragma unroll
+    for (int k = 0; k < kLineBatch; ++k) {
+      c[k] = cur + k <= numpixels ? static_cast<int>(ld_ro<kNc>(cm + static_cast<unsigned>(idx))) : 0;
+      num += numadd;
+      if (num >= den) {num -= den; idx += inc1;}
+      idx += inc2;
+    }
+    bool lethal = false;
+#pragma unroll
+    for (int k = 0; k < kLineBatch; ++k) {lethal = lethal || c[k] == LETHAL_OBSTACLE; cost = max(cost, c[k]);}
+    if (lethal) {return LETHAL_OBSTACLE;}
   }
   return cost;
 }
 
 // FootprintCollisionChecker::footprintCostAtPose + footprintCost.  P is the record in GLOBAL memory (the polygon
 // is not part of the hot copy); the scalars come from the caller's registers.  kNc: see ld_ro.
+// The reference interleaves "map the next vertex, return LETHAL_OBSTACLE if it is off the map" with the line walks; every
+// exit it takes for an off-map vertex returns the same value whatever the lines before it held, so the vertices are mapped
+// first, in a loop without exits: the two fp64 divisions per vertex (worldToMap) of all vertices overlap instead of each
+// waiting behind the previous line's loads.  Then the lines in the reference's order (0-1, 1-2, ..., and the closing line
+// from vertex 0 to the last one, in THAT direction: Bresenham is not symmetric), with its running maximum and its exit.
 template<bool kNc>
 __device__ __noinline__ int footprint_cost_at_pose(
   const DevParams * P, int n, double ox, double oy, double res, unsigned size_x, unsigned size_y,
@@ -343,26 +364,25 @@ __device__ __noinline__ int footprint_cost_at_pose(
   const double x = xf, y = yf, th = thf;
   double sin_th, cos_th;
   sincos(th, &sin_th, &cos_th);
-  unsigned x0, y0, x1, y1;
-  {
-    const double fx = ld_ro<kNc>(&P->fp_x[0]), fy = ld_ro<kNc>(&P->fp_y[0]);
+  int vx[MPPI_MAX_FOOTPRINT], vy[MPPI_MAX_FOOTPRINT];
+  bool off = false;
+  n = max(n, 1);   // an empty polygon reads vertex 0 of the record like the reference reads footprint[0]
+#pragma unroll 4
+  for (int i = 0; i < n; ++i) {
+    const double fx = ld_ro<kNc>(&P->fp_x[i]), fy = ld_ro<kNc>(&P->fp_y[i]);
     const double wx = x + (__dmul_rn(fx, cos_th) - __dmul_rn(fy, sin_th));
     const double wy = y + (__dmul_rn(fx, sin_th) + __dmul_rn(fy, cos_th));
-    if (world_to_cell(wx, wy, ox, oy, res, size_x, size_y, x0, y0) < 0) {return LETHAL_OBSTACLE;}
+    unsigned mx = 0u, my = 0u;
+    off = (world_to_cell(wx, wy, ox, oy, res, size_x, size_y, mx, my) < 0) || off;
+    vx[i] = static_cast<int>(mx); vy[i] = static_cast<int>(my);
   }
-  const unsigned xstart = x0, ystart = y0;
-  x1 = x0; y1 = y0;
+  if (off) {return LETHAL_OBSTACLE;}
   int footprint_cost = 0;
   for (int i = 0; i + 1 < n; ++i) {
-    const double fx = ld_ro<kNc>(&P->fp_x[i + 1]), fy = ld_ro<kNc>(&P->fp_y[i + 1]);
-    const double wx = x + (__dmul_rn(fx, cos_th) - __dmul_rn(fy, sin_th));
-    const double wy = y + (__dmul_rn(fx, sin_th) + __dmul_rn(fy, cos_th));
-    if (world_to_cell(wx, wy, ox, oy, res, size_x, size_y, x1, y1) < 0) {return LETHAL_OBSTACLE;}
-    footprint_cost = max(line_cost<kNc>(cm, size_x, x0, y0, x1, y1), footprint_cost);
-    x0 = x1; y0 = y1;
+    footprint_cost = max(line_cost<kNc>(cm, size_x, vx[i], vy[i], vx[i + 1], vy[i + 1]), footprint_cost);
     if (footprint_cost == LETHAL_OBSTACLE) {return footprint_cost;}
   }
-  return max(line_cost<kNc>(cm, size_x, xstart, ystart, x1, y1), footprint_cost);
+  return max(line_cost<kNc>(cm, size_x, vx[0], vy[0], vx[n - 1], vy[n - 1]), footprint_cost);
 }
 
 // CostCritic::inCollision / ObstaclesCritic::inCollision on a byte cost

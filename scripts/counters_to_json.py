@@ -7,7 +7,7 @@ issue-slot roofline).
 
 Entries are MERGED into the existing file, so a pass that re-collects only some launch sizes leaves the others alone.  A CSV
 whose name starts with "robots_" holds every launch of one step of a bound robot group (scripts/run_robots.py): its kernels
-are summed per kernel name and over the step (key robots_step@BxT, n_robots from the name).
+are summed per kernel name and over the step (key robots_step@BxT, n_robots from the name)."""
 import csv
 import glob
 import json
