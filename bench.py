@@ -762,9 +762,15 @@ def run_robots(ctx, steps, warmup, with_cpu_baseline, check_parity):
                                 + ("" if scale == 1.0 else f", scaled by {n}/{kc['n_robots']}"))
         if ctx.peaks["issue_gips"]:
             gips = kc["warp_inst"] * scale / (step_ms * 1e-3) / 1e9
-            roof["issue"] = {"bound": "issue", "achieved": gips, "peak": ctx.peaks["issue_gips"], "unit": "G warp-inst/s",
-                             "frac": gips / ctx.peaks["issue_gips"], "warp_inst_per_step": int(kc["warp_inst"] * scale),
-                             "peak_source": ctx.peaks["sm_src"]}
+            side = {"bound": "issue", "achieved": gips, "peak": ctx.peaks["issue_gips"], "unit": "G warp-inst/s",
+                    "frac": gips / ctx.peaks["issue_gips"], "warp_inst_per_step": int(kc["warp_inst"] * scale),
+                    "peak_source": ctx.peaks["sm_src"]}
+            if side["frac"] > roof["frac"]:   # the bound that binds is the larger fraction (as in make_roofline)
+                hbm_side = {k: roof[k] for k in ("bound", "achieved", "peak", "unit", "frac", "peak_source")}
+                roof.update(side)
+                roof["hbm"] = hbm_side
+            else:
+                roof["issue"] = side
         roof["per_kernel_ncu"] = {k: {"share_of_ncu_time": v["ncu_duration_us"] / max(kc["ncu_duration_us"], 1e-9),
                                       "dram_bytes": int(v["dram_bytes"] * scale), "warp_inst": int(v["warp_inst"] * scale)}
                                   for k, v in kc["per_kernel"].items()}
