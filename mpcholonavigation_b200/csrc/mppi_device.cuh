@@ -312,16 +312,11 @@ __device__ __forceinline__ int world_to_cell_fast(float xf, float yf, const Cell
 // cells are fetched kLineBatch at a time - the loads of a batch are in flight together instead of one L1/L2 round trip
 // per cell behind an exit test (the footprint checks of a boxed-in robot were 85 % of the stream rollout's time that
 // way) - and the walk stops behind the first batch that holds a lethal cell.  Cells past the end of the line are not
-// dereferenced.
-//
-// Cell k of the walk in closed form: the error term starts at den / 2 < den and grows by numadd <= den per step, so one
-// subtraction of den per step keeps it below den and after k steps the walk has taken m_k = floor((den / 2 + k numadd) / den)
-// minor steps: index_k = index_0 + k inc2 + m_k inc1.  The cells of a batch are then independent of each other (the serial
-// num -> compare -> index chain was what a lone warp waited for: 0.8 warps per scheduler in the boxed-in config 3).  The floor
-// is taken in fp32, exactly: a = den / 2 + k numadd + 0.5 is a half-integer below 2^22 for den < 2048 (exact in fp32, fmaf
-// rounds once), a / den is at least 0.5 / den away from every integer, and a * fl(1 / den) is within a 2^-22.99 relative of
-// it, i.e. within 0.5 / den for a < 2^22: truncation gives m_k (checked exhaustively for every den < 2048, numadd <= den,
-// k <= den by scripts/check_line_closed_form.c).  Longer lines (den >= 2048 cells) take the serial walk.
+// dereferenced.  The integer stepping is the reference's, cell for cell.
+// Measured against it in the boxed-in config 3 (profiles/README.md, K2 per cycle): the slots beyond the end reading the end
+// cell again so that every load is unconditional, 153 against 150 us (batches of 6 or 4: 156 us); the cells of a batch in
+// closed form, index_k = index_0 + k inc2 + floor((den / 2 + k numadd) / den) inc1 with an exact fp32 floor (no serial index
+// chain, but 38.6 M instead of 34.6 M warp instructions): 176 against 153 us under ncu.
 constexpr int kLineBatch = 8;
 template<bool kNc>
 __device__ __forceinline__ int line_cost(const uint8_t * cm, unsigned size_x, int x0, int y0, int x1, int y1)
@@ -341,33 +336,19 @@ __device__ __forceinline__ int line_cost(const uint8_t * cm, unsigned size_x, in
   int idx = y0 * sx + x0;
   const int inc1 = yinc1 * sx + xinc1, inc2 = yinc2 * sx + xinc2;
   int cost = 0;
-  if (den < 2048) {
-    const float a0 = __int2float_rn(num) + 0.5f, numadd_f = __int2float_rn(numadd);
-    const float inv_den = den > 0 ? __frcp_rn(__int2float_rn(den)) : 0.0f;   // den == 0: one cell, no step
-    for (int cur = 0; cur <= numpixels; cur += kLineBatch) {
-      const float cur_f = __int2float_rn(cur);
-      int c[kLineBatch];
+  for (int cur = 0; cur <= numpixels; cur += kLineBatch) {
+    int c[kLineBatch];
 #pragma unroll
-      for (int k = 0; k < kLineBatch; ++k) {
-        const float a = fmaf(cur_f + static_cast<float>(k), numadd_f, a0);         // exact
-        const int m = __float2int_rz(__fmul_rn(a, inv_den));                       // floor(a / den), see above
-        const int at = idx + (cur + k) * inc2 + m * inc1;
-        c[k] = cur + k <= numpixels ? static_cast<int>(ld_ro<kNc>(cm + static_cast<unsigned>(at))) : 0;
-      }
-      bool lethal = false;
-#pragma unroll
-      for (int k = 0; k < kLineBatch; ++k) {lethal = lethal || c[k] == LETHAL_OBSTACLE; cost = max(cost, c[k]);}
-      if (lethal) {return LETHAL_OBSTACLE;}
+    for (int k = 0; k < kLineBatch; ++k) {
+      c[k] = cur + k <= numpixels ? static_cast<int>(ld_ro<kNc>(cm + static_cast<unsigned>(idx))) : 0;
+      num += numadd;
+      if (num >= den) {num -= den; idx += inc1;}
+      idx += inc2;
     }
-    return cost;
-  }
-  for (int cur = 0; cur <= numpixels; ++cur) {
-    const int c = ld_ro<kNc>(cm + static_cast<unsigned>(idx));
-    if (c == LETHAL_OBSTACLE) {return c;}
-    cost = max(cost, c);
-    num += numadd;
-    if (num >= den) {num -= den; idx += inc1;}
-    idx += inc2;
+    bool lethal = false;
+#pragma unroll
+    for (int k = 0; k < kLineBatch; ++k) {lethal = lethal || c[k] == LETHAL_OBSTACLE; cost = max(cost, c[k]);}
+    if (lethal) {return LETHAL_OBSTACLE;}
   }
   return cost;
 }

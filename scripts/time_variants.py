@@ -24,6 +24,7 @@ def main():
     a = ap.parse_args()
     kw = {"batch": a.batch} if a.batch else {}
     sc, philox = {"omni_1000x56": (scenarios.config1, False), "obstacles_16384x56": (scenarios.config3, False),
+                  "obstacles_dense_16384x56": (lambda **kw: scenarios.config3(dense=True, **kw), False),
                   "sharded_262144x100": (scenarios.config4, True)}[a.workload]
     sc = sc(**kw)
     noise = None if philox else sc.noise()
