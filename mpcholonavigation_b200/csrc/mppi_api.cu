@@ -855,7 +855,7 @@ void launch_stream_instance(mppi_handle * h, int mode)
 {
   const int nthr = stream_block_threads(h);
   const int Tp = ((h->T + kStreamChunk - 1) / kStreamChunk) * kStreamChunk;
-  const size_t smem = kHotBytes + sizeof(float) * 3 * Tp;
+  const size_t smem = kHotBytes + sizeof(float) * 3 * (Tp + nthr);   // hot record, control sequence, footprint slots
   rollout_score_stream_kernel<F, kExact><<<(h->B + nthr - 1) / nthr, nthr, smem, h->stream>>>(
     reinterpret_cast<const DevParams *>(h->d_params), h->d_costmap, make_bufs(h, mode));
 }
@@ -1714,7 +1714,7 @@ mppi_status batch_stream_launch(mppi_handle * L, mppi_handle ** hs, int c0, int 
   {
     const int nthr = stream_block_threads(L);
     const int Tp = ((T + kStreamChunk - 1) / kStreamChunk) * kStreamChunk;
-    const size_t smem = kHotBytes + sizeof(float) * 3 * Tp;
+    const size_t smem = kHotBytes + sizeof(float) * 3 * (Tp + nthr);
     cudaError_t e;
     switch (inst) {
       case kSfOmniDefault: e = launch_stream_batch_instance<kSfOmniDefault, true>(L, jobs, n, nthr, smem); break;

@@ -992,6 +992,7 @@ __device__ __forceinline__ void rollout_score_stream_body(
   const int T = p.T, B = p.B;
   const int Tp = ((T + kStreamChunk - 1) / kStreamChunk) * kStreamChunk;   // horizon padded to whole chunks
   float * s_cs = s_hot + kHotFloats;   // [3][Tp], zero padded
+  float * s_fp = s_cs + 3 * Tp;        // [threads][3]: per warp 32 slots {x, y, yaw} for the compacted footprint checks
   for (int t = tid; t < Tp; t += nthr) {
     const bool in = t < T;
     s_cs[t] = in ? bufs.cs[t] : 0.0f;
@@ -1179,19 +1180,74 @@ __device__ __forceinline__ void rollout_score_stream_body(
       }
       // ---- phase F2: Cost / Obstacles, in step order (the collision short-circuits are order dependent); one branch
       //      per chunk: skipped while every pose of the chunk sits in free space
+      // Footprint mode: the poses of the chunk whose point cost sends a critic to the footprint check (cost_critic.cpp:204-209,
+      // obstacles_critic.cpp:214-220) are collected over the WARP first - 4 poses x 32 lanes, typically a seventh of them in a
+      // boxed-in scene - and checked one per lane in as few passes as possible, instead of one divergent call per pose with a
+      // handful of lanes active (7 threads per warp instruction in profiles/r02c, 85 % of the kernel's time).  The check is a
+      // pure function of the pose, so checking a pose the step-order walk below would have skipped (behind a collision
+      // earlier in the SAME chunk) changes nothing; the set collected is a superset of what the walk asks for.
+      int fpc[kStreamChunk];
+#pragma unroll
+      for (int u = 0; u < kStreamChunk; ++u) {fpc[u] = -1;}
+      const bool costed_any = kFp ? __any_sync(0xffffffffu, costed) != 0 : costed;
+      if (kFp && costed_any) {
+        bool need[kStreamChunk];
+        bool need_some = false;
+#pragma unroll
+        for (int u = 0; u < kStreamChunk; ++u) {
+          const float pc = static_cast<float>(pcost[u]);
+          const bool nc = cost_on && cost_fp && !cost_hit && pcost[u] >= 1 && (pc >= cost_pic || cost_pic < 1.0f);
+          const bool no = ob_on && ob_fp && !ob_hit && cell[u] >= 0 && (pc >= ob_pic || ob_pic < 1.0f);
+          need[u] = costed && (!kTail || t0 + u < T) && (nc || no);
+          need_some = need_some || need[u];
+        }
+        if (__any_sync(0xffffffffu, need_some)) {   // warp-uniform; one vote where no pose of the warp needs a check
+          const unsigned lane = static_cast<unsigned>(tid) & 31u, lt = (1u << lane) - 1u;
+          float * slot = s_fp + (tid & ~31) * 3;
+          int j[kStreamChunk];
+          int total = 0;
+#pragma unroll
+          for (int u = 0; u < kStreamChunk; ++u) {
+            const unsigned m = __ballot_sync(0xffffffffu, need[u]);
+            j[u] = need[u] ? total + __popc(m & lt) : -1;
+            total += __popc(m);
+          }
+          for (int r0 = 0; r0 < total; r0 += 32) {
+#pragma unroll
+            for (int u = 0; u < kStreamChunk; ++u) {
+              const int k = j[u] - r0;
+              if (k >= 0 && k < 32) {slot[3 * k] = px[u]; slot[3 * k + 1] = py[u]; slot[3 * k + 2] = yw[u];}
+            }
+            __syncwarp();
+            int res = 0;
+            if (r0 + static_cast<int>(lane) < total) {
+              res = footprint_cost_at_pose<true>(P, p.fp_n, p.ox, p.oy, p.res, cg.size_x, cg.size_y, cm,
+                  slot[3 * lane], slot[3 * lane + 1], slot[3 * lane + 2]);
+            }
+            __syncwarp();
+            slot[3 * lane] = __int_as_float(res);
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < kStreamChunk; ++u) {
+              const int k = j[u] - r0;
+              if (k >= 0 && k < 32) {fpc[u] = __float_as_int(slot[3 * k]);}
+            }
+            __syncwarp();
+          }
+        }
+      }
       if (costed) {
 #pragma unroll
         for (int u = 0; u < kStreamChunk; ++u) {
           const int t = t0 + u;
           if (!kTail || t < T) {
-            const float yaw = yw[u];
             if (want_cells && live) {bufs.spill_cells[g + static_cast<unsigned>(u) * static_cast<unsigned>(B)] = cell[u];}
             const int pose_cost = pcost[u];
             int fp_cost = -1;
             if (cost_on && !cost_hit && pose_cost >= 1) {   // cost_critic.cpp:139-162
               int c = pose_cost;
               if (kFp && cost_fp && (static_cast<float>(c) >= cost_pic || cost_pic < 1.0f)) {
-                fp_cost = footprint_cost_at_pose<true>(P, p.fp_n, p.ox, p.oy, p.res, cg.size_x, cg.size_y, cm, px[u], py[u], yaw);
+                fp_cost = fpc[u];
                 c = fp_cost;
               }
               if (in_collision(c, cost_fp, track_unknown)) {
@@ -1206,7 +1262,7 @@ __device__ __forceinline__ void rollout_score_stream_body(
               int c = pose_cost;
               int using_fp = 0;
               if (kFp && cell[u] >= 0 && ob_fp && (static_cast<float>(c) >= ob_pic || ob_pic < 1.0f)) {
-                if (fp_cost < 0) {fp_cost = footprint_cost_at_pose<true>(P, p.fp_n, p.ox, p.oy, p.res, cg.size_x, cg.size_y, cm, px[u], py[u], yaw);}
+                fp_cost = fpc[u];
                 c = fp_cost;
                 using_fp = 1;
               }
