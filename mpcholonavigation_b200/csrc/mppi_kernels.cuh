@@ -1186,6 +1186,10 @@ __device__ __forceinline__ void rollout_score_stream_body(
       // handful of lanes active (7 threads per warp instruction in profiles/r02c, 85 % of the kernel's time).  The check is a
       // pure function of the pose, so checking a pose the step-order walk below would have skipped (behind a collision
       // earlier in the SAME chunk) changes nothing; the set collected is a superset of what the walk asks for.
+      // Inlined on purpose: out of line (a __noinline__ helper taking the chunk's poses) the call makes the hot loop spill -
+      // 236 against 140 us at 262144 x 100, 45 against 32 us at 16384 x 56 (profiles/r02c_compaction_ab.txt).  The price of
+      // the inlined form is code that a scene without footprint checks still has to fetch: + 3 us on the COLD 29 us rollout
+      // of config 3's literal geometry (nothing warm), + 1 us of 140 us at 262144 x 100.
       int fpc[kStreamChunk];
 #pragma unroll
       for (int u = 0; u < kStreamChunk; ++u) {fpc[u] = -1;}
