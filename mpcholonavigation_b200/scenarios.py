@@ -119,17 +119,25 @@ def _omni_cfg(batch, steps, **kw):
 
 
 def config1(batch=1000, steps=56, map_size=100, n_path=40, heading=0.0, map_seed=0, noise_seed=1, k_discs=6,
-            footprint="circle", cost_consider_footprint=True, pose=None):
+            footprint="circle", cost_consider_footprint=True, pose=None, ring=None):
     """BASELINE configs[0]/[1]: Omni 1000x56, dt 0.05, default critic set, 100x100 costmap @0.05 m,
-    straight 40-point path."""
+    straight 40-point path.  ring = r [m] with footprint="rectangle": the robot boxed in by eight discs r away
+    (two of them across the path), so that CostCritic's footprint branch (cost_critic.cpp:204-209) is taken every cycle."""
     res = 0.05
     pose = pose if pose is not None else (map_size * res / 2.0, map_size * res / 2.0, heading)
     px, py, pyaw = straight_path(pose[0], pose[1], heading, n_path, 0.05)
     rng = np.random.default_rng(map_seed)
-    keep = [(pose[0], pose[1], 0.6)] + [(float(x), float(y), 0.3) for x, y in zip(px, py)]
+    keep = [(pose[0], pose[1], 0.6 if ring is None else 0.9)] + [(float(x), float(y), 0.3) for x, y in zip(px, py)]
     discs = random_discs(rng, k_discs, map_size, map_size, res, keep)
-    cm = inflated_disc_costmap(map_size, map_size, res, discs)
-    if footprint == "circle":
+    if ring is not None:
+        for k in range(8):
+            a = heading + 2.0 * np.pi * (k + 0.5) / 8
+            discs.append((pose[0] / res + ring / res * np.cos(a), pose[1] / res + ring / res * np.sin(a), 2.0))
+    cm = inflated_disc_costmap(map_size, map_size, res, discs, inscribed_radius=0.15 if footprint == "rectangle" else 0.25)
+    if footprint == "rectangle":
+        fp = np.array([[0.25, 0.15], [-0.25, 0.15], [-0.25, -0.15], [0.25, -0.15]])
+        insc, circ = 0.15, float(np.hypot(0.25, 0.15))
+    elif footprint == "circle":
         fp = circle_footprint(0.25)
         insc = circ = 0.25
     else:  # the bow-tie square of test/utils/factory.hpp:116-119

@@ -291,3 +291,31 @@ def test_fused_kernel_is_deterministic(product_fns, batch, steps):
             assert np.array_equal(got[3], ref[3]), f"repetition {rep}: costs differ"
         assert got[4:] == ref[4:]
     e.close()
+
+
+def test_boxed_in_footprint_branch_through_the_fused_kernel(product_fns, oracle_fns):
+    """configs[1] with the robot boxed in (rectangular footprint inside a ring of discs, scenarios.config1(ring=0.47)): CostCritic
+    takes the footprint branch (cost_critic.cpp:204-209) for more than a tenth of the visited poses in every cycle.  Exact
+    instance (what bench-style calls run) and the instance with outputs: cells and trajectories bit-equal, costs and controls
+    at the usual bars."""
+    import ctypes as C
+    sc = scenarios.config1(footprint="rectangle", ring=0.47)
+    noise = sc.noise()
+    exact, full, orc = _engine(product_fns, sc, noise), _engine(product_fns, sc, noise), _engine(oracle_fns, sc, noise)
+    for e in (full, orc):
+        e.set_outputs(trajectories=True, cells=True, critic_costs=True)
+    counters = (C.c_uint64 * 4)()
+    for cycle in range(6):
+        re_, rf, ro = exact.optimize(sc.cycle), full.optimize(sc.cycle), orc.optimize(sc.cycle)
+        _close(re_, ro, label=f"exact instance, cycle {cycle}")
+        _close(rf, ro, label=f"instance with outputs, cycle {cycle}")
+        assert np.array_equal(full.get_cells(), orc.get_cells())
+        for a, b in zip(full.get_trajectories(), orc.get_trajectories()):
+            assert np.array_equal(a, b)
+        for e in (exact, full):
+            np.testing.assert_allclose(e.get_costs(), orc.get_costs(), rtol=RTOL, atol=5e-6)
+            e.set_control_sequence(ro.vx, ro.vy, ro.wz)
+        oracle_fns["get_counters"](orc.h, counters)
+        assert counters[1] > 0.08 * counters[0] > 0, list(counters)
+    for e in (exact, full, orc):
+        e.close()
