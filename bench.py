@@ -338,6 +338,34 @@ def make_roofline(kernel, dur_ms, alg_bytes, B_local, T, peaks, note, tag=""):
     return roof
 
 
+def robots_roofline(roof, kc, n, step_ms, peaks):
+    """adds the ncu side of the 256-robot step to its roofline: counters of ONE step of a bound group (every launch of the
+    step summed, profiles/ncu_kernel_counters.json: robots_step@BxT), scaled to the n robots of this rank; the bound that
+    binds is the larger fraction, as in make_roofline"""
+    if not kc:
+        return roof
+    scale = n / kc["n_robots"]
+    roof["traffic"] = int(kc["dram_bytes"] * scale)
+    roof["counters_source"] = kc["source"]
+    roof["traffic_note"] = (f"sum over the {kc['launches']} launches of one step of {kc['n_robots']} robots"
+                            + ("" if scale == 1.0 else f", scaled by {n}/{kc['n_robots']}"))
+    if peaks["issue_gips"]:
+        gips = kc["warp_inst"] * scale / (step_ms * 1e-3) / 1e9
+        side = {"bound": "issue", "achieved": gips, "peak": peaks["issue_gips"], "unit": "G warp-inst/s",
+                "frac": gips / peaks["issue_gips"], "warp_inst_per_step": int(kc["warp_inst"] * scale),
+                "peak_source": peaks["sm_src"]}
+        if side["frac"] > roof["frac"]:
+            hbm_side = {k: roof[k] for k in ("bound", "achieved", "peak", "unit", "frac", "peak_source")}
+            roof.update(side)
+            roof["hbm"] = hbm_side
+        else:
+            roof["issue"] = side
+    roof["per_kernel_ncu"] = {k: {"share_of_ncu_time": v["ncu_duration_us"] / max(kc["ncu_duration_us"], 1e-9),
+                                  "dram_bytes": int(v["dram_bytes"] * scale), "warp_inst": int(v["warp_inst"] * scale)}
+                              for k, v in kc["per_kernel"].items()}
+    return roof
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # GPU side
 # ----------------------------------------------------------------------------------------------------------------
@@ -752,28 +780,8 @@ def run_robots(ctx, steps, warmup, with_cpu_baseline, check_parity):
     roof = make_roofline(kname, step_ms, alg, n * B, T, ctx.peaks,
                          "algorithmic bytes of the rank's robots (SURVEY 8d) over the device span of the step: first start "
                          "event to latest end event across the robots' launches (whole step, all kernels)")
-    kc = kernel_counters("robots_step", B, T) if bound and not tile else None
-    if kc:
-        # ncu counters of ONE step of a bound group (every launch of the step summed), scaled to this rank's robots
-        scale = n / kc["n_robots"]
-        roof["traffic"] = int(kc["dram_bytes"] * scale)
-        roof["counters_source"] = kc["source"]
-        roof["traffic_note"] = (f"sum over the {kc['launches']} launches of one step of {kc['n_robots']} robots"
-                                + ("" if scale == 1.0 else f", scaled by {n}/{kc['n_robots']}"))
-        if ctx.peaks["issue_gips"]:
-            gips = kc["warp_inst"] * scale / (step_ms * 1e-3) / 1e9
-            side = {"bound": "issue", "achieved": gips, "peak": ctx.peaks["issue_gips"], "unit": "G warp-inst/s",
-                    "frac": gips / ctx.peaks["issue_gips"], "warp_inst_per_step": int(kc["warp_inst"] * scale),
-                    "peak_source": ctx.peaks["sm_src"]}
-            if side["frac"] > roof["frac"]:   # the bound that binds is the larger fraction (as in make_roofline)
-                hbm_side = {k: roof[k] for k in ("bound", "achieved", "peak", "unit", "frac", "peak_source")}
-                roof.update(side)
-                roof["hbm"] = hbm_side
-            else:
-                roof["issue"] = side
-        roof["per_kernel_ncu"] = {k: {"share_of_ncu_time": v["ncu_duration_us"] / max(kc["ncu_duration_us"], 1e-9),
-                                      "dram_bytes": int(v["dram_bytes"] * scale), "warp_inst": int(v["warp_inst"] * scale)}
-                                  for k, v in kc["per_kernel"].items()}
+    if bound and not tile:
+        robots_roofline(roof, kernel_counters("robots_step", B, T), n, step_ms, ctx.peaks)
     line = {
         "metric": METRIC, "value": units / (dev_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",

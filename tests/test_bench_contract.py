@@ -77,3 +77,23 @@ def test_reference_arm_prints_the_same_config_object():
     want = bench.make_config("omni_1000x56", sc, "injected", 1, "peer", True)
     d = _run("--impl", "reference", "--steps", "3", "--warmup", "7")
     assert d["config"] == want and d["warmup"] == 7
+
+
+@pytest.mark.parametrize("n", [256, 128, 32])
+def test_robots_roofline_from_the_committed_counters(n):
+    """robots_256.roofline at N = 1, 2, 8: traffic and the issue side come from the counters of one 256-robot step, scaled to
+    the rank's robots; the reported bound is the larger fraction and frac == achieved / peak"""
+    import bench
+    peaks = bench.load_peaks()
+    kc = bench.kernel_counters("robots_step", 2000, 56)
+    assert kc and kc["n_robots"] == 256 and kc["launches"] == 4
+    step_ms = 0.5 * n / 256 + 0.1
+    alg = n * bench.algorithmic_bytes(2000, 56, 40, 10000)
+    roof = bench.make_roofline("robots", step_ms, alg, n * 2000, 56, peaks, "note")
+    roof = bench.robots_roofline(roof, kc, n, step_ms, peaks)
+    assert roof["traffic"] == int(kc["dram_bytes"] * n / 256) and roof["traffic"] > alg
+    assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12
+    other = roof.get("hbm") or roof.get("issue")
+    assert other and other["frac"] <= roof["frac"] and {other["bound"], roof["bound"]} == {"hbm", "issue"}
+    assert abs(sum(v["share_of_ncu_time"] for v in roof["per_kernel_ncu"].values()) - 1.0) < 1e-9
+    assert bench.robots_roofline({"frac": 0.1}, None, n, step_ms, peaks) == {"frac": 0.1}
