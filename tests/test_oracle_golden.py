@@ -244,6 +244,84 @@ def test_footprint_cost_second_opinion(oracle_fns):
     assert w2m(1e12, 0.5) == -1
 
 
+def _footprint_cost_device_order_np(cm, res, origin, fp, x, y, th, batch=8):
+    """The evaluation ORDER of the CUDA footprint check (mppi_device.cuh: footprint_cost_at_pose / line_cost), in numpy:
+    every vertex mapped first (any vertex off the map -> 254 before a single cell is read), then the lines in the reference's
+    order, each line's cells taken `batch` at a time: 254 if the batch holds a lethal cell, else the running maximum."""
+    c, s = math.cos(th), math.sin(th)
+    cells, off = [], False
+    for (fx, fy) in fp:
+        wx, wy = x + (fx * c - fy * s), y + (fx * s + fy * c)
+        if wx < origin[0] or wy < origin[1]:
+            off = True
+            continue
+        qx, qy = (wx - origin[0]) / res, (wy - origin[1]) / res
+        if not (qx < cm.shape[1]) or not (qy < cm.shape[0]):
+            off = True
+            continue
+        cells.append((int(qx), int(qy)))
+    if off:
+        return 254.0
+
+    def line(a, b):
+        pts = list(_bresenham(a[0], a[1], b[0], b[1]))
+        cost = 0.0
+        for i in range(0, len(pts), batch):
+            vals = [float(cm[py, px]) for (px, py) in pts[i:i + batch]]
+            if 254.0 in vals:
+                return 254.0
+            cost = max([cost] + vals)
+        return cost
+
+    n = len(cells)
+    total = 0.0
+    for i in range(n - 1):
+        total = max(total, line(cells[i], cells[i + 1]))
+        if total == 254.0:
+            return total
+    return max(line(cells[0], cells[n - 1]), total)
+
+
+@pytest.mark.parametrize("shape", ["rectangle", "circle", "bowtie"])
+def test_footprint_check_in_the_device_order_is_the_reference(oracle_fns, shape):
+    """The CUDA footprint check maps all vertices before it walks a line and fetches the cells of a line eight at a time
+    (mppi_device.cuh); the reference (restated in the oracle) interleaves vertices and lines and stops at the first lethal
+    cell.  On maps full of lethal (254) AND unknown (255) cells - where the order of the exits decides between 254 and 255 -
+    and for poses whose vertices leave the map, the two evaluation orders give the same cost."""
+    import ctypes as C
+    from mpcholonavigation_b200 import abi
+    rng = np.random.default_rng(23)
+    H = W = 50
+    res, origin = 0.05, (0.1, -0.2)
+    if shape == "rectangle":
+        fp = np.array([[0.35, 0.2], [-0.35, 0.2], [-0.35, -0.2], [0.35, -0.2]])   # 14-cell edges: two batches of eight
+        robot = make_robot(fp, 0.2, 0.41, True, 3.0, False)
+    elif shape == "circle":
+        fp = circle_footprint(0.25)
+        robot = make_robot(fp, 0.25, 0.25, True, 3.0, False)
+    else:
+        a = 0.15
+        fp = np.array([[a, a], [-a, -a], [a, -a], [-a, a]])
+        robot = make_robot(fp, a, a * math.sqrt(2.0), True, 3.0, False)
+    seen = set()
+    for density in (0.01, 0.04, 0.15):
+        cm = rng.integers(0, 253, size=(H, W)).astype(np.uint8)
+        cm[rng.random((H, W)) < density] = 254
+        cm[rng.random((H, W)) < density] = 255
+        cmap = abi.Costmap()
+        cmap.cells = cm.ctypes.data_as(abi.u8p)
+        cmap.size_x, cmap.size_y = W, H
+        cmap.resolution, cmap.origin_x, cmap.origin_y = res, origin[0], origin[1]
+        for _ in range(500):
+            # poses all over the map and a little beyond its edges (some vertices off the map)
+            x, y, th = rng.uniform(-0.1, 2.8), rng.uniform(-0.4, 2.5), rng.uniform(-7, 7)
+            got = oracle_fns["footprint_cost_at_pose"](C.byref(cmap), C.byref(robot), x, y, th)
+            exp = _footprint_cost_device_order_np(cm, res, origin, fp, x, y, th)
+            assert got == exp, (shape, density, x, y, th, got, exp)
+            seen.add(got)
+    assert 254.0 in seen and 255.0 in seen and any(v < 253.0 for v in seen)
+
+
 def test_philox_known_answers(oracle_fns):
     """Random123 kat_vectors for philox4x32-10"""
     import ctypes as C
