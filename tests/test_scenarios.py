@@ -68,3 +68,47 @@ def test_literal_config3_hardly_ever_takes_it(oracle_fns):
     oracle_fns["get_counters"](e.h, c)
     assert c[3] == 0
     e.close()
+
+
+def test_warp_collection_numbering_model():
+    """The numbering the stream rollout uses to collect the footprint checks of a chunk over the warp (mppi_kernels.cuh,
+    phase F2): item (lane, pose u) gets number total_before(u) + popc(ballot(u) & lanes_below); round r hands the items
+    32 r .. 32 r + 31 to lanes 0 .. 31 through one slot each and every owner reads its own result back.  Emulated lane by lane
+    for random need masks: every needed item is checked exactly once, with its own pose, and the owner gets that result."""
+    rng = np.random.default_rng(5)
+    chunk = 4
+    for trial in range(300):
+        density = rng.choice([0.0, 0.02, 0.14, 0.5, 1.0])
+        need = rng.random((32, chunk)) < density            # [lane][u]
+        pose = rng.integers(1, 1 << 30, size=(32, chunk))   # stands for (x, y, yaw)
+        check = lambda p: int(p) ^ 0x5A5A5A                 # the pure function of the pose
+        ballots = [sum(1 << l for l in range(32) if need[l, u]) for u in range(chunk)]
+        j = np.full((32, chunk), -1)
+        total = 0
+        for u in range(chunk):
+            for l in range(32):
+                if need[l, u]:
+                    j[l, u] = total + bin(ballots[u] & ((1 << l) - 1)).count("1")
+            total += bin(ballots[u]).count("1")
+        assert total == int(need.sum())
+        got = np.full((32, chunk), -1)
+        checked = 0
+        for r0 in range(0, total, 32):
+            slot = [None] * 32
+            for l in range(32):
+                for u in range(chunk):
+                    k = j[l, u] - r0
+                    if 0 <= k < 32:
+                        assert slot[k] is None
+                        slot[k] = pose[l, u]
+            res = [check(slot[l]) if r0 + l < total else 0 for l in range(32)]
+            checked += sum(1 for l in range(32) if r0 + l < total)
+            for l in range(32):
+                for u in range(chunk):
+                    k = j[l, u] - r0
+                    if 0 <= k < 32:
+                        got[l, u] = res[k]
+        assert checked == total
+        for l in range(32):
+            for u in range(chunk):
+                assert got[l, u] == (check(pose[l, u]) if need[l, u] else -1)
